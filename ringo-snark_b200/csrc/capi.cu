@@ -1,0 +1,556 @@
+// capi.cu -- the extern "C" surface declared in include/ringo_cuda.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace rs {
+
+thread_local PassProfile *g_pass_profile = nullptr;
+static thread_local char g_err[512] = "";
+static thread_local cudaStream_t g_stream = nullptr;
+static std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+cudaStream_t current_stream() { return g_stream; }
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// implemented in pointwise.cu
+int pointwise(int op, const rs_field *f, uint32_t *out, const uint32_t *a, const uint32_t *b, const uint32_t *c, size_t n);
+int eval_circuit(const rs_field *f, uint32_t *out, const uint32_t *pw, const uint32_t *w, const rs_term *d_terms,
+                 int n_terms, const uint32_t *d_coeffs, const uint32_t *bc, size_t rank);
+int quorem(const rs_field *f, uint32_t *quo, uint32_t *rem, const uint32_t *p, size_t rank, size_t N);
+int aut(const rs_field *f, uint32_t *out, const uint32_t *p, int logN, unsigned long long idx,
+        unsigned long long idx_inv, int is_ntt, size_t n_polys);
+int reverse_scale(const rs_field *f, uint32_t *out, const uint32_t *v, const uint32_t *scale, size_t N);
+int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uint32_t *coeffs, size_t n,
+           const uint32_t *x, const uint32_t *x_pow_ch, int CH);
+enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
+
+// ---- host-side field helpers (setup only) -------------------------------------------------
+template <int NL> static void host_mul_t(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *y) {
+    FieldParams<NL> F = make_params<NL>(f);
+    uint32_t t[NL];
+    mont_mul<NL, 0>(t, x, y, F);
+    memcpy(z, t, 4 * NL);
+}
+template <int NL> static void host_add_t(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *y) {
+    FieldParams<NL> F = make_params<NL>(f);
+    uint32_t t[NL];
+    mod_add<NL>(t, x, y, F);
+    memcpy(z, t, 4 * NL);
+}
+void host_mul(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *y) {
+    switch (f->NL) {
+        case 4: host_mul_t<4>(f, z, x, y); break;
+        case 8: host_mul_t<8>(f, z, x, y); break;
+        case 14: host_mul_t<14>(f, z, x, y); break;
+        case 28: host_mul_t<28>(f, z, x, y); break;
+    }
+}
+void host_add(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *y) {
+    switch (f->NL) {
+        case 4: host_add_t<4>(f, z, x, y); break;
+        case 8: host_add_t<8>(f, z, x, y); break;
+        case 14: host_add_t<14>(f, z, x, y); break;
+        case 28: host_add_t<28>(f, z, x, y); break;
+    }
+}
+void host_pow(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *e, int e_limbs) {
+    uint32_t r[RS_MAX_NL], b[RS_MAX_NL];
+    memcpy(r, f->one, 4 * f->NL);
+    memcpy(b, x, 4 * f->NL);
+    for (int i = 0; i < e_limbs; i++) {
+        uint32_t w = e[i];
+        for (int k = 0; k < 32; k++) {
+            if (w & 1) host_mul(f, r, r, b);
+            host_mul(f, b, b, b);
+            w >>= 1;
+        }
+    }
+    memcpy(z, r, 4 * f->NL);
+}
+void host_inverse(const rs_field *f, uint32_t *z, const uint32_t *x) {
+    // x^(q-2): value-level identical to Inverse (element.go:1396-1548), 0 -> 0
+    uint32_t e[RS_MAX_NL];
+    uint64_t borrow = 2;
+    for (int i = 0; i < f->NL; i++) {
+        uint64_t d = (uint64_t)f->q[i] - borrow;
+        e[i] = (uint32_t)d;
+        borrow = (d >> 63) & 1;
+    }
+    host_pow(f, z, x, e, f->NL);
+}
+void host_set_u64(const rs_field *f, uint32_t *z, uint64_t v) {
+    uint32_t t[RS_MAX_NL] = {0};
+    t[0] = (uint32_t)v;
+    t[1] = (uint32_t)(v >> 32);
+    host_mul(f, z, t, f->r2);
+}
+
+static bool geq(const uint32_t *a, const uint32_t *b, int n) {
+    for (int i = n - 1; i >= 0; i--) {
+        if (a[i] > b[i]) return true;
+        if (a[i] < b[i]) return false;
+    }
+    return true;
+}
+
+static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
+static int ilog2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
+
+static int ntt_dispatch(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse) {
+    switch (t->f->NL) {
+        case 4: return ntt_run_l4(t, out, in, n_polys, inverse);
+        case 8: return ntt_run_l8(t, out, in, n_polys, inverse);
+        case 14: return ntt_run_l14(t, out, in, n_polys, inverse);
+        case 28: return ntt_run_l28(t, out, in, n_polys, inverse);
+    }
+    return set_error(RS_ERR_UNSUPPORTED, "unsupported limb count %d", t->f->L64);
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+static inline uint32_t *elem_ptr(const rs_batch *b, size_t poly, size_t off = 0) {
+    return b->d + (poly * b->rank + off) * b->f->NL;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char *rs_last_error(void) { return g_err; }
+const char *rs_version(void) { return "ringo-b200 0.1 (sm_100a)"; }
+unsigned long long rs_launch_count(void) { return g_launches.load(); }
+
+int rs_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_error(RS_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    RS_REQUIRE(device >= 0 && device < n, RS_ERR_ARG, "rs_init: bad device index");
+    RS_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp p;
+    RS_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10) return set_error(RS_ERR_CUDA, "device %s is sm_%d%d; kernels are built for sm_100a only", p.name, p.major, p.minor);
+    return RS_OK;
+}
+
+int rs_set_stream(void *s) { g_stream = (cudaStream_t)s; return RS_OK; }
+int rs_sync(void) { RS_CUDA_CHECK(cudaStreamSynchronize(g_stream)); return RS_OK; }
+
+void *rs_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { set_error(RS_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void rs_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- field ----------------------------------------------------------------------------------
+int rs_field_create(const uint64_t *q, int L64, rs_field **out) {
+    RS_REQUIRE(q && out, RS_ERR_ARG, "rs_field_create: null argument");
+    RS_REQUIRE(L64 == 2 || L64 == 4 || L64 == 7 || L64 == 14, RS_ERR_UNSUPPORTED,
+               "rs_field_create: supported limb counts are 2, 4, 7, 14");
+    RS_REQUIRE(q[0] & 1, RS_ERR_ARG, "rs_field_create: modulus must be odd");
+    RS_REQUIRE(q[L64 - 1] != 0, RS_ERR_ARG, "rs_field_create: top limb of the modulus is zero");
+    rs_field *f = new rs_field();
+    memset(f, 0, sizeof(*f));
+    f->L64 = L64;
+    f->NL = 2 * L64;
+    for (int i = 0; i < L64; i++) { f->q[2 * i] = (uint32_t)q[i]; f->q[2 * i + 1] = (uint32_t)(q[i] >> 32); }
+    uint32_t inv = 1;
+    for (int i = 0; i < 5; i++) inv *= 2 - f->q[0] * inv;   // Newton: q^-1 mod 2^32
+    f->qinv = 0u - inv;
+    f->qs = 0;
+    if (f->q[0] == 1) f->qs = (f->q[1] == 0) ? 2 : 1;
+    // R mod q and R^2 mod q by doubling (same values as the generated rSquare, element.go:784)
+    uint32_t t[RS_MAX_NL] = {1};
+    const int n = f->NL;
+    for (int i = 0; i < 64 * n; i++) {
+        uint32_t c = 0;
+        for (int k = 0; k < n; k++) { uint32_t nc = t[k] >> 31; t[k] = (t[k] << 1) | c; c = nc; }
+        if (c || geq(t, f->q, n)) {
+            uint64_t br = 0;
+            for (int k = 0; k < n; k++) { uint64_t d = (uint64_t)t[k] - f->q[k] - br; t[k] = (uint32_t)d; br = (d >> 63) & 1; }
+        }
+        if (i == 32 * n - 1) memcpy(f->one, t, 4 * n);
+    }
+    memcpy(f->r2, t, 4 * n);
+    *out = f;
+    return RS_OK;
+}
+void rs_field_destroy(rs_field *f) { delete f; }
+int rs_field_limbs(const rs_field *f) { return f ? f->L64 : RS_ERR_ARG; }
+
+int rs_field_to_mont(const rs_field *f, uint64_t *out, const uint64_t *canonical) {
+    RS_REQUIRE(f && out && canonical, RS_ERR_ARG, "rs_field_to_mont: null argument");
+    uint32_t z[RS_MAX_NL];
+    host_mul(f, z, (const uint32_t *)canonical, f->r2);
+    memcpy(out, z, 4 * f->NL);
+    return RS_OK;
+}
+int rs_field_from_mont(const rs_field *f, uint64_t *out, const uint64_t *mont) {
+    RS_REQUIRE(f && out && mont, RS_ERR_ARG, "rs_field_from_mont: null argument");
+    uint32_t z[RS_MAX_NL], one[RS_MAX_NL] = {1};
+    host_mul(f, z, (const uint32_t *)mont, one);
+    memcpy(out, z, 4 * f->NL);
+    return RS_OK;
+}
+
+// ---- batches ----------------------------------------------------------------------------------
+int rs_batch_alloc(rs_field *f, size_t n_polys, size_t rank, rs_batch **out) {
+    RS_REQUIRE(f && out, RS_ERR_ARG, "rs_batch_alloc: null argument");
+    rs_batch *b = new rs_batch{f, n_polys, rank, nullptr, true};
+    const size_t bytes = n_polys * rank * f->NL * 4;
+    cudaError_t e = cudaMalloc((void **)&b->d, bytes ? bytes : 16);
+    if (e != cudaSuccess) { delete b; return set_error(RS_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    *out = b;
+    return RS_OK;
+}
+int rs_batch_wrap(rs_field *f, void *dptr, size_t n_polys, size_t rank, rs_batch **out) {
+    RS_REQUIRE(f && out && dptr, RS_ERR_ARG, "rs_batch_wrap: null argument");
+    RS_REQUIRE(((uintptr_t)dptr & 15) == 0, RS_ERR_ARG, "rs_batch_wrap: device pointer must be 16-byte aligned");
+    *out = new rs_batch{f, n_polys, rank, (uint32_t *)dptr, false};
+    return RS_OK;
+}
+void rs_batch_free(rs_batch *b) {
+    if (!b) return;
+    if (b->owned && b->d) cudaFree(b->d);
+    delete b;
+}
+void *rs_batch_device_ptr(rs_batch *b) { return b ? b->d : nullptr; }
+size_t rs_batch_polys(const rs_batch *b) { return b ? b->n_polys : 0; }
+size_t rs_batch_rank(const rs_batch *b) { return b ? b->rank : 0; }
+
+int rs_batch_upload(rs_batch *b, size_t poly0, size_t n, const uint64_t *host) {
+    RS_REQUIRE(b && host, RS_ERR_ARG, "rs_batch_upload: null argument");
+    RS_REQUIRE(poly0 + n <= b->n_polys, RS_ERR_SHAPE, "rs_batch_upload: poly range out of bounds");
+    RS_CUDA_CHECK(cudaMemcpyAsync(elem_ptr(b, poly0), host, n * b->rank * b->f->NL * 4, cudaMemcpyHostToDevice, g_stream));
+    return RS_OK;
+}
+int rs_batch_download(const rs_batch *b, size_t poly0, size_t n, uint64_t *host) {
+    RS_REQUIRE(b && host, RS_ERR_ARG, "rs_batch_download: null argument");
+    RS_REQUIRE(poly0 + n <= b->n_polys, RS_ERR_SHAPE, "rs_batch_download: poly range out of bounds");
+    RS_CUDA_CHECK(cudaMemcpyAsync(host, elem_ptr(b, poly0), n * b->rank * b->f->NL * 4, cudaMemcpyDeviceToHost, g_stream));
+    RS_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    return RS_OK;
+}
+int rs_batch_copy(rs_batch *dst, size_t dp, size_t doff, const rs_batch *src, size_t sp, size_t soff, size_t n) {
+    RS_REQUIRE(dst && src, RS_ERR_ARG, "rs_batch_copy: null argument");
+    RS_REQUIRE(dst->f->NL == src->f->NL, RS_ERR_SHAPE, "rs_batch_copy: field mismatch");
+    RS_REQUIRE(dp < dst->n_polys && sp < src->n_polys && doff + n <= dst->rank && soff + n <= src->rank, RS_ERR_SHAPE,
+               "rs_batch_copy: range out of bounds");
+    if (n) RS_CUDA_CHECK(cudaMemcpyAsync(elem_ptr(dst, dp, doff), elem_ptr(src, sp, soff), n * src->f->NL * 4,
+                                         cudaMemcpyDeviceToDevice, g_stream));
+    return RS_OK;
+}
+int rs_batch_zero(rs_batch *dst, size_t poly, size_t off, size_t n) {
+    RS_REQUIRE(dst, RS_ERR_ARG, "rs_batch_zero: null argument");
+    RS_REQUIRE(poly < dst->n_polys && off + n <= dst->rank, RS_ERR_SHAPE, "rs_batch_zero: range out of bounds");
+    if (n) RS_CUDA_CHECK(cudaMemsetAsync(elem_ptr(dst, poly, off), 0, n * dst->f->NL * 4, g_stream));
+    return RS_OK;
+}
+
+// ---- NTT ---------------------------------------------------------------------------------------
+int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
+    RS_REQUIRE(f && out, RS_ERR_ARG, "rs_ntt_create: null argument");
+    RS_REQUIRE(logN >= 0 && logN <= 26, RS_ERR_UNSUPPORTED, "rs_ntt_create: logN out of range");
+    const size_t N = (size_t)1 << logN;
+    const int n = f->NL;
+    // (q-1) mod 2N == 0  (ntt.go:35-37, :162-164)
+    {
+        uint64_t q0 = ((uint64_t)f->q[1] << 32) | f->q[0];
+        if (((q0 - 1) & (2 * N - 1)) != 0) return set_error(RS_ERR_NTT, "NTT not supported");
+    }
+    rs_ntt *t = new rs_ntt();
+    t->f = f; t->logN = logN; t->negacyclic = negacyclic; t->d_tw = t->d_twinv = nullptr;
+    t->h_tw.assign(N * n, 0);
+    t->h_twinv.assign(N * n, 0);
+    // generator search: smallest x >= 2 with (x^((q-1)/order))^(order/2) != 1  (ntt.go:40-53, :167-180)
+    const uint64_t order = negacyclic ? 2 * N : N;
+    uint32_t g[RS_MAX_NL], ginv[RS_MAX_NL];
+    if (order >= 2) {
+        uint32_t e[RS_MAX_NL], qm1[RS_MAX_NL];
+        memcpy(qm1, f->q, 4 * n);
+        qm1[0] -= 1;   // q odd
+        const int sh = ilog2(order);
+        for (int i = 0; i < n; i++) {
+            const int w = sh / 32, b = sh % 32;
+            uint32_t lo = (i + w < n) ? qm1[i + w] : 0, hi = (i + w + 1 < n) ? qm1[i + w + 1] : 0;
+            e[i] = b ? ((lo >> b) | (hi << (32 - b))) : lo;
+        }
+        uint32_t half[2] = {(uint32_t)(order >> 1), (uint32_t)((order >> 1) >> 32)};
+        for (uint64_t x = 2;; x++) {
+            uint32_t xm[RS_MAX_NL], gp[RS_MAX_NL];
+            host_set_u64(f, xm, x);
+            host_pow(f, g, xm, e, n);
+            host_pow(f, gp, g, half, 2);
+            if (memcmp(gp, f->one, 4 * n) != 0) break;
+        }
+        host_inverse(f, ginv, g);
+    } else {
+        memcpy(g, f->one, 4 * n);
+        memcpy(ginv, f->one, 4 * n);
+    }
+    auto brv = [](size_t i, int bits) { size_t r = 0; for (int k = 0; k < bits; k++) { r = (r << 1) | (i & 1); i >>= 1; } return r; };
+    if (negacyclic) {
+        // tw[brv(i)] = g^i, i < N  (ntt.go:183-192)
+        uint32_t p[RS_MAX_NL], pi[RS_MAX_NL];
+        memcpy(p, f->one, 4 * n); memcpy(pi, f->one, 4 * n);
+        for (size_t i = 0; i < N; i++) {
+            const size_t j = brv(i, logN);
+            memcpy(&t->h_tw[j * n], p, 4 * n);
+            memcpy(&t->h_twinv[j * n], pi, 4 * n);
+            host_mul(f, p, p, g);
+            host_mul(f, pi, pi, ginv);
+        }
+    } else if (N >= 2) {
+        // twRef[brv_{N/2}(i)] = g^i, i < N/2; tw[m+i] = twRef[i], i < m, m = 1,2,..,N/2  (ntt.go:56-84)
+        const size_t H = N / 2;
+        std::vector<uint32_t> ref(H * n), refi(H * n);
+        uint32_t p[RS_MAX_NL], pi[RS_MAX_NL];
+        memcpy(p, f->one, 4 * n); memcpy(pi, f->one, 4 * n);
+        for (size_t i = 0; i < H; i++) {
+            const size_t j = brv(i, logN - 1);
+            memcpy(&ref[j * n], p, 4 * n);
+            memcpy(&refi[j * n], pi, 4 * n);
+            host_mul(f, p, p, g);
+            host_mul(f, pi, pi, ginv);
+        }
+        for (size_t m = 1; m <= H; m <<= 1)
+            for (size_t i = 0; i < m; i++) {
+                memcpy(&t->h_tw[(m + i) * n], &ref[i * n], 4 * n);
+                memcpy(&t->h_twinv[(m + i) * n], &refi[i * n], 4 * n);
+            }
+    }
+    uint32_t nm[RS_MAX_NL];
+    host_set_u64(f, nm, (uint64_t)N);
+    host_inverse(f, t->ninv, nm);
+    if (N >= 2) host_mul(f, t->ninv_w1, t->ninv, &t->h_twinv[1 * n]);
+    else memcpy(t->ninv_w1, t->ninv, 4 * n);
+    const size_t bytes = N * n * 4;
+    cudaError_t e1 = cudaMalloc((void **)&t->d_tw, bytes), e2 = cudaMalloc((void **)&t->d_twinv, bytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        if (t->d_tw) cudaFree(t->d_tw);
+        if (t->d_twinv) cudaFree(t->d_twinv);
+        delete t;
+        return set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    cudaMemcpy(t->d_tw, t->h_tw.data(), bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(t->d_twinv, t->h_twinv.data(), bytes, cudaMemcpyHostToDevice);
+    *out = t;
+    return RS_OK;
+}
+void rs_ntt_destroy(rs_ntt *t) {
+    if (!t) return;
+    if (t->d_tw) cudaFree(t->d_tw);
+    if (t->d_twinv) cudaFree(t->d_twinv);
+    delete t;
+}
+int rs_ntt_rank_log2(const rs_ntt *t) { return t ? t->logN : RS_ERR_ARG; }
+int rs_ntt_tables(const rs_ntt *t, uint64_t *tw, uint64_t *twinv, uint64_t *rankinv) {
+    RS_REQUIRE(t, RS_ERR_ARG, "rs_ntt_tables: null argument");
+    if (tw) memcpy(tw, t->h_tw.data(), t->h_tw.size() * 4);
+    if (twinv) memcpy(twinv, t->h_twinv.data(), t->h_twinv.size() * 4);
+    if (rankinv) memcpy(rankinv, t->ninv, 4 * t->f->NL);
+    return RS_OK;
+}
+
+static int ntt_call(rs_ntt *t, rs_batch *dst, size_t dp, const rs_batch *src, size_t sp, size_t n, bool inverse) {
+    RS_REQUIRE(t && dst && src, RS_ERR_ARG, "ntt: null argument");
+    const size_t N = (size_t)1 << t->logN;
+    RS_REQUIRE(dst->rank == N && src->rank == N, RS_ERR_SHAPE, "inconsistent input(s)");
+    RS_REQUIRE(dst->f->NL == t->f->NL && src->f->NL == t->f->NL, RS_ERR_SHAPE, "ntt: field mismatch");
+    RS_REQUIRE(dp + n <= dst->n_polys && sp + n <= src->n_polys, RS_ERR_SHAPE, "ntt: poly range out of bounds");
+    return ntt_dispatch(t, elem_ptr(dst, dp), elem_ptr(src, sp), n, inverse);
+}
+int rs_ntt_forward(rs_ntt *t, rs_batch *dst, size_t dp, const rs_batch *src, size_t sp, size_t n) {
+    return ntt_call(t, dst, dp, src, sp, n, false);
+}
+int rs_ntt_inverse(rs_ntt *t, rs_batch *dst, size_t dp, const rs_batch *src, size_t sp, size_t n) {
+    return ntt_call(t, dst, dp, src, sp, n, true);
+}
+int rs_ntt_profile(rs_ntt *t, rs_batch *b, size_t n_polys, int inverse, int reps, float *pass_ms, int *n_passes) {
+    RS_REQUIRE(t && b && pass_ms && n_passes && reps > 0, RS_ERR_ARG, "rs_ntt_profile: bad argument");
+    RS_REQUIRE(b->rank == ((size_t)1 << t->logN) && n_polys <= b->n_polys, RS_ERR_SHAPE, "inconsistent input(s)");
+    PassProfile prof;
+    cudaEvent_t start;
+    RS_CUDA_CHECK(cudaEventCreate(&start));
+    for (int i = 0; i < 16; i++) RS_CUDA_CHECK(cudaEventCreate(&prof.ev[i]));
+    const int cap = *n_passes;
+    double acc[16] = {0};
+    int np = 0, rc = RS_OK;
+    for (int r = 0; r < reps && rc == RS_OK; r++) {
+        prof.n = 0;
+        RS_CUDA_CHECK(cudaEventRecord(start, g_stream));
+        g_pass_profile = &prof;
+        rc = ntt_dispatch(t, b->d, b->d, n_polys, inverse != 0);
+        g_pass_profile = nullptr;
+        if (rc) break;
+        RS_CUDA_CHECK(cudaStreamSynchronize(g_stream));
+        np = prof.n;
+        for (int i = 0; i < np; i++) {
+            float ms = 0;
+            RS_CUDA_CHECK(cudaEventElapsedTime(&ms, i ? prof.ev[i - 1] : start, prof.ev[i]));
+            acc[i] += ms;
+        }
+    }
+    cudaEventDestroy(start);
+    for (int i = 0; i < 16; i++) cudaEventDestroy(prof.ev[i]);
+    if (rc) return rc;
+    RS_REQUIRE(np <= cap, RS_ERR_ARG, "rs_ntt_profile: pass_ms too small");
+    for (int i = 0; i < np; i++) pass_ms[i] = (float)(acc[i] / reps);
+    *n_passes = np;
+    return RS_OK;
+}
+int rs_ntt_inverse_embed(rs_ntt *t, rs_batch *dst, size_t dp, const rs_batch *src, size_t sp, size_t n, int zero_pad) {
+    RS_REQUIRE(t && dst && src, RS_ERR_ARG, "ntt: null argument");
+    const size_t N = (size_t)1 << t->logN;
+    RS_REQUIRE(dst->rank >= N && src->rank >= N, RS_ERR_SHAPE, "inconsistent input(s)");
+    RS_REQUIRE(dp + n <= dst->n_polys && sp + n <= src->n_polys, RS_ERR_SHAPE, "ntt: poly range out of bounds");
+    for (size_t i = 0; i < n; i++) {
+        int rc = ntt_dispatch(t, elem_ptr(dst, dp + i), elem_ptr(src, sp + i), 1, true);
+        if (rc) return rc;
+        if (zero_pad && dst->rank > N) {
+            rc = rs_batch_zero(dst, dp + i, N, dst->rank - N);
+            if (rc) return rc;
+        }
+    }
+    return RS_OK;
+}
+
+// ---- element-wise --------------------------------------------------------------------------------
+static int pw_check(const rs_batch *o, size_t op, const rs_batch *a, size_t ap, const rs_batch *b, size_t bp, size_t n) {
+    RS_REQUIRE(o && a, RS_ERR_ARG, "vec op: null argument");
+    RS_REQUIRE(o->rank == a->rank && (!b || b->rank == a->rank), RS_ERR_SHAPE, "inconsistent input(s)");
+    RS_REQUIRE(o->f->NL == a->f->NL && (!b || b->f->NL == a->f->NL), RS_ERR_SHAPE, "vec op: field mismatch");
+    RS_REQUIRE(op + n <= o->n_polys && ap + n <= a->n_polys && (!b || bp + n <= b->n_polys), RS_ERR_SHAPE,
+               "vec op: poly range out of bounds");
+    return RS_OK;
+}
+#define RS_BINARY(NAME, OPC)                                                                                       \
+    int NAME(rs_batch *o, size_t op, const rs_batch *a, size_t ap, const rs_batch *b, size_t bp, size_t n) {        \
+        RS_REQUIRE(b, RS_ERR_ARG, "vec op: null argument");                                                         \
+        int rc = pw_check(o, op, a, ap, b, bp, n);                                                                  \
+        if (rc) return rc;                                                                                          \
+        return pointwise(OPC, o->f, elem_ptr(o, op), elem_ptr(a, ap), elem_ptr(b, bp), nullptr, n * o->rank);       \
+    }
+RS_BINARY(rs_vec_add, OP_ADD)
+RS_BINARY(rs_vec_sub, OP_SUB)
+RS_BINARY(rs_vec_mul, OP_MUL)
+RS_BINARY(rs_vec_mul_add, OP_MULADD)
+RS_BINARY(rs_vec_mul_sub, OP_MULSUB)
+int rs_vec_neg(rs_batch *o, size_t op, const rs_batch *a, size_t ap, size_t n) {
+    int rc = pw_check(o, op, a, ap, nullptr, 0, n);
+    if (rc) return rc;
+    return pointwise(OP_NEG, o->f, elem_ptr(o, op), elem_ptr(a, ap), nullptr, nullptr, n * o->rank);
+}
+#define RS_SCALAR(NAME, OPC)                                                                                        \
+    int NAME(rs_batch *o, size_t op, const rs_batch *a, size_t ap, const uint64_t *c, size_t n) {                    \
+        RS_REQUIRE(c, RS_ERR_ARG, "vec op: null scalar");                                                            \
+        int rc = pw_check(o, op, a, ap, nullptr, 0, n);                                                              \
+        if (rc) return rc;                                                                                           \
+        return pointwise(OPC, o->f, elem_ptr(o, op), elem_ptr(a, ap), nullptr, (const uint32_t *)c, n * o->rank);    \
+    }
+RS_SCALAR(rs_vec_scalar_mul, OP_SMUL)
+RS_SCALAR(rs_vec_scalar_mul_add, OP_SMULADD)
+RS_SCALAR(rs_vec_scalar_mul_sub, OP_SMULSUB)
+
+// ---- Buckler ---------------------------------------------------------------------------------------
+int rs_eval_circuit(rs_batch *out, size_t out_poly, const rs_batch *pw, const rs_batch *w, const rs_term *terms,
+                    size_t n_terms, const uint64_t *coeffs, size_t n_coeffs, const uint64_t *batch_const) {
+    RS_REQUIRE(out && w && terms && coeffs && batch_const, RS_ERR_ARG, "rs_eval_circuit: null argument");
+    RS_REQUIRE(out_poly < out->n_polys, RS_ERR_SHAPE, "rs_eval_circuit: out poly out of bounds");
+    RS_REQUIRE(w->rank == out->rank && (!pw || pw->rank == out->rank), RS_ERR_SHAPE, "inconsistent input(s)");
+    const int NL = out->f->NL;
+    for (size_t k = 0; k < n_terms; k++) {
+        const rs_term &t = terms[k];
+        RS_REQUIRE(t.coeff >= 0 && (size_t)t.coeff < n_coeffs, RS_ERR_ARG, "rs_eval_circuit: coeff index out of range");
+        RS_REQUIRE(t.n_w >= 0 && t.n_w <= RS_TERM_MAX_W, RS_ERR_ARG, "rs_eval_circuit: too many witness factors");
+        RS_REQUIRE(t.pw < 0 || (pw && (size_t)t.pw < pw->n_polys), RS_ERR_ARG, "rs_eval_circuit: public witness index out of range");
+        for (int x = 0; x < t.n_w; x++)
+            RS_REQUIRE(t.w[x] >= 0 && (size_t)t.w[x] < w->n_polys, RS_ERR_ARG, "rs_eval_circuit: witness index out of range");
+        RS_REQUIRE(k == 0 || t.constraint >= terms[k - 1].constraint, RS_ERR_ARG, "rs_eval_circuit: terms must be grouped by constraint");
+    }
+    rs_term *d_terms = nullptr;
+    uint32_t *d_coeffs = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_terms, (n_terms ? n_terms : 1) * sizeof(rs_term), g_stream));
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_coeffs, (n_coeffs ? n_coeffs : 1) * NL * 4, g_stream));
+    RS_CUDA_CHECK(cudaMemcpyAsync(d_terms, terms, n_terms * sizeof(rs_term), cudaMemcpyHostToDevice, g_stream));
+    RS_CUDA_CHECK(cudaMemcpyAsync(d_coeffs, coeffs, n_coeffs * NL * 4, cudaMemcpyHostToDevice, g_stream));
+    int rc = eval_circuit(out->f, elem_ptr(out, out_poly), pw ? pw->d : nullptr, w->d, d_terms, (int)n_terms, d_coeffs,
+                          (const uint32_t *)batch_const, out->rank);
+    cudaFreeAsync(d_terms, g_stream);
+    cudaFreeAsync(d_coeffs, g_stream);
+    return rc;
+}
+
+int rs_quorem_vanishing(rs_batch *quo, size_t qp, rs_batch *rem, size_t rp, const rs_batch *p, size_t pp, size_t N) {
+    RS_REQUIRE(quo && rem && p, RS_ERR_ARG, "rs_quorem_vanishing: null argument");
+    RS_REQUIRE(quo->rank == p->rank && rem->rank == p->rank, RS_ERR_SHAPE, "inputs not consistent");
+    RS_REQUIRE(qp < quo->n_polys && rp < rem->n_polys && pp < p->n_polys, RS_ERR_SHAPE, "rs_quorem_vanishing: poly out of bounds");
+    RS_REQUIRE(N >= 1, RS_ERR_ARG, "rs_quorem_vanishing: N must be >= 1");
+    RS_REQUIRE(elem_ptr(quo, qp) != elem_ptr(p, pp), RS_ERR_ARG, "rs_quorem_vanishing: quo must not alias p");
+    return quorem(p->f, elem_ptr(quo, qp), elem_ptr(rem, rp), elem_ptr(p, pp), p->rank, N);
+}
+
+int rs_aut(rs_batch *out, size_t op, const rs_batch *p, size_t pp, size_t n, long idx, int is_ntt) {
+    RS_REQUIRE(out && p, RS_ERR_ARG, "rs_aut: null argument");
+    RS_REQUIRE(out->rank == p->rank, RS_ERR_SHAPE, "inconsistent input(s)");
+    RS_REQUIRE(is_pow2(p->rank), RS_ERR_SHAPE, "rs_aut: rank must be a power of two");
+    RS_REQUIRE(idx % 2 != 0, RS_ERR_ARG, "AutTo: idx must be odd");
+    RS_REQUIRE(op + n <= out->n_polys && pp + n <= p->n_polys, RS_ERR_SHAPE, "rs_aut: poly range out of bounds");
+    RS_REQUIRE(elem_ptr(out, op) != elem_ptr(p, pp), RS_ERR_ARG, "rs_aut: out must not alias p");
+    const long twoN = 2 * (long)p->rank;
+    long i = idx % twoN;
+    if (i < 0) i += twoN;
+    // idx^-1 mod 2N (idx odd): Newton iteration in Z/2^k
+    unsigned long long inv = 1, ui = (unsigned long long)i;
+    for (int k = 0; k < 6; k++) inv *= 2 - ui * inv;
+    inv &= (unsigned long long)(twoN - 1);
+    return aut(p->f, elem_ptr(out, op), elem_ptr(p, pp), ilog2(p->rank), ui, inv, is_ntt, n);
+}
+
+int rs_reverse_scale(rs_batch *out, size_t op, const rs_batch *v, size_t vp, const uint64_t *scale) {
+    RS_REQUIRE(out && v && scale, RS_ERR_ARG, "rs_reverse_scale: null argument");
+    RS_REQUIRE(out->rank == v->rank, RS_ERR_SHAPE, "inconsistent input(s)");
+    RS_REQUIRE(op < out->n_polys && vp < v->n_polys, RS_ERR_SHAPE, "rs_reverse_scale: poly out of bounds");
+    RS_REQUIRE(elem_ptr(out, op) != elem_ptr(v, vp), RS_ERR_ARG, "rs_reverse_scale: out must not alias v");
+    return reverse_scale(v->f, elem_ptr(out, op), elem_ptr(v, vp), (const uint32_t *)scale, v->rank);
+}
+
+int rs_poly_evaluate(const rs_batch *p, size_t poly, size_t n_elems, const uint64_t *x, uint64_t *result) {
+    RS_REQUIRE(p && x && result, RS_ERR_ARG, "rs_poly_evaluate: null argument");
+    RS_REQUIRE(poly < p->n_polys && n_elems <= p->rank, RS_ERR_SHAPE, "rs_poly_evaluate: range out of bounds");
+    const rs_field *f = p->f;
+    const int NL = f->NL;
+    if (n_elems == 0) { memset(result, 0, 4 * NL); return RS_OK; }
+    const int CH = 64;
+    const size_t n_chunks = (n_elems + CH - 1) / CH;
+    uint32_t xch[RS_MAX_NL];
+    uint32_t e[2] = {(uint32_t)CH, 0};
+    host_pow(f, xch, (const uint32_t *)x, e, 1);
+    uint32_t *d_partial = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_partial, (n_chunks + 1) * NL * 4, g_stream));
+    uint32_t *d_result = d_partial + n_chunks * NL;
+    int rc = horner(f, d_result, d_partial, elem_ptr(p, poly), n_elems, (const uint32_t *)x, xch, CH);
+    if (rc == RS_OK) {
+        cudaError_t e2 = cudaMemcpyAsync(result, d_result, NL * 4, cudaMemcpyDeviceToHost, g_stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(g_stream);
+        if (e2 != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_poly_evaluate: %s", cudaGetErrorString(e2));
+    }
+    cudaFreeAsync(d_partial, g_stream);
+    return rc;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,61 @@
+// microbench.cu -- measures the integer-pipe roofline denominator used by bench.py:
+// sustained 32x32+64 multiply-add (IMAD.WIDE.U32) throughput of the whole chip.
+#include "common.cuh"
+
+namespace rs {
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256) imad_kernel(unsigned long long *out, uint32_t a, uint32_t b, int iters) {
+    unsigned long long acc[8];
+    uint32_t lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k] = threadIdx.x + k; lo[k] = threadIdx.x * 3 + k; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (WIDE) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
+                else asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[k]) : "r"(a + k), "r"(b));
+            }
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k] + lo[k];
+    if (s == 0x1234567ull) out[0] = s;   // keep the chains alive
+}
+
+}  // namespace rs
+
+extern "C" {
+#pragma GCC visibility push(default)
+// Returns sustained G IMAD/s: wide != 0 -> IMAD.WIDE.U32 (32x32+64), else 32-bit IMAD.
+int rs_bench_imad_peak(int wide, double *gops) {
+    using namespace rs;
+    RS_REQUIRE(gops, RS_ERR_ARG, "rs_bench_imad_peak: null argument");
+    unsigned long long *d = nullptr;
+    RS_CUDA_CHECK(cudaMalloc((void **)&d, 8));
+    const int iters = 4096, blocks = 148 * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    RS_CUDA_CHECK(cudaEventCreate(&e0));
+    RS_CUDA_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        RS_CUDA_CHECK(cudaEventRecord(e0, current_stream()));
+        if (wide) imad_kernel<true><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
+        else imad_kernel<false><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
+        count_launch();
+        RS_CUDA_CHECK(cudaEventRecord(e1, current_stream()));
+        RS_CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        RS_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    const double ops = (double)blocks * threads * (double)iters * 16 * 8;
+    *gops = ops / (best * 1e-3) / 1e9;
+    return RS_OK;
+}
+#pragma GCC visibility pop
+}

@@ -1,0 +1,99 @@
+// ntt_launch.cuh -- host-side pass planning + launches for ntt_pass_kernel (see ntt.cuh).
+#pragma once
+#include "common.cuh"
+#include "ntt.cuh"
+
+namespace rs {
+
+template <int NL> struct NttTuning {
+    // 2^R elements per thread between shared-memory exchanges
+    static constexpr int R = (NL <= 8) ? 3 : (NL <= 14 ? 2 : 1);
+    static constexpr int THREADS = 256;
+    static constexpr int TS = THREADS << R;
+    static constexpr int LOG_TS = 8 + R;
+};
+
+template <int NL, int QS, bool INV, bool SCALE>
+int launch_pass(const rs_ntt *t, uint32_t *out, const uint32_t *in, const NttConsts<NL> &C, const PassGeom &G,
+                unsigned long long tiles) {
+    using T = NttTuning<NL>;
+    auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, INV, SCALE>;
+    constexpr int smem = SmemLayout<NL, T::TS>::BYTES;
+    static bool configured = false;
+    if (!configured) {
+        RS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    RS_REQUIRE(tiles <= 0x7fffffffull, RS_ERR_UNSUPPORTED, "ntt: batch too large for one launch");
+    kern<<<(unsigned)tiles, T::THREADS, smem, current_stream()>>>(out, in, INV ? t->d_twinv : t->d_tw, C, G);
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    if (g_pass_profile && g_pass_profile->n < 16) RS_CUDA_CHECK(cudaEventRecord(g_pass_profile->ev[g_pass_profile->n++], current_stream()));
+    return RS_OK;
+}
+
+// Plans and launches the passes of one batched transform.
+//   forward : row-major passes over the top stages (s0 = 0 upward), then the contiguous pass
+//   inverse : the same passes in reverse order; the pass that owns stage 0 folds N^-1 in
+template <int NL, int QS>
+int ntt_run(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse) {
+    using T = NttTuning<NL>;
+    const int logN = t->logN;
+    if (n_polys == 0) return RS_OK;
+    if (logN == 0) {   // N = 1: both transforms are the identity (1^-1 = 1)
+        if (out != in)
+            RS_CUDA_CHECK(cudaMemcpyAsync(out, in, n_polys * NL * 4, cudaMemcpyDeviceToDevice, current_stream()));
+        return RS_OK;
+    }
+    NttConsts<NL> C;
+    C.F = make_params<NL>(t->f);
+    for (int i = 0; i < NL; i++) { C.ninv[i] = t->ninv[i]; C.ninv_w1[i] = t->ninv_w1[i]; }
+
+    const unsigned long long total = (unsigned long long)n_polys << logN;
+    const int KB = logN < T::LOG_TS ? logN : T::LOG_TS;   // stages of the contiguous pass
+    const int top = logN - KB;                              // stages left for column passes
+    const int KA_MAX = T::LOG_TS - 3;                       // keep >= 8 contiguous columns per row
+    const int n_row = top ? (top + KA_MAX - 1) / KA_MAX : 0;
+
+    PassGeom passes[8];
+    int np = 0;
+    int s = 0;
+    for (int r = 0; r < n_row; r++) {
+        const int K = (top - s + (n_row - r) - 1) / (n_row - r);   // even split of the remaining stages
+        PassGeom G{};
+        G.logN = logN; G.K = K; G.s0 = s; G.pl = logN - s - K; G.logW = T::LOG_TS - K; G.col_major = 0;
+        G.total_elems = total;
+        passes[np++] = G;
+        s += K;
+    }
+    {
+        PassGeom G{};
+        G.logN = logN; G.K = KB; G.s0 = top; G.pl = 0; G.logW = T::LOG_TS - KB; G.col_major = 1;
+        G.total_elems = total;
+        passes[np++] = G;
+    }
+    const unsigned long long tiles_col = (total + T::TS - 1) / T::TS;
+    const unsigned long long tiles_row = total / T::TS;   // logN > LOG_TS here, so it divides
+
+    const uint32_t *src = in;
+    if (!inverse) {
+        for (int p = 0; p < np; p++) {
+            const PassGeom &G = passes[p];
+            int rc = launch_pass<NL, QS, false, false>(t, out, src, C, G, G.col_major ? tiles_col : tiles_row);
+            if (rc) return rc;
+            src = out;
+        }
+    } else {
+        for (int p = np - 1; p >= 0; p--) {
+            const PassGeom &G = passes[p];
+            int rc = (G.s0 == 0)
+                         ? launch_pass<NL, QS, true, true>(t, out, src, C, G, G.col_major ? tiles_col : tiles_row)
+                         : launch_pass<NL, QS, true, false>(t, out, src, C, G, G.col_major ? tiles_col : tiles_row);
+            if (rc) return rc;
+            src = out;
+        }
+    }
+    return RS_OK;
+}
+
+}  // namespace rs

@@ -1,0 +1,354 @@
+// pointwise.cu -- element-wise field kernels and the fused Buckler constraint evaluator.
+//
+// Replaces math/bigpoly/vec.go:9-121 (addVecTo ... mulVecTo), base_op.go:49-171
+// (Add/Sub/Neg/ScalarMul/Mul/MulAdd/MulSub/ScalarMulAdd/ScalarMulSub To),
+// cyclic.go:18-37 (QuoRemByVanishing), cyclotomic.go:49-82 (autTo/autNTTTo),
+// buckler/prover.go:355-379 (evalCircuit), buckler/linear.go:38-41 and poly.go:64-76.
+// All of these stream each coefficient once: one thread per element, 16-byte vector
+// accesses, grid sized in whole waves of the 148 SMs.
+#include "common.cuh"
+
+namespace rs {
+
+enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
+
+template <int NL>
+__device__ __forceinline__ void ld_elem(uint32_t *x, const uint32_t *p) {
+    if (NL % 4 == 0) {
+#pragma unroll
+        for (int h = 0; h < NL / 4; h++) {
+            uint4 v = reinterpret_cast<const uint4 *>(p)[h];
+            x[4 * h] = v.x; x[4 * h + 1] = v.y; x[4 * h + 2] = v.z; x[4 * h + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < NL / 2; h++) {
+            uint2 v = reinterpret_cast<const uint2 *>(p)[h];
+            x[2 * h] = v.x; x[2 * h + 1] = v.y;
+        }
+    }
+}
+
+template <int NL>
+__device__ __forceinline__ void st_elem(uint32_t *p, const uint32_t *x) {
+    if (NL % 4 == 0) {
+#pragma unroll
+        for (int h = 0; h < NL / 4; h++)
+            reinterpret_cast<uint4 *>(p)[h] = make_uint4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
+    } else {
+#pragma unroll
+        for (int h = 0; h < NL / 2; h++) reinterpret_cast<uint2 *>(p)[h] = make_uint2(x[2 * h], x[2 * h + 1]);
+    }
+}
+
+template <int NL> struct Scalar { uint32_t v[NL]; };
+
+template <int NL, int QS, int OP>
+__global__ void __launch_bounds__(256) pointwise_kernel(uint32_t *out, const uint32_t *a, const uint32_t *b,
+                                                        const __grid_constant__ Scalar<NL> c,
+                                                        const __grid_constant__ FieldParams<NL> F, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x[NL], y[NL], z[NL];
+        ld_elem<NL>(x, a + i * NL);
+        if (OP == OP_ADD || OP == OP_SUB || OP == OP_MUL || OP == OP_MULADD || OP == OP_MULSUB) ld_elem<NL>(y, b + i * NL);
+        if (OP == OP_ADD) mod_add<NL>(z, x, y, F);
+        if (OP == OP_SUB) mod_sub<NL>(z, x, y, F);
+        if (OP == OP_NEG) mod_neg<NL>(z, x, F);
+        if (OP == OP_MUL || OP == OP_MULADD || OP == OP_MULSUB) mont_mul<NL, QS>(z, x, y, F);
+        if (OP == OP_SMUL || OP == OP_SMULADD || OP == OP_SMULSUB) mont_mul<NL, QS>(z, x, c.v, F);
+        if (OP == OP_MULADD || OP == OP_SMULADD) { ld_elem<NL>(x, out + i * NL); mod_add<NL>(z, x, z, F); }
+        if (OP == OP_MULSUB || OP == OP_SMULSUB) { ld_elem<NL>(x, out + i * NL); mod_sub<NL>(z, x, z, F); }
+        st_elem<NL>(out + i * NL, z);
+    }
+}
+
+static inline unsigned grid_for(size_t n, int threads) {
+    size_t blocks = (n + threads - 1) / threads;
+    const size_t cap = 148 * 16;   // whole waves of 148 SMs; the kernels grid-stride beyond that
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks ? blocks : 1);
+}
+
+template <int NL, int QS>
+static int pointwise_launch(int op, const rs_field *f, uint32_t *out, const uint32_t *a, const uint32_t *b,
+                            const uint32_t *c, size_t n) {
+    FieldParams<NL> F = make_params<NL>(f);
+    Scalar<NL> sc;
+    for (int i = 0; i < NL; i++) sc.v[i] = c ? c[i] : 0;
+    const unsigned grid = grid_for(n, 256);
+    cudaStream_t st = current_stream();
+#define RS_PW(OPC) case OPC: pointwise_kernel<NL, QS, OPC><<<grid, 256, 0, st>>>(out, a, b, sc, F, n); break;
+    switch (op) {
+        RS_PW(OP_ADD) RS_PW(OP_SUB) RS_PW(OP_NEG) RS_PW(OP_MUL) RS_PW(OP_MULADD) RS_PW(OP_MULSUB)
+        RS_PW(OP_SMUL) RS_PW(OP_SMULADD) RS_PW(OP_SMULSUB)
+        default: return set_error(RS_ERR_ARG, "pointwise: bad op");
+    }
+#undef RS_PW
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// dispatch over the compiled (limbs, modulus shape) combinations
+#define RS_FIELD_DISPATCH(f, CALL)                                              \
+    switch ((f)->NL) {                                                          \
+        case 4: if ((f)->qs >= 1) { CALL(4, 1); } else { CALL(4, 0); } break;   \
+        case 8: if ((f)->qs == 2) { CALL(8, 2); } else if ((f)->qs == 1) { CALL(8, 1); } else { CALL(8, 0); } break; \
+        case 14: if ((f)->qs == 2) { CALL(14, 2); } else { CALL(14, 0); } break; \
+        case 28: if ((f)->qs == 2) { CALL(28, 2); } else { CALL(28, 0); } break; \
+        default: return set_error(RS_ERR_UNSUPPORTED, "unsupported limb count %d", (f)->L64); \
+    }
+
+int pointwise(int op, const rs_field *f, uint32_t *out, const uint32_t *a, const uint32_t *b, const uint32_t *c, size_t n) {
+    if (n == 0) return RS_OK;
+#define CALL(NL, QS) return pointwise_launch<NL, QS>(op, f, out, a, b, c, n)
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// evalCircuit (buckler/prover.go:355-379), fused: one pass over the witnesses
+// ---------------------------------------------------------------------------
+template <int NL, int QS>
+__global__ void __launch_bounds__(256) eval_circuit_kernel(uint32_t *out, const uint32_t *pw, const uint32_t *w,
+                                                           const rs_term *terms, int n_terms, const uint32_t *coeffs,
+                                                           const __grid_constant__ Scalar<NL> bc,
+                                                           const __grid_constant__ FieldParams<NL> F, size_t rank) {
+    for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < rank; j += (size_t)gridDim.x * blockDim.x) {
+        uint32_t acc[NL], ev[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) { acc[l] = 0; ev[l] = 0; }
+        int cur = n_terms ? terms[0].constraint : -1;
+        for (int k = 0; k <= n_terms; k++) {
+            if (k == n_terms || terms[k].constraint != cur) {
+                // eval *= batchConst ; pOut += eval   (prover.go:374-375)
+                uint32_t t[NL];
+                mont_mul<NL, QS>(t, ev, bc.v, F);
+                mod_add<NL>(acc, acc, t, F);
+#pragma unroll
+                for (int l = 0; l < NL; l++) ev[l] = 0;
+                if (k == n_terms) break;
+                cur = terms[k].constraint;
+            }
+            const rs_term tm = terms[k];
+            uint32_t term[NL], fac[NL], t[NL];
+            ld_elem<NL>(term, coeffs + (size_t)tm.coeff * NL);
+            if (tm.pw >= 0) {
+                ld_elem<NL>(fac, pw + ((size_t)tm.pw * rank + j) * NL);
+                mont_mul<NL, QS>(t, term, fac, F);
+#pragma unroll
+                for (int l = 0; l < NL; l++) term[l] = t[l];
+            }
+            for (int x = 0; x < tm.n_w; x++) {
+                ld_elem<NL>(fac, w + ((size_t)tm.w[x] * rank + j) * NL);
+                mont_mul<NL, QS>(t, term, fac, F);
+#pragma unroll
+                for (int l = 0; l < NL; l++) term[l] = t[l];
+            }
+            mod_add<NL>(ev, ev, term, F);
+        }
+        st_elem<NL>(out + j * NL, acc);
+    }
+}
+
+int eval_circuit(const rs_field *f, uint32_t *out, const uint32_t *pw, const uint32_t *w, const rs_term *d_terms,
+                 int n_terms, const uint32_t *d_coeffs, const uint32_t *bc, size_t rank) {
+#define CALL(NL, QS)                                                                                       \
+    {                                                                                                      \
+        FieldParams<NL> F = make_params<NL>(f);                                                            \
+        Scalar<NL> s;                                                                                      \
+        for (int i = 0; i < NL; i++) s.v[i] = bc[i];                                                       \
+        eval_circuit_kernel<NL, QS><<<grid_for(rank, 128), 128, 0, current_stream()>>>(out, pw, w, d_terms, n_terms, \
+                                                                                  d_coeffs, s, F, rank);   \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// QuoRemByVanishing (cyclic.go:18-37).  The sequential fold over i = rank-1 .. N is, per
+// residue class r = i mod N, a suffix sum over the blocks k = i / N:
+//   S_k = p[kN + r] + S_{k+1}  (S beyond the top = 0);  quo[kN + r] = S_{k+1};
+//   rem[r] = S_0; rem[i >= N] = 0.
+// (a partial top block, rank not a multiple of N, is handled by bounds checks)
+// ---------------------------------------------------------------------------
+template <int NL>
+__global__ void __launch_bounds__(256) quorem_kernel(uint32_t *quo, uint32_t *rem, const uint32_t *p,
+                                                     const __grid_constant__ FieldParams<NL> F, size_t rank, size_t N) {
+    for (size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x; r < N && r < rank; r += (size_t)gridDim.x * blockDim.x) {
+        uint32_t S[NL], x[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) S[l] = 0;
+        const size_t nblk = (rank - r + N - 1) / N;   // blocks containing residue r
+        for (size_t k = nblk; k-- > 0;) {
+            const size_t i = k * N + r;
+            st_elem<NL>(quo + i * NL, S);                 // quo[kN + r] = S_{k+1}
+            ld_elem<NL>(x, p + i * NL);
+            mod_add<NL>(S, S, x, F);
+            if (k > 0) {
+#pragma unroll
+                for (int l = 0; l < NL; l++) x[l] = 0;
+                st_elem<NL>(rem + i * NL, x);
+            }
+        }
+        st_elem<NL>(rem + r * NL, S);
+    }
+    // rank < N leaves nothing to fold; rem = p is handled by the caller
+}
+
+int quorem(const rs_field *f, uint32_t *quo, uint32_t *rem, const uint32_t *p, size_t rank, size_t N) {
+#define CALL(NL, QS)                                                                                   \
+    {                                                                                                  \
+        FieldParams<NL> F = make_params<NL>(f);                                                        \
+        quorem_kernel<NL><<<grid_for(N, 256), 256, 0, current_stream()>>>(quo, rem, p, F, rank, N);     \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// automorphism X -> X^idx (cyclotomic.go:49-82), gather form
+//   coefficient domain: out[j] = +-p[i] with j = i*idx mod 2N  <=>  i = j*idx^-1 mod 2N
+//   NTT domain: out[brv(i)] = p[brv(((2i+1)*idx mod 2N - 1)/2)]
+// ---------------------------------------------------------------------------
+template <int NL>
+__global__ void __launch_bounds__(256) aut_kernel(uint32_t *out, const uint32_t *p,
+                                                  const __grid_constant__ FieldParams<NL> F, int logN,
+                                                  unsigned long long idx, unsigned long long idx_inv, int is_ntt,
+                                                  size_t n_polys) {
+    const size_t N = (size_t)1 << logN;
+    const unsigned long long mask2 = 2 * N - 1;
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n_polys * N; g += (size_t)gridDim.x * blockDim.x) {
+        const size_t poly = g >> logN, j = g & (N - 1);
+        uint32_t x[NL];
+        if (!is_ntt) {
+            // source i with i*idx = j or j+N (mod 2N)
+            unsigned long long i = ((unsigned long long)j * idx_inv) & mask2;
+            bool neg = false;
+            if (i >= N) { i -= N; neg = true; }   // (i+N)*idx = j + N (idx odd)  =>  sign flips
+            ld_elem<NL>(x, p + (poly * N + i) * NL);
+            if (neg) { uint32_t y[NL]; mod_neg<NL>(y, x, F);
+#pragma unroll
+                for (int l = 0; l < NL; l++) x[l] = y[l]; }
+        } else {
+            const unsigned long long i = logN ? (__brevll((unsigned long long)j) >> (64 - logN)) : 0;   // out index j = brv(i)
+            unsigned long long s = (((2 * i + 1) * idx) & mask2);
+            s = (s - 1) >> 1;
+            const unsigned long long src = logN ? (__brevll(s) >> (64 - logN)) : 0;
+            ld_elem<NL>(x, p + (poly * N + src) * NL);
+        }
+        st_elem<NL>(out + g * NL, x);
+    }
+}
+
+int aut(const rs_field *f, uint32_t *out, const uint32_t *p, int logN, unsigned long long idx,
+        unsigned long long idx_inv, int is_ntt, size_t n_polys) {
+#define CALL(NL, QS)                                                                                        \
+    {                                                                                                       \
+        FieldParams<NL> F = make_params<NL>(f);                                                             \
+        aut_kernel<NL><<<grid_for(n_polys << logN, 256), 256, 0, current_stream()>>>(out, p, F, logN, idx,   \
+                                                                                     idx_inv, is_ntt, n_polys); \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// out[i] = v[N-1-i] * scale   (buckler/linear.go:38-41)
+template <int NL, int QS>
+__global__ void __launch_bounds__(256) reverse_scale_kernel(uint32_t *out, const uint32_t *v,
+                                                            const __grid_constant__ Scalar<NL> c,
+                                                            const __grid_constant__ FieldParams<NL> F, size_t N) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x[NL], z[NL];
+        ld_elem<NL>(x, v + (N - 1 - i) * NL);
+        mont_mul<NL, QS>(z, x, c.v, F);
+        st_elem<NL>(out + i * NL, z);
+    }
+}
+
+int reverse_scale(const rs_field *f, uint32_t *out, const uint32_t *v, const uint32_t *scale, size_t N) {
+#define CALL(NL, QS)                                                                                      \
+    {                                                                                                     \
+        FieldParams<NL> F = make_params<NL>(f);                                                           \
+        Scalar<NL> s;                                                                                     \
+        for (int i = 0; i < NL; i++) s.v[i] = scale[i];                                                   \
+        reverse_scale_kernel<NL, QS><<<grid_for(N, 256), 256, 0, current_stream()>>>(out, v, s, F, N);     \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Poly.Evaluate (poly.go:64-76): Horner is N sequential products on the CPU; here each
+// thread Horner-evaluates a contiguous chunk of CH coefficients and the partial values are
+// combined as  sum_t part_t * x^(t*CH)  by a second tiny kernel (exact field arithmetic, so
+// the result is the same field element).
+// ---------------------------------------------------------------------------
+template <int NL, int QS>
+__global__ void __launch_bounds__(128) horner_chunks_kernel(uint32_t *partial, const uint32_t *coeffs,
+                                                            const __grid_constant__ Scalar<NL> x,
+                                                            const __grid_constant__ FieldParams<NL> F, size_t n, int CH) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t n_chunks = (n + CH - 1) / CH;
+    if (t >= n_chunks) return;
+    const size_t lo = t * CH, hi = (lo + CH < n) ? lo + CH : n;
+    uint32_t acc[NL], c[NL], tmp[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) acc[l] = 0;
+    for (size_t i = hi; i-- > lo;) {
+        mont_mul<NL, QS>(tmp, acc, x.v, F);
+        ld_elem<NL>(c, coeffs + i * NL);
+        mod_add<NL>(acc, tmp, c, F);
+    }
+    st_elem<NL>(partial + t * NL, acc);
+}
+
+template <int NL, int QS>
+__global__ void horner_combine_kernel(uint32_t *result, const uint32_t *partial,
+                                      const __grid_constant__ Scalar<NL> xch,
+                                      const __grid_constant__ FieldParams<NL> F, size_t n_chunks) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t acc[NL], c[NL], tmp[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) acc[l] = 0;
+    for (size_t i = n_chunks; i-- > 0;) {
+        mont_mul<NL, QS>(tmp, acc, xch.v, F);
+        ld_elem<NL>(c, partial + i * NL);
+        mod_add<NL>(acc, tmp, c, F);
+    }
+    st_elem<NL>(result, acc);
+}
+
+int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uint32_t *coeffs, size_t n,
+           const uint32_t *x, const uint32_t *x_pow_ch, int CH) {
+    const size_t n_chunks = (n + CH - 1) / CH;
+#define CALL(NL, QS)                                                                                          \
+    {                                                                                                         \
+        FieldParams<NL> F = make_params<NL>(f);                                                               \
+        Scalar<NL> sx, sp;                                                                                    \
+        for (int i = 0; i < NL; i++) { sx.v[i] = x[i]; sp.v[i] = x_pow_ch[i]; }                               \
+        horner_chunks_kernel<NL, QS><<<(unsigned)((n_chunks + 127) / 128), 128, 0, current_stream()>>>(        \
+            d_partial, coeffs, sx, F, n, CH);                                                                 \
+        horner_combine_kernel<NL, QS><<<1, 32, 0, current_stream()>>>(d_result, d_partial, sp, F, n_chunks);   \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch(2);
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+}  // namespace rs
