@@ -28,7 +28,13 @@ def _newer(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=""):
+    """defines/tag: build an experimental variant (tools/) into libringo_b200<tag>.so."""
+    global OBJ, LIB
+    if tag:
+        OBJ = os.path.join(HERE, "build" + tag)
+        LIB = os.path.join(HERE, f"libringo_b200{tag}.so")
+    FLAGS.extend("-D" + d for d in defines)
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "ringo_cuda.h")]
@@ -56,4 +62,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tag = next((a[6:] for a in sys.argv[1:] if a.startswith("--tag=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, tag=tag))

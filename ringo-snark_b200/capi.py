@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libringo_b200.so")
+LIB_PATH = os.environ.get("RINGO_B200_LIB", os.path.join(HERE, "libringo_b200.so"))   # env: tuning variants only
 
 RS_OK = 0
 RS_TERM_MAX_W = 8

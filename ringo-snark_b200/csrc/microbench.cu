@@ -26,11 +26,70 @@ __global__ void __launch_bounds__(256) imad_kernel(unsigned long long *out, uint
     if (s == 0x1234567ull) out[0] = s;   // keep the chains alive
 }
 
+// carry-chained form used by the Montgomery product: mad.lo.cc / madc.hi.cc pairs that ptxas
+// fuses into IMAD.WIDE.U32.X (carry in and out through predicates)
+__global__ void __launch_bounds__(256) imad_chain_kernel(unsigned long long *out, uint32_t a, uint32_t b, int iters) {
+    uint32_t x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { x[k] = threadIdx.x + k; y[k] = threadIdx.x * 3 + k; }
+    const uint32_t a0 = a, a1 = a + 1, a2 = a + 2, a3 = a + 3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(x[0]) : "r"(a0), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(x[1]) : "r"(a0), "r"(b));
+            asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(x[2]) : "r"(a1), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(x[3]) : "r"(a1), "r"(b));
+            asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(x[4]) : "r"(a2), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(x[5]) : "r"(a2), "r"(b));
+            asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(x[6]) : "r"(a3), "r"(b));
+            asm volatile("madc.hi.u32 %0, %1, %2, %0;" : "+r"(x[7]) : "r"(a3), "r"(b));
+            asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(y[0]) : "r"(a0), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(y[1]) : "r"(a0), "r"(b));
+            asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(y[2]) : "r"(a1), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(y[3]) : "r"(a1), "r"(b));
+            asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(y[4]) : "r"(a2), "r"(b));
+            asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(y[5]) : "r"(a2), "r"(b));
+            asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(y[6]) : "r"(a3), "r"(b));
+            asm volatile("madc.hi.u32 %0, %1, %2, %0;" : "+r"(y[7]) : "r"(a3), "r"(b));
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += x[k] + y[k];
+    if (s == 0x1234567ull) out[0] = s;
+}
+
+// add-with-carry chains (IADD3.X), 8 limbs
+__global__ void __launch_bounds__(256) iadd_chain_kernel(unsigned long long *out, uint32_t a, int iters) {
+    uint32_t x[8], y[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { x[k] = threadIdx.x + k; y[k] = threadIdx.x * 3 + k; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(x[0]) : "r"(a));
+#pragma unroll
+            for (int k = 1; k < 7; k++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(x[k]) : "r"(a + k));
+            asm volatile("addc.u32 %0, %0, %1;" : "+r"(x[7]) : "r"(a));
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(y[0]) : "r"(a));
+#pragma unroll
+            for (int k = 1; k < 7; k++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(y[k]) : "r"(a + k));
+            asm volatile("addc.u32 %0, %0, %1;" : "+r"(y[7]) : "r"(a));
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += x[k] + y[k];
+    if (s == 0x1234567ull) out[0] = s;
+}
+
 }  // namespace rs
 
 extern "C" {
 #pragma GCC visibility push(default)
-// Returns sustained G IMAD/s: wide != 0 -> IMAD.WIDE.U32 (32x32+64), else 32-bit IMAD.
+// Returns sustained G op/s.  wide: 0 = 32-bit IMAD, 1 = IMAD.WIDE.U32 (32x32+64, no carry),
+// 2 = carry-chained IMAD.WIDE.U32.X (the Montgomery inner loop), 3 = IADD3.X carry chains.
 int rs_bench_imad_peak(int wide, double *gops) {
     using namespace rs;
     RS_REQUIRE(gops, RS_ERR_ARG, "rs_bench_imad_peak: null argument");
@@ -43,7 +102,9 @@ int rs_bench_imad_peak(int wide, double *gops) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
         RS_CUDA_CHECK(cudaEventRecord(e0, current_stream()));
-        if (wide) imad_kernel<true><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
+        if (wide == 1) imad_kernel<true><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
+        else if (wide == 2) imad_chain_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
+        else if (wide == 3) iadd_chain_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, iters);
         else imad_kernel<false><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
         count_launch();
         RS_CUDA_CHECK(cudaEventRecord(e1, current_stream()));
@@ -53,7 +114,8 @@ int rs_bench_imad_peak(int wide, double *gops) {
         if (rep > 0 && ms < best) best = ms;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
-    const double ops = (double)blocks * threads * (double)iters * 16 * 8;
+    // per inner iteration: 8 MADs (modes 0/1), 8 fused wide MADs (mode 2), 16 adds (mode 3)
+    const double ops = (double)blocks * threads * (double)iters * 16 * (wide == 3 ? 16 : 8);
     *gops = ops / (best * 1e-3) / 1e9;
     return RS_OK;
 }

@@ -222,8 +222,8 @@ __device__ __forceinline__ void move_tile(uint32_t *sm, const uint32_t *gin, uin
     }
 }
 
-template <int NL, int QS, int R, int THREADS, bool INV, bool SCALE>
-__global__ void __launch_bounds__(THREADS, (NL <= 8 ? 2 : 1)) ntt_pass_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ in,
+template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE>
+__global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ in,
                                                            const uint32_t *__restrict__ tw,
                                                            const __grid_constant__ NttConsts<NL> C,
                                                            const __grid_constant__ PassGeom G) {

@@ -5,19 +5,27 @@
 
 namespace rs {
 
+#ifndef RS_NTT_R_SMALL
+#define RS_NTT_R_SMALL 3      // radix-2^R rounds for <= 8 limbs (tuning knob)
+#endif
+#ifndef RS_NTT_MINB_SMALL
+#define RS_NTT_MINB_SMALL 2   // resident CTAs per SM the register allocation is capped for
+#endif
+
 template <int NL> struct NttTuning {
     // 2^R elements per thread between shared-memory exchanges
-    static constexpr int R = (NL <= 8) ? 3 : (NL <= 14 ? 2 : 1);
+    static constexpr int R = (NL <= 8) ? RS_NTT_R_SMALL : (NL <= 14 ? 2 : 1);
     static constexpr int THREADS = 256;
     static constexpr int TS = THREADS << R;
     static constexpr int LOG_TS = 8 + R;
+    static constexpr int MINB = (NL <= 8) ? RS_NTT_MINB_SMALL : 1;
 };
 
 template <int NL, int QS, bool INV, bool SCALE>
 int launch_pass(const rs_ntt *t, uint32_t *out, const uint32_t *in, const NttConsts<NL> &C, const PassGeom &G,
                 unsigned long long tiles) {
     using T = NttTuning<NL>;
-    auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, INV, SCALE>;
+    auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, T::MINB, INV, SCALE>;
     constexpr int smem = SmemLayout<NL, T::TS>::BYTES;
     static bool configured = false;
     if (!configured) {
