@@ -8,6 +8,6 @@ so the parity tests read like the reference's own.  There is no CPU fallback: im
 works anywhere, but every compute call needs libringo_b200.so and a B200.
 """
 from . import capi            # noqa: F401
-from .capi import RingoError, lib, load  # noqa: F401
+from .capi import RingoError, lib, load, check  # noqa: F401
 from .bigpoly import (Field, Batch, Poly, CyclicTransformer, CyclotomicTransformer,  # noqa: F401
                       CyclicEvaluator, CyclotomicEvaluator)
