@@ -1,0 +1,104 @@
+/*
+ * ringo_jindo.h -- C ABI for the Jindo polynomial-commitment hot path (libringo_b200.so).
+ *
+ * Replaces the inner loops of jindo.Prover.Commit / Evaluate (jindo/prover.go:45-324), the
+ * encoder (jindo/encoder.go:113-201), the RNS reconstruction / cut-off pipeline
+ * (jindo/rns.go:76-114, prover.go:164-176, :190-200) and the lattigo ring.Ring calls they make
+ * (NTT/INTT, MForm/IMForm, MulCoeffsMontgomeryThenAdd, Add, MulScalarThenSub).
+ *
+ * Everything that is a *convention* of the host library stays an INPUT, so this library embeds
+ * no assumption about lattigo or Go's math package:
+ *   - RNS primes and their 2d-th primitive roots psi (lattigo ring.SubRing),
+ *   - the commit key polynomials (jindo.NewCommitKey, entities.go:21-61),
+ *   - the encoder's float64 constants deltaInv (encoder.go:50-67),
+ *   - the TwinCDT tables (math/csprng/gaussian_twin_cdt.go:13-35) and all randomness:
+ *     raw uniform uint64 draws for TwinCDT rows, already-sampled integers for the rows the
+ *     reference samples with data-dependent rejection loops (COSAC / rounded Gaussian),
+ *     and the MustSetRandom field elements of the first/last/mask rows.
+ * The Go shim produces them with the reference's own csprng; tests produce them with the oracle.
+ *
+ * Ring polynomials use lattigo's layout: Coeffs[limb][coeff] uint64, limb-major.
+ */
+#ifndef RINGO_JINDO_H
+#define RINGO_JINDO_H
+
+#include "ringo_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_JINDO_MAX_LIMBS 4
+#define RS_JINDO_MAX_EXP 64
+
+typedef struct rs_jindo rs_jindo;
+typedef struct rs_opening rs_opening;
+
+/* jindo.Parameters (jindo/params.go:53-124) -- the fields the prover's arithmetic needs */
+typedef struct rs_jindo_params {
+    int32_t d;                 /* ring degree (256) */
+    int32_t slots;             /* params.slots */
+    int32_t exp;               /* params.ecd.exp */
+    uint64_t base;             /* params.ecd.base */
+    int32_t rows, cols;
+    int32_t in_msis, mlwe, out_msis;
+    int32_t log_in_cut, log_out_cut;
+    int32_t n_q, n_qout;                       /* RNS limbs of ringQ / ringQOut */
+    uint64_t q[RS_JINDO_MAX_LIMBS];            /* ringQ.SubRings[l].Modulus */
+    uint64_t qout[RS_JINDO_MAX_LIMBS];
+    uint64_t psi_q[RS_JINDO_MAX_LIMBS];        /* primitive 2d-th root used by ringQ's NTT (canonical) */
+    uint64_t psi_qout[RS_JINDO_MAX_LIMBS];
+    double delta_inv[RS_JINDO_MAX_EXP];        /* Encoder.deltaInv (encoder.go:50-67) */
+    /* TwinCDT sampler of the encoder (sigma = ecdStdDev): 128 tables of cdt_len entries */
+    int32_t cdt_len;
+    int64_t cdt_tail_lo;
+    double cdt_sigma;
+} rs_jindo_params;
+
+/* NewProver (jindo/prover.go:28-40): uploads the commit key (ck.In [in_msis][rows], ck.MLWE
+ * [in_msis][mlwe] over ringQ; ck.Out [out_msis][(cols+1)*in_msis] over ringQOut) and the
+ * 128 x cdt_len TwinCDT tables. */
+int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in, const uint64_t *ck_mlwe,
+                    const uint64_t *ck_out, const uint64_t *cdt_tables, rs_jindo **out);
+void rs_jindo_destroy(rs_jindo *j);
+
+/* Randomness / noise inputs of one Commit, in the reference's consumption order. */
+typedef struct rs_jindo_tape {
+    const uint64_t *first_row;   /* cols*slots field elements (Montgomery)       prover.go:65-86 */
+    const uint64_t *last_row;    /* cols*slots field elements */
+    const uint64_t *mask_rows;   /* n_mask_rows*slots field elements, encode order prover.go:93-115 */
+    size_t n_mask_rows;
+    const uint64_t *twin_u;      /* one uniform draw per TwinCDT sample, call order  encoder.go:168-169 */
+    size_t n_twin_u;
+    const int64_t *cosac_g;      /* sampled g for the COSAC rows: data columns' row 0 (col order), then
+                                    the mask column's rows in encode order; d values each */
+    size_t n_cosac_polys;
+    const int64_t *mlwe;         /* (cols+1)*(in_msis+mlwe)*d noise samples          prover.go:130-139 */
+} rs_jindo_tape;
+
+/* Prover.Commit (jindo/prover.go:45-62).  v: device batch holding the committed vector
+ * (poly v_poly, first len coefficients, len <= rank).  commitment_out: out_msis polys over
+ * ringQOut (host, n_qout*d words each) -- Commitment.Value in NTT+Montgomery form. */
+int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
+                    rs_opening **open, uint64_t *commitment_out);
+void rs_opening_free(rs_opening *o);
+/* accessors (tests / the Go shim's Opening view): kind 0 = Encode[col][row] (ringQ),
+ * 1 = MLWE[col][idx] (ringQ), 2 = InCommit[idx] (ringQOut, col ignored) */
+int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, uint64_t *poly_out);
+
+/* Prover.Evaluate (jindo/prover.go:205-324), split around the host transcript:
+ *   phase 1: Partial[i] = sum_j left[j] (.) Encode[i][j]  for i <= cols  (prover.go:281-289)
+ *            left: rows polys over ringQ (encoded leftVec, NTT+Montgomery form, host)
+ *            partial_out: (cols+1) polys (host); index cols is PartialMask
+ *   phase 2: responses  Encode[i] = Enc[cols][i] + sum_j chal[j] (.) Enc[j][i]   (prover.go:304-316)
+ *            chals: cols polys over ringQ (host); enc_out: rows polys, mlwe_out: mlwe+in_msis polys */
+int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out);
+int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, uint64_t *enc_out, uint64_t *mlwe_out);
+/* batch > 1 (prover.go:251-265): acc += open (.) challenge, over every polynomial of the opening */
+int rs_opening_alloc_zero(rs_jindo *j, rs_opening **out);
+int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RINGO_JINDO_H */

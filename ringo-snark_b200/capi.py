@@ -25,7 +25,30 @@ class Term(ctypes.Structure):
                 ("n_w", ctypes.c_int32), ("w", ctypes.c_int32 * RS_TERM_MAX_W)]
 
 
-# name -> (restype, argtypes); mirrors include/ringo_cuda.h one to one
+RS_JINDO_MAX_LIMBS = 4
+RS_JINDO_MAX_EXP = 64
+
+
+class JindoParams(ctypes.Structure):
+    """rs_jindo_params (include/ringo_jindo.h)"""
+    _fields_ = [("d", ctypes.c_int32), ("slots", ctypes.c_int32), ("exp", ctypes.c_int32), ("base", ctypes.c_uint64),
+                ("rows", ctypes.c_int32), ("cols", ctypes.c_int32),
+                ("in_msis", ctypes.c_int32), ("mlwe", ctypes.c_int32), ("out_msis", ctypes.c_int32),
+                ("log_in_cut", ctypes.c_int32), ("log_out_cut", ctypes.c_int32),
+                ("n_q", ctypes.c_int32), ("n_qout", ctypes.c_int32),
+                ("q", ctypes.c_uint64 * RS_JINDO_MAX_LIMBS), ("qout", ctypes.c_uint64 * RS_JINDO_MAX_LIMBS),
+                ("psi_q", ctypes.c_uint64 * RS_JINDO_MAX_LIMBS), ("psi_qout", ctypes.c_uint64 * RS_JINDO_MAX_LIMBS),
+                ("delta_inv", ctypes.c_double * RS_JINDO_MAX_EXP),
+                ("cdt_len", ctypes.c_int32), ("cdt_tail_lo", ctypes.c_int64), ("cdt_sigma", ctypes.c_double)]
+
+
+class JindoTape(ctypes.Structure):
+    """rs_jindo_tape (include/ringo_jindo.h)"""
+    _fields_ = [("first_row", c_vp), ("last_row", c_vp), ("mask_rows", c_vp), ("n_mask_rows", c_size),
+                ("twin_u", c_vp), ("n_twin_u", c_size), ("cosac_g", c_vp), ("n_cosac_polys", c_size), ("mlwe", c_vp)]
+
+
+# name -> (restype, argtypes); mirrors include/ringo_cuda.h and include/ringo_jindo.h one to one
 _SIGS = {
     "rs_init": (ctypes.c_int, [ctypes.c_int]),
     "rs_set_stream": (ctypes.c_int, [c_vp]),
@@ -73,6 +96,16 @@ _SIGS = {
     "rs_aut": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_size, ctypes.c_long, ctypes.c_int]),
     "rs_reverse_scale": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p]),
     "rs_poly_evaluate": (ctypes.c_int, [c_vp, c_size, c_size, c_u64p, c_u64p]),
+    # ringo_jindo.h
+    "rs_jindo_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "rs_jindo_destroy": (None, [c_vp]),
+    "rs_jindo_commit": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
+    "rs_opening_free": (None, [c_vp]),
+    "rs_opening_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_size, c_size, c_vp]),
+    "rs_jindo_partial": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "rs_jindo_respond": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rs_opening_alloc_zero": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "rs_opening_mul_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -1,0 +1,884 @@
+// jindo.cu -- Jindo commitment hot path (include/ringo_jindo.h).
+//
+// Reference: jindo/prover.go:45-324 (Commit, commitColTo, outerCommitTo, Evaluate),
+// jindo/encoder.go:113-201 (baseEncodeTo, randEncodeTo), jindo/rns.go:76-114, jindo/utils.go:12-60,
+// and the lattigo ring.Ring calls they make.  Ring polynomials are Coeffs[limb][256] uint64.
+//
+// Kernels
+//   encode_kernel   one CTA per ring polynomial: fromMont + base-b digits -> float64 centre ->
+//                   TwinCDT sample (or supplied noise) -> MForm(digits) + (X^slots - b) g -> 256-point
+//                   NTT per RNS limb -> Opening.  One HBM round trip per polynomial.
+//   matvec_kernel   NTT-domain ring matrix-vector products (inner/outer commit, Partial, responses):
+//                   per (limb, coefficient) slot, 128-bit lazy accumulation of 64x64 products, one
+//                   Montgomery reduction per output.
+//   cut_kernel      IMForm/INTT -> CRT to a centred multi-word integer -> arithmetic >> cut ->
+//                   residues mod the outer primes -> MForm/NTT  (prover.go:164-176, :190-200).
+#include <string.h>
+
+#include "../../include/ringo_jindo.h"
+#include "common.cuh"
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+#define JD 256            // ring degree handled by these kernels
+#define JMAXL RS_JINDO_MAX_LIMBS
+#define JW 5              // 64-bit words of the centred integers (Q <= 240 bits, + products)
+
+struct RingDev {
+    int n;
+    u64 q[JMAXL];
+    u64 qinvneg[JMAXL];     // -q^-1 mod 2^64
+    u64 r2[JMAXL];          // 2^128 mod q  (MForm multiplier)
+    u64 ninv[JMAXL];        // d^-1 mod q, plain (INTT scale that also leaves Montgomery form)
+    const u64 *roots;       // [limb][d]  psi^brv(j) * 2^64 mod q   (forward twiddles)
+    const u64 *roots_inv;   // [limb][d]  psi^-brv(j) * 2^64 mod q
+};
+
+struct CrtDev {             // RNSReconstructor constants of the *source* ring (rns.go:33-55)
+    u64 Q[JW];              // product of the primes
+    u64 Qhalf[JW];          // Q >> 1
+    u64 Qdiv[JMAXL][JW];    // Q / q_l
+    u64 inv_mont[JMAXL];    // ((Q/q_l)^-1 mod q_l) * 2^64 mod q_l
+};
+
+struct rs_jindo {
+    rs_field *f;
+    rs_jindo_params p;
+    RingDev rq, rqo;
+    CrtDev crt_q, crt_qo;
+    u64 *d_roots;           // all twiddle tables
+    u64 *d_ck_in, *d_ck_mlwe, *d_ck_out;
+    u64 *d_cdt;
+    u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
+};
+
+struct rs_opening {
+    rs_jindo *j;
+    u64 *d_encode;          // (cols+1)*rows polys over ringQ
+    u64 *d_mlwe;            // (cols+1)*(mlwe+in_msis) polys over ringQ
+    u64 *d_incommit;        // (cols+1)*in_msis polys over ringQOut
+};
+
+namespace rs {
+
+// ---------------------------------------------------------------------------------------------
+// word-size Montgomery arithmetic (lattigo MRed semantics: x*y*2^-64 mod q, canonical)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ u64 hmulhi(u64 a, u64 b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b);
+#else
+    return (u64)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+__host__ __device__ __forceinline__ u64 redc128(u64 hi, u64 lo, u64 q, u64 qinvneg) {
+    // (hi:lo) < q * 2^64
+    const u64 m = lo * qinvneg;
+    u64 r = hi + hmulhi(m, q) + (lo != 0);
+    return r >= q ? r - q : r;
+}
+__host__ __device__ __forceinline__ u64 mont64(u64 a, u64 b, u64 q, u64 qinvneg) {
+    return redc128(hmulhi(a, b), a * b, q, qinvneg);
+}
+__host__ __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { u64 s = a + b; return s >= q ? s - q : s; }
+__host__ __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+
+// signed 64-bit value -> canonical residue (setCoeffSigned utils.go:49-60 followed by MForm's reduction)
+__device__ __forceinline__ u64 signed_res(i64 c, u64 q) {
+    if (c >= 0) { u64 u = (u64)c; return u >= q ? u % q : u; }
+    u64 m = (u64)(-c);
+    if (m >= q) m %= q;
+    return m ? q - m : 0;
+}
+
+// 256-point negacyclic NTT of one limb in shared memory, Montgomery domain, 128 threads (t in [0,128)).
+// [lattigo] Cooley-Tukey, out[i] = a(psi^(2 brv(i)+1)).
+__device__ __forceinline__ void ntt256(u64 *a, const u64 *__restrict__ roots, u64 q, u64 qi, int t, int bar, int nthreads) {
+    int tt = JD;
+#pragma unroll 1
+    for (int m = 1; m < JD; m <<= 1) {
+        tt >>= 1;
+        const int i = t / tt, j = 2 * i * tt + (t % tt);
+        const u64 w = __ldg(roots + m + i);
+        const u64 u = a[j], v = mont64(a[j + tt], w, q, qi);
+        a[j] = addmod(u, v, q);
+        a[j + tt] = submod(u, v, q);
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads));
+    }
+}
+// [lattigo] Gentleman-Sande inverse; `scale` = d^-1 (plain) also strips the Montgomery factor,
+// or d^-1 * 2^64 (Montgomery) to stay in Montgomery form.
+__device__ __forceinline__ void intt256(u64 *a, const u64 *__restrict__ roots_inv, u64 q, u64 qi, u64 scale, int t, int bar, int nthreads) {
+    int tt = 1;
+#pragma unroll 1
+    for (int m = JD; m > 1; m >>= 1) {
+        const int h = m >> 1;
+        const int i = t / tt, j = 2 * i * tt + (t % tt);
+        const u64 w = __ldg(roots_inv + h + i);
+        const u64 u = a[j], v = a[j + tt];
+        a[j] = addmod(u, v, q);
+        a[j + tt] = mont64(submod(u, v, q), w, q, qi);
+        tt <<= 1;
+        asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads));
+    }
+    a[t] = mont64(a[t], scale, q, qi);
+    a[t + 128] = mont64(a[t + 128], scale, q, qi);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads));
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode kernel
+// ---------------------------------------------------------------------------------------------
+struct EncDesc {
+    int src_kind;        // 0: elements from the committed vector, 1: from the aux element buffer, 2: no digits (noise poly)
+    int cnt;             // number of field elements (<= slots)
+    i64 src_off;         // element offset
+    int noise_kind;      // 0: TwinCDT from uniform tape, 1: supplied integers
+    i64 noise_off;       // offset (in samples) into twin_u / given noise
+    i64 out_poly;        // destination polynomial index
+};
+
+struct EncConsts {
+    int slots, exp, cdt_len;
+    u64 base, base_magic;       // base_magic = floor(2^64 / base) + 1  (base is not a power of two)
+    i64 tail_lo;
+    double sigma;
+    double delta_inv[RS_JINDO_MAX_EXP];
+    u64 base_mont[JMAXL];
+};
+
+template <int NL>
+__global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, const EncDesc *__restrict__ descs,
+                                                     const uint32_t *__restrict__ vec, const uint32_t *__restrict__ aux,
+                                                     const u64 *__restrict__ twin_u, const i64 *__restrict__ given,
+                                                     const u64 *__restrict__ cdt, const __grid_constant__ RingDev R,
+                                                     const __grid_constant__ EncConsts E,
+                                                     const __grid_constant__ FieldParams<NL> F) {
+    __shared__ u64 s_digit[JD];
+    __shared__ i64 s_g[JD];
+    __shared__ u64 s_poly[JMAXL][JD];
+    const EncDesc D = descs[blockIdx.x];
+    const int c = threadIdx.x;
+
+    // ---- baseEncodeTo (encoder.go:120-146): canonical limbs -> exp base-b digits at stride `slots`
+    s_digit[c] = 0;
+    __syncthreads();
+    if (D.src_kind != 2 && c < D.cnt) {
+        const uint32_t *src = (D.src_kind == 0 ? vec : aux) + (size_t)(D.src_off + c) * NL;
+        uint32_t x[NL], one[NL], y[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) { x[l] = src[l]; one[l] = 0; }
+        one[0] = 1;
+        mont_mul<NL, 0>(y, x, one, F);                     // Slice(): fromMont (element.go:1769-1773)
+        const u64 b = E.base;
+        for (int j = 0; j < E.exp - 1; j++) {
+            u64 r = 0;                                     // divMod64 (utils.go:12-18) on 32-bit limbs
+#pragma unroll
+            for (int l = NL - 1; l >= 0; l--) {
+                const u64 cur = (r << 32) | y[l];
+                u64 qd = hmulhi(cur, E.base_magic);        // floor(cur / b) or one more (cur < b * 2^32)
+                u64 rem = cur - qd * b;
+                if ((i64)rem < 0) { rem += b; qd--; }
+                y[l] = (uint32_t)qd;
+                r = rem;
+            }
+            s_digit[j * E.slots + c] = r;
+        }
+        s_digit[(E.exp - 1) * E.slots + c] = ((u64)y[1] << 32) | y[0];
+    }
+    __syncthreads();
+
+    // ---- Gaussian vector g
+    i64 g;
+    if (D.noise_kind == 1) {
+        g = given[D.noise_off + c];
+    } else {
+        // float64 centre (encoder.go:152-164), unfused multiply-add in the reference's order
+        double fp = 0.0;
+        for (int i = 0; i < E.exp; i++) {
+            const double di = E.delta_inv[i];
+            if (di == 0.0) continue;
+            const int w = (i + 1) * E.slots;               // N - d
+            if (c >= JD - w) fp = __dadd_rn(fp, __dmul_rn(di, (double)s_digit[c - (JD - w)]));
+            else fp = __dsub_rn(fp, __dmul_rn(di, (double)s_digit[c + w]));
+        }
+        // TwinCDT (gaussian_twin_cdt.go:77-111)
+        const double center = -fp;
+        const double cfloor = floor(center);
+        const double cfrac = __dsub_rn(center, cfloor);
+        const double sc = __dmul_rn(128.0, cfrac);
+        const int c0 = (int)(((i64)floor(sc)) % 128), c1 = (int)(((i64)ceil(sc)) % 128);
+        const u64 u = twin_u[D.noise_off + c];
+        int v[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const u64 *tab = cdt + (size_t)(k ? c1 : c0) * E.cdt_len;
+            int lo = 0, hi = E.cdt_len;
+            while (lo < hi) {                              // slices.BinarySearch: leftmost index with tab >= u
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(tab + mid) < u) lo = mid + 1; else hi = mid;
+            }
+            if (lo < E.cdt_len && __ldg(tab + lo) == u) lo -= 1;
+            v[k] = lo;
+        }
+        int pick = v[0];
+        if (v[0] != v[1]) {
+            double cdf = 0.0;
+            const double norm = __dmul_rn(sqrt(6.283185307179586), E.sigma);
+            const double den = __dmul_rn(__dmul_rn(2.0, E.sigma), E.sigma);
+            for (i64 x = E.tail_lo; x <= (i64)v[0]; x++) {
+                const double t = __dsub_rn((double)x, cfrac);
+                cdf = __dadd_rn(cdf, __ddiv_rn(exp(__ddiv_rn(__dmul_rn(-t, t), den)), norm));
+            }
+            const double p = __dmul_rn(__ull2double_rn(u), 5.421010862427522e-20);   // u / 2^64
+            pick = (p < cdf) ? v[0] : v[1];
+        }
+        g = (i64)pick + (i64)cfloor + E.tail_lo;
+    }
+    s_g[c] = g;
+    __syncthreads();
+
+    // ---- MForm(digits) + MForm(X^slots g - base g)  (encoder.go:166-199), per RNS limb
+    for (int l = 0; l < R.n; l++) {
+        const u64 q = R.q[l], qi = R.qinvneg[l];
+        u64 val;
+        if (D.src_kind == 2) {
+            val = signed_res(g, q);                        // noise polynomial: setCoeffSigned (prover.go:130-139)
+        } else {
+            const u64 gm = signed_res(g, q);
+            const u64 gs = (c >= E.slots) ? signed_res(s_g[c - E.slots], q)
+                                          : submod(0, signed_res(s_g[c + JD - E.slots], q), q);
+            const u64 bg = mont64(E.base_mont[l], gm, q, qi);        // base * g mod q
+            val = submod(addmod(s_digit[c] >= q ? s_digit[c] % q : s_digit[c], gs, q), bg, q);
+        }
+        s_poly[l][c] = mont64(val, R.r2[l], q, qi);        // MForm
+    }
+    __syncthreads();
+    // ---- NTT: two limbs at a time (threads 0-127 / 128-255)
+    for (int l0 = 0; l0 < R.n; l0 += 2) {
+        const int l = l0 + (c >> 7);
+        if (l < R.n) ntt256(s_poly[l], R.roots + (size_t)l * JD, R.q[l], R.qinvneg[l], c & 127, 1 + (c >> 7), 128);
+    }
+    __syncthreads();
+    u64 *dst = out + (size_t)D.out_poly * R.n * JD;
+    for (int l = 0; l < R.n; l++) dst[(size_t)l * JD + c] = s_poly[l][c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// matvec kernel:  out[cc][o] (+)= REDC( sum_k key[o][k] * x[cc][k] )  per slot
+//   key poly index  = o * key_os + k * key_ks      x poly index = cc * x_cs + k * x_ks
+//   out poly index  = cc * out_cs + o * out_os     addend poly index = cc * add_cs + o * add_os
+// ---------------------------------------------------------------------------------------------
+struct MatvecGeom {
+    int n_limbs, O, C, K;
+    i64 key_os, key_ks, x_cs, x_ks, out_cs, out_os, add_cs, add_os;
+    int accumulate;      // add the reduced sum to the existing out value
+    int has_addend;
+    int fold_every;      // reduce the high word mod q every this many terms (0 = never)
+    u64 q[JMAXL], qinvneg[JMAXL];
+};
+
+template <int OT, int CT>
+__global__ void __launch_bounds__(128) matvec_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
+                                                     const u64 *__restrict__ x, const u64 *__restrict__ addend,
+                                                     const __grid_constant__ MatvecGeom G) {
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;          // limb * 256 + coeff
+    const int n_slots = G.n_limbs * JD;
+    if (slot >= n_slots) return;
+    const int o_tiles = (G.O + OT - 1) / OT;
+    const int o0 = (blockIdx.y % o_tiles) * OT, c0 = (blockIdx.y / o_tiles) * CT;
+    const int limb = slot / JD;
+    const u64 q = G.q[limb], qi = G.qinvneg[limb];
+    const size_t pw = (size_t)n_slots;                                // words per polynomial
+    u64 lo[OT][CT], hi[OT][CT];
+#pragma unroll
+    for (int a = 0; a < OT; a++)
+#pragma unroll
+        for (int b = 0; b < CT; b++) { lo[a][b] = 0; hi[a][b] = 0; }
+    int since = 0;
+    for (int k = 0; k < G.K; k++) {
+        u64 kv[OT], xv[CT];
+#pragma unroll
+        for (int a = 0; a < OT; a++) kv[a] = (o0 + a < G.O) ? __ldg(key + ((o0 + a) * G.key_os + k * G.key_ks) * pw + slot) : 0;
+#pragma unroll
+        for (int b = 0; b < CT; b++) xv[b] = (c0 + b < G.C) ? __ldg(x + ((c0 + b) * G.x_cs + k * G.x_ks) * pw + slot) : 0;
+#pragma unroll
+        for (int a = 0; a < OT; a++)
+#pragma unroll
+            for (int b = 0; b < CT; b++) {
+                const u64 pl = kv[a] * xv[b], ph = __umul64hi(kv[a], xv[b]);
+                const u64 nl = lo[a][b] + pl;
+                hi[a][b] += ph + (nl < pl);
+                lo[a][b] = nl;
+            }
+        if (G.fold_every && ++since == G.fold_every) {
+            since = 0;
+#pragma unroll
+            for (int a = 0; a < OT; a++)
+#pragma unroll
+                for (int b = 0; b < CT; b++) hi[a][b] %= q;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < OT; a++)
+#pragma unroll
+        for (int b = 0; b < CT; b++) {
+            if (o0 + a >= G.O || c0 + b >= G.C) continue;
+            u64 h = hi[a][b];
+            if (h >= q) h %= q;
+            u64 r = redc128(h, lo[a][b], q, qi);           // MulCoeffsMontgomeryThenAdd: sum a*b*2^-64 mod q
+            u64 *dst = out + ((c0 + b) * G.out_cs + (o0 + a) * G.out_os) * pw + slot;
+            if (G.accumulate) r = addmod(r, *dst, q);
+            if (G.has_addend) r = addmod(r, __ldg(addend + ((c0 + b) * G.add_cs + (o0 + a) * G.add_os) * pw + slot), q);
+            *dst = r;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// cut-off pipeline (prover.go:164-176, :190-200; rns.go:76-114)
+// ---------------------------------------------------------------------------------------------
+struct CutConsts {
+    int log_cut;
+    RingDev in, outr;
+    CrtDev crt;
+};
+
+__device__ __forceinline__ bool mw_geq(const u64 *a, const u64 *b) {
+    for (int i = JW - 1; i >= 0; i--) { if (a[i] > b[i]) return true; if (a[i] < b[i]) return false; }
+    return true;
+}
+__device__ __forceinline__ void mw_sub(u64 *a, const u64 *b) {
+    u64 br = 0;
+    for (int i = 0; i < JW; i++) {
+        const u64 d = a[i] - b[i], d2 = d - br;
+        br = (a[i] < b[i]) | (d < br);
+        a[i] = d2;
+    }
+}
+
+__global__ void __launch_bounds__(256) cut_kernel(u64 *__restrict__ out, const u64 *__restrict__ in,
+                                                  const __grid_constant__ CutConsts K) {
+    __shared__ u64 s[JMAXL][JD];
+    const int c = threadIdx.x;
+    const RingDev &A = K.in, &B = K.outr;
+    const u64 *src = in + (size_t)blockIdx.x * A.n * JD;
+    for (int l = 0; l < A.n; l++) s[l][c] = src[(size_t)l * JD + c];
+    __syncthreads();
+    // IMForm + INTT (plain canonical coefficients)
+    for (int l0 = 0; l0 < A.n; l0 += 2) {
+        const int l = l0 + (c >> 7);
+        if (l < A.n) intt256(s[l], A.roots_inv + (size_t)l * JD, A.q[l], A.qinvneg[l], A.ninv[l], c & 127, 1 + (c >> 7), 128);
+    }
+    __syncthreads();
+    // reconstructTo (rns.go:76-105) -> centred integer V (two's complement, JW words)
+    u64 V[JW];
+    bool neg = false;
+    {
+        bool small = true;
+        const u64 x0 = s[0][c];
+        const i64 bal0 = (x0 > (A.q[0] >> 1)) ? (i64)x0 - (i64)A.q[0] : (i64)x0;       // toBalanced rns.go:68-73
+        for (int l = 1; l < A.n; l++) {
+            const u64 xl = s[l][c];
+            const i64 bl = (xl > (A.q[l] >> 1)) ? (i64)xl - (i64)A.q[l] : (i64)xl;
+            if (bl != bal0) { small = false; break; }
+        }
+        if (small) {
+            neg = bal0 < 0;
+            V[0] = (u64)bal0;
+            for (int i = 1; i < JW; i++) V[i] = neg ? ~0ull : 0ull;
+        } else {
+            // acc = sum_l c_l * gad_l mod Q, computed as sum_l y_l * (Q/q_l) with y_l = c_l (Q/q_l)^-1 mod q_l
+            for (int i = 0; i < JW; i++) V[i] = 0;
+            for (int l = 0; l < A.n; l++) {
+                const u64 y = mont64(s[l][c], K.crt.inv_mont[l], A.q[l], A.qinvneg[l]);
+                u64 carry = 0;
+                for (int i = 0; i < JW; i++) {
+                    const u64 pl = y * K.crt.Qdiv[l][i], ph = __umul64hi(y, K.crt.Qdiv[l][i]);
+                    u64 t = V[i] + pl;
+                    u64 cy = t < pl;
+                    const u64 t2 = t + carry;
+                    cy += t2 < t;
+                    V[i] = t2;
+                    carry = ph + cy;
+                }
+            }
+            for (int it = 0; it < JMAXL && mw_geq(V, K.crt.Q); it++) mw_sub(V, K.crt.Q);
+            if (mw_geq(V, K.crt.Qhalf)) { mw_sub(V, K.crt.Q); neg = true; }             // acc >= Q>>1 -> acc - Q
+        }
+    }
+    // Rsh(log_cut): arithmetic shift (floor for negatives, like big.Int.Rsh)
+    {
+        const int ws = K.log_cut / 64, bs = K.log_cut % 64;
+        const u64 fill = neg ? ~0ull : 0ull;
+        u64 Wv[JW];
+        for (int i = 0; i < JW; i++) {
+            const u64 a = (i + ws < JW) ? V[i + ws] : fill;
+            const u64 b = (i + ws + 1 < JW) ? V[i + ws + 1] : fill;
+            Wv[i] = bs ? ((a >> bs) | (b << (64 - bs))) : a;
+        }
+        for (int i = 0; i < JW; i++) V[i] = Wv[i];
+    }
+    // setBigCoeffTo (rns.go:108-114): Euclidean residue mod each outer prime
+    {
+        u64 M[JW];                                                                      // |V|
+        if (neg) {
+            u64 cy = 1;
+            for (int i = 0; i < JW; i++) { const u64 t = ~V[i] + cy; cy = (cy && t == 0); M[i] = t; }
+        } else {
+            for (int i = 0; i < JW; i++) M[i] = V[i];
+        }
+        __syncthreads();
+        for (int l = 0; l < B.n; l++) {
+            const u64 q = B.q[l];
+            u64 r = 0;
+            // Horner over 64-bit words: r <- r * 2^64 + M[i] (mod q); r * 2^64 = mont64(r, 2^128 mod q)
+            for (int i = JW - 1; i >= 0; i--) r = addmod(mont64(r, B.r2[l], q, B.qinvneg[l]), M[i] % q, q);
+            if (neg && r) r = q - r;
+            s[l][c] = mont64(r, B.r2[l], q, B.qinvneg[l]);                              // MForm
+        }
+    }
+    __syncthreads();
+    for (int l0 = 0; l0 < B.n; l0 += 2) {
+        const int l = l0 + (c >> 7);
+        if (l < B.n) ntt256(s[l], B.roots + (size_t)l * JD, B.q[l], B.qinvneg[l], c & 127, 1 + (c >> 7), 128);
+    }
+    __syncthreads();
+    u64 *dst = out + (size_t)blockIdx.x * B.n * JD;
+    for (int l = 0; l < B.n; l++) dst[(size_t)l * JD + c] = s[l][c];
+}
+
+// acc[p] += o[p] (.) chal   for n_polys polynomials (Evaluate batch combine, prover.go:251-265)
+__global__ void __launch_bounds__(256) muladd_bcast_kernel(u64 *__restrict__ acc, const u64 *__restrict__ o,
+                                                           const u64 *__restrict__ chal, size_t n_polys, int n_limbs,
+                                                           const __grid_constant__ MatvecGeom G) {
+    const size_t pw = (size_t)n_limbs * JD;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_polys * pw; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t slot = i % pw;
+        const int limb = (int)(slot / JD);
+        const u64 q = G.q[limb];
+        acc[i] = addmod(acc[i], mont64(o[i], __ldg(chal + slot), q, G.qinvneg[limb]), q);
+    }
+}
+
+}  // namespace rs
+
+// =============================================================================================
+// host side
+// =============================================================================================
+using namespace rs;
+typedef unsigned __int128 u128;
+
+static u64 h_mulmod(u64 a, u64 b, u64 q) { return (u64)(((u128)a * b) % q); }
+static u64 h_powmod(u64 a, u64 e, u64 q) {
+    u64 r = 1 % q;
+    a %= q;
+    while (e) { if (e & 1) r = h_mulmod(r, a, q); a = h_mulmod(a, a, q); e >>= 1; }
+    return r;
+}
+static u64 h_brv(u64 i, int bits) { u64 r = 0; for (int k = 0; k < bits; k++) { r = (r << 1) | (i & 1); i >>= 1; } return r; }
+
+// multi-word helpers (JW words)
+static void mw_mul_word(u64 *a, u64 w) {
+    u64 carry = 0;
+    for (int i = 0; i < JW; i++) { u128 t = (u128)a[i] * w + carry; a[i] = (u64)t; carry = (u64)(t >> 64); }
+}
+static u64 mw_mod_word(const u64 *a, u64 q) {
+    u128 r = 0;
+    for (int i = JW - 1; i >= 0; i--) r = ((r << 64) | a[i]) % q;
+    return (u64)r;
+}
+
+static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi, u64 *h_roots /* 2*n*JD */) {
+    memset(&R, 0, sizeof(R));
+    memset(&C, 0, sizeof(C));
+    R.n = n;
+    for (int l = 0; l < n; l++) {
+        const u64 ql = q[l];
+        if (!(ql & 1) || ql >= (1ull << 62) || ql < (1ull << 33)) return set_error(RS_ERR_UNSUPPORTED, "jindo: RNS prime out of the supported range (2^33, 2^62)");
+        R.q[l] = ql;
+        u64 inv = 1;
+        for (int i = 0; i < 6; i++) inv *= 2 - ql * inv;
+        R.qinvneg[l] = 0 - inv;
+        const u64 r1 = (u64)((((u128)1) << 64) % ql);
+        R.r2[l] = h_mulmod(r1, r1, ql);
+        R.ninv[l] = h_powmod(JD, ql - 2, ql);
+        if (h_powmod(psi[l], JD, ql) != ql - 1) return set_error(RS_ERR_ARG, "jindo: psi is not a primitive 2d-th root of unity");
+        const u64 psi_inv = h_powmod(psi[l], ql - 2, ql);
+        u64 pw = 1, pwi = 1;
+        for (int j = 0; j < JD; j++) {
+            const u64 b = h_brv(j, 8);
+            h_roots[(size_t)l * JD + b] = h_mulmod(pw, r1, ql);
+            h_roots[(size_t)(n + l) * JD + b] = h_mulmod(pwi, r1, ql);
+            pw = h_mulmod(pw, psi[l], ql);
+            pwi = h_mulmod(pwi, psi_inv, ql);
+        }
+    }
+    // CRT constants (rns.go:33-55)
+    C.Q[0] = 1;
+    for (int l = 0; l < n; l++) mw_mul_word(C.Q, q[l]);
+    for (int i = 0; i < JW; i++) C.Qhalf[i] = (C.Q[i] >> 1) | (i + 1 < JW ? (C.Q[i + 1] << 63) : 0);
+    for (int l = 0; l < n; l++) {
+        C.Qdiv[l][0] = 1;
+        for (int k = 0; k < n; k++) if (k != l) mw_mul_word(C.Qdiv[l], q[k]);
+        const u64 dm = mw_mod_word(C.Qdiv[l], q[l]);
+        const u64 r1 = (u64)((((u128)1) << 64) % q[l]);
+        C.inv_mont[l] = h_mulmod(h_powmod(dm, q[l] - 2, q[l]), r1, q[l]);
+    }
+    return RS_OK;
+}
+
+static void fill_geom_ring(MatvecGeom &G, const RingDev &R) {
+    G.n_limbs = R.n;
+    for (int l = 0; l < R.n; l++) { G.q[l] = R.q[l]; G.qinvneg[l] = R.qinvneg[l]; }
+    // 128-bit accumulation of K products below q^2: fold the high word when K * q^2 could reach 2^128
+    int bits = 0;
+    for (int l = 0; l < R.n; l++) { int b = 64 - __builtin_clzll(R.q[l]); if (b > bits) bits = b; }
+    const int headroom = 127 - 2 * bits;                 // terms allowed = 2^headroom
+    G.fold_every = (headroom >= 20) ? 0 : (headroom < 1 ? 1 : (1 << (headroom - 1)));
+    if (G.fold_every == 0 && G.K > (1 << 20)) G.fold_every = 1 << 19;
+}
+
+static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *addend, MatvecGeom G, const RingDev &R) {
+    fill_geom_ring(G, R);
+    const int n_slots = R.n * JD;
+    constexpr int OT = 4, CT = 2;
+    dim3 grid((n_slots + 127) / 128, ((G.O + OT - 1) / OT) * ((G.C + CT - 1) / CT));
+    matvec_kernel<OT, CT><<<grid, 128, 0, current_stream()>>>(out, key, x, addend, G);
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+template <int NL>
+static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n, const uint32_t *vec, const uint32_t *aux,
+                         const u64 *twin_u, const i64 *given) {
+    if (n == 0) return RS_OK;
+    EncConsts E;
+    memset(&E, 0, sizeof(E));
+    E.slots = j->p.slots; E.exp = j->p.exp; E.cdt_len = j->p.cdt_len;
+    E.base = j->p.base; E.base_magic = (u64)((((u128)1) << 64) / j->p.base) + 1;
+    E.tail_lo = j->p.cdt_tail_lo; E.sigma = j->p.cdt_sigma;
+    for (int i = 0; i < j->p.exp; i++) E.delta_inv[i] = j->p.delta_inv[i];
+    for (int l = 0; l < j->rq.n; l++) E.base_mont[l] = j->base_mont_q[l];
+    FieldParams<NL> F = make_params<NL>(j->f);
+    encode_kernel<NL><<<(unsigned)n, 256, 0, current_stream()>>>(out, d_descs, vec, aux, twin_u, given, j->d_cdt, j->rq, E, F);
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+static int encode_dispatch(rs_jindo *j, u64 *out, const EncDesc *d, size_t n, const uint32_t *vec, const uint32_t *aux,
+                           const u64 *tw, const i64 *gv) {
+    switch (j->f->NL) {
+        case 4: return launch_encode<4>(j, out, d, n, vec, aux, tw, gv);
+        case 8: return launch_encode<8>(j, out, d, n, vec, aux, tw, gv);
+        case 14: return launch_encode<14>(j, out, d, n, vec, aux, tw, gv);
+        case 28: return launch_encode<28>(j, out, d, n, vec, aux, tw, gv);
+    }
+    return set_error(RS_ERR_UNSUPPORTED, "unsupported limb count");
+}
+
+static int launch_cut(rs_jindo *j, u64 *out, const u64 *in, size_t n_polys, bool outer) {
+    CutConsts K;
+    K.log_cut = outer ? j->p.log_out_cut : j->p.log_in_cut;
+    K.in = outer ? j->rqo : j->rq;
+    K.outr = j->rqo;
+    K.crt = outer ? j->crt_qo : j->crt_q;
+    cut_kernel<<<(unsigned)n_polys, 256, 0, current_stream()>>>(out, in, K);
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+static size_t pq(const rs_jindo *j) { return (size_t)j->rq.n * JD; }       // words per ringQ poly
+static size_t pqo(const rs_jindo *j) { return (size_t)j->rqo.n * JD; }
+
+template <typename T>
+static int upload(T **d, const T *h, size_t count) {
+    *d = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)d, (count ? count : 1) * sizeof(T), current_stream()));
+    if (count) RS_CUDA_CHECK(cudaMemcpyAsync(*d, h, count * sizeof(T), cudaMemcpyHostToDevice, current_stream()));
+    return RS_OK;
+}
+
+static int opening_alloc(rs_jindo *j, rs_opening **out) {
+    rs_opening *o = new rs_opening{j, nullptr, nullptr, nullptr};
+    const rs_jindo_params &p = j->p;
+    const size_t ne = (size_t)(p.cols + 1) * p.rows * pq(j), nm = (size_t)(p.cols + 1) * (p.mlwe + p.in_msis) * pq(j),
+                 ni = (size_t)(p.cols + 1) * p.in_msis * pqo(j);
+    cudaError_t e = cudaMalloc((void **)&o->d_encode, ne * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_mlwe, nm * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_incommit, ni * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_encode, 0, ne * 8, current_stream());
+    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_mlwe, 0, nm * 8, current_stream());
+    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_incommit, 0, ni * 8, current_stream());
+    if (e != cudaSuccess) { rs_opening_free(o); return set_error(RS_ERR_CUDA, "opening alloc: %s", cudaGetErrorString(e)); }
+    *out = o;
+    return RS_OK;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in, const uint64_t *ck_mlwe,
+                    const uint64_t *ck_out, const uint64_t *cdt_tables, rs_jindo **out) {
+    RS_REQUIRE(f && p && ck_in && ck_mlwe && ck_out && cdt_tables && out, RS_ERR_ARG, "rs_jindo_create: null argument");
+    RS_REQUIRE(p->d == JD, RS_ERR_UNSUPPORTED, "rs_jindo_create: ring degree must be 256");
+    RS_REQUIRE(p->n_q >= 1 && p->n_q <= JMAXL && p->n_qout >= 1 && p->n_qout <= JMAXL, RS_ERR_UNSUPPORTED, "rs_jindo_create: 1..4 RNS limbs");
+    RS_REQUIRE(p->exp >= 1 && p->exp <= RS_JINDO_MAX_EXP && p->slots * p->exp == JD, RS_ERR_ARG, "rs_jindo_create: slots*exp != d");
+    RS_REQUIRE(p->base >= 2 && p->base < (1ull << 31) && (p->base & (p->base - 1)) != 0, RS_ERR_UNSUPPORTED, "rs_jindo_create: base must be < 2^31 and not a power of two");
+    RS_REQUIRE(p->rows >= 2 && p->cols >= 1 && p->in_msis >= 1 && p->out_msis >= 1 && p->mlwe >= 1, RS_ERR_ARG, "rs_jindo_create: bad shape");
+    RS_REQUIRE(p->cdt_len >= 1, RS_ERR_ARG, "rs_jindo_create: bad CDT");
+    rs_jindo *j = new rs_jindo();
+    memset(j, 0, sizeof(*j));
+    j->f = f;
+    j->p = *p;
+    std::vector<u64> roots((size_t)2 * (p->n_q + p->n_qout) * JD);
+    u64 *rq_h = roots.data(), *rqo_h = roots.data() + (size_t)2 * p->n_q * JD;
+    int rc = ring_setup(j->rq, j->crt_q, p->n_q, (const u64 *)p->q, (const u64 *)p->psi_q, rq_h);
+    if (rc == RS_OK) rc = ring_setup(j->rqo, j->crt_qo, p->n_qout, (const u64 *)p->qout, (const u64 *)p->psi_qout, rqo_h);
+    if (rc != RS_OK) { delete j; return rc; }
+    for (int l = 0; l < p->n_q; l++) j->base_mont_q[l] = h_mulmod(p->base % p->q[l], (u64)((((u128)1) << 64) % p->q[l]), p->q[l]);
+    const size_t n_in = (size_t)p->in_msis * p->rows * pq(j), n_ml = (size_t)p->in_msis * p->mlwe * pq(j),
+                 n_out = (size_t)p->out_msis * (p->cols + 1) * p->in_msis * pqo(j), n_cdt = (size_t)128 * p->cdt_len;
+    cudaError_t e = cudaMalloc((void **)&j->d_roots, roots.size() * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&j->d_ck_in, n_in * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&j->d_ck_mlwe, n_ml * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&j->d_ck_out, n_out * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&j->d_cdt, n_cdt * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(j->d_roots, roots.data(), roots.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_in, ck_in, n_in * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_mlwe, ck_mlwe, n_ml * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_out, ck_out, n_out * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(j->d_cdt, cdt_tables, n_cdt * 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { rs_jindo_destroy(j); return set_error(RS_ERR_CUDA, "rs_jindo_create: %s", cudaGetErrorString(e)); }
+    j->rq.roots = j->d_roots;
+    j->rq.roots_inv = j->d_roots + (size_t)p->n_q * JD;
+    j->rqo.roots = j->d_roots + (size_t)2 * p->n_q * JD;
+    j->rqo.roots_inv = j->rqo.roots + (size_t)p->n_qout * JD;
+    *out = j;
+    return RS_OK;
+}
+
+void rs_jindo_destroy(rs_jindo *j) {
+    if (!j) return;
+    cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt);
+    delete j;
+}
+
+void rs_opening_free(rs_opening *o) {
+    if (!o) return;
+    cudaFree(o->d_encode); cudaFree(o->d_mlwe); cudaFree(o->d_incommit);
+    delete o;
+}
+
+int rs_opening_alloc_zero(rs_jindo *j, rs_opening **out) {
+    RS_REQUIRE(j && out, RS_ERR_ARG, "rs_opening_alloc_zero: null argument");
+    return opening_alloc(j, out);
+}
+
+int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, uint64_t *poly_out) {
+    RS_REQUIRE(o && poly_out, RS_ERR_ARG, "rs_opening_download: null argument");
+    const rs_jindo *j = o->j;
+    const rs_jindo_params &p = j->p;
+    const u64 *src; size_t words;
+    if (kind == 0) {
+        RS_REQUIRE(col <= (size_t)p.cols && idx < (size_t)p.rows, RS_ERR_SHAPE, "rs_opening_download: out of range");
+        words = pq(j); src = o->d_encode + (col * p.rows + idx) * words;
+    } else if (kind == 1) {
+        RS_REQUIRE(col <= (size_t)p.cols && idx < (size_t)(p.mlwe + p.in_msis), RS_ERR_SHAPE, "rs_opening_download: out of range");
+        words = pq(j); src = o->d_mlwe + (col * (p.mlwe + p.in_msis) + idx) * words;
+    } else if (kind == 2) {
+        RS_REQUIRE(idx < (size_t)(p.cols + 1) * p.in_msis, RS_ERR_SHAPE, "rs_opening_download: out of range");
+        words = pqo(j); src = o->d_incommit + idx * words;
+    } else {
+        return set_error(RS_ERR_ARG, "rs_opening_download: bad kind");
+    }
+    RS_CUDA_CHECK(cudaMemcpyAsync(poly_out, src, words * 8, cudaMemcpyDeviceToHost, current_stream()));
+    RS_CUDA_CHECK(cudaStreamSynchronize(current_stream()));
+    return RS_OK;
+}
+
+int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
+                    rs_opening **open, uint64_t *commitment_out) {
+    RS_REQUIRE(j && v && tape && open && commitment_out, RS_ERR_ARG, "rs_jindo_commit: null argument");
+    const rs_jindo_params &p = j->p;
+    const size_t rank = (size_t)p.cols * (p.rows - 1) * p.slots;
+    RS_REQUIRE(len <= rank, RS_ERR_SHAPE, "len(v) > params.rank");                    // prover.go:47-49
+    RS_REQUIRE(len >= 1 && v_poly < v->n_polys && len <= v->rank, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
+    RS_REQUIRE(v->f->NL == j->f->NL, RS_ERR_SHAPE, "rs_jindo_commit: field mismatch");
+    RS_REQUIRE(tape->first_row && tape->last_row && tape->mask_rows && tape->cosac_g && tape->mlwe, RS_ERR_ARG, "rs_jindo_commit: incomplete tape");
+    const int NL = j->f->NL, d = JD, slots = p.slots, rows = p.rows, cols = p.cols;
+    const size_t cs = (size_t)cols * slots;
+
+    // ---- descriptors, in the order of commitColTo (prover.go:89-128)
+    std::vector<EncDesc> descs;
+    size_t twin = 0, cosac = 0, mask = 0;
+    auto add = [&](int kind, size_t off, int cnt, int nk, size_t noff, size_t col, size_t row) {
+        descs.push_back(EncDesc{kind, cnt, (i64)off, nk, (i64)(noff * d), (i64)(col * rows + row)});
+    };
+    for (int i = 0; i < cols; i++) {
+        add(1, (size_t)i * slots, slots, 1, (size_t)i, i, 0);                           // firstRow, COSAC (ecdBlindStdDev)
+    }
+    cosac = cols;
+    for (int i = 0; i < cols; i++) {
+        for (int r = 1; r < rows - 1; r++) {
+            const size_t s = (size_t)r * cs + (size_t)i * slots, e = s + slots;
+            if (s > len) break;                                                         // note '>' (prover.go:121)
+            const size_t hi = e < len ? e : len;
+            add(0, v_poly * v->rank + s, (int)(hi - s), 0, twin++, i, r);
+        }
+        add(1, cs + (size_t)i * slots, slots, 0, twin++, i, rows - 1);                  // lastRow, TwinCDT (ecdStdDev)
+    }
+    {   // mask column (prover.go:93-115): every row COSAC, fresh random elements per row
+        add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, 0);
+        for (int r = 1; r < rows - 1; r++) {
+            if ((size_t)r * cs > len) break;
+            add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, r);
+        }
+        add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, rows - 1);
+    }
+    RS_REQUIRE(tape->n_mask_rows == mask, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of mask rows");
+    RS_REQUIRE(tape->n_cosac_polys == cosac, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of COSAC polynomials");
+    RS_REQUIRE(tape->n_twin_u == twin * d && (twin == 0 || tape->twin_u), RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of TwinCDT draws");
+
+    rs_opening *o = nullptr;
+    int rc = opening_alloc(j, &o);
+    if (rc) return rc;
+
+    // ---- uploads
+    std::vector<uint32_t> aux((2 * cs + mask * slots) * NL);
+    memcpy(aux.data(), tape->first_row, cs * NL * 4);
+    memcpy(aux.data() + cs * NL, tape->last_row, cs * NL * 4);
+    memcpy(aux.data() + 2 * cs * NL, tape->mask_rows, mask * slots * NL * 4);
+    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr; EncDesc *d_descs = nullptr, *d_ndescs = nullptr;
+    u64 *d_com = nullptr, *d_com2 = nullptr, *d_value = nullptr;
+    const size_t n_noise = (size_t)(cols + 1) * (p.in_msis + p.mlwe);
+    std::vector<EncDesc> ndescs(n_noise);
+    for (size_t k = 0; k < n_noise; k++) ndescs[k] = EncDesc{2, 0, 0, 1, (i64)(k * d), (i64)k};
+#define RS_TRY(x) do { rc = (x); if (rc) goto fail; } while (0)
+    RS_TRY(upload(&d_aux, aux.data(), aux.size()));
+    RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
+    RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
+    RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
+    RS_TRY(upload(&d_descs, descs.data(), descs.size()));
+    RS_TRY(upload(&d_ndescs, ndescs.data(), ndescs.size()));
+    {
+        const size_t n_com = (size_t)(cols + 1) * p.in_msis;
+        if (cudaMallocAsync((void **)&d_com, n_com * pq(j) * 8, current_stream()) != cudaSuccess ||
+            cudaMallocAsync((void **)&d_com2, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess ||
+            cudaMallocAsync((void **)&d_value, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess) {
+            rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: cudaMallocAsync failed");
+            goto fail;
+        }
+        // ---- encodes + noise polynomials
+        RS_TRY(encode_dispatch(j, o->d_encode, d_descs, descs.size(), v->d, d_aux, d_twin, d_cosac));
+        RS_TRY(encode_dispatch(j, o->d_mlwe, d_ndescs, n_noise, v->d, d_aux, d_twin, d_mlwe_s));
+        // ---- inner commit (prover.go:144-157)
+        MatvecGeom G;
+        memset(&G, 0, sizeof(G));
+        G.O = p.in_msis; G.C = cols + 1; G.K = rows;
+        G.key_os = rows; G.key_ks = 1; G.x_cs = rows; G.x_ks = 1; G.out_cs = p.in_msis; G.out_os = 1;
+        RS_TRY(launch_matvec(d_com, j->d_ck_in, o->d_encode, nullptr, G, j->rq));
+        G.K = p.mlwe; G.key_os = p.mlwe; G.x_cs = p.mlwe + p.in_msis; G.accumulate = 1;
+        G.has_addend = 1; G.add_cs = p.mlwe + p.in_msis; G.add_os = 1;
+        RS_TRY(launch_matvec(d_com, j->d_ck_mlwe, o->d_mlwe, o->d_mlwe + (size_t)p.mlwe * pq(j), G, j->rq));
+        // ---- cut-off pipeline (prover.go:164-176)
+        RS_TRY(launch_cut(j, o->d_incommit, d_com, n_com, false));
+        // ---- outer commit (prover.go:180-202)
+        memset(&G, 0, sizeof(G));
+        G.O = p.out_msis; G.C = 1; G.K = (int)n_com;
+        G.key_os = (i64)n_com; G.key_ks = 1; G.x_cs = 0; G.x_ks = 1; G.out_cs = 0; G.out_os = 1;
+        RS_TRY(launch_matvec(d_com2, j->d_ck_out, o->d_incommit, nullptr, G, j->rqo));
+        RS_TRY(launch_cut(j, d_value, d_com2, p.out_msis, true));
+        if (cudaMemcpyAsync(commitment_out, d_value, (size_t)p.out_msis * pqo(j) * 8, cudaMemcpyDeviceToHost, current_stream()) != cudaSuccess ||
+            cudaStreamSynchronize(current_stream()) != cudaSuccess) {
+            rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: %s", cudaGetErrorString(cudaGetLastError()));
+            goto fail;
+        }
+    }
+fail:
+#undef RS_TRY
+    cudaFreeAsync(d_aux, current_stream()); cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream());
+    cudaFreeAsync(d_mlwe_s, current_stream()); cudaFreeAsync(d_descs, current_stream()); cudaFreeAsync(d_ndescs, current_stream());
+    cudaFreeAsync(d_com, current_stream()); cudaFreeAsync(d_com2, current_stream()); cudaFreeAsync(d_value, current_stream());
+    if (rc) { rs_opening_free(o); return rc; }
+    *open = o;
+    return RS_OK;
+}
+
+int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out) {
+    RS_REQUIRE(j && o && left && partial_out, RS_ERR_ARG, "rs_jindo_partial: null argument");
+    const rs_jindo_params &p = j->p;
+    u64 *d_left = nullptr, *d_out = nullptr;
+    int rc = upload(&d_left, (const u64 *)left, (size_t)p.rows * pq(j));
+    if (rc) return rc;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_out, (size_t)(p.cols + 1) * pq(j) * 8, current_stream()));
+    MatvecGeom G;
+    memset(&G, 0, sizeof(G));
+    G.O = 1; G.C = p.cols + 1; G.K = p.rows;
+    G.key_os = 0; G.key_ks = 1; G.x_cs = p.rows; G.x_ks = 1; G.out_cs = 1; G.out_os = 0;
+    rc = launch_matvec(d_out, d_left, o->d_encode, nullptr, G, j->rq);
+    if (rc == RS_OK) {
+        cudaError_t e = cudaMemcpyAsync(partial_out, d_out, (size_t)(p.cols + 1) * pq(j) * 8, cudaMemcpyDeviceToHost, current_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+        if (e != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_partial: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d_left, current_stream()); cudaFreeAsync(d_out, current_stream());
+    return rc;
+}
+
+int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, uint64_t *enc_out, uint64_t *mlwe_out) {
+    RS_REQUIRE(j && o && chals && enc_out && mlwe_out, RS_ERR_ARG, "rs_jindo_respond: null argument");
+    const rs_jindo_params &p = j->p;
+    const int nm = p.mlwe + p.in_msis;
+    u64 *d_ch = nullptr, *d_e = nullptr, *d_m = nullptr;
+    int rc = upload(&d_ch, (const u64 *)chals, (size_t)p.cols * pq(j));
+    if (rc) return rc;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_e, (size_t)p.rows * pq(j) * 8, current_stream()));
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_m, (size_t)nm * pq(j) * 8, current_stream()));
+    MatvecGeom G;
+    memset(&G, 0, sizeof(G));
+    // Encode[i] = Enc[cols][i] + sum_j chal[j] (.) Enc[j][i]: "columns" of the product are the rows i
+    G.O = 1; G.C = p.rows; G.K = p.cols;
+    G.key_os = 0; G.key_ks = 1; G.x_cs = 1; G.x_ks = p.rows; G.out_cs = 1; G.out_os = 0;
+    G.has_addend = 1; G.add_cs = 1; G.add_os = 0;
+    rc = launch_matvec(d_e, d_ch, o->d_encode, o->d_encode + (size_t)p.cols * p.rows * pq(j), G, j->rq);
+    if (rc == RS_OK) {
+        G.C = nm; G.x_ks = nm;
+        rc = launch_matvec(d_m, d_ch, o->d_mlwe, o->d_mlwe + (size_t)p.cols * nm * pq(j), G, j->rq);
+    }
+    if (rc == RS_OK) {
+        cudaError_t e = cudaMemcpyAsync(enc_out, d_e, (size_t)p.rows * pq(j) * 8, cudaMemcpyDeviceToHost, current_stream());
+        if (e == cudaSuccess) e = cudaMemcpyAsync(mlwe_out, d_m, (size_t)nm * pq(j) * 8, cudaMemcpyDeviceToHost, current_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+        if (e != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_respond: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d_ch, current_stream()); cudaFreeAsync(d_e, current_stream()); cudaFreeAsync(d_m, current_stream());
+    return rc;
+}
+
+int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout) {
+    RS_REQUIRE(j && acc && o && chal_q && chal_qout, RS_ERR_ARG, "rs_opening_mul_add: null argument");
+    const rs_jindo_params &p = j->p;
+    u64 *d_cq = nullptr, *d_co = nullptr;
+    int rc = upload(&d_cq, (const u64 *)chal_q, pq(j));
+    if (rc == RS_OK) rc = upload(&d_co, (const u64 *)chal_qout, pqo(j));
+    if (rc) return rc;
+    MatvecGeom Gq, Go;
+    memset(&Gq, 0, sizeof(Gq)); memset(&Go, 0, sizeof(Go));
+    fill_geom_ring(Gq, j->rq); fill_geom_ring(Go, j->rqo);
+    const size_t ne = (size_t)(p.cols + 1) * p.rows, nm = (size_t)(p.cols + 1) * (p.mlwe + p.in_msis), ni = (size_t)(p.cols + 1) * p.in_msis;
+    muladd_bcast_kernel<<<148 * 8, 256, 0, current_stream()>>>(acc->d_encode, o->d_encode, d_cq, ne, j->rq.n, Gq);
+    muladd_bcast_kernel<<<148 * 2, 256, 0, current_stream()>>>(acc->d_mlwe, o->d_mlwe, d_cq, nm, j->rq.n, Gq);
+    muladd_bcast_kernel<<<148 * 2, 256, 0, current_stream()>>>(acc->d_incommit, o->d_incommit, d_co, ni, j->rqo.n, Go);
+    count_launch(3);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_cq, current_stream()); cudaFreeAsync(d_co, current_stream());
+    if (e != cudaSuccess) return set_error(RS_ERR_CUDA, "rs_opening_mul_add: %s", cudaGetErrorString(e));
+    return RS_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

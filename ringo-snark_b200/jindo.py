@@ -1,0 +1,119 @@
+"""Host-side mirror of jindo.Prover (jindo/prover.go) over the C ABI of include/ringo_jindo.h.
+
+`Prover.Commit(v)` / `Prover.Evaluate(...)` keep the reference's names and argument meaning.
+Everything that is a host-library convention or a random draw in the reference is an explicit
+input here (`params`: primes, psi, deltaInv, CDT tables; `tape`: the randomness of one Commit),
+exactly as the Go shim would pass them.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib, c_vp
+
+
+def _vp(a):
+    return a.ctypes.data_as(c_vp)
+
+
+class Opening:
+    def __init__(self, prover, handle):
+        self.prover = prover
+        self.h = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().rs_opening_free(self.h)
+        except Exception:
+            pass
+
+    def _get(self, kind, col, idx, n_limbs):
+        out = np.zeros((n_limbs, self.prover.d), dtype=np.uint64)
+        check(lib().rs_opening_download(self.h, kind, col, idx, _vp(out)))
+        return out
+
+    def Encode(self, col, row): return self._get(0, col, row, self.prover.n_q)
+    def MLWE(self, col, idx): return self._get(1, col, idx, self.prover.n_q)
+    def InCommit(self, idx): return self._get(2, 0, idx, self.prover.n_qout)
+
+
+class Prover:
+    """jindo.NewProver (prover.go:28-40).  `p` is a dict with the jindo.Parameters fields, the
+    RNS primes / psi, deltaInv and the TwinCDT tables; `ck_*` are the commit-key polynomials as
+    uint64 arrays [.., limb, 256]."""
+
+    def __init__(self, field, p, ck_in, ck_mlwe, ck_out, cdt_tables):
+        self.field = field
+        self.p = dict(p)
+        self.d = p["d"]
+        self.n_q, self.n_qout = len(p["q"]), len(p["qout"])
+        P = capi.JindoParams()
+        for k in ("d", "slots", "exp", "base", "rows", "cols", "in_msis", "mlwe", "out_msis", "log_in_cut", "log_out_cut"):
+            setattr(P, k, int(p[k]))
+        P.n_q, P.n_qout = self.n_q, self.n_qout
+        for i, v in enumerate(p["q"]): P.q[i] = v
+        for i, v in enumerate(p["qout"]): P.qout[i] = v
+        for i, v in enumerate(p["psi_q"]): P.psi_q[i] = v
+        for i, v in enumerate(p["psi_qout"]): P.psi_qout[i] = v
+        for i, v in enumerate(p["delta_inv"]): P.delta_inv[i] = v
+        cdt = np.ascontiguousarray(cdt_tables, dtype=np.uint64)
+        P.cdt_len = cdt.shape[1]
+        P.cdt_tail_lo = int(p["cdt_tail_lo"])
+        P.cdt_sigma = float(p["cdt_sigma"])
+        h = c_vp()
+        ck_in = np.ascontiguousarray(ck_in, dtype=np.uint64); ck_mlwe = np.ascontiguousarray(ck_mlwe, dtype=np.uint64)
+        ck_out = np.ascontiguousarray(ck_out, dtype=np.uint64)
+        check(lib().rs_jindo_create(field.h, ctypes.byref(P), _vp(ck_in), _vp(ck_mlwe), _vp(ck_out), _vp(cdt), ctypes.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().rs_jindo_destroy(self.h)
+        except Exception:
+            pass
+
+    def Commit(self, batch, poly, length, tape):
+        """prover.go:45-62.  batch/poly/length: device-resident committed vector; tape: dict of
+        numpy arrays first_row, last_row, mask_rows (uint64 Montgomery limbs), twin_u (uint64),
+        cosac_g, mlwe (int64).  Returns (commitment [out_msis, n_qout, 256], Opening)."""
+        keep = {k: np.ascontiguousarray(tape[k], dtype=(np.int64 if k in ("cosac_g", "mlwe") else np.uint64))
+                for k in ("first_row", "last_row", "mask_rows", "twin_u", "cosac_g", "mlwe")}
+        L = self.field.L
+        T = capi.JindoTape()
+        T.first_row, T.last_row, T.mask_rows = _vp(keep["first_row"]), _vp(keep["last_row"]), _vp(keep["mask_rows"])
+        T.n_mask_rows = keep["mask_rows"].size // (L * self.p["slots"])
+        T.twin_u, T.n_twin_u = _vp(keep["twin_u"]), keep["twin_u"].size
+        T.cosac_g, T.n_cosac_polys = _vp(keep["cosac_g"]), keep["cosac_g"].size // self.d
+        T.mlwe = _vp(keep["mlwe"])
+        com = np.zeros((self.p["out_msis"], self.n_qout, self.d), dtype=np.uint64)
+        oh = c_vp()
+        check(lib().rs_jindo_commit(self.h, batch.h, poly, length, ctypes.byref(T), ctypes.byref(oh), _vp(com)))
+        return com, Opening(self, oh)
+
+    def Partial(self, opening, left):
+        """prover.go:281-289: returns [cols+1, n_q, 256]; index cols is PartialMask."""
+        left = np.ascontiguousarray(left, dtype=np.uint64)
+        out = np.zeros((self.p["cols"] + 1, self.n_q, self.d), dtype=np.uint64)
+        check(lib().rs_jindo_partial(self.h, opening.h, _vp(left), _vp(out)))
+        return out
+
+    def Respond(self, opening, chals):
+        """prover.go:304-316: returns (Encode [rows,..], MLWE [mlwe+in_msis,..])."""
+        chals = np.ascontiguousarray(chals, dtype=np.uint64)
+        enc = np.zeros((self.p["rows"], self.n_q, self.d), dtype=np.uint64)
+        ml = np.zeros((self.p["mlwe"] + self.p["in_msis"], self.n_q, self.d), dtype=np.uint64)
+        check(lib().rs_jindo_respond(self.h, opening.h, _vp(chals), _vp(enc), _vp(ml)))
+        return enc, ml
+
+    def NewOpening(self):
+        oh = c_vp()
+        check(lib().rs_opening_alloc_zero(self.h, ctypes.byref(oh)))
+        return Opening(self, oh)
+
+    def OpeningMulAdd(self, acc, opening, chal_q, chal_qout):
+        """prover.go:251-265: acc += opening (.) challenge (both rings)."""
+        cq = np.ascontiguousarray(chal_q, dtype=np.uint64); co = np.ascontiguousarray(chal_qout, dtype=np.uint64)
+        check(lib().rs_opening_mul_add(self.h, acc.h, opening.h, _vp(cq), _vp(co)))

@@ -1,0 +1,114 @@
+"""GPU parity tests for the Jindo path (rs_jindo_* through the C ABI) against the oracle
+(oracle/jindo_ref.py) on the same parameters, commit key and randomness tape -- bit-exact on
+every polynomial of the Opening, the Commitment and the Evaluate responses."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import jindo_ref as J, pyref
+from jindo_util import cdt_array, params_dict, polys_array, tape_arrays
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rs(product):
+    L = product.load()
+    assert L.rs_init(0) == 0, L.rs_last_error()
+    return product
+
+
+CASES = [
+    ("zp255", 1024, 1, 1024),    # TestJindo single (jindo_test.go:16-52): 2 limbs -> 1 limb
+    ("zp255", 1024, 1, 700),     # short vector: rows past len(v) stay zero (prover.go:118-125)
+    ("zp255", 1024, 1, 1),       # single coefficient
+    ("zp128", 700, 2, 700),      # 3-limb rings, 128-bit field, batch parameters
+    ("zp220", 2049, 9, 2049),    # TestPublicKey commitment shape
+    ("zp240", 600, 3, 513),
+]
+
+
+@pytest.mark.parametrize("name,N,batch,length", CASES)
+def test_commit_and_evaluate_parity(rs, name, N, batch, length):
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    p = J.new_parameters(q, N, batch)
+    tape = J.Tape(b"gpu-parity-" + name.encode())
+    prv = J.Prover(p, b"Jindo!", tape)
+    gp = rs.jindo.Prover(fg, params_dict(p, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
+                         polys_array(prv.ck.Out), cdt_array(prv.ecd))
+    v = [J.field_set_random(tape, q) for _ in range(length)]
+    com_o, open_o = prv.commit(v)
+    rec = prv.trace
+    # committed vector lives in a device batch, at a non-zero poly index
+    rank_pad = max(length, 8)
+    B = rs.Batch(fg, 2, rank_pad)
+    host = np.zeros((2, rank_pad, fo.L), dtype=np.uint64)
+    host[1, :length] = fo.to_mont(v)
+    B.upload(host)
+    com_g, open_g = gp.Commit(B, 1, length, tape_arrays(fo, p, rec))
+    # Opening: every Encode / MLWE / InCommit polynomial
+    for i in range(p.cols + 1):
+        for j in range(p.rows):
+            assert np.array_equal(open_g.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", i, j)
+        for j in range(p.mlwe + p.in_msis):
+            assert np.array_equal(open_g.MLWE(i, j), polys_array(open_o.MLWE[i][j])), ("MLWE", i, j)
+    for k in range(p.in_com_dcmp_len):
+        assert np.array_equal(open_g.InCommit(k), polys_array(open_o.InCommit[k])), ("InCommit", k)
+    assert np.array_equal(com_g, polys_array(com_o))
+    # Evaluate (batch-1 flow of prover.go:267-316 on this opening)
+    x = J.field_set_random(tape, q)
+    left = polys_array([prv.ecd.encode([le]) for le in J.left_vec(p, x)])
+    part = gp.Partial(open_g, left)
+    ring = p.ringQ
+    exp_part = []
+    for i in range(p.cols + 1):
+        acc = ring.new_poly()
+        for j in range(p.rows):
+            acc = ring.mul_mont_then_add(left[j].tolist(), open_o.Encode[i][j], acc)
+        exp_part.append(acc)
+    assert np.array_equal(part, polys_array(exp_part))
+    chal_bytes = [bytes([17 * (i + 1) % 256] * 16) for i in range(p.cols)]
+    chals = [J.encode_challenge(p, ring, cb) for cb in chal_bytes]
+    enc_g, mlwe_g = gp.Respond(open_g, polys_array(chals))
+    for i in range(p.rows):
+        acc = [list(c) for c in open_o.Encode[p.cols][i]]
+        for j in range(p.cols):
+            acc = ring.mul_mont_then_add(chals[j], open_o.Encode[j][i], acc)
+        assert np.array_equal(enc_g[i], polys_array(acc)), ("resp Encode", i)
+    for i in range(p.mlwe + p.in_msis):
+        acc = [list(c) for c in open_o.MLWE[p.cols][i]]
+        for j in range(p.cols):
+            acc = ring.mul_mont_then_add(chals[j], open_o.MLWE[j][i], acc)
+        assert np.array_equal(mlwe_g[i], polys_array(acc)), ("resp MLWE", i)
+    # batch combine (prover.go:251-265): acc = 0 + open (.) challenge
+    cq = J.encode_challenge(p, ring, b"\x05" * 16); co = J.encode_challenge(p, p.ringQOut, b"\x05" * 16)
+    acc_g = gp.NewOpening()
+    gp.OpeningMulAdd(acc_g, open_g, polys_array(cq), polys_array(co))
+    gp.OpeningMulAdd(acc_g, open_g, polys_array(cq), polys_array(co))
+    z = ring.new_poly()
+    e = ring.mul_mont_then_add(open_o.Encode[0][1], cq, ring.mul_mont_then_add(open_o.Encode[0][1], cq, z))
+    assert np.array_equal(acc_g.Encode(0, 1), polys_array(e))
+    zo = p.ringQOut.new_poly()
+    e = p.ringQOut.mul_mont_then_add(open_o.InCommit[3], co, p.ringQOut.mul_mont_then_add(open_o.InCommit[3], co, zo))
+    assert np.array_equal(acc_g.InCommit(3), polys_array(e))
+
+
+def test_commit_shape_errors(rs):
+    q = pyref.modulus("zp255")
+    fo = oracle.Field(q); fg = rs.Field(q)
+    p = J.new_parameters(q, 1024, 1)
+    tape = J.Tape(b"err")
+    prv = J.Prover(p, b"Jindo!", tape)
+    gp = rs.jindo.Prover(fg, params_dict(p, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
+                         polys_array(prv.ck.Out), cdt_array(prv.ecd))
+    v = [J.field_set_random(tape, q) for _ in range(64)]
+    prv.commit(v)
+    t = tape_arrays(fo, p, prv.trace)
+    B = rs.Batch(fg, 1, 4096)
+    with pytest.raises(rs.RingoError) as e:
+        gp.Commit(B, 0, p.rank + 1, t)                       # "len(v) > params.rank" (prover.go:47-49)
+    assert "len(v) > params.rank" in str(e.value)
+    t["twin_u"] = t["twin_u"][:-1]
+    with pytest.raises(rs.RingoError):
+        gp.Commit(B, 0, 64, t)
