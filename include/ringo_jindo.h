@@ -74,11 +74,13 @@ typedef struct rs_jindo_tape {
                                     the mask column's rows in encode order; d values each */
     size_t n_cosac_polys;
     const int64_t *mlwe;         /* (cols+1)*(in_msis+mlwe)*d noise samples          prover.go:130-139 */
+    int32_t on_device;           /* != 0: every pointer above is a device pointer (tape already resident in HBM) */
 } rs_jindo_tape;
 
 /* Prover.Commit (jindo/prover.go:45-62).  v: device batch holding the committed vector
  * (poly v_poly, first len coefficients, len <= rank).  commitment_out: out_msis polys over
- * ringQOut (host, n_qout*d words each) -- Commitment.Value in NTT+Montgomery form. */
+ * ringQOut (host, n_qout*d words each) -- Commitment.Value in NTT+Montgomery form.
+ * *open: NULL on entry -> a new Opening is allocated; otherwise the given Opening is overwritten. */
 int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
                     rs_opening **open, uint64_t *commitment_out);
 void rs_opening_free(rs_opening *o);

@@ -45,7 +45,8 @@ class JindoParams(ctypes.Structure):
 class JindoTape(ctypes.Structure):
     """rs_jindo_tape (include/ringo_jindo.h)"""
     _fields_ = [("first_row", c_vp), ("last_row", c_vp), ("mask_rows", c_vp), ("n_mask_rows", c_size),
-                ("twin_u", c_vp), ("n_twin_u", c_size), ("cosac_g", c_vp), ("n_cosac_polys", c_size), ("mlwe", c_vp)]
+                ("twin_u", c_vp), ("n_twin_u", c_size), ("cosac_g", c_vp), ("n_cosac_polys", c_size), ("mlwe", c_vp),
+                ("on_device", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/ringo_cuda.h and include/ringo_jindo.h one to one

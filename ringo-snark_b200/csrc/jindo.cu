@@ -13,7 +13,10 @@
 //                   Montgomery reduction per output.
 //   cut_kernel      IMForm/INTT -> CRT to a centred multi-word integer -> arithmetic >> cut ->
 //                   residues mod the outer primes -> MForm/NTT  (prover.go:164-176, :190-200).
+#include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "../../include/ringo_jindo.h"
 #include "common.cuh"
@@ -42,7 +45,16 @@ struct CrtDev {             // RNSReconstructor constants of the *source* ring (
     u64 inv_mont[JMAXL];    // ((Q/q_l)^-1 mod q_l) * 2^64 mod q_l
 };
 
+namespace rs { struct EncDesc; }
+struct DescCache {            // encode descriptors of one committed length, resident on the device
+    size_t len;
+    rs::EncDesc *d_descs;
+    size_t n_descs, twin, cosac, mask;
+};
+
 struct rs_jindo {
+    std::vector<DescCache> *cache;
+    rs::EncDesc *d_ndescs;    // descriptors of the MLWE noise polynomials
     rs_field *f;
     rs_jindo_params p;
     RingDev rq, rqo;
@@ -148,121 +160,150 @@ struct EncConsts {
     u64 base_mont[JMAXL];
 };
 
+// One CTA handles G = 256 / slots consecutive descriptors.  Phase 1 (all 256 threads, one field
+// element each): fromMont + long division into base-b digits.  Phase 2 (per polynomial, one thread
+// per coefficient): centre, sample, combine, NTT.
 template <int NL>
-__global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, const EncDesc *__restrict__ descs,
+__global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, const EncDesc *__restrict__ descs, int n_descs,
                                                      const uint32_t *__restrict__ vec, const uint32_t *__restrict__ aux,
                                                      const u64 *__restrict__ twin_u, const i64 *__restrict__ given,
                                                      const u64 *__restrict__ cdt, const __grid_constant__ RingDev R,
                                                      const __grid_constant__ EncConsts E,
                                                      const __grid_constant__ FieldParams<NL> F) {
-    __shared__ u64 s_digit[JD];
-    __shared__ i64 s_g[JD];
-    __shared__ u64 s_poly[JMAXL][JD];
-    const EncDesc D = descs[blockIdx.x];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: digits [G][256] u32 | g [256] i64 | poly [JMAXL][256] u64
+    const int G = JD / E.slots;
+    uint32_t *s_dig = reinterpret_cast<uint32_t *>(smem_raw);
+    i64 *s_g = reinterpret_cast<i64 *>(smem_raw + (size_t)G * JD * 4);
+    u64(*s_poly)[JD] = reinterpret_cast<u64(*)[JD]>(smem_raw + (size_t)G * JD * 4 + JD * 8);
     const int c = threadIdx.x;
+    const int d0 = blockIdx.x * G;
 
-    // ---- baseEncodeTo (encoder.go:120-146): canonical limbs -> exp base-b digits at stride `slots`
-    s_digit[c] = 0;
+    // ---- phase 1: baseEncodeTo (encoder.go:120-146) for G polynomials at once
+    for (int k = c; k < G * JD; k += 256) s_dig[k] = 0;
     __syncthreads();
-    if (D.src_kind != 2 && c < D.cnt) {
-        const uint32_t *src = (D.src_kind == 0 ? vec : aux) + (size_t)(D.src_off + c) * NL;
-        uint32_t x[NL], one[NL], y[NL];
+    {
+        const int g = c / E.slots, i = c % E.slots;
+        if (d0 + g < n_descs) {
+            const EncDesc D = descs[d0 + g];
+            if (D.src_kind != 2 && i < D.cnt) {
+                const uint32_t *src = (D.src_kind == 0 ? vec : aux) + (size_t)(D.src_off + i) * NL;
+                uint32_t x[NL], one[NL], y[NL];
 #pragma unroll
-        for (int l = 0; l < NL; l++) { x[l] = src[l]; one[l] = 0; }
-        one[0] = 1;
-        mont_mul<NL, 0>(y, x, one, F);                     // Slice(): fromMont (element.go:1769-1773)
-        const u64 b = E.base;
-        for (int j = 0; j < E.exp - 1; j++) {
-            u64 r = 0;                                     // divMod64 (utils.go:12-18) on 32-bit limbs
+                for (int l = 0; l < NL; l++) { x[l] = src[l]; one[l] = 0; }
+                one[0] = 1;
+                mont_mul<NL, 0>(y, x, one, F);                 // Slice(): fromMont (element.go:1769-1773)
+                const uint32_t b = (uint32_t)E.base;
+                uint32_t *dst = s_dig + g * JD + i;
+                for (int j = 0; j < E.exp - 1; j++) {
+                    uint32_t r = 0;                            // divMod64 (utils.go:12-18) on 32-bit limbs
 #pragma unroll
-            for (int l = NL - 1; l >= 0; l--) {
-                const u64 cur = (r << 32) | y[l];
-                u64 qd = hmulhi(cur, E.base_magic);        // floor(cur / b) or one more (cur < b * 2^32)
-                u64 rem = cur - qd * b;
-                if ((i64)rem < 0) { rem += b; qd--; }
-                y[l] = (uint32_t)qd;
-                r = rem;
+                    for (int l = NL - 1; l >= 0; l--) {
+                        const u64 cur = ((u64)r << 32) | y[l];
+                        u64 qd = hmulhi(cur, E.base_magic);    // floor(cur / b) or one more (cur < b * 2^32)
+                        i64 rem = (i64)(cur - qd * b);
+                        if (rem < 0) { rem += b; qd--; }
+                        y[l] = (uint32_t)qd;
+                        r = (uint32_t)rem;
+                    }
+                    dst[j * E.slots] = r;
+                }
+                dst[(E.exp - 1) * E.slots] = y[0];             // remaining quotient (<= base)
             }
-            s_digit[j * E.slots + c] = r;
         }
-        s_digit[(E.exp - 1) * E.slots + c] = ((u64)y[1] << 32) | y[0];
     }
     __syncthreads();
 
-    // ---- Gaussian vector g
-    i64 g;
-    if (D.noise_kind == 1) {
-        g = given[D.noise_off + c];
-    } else {
-        // float64 centre (encoder.go:152-164), unfused multiply-add in the reference's order
-        double fp = 0.0;
-        for (int i = 0; i < E.exp; i++) {
-            const double di = E.delta_inv[i];
-            if (di == 0.0) continue;
-            const int w = (i + 1) * E.slots;               // N - d
-            if (c >= JD - w) fp = __dadd_rn(fp, __dmul_rn(di, (double)s_digit[c - (JD - w)]));
-            else fp = __dsub_rn(fp, __dmul_rn(di, (double)s_digit[c + w]));
-        }
-        // TwinCDT (gaussian_twin_cdt.go:77-111)
-        const double center = -fp;
-        const double cfloor = floor(center);
-        const double cfrac = __dsub_rn(center, cfloor);
-        const double sc = __dmul_rn(128.0, cfrac);
-        const int c0 = (int)(((i64)floor(sc)) % 128), c1 = (int)(((i64)ceil(sc)) % 128);
-        const u64 u = twin_u[D.noise_off + c];
-        int v[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const u64 *tab = cdt + (size_t)(k ? c1 : c0) * E.cdt_len;
-            int lo = 0, hi = E.cdt_len;
-            while (lo < hi) {                              // slices.BinarySearch: leftmost index with tab >= u
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(tab + mid) < u) lo = mid + 1; else hi = mid;
+    // ---- phase 2
+    for (int g = 0; g < G && d0 + g < n_descs; g++) {
+        const EncDesc D = descs[d0 + g];
+        const uint32_t *dig = s_dig + g * JD;
+        i64 gv;
+        if (D.noise_kind == 1) {
+            gv = given[D.noise_off + c];
+        } else {
+            // float64 centre (encoder.go:152-164), unfused multiply-add in the reference's order
+            double fp = 0.0;
+            for (int i = 0; i < E.exp; i++) {
+                const double di = E.delta_inv[i];
+                if (di == 0.0) continue;
+                const int w = (i + 1) * E.slots;           // N - d
+                if (c >= JD - w) fp = __dadd_rn(fp, __dmul_rn(di, (double)dig[c - (JD - w)]));
+                else fp = __dsub_rn(fp, __dmul_rn(di, (double)dig[c + w]));
             }
-            if (lo < E.cdt_len && __ldg(tab + lo) == u) lo -= 1;
-            v[k] = lo;
-        }
-        int pick = v[0];
-        if (v[0] != v[1]) {
-            double cdf = 0.0;
+            // TwinCDT (gaussian_twin_cdt.go:77-111)
+            const double center = -fp;
+            const double cfloor = floor(center);
+            const double cfrac = __dsub_rn(center, cfloor);
+            const double sc = __dmul_rn(128.0, cfrac);
+            const int c0 = (int)(((i64)floor(sc)) % 128), c1 = (int)(((i64)ceil(sc)) % 128);
+            const u64 u = __ldg(twin_u + D.noise_off + c);
+            int v[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const u64 *tab = cdt + (size_t)(k ? c1 : c0) * E.cdt_len;
+                int lo = 0, hi = E.cdt_len;
+                while (lo < hi) {                          // slices.BinarySearch: leftmost index with tab >= u
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(tab + mid) < u) lo = mid + 1; else hi = mid;
+                }
+                if (lo < E.cdt_len && __ldg(tab + lo) == u) lo -= 1;
+                v[k] = lo;
+            }
+            // Slow path (gaussian_twin_cdt.go:95-110): CDF at v0 for the exact centre.  ~1% of the samples
+            // take it; the warp serves its slow lanes one at a time, all 32 lanes evaluating the terms
+            // rho(x), x = tail_lo .. v0, in parallel (lane-strided partial sums, then a shuffle tree).
+            int pick = v[0];
+            unsigned slow = __ballot_sync(0xffffffffu, v[0] != v[1]);
+            const int lane = c & 31;
             const double norm = __dmul_rn(sqrt(6.283185307179586), E.sigma);
             const double den = __dmul_rn(__dmul_rn(2.0, E.sigma), E.sigma);
-            for (i64 x = E.tail_lo; x <= (i64)v[0]; x++) {
-                const double t = __dsub_rn((double)x, cfrac);
-                cdf = __dadd_rn(cdf, __ddiv_rn(exp(__ddiv_rn(__dmul_rn(-t, t), den)), norm));
+            while (slow) {
+                const int src = __ffs(slow) - 1;
+                slow &= slow - 1;
+                const double cf = __shfl_sync(0xffffffffu, cfrac, src);
+                const int top = __shfl_sync(0xffffffffu, v[0], src);
+                double part = 0.0;
+                for (i64 x = E.tail_lo + lane; x <= (i64)top; x += 32) {
+                    const double t = __dsub_rn((double)x, cf);
+                    part = __dadd_rn(part, __ddiv_rn(exp(__ddiv_rn(__dmul_rn(-t, t), den)), norm));
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+                if (lane == src) {
+                    const double p = __dmul_rn(__ull2double_rn(u), 5.421010862427522e-20);   // u / 2^64
+                    pick = (p < part) ? v[0] : v[1];
+                }
             }
-            const double p = __dmul_rn(__ull2double_rn(u), 5.421010862427522e-20);   // u / 2^64
-            pick = (p < cdf) ? v[0] : v[1];
+            gv = (i64)pick + (i64)cfloor + E.tail_lo;
         }
-        g = (i64)pick + (i64)cfloor + E.tail_lo;
-    }
-    s_g[c] = g;
-    __syncthreads();
-
-    // ---- MForm(digits) + MForm(X^slots g - base g)  (encoder.go:166-199), per RNS limb
-    for (int l = 0; l < R.n; l++) {
-        const u64 q = R.q[l], qi = R.qinvneg[l];
-        u64 val;
-        if (D.src_kind == 2) {
-            val = signed_res(g, q);                        // noise polynomial: setCoeffSigned (prover.go:130-139)
-        } else {
-            const u64 gm = signed_res(g, q);
-            const u64 gs = (c >= E.slots) ? signed_res(s_g[c - E.slots], q)
-                                          : submod(0, signed_res(s_g[c + JD - E.slots], q), q);
-            const u64 bg = mont64(E.base_mont[l], gm, q, qi);        // base * g mod q
-            val = submod(addmod(s_digit[c] >= q ? s_digit[c] % q : s_digit[c], gs, q), bg, q);
+        s_g[c] = gv;
+        __syncthreads();
+        // MForm(digits) + MForm(X^slots g - base g)  (encoder.go:166-199), per RNS limb
+        for (int l = 0; l < R.n; l++) {
+            const u64 q = R.q[l], qi = R.qinvneg[l];
+            u64 val;
+            if (D.src_kind == 2) {
+                val = signed_res(gv, q);                   // noise polynomial: setCoeffSigned (prover.go:130-139)
+            } else {
+                const u64 gm = signed_res(gv, q);
+                const u64 gs = (c >= E.slots) ? signed_res(s_g[c - E.slots], q)
+                                              : submod(0, signed_res(s_g[c + JD - E.slots], q), q);
+                const u64 bg = mont64(E.base_mont[l], gm, q, qi);        // base * g mod q
+                val = submod(addmod((u64)dig[c], gs, q), bg, q);          // digits <= base < 2^31 < q
+            }
+            s_poly[l][c] = mont64(val, R.r2[l], q, qi);    // MForm
         }
-        s_poly[l][c] = mont64(val, R.r2[l], q, qi);        // MForm
+        __syncthreads();
+        for (int l0 = 0; l0 < R.n; l0 += 2) {              // NTT: two limbs at a time
+            const int l = l0 + (c >> 7);
+            if (l < R.n) ntt256(s_poly[l], R.roots + (size_t)l * JD, R.q[l], R.qinvneg[l], c & 127, 1 + (c >> 7), 128);
+        }
+        __syncthreads();
+        u64 *dst = out + (size_t)D.out_poly * R.n * JD;
+        for (int l = 0; l < R.n; l++) dst[(size_t)l * JD + c] = s_poly[l][c];
+        __syncthreads();
     }
-    __syncthreads();
-    // ---- NTT: two limbs at a time (threads 0-127 / 128-255)
-    for (int l0 = 0; l0 < R.n; l0 += 2) {
-        const int l = l0 + (c >> 7);
-        if (l < R.n) ntt256(s_poly[l], R.roots + (size_t)l * JD, R.q[l], R.qinvneg[l], c & 127, 1 + (c >> 7), 128);
-    }
-    __syncthreads();
-    u64 *dst = out + (size_t)D.out_poly * R.n * JD;
-    for (int l = 0; l < R.n; l++) dst[(size_t)l * JD + c] = s_poly[l][c];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,52 +313,94 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
 // ---------------------------------------------------------------------------------------------
 struct MatvecGeom {
     int n_limbs, O, C, K;
-    i64 key_os, key_ks, x_cs, x_ks, out_cs, out_os, add_cs, add_os;
+    i64 key_os, key_ks, key_cs, x_cs, x_ks, out_cs, out_os, add_cs, add_os;
     int accumulate;      // add the reduced sum to the existing out value
     int has_addend;
     int fold_every;      // reduce the high word mod q every this many terms (0 = never)
-    u64 q[JMAXL], qinvneg[JMAXL];
+    u64 q[JMAXL], qinvneg[JMAXL], r2[JMAXL];
 };
 
-template <int OT, int CT>
-__global__ void __launch_bounds__(128) matvec_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
-                                                     const u64 *__restrict__ x, const u64 *__restrict__ addend,
-                                                     const __grid_constant__ MatvecGeom G) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;          // limb * 256 + coeff
+// block = (32 slots, WARPS column tiles): the warps of a CTA work on the same slots and the same
+// output rows, so the key values they load are shared through L1.  Measured alternatives (B200,
+// 2^22 commit): CT = 1 per thread or 8+ column tiles per CTA run 5-10x slower (many polynomial streams
+// ~8 MB apart per SM); one column tile per CTA with 4 slot chunks is 1.3x slower (4x the key traffic).
+// The kernel is memory-latency bound (12 warps/SM, ~170 registers); the planned next step is a
+// cp.async.bulk + mbarrier ring of key/x rows in shared memory.
+//
+// Each 64x64 product is accumulated lazily, split by 32-bit halves so that no multiply needs a
+// carry-in (the carry-in form IMAD.WIDE.X runs at half rate on sm_100):
+//   S0 (96 bit)  += k0*x0      one IMAD.WIDE with carry-out + one IADD3.X
+//   S1 (64 bit)  += k0*x1 + k1*x0,   S2 (64 bit) += k1*x1     plain IMAD.WIDE (k1, x1 < 2^(bits-32))
+// FOLD: spill the high words of S1/S2 every fold_every terms (only needed for primes > ~50 bits and
+// long sums).  One Montgomery reduction per output at the end: the result is the same field element
+// as the reference's chain of MulCoeffsMontgomeryThenAdd.
+template <int OT, int CT, int WARPS, bool FOLD>
+__global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
+                                                           const u64 *__restrict__ x, const u64 *__restrict__ addend,
+                                                           const __grid_constant__ MatvecGeom G) {
+    const int slot = blockIdx.x * 32 + threadIdx.x;          // limb * 256 + coeff
     const int n_slots = G.n_limbs * JD;
-    if (slot >= n_slots) return;
-    const int o_tiles = (G.O + OT - 1) / OT;
-    const int o0 = (blockIdx.y % o_tiles) * OT, c0 = (blockIdx.y / o_tiles) * CT;
+    const int o0 = blockIdx.y * OT;
+    const int c0 = (blockIdx.z * WARPS + threadIdx.y) * CT;
+    if (slot >= n_slots || c0 >= G.C) return;
     const int limb = slot / JD;
     const u64 q = G.q[limb], qi = G.qinvneg[limb];
     const size_t pw = (size_t)n_slots;                                // words per polynomial
-    u64 lo[OT][CT], hi[OT][CT];
+    uint32_t s0a[OT][CT], s0b[OT][CT], s0c[OT][CT];
+    u64 s1[OT][CT], s2[OT][CT], s1h[OT][CT], s2h[OT][CT];
 #pragma unroll
     for (int a = 0; a < OT; a++)
 #pragma unroll
-        for (int b = 0; b < CT; b++) { lo[a][b] = 0; hi[a][b] = 0; }
+        for (int b = 0; b < CT; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = 0; s1h[a][b] = s2h[a][b] = 0; }
     int since = 0;
+    // running pointers (ragged tiles clamp to the last valid row / column; their results are not stored)
+    const u64 *xp[CT], *kp[OT][CT];
+#pragma unroll
+    for (int b = 0; b < CT; b++) {
+        const int cc = (c0 + b < G.C) ? c0 + b : G.C - 1;
+        xp[b] = x + (size_t)(cc * G.x_cs) * pw + slot;
+#pragma unroll
+        for (int a = 0; a < OT; a++) {
+            const int oo = (o0 + a < G.O) ? o0 + a : G.O - 1;
+            kp[a][b] = key + (size_t)(oo * G.key_os + cc * G.key_cs) * pw + slot;
+        }
+    }
+    const size_t x_step = (size_t)G.x_ks * pw, k_step = (size_t)G.key_ks * pw;
+    const bool key_per_col = (G.key_cs != 0);
+#pragma unroll 2
     for (int k = 0; k < G.K; k++) {
-        u64 kv[OT], xv[CT];
+        u64 kv[OT][CT], xv[CT];
 #pragma unroll
-        for (int a = 0; a < OT; a++) kv[a] = (o0 + a < G.O) ? __ldg(key + ((o0 + a) * G.key_os + k * G.key_ks) * pw + slot) : 0;
-#pragma unroll
-        for (int b = 0; b < CT; b++) xv[b] = (c0 + b < G.C) ? __ldg(x + ((c0 + b) * G.x_cs + k * G.x_ks) * pw + slot) : 0;
+        for (int b = 0; b < CT; b++) { xv[b] = __ldg(xp[b]); xp[b] += x_step; }
 #pragma unroll
         for (int a = 0; a < OT; a++)
 #pragma unroll
             for (int b = 0; b < CT; b++) {
-                const u64 pl = kv[a] * xv[b], ph = __umul64hi(kv[a], xv[b]);
-                const u64 nl = lo[a][b] + pl;
-                hi[a][b] += ph + (nl < pl);
-                lo[a][b] = nl;
+                if (!key_per_col && b > 0) { kv[a][b] = kv[a][0]; continue; }
+                kv[a][b] = __ldg(kp[a][b]);
+                kp[a][b] += k_step;
             }
-        if (G.fold_every && ++since == G.fold_every) {
+#pragma unroll
+        for (int a = 0; a < OT; a++)
+#pragma unroll
+            for (int b = 0; b < CT; b++) {
+                const uint32_t k0 = (uint32_t)kv[a][b], k1 = (uint32_t)(kv[a][b] >> 32);
+                const uint32_t x0 = (uint32_t)xv[b], x1 = (uint32_t)(xv[b] >> 32);
+                asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                    : "+r"(s0a[a][b]), "+r"(s0b[a][b]), "+r"(s0c[a][b]) : "r"(k0), "r"(x0));
+                s1[a][b] += (u64)k0 * x1;
+                s1[a][b] += (u64)k1 * x0;
+                s2[a][b] += (u64)k1 * x1;
+            }
+        if (FOLD && ++since == G.fold_every) {
             since = 0;
 #pragma unroll
             for (int a = 0; a < OT; a++)
 #pragma unroll
-                for (int b = 0; b < CT; b++) hi[a][b] %= q;
+                for (int b = 0; b < CT; b++) {
+                    s1h[a][b] += s1[a][b] >> 32; s1[a][b] &= 0xffffffffull;
+                    s2h[a][b] += s2[a][b] >> 32; s2[a][b] &= 0xffffffffull;
+                }
         }
     }
 #pragma unroll
@@ -325,14 +408,39 @@ __global__ void __launch_bounds__(128) matvec_kernel(u64 *__restrict__ out, cons
 #pragma unroll
         for (int b = 0; b < CT; b++) {
             if (o0 + a >= G.O || c0 + b >= G.C) continue;
-            u64 h = hi[a][b];
-            if (h >= q) h %= q;
-            u64 r = redc128(h, lo[a][b], q, qi);           // MulCoeffsMontgomeryThenAdd: sum a*b*2^-64 mod q
+            // T = S0 + (S1 + S1h 2^32) 2^32 + (S2 + S2h 2^32) 2^64   as three 64-bit words (w2 small)
+            u64 w0 = ((u64)s0b[a][b] << 32) | s0a[a][b], w1 = s0c[a][b], w2 = 0;
+            auto add_at32 = [&](u64 v) {       // T += v << 32
+                const u64 lo = v << 32, hi = v >> 32;
+                const u64 n0 = w0 + lo; const u64 cy = n0 < lo; w0 = n0;
+                const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
+            };
+            auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
+            add_at32(s1[a][b]);
+            add_at64(s2[a][b]);
+            if (FOLD) { add_at64(s1h[a][b]); const u64 v = s2h[a][b]; add_at64(v << 32); w2 += v >> 32; }
+            // h = (w2 2^64 + w1) mod q ;  result = (h 2^64 + w0) 2^-64 mod q
+            u64 h = w1 >= q ? w1 % q : w1;
+            if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
+            u64 r = redc128(h, w0, q, qi);                 // == sum_k key*x * 2^-64 mod q (MulCoeffsMontgomeryThenAdd chain)
             u64 *dst = out + ((c0 + b) * G.out_cs + (o0 + a) * G.out_os) * pw + slot;
             if (G.accumulate) r = addmod(r, *dst, q);
             if (G.has_addend) r = addmod(r, __ldg(addend + ((c0 + b) * G.add_cs + (o0 + a) * G.add_os) * pw + slot), q);
             *dst = r;
         }
+}
+
+// out[o] = sum_c part[c][o] mod q   (split-K reduction of the outer commit)
+__global__ void __launch_bounds__(256) reduce_cols_kernel(u64 *__restrict__ out, const u64 *__restrict__ part, int C, int O,
+                                                          const __grid_constant__ MatvecGeom G) {
+    const size_t pw = (size_t)G.n_limbs * JD;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)O * pw) return;
+    const size_t o = i / pw, slot = i % pw;
+    const u64 q = G.q[slot / JD];
+    u64 acc = 0;
+    for (int c = 0; c < C; c++) acc = addmod(acc, part[((size_t)c * O + o) * pw + slot], q);
+    out[i] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -530,21 +638,26 @@ static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi
 
 static void fill_geom_ring(MatvecGeom &G, const RingDev &R) {
     G.n_limbs = R.n;
-    for (int l = 0; l < R.n; l++) { G.q[l] = R.q[l]; G.qinvneg[l] = R.qinvneg[l]; }
-    // 128-bit accumulation of K products below q^2: fold the high word when K * q^2 could reach 2^128
+    for (int l = 0; l < R.n; l++) { G.q[l] = R.q[l]; G.qinvneg[l] = R.qinvneg[l]; G.r2[l] = R.r2[l]; }
+    // S1 receives two terms below 2^(32+hb) per product (hb = bits-32): it can take 2^(31-hb) products
     int bits = 0;
     for (int l = 0; l < R.n; l++) { int b = 64 - __builtin_clzll(R.q[l]); if (b > bits) bits = b; }
-    const int headroom = 127 - 2 * bits;                 // terms allowed = 2^headroom
-    G.fold_every = (headroom >= 20) ? 0 : (headroom < 1 ? 1 : (1 << (headroom - 1)));
-    if (G.fold_every == 0 && G.K > (1 << 20)) G.fold_every = 1 << 19;
+    const int hb = bits > 32 ? bits - 32 : 0;
+    const long long cap = 1ll << (31 - hb);
+    G.fold_every = (G.K < cap) ? 0 : (int)(cap > 1 ? cap - 1 : 1);
 }
 
 static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *addend, MatvecGeom G, const RingDev &R) {
     fill_geom_ring(G, R);
     const int n_slots = R.n * JD;
-    constexpr int OT = 4, CT = 2;
-    dim3 grid((n_slots + 127) / 128, ((G.O + OT - 1) / OT) * ((G.C + CT - 1) / CT));
-    matvec_kernel<OT, CT><<<grid, 128, 0, current_stream()>>>(out, key, x, addend, G);
+#define RS_MV(OT, CT, WARPS)                                                                                         \
+    {                                                                                                                \
+        dim3 grid((n_slots + 31) / 32, (G.O + OT - 1) / OT, (G.C + CT * WARPS - 1) / (CT * WARPS));                   \
+        if (G.fold_every) matvec_kernel<OT, CT, WARPS, true><<<grid, dim3(32, WARPS), 0, current_stream()>>>(out, key, x, addend, G); \
+        else matvec_kernel<OT, CT, WARPS, false><<<grid, dim3(32, WARPS), 0, current_stream()>>>(out, key, x, addend, G);             \
+    }
+    RS_MV(5, 2, 4)
+#undef RS_MV
     count_launch();
     RS_CUDA_CHECK(cudaGetLastError());
     return RS_OK;
@@ -562,7 +675,15 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
     for (int i = 0; i < j->p.exp; i++) E.delta_inv[i] = j->p.delta_inv[i];
     for (int l = 0; l < j->rq.n; l++) E.base_mont[l] = j->base_mont_q[l];
     FieldParams<NL> F = make_params<NL>(j->f);
-    encode_kernel<NL><<<(unsigned)n, 256, 0, current_stream()>>>(out, d_descs, vec, aux, twin_u, given, j->d_cdt, j->rq, E, F);
+    const int G = JD / j->p.slots;
+    const size_t smem = (size_t)G * JD * 4 + JD * 8 + (size_t)JMAXL * JD * 8;
+    static bool configured = false;
+    if (!configured) {
+        RS_CUDA_CHECK(cudaFuncSetAttribute(encode_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    encode_kernel<NL><<<(unsigned)((n + G - 1) / G), 256, smem, current_stream()>>>(out, d_descs, (int)n, vec, aux, twin_u, given,
+                                                                                   j->d_cdt, j->rq, E, F);
     count_launch();
     RS_CUDA_CHECK(cudaGetLastError());
     return RS_OK;
@@ -632,6 +753,7 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
     RS_REQUIRE(p->cdt_len >= 1, RS_ERR_ARG, "rs_jindo_create: bad CDT");
     rs_jindo *j = new rs_jindo();
     memset(j, 0, sizeof(*j));
+    j->cache = new std::vector<DescCache>();
     j->f = f;
     j->p = *p;
     std::vector<u64> roots((size_t)2 * (p->n_q + p->n_qout) * JD);
@@ -664,6 +786,8 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
 void rs_jindo_destroy(rs_jindo *j) {
     if (!j) return;
     cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt);
+    if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
+    cudaFree(j->d_ndescs);
     delete j;
 }
 
@@ -712,69 +836,97 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
     const int NL = j->f->NL, d = JD, slots = p.slots, rows = p.rows, cols = p.cols;
     const size_t cs = (size_t)cols * slots;
 
-    // ---- descriptors, in the order of commitColTo (prover.go:89-128)
-    std::vector<EncDesc> descs;
-    size_t twin = 0, cosac = 0, mask = 0;
-    auto add = [&](int kind, size_t off, int cnt, int nk, size_t noff, size_t col, size_t row) {
-        descs.push_back(EncDesc{kind, cnt, (i64)off, nk, (i64)(noff * d), (i64)(col * rows + row)});
-    };
-    for (int i = 0; i < cols; i++) {
-        add(1, (size_t)i * slots, slots, 1, (size_t)i, i, 0);                           // firstRow, COSAC (ecdBlindStdDev)
-    }
-    cosac = cols;
-    for (int i = 0; i < cols; i++) {
-        for (int r = 1; r < rows - 1; r++) {
-            const size_t s = (size_t)r * cs + (size_t)i * slots, e = s + slots;
-            if (s > len) break;                                                         // note '>' (prover.go:121)
-            const size_t hi = e < len ? e : len;
-            add(0, v_poly * v->rank + s, (int)(hi - s), 0, twin++, i, r);
+    // ---- descriptors, in the order of commitColTo (prover.go:89-128); cached per committed length
+    const DescCache *dc = nullptr;
+    for (auto &c : *j->cache) if (c.len == len) dc = &c;
+    if (!dc) {
+        std::vector<EncDesc> descs;
+        size_t twin = 0, cosac = 0, mask = 0;
+        auto add = [&](int kind, size_t off, int cnt, int nk, size_t noff, size_t col, size_t row) {
+            descs.push_back(EncDesc{kind, cnt, (i64)off, nk, (i64)(noff * d), (i64)(col * rows + row)});
+        };
+        for (int i = 0; i < cols; i++) add(1, (size_t)i * slots, slots, 1, (size_t)i, i, 0);   // firstRow, COSAC (ecdBlindStdDev)
+        cosac = cols;
+        for (int i = 0; i < cols; i++) {
+            for (int r = 1; r < rows - 1; r++) {
+                const size_t s0 = (size_t)r * cs + (size_t)i * slots, e0 = s0 + slots;
+                if (s0 > len) break;                                                     // note '>' (prover.go:121)
+                const size_t hi = e0 < len ? e0 : len;
+                add(0, s0, (int)(hi - s0), 0, twin++, i, r);
+            }
+            add(1, cs + (size_t)i * slots, slots, 0, twin++, i, rows - 1);               // lastRow, TwinCDT (ecdStdDev)
         }
-        add(1, cs + (size_t)i * slots, slots, 0, twin++, i, rows - 1);                  // lastRow, TwinCDT (ecdStdDev)
-    }
-    {   // mask column (prover.go:93-115): every row COSAC, fresh random elements per row
+        // mask column (prover.go:93-115): every row COSAC, fresh random elements per row
         add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, 0);
         for (int r = 1; r < rows - 1; r++) {
             if ((size_t)r * cs > len) break;
             add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, r);
         }
         add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, rows - 1);
+        DescCache nc{len, nullptr, descs.size(), twin, cosac, mask};
+        RS_CUDA_CHECK(cudaMalloc((void **)&nc.d_descs, descs.size() * sizeof(EncDesc)));
+        RS_CUDA_CHECK(cudaMemcpy(nc.d_descs, descs.data(), descs.size() * sizeof(EncDesc), cudaMemcpyHostToDevice));
+        if (j->cache->size() >= 64) { cudaFree(j->cache->front().d_descs); j->cache->erase(j->cache->begin()); }
+        j->cache->push_back(nc);
+        dc = &j->cache->back();
+    }
+    const size_t twin = dc->twin, cosac = dc->cosac, mask = dc->mask, n_descs = dc->n_descs;
+    const size_t n_noise = (size_t)(cols + 1) * (p.in_msis + p.mlwe);
+    if (!j->d_ndescs) {
+        std::vector<EncDesc> ndescs(n_noise);
+        for (size_t k = 0; k < n_noise; k++) ndescs[k] = EncDesc{2, 0, 0, 1, (i64)(k * d), (i64)k};
+        RS_CUDA_CHECK(cudaMalloc((void **)&j->d_ndescs, n_noise * sizeof(EncDesc)));
+        RS_CUDA_CHECK(cudaMemcpy(j->d_ndescs, ndescs.data(), n_noise * sizeof(EncDesc), cudaMemcpyHostToDevice));
     }
     RS_REQUIRE(tape->n_mask_rows == mask, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of mask rows");
     RS_REQUIRE(tape->n_cosac_polys == cosac, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of COSAC polynomials");
     RS_REQUIRE(tape->n_twin_u == twin * d && (twin == 0 || tape->twin_u), RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of TwinCDT draws");
 
-    rs_opening *o = nullptr;
-    int rc = opening_alloc(j, &o);
-    if (rc) return rc;
+    const bool reuse = (*open != nullptr);
+    rs_opening *o = *open;
+    int rc = RS_OK;
+    if (!reuse) {
+        rc = opening_alloc(j, &o);
+        if (rc) return rc;
+    } else {
+        RS_REQUIRE(o->j == j, RS_ERR_ARG, "rs_jindo_commit: opening belongs to another prover");
+        if (n_descs < (size_t)(cols + 1) * rows)           // rows past len(v) must read as zero polynomials
+            RS_CUDA_CHECK(cudaMemsetAsync(o->d_encode, 0, (size_t)(cols + 1) * rows * pq(j) * 8, current_stream()));
+    }
 
-    // ---- uploads
-    std::vector<uint32_t> aux((2 * cs + mask * slots) * NL);
-    memcpy(aux.data(), tape->first_row, cs * NL * 4);
-    memcpy(aux.data() + cs * NL, tape->last_row, cs * NL * 4);
-    memcpy(aux.data() + 2 * cs * NL, tape->mask_rows, mask * slots * NL * 4);
-    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr; EncDesc *d_descs = nullptr, *d_ndescs = nullptr;
-    u64 *d_com = nullptr, *d_com2 = nullptr, *d_value = nullptr;
-    const size_t n_noise = (size_t)(cols + 1) * (p.in_msis + p.mlwe);
-    std::vector<EncDesc> ndescs(n_noise);
-    for (size_t k = 0; k < n_noise; k++) ndescs[k] = EncDesc{2, 0, 0, 1, (i64)(k * d), (i64)k};
+    // ---- uploads (skipped when the tape is already device resident)
+    const bool dev = tape->on_device != 0;
+    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
+    u64 *d_com = nullptr, *d_com2 = nullptr, *d_value = nullptr, *d_part = nullptr;
+    const uint32_t *vec = v->d + v_poly * v->rank * NL;
 #define RS_TRY(x) do { rc = (x); if (rc) goto fail; } while (0)
-    RS_TRY(upload(&d_aux, aux.data(), aux.size()));
-    RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
-    RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
-    RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
-    RS_TRY(upload(&d_descs, descs.data(), descs.size()));
-    RS_TRY(upload(&d_ndescs, ndescs.data(), ndescs.size()));
+    {
+        const size_t aux_words = (2 * cs + mask * slots) * NL;
+        if (cudaMallocAsync((void **)&d_aux, aux_words * 4, current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: cudaMallocAsync failed"); goto fail; }
+        const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        cudaMemcpyAsync(d_aux, tape->first_row, cs * NL * 4, kind, current_stream());
+        cudaMemcpyAsync(d_aux + cs * NL, tape->last_row, cs * NL * 4, kind, current_stream());
+        cudaMemcpyAsync(d_aux + 2 * cs * NL, tape->mask_rows, mask * slots * NL * 4, kind, current_stream());
+    }
+    if (dev) {
+        d_twin = (u64 *)tape->twin_u; d_cosac = (i64 *)tape->cosac_g; d_mlwe_s = (i64 *)tape->mlwe;
+    } else {
+        RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
+        RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
+        RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
+    }
     {
         const size_t n_com = (size_t)(cols + 1) * p.in_msis;
         if (cudaMallocAsync((void **)&d_com, n_com * pq(j) * 8, current_stream()) != cudaSuccess ||
             cudaMallocAsync((void **)&d_com2, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess ||
+            cudaMallocAsync((void **)&d_part, (size_t)(cols + 1) * p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess ||
             cudaMallocAsync((void **)&d_value, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess) {
             rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: cudaMallocAsync failed");
             goto fail;
         }
         // ---- encodes + noise polynomials
-        RS_TRY(encode_dispatch(j, o->d_encode, d_descs, descs.size(), v->d, d_aux, d_twin, d_cosac));
-        RS_TRY(encode_dispatch(j, o->d_mlwe, d_ndescs, n_noise, v->d, d_aux, d_twin, d_mlwe_s));
+        RS_TRY(encode_dispatch(j, o->d_encode, dc->d_descs, n_descs, vec, d_aux, d_twin, d_cosac));
+        RS_TRY(encode_dispatch(j, o->d_mlwe, j->d_ndescs, n_noise, vec, d_aux, d_twin, d_mlwe_s));
         // ---- inner commit (prover.go:144-157)
         MatvecGeom G;
         memset(&G, 0, sizeof(G));
@@ -786,11 +938,21 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
         RS_TRY(launch_matvec(d_com, j->d_ck_mlwe, o->d_mlwe, o->d_mlwe + (size_t)p.mlwe * pq(j), G, j->rq));
         // ---- cut-off pipeline (prover.go:164-176)
         RS_TRY(launch_cut(j, o->d_incommit, d_com, n_com, false));
-        // ---- outer commit (prover.go:180-202)
+        // ---- outer commit (prover.go:180-202): split over the cols+1 column blocks of InCommit,
+        //      partial sums reduced mod q afterwards (same field element as the sequential sum)
         memset(&G, 0, sizeof(G));
-        G.O = p.out_msis; G.C = 1; G.K = (int)n_com;
-        G.key_os = (i64)n_com; G.key_ks = 1; G.x_cs = 0; G.x_ks = 1; G.out_cs = 0; G.out_os = 1;
-        RS_TRY(launch_matvec(d_com2, j->d_ck_out, o->d_incommit, nullptr, G, j->rqo));
+        G.O = p.out_msis; G.C = cols + 1; G.K = p.in_msis;
+        G.key_os = (i64)n_com; G.key_cs = p.in_msis; G.key_ks = 1; G.x_cs = p.in_msis; G.x_ks = 1;
+        G.out_cs = p.out_msis; G.out_os = 1;
+        RS_TRY(launch_matvec(d_part, j->d_ck_out, o->d_incommit, nullptr, G, j->rqo));
+        {
+            MatvecGeom Gr;
+            memset(&Gr, 0, sizeof(Gr));
+            fill_geom_ring(Gr, j->rqo);
+            const size_t tot = (size_t)p.out_msis * pqo(j);
+            reduce_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, current_stream()>>>(d_com2, d_part, cols + 1, p.out_msis, Gr);
+            count_launch();
+        }
         RS_TRY(launch_cut(j, d_value, d_com2, p.out_msis, true));
         if (cudaMemcpyAsync(commitment_out, d_value, (size_t)p.out_msis * pqo(j) * 8, cudaMemcpyDeviceToHost, current_stream()) != cudaSuccess ||
             cudaStreamSynchronize(current_stream()) != cudaSuccess) {
@@ -800,10 +962,11 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
     }
 fail:
 #undef RS_TRY
-    cudaFreeAsync(d_aux, current_stream()); cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream());
-    cudaFreeAsync(d_mlwe_s, current_stream()); cudaFreeAsync(d_descs, current_stream()); cudaFreeAsync(d_ndescs, current_stream());
+    cudaFreeAsync(d_aux, current_stream());
+    if (!dev) { cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); cudaFreeAsync(d_mlwe_s, current_stream()); }
+    cudaFreeAsync(d_part, current_stream());
     cudaFreeAsync(d_com, current_stream()); cudaFreeAsync(d_com2, current_stream()); cudaFreeAsync(d_value, current_stream());
-    if (rc) { rs_opening_free(o); return rc; }
+    if (rc) { if (!reuse) rs_opening_free(o); return rc; }
     *open = o;
     return RS_OK;
 }

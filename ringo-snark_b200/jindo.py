@@ -93,6 +93,12 @@ class Prover:
         check(lib().rs_jindo_commit(self.h, batch.h, poly, length, ctypes.byref(T), ctypes.byref(oh), _vp(com)))
         return com, Opening(self, oh)
 
+    def CommitInto(self, batch, poly, length, tape_struct, opening, com_out):
+        """Same call with a prebuilt rs_jindo_tape (host or device pointers) that overwrites an existing
+        Opening -- the allocation-free form used by bench.py."""
+        oh = c_vp(opening.h.value)
+        check(lib().rs_jindo_commit(self.h, batch.h, poly, length, ctypes.byref(tape_struct), ctypes.byref(oh), _vp(com_out)))
+
     def Partial(self, opening, left):
         """prover.go:281-289: returns [cols+1, n_q, 256]; index cols is PartialMask."""
         left = np.ascontiguousarray(left, dtype=np.uint64)
