@@ -1,5 +1,6 @@
 // capi.cu -- the extern "C" surface declared in include/ringo_cuda.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -108,6 +109,10 @@ static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 static int ilog2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
 static int ntt_dispatch(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse) {
+    if (!inverse && t->rr_W && 1 + 3 * t->logN <= t->rr_max_bound) {
+        const int rc = ntt_rr_run_l8(const_cast<rs_ntt *>(t), out, in, n_polys);
+        if (rc != RS_ERR_UNSUPPORTED) return rc;
+    }
     switch (t->f->NL) {
         case 4: return ntt_run_l4(t, out, in, n_polys, inverse);
         case 8: return ntt_run_l8(t, out, in, n_polys, inverse);
@@ -185,6 +190,14 @@ int rs_field_create(const uint64_t *q, int L64, rs_field **out) {
         if (i == 32 * n - 1) memcpy(f->one, t, 4 * n);
     }
     memcpy(f->r2, t, 4 * n);
+    // lazy [0, 2q) arithmetic needs 3q 2^32 + 2q < 2^(32 (n+1)); checked as 3q + 1 < 2^(32 n) (and 2q fits n limbs)
+    {
+        uint64_t c = 0; uint32_t q3[RS_MAX_NL + 1];
+        for (int k = 0; k < n; k++) { c += (uint64_t)f->q[k] * 3 + (k == 0 ? 1 : 0); q3[k] = (uint32_t)c; c >>= 32; }
+        f->lazy_ok = (c == 0) && !getenv("RS_NTT_NO_LAZY");
+        c = 0;
+        for (int k = 0; k < n; k++) { c += (uint64_t)f->q[k] * 2; f->q2[k] = (uint32_t)c; c >>= 32; }
+    }
     *out = f;
     return RS_OK;
 }
@@ -337,8 +350,63 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
     host_inverse(f, t->ninv, nm);
     if (N >= 2) host_mul(f, t->ninv_w1, t->ninv, &t->h_twinv[1 * n]);
     else memcpy(t->ninv_w1, t->ninv, 4 * n);
+    // ---- reduced-radix lazy forward path (8-limb fields with q == 1 mod 2^29)
+    t->rr_W = 0; t->d_tw_rr = nullptr; t->d_scratch = nullptr; t->scratch_words = 0;
+    std::vector<uint32_t> tw_rr;
+    if (n == 8 && (f->q[0] & ((1u << 29) - 1)) == 1 && N >= 2 && getenv("RS_NTT_RR")) {   // experimental, slower than the lazy full-radix kernels
+        int bits = 0;
+        for (int i = n - 1; i >= 0; i--) if (f->q[i]) { bits = 32 * i + (32 - __builtin_clz(f->q[i])); break; }
+        const int W = (bits + 33) / 29;
+        if (W == 8 || W == 9) {
+            auto limbs29 = [&](const uint32_t *w, int nw, uint32_t *out) {     // slice nw 32-bit words into W 29-bit limbs
+                for (int j = 0; j < W; j++) {
+                    const int bit = 29 * j, wi = bit / 32, sh = bit % 32;
+                    const uint64_t lo = wi < nw ? w[wi] : 0, hi = wi + 1 < nw ? w[wi + 1] : 0;
+                    const uint64_t v = ((hi << 32) | lo) >> sh;
+                    out[j] = (j == W - 1) ? (uint32_t)v : (uint32_t)(v & ((1u << 29) - 1));
+                }
+            };
+            uint32_t q1[10] = {0}, q2w[10] = {0}, q3[10] = {0};
+            memcpy(q1, f->q, 4 * n);
+            uint64_t c = 0;
+            for (int i = 0; i < 10; i++) { c += (uint64_t)q1[i] * 2; q2w[i] = (uint32_t)c; c >>= 32; }
+            c = 0;
+            for (int i = 0; i < 10; i++) { c += (uint64_t)q1[i] * 3; q3[i] = (uint32_t)c; c >>= 32; }
+            uint32_t m3[12];
+            limbs29(q1, 10, t->rr_q); limbs29(q2w, 10, t->rr_q2); limbs29(q3, 10, m3);
+            // 3q in limb-dominating form (rr_sub): every limb >= 2^29 - 1, same integer
+            t->rr_c3q[0] = m3[0] + (1u << 29);
+            for (int j = 1; j < W - 1; j++) t->rr_c3q[j] = m3[j] + (1u << 29) - 1;
+            t->rr_c3q[W - 1] = m3[W - 1] - 1;
+            // R' = 2^(29 W) mod q by doubling
+            uint32_t rp[RS_MAX_NL] = {1};
+            for (int i = 0; i < 29 * W; i++) {
+                uint32_t cy = 0;
+                for (int k = 0; k < n; k++) { const uint32_t nc = rp[k] >> 31; rp[k] = (rp[k] << 1) | cy; cy = nc; }
+                if (cy || geq(rp, f->q, n)) {
+                    uint64_t br = 0;
+                    for (int k = 0; k < n; k++) { const uint64_t d = (uint64_t)rp[k] - f->q[k] - br; rp[k] = (uint32_t)d; br = (d >> 63) & 1; }
+                }
+            }
+            limbs29(rp, n, t->rr_one);
+            t->rr_QZ = (t->rr_q[1] == 0) ? 1 : 0;
+            // largest lazy bound B with B * q < 2^(29 W): from the headroom bits (conservative)
+            t->rr_max_bound = 1 << (29 * W - bits);
+            t->rr_W = W;
+            tw_rr.assign(N * 12, 0);
+            for (size_t i = 1; i < N; i++) {
+                uint32_t w[RS_MAX_NL];
+                host_mul(f, w, &t->h_tw[i * n], rp);             // omega 2^256 * R' * 2^-256 = omega R' mod q
+                limbs29(w, n, &tw_rr[i * 12]);
+            }
+        }
+    }
     const size_t bytes = N * n * 4;
     cudaError_t e1 = cudaMalloc((void **)&t->d_tw, bytes), e2 = cudaMalloc((void **)&t->d_twinv, bytes);
+    if (e1 == cudaSuccess && e2 == cudaSuccess && t->rr_W) {
+        e1 = cudaMalloc((void **)&t->d_tw_rr, tw_rr.size() * 4);
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(t->d_tw_rr, tw_rr.data(), tw_rr.size() * 4, cudaMemcpyHostToDevice);
+    }
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         if (t->d_tw) cudaFree(t->d_tw);
         if (t->d_twinv) cudaFree(t->d_twinv);
@@ -354,6 +422,8 @@ void rs_ntt_destroy(rs_ntt *t) {
     if (!t) return;
     if (t->d_tw) cudaFree(t->d_tw);
     if (t->d_twinv) cudaFree(t->d_twinv);
+    if (t->d_tw_rr) cudaFree(t->d_tw_rr);
+    if (t->d_scratch) cudaFree(t->d_scratch);
     delete t;
 }
 int rs_ntt_rank_log2(const rs_ntt *t) { return t ? t->logN : RS_ERR_ARG; }

@@ -17,6 +17,8 @@ struct rs_field {
     int L64;
     int NL;          // 32-bit limbs
     int qs;          // modulus shape: 0 generic, 1: q == 1 mod 2^32, 2: q == 1 mod 2^64
+    int lazy_ok;     // 3q 2^32 + 2q < 2^(32 (NL+1)): the lazy [0, 2q) NTT arithmetic is valid
+    uint32_t q2[RS_MAX_NL];   // 2q
     uint32_t q[RS_MAX_NL];
     uint32_t qinv;   // -q^-1 mod 2^32
     uint32_t one[RS_MAX_NL];
@@ -32,6 +34,12 @@ struct rs_ntt {
     std::vector<uint32_t> h_tw, h_twinv;
     uint32_t ninv[RS_MAX_NL];
     uint32_t ninv_w1[RS_MAX_NL];
+    // reduced-radix lazy forward path (rr_field.cuh / ntt_rr.cuh); rr_W == 0: not available
+    int rr_W, rr_QZ, rr_max_bound;
+    uint32_t rr_q[12], rr_c3q[12], rr_q2[12], rr_one[12];
+    uint32_t *d_tw_rr;       // N x 12 words: omega * 2^(29 W) mod q in 29-bit limbs
+    uint32_t *d_scratch;     // lazy elements between passes (planes)
+    size_t scratch_words;
 };
 
 struct rs_batch {
@@ -55,7 +63,7 @@ void count_launch(unsigned n = 1);
 template <int NL>
 inline FieldParams<NL> make_params(const rs_field *f) {
     FieldParams<NL> F;
-    for (int i = 0; i < NL; i++) { F.q[i] = f->q[i]; F.one[i] = f->one[i]; F.r2[i] = f->r2[i]; }
+    for (int i = 0; i < NL; i++) { F.q[i] = f->q[i]; F.one[i] = f->one[i]; F.r2[i] = f->r2[i]; F.q2[i] = f->q2[i]; }
     F.qinv = f->qinv;
     return F;
 }
@@ -72,6 +80,8 @@ int ntt_run_l4(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_poly
 int ntt_run_l8(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 int ntt_run_l14(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 int ntt_run_l28(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
+// forward transform on the reduced-radix lazy kernels (8-limb fields); RS_ERR_UNSUPPORTED if not applicable
+int ntt_rr_run_l8(rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys);
 
 }  // namespace rs
 

@@ -77,6 +77,7 @@ struct FieldParams {
     uint32_t qinv;        // -q^-1 mod 2^32
     uint32_t one[NL];     // R mod q
     uint32_t r2[NL];      // R^2 mod q
+    uint32_t q2[NL];      // 2q (lazy [0, 2q) arithmetic; only meaningful when 3q < 2^(32 NL))
 };
 
 // ---------------------------------------------------------------------------
@@ -244,6 +245,140 @@ RS_HD void mont_mul(uint32_t *z, const uint32_t *x, const uint32_t *y, const Fie
     const bool keep = (borrow == 0xffffffffu);   // r < q
 #pragma unroll
     for (int k = 0; k < NL; k++) z[k] = keep ? r[k] : d[k];
+}
+
+// ---------------------------------------------------------------------------
+// Lazy [0, 2q) variants, for moduli with q < 2^(32 NL) / 3 (every jindo modulus except the
+// 128-bit one).  The NTT keeps all intermediate values in [0, 2q): the Montgomery product then
+// needs neither the overflow word `top` nor the final conditional subtraction (x < 2q, y < q give
+// x*y*R^-1 + q < 2q), which removes ~50 of the ~300 instructions of a butterfly.  Values are brought
+// back to [0, q) once, in the last stage.
+// ---------------------------------------------------------------------------
+template <int NL>
+RS_HD void mod_add_m(uint32_t *z, const uint32_t *x, const uint32_t *y, const uint32_t *mod) {
+    CC c;
+    uint32_t s[NL], d[NL], carry, borrow;
+    c.add_cc(s[0], x[0], y[0]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) c.addc_cc(s[i], x[i], y[i]);
+    c.addc(carry, 0, 0);
+    c.sub_cc(d[0], s[0], mod[0]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) c.subc_cc(d[i], s[i], mod[i]);
+    c.subc(borrow, carry, 0);
+    const bool keep = (borrow == 0xffffffffu);
+#pragma unroll
+    for (int i = 0; i < NL; i++) z[i] = keep ? s[i] : d[i];
+}
+
+template <int NL>
+RS_HD void mod_sub_m(uint32_t *z, const uint32_t *x, const uint32_t *y, const uint32_t *mod) {
+    CC c;
+    uint32_t d[NL], mask;
+    c.sub_cc(d[0], x[0], y[0]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) c.subc_cc(d[i], x[i], y[i]);
+    c.subc(mask, 0, 0);
+    c.add_cc(z[0], d[0], mod[0] & mask);
+#pragma unroll
+    for (int i = 1; i < NL - 1; i++) c.addc_cc(z[i], d[i], mod[i] & mask);
+    c.addc(z[NL - 1], d[NL - 1], mod[NL - 1] & mask);
+}
+
+// x in [0, 2 mod) -> [0, mod)
+template <int NL>
+RS_HD void cond_sub(uint32_t *x, const uint32_t *mod) {
+    CC c;
+    uint32_t d[NL], borrow;
+    c.sub_cc(d[0], x[0], mod[0]);
+#pragma unroll
+    for (int i = 1; i < NL; i++) c.subc_cc(d[i], x[i], mod[i]);
+    c.subc(borrow, 0, 0);
+    const bool keep = (borrow == 0xffffffffu);
+#pragma unroll
+    for (int i = 0; i < NL; i++) x[i] = keep ? x[i] : d[i];
+}
+
+// mont_row without the overflow word (valid while T stays below 2^(32 (NL+1)): 3q 2^32 + 2q < 2^(32(NL+1)))
+template <int NL, int QS>
+RS_HD void mont_row_nt(uint32_t *A, uint32_t *B, const uint32_t *x, uint32_t yi, const FieldParams<NL> &F, bool first) {
+    CC c;
+    if (first) {
+#pragma unroll
+        for (int j = 0; j < NL; j += 2) {
+            A[j] = mul_lo(x[j], yi);
+            A[j + 1] = mul_hi(x[j], yi);
+            B[j] = mul_lo(x[j + 1], yi);
+            B[j + 1] = mul_hi(x[j + 1], yi);
+        }
+    } else {
+        c.add_cc(A[0], A[0], B[1]);
+#pragma unroll
+        for (int j = 0; j < NL - 2; j += 2) {
+            c.madc_lo_cc(B[j], x[j + 1], yi, B[j + 2]);
+            c.madc_hi_cc(B[j + 1], x[j + 1], yi, B[j + 3]);
+        }
+        c.madc_lo_cc(B[NL - 2], x[NL - 1], yi, 0);
+        c.madc_hi_cc(B[NL - 1], x[NL - 1], yi, 0);
+        c.mad_lo_cc(A[0], x[0], yi, A[0]);
+        c.madc_hi_cc(A[1], x[0], yi, A[1]);
+#pragma unroll
+        for (int j = 2; j < NL; j += 2) {
+            c.madc_lo_cc(A[j], x[j], yi, A[j]);
+            c.madc_hi_cc(A[j + 1], x[j], yi, A[j + 1]);
+        }
+        c.addc(B[NL - 1], B[NL - 1], 0);
+    }
+    const uint32_t m = mul_lo(A[0], F.qinv);
+    if (QS >= 2) {
+        if (NL > 2) {
+            c.mad_lo_cc(B[2], m, F.q[3], B[2]);
+            c.madc_hi_cc(B[3], m, F.q[3], B[3]);
+#pragma unroll
+            for (int j = 5; j < NL; j += 2) {
+                c.madc_lo_cc(B[j - 1], m, F.q[j], B[j - 1]);
+                c.madc_hi_cc(B[j], m, F.q[j], B[j]);
+            }
+        }
+    } else {
+        c.mad_lo_cc(B[0], m, F.q[1], B[0]);
+        c.madc_hi_cc(B[1], m, F.q[1], B[1]);
+#pragma unroll
+        for (int j = 3; j < NL; j += 2) {
+            c.madc_lo_cc(B[j - 1], m, F.q[j], B[j - 1]);
+            c.madc_hi_cc(B[j], m, F.q[j], B[j]);
+        }
+    }
+    if (QS >= 1) {
+        c.add_cc(A[0], A[0], m);
+        c.addc_cc(A[1], A[1], 0);
+    } else {
+        c.mad_lo_cc(A[0], m, F.q[0], A[0]);
+        c.madc_hi_cc(A[1], m, F.q[0], A[1]);
+    }
+#pragma unroll
+    for (int j = 2; j < NL; j += 2) {
+        c.madc_lo_cc(A[j], m, F.q[j], A[j]);
+        c.madc_hi_cc(A[j + 1], m, F.q[j], A[j + 1]);
+    }
+    c.addc(B[NL - 1], B[NL - 1], 0);
+}
+
+// z = x * y * R^-1 (mod q), x in [0, 2q), y in [0, q)  ->  z in [0, 2q); no final subtraction
+template <int NL, int QS>
+RS_HD void mont_mul_lazy(uint32_t *z, const uint32_t *x, const uint32_t *y, const FieldParams<NL> &F) {
+    static_assert(NL % 2 == 0 && NL >= 2, "NL must be even");
+    uint32_t P[NL], Q[NL];
+#pragma unroll
+    for (int i = 0; i < NL; i += 2) {
+        mont_row_nt<NL, QS>(P, Q, x, y[i], F, i == 0);
+        mont_row_nt<NL, QS>(Q, P, x, y[i + 1], F, false);
+    }
+    CC c;
+    c.add_cc(z[0], P[0], Q[1]);
+#pragma unroll
+    for (int k = 1; k < NL - 1; k++) c.addc_cc(z[k], P[k], Q[k + 1]);
+    c.addc(z[NL - 1], P[NL - 1], 0);
 }
 
 }  // namespace rs

@@ -84,12 +84,35 @@ __global__ void __launch_bounds__(256) iadd_chain_kernel(unsigned long long *out
     if (s == 0x1234567ull) out[0] = s;
 }
 
+// mixed stream: independent IMAD.WIDE (fma pipe) and 3-input adds / logic ops (alu pipe), 1:1
+__global__ void __launch_bounds__(256) mixed_kernel(unsigned long long *out, uint32_t a, uint32_t b, int iters) {
+    unsigned long long acc[8];
+    uint32_t x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k] = threadIdx.x + k; x[k] = threadIdx.x * 3 + k; }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a + k), "r"(b));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[k]) : "r"(a), "r"(b + k));
+            }
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k] + x[k];
+    if (s == 0x1234567ull) out[0] = s;
+}
+
 }  // namespace rs
 
 extern "C" {
 #pragma GCC visibility push(default)
 // Returns sustained G op/s.  wide: 0 = 32-bit IMAD, 1 = IMAD.WIDE.U32 (32x32+64, no carry),
-// 2 = carry-chained IMAD.WIDE.U32.X (the Montgomery inner loop), 3 = IADD3.X carry chains.
+// 2 = carry-chained IMAD.WIDE.U32.X (the Montgomery inner loop), 3 = IADD3.X carry chains,
+// 4 = 1:1 mix of independent IMAD.WIDE.U32 and LOP3 (counts both): can the two pipes run concurrently?
 int rs_bench_imad_peak(int wide, double *gops) {
     using namespace rs;
     RS_REQUIRE(gops, RS_ERR_ARG, "rs_bench_imad_peak: null argument");
@@ -105,6 +128,7 @@ int rs_bench_imad_peak(int wide, double *gops) {
         if (wide == 1) imad_kernel<true><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
         else if (wide == 2) imad_chain_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
         else if (wide == 3) iadd_chain_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, iters);
+        else if (wide == 4) mixed_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
         else imad_kernel<false><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
         count_launch();
         RS_CUDA_CHECK(cudaEventRecord(e1, current_stream()));
@@ -115,7 +139,7 @@ int rs_bench_imad_peak(int wide, double *gops) {
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     // per inner iteration: 8 MADs (modes 0/1), 8 fused wide MADs (mode 2), 16 adds (mode 3)
-    const double ops = (double)blocks * threads * (double)iters * 16 * (wide == 3 ? 16 : 8);
+    const double ops = (double)blocks * threads * (double)iters * 16 * (wide == 3 || wide == 4 ? 16 : 8);
     *gops = ops / (best * 1e-3) / 1e9;
     return RS_OK;
 }

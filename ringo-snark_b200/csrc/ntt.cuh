@@ -106,7 +106,8 @@ __device__ __forceinline__ void load_twiddle(uint32_t *w, const uint32_t *__rest
 //   s_top : global stage index of the round's highest local bit (u-bit RR-1)
 //   hi    : index of this group among the groups of the round inside its polynomial
 //   SCALE : (inverse only) the round's last stage is stage 0 of the transform: fold N^-1 in
-template <int NL, int QS, int RR, bool INV, bool SCALE>
+//   LAZY  : values are kept in [0, 2q) (field.cuh lazy variants); the caller canonicalises at the end
+template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY>
 __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const uint32_t *__restrict__ tw,
                                             int s_top, unsigned hi, const NttConsts<NL> &C) {
     const FieldParams<NL> &F = C.F;
@@ -127,23 +128,34 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
                 if (!INV) {
                     // ntt.go:254-259   v = v*w ; u' = u+v ; v' = u-v
                     uint32_t v[NL];
-                    mont_mul<NL, QS>(v, x[u1], w, F);
-                    mod_sub<NL>(x[u1], x[u0], v, F);
-                    mod_add<NL>(x[u0], x[u0], v, F);
+                    if (LAZY) {
+                        mont_mul_lazy<NL, QS>(v, x[u1], w, F);
+                        mod_sub_m<NL>(x[u1], x[u0], v, F.q2);
+                        mod_add_m<NL>(x[u0], x[u0], v, F.q2);
+                    } else {
+                        mont_mul<NL, QS>(v, x[u1], w, F);
+                        mod_sub<NL>(x[u1], x[u0], v, F);
+                        mod_add<NL>(x[u0], x[u0], v, F);
+                    }
                 } else {
                     // ntt.go:365-370   u' = u+v ; v' = (u-v)*w
                     uint32_t d[NL];
-                    mod_sub<NL>(d, x[u0], x[u1], F);
-                    mod_add<NL>(x[u0], x[u0], x[u1], F);
+                    if (LAZY) {
+                        mod_sub_m<NL>(d, x[u0], x[u1], F.q2);
+                        mod_add_m<NL>(x[u0], x[u0], x[u1], F.q2);
+                    } else {
+                        mod_sub<NL>(d, x[u0], x[u1], F);
+                        mod_add<NL>(x[u0], x[u0], x[u1], F);
+                    }
                     if (last_scaled) {
                         // stage m = 1 with the trailing scalarMulVecTo(N^-1) (ntt.go:134-135, :242-243) folded in
                         uint32_t t[NL];
-                        mont_mul<NL, QS>(t, x[u0], C.ninv, F);
+                        if (LAZY) mont_mul_lazy<NL, QS>(t, x[u0], C.ninv, F); else mont_mul<NL, QS>(t, x[u0], C.ninv, F);
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u0][l] = t[l];
-                        mont_mul<NL, QS>(x[u1], d, C.ninv_w1, F);
+                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F); else mont_mul<NL, QS>(x[u1], d, C.ninv_w1, F);
                     } else {
-                        mont_mul<NL, QS>(x[u1], d, w, F);
+                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F); else mont_mul<NL, QS>(x[u1], d, w, F);
                     }
                 }
             }
@@ -152,7 +164,8 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
 }
 
 // rounds of one pass over the tile in shared memory
-template <int NL, int QS, int RR, bool INV, bool SCALE, int THREADS, int TS>
+//   FINAL : (LAZY only) this round contains the last stage of the transform: bring values back to [0, q)
+template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY, bool FINAL, int THREADS, int TS>
 __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restrict__ tw, const PassGeom &G,
                                           int lb, unsigned long long tile, const NttConsts<NL> &C) {
     // group geometry (see header comment): element u of group gid sits at base + u * ustride
@@ -184,9 +197,12 @@ __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restri
         uint32_t x[1 << RR][NL];
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) smem_load_elem<NL, TS>(x[u], sm, base + u * ustride);
-        radix_round<NL, QS, RR, INV, SCALE>(x, tw, s_top, hi, C);
+        radix_round<NL, QS, RR, INV, SCALE, LAZY>(x, tw, s_top, hi, C);
 #pragma unroll
-        for (int u = 0; u < (1 << RR); u++) smem_store_elem<NL, TS>(sm, base + u * ustride, x[u]);
+        for (int u = 0; u < (1 << RR); u++) {
+            if (LAZY && FINAL) cond_sub<NL>(x[u], C.F.q);
+            smem_store_elem<NL, TS>(sm, base + u * ustride, x[u]);
+        }
     }
 }
 
@@ -222,7 +238,8 @@ __device__ __forceinline__ void move_tile(uint32_t *sm, const uint32_t *gin, uin
     }
 }
 
-template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE>
+// LAST: this pass ends the transform (forward: owns stage logN-1; inverse: owns stage 0, == SCALE)
+template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE, bool LAZY, bool LAST>
 __global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ in,
                                                            const uint32_t *__restrict__ tw,
                                                            const __grid_constant__ NttConsts<NL> C,
@@ -238,17 +255,18 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *__res
     // the one partial round (K mod R stages) comes last in both directions.
     const int K = G.K;
     const int full = K / R, rem = K % R;
-    // With SCALE (inverse pass that contains stage 0) the round executed last owns stage 0.
+    // The round executed last in the LAST pass owns the final stage of the transform
+    // (inverse: stage 0 with the N^-1 scaling; lazy mode: the canonicalising subtraction).
     for (int r = 0; r < full; r++) {
         const int lb = INV ? r * R : K - (r + 1) * R;
-        if (SCALE && rem == 0 && r == full - 1) run_round<NL, QS, R, INV, SCALE, THREADS, TS>(sm, tw, G, lb, tile, C);
-        else run_round<NL, QS, R, INV, false, THREADS, TS>(sm, tw, G, lb, tile, C);
+        if (LAST && rem == 0 && r == full - 1) run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS>(sm, tw, G, lb, tile, C);
+        else run_round<NL, QS, R, INV, false, LAZY, false, THREADS, TS>(sm, tw, G, lb, tile, C);
         __syncthreads();
     }
     if (rem) {
         const int lb = INV ? full * R : 0;
-        if (R >= 2 && rem == 1) run_round<NL, QS, 1, INV, SCALE, THREADS, TS>(sm, tw, G, lb, tile, C);
-        if (R >= 3 && rem == 2) run_round<NL, QS, (R >= 3 ? 2 : 1), INV, SCALE, THREADS, TS>(sm, tw, G, lb, tile, C);
+        if (R >= 2 && rem == 1) run_round<NL, QS, 1, INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
+        if (R >= 3 && rem == 2) run_round<NL, QS, (R >= 3 ? 2 : 1), INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
         __syncthreads();
     }
     move_tile<NL, THREADS, TS, true>(sm, in, out, G, tile);

@@ -21,11 +21,11 @@ template <int NL> struct NttTuning {
     static constexpr int MINB = (NL <= 8) ? RS_NTT_MINB_SMALL : 1;
 };
 
-template <int NL, int QS, bool INV, bool SCALE>
+template <int NL, int QS, bool INV, bool LAST, bool LAZY>
 int launch_pass(const rs_ntt *t, uint32_t *out, const uint32_t *in, const NttConsts<NL> &C, const PassGeom &G,
                 unsigned long long tiles) {
     using T = NttTuning<NL>;
-    auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, T::MINB, INV, SCALE>;
+    auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, T::MINB, INV, (INV && LAST), LAZY, LAST>;
     constexpr int smem = SmemLayout<NL, T::TS>::BYTES;
     static bool configured = false;
     if (!configured) {
@@ -83,23 +83,23 @@ int ntt_run(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, 
     const unsigned long long tiles_col = (total + T::TS - 1) / T::TS;
     const unsigned long long tiles_row = total / T::TS;   // logN > LOG_TS here, so it divides
 
+    // lazy [0, 2q) arithmetic when the modulus leaves room (3q < 2^(32 NL)); compiled for <= 8 limbs
+    const bool lazy = (NL <= 8) && t->f->lazy_ok;
     const uint32_t *src = in;
-    if (!inverse) {
-        for (int p = 0; p < np; p++) {
-            const PassGeom &G = passes[p];
-            int rc = launch_pass<NL, QS, false, false>(t, out, src, C, G, G.col_major ? tiles_col : tiles_row);
-            if (rc) return rc;
-            src = out;
-        }
-    } else {
-        for (int p = np - 1; p >= 0; p--) {
-            const PassGeom &G = passes[p];
-            int rc = (G.s0 == 0)
-                         ? launch_pass<NL, QS, true, true>(t, out, src, C, G, G.col_major ? tiles_col : tiles_row)
-                         : launch_pass<NL, QS, true, false>(t, out, src, C, G, G.col_major ? tiles_col : tiles_row);
-            if (rc) return rc;
-            src = out;
-        }
+    for (int k = 0; k < np; k++) {
+        const int p = inverse ? np - 1 - k : k;
+        const PassGeom &G = passes[p];
+        const unsigned long long tiles = G.col_major ? tiles_col : tiles_row;
+        const bool last = (k == np - 1);
+        int rc;
+#define RS_PASS(INV, LAST, LAZY) launch_pass<NL, QS, INV, LAST, ((NL <= 8) && LAZY)>(t, out, src, C, G, tiles)
+        if (!inverse) rc = last ? (lazy ? RS_PASS(false, true, true) : RS_PASS(false, true, false))
+                                : (lazy ? RS_PASS(false, false, true) : RS_PASS(false, false, false));
+        else rc = last ? (lazy ? RS_PASS(true, true, true) : RS_PASS(true, true, false))
+                       : (lazy ? RS_PASS(true, false, true) : RS_PASS(true, false, false));
+#undef RS_PASS
+        if (rc) return rc;
+        src = out;
     }
     return RS_OK;
 }

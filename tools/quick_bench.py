@@ -9,7 +9,7 @@ from oracle import pyref
 rs = load_product(); L = rs.load()
 assert L.rs_init(0) == 0, L.rs_last_error()
 g = ctypes.c_double()
-for wide in (1, 0, 2, 3):
+for wide in (1, 0, 2, 3, 4):
     assert L.rs_bench_imad_peak(wide, ctypes.byref(g)) == 0
     print(f"imad peak wide={wide}: {g.value:.1f} G/s", flush=True)
 cases = [("zp255", 16, 512), ("zp128", 16, 512), ("zp255", 12, 4096), ("zp255", 14, 1024), ("zp255", 17, 256),
