@@ -1,0 +1,125 @@
+"""GPU parity for the Buckler prover's polynomial pipeline (buckler/prover.go), composed exactly as
+Prove composes it, against the oracle's composition of the same steps:
+
+  Encode            cyclic INTT at rank N into an embRank poly, zero padded   (buckler/encoder.go:32-38)
+  RandEncode        + blinding coefficient N                                  (encoder.go:50-54)
+  polyEval.NTT      cyclic NTT at embRank                                     (prover.go:128,150)
+  arithCheck        evalCircuit -> InvNTT -> QuoRemByVanishing                (prover.go:355-379, :399-404)
+  linCheck pieces   nttChecker.TransposeTo (reverse*N + negacyclic INTT), MulTo / MulSubTo / ScalarMulTo / AddTo
+                                                                              (linear.go:38-43, prover.go:406-441)
+MultCircuit constraint set of examples/mult/main.go:35-65 (N = 2^11, embRank = 4N, 128-bit field)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import pyref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rs(product):
+    L = product.load()
+    assert L.rs_init(0) == 0, L.rs_last_error()
+    return product
+
+
+def rand_vals(q, n, seed, small=None):
+    rng = np.random.default_rng(seed)
+    if small is not None:
+        return [int(x) for x in rng.integers(0, small, size=n)]
+    return [int.from_bytes(rng.bytes(24), "little") % q for _ in range(n)]
+
+
+@pytest.mark.parametrize("name,logN", [("zp128", 11), ("zp240", 10)])
+def test_prover_pipeline(rs, name, logN):
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    N = 1 << logN
+    E = 4 * N                                            # embRank = nextpow2(3N + 1) (compile.go:180)
+    lib = rs.lib()
+    u64p = rs.capi.c_u64p
+    # witnesses: X in [0,5], Y 63-bit, Z = X*Y, ternary digits of X (decomposeBase(5) = [3,1,1])
+    X = rand_vals(q, N, 1, small=6); Y = rand_vals(q, N, 2, small=1 << 62)
+    Z = [(a * b) % q for a, b in zip(X, Y)]
+    dig = {0: (0, 0, 0), 1: (0, 1, 0), 2: (0, 1, 1), 3: (1, 0, 0), 4: (1, 1, 0), 5: (1, 1, 1)}
+    W = [X, Y, Z, rand_vals(q, N, 3)] + [[dig[x][k] for x in X] for k in range(3)]
+    PW = [rand_vals(q, N, 4)]
+    blind = rand_vals(q, len(W), 5)                      # MustSetRandom of RandEncodeTo (host randomness)
+    n_w = len(W)
+    # ---- oracle composition
+    enc_o = oracle.NTT(fo, logN, False); emb_o = oracle.NTT(fo, logN + 2, False)
+    def encode_o(v, r=None):
+        c = np.zeros((E, fo.L), dtype=np.uint64)
+        c[:N] = enc_o.inv(fo.to_mont(v))
+        if r is not None:
+            c[N] = fo.to_mont([r])[0]
+            c[0] = fo.vec_sub(c[0:1], c[N:N + 1])[0]
+        return c
+    w_ecd_o = [encode_o(W[i], blind[i]) for i in range(n_w)]
+    w_ntt_o = [emb_o.fwd(c) for c in w_ecd_o]
+    pw_ntt_o = [emb_o.fwd(encode_o(PW[0]))]
+    coeffs = fo.to_mont([1, q - 1, q - 3])
+    terms = [(0, 0, -1, [1, 0]), (0, 1, -1, [2]),                                   # Y*X - Z
+             (1, 0, -1, [4, 4, 4]), (1, 1, -1, [4]), (2, 0, -1, [5, 5, 5]), (2, 1, -1, [5]),
+             (3, 0, -1, [6, 6, 6]), (3, 1, -1, [6]),                                 # w^3 - w
+             (4, 0, -1, [0]), (4, 2, -1, [4]), (4, 1, -1, [5]), (4, 1, -1, [6]),     # X - 3w0 - w1 - w2
+             (5, 0, 0, [3])]                                                         # pw * w3
+    bc = fo.to_mont(rand_vals(q, 1, 6))[0]
+    ev_o = fo.eval_circuit(pw_ntt_o, w_ntt_o, terms, coeffs, bc, E)
+    quo_o, rem_o = fo.quorem_vanishing(emb_o.inv(ev_o), N)
+    # ---- GPU composition through the C ABI
+    enc_g = rs.CyclicTransformer(fg, N); emb_g = rs.CyclicEvaluator(fg, E)
+    vals = rs.Batch(fg, n_w + 1, N).upload(np.stack([fo.to_mont(w) for w in W] + [fo.to_mont(PW[0])]))
+    ecd = rs.Batch(fg, n_w + 1, E)
+    assert lib.rs_ntt_inverse_embed(enc_g.h, ecd.h, 0, vals.h, 0, n_w + 1, 1) == 0, lib.rs_last_error()
+    # RandEncodeTo: c[N] <- r ; c[0] -= c[N]   (one-element uploads / vec ops on 1-coefficient views)
+    one = rs.Batch(fg, 2, 1)
+    for i in range(n_w):
+        one.upload(np.stack([fo.to_mont([blind[i]]), fo.to_mont([0])]).reshape(2, 1, fo.L))
+        assert lib.rs_batch_copy(ecd.h, i, N, one.h, 0, 0, 1) == 0
+        assert lib.rs_batch_copy(one.h, 1, 0, ecd.h, i, 0, 1) == 0
+        assert lib.rs_vec_sub(one.h, 1, one.h, 1, one.h, 0, 1) == 0
+        assert lib.rs_batch_copy(ecd.h, i, 0, one.h, 1, 0, 1) == 0
+    got_ecd = ecd.download()
+    for i in range(n_w):
+        assert np.array_equal(got_ecd[i], w_ecd_o[i]), ("RandEncode", i)
+    nt = rs.Batch(fg, n_w + 1, E)
+    emb_g.ntt.FwdNTTTo(nt, ecd)
+    got_ntt = nt.download()
+    for i in range(n_w):
+        assert np.array_equal(got_ntt[i], w_ntt_o[i]), ("NTT", i)
+    assert np.array_equal(got_ntt[n_w], pw_ntt_o[0])
+    wb = rs.Batch(fg, n_w, E, device_ptr=lib.rs_batch_device_ptr(nt.h), keepalive=nt)
+    pwb = rs.Batch(fg, 1, E); assert lib.rs_batch_copy(pwb.h, 0, 0, nt.h, n_w, 0, E) == 0
+    T = (rs.capi.Term * len(terms))()
+    for i, (c, co, p, ws) in enumerate(terms):
+        T[i].constraint, T[i].coeff, T[i].pw, T[i].n_w = c, co, p, len(ws)
+        for k, x in enumerate(ws):
+            T[i].w[k] = x
+    work = rs.Batch(fg, 3, E)
+    assert lib.rs_eval_circuit(work.h, 0, pwb.h, wb.h, T, len(terms), coeffs.ctypes.data_as(u64p), len(coeffs),
+                               bc.ctypes.data_as(u64p)) == 0, lib.rs_last_error()
+    assert np.array_equal(work.download(0, 1)[0], ev_o)
+    ev = work.poly(0, is_ntt=True)
+    emb_g.InvNTTTo(ev, ev)
+    quo, rem = emb_g.QuoRemByVanishing(ev, N, work.poly(1), work.poly(2))
+    assert np.array_equal(quo.Coeffs, quo_o) and np.array_equal(rem.Coeffs, rem_o)
+    # the quotient of an honest witness has degree < arithCheckMaxRank - N = 2N + 1 and rem == 0 on the mult constraint part
+    # ---- linCheck pieces: nttChecker.TransposeTo + the per-constraint MulTo / MulSubTo / ScalarMulTo / AddTo
+    neg_o = oracle.NTT(fo, logN, True); neg_g = rs.CyclotomicTransformer(fg, N)
+    lin = fo.to_mont(rand_vals(q, N, 9))
+    scale = fo.to_mont([N])[0]
+    tr_o = neg_o.inv(fo.vec_scalar_mul(lin[::-1].copy(), scale))
+    LB = rs.Batch(fg, 2, N).upload(np.stack([lin, lin]))
+    assert lib.rs_reverse_scale(LB.h, 1, LB.h, 0, scale.ctypes.data_as(u64p)) == 0
+    neg_g.InvNTTTo(LB, LB, dst_poly=1, src_poly=1, n_polys=1)
+    assert np.array_equal(LB.download(1, 1)[0], tr_o)
+    a, b, c3 = w_ntt_o[0], w_ntt_o[1], w_ntt_o[2]
+    term_o = fo.vec_sub(fo.vec_mul(a, b), fo.vec_mul(c3, a))
+    eval_o = fo.vec_add(fo.vec_scalar_mul(term_o, bc), term_o)
+    P = [work.poly(i, is_ntt=True) for i in range(3)]
+    A_, B_, C_ = nt.poly(0, True), nt.poly(1, True), nt.poly(2, True)
+    emb_g.MulTo(P[0], A_, B_); emb_g.MulSubTo(P[0], C_, A_)
+    emb_g.ScalarMulTo(P[1], P[0], bc); emb_g.AddTo(P[1], P[1], P[0])
+    assert np.array_equal(P[1].Coeffs, eval_o)

@@ -1,0 +1,60 @@
+"""CPU test of the N>1 path: world_size-2 gloo processes shard independent units, all-gather their
+(synthetic) commitments and must end with the same transcript on every rank, identical to the
+single-process order."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _unit_commitment(u, words):
+    rng = np.random.default_rng(1000 + u)
+    return rng.integers(0, 1 << 62, size=words, dtype=np.uint64)
+
+
+def _worker(rank, world, n_total, words, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from conftest import load_product
+    par = load_product().parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a, b = par.shard_range(n_total, rank, world)
+    local = np.stack([_unit_commitment(u, words) for u in range(a, b)]) if b > a else np.zeros((0, words), dtype=np.uint64)
+    full = par.all_gather_commitments(local, n_total, rank, world)
+    q.put((rank, (a, b), par.transcript_digest(full)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [7, 2, 1])
+def test_sharded_commitments_allgather(n_total, product):
+    world, words = 2, 6 * 256
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n_total) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, n_total, words, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = product.parallel.transcript_digest(np.stack([_unit_commitment(u, words) for u in range(n_total)]))
+    ranges = sorted(r[1] for r in res)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_total and ranges[0][1] == ranges[1][0]
+    assert all(r[2] == expect for r in res)
+
+
+def test_shard_range_partition(product):
+    par = product.parallel
+    for n in (0, 1, 5, 8, 513):
+        for w in (1, 2, 3, 8):
+            spans = [par.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
