@@ -83,6 +83,10 @@ size_t rs_batch_polys(const rs_batch *b);
 size_t rs_batch_rank(const rs_batch *b);
 int rs_batch_upload(rs_batch *b, size_t poly0, size_t n_polys, const uint64_t *host_aos);
 int rs_batch_download(const rs_batch *b, size_t poly0, size_t n_polys, uint64_t *host_aos);
+/* same copy without the trailing stream synchronisation (host_aos must be pinned; the caller
+ * synchronises with rs_sync) -- lets uploads, transforms and downloads of different chunks overlap
+ * on different streams */
+int rs_batch_download_async(const rs_batch *b, size_t poly0, size_t n_polys, uint64_t *host_aos);
 /* element-range copies (EncodeTo zero-padding, Coeffs[:N+1] slices, remLo/remHi moves;
  * buckler/encoder.go:32-38, buckler/prover.go:152, :443-456) */
 int rs_batch_copy(rs_batch *dst, size_t dst_poly, size_t dst_off,

@@ -73,6 +73,7 @@ _SIGS = {
     "rs_batch_rank": (c_size, [c_vp]),
     "rs_batch_upload": (ctypes.c_int, [c_vp, c_size, c_size, c_vp]),
     "rs_batch_download": (ctypes.c_int, [c_vp, c_size, c_size, c_vp]),
+    "rs_batch_download_async": (ctypes.c_int, [c_vp, c_size, c_size, c_vp]),
     "rs_batch_copy": (ctypes.c_int, [c_vp, c_size, c_size, c_vp, c_size, c_size, c_size]),
     "rs_batch_zero": (ctypes.c_int, [c_vp, c_size, c_size, c_size]),
     "rs_ntt_create": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),

@@ -257,6 +257,12 @@ int rs_batch_download(const rs_batch *b, size_t poly0, size_t n, uint64_t *host)
     RS_CUDA_CHECK(cudaStreamSynchronize(g_stream));
     return RS_OK;
 }
+int rs_batch_download_async(const rs_batch *b, size_t poly0, size_t n, uint64_t *host) {
+    RS_REQUIRE(b && host, RS_ERR_ARG, "rs_batch_download_async: null argument");
+    RS_REQUIRE(poly0 + n <= b->n_polys, RS_ERR_SHAPE, "rs_batch_download_async: poly range out of bounds");
+    RS_CUDA_CHECK(cudaMemcpyAsync(host, elem_ptr(b, poly0), n * b->rank * b->f->NL * 4, cudaMemcpyDeviceToHost, g_stream));
+    return RS_OK;
+}
 int rs_batch_copy(rs_batch *dst, size_t dp, size_t doff, const rs_batch *src, size_t sp, size_t soff, size_t n) {
     RS_REQUIRE(dst && src, RS_ERR_ARG, "rs_batch_copy: null argument");
     RS_REQUIRE(dst->f->NL == src->f->NL, RS_ERR_SHAPE, "rs_batch_copy: field mismatch");

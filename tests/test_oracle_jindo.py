@@ -87,3 +87,20 @@ def test_jindo_commit_evaluate_verify(name, N, batch):
     # decoding an encoding returns the encoded values (encoder.go:204-219)
     enc = prv.ecd.encode(vs[0][:p.slots])
     assert prv.ecd.decode(p.ringQ.intt(p.ringQ.imform(enc)))[:p.slots] == vs[0][:p.slots]
+
+
+def test_product_host_parameter_mirror_matches_oracle(product):
+    """ringo-snark_b200/jindo_host.py (inputs of the C ABI) derives the same parameters, primes, psi,
+    deltaInv and CDT tables as the oracle's restatement."""
+    JH = product.jindo_host
+    for name, N, batch in [("zp255", 1 << 22, 1), ("zp128", 16385, 12), ("zp220", 2049, 9)]:
+        q = pyref.modulus(name)
+        po = J.new_parameters(q, N, batch); ph = JH.new_parameters(q, N, batch)
+        for k in ("rows", "cols", "slots", "exp", "base", "in_msis", "mlwe", "out_msis", "log_in_cut", "log_out_cut",
+                  "q_primes", "qout_primes", "rank", "in_com_dcmp_len", "ecd_std", "mlwe_std"):
+            assert getattr(po, k) == getattr(ph, k), (name, k)
+        enc = J.Encoder(po, J.Tape(b"x"))
+        d, tables = JH.prover_inputs(ph)
+        assert d["delta_inv"] == enc.delta_inv and d["cdt_tail_lo"] == enc.twin.tail_lo
+        assert d["psi_q"] == [s.psi for s in po.ringQ.sub] and d["psi_qout"] == [s.psi for s in po.ringQOut.sub]
+        assert tables == enc.twin.tables
