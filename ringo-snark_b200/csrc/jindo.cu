@@ -430,6 +430,138 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
         }
 }
 
+// ---------------------------------------------------------------------------------------------
+// matvec_pipe_kernel: same product as matvec_kernel, with the key / x rows streamed through a
+// multi-stage shared-memory ring by cp.async (LDGSTS) so that the memory-level parallelism needed to
+// cover HBM latency lives in shared memory instead of registers.
+//   CTA tile : MS = 64 slots x OT key rows x CTC = 16 columns; 512 threads = 64 slots x 8 column pairs,
+//              10 outputs per thread.  A stage holds KS = 4 consecutive k-steps (42 KB); 3 stages.
+//   Per k-step a thread reads 5 key values (broadcast across the 8 column-pair groups) and 2 x values
+//   from shared memory and issues 10 lazy multiply-accumulates.
+// ---------------------------------------------------------------------------------------------
+constexpr int MP_MS = 64, MP_OT = 5, MP_CTC = 16, MP_KS = 4, MP_STAGES = 3, MP_THREADS = 512;
+constexpr int MP_ROWS = MP_OT + MP_CTC;                         // polynomial rows per k-step
+constexpr int MP_STAGE_WORDS = MP_KS * MP_ROWS * MP_MS;         // u64 words per stage
+constexpr int MP_SMEM_BYTES = MP_STAGES * MP_STAGE_WORDS * 8;
+
+template <bool FOLD>
+__global__ void __launch_bounds__(MP_THREADS, 1) matvec_pipe_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
+                                                                   const u64 *__restrict__ x, const u64 *__restrict__ addend,
+                                                                   const __grid_constant__ MatvecGeom G) {
+    extern __shared__ __align__(16) u64 ring[];
+    const int tx = threadIdx.x & (MP_MS - 1), ty = threadIdx.x / MP_MS;     // slot in tile, column pair
+    const int slot0 = blockIdx.x * MP_MS;
+    const int n_slots = G.n_limbs * JD;
+    const int o0 = blockIdx.y * MP_OT, cb = blockIdx.z * MP_CTC;
+    const size_t pw = (size_t)n_slots;
+    const int limb = (slot0 + tx) / JD;
+    const u64 q = G.q[limb], qi = G.qinvneg[limb];
+
+    // ---- loader: chunk id -> (k_local, row, 16-byte piece); rows 0..OT-1 are key rows, the rest x columns
+    constexpr int PIECES = MP_MS / 2;                               // 16-byte pieces per row
+    constexpr int CHUNKS = MP_KS * MP_ROWS * PIECES;
+    auto load_stage = [&](int it, int buf) {
+        u64 *dst = ring + (size_t)buf * MP_STAGE_WORDS;
+        for (int ch = threadIdx.x; ch < CHUNKS; ch += MP_THREADS) {
+            const int piece = ch % PIECES, row = (ch / PIECES) % MP_ROWS, kl = ch / (PIECES * MP_ROWS);
+            int k = it * MP_KS + kl;
+            if (k >= G.K) k = G.K - 1;                              // tail: harmless duplicate, not accumulated
+            const u64 *src;
+            if (row < MP_OT) {
+                const int oo = (o0 + row < G.O) ? o0 + row : G.O - 1;
+                // key may depend on the column block (outer commit: key_cs != 0 requires CTC == 1 handling -> host uses matvec_kernel)
+                src = key + (size_t)(oo * G.key_os + k * G.key_ks) * pw;
+            } else {
+                const int cc = (cb + row - MP_OT < G.C) ? cb + row - MP_OT : G.C - 1;
+                src = x + (size_t)(cc * G.x_cs + k * G.x_ks) * pw;
+            }
+            src += slot0 + piece * 2;
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + ((size_t)kl * MP_ROWS + row) * MP_MS + piece * 2);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    uint32_t s0a[MP_OT][2], s0b[MP_OT][2], s0c[MP_OT][2];
+    u64 s1[MP_OT][2], s2[MP_OT][2], s1h[MP_OT][2], s2h[MP_OT][2];
+#pragma unroll
+    for (int a = 0; a < MP_OT; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = 0; s1h[a][b] = s2h[a][b] = 0; }
+
+    const int n_it = (G.K + MP_KS - 1) / MP_KS;
+    for (int st = 0; st < MP_STAGES - 1; st++) {
+        if (st < n_it) load_stage(st, st); else asm volatile("cp.async.commit_group;");
+    }
+    int since = 0;
+    for (int it = 0; it < n_it; it++) {
+        // keep STAGES-1 groups in flight: issue the load for iteration it + STAGES - 1 into the buffer freed last round
+        if (it + MP_STAGES - 1 < n_it) load_stage(it + MP_STAGES - 1, (it + MP_STAGES - 1) % MP_STAGES);
+        else asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group %0;" ::"n"(MP_STAGES - 1));
+        __syncthreads();
+        const u64 *buf = ring + (size_t)(it % MP_STAGES) * MP_STAGE_WORDS;
+#pragma unroll
+        for (int kl = 0; kl < MP_KS; kl++) {
+            if (it * MP_KS + kl >= G.K) break;
+            const u64 *rowp = buf + (size_t)kl * MP_ROWS * MP_MS + tx;
+            u64 kv[MP_OT], xv[2];
+#pragma unroll
+            for (int a = 0; a < MP_OT; a++) kv[a] = rowp[a * MP_MS];
+#pragma unroll
+            for (int b = 0; b < 2; b++) xv[b] = rowp[(MP_OT + ty * 2 + b) * MP_MS];
+#pragma unroll
+            for (int a = 0; a < MP_OT; a++)
+#pragma unroll
+                for (int b = 0; b < 2; b++) {
+                    const uint32_t k0 = (uint32_t)kv[a], k1 = (uint32_t)(kv[a] >> 32);
+                    const uint32_t x0 = (uint32_t)xv[b], x1 = (uint32_t)(xv[b] >> 32);
+                    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                        : "+r"(s0a[a][b]), "+r"(s0b[a][b]), "+r"(s0c[a][b]) : "r"(k0), "r"(x0));
+                    s1[a][b] += (u64)k0 * x1;
+                    s1[a][b] += (u64)k1 * x0;
+                    s2[a][b] += (u64)k1 * x1;
+                }
+            if (FOLD && ++since == G.fold_every) {
+                since = 0;
+#pragma unroll
+                for (int a = 0; a < MP_OT; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        s1h[a][b] += s1[a][b] >> 32; s1[a][b] &= 0xffffffffull;
+                        s2h[a][b] += s2[a][b] >> 32; s2[a][b] &= 0xffffffffull;
+                    }
+            }
+        }
+        __syncthreads();                                            // the buffer may be overwritten next round
+    }
+    const int slot = slot0 + tx;
+#pragma unroll
+    for (int a = 0; a < MP_OT; a++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const int oo = o0 + a, cc = cb + ty * 2 + b;
+            if (oo >= G.O || cc >= G.C) continue;
+            u64 w0 = ((u64)s0b[a][b] << 32) | s0a[a][b], w1 = s0c[a][b], w2 = 0;
+            auto add_at32 = [&](u64 v) {
+                const u64 lo = v << 32, hi = v >> 32;
+                const u64 n0 = w0 + lo; const u64 cy = n0 < lo; w0 = n0;
+                const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
+            };
+            auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
+            add_at32(s1[a][b]);
+            add_at64(s2[a][b]);
+            if (FOLD) { add_at64(s1h[a][b]); const u64 v = s2h[a][b]; add_at64(v << 32); w2 += v >> 32; }
+            u64 h = w1 >= q ? w1 % q : w1;
+            if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
+            u64 r = redc128(h, w0, q, qi);
+            u64 *dst = out + ((size_t)cc * G.out_cs + (size_t)oo * G.out_os) * pw + slot;
+            if (G.accumulate) r = addmod(r, *dst, q);
+            if (G.has_addend) r = addmod(r, __ldg(addend + ((size_t)cc * G.add_cs + (size_t)oo * G.add_os) * pw + slot), q);
+            *dst = r;
+        }
+}
+
 // out[o] = sum_c part[c][o] mod q   (split-K reduction of the outer commit)
 __global__ void __launch_bounds__(256) reduce_cols_kernel(u64 *__restrict__ out, const u64 *__restrict__ part, int C, int O,
                                                           const __grid_constant__ MatvecGeom G) {
@@ -650,6 +782,21 @@ static void fill_geom_ring(MatvecGeom &G, const RingDev &R) {
 static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *addend, MatvecGeom G, const RingDev &R) {
     fill_geom_ring(G, R);
     const int n_slots = R.n * JD;
+    // large products (inner commit, Partial, responses): shared-memory ring version
+    if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !getenv("RS_MV_NOPIPE")) {
+        static bool configured = false;
+        if (!configured) {
+            RS_CUDA_CHECK(cudaFuncSetAttribute(matvec_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_SMEM_BYTES));
+            RS_CUDA_CHECK(cudaFuncSetAttribute(matvec_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_SMEM_BYTES));
+            configured = true;
+        }
+        dim3 grid(n_slots / MP_MS, (G.O + MP_OT - 1) / MP_OT, (G.C + MP_CTC - 1) / MP_CTC);
+        if (G.fold_every) matvec_pipe_kernel<true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(out, key, x, addend, G);
+        else matvec_pipe_kernel<false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(out, key, x, addend, G);
+        count_launch();
+        RS_CUDA_CHECK(cudaGetLastError());
+        return RS_OK;
+    }
 #define RS_MV(OT, CT, WARPS)                                                                                         \
     {                                                                                                                \
         dim3 grid((n_slots + 31) / 32, (G.O + OT - 1) / OT, (G.C + CT * WARPS - 1) / (CT * WARPS));                   \
