@@ -36,6 +36,8 @@ struct RingDev {
     u64 ninv[JMAXL];        // d^-1 mod q, plain (INTT scale that also leaves Montgomery form)
     const u64 *roots;       // [limb][d]  psi^brv(j) * 2^64 mod q   (forward twiddles)
     const u64 *roots_inv;   // [limb][d]  psi^-brv(j) * 2^64 mod q
+    const u64 *roots_plain; // [limb][d]  psi^brv(j) mod q             (Shoup butterflies of the warp NTT)
+    const u64 *roots_shoup; // [limb][d]  floor(psi^brv(j) * 2^64 / q)
 };
 
 struct CrtDev {             // RNSReconstructor constants of the *source* ring (rns.go:33-55)
@@ -140,6 +142,73 @@ __device__ __forceinline__ void intt256(u64 *a, const u64 *__restrict__ roots_in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Warp-level 256-point forward NTT (one warp, 8 coefficients per lane, radix-8 / radix-8 / radix-4
+// rounds in registers with two shared-memory exchanges, no block barrier).  Same transform as ntt256
+// ([lattigo] Cooley-Tukey, psi powers in bit-reversed order); butterflies are Harvey-lazy with Shoup
+// constants: w' = floor(w 2^64 / q), x*w mod q = x*w - hi(x*w')*q in [0, 2q); values stay in [0, 4q)
+// (q < 2^62) and are reduced to [0, q) at the end, so the output equals ntt256's bit for bit.
+// The polynomial sits in shared memory with 4 pad elements per 32 (index j + (j >> 5) * 4).
+// ---------------------------------------------------------------------------------------------
+constexpr int NTTW_STRIDE = JD + (JD / 32) * 4;           // padded length of one limb polynomial
+__device__ __forceinline__ int nttw_idx(int j) { return j + ((j >> 5) << 2); }
+
+__device__ __forceinline__ void harvey_bfly(u64 &X, u64 &Y, u64 w, u64 ws, u64 q, u64 q2) {
+    const u64 x = X >= q2 ? X - q2 : X;                    // [0, 2q)
+    const u64 qe = __umul64hi(Y, ws);
+    const u64 t = Y * w - qe * q;                          // [0, 2q)
+    X = x + t;
+    Y = x - t + q2;
+}
+
+__device__ __forceinline__ void ntt256_warp(u64 *a, const u64 *__restrict__ rp, const u64 *__restrict__ rs, u64 q, int lane) {
+    const u64 q2 = 2 * q;
+    u64 v[8];
+    // round 1: stages t = 128, 64, 32 on elements j = u*32 + lane
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = a[nttw_idx(u * 32 + lane)];
+#pragma unroll
+    for (int u = 0; u < 4; u++) harvey_bfly(v[u], v[u + 4], __ldg(rp + 1), __ldg(rs + 1), q, q2);
+#pragma unroll
+    for (int u = 0; u < 8; u++) if ((u & 2) == 0) harvey_bfly(v[u], v[u + 2], __ldg(rp + 2 + (u >> 2)), __ldg(rs + 2 + (u >> 2)), q, q2);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) harvey_bfly(v[u], v[u + 1], __ldg(rp + 4 + (u >> 1)), __ldg(rs + 4 + (u >> 1)), q, q2);
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[nttw_idx(u * 32 + lane)] = v[u];
+    __syncwarp();
+    // round 2: stages t = 16, 8, 4 on elements j = hi*32 + u*4 + lo, hi = lane >> 2, lo = lane & 3
+    const int hi = lane >> 2, lo = lane & 3;
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = a[nttw_idx(hi * 32 + u * 4 + lo)];
+    {
+        const u64 w = __ldg(rp + 8 + hi), ws = __ldg(rs + 8 + hi);
+#pragma unroll
+        for (int u = 0; u < 4; u++) harvey_bfly(v[u], v[u + 4], w, ws, q, q2);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) if ((u & 2) == 0) harvey_bfly(v[u], v[u + 2], __ldg(rp + 16 + hi * 2 + (u >> 2)), __ldg(rs + 16 + hi * 2 + (u >> 2)), q, q2);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) harvey_bfly(v[u], v[u + 1], __ldg(rp + 32 + hi * 4 + (u >> 1)), __ldg(rs + 32 + hi * 4 + (u >> 1)), q, q2);
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[nttw_idx(hi * 32 + u * 4 + lo)] = v[u];
+    __syncwarp();
+    // round 3: stages t = 2, 1 on the 8 consecutive elements j = lane*8 + u
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = a[nttw_idx(lane * 8 + u)];
+#pragma unroll
+    for (int u = 0; u < 8; u++) if ((u & 2) == 0) harvey_bfly(v[u], v[u + 2], __ldg(rp + 64 + lane * 2 + (u >> 2)), __ldg(rs + 64 + lane * 2 + (u >> 2)), q, q2);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) harvey_bfly(v[u], v[u + 1], __ldg(rp + 128 + lane * 4 + (u >> 1)), __ldg(rs + 128 + lane * 4 + (u >> 1)), q, q2);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        u64 x = v[u];
+        x = x >= q2 ? x - q2 : x;
+        x = x >= q ? x - q : x;
+        a[nttw_idx(lane * 8 + u)] = x;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
 // encode kernel
 // ---------------------------------------------------------------------------------------------
 struct EncDesc {
@@ -152,7 +221,8 @@ struct EncDesc {
 };
 
 struct EncConsts {
-    int slots, exp, cdt_len;
+    int slots, exp, cdt_len, group;   // group: polynomials per CTA
+    int subgroup, cdt_pow2;           // polynomials per NTT staging round; largest power of two <= cdt_len
     u64 base, base_magic;       // base_magic = floor(2^64 / base) + 1  (base is not a power of two)
     i64 tail_lo;
     double sigma;
@@ -171,11 +241,11 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                                                      const __grid_constant__ EncConsts E,
                                                      const __grid_constant__ FieldParams<NL> F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: digits [G][256] u32 | g [256] i64 | poly [JMAXL][256] u64
-    const int G = JD / E.slots;
+    // layout: digits [G][256] u32 | g [2][256] i64 | poly [G * limbs][NTTW_STRIDE] u64
+    const int G = E.group;
     uint32_t *s_dig = reinterpret_cast<uint32_t *>(smem_raw);
-    i64 *s_g = reinterpret_cast<i64 *>(smem_raw + (size_t)G * JD * 4);
-    u64(*s_poly)[JD] = reinterpret_cast<u64(*)[JD]>(smem_raw + (size_t)G * JD * 4 + JD * 8);
+    i64 *s_gbuf = reinterpret_cast<i64 *>(smem_raw + (size_t)G * JD * 4);
+    u64 *s_poly = reinterpret_cast<u64 *>(smem_raw + (size_t)G * JD * 4 + 2 * JD * 8);
     const int c = threadIdx.x;
     const int d0 = blockIdx.x * G;
 
@@ -184,7 +254,7 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
     __syncthreads();
     {
         const int g = c / E.slots, i = c % E.slots;
-        if (d0 + g < n_descs) {
+        if (g < G && d0 + g < n_descs) {
             const EncDesc D = descs[d0 + g];
             if (D.src_kind != 2 && i < D.cnt) {
                 const uint32_t *src = (D.src_kind == 0 ? vec : aux) + (size_t)(D.src_off + i) * NL;
@@ -214,10 +284,17 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
     }
     __syncthreads();
 
-    // ---- phase 2
-    for (int g = 0; g < G && d0 + g < n_descs; g++) {
+    // Phase 2 runs in sub-groups of SG polynomials so that the NTT staging buffer stays small
+    // (shared memory per CTA ~40 KB: 4-5 CTAs per SM and room in L1 for the TwinCDT tables).
+    const int SG = E.subgroup;
+    const int n_poly = (n_descs - d0 < G) ? n_descs - d0 : G;
+    for (int g0 = 0; g0 < n_poly; g0 += SG) {
+    const int g1 = (g0 + SG < n_poly) ? g0 + SG : n_poly;
+    // ---- phase 2a: per polynomial, one thread per coefficient: centre, sample, combine -> s_poly
+    for (int g = g0; g < g1; g++) {
         const EncDesc D = descs[d0 + g];
         const uint32_t *dig = s_dig + g * JD;
+        i64 *s_g = s_gbuf + (g & 1) * JD;
         i64 gv;
         if (D.noise_kind == 1) {
             gv = given[D.noise_off + c];
@@ -238,17 +315,22 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             const double sc = __dmul_rn(128.0, cfrac);
             const int c0 = (int)(((i64)floor(sc)) % 128), c1 = (int)(((i64)ceil(sc)) % 128);
             const u64 u = __ldg(twin_u + D.noise_off + c);
+            // slices.BinarySearch on both tables at once (branch-free lower bound: number of entries < u),
+            // minus one on an exact hit (gaussian_twin_cdt.go:86-93)
             int v[2];
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const u64 *tab = cdt + (size_t)(k ? c1 : c0) * E.cdt_len;
-                int lo = 0, hi = E.cdt_len;
-                while (lo < hi) {                          // slices.BinarySearch: leftmost index with tab >= u
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(tab + mid) < u) lo = mid + 1; else hi = mid;
+            {
+                const u64 *t0 = cdt + (size_t)c0 * E.cdt_len, *t1 = cdt + (size_t)c1 * E.cdt_len;
+                int l0 = 0, l1 = 0;
+                for (int half = E.cdt_pow2; half >= 1; half >>= 1) {
+                    const int p0 = l0 + half, p1 = l1 + half;
+                    const u64 a0 = (p0 <= E.cdt_len) ? __ldg(t0 + p0 - 1) : ~0ull;
+                    const u64 a1 = (p1 <= E.cdt_len) ? __ldg(t1 + p1 - 1) : ~0ull;
+                    if (p0 <= E.cdt_len && a0 < u) l0 = p0;
+                    if (p1 <= E.cdt_len && a1 < u) l1 = p1;
                 }
-                if (lo < E.cdt_len && __ldg(tab + lo) == u) lo -= 1;
-                v[k] = lo;
+                if (l0 < E.cdt_len && __ldg(t0 + l0) == u) l0 -= 1;
+                if (l1 < E.cdt_len && __ldg(t1 + l1) == u) l1 -= 1;
+                v[0] = l0; v[1] = l1;
             }
             // Slow path (gaussian_twin_cdt.go:95-110): CDF at v0 for the exact centre.  ~1% of the samples
             // take it; the warp serves its slow lanes one at a time, all 32 lanes evaluating the terms
@@ -292,18 +374,24 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                 const u64 bg = mont64(E.base_mont[l], gm, q, qi);        // base * g mod q
                 val = submod(addmod((u64)dig[c], gs, q), bg, q);          // digits <= base < 2^31 < q
             }
-            s_poly[l][c] = mont64(val, R.r2[l], q, qi);    // MForm
+            s_poly[(size_t)((g - g0) * R.n + l) * NTTW_STRIDE + nttw_idx(c)] = mont64(val, R.r2[l], q, qi);    // MForm
         }
-        __syncthreads();
-        for (int l0 = 0; l0 < R.n; l0 += 2) {              // NTT: two limbs at a time
-            const int l = l0 + (c >> 7);
-            if (l < R.n) ntt256(s_poly[l], R.roots + (size_t)l * JD, R.q[l], R.qinvneg[l], c & 127, 1 + (c >> 7), 128);
-        }
-        __syncthreads();
-        u64 *dst = out + (size_t)D.out_poly * R.n * JD;
-        for (int l = 0; l < R.n; l++) dst[(size_t)l * JD + c] = s_poly[l][c];
-        __syncthreads();
     }
+    __syncthreads();
+    // ---- phase 2b: one warp per (polynomial, limb): 256-point NTT in registers, then the coalesced store
+    {
+        const int warp = c >> 5, lane = c & 31;
+        for (int task = warp; task < (g1 - g0) * R.n; task += 8) {
+            const int g = g0 + task / R.n, l = task % R.n;
+            u64 *a = s_poly + (size_t)task * NTTW_STRIDE;
+            ntt256_warp(a, R.roots_plain + (size_t)l * JD, R.roots_shoup + (size_t)l * JD, R.q[l], lane);
+            u64 *dst = out + ((size_t)descs[d0 + g].out_poly * R.n + l) * JD;
+#pragma unroll
+            for (int u = 0; u < 8; u++) dst[u * 32 + lane] = a[nttw_idx(u * 32 + lane)];
+        }
+    }
+    __syncthreads();
+    }   // sub-groups
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -729,7 +817,7 @@ static u64 mw_mod_word(const u64 *a, u64 q) {
     return (u64)r;
 }
 
-static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi, u64 *h_roots /* 2*n*JD */) {
+static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi, u64 *h_roots /* 4*n*JD */) {
     memset(&R, 0, sizeof(R));
     memset(&C, 0, sizeof(C));
     R.n = n;
@@ -750,6 +838,8 @@ static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi
             const u64 b = h_brv(j, 8);
             h_roots[(size_t)l * JD + b] = h_mulmod(pw, r1, ql);
             h_roots[(size_t)(n + l) * JD + b] = h_mulmod(pwi, r1, ql);
+            h_roots[(size_t)(2 * n + l) * JD + b] = pw;
+            h_roots[(size_t)(3 * n + l) * JD + b] = (u64)((((u128)pw) << 64) / ql);
             pw = h_mulmod(pw, psi[l], ql);
             pwi = h_mulmod(pwi, psi_inv, ql);
         }
@@ -822,8 +912,14 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
     for (int i = 0; i < j->p.exp; i++) E.delta_inv[i] = j->p.delta_inv[i];
     for (int l = 0; l < j->rq.n; l++) E.base_mont[l] = j->base_mont_q[l];
     FieldParams<NL> F = make_params<NL>(j->f);
-    const int G = JD / j->p.slots;
-    const size_t smem = (size_t)G * JD * 4 + JD * 8 + (size_t)JMAXL * JD * 8;
+    int G = JD / j->p.slots;
+    if (G > 16) G = 16;
+    E.group = G;
+    E.subgroup = 8 / j->rq.n > 0 ? 8 / j->rq.n : 1;
+    if (E.subgroup > G) E.subgroup = G;
+    E.cdt_pow2 = 1;
+    while (E.cdt_pow2 * 2 <= E.cdt_len) E.cdt_pow2 *= 2;
+    const size_t smem = (size_t)G * JD * 4 + 2 * JD * 8 + (size_t)E.subgroup * j->rq.n * NTTW_STRIDE * 8;
     static bool configured = false;
     if (!configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(encode_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -903,8 +999,8 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
     j->cache = new std::vector<DescCache>();
     j->f = f;
     j->p = *p;
-    std::vector<u64> roots((size_t)2 * (p->n_q + p->n_qout) * JD);
-    u64 *rq_h = roots.data(), *rqo_h = roots.data() + (size_t)2 * p->n_q * JD;
+    std::vector<u64> roots((size_t)4 * (p->n_q + p->n_qout) * JD);
+    u64 *rq_h = roots.data(), *rqo_h = roots.data() + (size_t)4 * p->n_q * JD;
     int rc = ring_setup(j->rq, j->crt_q, p->n_q, (const u64 *)p->q, (const u64 *)p->psi_q, rq_h);
     if (rc == RS_OK) rc = ring_setup(j->rqo, j->crt_qo, p->n_qout, (const u64 *)p->qout, (const u64 *)p->psi_qout, rqo_h);
     if (rc != RS_OK) { delete j; return rc; }
@@ -924,8 +1020,12 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
     if (e != cudaSuccess) { rs_jindo_destroy(j); return set_error(RS_ERR_CUDA, "rs_jindo_create: %s", cudaGetErrorString(e)); }
     j->rq.roots = j->d_roots;
     j->rq.roots_inv = j->d_roots + (size_t)p->n_q * JD;
-    j->rqo.roots = j->d_roots + (size_t)2 * p->n_q * JD;
+    j->rq.roots_plain = j->d_roots + (size_t)2 * p->n_q * JD;
+    j->rq.roots_shoup = j->d_roots + (size_t)3 * p->n_q * JD;
+    j->rqo.roots = j->d_roots + (size_t)4 * p->n_q * JD;
     j->rqo.roots_inv = j->rqo.roots + (size_t)p->n_qout * JD;
+    j->rqo.roots_plain = j->rqo.roots + (size_t)2 * p->n_qout * JD;
+    j->rqo.roots_shoup = j->rqo.roots + (size_t)3 * p->n_qout * JD;
     *out = j;
     return RS_OK;
 }
