@@ -241,11 +241,11 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                                                      const __grid_constant__ EncConsts E,
                                                      const __grid_constant__ FieldParams<NL> F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: digits [G][256] u32 | g [2][256] i64 | poly [G * limbs][NTTW_STRIDE] u64
+    // layout: digits [G][256] u32 | g [SG][256] i64 | poly [SG * limbs][NTTW_STRIDE] u64
     const int G = E.group;
     uint32_t *s_dig = reinterpret_cast<uint32_t *>(smem_raw);
     i64 *s_gbuf = reinterpret_cast<i64 *>(smem_raw + (size_t)G * JD * 4);
-    u64 *s_poly = reinterpret_cast<u64 *>(smem_raw + (size_t)G * JD * 4 + 2 * JD * 8);
+    u64 *s_poly = reinterpret_cast<u64 *>(smem_raw + (size_t)G * JD * 4 + (size_t)E.subgroup * JD * 8);
     const int c = threadIdx.x;
     const int d0 = blockIdx.x * G;
 
@@ -290,11 +290,12 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
     const int n_poly = (n_descs - d0 < G) ? n_descs - d0 : G;
     for (int g0 = 0; g0 < n_poly; g0 += SG) {
     const int g1 = (g0 + SG < n_poly) ? g0 + SG : n_poly;
-    // ---- phase 2a: per polynomial, one thread per coefficient: centre, sample, combine -> s_poly
+    // ---- phase 2a: one thread per coefficient.  First the Gaussian vectors of all SG polynomials
+    //      (no barrier in between), then one barrier, then the combination into s_poly.
     for (int g = g0; g < g1; g++) {
         const EncDesc D = descs[d0 + g];
         const uint32_t *dig = s_dig + g * JD;
-        i64 *s_g = s_gbuf + (g & 1) * JD;
+        i64 *s_g = s_gbuf + (g - g0) * JD;
         i64 gv;
         if (D.noise_kind == 1) {
             gv = given[D.noise_off + c];
@@ -360,7 +361,13 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             gv = (i64)pick + (i64)cfloor + E.tail_lo;
         }
         s_g[c] = gv;
-        __syncthreads();
+    }
+    __syncthreads();
+    for (int g = g0; g < g1; g++) {
+        const EncDesc D = descs[d0 + g];
+        const uint32_t *dig = s_dig + g * JD;
+        const i64 *s_g = s_gbuf + (g - g0) * JD;
+        const i64 gv = s_g[c];
         // MForm(digits) + MForm(X^slots g - base g)  (encoder.go:166-199), per RNS limb
         for (int l = 0; l < R.n; l++) {
             const u64 q = R.q[l], qi = R.qinvneg[l];
@@ -919,7 +926,7 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
     if (E.subgroup > G) E.subgroup = G;
     E.cdt_pow2 = 1;
     while (E.cdt_pow2 * 2 <= E.cdt_len) E.cdt_pow2 *= 2;
-    const size_t smem = (size_t)G * JD * 4 + 2 * JD * 8 + (size_t)E.subgroup * j->rq.n * NTTW_STRIDE * 8;
+    const size_t smem = (size_t)G * JD * 4 + (size_t)E.subgroup * JD * 8 + (size_t)E.subgroup * j->rq.n * NTTW_STRIDE * 8;
     static bool configured = false;
     if (!configured) {
         RS_CUDA_CHECK(cudaFuncSetAttribute(encode_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
