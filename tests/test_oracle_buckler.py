@@ -1,0 +1,72 @@
+"""CPU test of the Buckler oracle: the reference's own check (buckler/buckler_test.go:82-99),
+Verify(Prove(circuit)) == true, on the restatement -- for PublicKeyCircuit (the reference's test
+circuit, zp220) and MultCircuit (examples/mult, the 128-bit field), plus a rejected bad witness."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import buckler_ref as B, jindo_ref as J, pyref
+
+
+def mult_witness(q, N, seed):
+    f = oracle.Field(q)
+    rng = random.Random(seed)
+    ntt = oracle.NTT(f, N.bit_length() - 1, True)
+    X = [rng.randrange(6) for _ in range(N)]                       # |X| <= 5 (examples/mult/main.go:75-78)
+    Y = [rng.getrandbits(63) for _ in range(N)]
+    Xn = ntt.fwd(f.to_mont(X)); Yn = ntt.fwd(f.to_mont(Y))
+    Zn = f.vec_mul(Xn, Yn)
+    Z = ntt.inv(Zn)
+    g = lambda a: f.from_mont(a)
+    return [g(Yn)], [X, g(Z), g(Xn), g(Zn)]
+
+
+def pk_witness(q, N, seed):
+    f = oracle.Field(q)
+    rng = random.Random(seed)
+    ntt = oracle.NTT(f, N.bit_length() - 1, True)
+    sk = [rng.randrange(3) - 1 for _ in range(N)]; noise = [rng.randrange(3) - 1 for _ in range(N)]
+    skn = ntt.fwd(f.to_mont(sk)); nn = ntt.fwd(f.to_mont(noise))
+    pk0 = f.to_mont([rng.randrange(q) for _ in range(N)])
+    pk1 = f.vec_add(f.vec_mul(pk0, skn), nn)
+    g = lambda a: f.from_mont(a)
+    return [g(pk0), g(pk1)], [[x % q for x in sk], g(skn), [x % q for x in noise], g(nn)]
+
+
+@pytest.mark.parametrize("circuit,name,N", [("pk", "zp220", 256), ("mult", "zp128", 256)])
+def test_prove_verify(circuit, name, N):
+    q = pyref.modulus(name)
+    define, n_pw, n_w = (B.public_key_circuit if circuit == "pk" else B.mult_circuit)(N)
+    tape = J.Tape(b"buckler-" + circuit.encode())
+    C = B.compile_circuit(q, N, define, n_pw, n_w, b"Buckler!", tape)
+    pw, w = (pk_witness if circuit == "pk" else mult_witness)(q, N, 3)
+    pf = B.Prover(C, tape).prove(pw, w)
+    assert len(pf["Witness"]) == C.ctx.batch() == len(pf["Evals"])
+    assert B.Verifier(C).verify(pw, pf)
+    # a witness violating the arithmetic constraint is rejected
+    w_bad = [list(v) for v in w]
+    w_bad[3][5] = (w_bad[3][5] + 1) % q
+    pf_bad = B.Prover(C, tape).prove(pw, w_bad)
+    assert not B.Verifier(C).verify(pw, pf_bad)
+    # a proof does not verify against other public inputs
+    pw2 = [list(v) for v in pw]; pw2[0][0] = (pw2[0][0] + 1) % q
+    assert not B.Verifier(C).verify(pw2, pf)
+
+
+def test_context_metadata_matches_survey():
+    """MultCircuit -> 7 witnesses, 1 public, arithCheckMaxRank 3N+1, embRank 4N, batch 12,
+    commitRank 2N+1; decomposeBase(5) = [3, 1, 1]."""
+    N = 1 << 13
+    q = pyref.modulus("zp128")
+    define, n_pw, n_w = B.mult_circuit(N)
+    ctx = B.Context(q, N, n_pw, n_w)
+    define(ctx, oracle.Field(q))
+    assert B.decompose_base(5) == [3, 1, 1]
+    assert (ctx.w_cnt, ctx.pw_cnt, ctx.arith_max_rank, ctx.batch(), ctx.commit_rank()) == (7, 1, 3 * N + 1, 12, 2 * N + 1)
+    assert 1 << (ctx.arith_max_rank - 1).bit_length() == 4 * N
+    assert len(ctx.arith_constraints) == 5 and sum(len(c.witness) for c in ctx.arith_constraints) == 12
+    for x in range(-5, 6):
+        d = B.decompose_big(x % q, [3, 1, 1], q)
+        assert sum(a * b for a, b in zip(d, [3, 1, 1])) == x and all(v in (-1, 0, 1) for v in d)
