@@ -277,6 +277,7 @@ class Prover:
             vals[i] = J.field_set_random(self.tape, q)
             vals[i - N] = (vals[i - N] - vals[i]) % q
         self.trace["mask"].append(list(vals[:mask_rank]))
+        self.trace.setdefault("mask_sum", []).append(mask_sum)
         return C.f.to_mont(vals), mask_sum
 
     def prove(self, pw_vals, w_vals):
@@ -293,6 +294,7 @@ class Prover:
                 d = decompose_big(w[wid][i], base, q)
                 for j, x in enumerate(wds):
                     w[x][i] = d[j] % q
+        self.trace["w_full"], self.trace["pw_full"] = w, pw
         tr = Transcript(CHAL_NAMES)
         pw_ecd_ntt = [C.emb_ntt.fwd(encode(C, f.to_mont(v))) for v in pw]
         w_ecd, w_ntt = [None] * ctx.w_cnt, [None] * ctx.w_cnt

@@ -1,0 +1,225 @@
+"""Host-side mirror of buckler.Prover.Prove (buckler/prover.go:42-353) over the C ABI.
+
+The orchestration (round structure, Fiat-Shamir transcript, which polynomial is committed when)
+follows the reference line by line; every polynomial operation is a device call:
+
+  Encode / RandEncode      rs_ntt_inverse_embed (+ one blinding coefficient)      buckler/encoder.go:32-54
+  polyEval.NTT             rs_ntt_forward at embRank                               prover.go:128,150
+  polyProver.Commit        rs_jindo_commit on the device-resident coefficients    prover.go:152
+  arithCheck               rs_eval_circuit -> rs_ntt_inverse -> rs_quorem_vanishing   prover.go:355-404
+  linCheck                 rs_reverse_scale + negacyclic INTT (TransposeTo), rs_vec_* , QuoRem   prover.go:406-459
+  polyProver.Evaluate      rs_opening_mul_add / rs_jindo_partial / rs_jindo_respond / rs_poly_evaluate  jindo/prover.go:205-324
+
+What stays on the host is what the reference keeps on the host in any deployment: the transcript
+(SHA-256 / SHAKE128), big-integer witness decomposition (done by the caller: `w` must already contain
+the decomposition witnesses, prover.go:77-86), powers of the linCheck constant, and all randomness,
+which is an explicit input (`rand`: blinding elements, mask polynomials and one Jindo tape per Commit,
+in call order) exactly like the tapes of include/ringo_jindo.h.
+
+`circuit` is the compiled description a Go caller gets from buckler.Compile (plain data):
+  rank, emb_rank, w_cnt, pw_cnt, arith_max_rank, arith_terms [(constraint, coeff_idx, pw|-1, [w..])],
+  arith_coeffs [ints], lin [(checker_kind, [(w_out, w_in), ...])] with checker_kind == "ntt".
+"""
+import ctypes
+import hashlib
+
+import numpy as np
+
+from . import capi, jindo_host as JH
+from .bigpoly import Batch, CyclicTransformer, CyclotomicTransformer
+from .capi import check, lib, c_u64p
+
+CHAL_NAMES = ["projConst", "arithBatchConst", "linCheckBatchConst", "linCheckConst", "sumCheckBatchConst", "evalPoint"]
+
+
+class Transcript:
+    """gnark-crypto fiat-shamir over SHA-256: H(name || previous challenge || bindings) (restated)."""
+
+    def __init__(self, names):
+        self.names, self.bindings, self.values = list(names), {n: [] for n in names}, {}
+
+    def bind(self, name, data):
+        self.bindings[name].append(bytes(data))
+
+    def compute_challenge(self, name):
+        pos = self.names.index(name)
+        h = hashlib.sha256(name.encode())
+        if pos:
+            h.update(self.values[self.names[pos - 1]])
+        for b in self.bindings[name]:
+            h.update(b)
+        self.values[name] = h.digest()
+        return self.values[name]
+
+
+def _p(a):
+    return a.ctypes.data_as(c_u64p)
+
+
+class Prover:
+    def __init__(self, field, q, circuit, jindo_params, jindo_prover):
+        self.f, self.q, self.c, self.jp, self.gp = field, q, circuit, jindo_params, jindo_prover
+        self.L = field.L
+        self.R = 1 << (64 * self.L)
+        N, E = circuit["rank"], circuit["emb_rank"]
+        self.enc = CyclicTransformer(field, N)           # Encoder.ntt (encoder.go:15-20)
+        self.emb = CyclicTransformer(field, E)           # polyEval (compile.go:186)
+        self.neg = CyclotomicTransformer(field, N)       # nttChecker (linear.go:26-33)
+        self.ringQ = JH.HostRing(jindo_params.d, jindo_params.q_primes, [JH.psi_for(x, jindo_params.d) for x in jindo_params.q_primes])
+        self.ringQOut = JH.HostRing(jindo_params.d, jindo_params.qout_primes, [JH.psi_for(x, jindo_params.d) for x in jindo_params.qout_primes])
+
+    # ---- scalars (host) -------------------------------------------------------------------------
+    def mont(self, x):
+        return np.array([((x % self.q) * self.R % self.q >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(self.L)], dtype=np.uint64)
+
+    def from_mont_arr(self, a):
+        rinv = pow(self.R, -1, self.q)
+        return sum(int(v) << (64 * i) for i, v in enumerate(a)) * rinv % self.q
+
+    def _set_elem(self, batch, poly, off, value):
+        one = Batch(self.f, 1, 1).upload(self.mont(value).reshape(1, 1, self.L))
+        check(lib().rs_batch_copy(batch.h, poly, off, one.h, 0, 0, 1))
+
+    # ---- Jindo commit of coefficients [0, length) of batch[poly] ---------------------------------
+    def _commit(self, batch, poly, length, tape):
+        com, op = self.gp.Commit(batch, poly, length, tape)
+        return com, op
+
+    def prove(self, pw_mont, w_mont, rand):
+        """pw_mont / w_mont: uint64 arrays [pw_cnt, N, L] / [w_cnt, N, L] (Montgomery).  rand: dict with
+        "blind" (ints, one per witness), "mask" (list of int lists) and "tapes" (one Jindo tape dict per
+        Commit, in call order).  Returns the proof as plain data."""
+        c, f, q = self.c, self.f, self.q
+        N, E, wc, pc = c["rank"], c["emb_rank"], c["w_cnt"], c["pw_cnt"]
+        L = lib()
+        tapes = iter(rand["tapes"])
+        tr = Transcript(CHAL_NAMES)
+        # ---- Encode + NTT of all (public) witnesses: 1 upload, 2 batched transforms
+        vals = Batch(f, wc + pc, N).upload(np.concatenate([w_mont, pw_mont]))
+        ecd = Batch(f, wc + pc, E)
+        check(L.rs_ntt_inverse_embed(self.enc.h, ecd.h, 0, vals.h, 0, wc + pc, 1))
+        tmp = Batch(f, 2, 1)
+        for i in range(wc):                              # RandEncodeTo: c[N] <- r ; c[0] -= c[N]
+            self._set_elem(ecd, i, N, rand["blind"][i])
+            check(L.rs_batch_copy(tmp.h, 0, 0, ecd.h, i, 0, 1))
+            check(L.rs_batch_copy(tmp.h, 1, 0, ecd.h, i, N, 1))
+            check(L.rs_vec_sub(tmp.h, 0, tmp.h, 0, tmp.h, 1, 1))
+            check(L.rs_batch_copy(ecd.h, i, 0, tmp.h, 0, 0, 1))
+        ntt = Batch(f, wc + pc, E)
+        self.emb.FwdNTTTo(ntt, ecd)
+        w_ntt = Batch(f, wc, E, device_ptr=L.rs_batch_device_ptr(ntt.h), keepalive=ntt)
+        pw_ntt = Batch(f, max(pc, 1), E)
+        for k in range(pc):
+            check(L.rs_batch_copy(pw_ntt.h, k, 0, ntt.h, wc + k, 0, E))
+        n_com = wc + (1 if c["arith_terms"] else 0) + (4 if c["lin"] else 0)
+        coms, opens, views = [None] * n_com, [None] * n_com, [None] * n_com
+        for i in range(wc):                              # first-round witnesses (no second-round witnesses here)
+            coms[i], opens[i] = self._commit(ecd, i, N + 1, next(tapes))
+            views[i] = (ecd, i, N + 1)
+            tr.bind("projConst", JH.commitment_write_raw(self.jp, coms[i].tolist()))
+        tr.compute_challenge("projConst")
+        idx = wc
+        work = Batch(f, 8, E)                            # 0 mask, 1 eval, 2 quo, 3 rem, 4 term, 5 linEcd, 6 linEcdTr, 7 scratch
+        lin_mask_sum = None
+        if c["lin"]:
+            mask = rand["mask"][0]
+            host = np.zeros((1, E, self.L), dtype=np.uint64)
+            host[0, :2 * N] = np.stack([self.mont(v) for v in mask])
+            work.upload(host, 0)
+            lin_mask_sum = rand["mask_sum"][0]
+            coms[idx], opens[idx] = self._commit(work, 0, 2 * N, next(tapes)); views[idx] = (work, 0, 2 * N)
+            tr.bind("arithBatchConst", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
+            tr.bind("arithBatchConst", lin_mask_sum.to_bytes(8 * self.L, "big"))
+            idx += 1
+        arith_bc = int.from_bytes(tr.compute_challenge("arithBatchConst"), "big") % q
+        keep = []                                        # committed polynomials must stay alive until Evaluate
+        if c["arith_terms"]:
+            T = (capi.Term * len(c["arith_terms"]))()
+            for k, (ci, co, pw, ws) in enumerate(c["arith_terms"]):
+                T[k].constraint, T[k].coeff, T[k].pw, T[k].n_w = ci, co, pw, len(ws)
+                for j, x in enumerate(ws):
+                    T[k].w[j] = x
+            coeffs = np.stack([self.mont(v) for v in c["arith_coeffs"]])
+            check(L.rs_eval_circuit(work.h, 1, pw_ntt.h, w_ntt.h, T, len(c["arith_terms"]), _p(coeffs), len(coeffs), _p(self.mont(arith_bc))))
+            check(L.rs_ntt_inverse(self.emb.h, work.h, 1, work.h, 1, 1))
+            quo_b = Batch(f, 2, E)
+            check(L.rs_quorem_vanishing(quo_b.h, 0, quo_b.h, 1, work.h, 1, N))
+            keep.append(quo_b)
+            coms[idx], opens[idx] = self._commit(quo_b, 0, c["arith_max_rank"] - N, next(tapes)); views[idx] = (quo_b, 0, c["arith_max_rank"] - N)
+            tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
+            idx += 1
+        lin_bc = int.from_bytes(tr.compute_challenge("linCheckBatchConst"), "big") % q
+        lin_c = int.from_bytes(tr.compute_challenge("linCheckConst"), "big") % q
+        if c["lin"]:
+            vec = [1]
+            for _ in range(1, N):
+                vec.append(vec[-1] * lin_c % q)
+            lv = Batch(f, 2, N).upload(np.stack([np.stack([self.mont(v) for v in vec])] * 2))
+            le = Batch(f, 2, E)
+            check(L.rs_ntt_inverse_embed(self.enc.h, le.h, 0, lv.h, 0, 1, 1))
+            check(L.rs_ntt_forward(self.emb.h, le.h, 0, le.h, 0, 1))                     # linCheckEcd (NTT form)
+            check(L.rs_batch_zero(work.h, 1, 0, E))                                      # eval = 0
+            bcm = self.mont(lin_bc)
+            for kind, pairs in c["lin"]:
+                assert kind == "ntt"
+                check(L.rs_reverse_scale(lv.h, 1, lv.h, 0, _p(self.mont(N))))            # TransposeTo (linear.go:38-43)
+                check(L.rs_ntt_inverse(self.neg.h, lv.h, 1, lv.h, 1, 1))
+                check(L.rs_ntt_inverse_embed(self.enc.h, le.h, 1, lv.h, 1, 1, 1))
+                check(L.rs_ntt_forward(self.emb.h, le.h, 1, le.h, 1, 1))                 # linCheckEcdTr
+                for (w_out, w_in) in pairs:
+                    check(L.rs_vec_mul(work.h, 4, le.h, 1, w_ntt.h, w_in, 1))            # term = EcdTr * wIn
+                    check(L.rs_vec_mul_sub(work.h, 4, le.h, 0, w_ntt.h, w_out, 1))       # term -= Ecd * wOut
+                    check(L.rs_vec_scalar_mul(work.h, 1, work.h, 1, _p(bcm), 1))         # eval *= batchConst
+                    check(L.rs_vec_add(work.h, 1, work.h, 1, work.h, 4, 1))              # eval += term
+            check(L.rs_vec_scalar_mul(work.h, 1, work.h, 1, _p(bcm), 1))
+            check(L.rs_ntt_inverse(self.emb.h, work.h, 1, work.h, 1, 1))
+            check(L.rs_vec_add(work.h, 1, work.h, 1, work.h, 0, 1))                      # + linCheckMask
+            qr = Batch(f, 2, E)
+            check(L.rs_quorem_vanishing(qr.h, 0, qr.h, 1, work.h, 1, N))
+            Rk = self.jp.rank
+            rem = Batch(f, 2, max(Rk, N))                                                # 0: remLo, 1: remHi
+            check(L.rs_batch_zero(rem.h, 0, 0, rem.rank)); check(L.rs_batch_zero(rem.h, 1, 0, rem.rank))
+            check(L.rs_batch_copy(rem.h, 0, 0, qr.h, 1, 1, N - 1))
+            check(L.rs_batch_copy(rem.h, 1, Rk - (N - 1), qr.h, 1, 1, N - 1))
+            keep += [qr, rem]
+            for (b, p, ln) in ((qr, 0, N), (rem, 0, N - 1), (rem, 1, Rk)):
+                coms[idx], opens[idx] = self._commit(b, p, ln, next(tapes)); views[idx] = (b, p, ln)
+                tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
+                idx += 1
+        tr.compute_challenge("sumCheckBatchConst")
+        x = int.from_bytes(tr.compute_challenge("evalPoint"), "big") % q
+        evals, pf = self.evaluate(x, views, coms, opens)
+        return {"Witness": [cm.tolist() for cm in coms], "LinCheckMaskSum": lin_mask_sum, "SumCheckMaskSum": None,
+                "Evals": evals, "EvalProof": pf, "_eval_point": x}
+
+    def evaluate(self, x, views, coms, opens):
+        """jindo.Prover.Evaluate (jindo/prover.go:205-324); views: (batch, poly, length) of each committed vector."""
+        jp, gp, q = self.jp, self.gp, self.q
+        batch = len(coms)
+        prefix = gp.crs + b"".join(JH.commitment_write_raw(jp, cm.tolist()) for cm in coms) + x.to_bytes(8 * self.L, "big")
+        if batch > 1:
+            bb = hashlib.shake_128(prefix).digest(16 * batch)
+            prefix += bb
+            ob = gp.NewOpening()
+            for i in range(batch):
+                cq = JH.encode_challenge(jp, self.ringQ, bb[16 * i:16 * i + 16])
+                co = JH.encode_challenge(jp, self.ringQOut, bb[16 * i:16 * i + 16])
+                gp.OpeningMulAdd(ob, opens[i], np.array(cq, dtype=np.uint64), np.array(co, dtype=np.uint64))
+        else:
+            ob = opens[0]
+        left = np.array([JH.encode_elements(jp, self.ringQ, q, [le]) for le in JH.left_vec(jp, q, x)], dtype=np.uint64)
+        part = gp.Partial(ob, left)
+        pf = {"Partial": part[:jp.cols].tolist(), "PartialMask": part[jp.cols].tolist(),
+              "InCommit": [ob.InCommit(k).tolist() for k in range(jp.in_com_dcmp_len)]}
+        tr = prefix + b"".join(JH.poly_write_to(c) for c in pf["Partial"]) + JH.poly_write_to(pf["PartialMask"])
+        cs = hashlib.shake_128(tr).digest(16 * jp.cols)
+        chals = np.array([JH.encode_challenge(jp, self.ringQ, cs[16 * i:16 * i + 16]) for i in range(jp.cols)], dtype=np.uint64)
+        enc, ml = gp.Respond(ob, chals)
+        pf["Encode"], pf["MLWE"] = enc.tolist(), ml.tolist()
+        xm = self.mont(x)
+        evals = []
+        for (b, p, ln) in views:
+            out = np.zeros(self.L, dtype=np.uint64)
+            check(lib().rs_poly_evaluate(b.h, p, ln, _p(xm), _p(out)))
+            evals.append(self.from_mont_arr(out))
+        return evals, pf

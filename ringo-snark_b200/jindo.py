@@ -44,8 +44,9 @@ class Prover:
     RNS primes / psi, deltaInv and the TwinCDT tables; `ck_*` are the commit-key polynomials as
     uint64 arrays [.., limb, 256]."""
 
-    def __init__(self, field, p, ck_in, ck_mlwe, ck_out, cdt_tables):
+    def __init__(self, field, p, ck_in, ck_mlwe, ck_out, cdt_tables, crs=b""):
         self.field = field
+        self.crs = bytes(crs)           # CommitKey.WriteRawTo (entities.go:75-77): bound into the Evaluate transcript
         self.p = dict(p)
         self.d = p["d"]
         self.n_q, self.n_qout = len(p["q"]), len(p["qout"])

@@ -305,3 +305,112 @@ def prover_inputs(p):
         "delta_inv": delta_inv(p), "cdt_tail_lo": -tail_hi, "cdt_sigma": p.ecd_std,
     }
     return d, tables
+
+
+# ---------------------------------------------------------------------------------------------
+# Host-side ring helpers of jindo.Prover.Evaluate (jindo/utils.go:21-82, encoder.go:113-146): the
+# challenge and left-vector polynomials are tiny and sequentially derived from the transcript, so the
+# reference computes them on the host; so does this mirror ([lattigo] NTT conventions restated).
+# ---------------------------------------------------------------------------------------------
+def brv(i, bits):
+    r = 0
+    for _ in range(bits):
+        r = (r << 1) | (i & 1)
+        i >>= 1
+    return r
+
+
+class HostRing:
+    def __init__(self, d, primes, psis):
+        self.d, self.primes = d, list(primes)
+        logd = d.bit_length() - 1
+        self.roots = []
+        for q, psi in zip(primes, psis):
+            r = [0] * d
+            pw = 1
+            for j in range(d):
+                r[brv(j, logd)] = pw
+                pw = pw * psi % q
+            self.roots.append(r)
+
+    def ntt_mform(self, poly):
+        """NTT(MForm(poly)): poly = [limb][coeff] canonical ints."""
+        out = []
+        for q, roots, c in zip(self.primes, self.roots, poly):
+            a = [x * (1 << 64) % q for x in c]
+            t = self.d; m = 1
+            while m < self.d:
+                t >>= 1
+                for i in range(m):
+                    w = roots[m + i]
+                    for j in range(2 * i * t, 2 * i * t + t):
+                        v = a[j + t] * w % q
+                        u = a[j]
+                        a[j] = (u + v) % q
+                        a[j + t] = (u - v) % q
+                m <<= 1
+            out.append(a)
+        return out
+
+
+def div_mod64(x, y):
+    r = 0
+    for i in range(len(x) - 1, -1, -1):
+        cur = (r << 64) | x[i]
+        x[i] = cur // y
+        r = cur % y
+    return r
+
+
+def encode_challenge(p, ring, chal_bytes):
+    """jindo/utils.go:21-46"""
+    poly = [[0] * p.d for _ in ring.primes]
+    c = [int.from_bytes(chal_bytes[:8], "big"), int.from_bytes(chal_bytes[8:16], "big")]
+    bound = min(p.base, 1 << (120 // p.exp)) // 2
+    for i in range(p.exp):
+        r = div_mod64(c, bound)
+        for k, q in enumerate(ring.primes):
+            poly[k][i * p.slots] = (q - (bound - r)) if r > bound // 2 else r
+    return ring.ntt_mform(poly)
+
+
+def encode_elements(p, ring, q_field, values):
+    """Encoder.encode (jindo/encoder.go:106-146) of up to `slots` canonical field values."""
+    L = (q_field.bit_length() + 63) // 64
+    coeffs = [0] * p.d
+    for i, x in enumerate(values):
+        limbs = [(x >> (64 * k)) & MASK64 for k in range(L)]
+        for j in range(p.exp - 1):
+            coeffs[j * p.slots + i] = div_mod64(limbs, p.base)
+        coeffs[(p.exp - 1) * p.slots + i] = limbs[0]
+    return ring.ntt_mform([list(coeffs) for _ in ring.primes])
+
+
+def left_vec(p, q_field, x):
+    """jindo/utils.go:63-73"""
+    skip = pow(x, p.cols * p.slots, q_field)
+    left = [1]
+    for _ in range(1, p.rows):
+        left.append(left[-1] * skip % q_field)
+    left[p.rows - 1] = x
+    return left
+
+
+def poly_write_to(poly):
+    """[lattigo] ring.Poly.WriteTo framing (restated; see DESIGN.md "unpinned")."""
+    import struct
+    out = [struct.pack("<Q", len(poly))]
+    for c in poly:
+        out.append(struct.pack("<Q", len(c)))
+        out.append(struct.pack("<%dQ" % len(c), *[int(v) for v in c]))
+    return b"".join(out)
+
+
+def commitment_write_raw(p, value):
+    """Commitment.WriteRawTo (jindo/entities.go:85-100): polys allocated with ringQ's limb count."""
+    nl = len(p.q_primes)
+    out = []
+    for v in value:
+        limbs = [list(c) for c in v] + [[0] * p.d for _ in range(nl - len(v))]
+        out.append(poly_write_to(limbs))
+    return b"".join(out)
