@@ -62,13 +62,23 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
                     const uint64_t *ck_out, const uint64_t *cdt_tables, rs_jindo **out);
 void rs_jindo_destroy(rs_jindo *j);
 
+/* GPU-resident uniform source of the encoder's TwinCDT sampler.
+ * Reproduces csprng.UniformSampler (math/csprng/uniform.go:26-70) in HBM: AES-256-CTR keyed by
+ * key32 || iv16 = SHA-384(seed) (uniform.go:38-46, hashed by the caller), 8-byte little-endian draws out
+ * of the XOR-accumulating 8 KiB buffer.  The stream is stateful like the Go sampler: every Commit whose
+ * tape has twin_u == NULL consumes the next n_twin*d draws.  rs_jindo_twin_stream_draw hands the next n
+ * draws to the host instead (tests; sample_n / sample_float callers). */
+int rs_jindo_set_twin_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *iv16);
+int rs_jindo_twin_stream_draw(rs_jindo *j, size_t n, uint64_t *out);
+
 /* Randomness / noise inputs of one Commit, in the reference's consumption order. */
 typedef struct rs_jindo_tape {
     const uint64_t *first_row;   /* cols*slots field elements (Montgomery)       prover.go:65-86 */
     const uint64_t *last_row;    /* cols*slots field elements */
     const uint64_t *mask_rows;   /* n_mask_rows*slots field elements, encode order prover.go:93-115 */
     size_t n_mask_rows;
-    const uint64_t *twin_u;      /* one uniform draw per TwinCDT sample, call order  encoder.go:168-169 */
+    const uint64_t *twin_u;      /* one uniform draw per TwinCDT sample, call order  encoder.go:168-169;
+                                    NULL: drawn on the device from the stream set by rs_jindo_set_twin_stream */
     size_t n_twin_u;
     const int64_t *cosac_g;      /* sampled g for the COSAC rows: data columns' row 0 (col order), then
                                     the mask column's rows in encode order; d values each */

@@ -38,6 +38,7 @@ class UniformSampler:
     BUF = 8192  # uniform.go:12
 
     def __init__(self, seed):
+        self.seed = bytes(seed)
         h = hashlib.sha384(bytes(seed)).digest()            # uniform.go:38-39
         self._enc = Cipher(algorithms.AES(h[:32]), modes.CTR(h[32:48])).encryptor()   # :41-46
         self.buf = bytearray(self.BUF)

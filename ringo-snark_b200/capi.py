@@ -101,6 +101,8 @@ _SIGS = {
     # ringo_jindo.h
     "rs_jindo_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "rs_jindo_destroy": (None, [c_vp]),
+    "rs_jindo_set_twin_stream": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "rs_jindo_twin_stream_draw": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_commit": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
     "rs_opening_free": (None, [c_vp]),
     "rs_opening_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_size, c_size, c_vp]),

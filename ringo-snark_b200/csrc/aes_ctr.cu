@@ -1,0 +1,179 @@
+// aes_ctr.cu -- GPU-resident uniform draws for the TwinCDT rows (SURVEY.md 8f "next" row 1).
+//
+// Reproduces math/csprng/uniform.go bit for bit: AES-256 in CTR mode (Go crypto/cipher.NewCTR:
+// 128-bit big-endian counter starting at the IV), keystream consumed 8 bytes little-endian per
+// Sample() from an 8 KiB buffer that is refilled with XORKeyStream(buf, buf) on a never-cleared
+// buffer (uniform.go:64-70) -- so the n-th 8 KiB chunk handed out is the XOR of keystream chunks 0..n.
+// The key / IV are SHA-384(seed) split 32 / 16 bytes by the host (uniform.go:38-46).
+//
+//   aes_keystream_kernel   one thread per 16-byte block: T-table AES-256 of (IV + block index)
+//   xor_scan_*             prefix XOR over chunks, independently for each of the 1024 word offsets of a
+//                          chunk, seeded with the sampler's running buffer state (3-phase segmented scan)
+#include <string.h>
+
+#include "common.cuh"
+
+typedef unsigned long long u64;
+
+namespace rs {
+
+struct AesKey { uint32_t rk[60]; };          // AES-256 expanded key, big-endian words
+
+__constant__ uint8_t c_sbox[256];
+
+__device__ __forceinline__ uint32_t xtime(uint32_t x) { return ((x << 1) ^ (((x >> 7) & 1) * 0x1b)) & 0xff; }
+
+// keystream for blocks [blk0, blk0 + n): out as 16 bytes each
+__global__ void __launch_bounds__(256) aes_keystream_kernel(uint4 *__restrict__ out, const __grid_constant__ AesKey K,
+                                                            u64 iv_hi, u64 iv_lo, u64 blk0, size_t n) {
+    __shared__ uint32_t Te0[256];
+    {
+        const uint32_t s = c_sbox[threadIdx.x], s2 = xtime(s), s3 = s2 ^ s;
+        Te0[threadIdx.x] = (s2 << 24) | (s << 16) | (s << 8) | s3;       // (02 01 01 03) * S[x], big-endian word
+    }
+    __syncthreads();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        // counter = IV + (blk0 + i) as a 128-bit big-endian integer
+        const u64 add = blk0 + i;
+        const u64 lo = iv_lo + add, hi = iv_hi + (lo < add);
+        uint32_t s0 = (uint32_t)(hi >> 32) ^ K.rk[0], s1 = (uint32_t)hi ^ K.rk[1], s2 = (uint32_t)(lo >> 32) ^ K.rk[2], s3 = (uint32_t)lo ^ K.rk[3];
+#define ROTR(x, r) (((x) >> (r)) | ((x) << (32 - (r))))
+#pragma unroll
+        for (int r = 1; r < 14; r++) {
+            const uint32_t t0 = Te0[s0 >> 24] ^ ROTR(Te0[(s1 >> 16) & 0xff], 8) ^ ROTR(Te0[(s2 >> 8) & 0xff], 16) ^ ROTR(Te0[s3 & 0xff], 24) ^ K.rk[4 * r];
+            const uint32_t t1 = Te0[s1 >> 24] ^ ROTR(Te0[(s2 >> 16) & 0xff], 8) ^ ROTR(Te0[(s3 >> 8) & 0xff], 16) ^ ROTR(Te0[s0 & 0xff], 24) ^ K.rk[4 * r + 1];
+            const uint32_t t2 = Te0[s2 >> 24] ^ ROTR(Te0[(s3 >> 16) & 0xff], 8) ^ ROTR(Te0[(s0 >> 8) & 0xff], 16) ^ ROTR(Te0[s1 & 0xff], 24) ^ K.rk[4 * r + 2];
+            const uint32_t t3 = Te0[s3 >> 24] ^ ROTR(Te0[(s0 >> 16) & 0xff], 8) ^ ROTR(Te0[(s1 >> 8) & 0xff], 16) ^ ROTR(Te0[s2 & 0xff], 24) ^ K.rk[4 * r + 3];
+            s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+        }
+#undef ROTR
+        // final round: SubBytes + ShiftRows + AddRoundKey
+        const uint32_t o0 = ((uint32_t)c_sbox[s0 >> 24] << 24 | (uint32_t)c_sbox[(s1 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s2 >> 8) & 0xff] << 8 | c_sbox[s3 & 0xff]) ^ K.rk[56];
+        const uint32_t o1 = ((uint32_t)c_sbox[s1 >> 24] << 24 | (uint32_t)c_sbox[(s2 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s3 >> 8) & 0xff] << 8 | c_sbox[s0 & 0xff]) ^ K.rk[57];
+        const uint32_t o2 = ((uint32_t)c_sbox[s2 >> 24] << 24 | (uint32_t)c_sbox[(s3 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s0 >> 8) & 0xff] << 8 | c_sbox[s1 & 0xff]) ^ K.rk[58];
+        const uint32_t o3 = ((uint32_t)c_sbox[s3 >> 24] << 24 | (uint32_t)c_sbox[(s0 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s1 >> 8) & 0xff] << 8 | c_sbox[s2 & 0xff]) ^ K.rk[59];
+        // words are big-endian byte strings; memory order = byte order
+        out[i] = make_uint4(__byte_perm(o0, 0, 0x0123), __byte_perm(o1, 0, 0x0123), __byte_perm(o2, 0, 0x0123), __byte_perm(o3, 0, 0x0123));
+    }
+}
+
+constexpr int CH_WORDS = 1024;              // u64 words per 8 KiB chunk (uniform.go:12 bufSize)
+
+// phase 1: XOR total of each segment of `seg` chunks, per word offset
+__global__ void xor_scan_totals(u64 *__restrict__ totals, const u64 *__restrict__ ks, size_t n_chunks, int seg) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;             // word offset
+    const size_t s = blockIdx.y;                                      // segment
+    if (o >= CH_WORDS) return;
+    const size_t c0 = s * seg, c1 = (c0 + seg < n_chunks) ? c0 + seg : n_chunks;
+    u64 acc = 0;
+    for (size_t c = c0; c < c1; c++) acc ^= ks[c * CH_WORDS + o];
+    totals[s * CH_WORDS + o] = acc;
+}
+// phase 2: exclusive prefix over segments, seeded with the sampler state; also leaves the new state
+__global__ void xor_scan_prefix(u64 *__restrict__ totals, u64 *__restrict__ state, size_t n_seg) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= CH_WORDS) return;
+    u64 acc = state[o];
+    for (size_t s = 0; s < n_seg; s++) { const u64 t = totals[s * CH_WORDS + o]; totals[s * CH_WORDS + o] = acc; acc ^= t; }
+    state[o] = acc;
+}
+// phase 3: running XOR inside each segment (in place: keystream -> handed-out buffer contents)
+__global__ void xor_scan_apply(u64 *__restrict__ ks, const u64 *__restrict__ totals, size_t n_chunks, int seg) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t s = blockIdx.y;
+    if (o >= CH_WORDS) return;
+    const size_t c0 = s * seg, c1 = (c0 + seg < n_chunks) ? c0 + seg : n_chunks;
+    u64 acc = totals[s * CH_WORDS + o];
+    for (size_t c = c0; c < c1; c++) { acc ^= ks[c * CH_WORDS + o]; ks[c * CH_WORDS + o] = acc; }
+}
+
+// ---- host: AES-256 key schedule ---------------------------------------------------------------
+static const uint8_t h_sbox[256] = {
+    0x63,0x7c,0x77,0x7b,0xf2,0x6b,0x6f,0xc5,0x30,0x01,0x67,0x2b,0xfe,0xd7,0xab,0x76,0xca,0x82,0xc9,0x7d,0xfa,0x59,0x47,0xf0,0xad,0xd4,0xa2,0xaf,0x9c,0xa4,0x72,0xc0,
+    0xb7,0xfd,0x93,0x26,0x36,0x3f,0xf7,0xcc,0x34,0xa5,0xe5,0xf1,0x71,0xd8,0x31,0x15,0x04,0xc7,0x23,0xc3,0x18,0x96,0x05,0x9a,0x07,0x12,0x80,0xe2,0xeb,0x27,0xb2,0x75,
+    0x09,0x83,0x2c,0x1a,0x1b,0x6e,0x5a,0xa0,0x52,0x3b,0xd6,0xb3,0x29,0xe3,0x2f,0x84,0x53,0xd1,0x00,0xed,0x20,0xfc,0xb1,0x5b,0x6a,0xcb,0xbe,0x39,0x4a,0x4c,0x58,0xcf,
+    0xd0,0xef,0xaa,0xfb,0x43,0x4d,0x33,0x85,0x45,0xf9,0x02,0x7f,0x50,0x3c,0x9f,0xa8,0x51,0xa3,0x40,0x8f,0x92,0x9d,0x38,0xf5,0xbc,0xb6,0xda,0x21,0x10,0xff,0xf3,0xd2,
+    0xcd,0x0c,0x13,0xec,0x5f,0x97,0x44,0x17,0xc4,0xa7,0x7e,0x3d,0x64,0x5d,0x19,0x73,0x60,0x81,0x4f,0xdc,0x22,0x2a,0x90,0x88,0x46,0xee,0xb8,0x14,0xde,0x5e,0x0b,0xdb,
+    0xe0,0x32,0x3a,0x0a,0x49,0x06,0x24,0x5c,0xc2,0xd3,0xac,0x62,0x91,0x95,0xe4,0x79,0xe7,0xc8,0x37,0x6d,0x8d,0xd5,0x4e,0xa9,0x6c,0x56,0xf4,0xea,0x65,0x7a,0xae,0x08,
+    0xba,0x78,0x25,0x2e,0x1c,0xa6,0xb4,0xc6,0xe8,0xdd,0x74,0x1f,0x4b,0xbd,0x8b,0x8a,0x70,0x3e,0xb5,0x66,0x48,0x03,0xf6,0x0e,0x61,0x35,0x57,0xb9,0x86,0xc1,0x1d,0x9e,
+    0xe1,0xf8,0x98,0x11,0x69,0xd9,0x8e,0x94,0x9b,0x1e,0x87,0xe9,0xce,0x55,0x28,0xdf,0x8c,0xa1,0x89,0x0d,0xbf,0xe6,0x42,0x68,0x41,0x99,0x2d,0x0f,0xb0,0x54,0xbb,0x16};
+
+static void aes256_expand(const uint8_t key[32], AesKey &K) {
+    for (int i = 0; i < 8; i++) K.rk[i] = (uint32_t)key[4 * i] << 24 | (uint32_t)key[4 * i + 1] << 16 | (uint32_t)key[4 * i + 2] << 8 | key[4 * i + 3];
+    uint32_t rcon = 1;
+    for (int i = 8; i < 60; i++) {
+        uint32_t t = K.rk[i - 1];
+        if (i % 8 == 0) {
+            t = (t << 8) | (t >> 24);
+            t = (uint32_t)h_sbox[t >> 24] << 24 | (uint32_t)h_sbox[(t >> 16) & 0xff] << 16 | (uint32_t)h_sbox[(t >> 8) & 0xff] << 8 | h_sbox[t & 0xff];
+            t ^= rcon << 24;
+            rcon = ((rcon << 1) ^ ((rcon >> 7) * 0x11b)) & 0xff;
+        } else if (i % 8 == 4) {
+            t = (uint32_t)h_sbox[t >> 24] << 24 | (uint32_t)h_sbox[(t >> 16) & 0xff] << 16 | (uint32_t)h_sbox[(t >> 8) & 0xff] << 8 | h_sbox[t & 0xff];
+        }
+        K.rk[i] = K.rk[i - 8] ^ t;
+    }
+}
+
+struct UniformStream {
+    AesKey key;
+    u64 iv_hi, iv_lo;
+    u64 pos;             // samples handed out so far
+    u64 *d_state;        // 1024 words: current contents of the sampler's 8 KiB buffer
+};
+
+static bool g_sbox_uploaded = false;
+
+int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_t iv[16]) {
+    UniformStream *s = new UniformStream();
+    aes256_expand(key, s->key);
+    s->iv_hi = s->iv_lo = 0;
+    for (int i = 0; i < 8; i++) { s->iv_hi = (s->iv_hi << 8) | iv[i]; s->iv_lo = (s->iv_lo << 8) | iv[8 + i]; }
+    s->pos = 0;
+    RS_CUDA_CHECK(cudaMalloc((void **)&s->d_state, CH_WORDS * 8));
+    RS_CUDA_CHECK(cudaMemset(s->d_state, 0, CH_WORDS * 8));
+    if (!g_sbox_uploaded) { RS_CUDA_CHECK(cudaMemcpyToSymbol(c_sbox, h_sbox, 256)); g_sbox_uploaded = true; }
+    *out = s;
+    return RS_OK;
+}
+void uniform_stream_free(UniformStream *s) { if (s) { cudaFree(s->d_state); delete s; } }
+
+// Produces the next n Sample() values of the stream in HBM and advances it.
+// *d_buf is the allocation (cudaFreeAsync it on the current stream when done), *d_samples points at sample 0.
+// Layout of the allocation: [ current 8 KiB buffer of the sampler | every chunk refilled by this call ].
+int uniform_stream_draw(UniformStream *s, size_t n, u64 **d_buf, const u64 **d_samples) {
+    *d_buf = nullptr; *d_samples = nullptr;
+    if (n == 0) return RS_OK;
+    cudaStream_t st = current_stream();
+    const u64 off = s->pos % CH_WORDS;
+    const u64 c_start = s->pos / CH_WORDS + (off ? 1 : 0);                  // first chunk not yet refilled
+    const u64 c_end = (s->pos + n + CH_WORDS - 1) / CH_WORDS;
+    const size_t n_chunks = c_end > c_start ? (size_t)(c_end - c_start) : 0;
+    u64 *buf = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&buf, (n_chunks + 1) * CH_WORDS * 8, st));
+    RS_CUDA_CHECK(cudaMemcpyAsync(buf, s->d_state, CH_WORDS * 8, cudaMemcpyDeviceToDevice, st));
+    if (n_chunks) {
+        u64 *ks = buf + CH_WORDS;
+        aes_keystream_kernel<<<148 * 8, 256, 0, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
+        const int seg = n_chunks > 4096 ? 256 : (n_chunks > 64 ? 16 : 1);
+        const size_t n_seg = (n_chunks + seg - 1) / seg;
+        u64 *d_tot = nullptr;
+        if (cudaMallocAsync((void **)&d_tot, n_seg * CH_WORDS * 8, st) != cudaSuccess) {
+            cudaFreeAsync(buf, st);
+            return set_error(RS_ERR_CUDA, "uniform_stream_draw: cudaMallocAsync failed");
+        }
+        dim3 grid(CH_WORDS / 256, (unsigned)n_seg);
+        xor_scan_totals<<<grid, 256, 0, st>>>(d_tot, ks, n_chunks, seg);
+        xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(d_tot, s->d_state, n_seg);
+        xor_scan_apply<<<grid, 256, 0, st>>>(ks, d_tot, n_chunks, seg);
+        count_launch(4);
+        cudaFreeAsync(d_tot, st);
+        if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(buf, st); return set_error(RS_ERR_CUDA, "uniform_stream_draw: launch failed"); }
+    }
+    s->pos += n;
+    *d_buf = buf;
+    *d_samples = buf + (off ? off : CH_WORDS);
+    return RS_OK;
+}
+
+}  // namespace rs

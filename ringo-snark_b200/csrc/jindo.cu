@@ -54,6 +54,13 @@ struct DescCache {            // encode descriptors of one committed length, res
     size_t n_descs, twin, cosac, mask;
 };
 
+namespace rs {
+struct UniformStream;
+int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_t iv[16]);
+void uniform_stream_free(UniformStream *s);
+int uniform_stream_draw(UniformStream *s, size_t n, u64 **d_buf, const u64 **d_samples);
+}  // namespace rs
+
 struct rs_jindo {
     std::vector<DescCache> *cache;
     rs::EncDesc *d_ndescs;    // descriptors of the MLWE noise polynomials
@@ -65,6 +72,7 @@ struct rs_jindo {
     u64 *d_ck_in, *d_ck_mlwe, *d_ck_out;
     u64 *d_cdt;
     u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
+    rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
 };
 
 struct rs_opening {
@@ -1042,7 +1050,27 @@ void rs_jindo_destroy(rs_jindo *j) {
     cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt);
     if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
     cudaFree(j->d_ndescs);
+    rs::uniform_stream_free(j->twin_stream);
     delete j;
+}
+
+int rs_jindo_set_twin_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *iv16) {
+    RS_REQUIRE(j && key32 && iv16, RS_ERR_ARG, "rs_jindo_set_twin_stream: null argument");
+    rs::uniform_stream_free(j->twin_stream);
+    j->twin_stream = nullptr;
+    return rs::uniform_stream_init(&j->twin_stream, key32, iv16);
+}
+
+int rs_jindo_twin_stream_draw(rs_jindo *j, size_t n, uint64_t *out) {
+    RS_REQUIRE(j && j->twin_stream && (out || n == 0), RS_ERR_ARG, "rs_jindo_twin_stream_draw: no stream / null argument");
+    u64 *buf = nullptr; const u64 *smp = nullptr;
+    int rc = rs::uniform_stream_draw(j->twin_stream, n, &buf, &smp);
+    if (rc || n == 0) return rc;
+    cudaError_t e = cudaMemcpyAsync(out, smp, n * 8, cudaMemcpyDeviceToHost, rs::current_stream());
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rs::current_stream());
+    cudaFreeAsync(buf, rs::current_stream());
+    if (e != cudaSuccess) return rs::set_error(RS_ERR_CUDA, "rs_jindo_twin_stream_draw: %s", cudaGetErrorString(e));
+    return RS_OK;
 }
 
 void rs_opening_free(rs_opening *o) {
@@ -1134,7 +1162,11 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
     }
     RS_REQUIRE(tape->n_mask_rows == mask, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of mask rows");
     RS_REQUIRE(tape->n_cosac_polys == cosac, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of COSAC polynomials");
-    RS_REQUIRE(tape->n_twin_u == twin * d && (twin == 0 || tape->twin_u), RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of TwinCDT draws");
+    const bool gen_twin = (tape->twin_u == nullptr && twin != 0);
+    if (gen_twin)
+        RS_REQUIRE(j->twin_stream, RS_ERR_ARG, "rs_jindo_commit: tape carries no TwinCDT draws and no stream was set (rs_jindo_set_twin_stream)");
+    else
+        RS_REQUIRE(tape->n_twin_u == twin * d, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of TwinCDT draws");
 
     const bool reuse = (*open != nullptr);
     rs_opening *o = *open;
@@ -1150,7 +1182,7 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
 
     // ---- uploads (skipped when the tape is already device resident)
     const bool dev = tape->on_device != 0;
-    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
+    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr, *d_twin_buf = nullptr; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
     u64 *d_com = nullptr, *d_com2 = nullptr, *d_value = nullptr, *d_part = nullptr;
     const uint32_t *vec = v->d + v_poly * v->rank * NL;
 #define RS_TRY(x) do { rc = (x); if (rc) goto fail; } while (0)
@@ -1165,9 +1197,14 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
     if (dev) {
         d_twin = (u64 *)tape->twin_u; d_cosac = (i64 *)tape->cosac_g; d_mlwe_s = (i64 *)tape->mlwe;
     } else {
-        RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
+        if (!gen_twin) RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
         RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
         RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
+    }
+    if (gen_twin) {       // draws come from the prover's own AES-CTR stream, generated in HBM
+        const u64 *smp = nullptr;
+        RS_TRY(uniform_stream_draw(j->twin_stream, twin * d, &d_twin_buf, &smp));
+        d_twin = (u64 *)smp;
     }
     {
         const size_t n_com = (size_t)(cols + 1) * p.in_msis;
@@ -1217,7 +1254,8 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
 fail:
 #undef RS_TRY
     cudaFreeAsync(d_aux, current_stream());
-    if (!dev) { cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); cudaFreeAsync(d_mlwe_s, current_stream()); }
+    if (!dev) { if (!gen_twin) cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); cudaFreeAsync(d_mlwe_s, current_stream()); }
+    if (d_twin_buf) cudaFreeAsync(d_twin_buf, current_stream());
     cudaFreeAsync(d_part, current_stream());
     cudaFreeAsync(d_com, current_stream()); cudaFreeAsync(d_com2, current_stream()); cudaFreeAsync(d_value, current_stream());
     if (rc) { if (!reuse) rs_opening_free(o); return rc; }

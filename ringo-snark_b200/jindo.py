@@ -76,17 +76,33 @@ class Prover:
         except Exception:
             pass
 
+    def SetTwinSeed(self, seed):
+        """Seeds the encoder's TwinCDT uniform source on the device, as csprng.NewUniformSamplerWithSeed
+        does on the host (uniform.go:38-46): key || iv = SHA-384(seed).  Commits whose tape has no
+        `twin_u` then draw from this stream in HBM instead of uploading one u64 per sample."""
+        import hashlib
+        h = hashlib.sha384(bytes(seed)).digest()
+        key = np.frombuffer(h[:32], dtype=np.uint8).copy(); iv = np.frombuffer(h[32:48], dtype=np.uint8).copy()
+        check(lib().rs_jindo_set_twin_stream(self.h, _vp(key), _vp(iv)))
+
+    def TwinStreamDraw(self, n):
+        """The next n Sample() values of the device stream (advances it)."""
+        out = np.zeros(n, dtype=np.uint64)
+        check(lib().rs_jindo_twin_stream_draw(self.h, n, _vp(out)))
+        return out
+
     def Commit(self, batch, poly, length, tape):
         """prover.go:45-62.  batch/poly/length: device-resident committed vector; tape: dict of
         numpy arrays first_row, last_row, mask_rows (uint64 Montgomery limbs), twin_u (uint64),
         cosac_g, mlwe (int64).  Returns (commitment [out_msis, n_qout, 256], Opening)."""
         keep = {k: np.ascontiguousarray(tape[k], dtype=(np.int64 if k in ("cosac_g", "mlwe") else np.uint64))
-                for k in ("first_row", "last_row", "mask_rows", "twin_u", "cosac_g", "mlwe")}
+                for k in ("first_row", "last_row", "mask_rows", "twin_u", "cosac_g", "mlwe") if tape.get(k) is not None}
         L = self.field.L
         T = capi.JindoTape()
         T.first_row, T.last_row, T.mask_rows = _vp(keep["first_row"]), _vp(keep["last_row"]), _vp(keep["mask_rows"])
         T.n_mask_rows = keep["mask_rows"].size // (L * self.p["slots"])
-        T.twin_u, T.n_twin_u = _vp(keep["twin_u"]), keep["twin_u"].size
+        if "twin_u" in keep:        # else: drawn on the device from the stream set by SetTwinSeed
+            T.twin_u, T.n_twin_u = _vp(keep["twin_u"]), keep["twin_u"].size
         T.cosac_g, T.n_cosac_polys = _vp(keep["cosac_g"]), keep["cosac_g"].size // self.d
         T.mlwe = _vp(keep["mlwe"])
         com = np.zeros((self.p["out_msis"], self.n_qout, self.d), dtype=np.uint64)

@@ -166,3 +166,48 @@ def test_gpu_proof_verifies(rs, batch):
     assert vrf.verify(x, coms, ys, pf)
     bad = list(ys); bad[0] = (bad[0] + 1) % q
     assert not vrf.verify(x, coms, bad, pf)
+
+
+def _prover_pair(rs, name, N, batch, seed):
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    p = J.new_parameters(q, N, batch)
+    tape = J.Tape(seed)
+    prv = J.Prover(p, b"Jindo!", tape)
+    gp = rs.jindo.Prover(fg, params_dict(p, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
+                         polys_array(prv.ck.Out), cdt_array(prv.ecd))
+    return q, fo, fg, p, tape, prv, gp
+
+
+def test_device_uniform_stream_matches_csprng(rs):
+    """rs_jindo_set_twin_stream / _draw against the restated csprng.UniformSampler (uniform.go:26-70):
+    AES-256-CTR + the XOR-accumulating 8 KiB refill, across refill boundaries and unaligned call sizes."""
+    q, fo, fg, p, tape, prv, gp = _prover_pair(rs, "zp255", 1024, 1, b"stream")
+    for seed in (b"\x00" * 32, bytes(range(32)), b"short"):
+        ref = J.UniformSampler(seed)
+        gp.SetTwinSeed(seed)
+        for n in (1, 100, 923, 1024, 5000, 0, 7, 300000, 1024 * 33, 1, 4097 * 1024 + 5):
+            got = gp.TwinStreamDraw(n)
+            assert np.array_equal(got, ref.sample_many(n)), (seed, n)
+
+
+def test_commit_with_device_twin_stream(rs):
+    """Two consecutive Commits drawing the TwinCDT uniforms on the device (tape.twin_u = NULL) give the
+    same Opening / Commitment as the oracle, whose encoder owns one stateful sampler (encoder.go:56-62)."""
+    q, fo, fg, p, tape, prv, gp = _prover_pair(rs, "zp128", 700, 2, b"dev-twin")
+    gp.SetTwinSeed(prv.ecd.twin.base.seed)
+    for length in (700, 333):
+        v = [J.field_set_random(tape, q) for _ in range(length)]
+        com_o, open_o = prv.commit(v)
+        B = rs.Batch(fg, 1, 1024)
+        host = np.zeros((1, 1024, fo.L), dtype=np.uint64)
+        host[0, :length] = fo.to_mont(v)
+        B.upload(host)
+        t = tape_arrays(fo, p, prv.trace)
+        assert len(t["twin_u"]) > 0
+        t["twin_u"] = None
+        com_g, open_g = gp.Commit(B, 0, length, t)
+        assert np.array_equal(com_g, polys_array(com_o))
+        for i in range(p.cols + 1):
+            for j in range(p.rows):
+                assert np.array_equal(open_g.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", i, j)
