@@ -82,7 +82,7 @@ void orc_neg(const orc_field *f, uint64_t *z, const uint64_t *x) {
 /* Montgomery CIOS product z = x*y*R^-1 mod q  (element.go:481-602 _mulGeneric).
  * One extra word keeps the running sum for moduli without a spare bit. */
 #define DEFINE_MUL(NAME, LL)                                                          \
-    static void NAME(const orc_field *f, uint64_t *z, const uint64_t *x, const uint64_t *y) { \
+    static inline void NAME(const orc_field *f, uint64_t *z, const uint64_t *x, const uint64_t *y) { \
         uint64_t t[(LL) + 2];                                                         \
         for (int i = 0; i < (LL) + 2; i++) t[i] = 0;                                  \
         const uint64_t *q = f->q;                                                     \
@@ -364,10 +364,79 @@ static inline void inv_butterfly(const orc_field *f, uint64_t *u, uint64_t *v, c
     orc_mul(f, v, v, w);
 }
 
+/* Fixed-width copies of the two transforms for the limb counts the reference's moduli use: same
+ * butterfly sequence, with the field ops inlined and unrolled so the timed CPU baseline is not handicapped
+ * by the generic-L loops (the reference's Element code is generated per modulus with fixed limb counts). */
+#define DEFINE_NTT(LL)                                                                                    \
+    static inline void add_##LL(const uint64_t *q, uint64_t *z, const uint64_t *x, const uint64_t *y) {   \
+        uint64_t t[LL], c = 0;                                                                            \
+        for (int i = 0; i < (LL); i++) { u128 s = (u128)x[i] + y[i] + c; t[i] = (uint64_t)s; c = (uint64_t)(s >> 64); } \
+        if (c || limbs_geq(t, q, (LL))) limbs_sub(t, t, q, (LL));                                         \
+        for (int i = 0; i < (LL); i++) z[i] = t[i];                                                       \
+    }                                                                                                     \
+    static inline void sub_##LL(const uint64_t *q, uint64_t *z, const uint64_t *x, const uint64_t *y) {   \
+        uint64_t t[LL];                                                                                   \
+        uint64_t b = limbs_sub(t, x, y, (LL));                                                            \
+        if (b) limbs_add(t, t, q, (LL));                                                                  \
+        for (int i = 0; i < (LL); i++) z[i] = t[i];                                                       \
+    }                                                                                                     \
+    static void ntt_in_place_##LL(const orc_ntt *t, uint64_t *p) {                                        \
+        const orc_field *f = t->f;                                                                        \
+        const uint64_t *q = f->q;                                                                         \
+        const size_t N = t->N;                                                                            \
+        size_t tt = N;                                                                                    \
+        for (size_t m = 1; m <= N / 2; m <<= 1) {                                                         \
+            tt >>= 1;                                                                                     \
+            for (size_t i = 0; i < m; i++) {                                                              \
+                size_t j1 = (i * tt) << 1, j2 = j1 + tt;                                                  \
+                const uint64_t *w = t->tw + (m + i) * (LL);                                               \
+                for (size_t j = j1; j < j2; j++) {                                                        \
+                    uint64_t *u = p + j * (LL), *v = p + (j + tt) * (LL), d[LL];                          \
+                    mul_##LL(f, v, v, w);                                                                 \
+                    add_##LL(q, u, u, v);                                                                 \
+                    add_##LL(q, d, v, v);                                                                 \
+                    sub_##LL(q, v, u, d);                                                                 \
+                }                                                                                         \
+            }                                                                                             \
+        }                                                                                                 \
+    }                                                                                                     \
+    static void intt_in_place_##LL(const orc_ntt *t, uint64_t *p) {                                       \
+        const orc_field *f = t->f;                                                                        \
+        const uint64_t *q = f->q;                                                                         \
+        const size_t N = t->N;                                                                            \
+        size_t tt = 1;                                                                                    \
+        for (size_t m = N / 2; m >= 1; m >>= 1) {                                                         \
+            for (size_t i = 0; i < m; i++) {                                                              \
+                size_t j1 = (i * tt) << 1, j2 = j1 + tt;                                                  \
+                const uint64_t *w = t->twinv + (m + i) * (LL);                                            \
+                for (size_t j = j1; j < j2; j++) {                                                        \
+                    uint64_t *u = p + j * (LL), *v = p + (j + tt) * (LL), d[LL];                          \
+                    add_##LL(q, u, u, v);                                                                 \
+                    add_##LL(q, d, v, v);                                                                 \
+                    sub_##LL(q, v, u, d);                                                                 \
+                    mul_##LL(f, v, v, w);                                                                 \
+                }                                                                                         \
+            }                                                                                             \
+            tt <<= 1;                                                                                     \
+        }                                                                                                 \
+    }
+
+DEFINE_NTT(2)
+DEFINE_NTT(4)
+DEFINE_NTT(7)
+DEFINE_NTT(14)
+
 /* ntt.go:261-275 nttInPlaceRef (the unrolled variant computes the same values) */
 static void ntt_in_place(const orc_ntt *t, uint64_t *p) {
     const orc_field *f = t->f;
     const int L = f->L;
+    switch (L) {
+        case 2: ntt_in_place_2(t, p); return;
+        case 4: ntt_in_place_4(t, p); return;
+        case 7: ntt_in_place_7(t, p); return;
+        case 14: ntt_in_place_14(t, p); return;
+        default: break;
+    }
     const size_t N = t->N;
     size_t tt = N;
     for (size_t m = 1; m <= N / 2; m <<= 1) {
@@ -384,6 +453,13 @@ static void ntt_in_place(const orc_ntt *t, uint64_t *p) {
 static void intt_in_place(const orc_ntt *t, uint64_t *p) {
     const orc_field *f = t->f;
     const int L = f->L;
+    switch (L) {
+        case 2: intt_in_place_2(t, p); return;
+        case 4: intt_in_place_4(t, p); return;
+        case 7: intt_in_place_7(t, p); return;
+        case 14: intt_in_place_14(t, p); return;
+        default: break;
+    }
     const size_t N = t->N;
     size_t tt = 1;
     for (size_t m = N / 2; m >= 1; m >>= 1) {
