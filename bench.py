@@ -358,6 +358,24 @@ def run_ours(args):
     imad_alg_total = BATCH * N * (LOGN / 2) * (2 * nl * nl + nl)       # (log2N/2)(2l^2+l) per coeff
     imad_ach = imad_alg_total / (sum(passes) * 1e-3) / 1e9
 
+    # ---- the other transforms of the sweep (BASELINE configs[1]), same batch, device resident ----
+    def timed(fn):
+        fn(); torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return BATCH * N / (a.elapsed_time(b) / 3 * 1e-3) / 1e6
+    cyc = rs.CyclicTransformer(f, N)             # buckler.Encoder / polyEval transform (encoder.go:17, compile.go:186)
+    variants = {
+        "negacyclic_inverse": timed(lambda: ntt.InvNTTTo(dst, src)),
+        "cyclic_forward": timed(lambda: cyc.FwdNTTTo(dst, src)),
+        "cyclic_inverse": timed(lambda: cyc.InvNTTTo(dst, src)),
+        "unit": "Mcoeff/s per GPU",
+        "note": "cyclic tables have tw[2^s] = 1: the opening radix-8 round skips 7 of its 12 products",
+    }
+
     # ---- e2e leg: host buffers through the C ABI, copies inside the timed region ----
     # The batch is cut into chunks that ride three streams (upload / transform / download of different
     # chunks overlap; PCIe is full duplex), exactly what a host caller streaming witnesses would do.
@@ -414,6 +432,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": float(t2.item()), "pipeline": f"{n_chunks} chunks on {n_streams} streams (pinned host memory)",
                 "result_checked": e2e_ok},
+        "ntt_variants": variants,
         "commit": commit,
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),

@@ -34,6 +34,7 @@ struct PassGeom {
     int pl;          // bit position of the pass's lowest butterfly stride (logN - s0 - K)
     int logW;        // log2 columns per tile
     int col_major;   // 1: contiguous tiles (pl == 0)
+    int triv;        // 1: tw[2^s] == 1 for every stage (cyclic tables, ntt.go:56-84) -> stage-0 rounds skip those products
     unsigned long long total_elems;   // n_polys * N
 };
 
@@ -107,7 +108,10 @@ __device__ __forceinline__ void load_twiddle(uint32_t *w, const uint32_t *__rest
 //   hi    : index of this group among the groups of the round inside its polynomial
 //   SCALE : (inverse only) the round's last stage is stage 0 of the transform: fold N^-1 in
 //   LAZY  : values are kept in [0, 2q) (field.cuh lazy variants); the caller canonicalises at the end
-template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY>
+//   TRIV  : the round starts at stage 0 of the transform (s_top == 0, hi == 0): the first twiddle of every
+//           stage is tw[2^s] = 1 (Montgomery one), so those products are skipped -- 7 of the 12 in a
+//           radix-8 round.  x * R * R^-1 = x exactly, so the values are the ones the reference computes.
+template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY, bool TRIV = false>
 __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const uint32_t *__restrict__ tw,
                                             int s_top, unsigned hi, const NttConsts<NL> &C) {
     const FieldParams<NL> &F = C.F;
@@ -121,19 +125,24 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
             uint32_t w[NL];
             constexpr bool SC = INV && SCALE;
             const bool last_scaled = SC && (beta == RR - 1);   // compile-time after unrolling
-            if (!last_scaled) load_twiddle<NL>(w, tw, tbase + g);
+            const bool triv = TRIV && (g == 0);                 // compile-time after unrolling
+            if (!last_scaled && !triv) load_twiddle<NL>(w, tw, tbase + g);
 #pragma unroll
             for (int k = 0; k < (1 << beta); k++) {
                 const int u0 = (g << (beta + 1)) + k, u1 = u0 + (1 << beta);
                 if (!INV) {
                     // ntt.go:254-259   v = v*w ; u' = u+v ; v' = u-v
                     uint32_t v[NL];
+                    if (triv) {
+#pragma unroll
+                        for (int l = 0; l < NL; l++) v[l] = x[u1][l];
+                    }
                     if (LAZY) {
-                        mont_mul_lazy<NL, QS>(v, x[u1], w, F);
+                        if (!triv) mont_mul_lazy<NL, QS>(v, x[u1], w, F);
                         mod_sub_m<NL>(x[u1], x[u0], v, F.q2);
                         mod_add_m<NL>(x[u0], x[u0], v, F.q2);
                     } else {
-                        mont_mul<NL, QS>(v, x[u1], w, F);
+                        if (!triv) mont_mul<NL, QS>(v, x[u1], w, F);
                         mod_sub<NL>(x[u1], x[u0], v, F);
                         mod_add<NL>(x[u0], x[u0], v, F);
                     }
@@ -154,6 +163,9 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u0][l] = t[l];
                         if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F); else mont_mul<NL, QS>(x[u1], d, C.ninv_w1, F);
+                    } else if (triv) {
+#pragma unroll
+                        for (int l = 0; l < NL; l++) x[u1][l] = d[l];
                     } else {
                         if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F); else mont_mul<NL, QS>(x[u1], d, w, F);
                     }
@@ -165,7 +177,7 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
 
 // rounds of one pass over the tile in shared memory
 //   FINAL : (LAZY only) this round contains the last stage of the transform: bring values back to [0, q)
-template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY, bool FINAL, int THREADS, int TS>
+template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY, bool FINAL, int THREADS, int TS, bool TRIV = false>
 __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restrict__ tw, const PassGeom &G,
                                           int lb, unsigned long long tile, const NttConsts<NL> &C) {
     // group geometry (see header comment): element u of group gid sits at base + u * ustride
@@ -197,7 +209,7 @@ __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restri
         uint32_t x[1 << RR][NL];
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) smem_load_elem<NL, TS>(x[u], sm, base + u * ustride);
-        radix_round<NL, QS, RR, INV, SCALE, LAZY>(x, tw, s_top, hi, C);
+        radix_round<NL, QS, RR, INV, SCALE, LAZY, TRIV>(x, tw, s_top, hi, C);
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) {
             if (LAZY && FINAL) cond_sub<NL>(x[u], C.F.q);
@@ -259,7 +271,11 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *__res
     // (inverse: stage 0 with the N^-1 scaling; lazy mode: the canonicalising subtraction).
     for (int r = 0; r < full; r++) {
         const int lb = INV ? r * R : K - (r + 1) * R;
-        if (LAST && rem == 0 && r == full - 1) run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS>(sm, tw, G, lb, tile, C);
+        // (the inverse's closing round and the forward's opening round sit at stage 0: trivial first twiddles)
+        if (LAST && rem == 0 && r == full - 1) {
+            if (INV && SCALE && G.triv) run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS, INV && SCALE>(sm, tw, G, lb, tile, C);
+            else run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS>(sm, tw, G, lb, tile, C);
+        } else if (!INV && r == 0 && G.s0 == 0 && G.triv) run_round<NL, QS, R, false, false, LAZY, false, THREADS, TS, true>(sm, tw, G, lb, tile, C);
         else run_round<NL, QS, R, INV, false, LAZY, false, THREADS, TS>(sm, tw, G, lb, tile, C);
         __syncthreads();
     }

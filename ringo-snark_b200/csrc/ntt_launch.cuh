@@ -70,14 +70,14 @@ int ntt_run(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, 
         const int K = (top - s + (n_row - r) - 1) / (n_row - r);   // even split of the remaining stages
         PassGeom G{};
         G.logN = logN; G.K = K; G.s0 = s; G.pl = logN - s - K; G.logW = T::LOG_TS - K; G.col_major = 0;
-        G.total_elems = total;
+        G.total_elems = total; G.triv = !t->negacyclic;
         passes[np++] = G;
         s += K;
     }
     {
         PassGeom G{};
         G.logN = logN; G.K = KB; G.s0 = top; G.pl = 0; G.logW = T::LOG_TS - KB; G.col_major = 1;
-        G.total_elems = total;
+        G.total_elems = total; G.triv = !t->negacyclic;
         passes[np++] = G;
     }
     const unsigned long long tiles_col = (total + T::TS - 1) / T::TS;

@@ -22,11 +22,12 @@ for name, logN, batch in cases:
     host = rng.integers(0, 1 << 62, size=(batch, N, f.L), dtype=np.uint64)
     host[..., f.L - 1] &= np.uint64((1 << ((q.bit_length() - 1) % 64)) - 1)
     B = rs.Batch(f, batch, N).upload(host)
-    t = rs.CyclotomicTransformer(f, N)
-    for inv in (0, 1):
-        ms = (ctypes.c_float * 16)(); n = ctypes.c_int(16)
-        assert L.rs_ntt_profile(t.h, B.h, batch, inv, 2, ms, ctypes.byref(n)) == 0
-        assert L.rs_ntt_profile(t.h, B.h, batch, inv, 5, ms, ctypes.byref(n)) == 0, L.rs_last_error()
-        tot = sum(ms[i] for i in range(n.value))
-        print(f"{name} logN={logN} batch={batch} inv={inv}: passes={[round(ms[i],3) for i in range(n.value)]} ms "
-              f"total={tot:.3f} ms  {batch*N/tot/1e3:.0f} Mcoeff/s  {batch*N*f.L*16/tot/1e6:.0f} GB/s(alg)", flush=True)
+    for kind in ("cyclic", "cyclotomic"):
+        t = rs.CyclicTransformer(f, N) if kind == "cyclic" else rs.CyclotomicTransformer(f, N)
+        for inv in (0, 1):
+            ms = (ctypes.c_float * 16)(); n = ctypes.c_int(16)
+            assert L.rs_ntt_profile(t.h, B.h, batch, inv, 2, ms, ctypes.byref(n)) == 0
+            assert L.rs_ntt_profile(t.h, B.h, batch, inv, 5, ms, ctypes.byref(n)) == 0, L.rs_last_error()
+            tot = sum(ms[i] for i in range(n.value))
+            print(f"{name} {kind} logN={logN} batch={batch} inv={inv}: passes={[round(ms[i],3) for i in range(n.value)]} ms "
+                  f"total={tot:.3f} ms  {batch*N/tot/1e3:.0f} Mcoeff/s  {batch*N*f.L*16/tot/1e6:.0f} GB/s(alg)", flush=True)
