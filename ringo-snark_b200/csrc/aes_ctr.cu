@@ -23,38 +23,52 @@ __constant__ uint8_t c_sbox[256];
 
 __device__ __forceinline__ uint32_t xtime(uint32_t x) { return ((x << 1) ^ (((x >> 7) & 1) * 0x1b)) & 0xff; }
 
-// keystream for blocks [blk0, blk0 + n): out as 16 bytes each
+// keystream for blocks [blk0, blk0 + n): out as 16 bytes each.
+// The round table Te0 is replicated 32 times in shared memory (word index*32 + lane): every lane reads
+// its own bank, so the 224 data-dependent lookups per block are conflict-free; Te1..Te3 are byte
+// rotations of Te0 (one PRMT each).
 __global__ void __launch_bounds__(256) aes_keystream_kernel(uint4 *__restrict__ out, const __grid_constant__ AesKey K,
                                                             u64 iv_hi, u64 iv_lo, u64 blk0, size_t n) {
-    __shared__ uint32_t Te0[256];
+    extern __shared__ uint32_t Te[];                 // [256][32]
+    __shared__ uint32_t Sb[256];                     // S-box for the last round, one word per entry
     {
         const uint32_t s = c_sbox[threadIdx.x], s2 = xtime(s), s3 = s2 ^ s;
-        Te0[threadIdx.x] = (s2 << 24) | (s << 16) | (s << 8) | s3;       // (02 01 01 03) * S[x], big-endian word
+        const uint32_t t = (s2 << 24) | (s << 16) | (s << 8) | s3;       // (02 01 01 03) * S[x], big-endian word
+#pragma unroll
+        for (int c = 0; c < 32; c++) Te[threadIdx.x * 32 + c] = t;
+        Sb[threadIdx.x] = s;
     }
     __syncthreads();
+    const uint32_t *T = Te + (threadIdx.x & 31);
+#define TE(b) T[(b) << 5]
+#define ROT8(x) __byte_perm((x), 0, 0x0321)
+#define ROT16(x) __byte_perm((x), 0, 0x1032)
+#define ROT24(x) __byte_perm((x), 0, 0x2103)
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         // counter = IV + (blk0 + i) as a 128-bit big-endian integer
         const u64 add = blk0 + i;
         const u64 lo = iv_lo + add, hi = iv_hi + (lo < add);
         uint32_t s0 = (uint32_t)(hi >> 32) ^ K.rk[0], s1 = (uint32_t)hi ^ K.rk[1], s2 = (uint32_t)(lo >> 32) ^ K.rk[2], s3 = (uint32_t)lo ^ K.rk[3];
-#define ROTR(x, r) (((x) >> (r)) | ((x) << (32 - (r))))
 #pragma unroll
         for (int r = 1; r < 14; r++) {
-            const uint32_t t0 = Te0[s0 >> 24] ^ ROTR(Te0[(s1 >> 16) & 0xff], 8) ^ ROTR(Te0[(s2 >> 8) & 0xff], 16) ^ ROTR(Te0[s3 & 0xff], 24) ^ K.rk[4 * r];
-            const uint32_t t1 = Te0[s1 >> 24] ^ ROTR(Te0[(s2 >> 16) & 0xff], 8) ^ ROTR(Te0[(s3 >> 8) & 0xff], 16) ^ ROTR(Te0[s0 & 0xff], 24) ^ K.rk[4 * r + 1];
-            const uint32_t t2 = Te0[s2 >> 24] ^ ROTR(Te0[(s3 >> 16) & 0xff], 8) ^ ROTR(Te0[(s0 >> 8) & 0xff], 16) ^ ROTR(Te0[s1 & 0xff], 24) ^ K.rk[4 * r + 2];
-            const uint32_t t3 = Te0[s3 >> 24] ^ ROTR(Te0[(s0 >> 16) & 0xff], 8) ^ ROTR(Te0[(s1 >> 8) & 0xff], 16) ^ ROTR(Te0[s2 & 0xff], 24) ^ K.rk[4 * r + 3];
+            const uint32_t t0 = TE(s0 >> 24) ^ ROT8(TE((s1 >> 16) & 0xff)) ^ ROT16(TE((s2 >> 8) & 0xff)) ^ ROT24(TE(s3 & 0xff)) ^ K.rk[4 * r];
+            const uint32_t t1 = TE(s1 >> 24) ^ ROT8(TE((s2 >> 16) & 0xff)) ^ ROT16(TE((s3 >> 8) & 0xff)) ^ ROT24(TE(s0 & 0xff)) ^ K.rk[4 * r + 1];
+            const uint32_t t2 = TE(s2 >> 24) ^ ROT8(TE((s3 >> 16) & 0xff)) ^ ROT16(TE((s0 >> 8) & 0xff)) ^ ROT24(TE(s1 & 0xff)) ^ K.rk[4 * r + 2];
+            const uint32_t t3 = TE(s3 >> 24) ^ ROT8(TE((s0 >> 16) & 0xff)) ^ ROT16(TE((s1 >> 8) & 0xff)) ^ ROT24(TE(s2 & 0xff)) ^ K.rk[4 * r + 3];
             s0 = t0; s1 = t1; s2 = t2; s3 = t3;
         }
-#undef ROTR
         // final round: SubBytes + ShiftRows + AddRoundKey
-        const uint32_t o0 = ((uint32_t)c_sbox[s0 >> 24] << 24 | (uint32_t)c_sbox[(s1 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s2 >> 8) & 0xff] << 8 | c_sbox[s3 & 0xff]) ^ K.rk[56];
-        const uint32_t o1 = ((uint32_t)c_sbox[s1 >> 24] << 24 | (uint32_t)c_sbox[(s2 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s3 >> 8) & 0xff] << 8 | c_sbox[s0 & 0xff]) ^ K.rk[57];
-        const uint32_t o2 = ((uint32_t)c_sbox[s2 >> 24] << 24 | (uint32_t)c_sbox[(s3 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s0 >> 8) & 0xff] << 8 | c_sbox[s1 & 0xff]) ^ K.rk[58];
-        const uint32_t o3 = ((uint32_t)c_sbox[s3 >> 24] << 24 | (uint32_t)c_sbox[(s0 >> 16) & 0xff] << 16 | (uint32_t)c_sbox[(s1 >> 8) & 0xff] << 8 | c_sbox[s2 & 0xff]) ^ K.rk[59];
+        const uint32_t o0 = (Sb[s0 >> 24] << 24 | Sb[(s1 >> 16) & 0xff] << 16 | Sb[(s2 >> 8) & 0xff] << 8 | Sb[s3 & 0xff]) ^ K.rk[56];
+        const uint32_t o1 = (Sb[s1 >> 24] << 24 | Sb[(s2 >> 16) & 0xff] << 16 | Sb[(s3 >> 8) & 0xff] << 8 | Sb[s0 & 0xff]) ^ K.rk[57];
+        const uint32_t o2 = (Sb[s2 >> 24] << 24 | Sb[(s3 >> 16) & 0xff] << 16 | Sb[(s0 >> 8) & 0xff] << 8 | Sb[s1 & 0xff]) ^ K.rk[58];
+        const uint32_t o3 = (Sb[s3 >> 24] << 24 | Sb[(s0 >> 16) & 0xff] << 16 | Sb[(s1 >> 8) & 0xff] << 8 | Sb[s2 & 0xff]) ^ K.rk[59];
         // words are big-endian byte strings; memory order = byte order
         out[i] = make_uint4(__byte_perm(o0, 0, 0x0123), __byte_perm(o1, 0, 0x0123), __byte_perm(o2, 0, 0x0123), __byte_perm(o3, 0, 0x0123));
     }
+#undef TE
+#undef ROT8
+#undef ROT16
+#undef ROT24
 }
 
 constexpr int CH_WORDS = 1024;              // u64 words per 8 KiB chunk (uniform.go:12 bufSize)
@@ -120,6 +134,8 @@ struct UniformStream {
     u64 iv_hi, iv_lo;
     u64 pos;             // samples handed out so far
     u64 *d_state;        // 1024 words: current contents of the sampler's 8 KiB buffer
+    cudaStream_t side;   // generation runs here, so it overlaps the caller's uploads on the main stream
+    cudaEvent_t ready;
 };
 
 static bool g_sbox_uploaded = false;
@@ -132,19 +148,27 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
     s->pos = 0;
     RS_CUDA_CHECK(cudaMalloc((void **)&s->d_state, CH_WORDS * 8));
     RS_CUDA_CHECK(cudaMemset(s->d_state, 0, CH_WORDS * 8));
+    RS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
     if (!g_sbox_uploaded) { RS_CUDA_CHECK(cudaMemcpyToSymbol(c_sbox, h_sbox, 256)); g_sbox_uploaded = true; }
     *out = s;
     return RS_OK;
 }
-void uniform_stream_free(UniformStream *s) { if (s) { cudaFree(s->d_state); delete s; } }
+void uniform_stream_free(UniformStream *s) {
+    if (!s) return;
+    cudaStreamSynchronize(s->side);
+    cudaFree(s->d_state); cudaEventDestroy(s->ready); cudaStreamDestroy(s->side);
+    delete s;
+}
 
-// Produces the next n Sample() values of the stream in HBM and advances it.
+// Produces the next n Sample() values of the stream in HBM and advances it.  The kernels run on the
+// stream's own side stream; the current stream is made to wait for them before this returns.
 // *d_buf is the allocation (cudaFreeAsync it on the current stream when done), *d_samples points at sample 0.
 // Layout of the allocation: [ current 8 KiB buffer of the sampler | every chunk refilled by this call ].
 int uniform_stream_draw(UniformStream *s, size_t n, u64 **d_buf, const u64 **d_samples) {
     *d_buf = nullptr; *d_samples = nullptr;
     if (n == 0) return RS_OK;
-    cudaStream_t st = current_stream();
+    cudaStream_t st = s->side;
     const u64 off = s->pos % CH_WORDS;
     const u64 c_start = s->pos / CH_WORDS + (off ? 1 : 0);                  // first chunk not yet refilled
     const u64 c_end = (s->pos + n + CH_WORDS - 1) / CH_WORDS;
@@ -154,7 +178,7 @@ int uniform_stream_draw(UniformStream *s, size_t n, u64 **d_buf, const u64 **d_s
     RS_CUDA_CHECK(cudaMemcpyAsync(buf, s->d_state, CH_WORDS * 8, cudaMemcpyDeviceToDevice, st));
     if (n_chunks) {
         u64 *ks = buf + CH_WORDS;
-        aes_keystream_kernel<<<148 * 8, 256, 0, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
+        aes_keystream_kernel<<<148 * 4, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
         const int seg = n_chunks > 4096 ? 256 : (n_chunks > 64 ? 16 : 1);
         const size_t n_seg = (n_chunks + seg - 1) / seg;
         u64 *d_tot = nullptr;
@@ -170,6 +194,8 @@ int uniform_stream_draw(UniformStream *s, size_t n, u64 **d_buf, const u64 **d_s
         cudaFreeAsync(d_tot, st);
         if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(buf, st); return set_error(RS_ERR_CUDA, "uniform_stream_draw: launch failed"); }
     }
+    RS_CUDA_CHECK(cudaEventRecord(s->ready, st));
+    RS_CUDA_CHECK(cudaStreamWaitEvent(current_stream(), s->ready, 0));
     s->pos += n;
     *d_buf = buf;
     *d_samples = buf + (off ? off : CH_WORDS);

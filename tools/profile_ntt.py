@@ -16,9 +16,13 @@ host = rng.integers(0, 1 << 62, size=(batch, N, f.L), dtype=np.uint64)
 host[..., f.L - 1] &= np.uint64((1 << ((q.bit_length() - 1) % 64)) - 1)
 B = rs.Batch(f, batch, N).upload(host)
 t = rs.CyclotomicTransformer(f, N)
+c = rs.CyclicTransformer(f, N)
 for _ in range(3):
     t.FwdNTTTo(B, B)
     t.InvNTTTo(B, B)
+for _ in range(2):
+    c.FwdNTTTo(B, B)
+    c.InvNTTTo(B, B)
 assert L.rs_sync() == 0
 assert np.array_equal(B.download(), host)
 print("ok")
