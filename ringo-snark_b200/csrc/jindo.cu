@@ -71,6 +71,7 @@ struct rs_jindo {
     u64 *d_roots;           // all twiddle tables
     u64 *d_ck_in, *d_ck_mlwe, *d_ck_out;
     u64 *d_cdt;
+    uint8_t *d_cdt_guide;   // [128][257]: number of table entries below b << 56 (search window per top byte of u)
     u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
     rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
 };
@@ -108,10 +109,9 @@ __host__ __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >
 
 // signed 64-bit value -> canonical residue (setCoeffSigned utils.go:49-60 followed by MForm's reduction)
 __device__ __forceinline__ u64 signed_res(i64 c, u64 q) {
-    if (c >= 0) { u64 u = (u64)c; return u >= q ? u % q : u; }
-    u64 m = (u64)(-c);
-    if (m >= q) m %= q;
-    return m ? q - m : 0;
+    u64 m = (u64)(c < 0 ? -c : c);
+    if (__builtin_expect(m >= q, 0)) m %= q;              // never for Gaussian-sized values; kept for the contract
+    return (c < 0 && m) ? q - m : m;
 }
 
 // 256-point negacyclic NTT of one limb in shared memory, Montgomery domain, 128 threads (t in [0,128)).
@@ -245,7 +245,8 @@ template <int NL>
 __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, const EncDesc *__restrict__ descs, int n_descs,
                                                      const uint32_t *__restrict__ vec, const uint32_t *__restrict__ aux,
                                                      const u64 *__restrict__ twin_u, const i64 *__restrict__ given,
-                                                     const u64 *__restrict__ cdt, const __grid_constant__ RingDev R,
+                                                     const u64 *__restrict__ cdt, const uint8_t *__restrict__ guide,
+                                                     const __grid_constant__ RingDev R,
                                                      const __grid_constant__ EncConsts E,
                                                      const __grid_constant__ FieldParams<NL> F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -330,12 +331,28 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             {
                 const u64 *t0 = cdt + (size_t)c0 * E.cdt_len, *t1 = cdt + (size_t)c1 * E.cdt_len;
                 int l0 = 0, l1 = 0;
-                for (int half = E.cdt_pow2; half >= 1; half >>= 1) {
-                    const int p0 = l0 + half, p1 = l1 + half;
-                    const u64 a0 = (p0 <= E.cdt_len) ? __ldg(t0 + p0 - 1) : ~0ull;
-                    const u64 a1 = (p1 <= E.cdt_len) ? __ldg(t1 + p1 - 1) : ~0ull;
-                    if (p0 <= E.cdt_len && a0 < u) l0 = p0;
-                    if (p1 <= E.cdt_len && a1 < u) l1 = p1;
+                if (guide) {
+                    // the top byte of u narrows the lower bound to [guide[b], guide[b+1]]: 0-1 probes for the
+                    // bulk of the distribution, log2(tail length) for the two tail buckets
+                    const unsigned b = (unsigned)(u >> 56);
+                    const uint8_t *g0p = guide + c0 * 257 + b, *g1p = guide + c1 * 257 + b;
+                    int h0 = g0p[1], h1 = g1p[1];
+                    l0 = g0p[0]; l1 = g1p[0];
+                    while (l0 < h0 || l1 < h1) {
+                        const int m0 = (l0 + h0) >> 1, m1 = (l1 + h1) >> 1;
+                        const u64 a0 = (l0 < h0) ? __ldg(t0 + m0) : ~0ull;
+                        const u64 a1 = (l1 < h1) ? __ldg(t1 + m1) : ~0ull;
+                        if (l0 < h0) { if (a0 < u) l0 = m0 + 1; else h0 = m0; }
+                        if (l1 < h1) { if (a1 < u) l1 = m1 + 1; else h1 = m1; }
+                    }
+                } else {
+                    for (int half = E.cdt_pow2; half >= 1; half >>= 1) {
+                        const int p0 = l0 + half, p1 = l1 + half;
+                        const u64 a0 = (p0 <= E.cdt_len) ? __ldg(t0 + p0 - 1) : ~0ull;
+                        const u64 a1 = (p1 <= E.cdt_len) ? __ldg(t1 + p1 - 1) : ~0ull;
+                        if (p0 <= E.cdt_len && a0 < u) l0 = p0;
+                        if (p1 <= E.cdt_len && a1 < u) l1 = p1;
+                    }
                 }
                 if (l0 < E.cdt_len && __ldg(t0 + l0) == u) l0 -= 1;
                 if (l1 < E.cdt_len && __ldg(t1 + l1) == u) l1 -= 1;
@@ -941,7 +958,7 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
         configured = true;
     }
     encode_kernel<NL><<<(unsigned)((n + G - 1) / G), 256, smem, current_stream()>>>(out, d_descs, (int)n, vec, aux, twin_u, given,
-                                                                                   j->d_cdt, j->rq, E, F);
+                                                                                   j->d_cdt, j->d_cdt_guide, j->rq, E, F);
     count_launch();
     RS_CUDA_CHECK(cudaGetLastError());
     return RS_OK;
@@ -1032,6 +1049,20 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
     if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_mlwe, ck_mlwe, n_ml * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_out, ck_out, n_out * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(j->d_cdt, cdt_tables, n_cdt * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && p->cdt_len <= 255 && !getenv("RS_JINDO_NOGUIDE")) {
+        // guide[t][b] = #{ i : table_t[i] < b << 56 }, b = 0..256 (tables are sorted: gaussian_twin_cdt.go:13-35)
+        std::vector<uint8_t> guide((size_t)128 * 257);
+        for (int t = 0; t < 128; t++) {
+            const uint64_t *tab = cdt_tables + (size_t)t * p->cdt_len;
+            int i = 0;
+            for (int b = 0; b <= 256; b++) {
+                while (i < p->cdt_len && (b == 256 || tab[i] < ((uint64_t)b << 56))) i++;
+                guide[(size_t)t * 257 + b] = (uint8_t)i;
+            }
+        }
+        e = cudaMalloc((void **)&j->d_cdt_guide, guide.size());
+        if (e == cudaSuccess) e = cudaMemcpy(j->d_cdt_guide, guide.data(), guide.size(), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) { rs_jindo_destroy(j); return set_error(RS_ERR_CUDA, "rs_jindo_create: %s", cudaGetErrorString(e)); }
     j->rq.roots = j->d_roots;
     j->rq.roots_inv = j->d_roots + (size_t)p->n_q * JD;
@@ -1047,7 +1078,7 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
 
 void rs_jindo_destroy(rs_jindo *j) {
     if (!j) return;
-    cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt);
+    cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt); cudaFree(j->d_cdt_guide);
     if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
     cudaFree(j->d_ndescs);
     rs::uniform_stream_free(j->twin_stream);
