@@ -211,3 +211,109 @@ def test_commit_with_device_twin_stream(rs):
         for i in range(p.cols + 1):
             for j in range(p.rows):
                 assert np.array_equal(open_g.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", i, j)
+
+
+def test_commit_full_size_properties(rs):
+    """BASELINE configs[2]: one Commit of 2^22 coefficients over the 255-bit field (NewParameters(2^22, 1)),
+    synthetic key and tape.  The Python restatement cannot commit at this size, so the check is through
+    size-independent properties of the result:
+      (1) decode: every encoded polynomial evaluates, at X^slots = b, to the field elements it carries
+          (encoder.go:120-146 digits + (X^slots - b) g, and b^exp = -1 mod q) -- sampled over data rows,
+          first / last rows, the mask column and the ragged tail;
+      (2) one inner-commitment column recomputed from the downloaded Opening with the oracle's ring
+          arithmetic and cut-off pipeline (prover.go:144-176) equals Opening.InCommit;
+      (3) the same tape gives the same commitment (determinism)."""
+    name, N = "zp255", 1 << 22
+    length = N - 12345                                    # ragged: the last data row is partial
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    p = J.new_parameters(q, N, 1)
+    ecd = J.Encoder(p, J.Tape(b"full-size"))
+    rng = np.random.default_rng(2022)
+
+    def rpolys(shape, primes):
+        a = np.empty(shape + (len(primes), p.d), dtype=np.uint64)
+        for l, pr in enumerate(primes):
+            a[..., l, :] = rng.integers(0, pr, size=shape + (p.d,), dtype=np.uint64)
+        return a
+
+    def felems(n):                                        # Montgomery limbs of canonical elements (top limb < 2^62 < q's)
+        return rng.integers(0, 1 << 62, size=(n, fo.L), dtype=np.uint64)
+    cs = p.cols * p.slots
+    data_rows = [r for r in range(1, p.rows - 1) if r * cs <= length]          # mask column rule (prover.go:103)
+    # data columns: row r of column i exists while r*cs + i*slots <= len(v)   (note '>' in prover.go:121)
+    col_rows = [sum(1 for r in range(1, p.rows - 1) if r * cs + i * p.slots <= length) for i in range(p.cols)]
+    n_twin = sum(col_rows) + p.cols; n_mask = len(data_rows) + 2; n_cosac = p.cols + n_mask
+    n_noise = (p.cols + 1) * (p.in_msis + p.mlwe)
+    ck_in, ck_mlwe = rpolys((p.in_msis, p.rows), p.q_primes), rpolys((p.in_msis, p.mlwe), p.q_primes)
+    ck_out = rpolys((p.out_msis, p.in_com_dcmp_len), p.qout_primes)
+    tape = {"first_row": felems(cs), "last_row": felems(cs), "mask_rows": felems(n_mask * p.slots),
+            "twin_u": rng.integers(0, 1 << 63, size=n_twin * p.d, dtype=np.int64).view(np.uint64),
+            "cosac_g": rng.integers(-5000, 5000, size=n_cosac * p.d, dtype=np.int64),
+            "mlwe": rng.integers(-20, 20, size=n_noise * p.d, dtype=np.int64)}
+    gp = rs.jindo.Prover(fg, params_dict(p, ecd), ck_in, ck_mlwe, ck_out, cdt_array(ecd))
+    v = felems(length)
+    B = rs.Batch(fg, 1, N)
+    host = np.zeros((1, N, fo.L), dtype=np.uint64); host[0, :length] = v
+    B.upload(host)
+    com, op = gp.Commit(B, 0, length, tape)
+
+    ring = p.ringQ
+    rec = J.RNSReconstructor(ring)
+    R = 1 << (64 * fo.L)
+
+    def to_int(limbs):                                    # Montgomery limbs -> canonical value
+        x = sum(int(w) << (64 * k) for k, w in enumerate(limbs))
+        return x * pow(R, -1, q) % q
+
+    def decode(poly):                                     # NTT+Montgomery ring polynomial -> slots field values
+        c = rec.reconstruct(ring.intt(ring.imform([[int(x) for x in limb] for limb in poly])))
+        return [sum(c[k * p.slots + s] * pow(p.base, k, q) for k in range(p.exp)) % q for s in range(p.slots)]
+
+    # (1) decode property on sampled polynomials
+    last_data = data_rows[-1]
+    samples = [(0, 1), (p.cols - 1, 1), (7, 100), (p.cols // 2, last_data // 2), (0, last_data), (p.cols - 1, last_data),
+               (3, 0), (p.cols - 1, 0), (5, p.rows - 1), (p.cols, 0), (p.cols, 3), (p.cols, p.rows - 1)]
+    samples += [(int(rng.integers(0, p.cols)), int(rng.integers(1, last_data))) for _ in range(12)]
+    mask_index = {0: 0, p.rows - 1: n_mask - 1}
+    for (i, j) in samples:
+        got = decode(op.Encode(i, j))
+        if i == p.cols:
+            m = mask_index.get(j, j)
+            exp = [to_int(e) for e in tape["mask_rows"][m * p.slots:(m + 1) * p.slots]]
+        elif j == 0:
+            exp = [to_int(e) for e in tape["first_row"][i * p.slots:(i + 1) * p.slots]]
+        elif j == p.rows - 1:
+            exp = [to_int(e) for e in tape["last_row"][i * p.slots:(i + 1) * p.slots]]
+        else:
+            s0 = j * cs + i * p.slots
+            if s0 > length:                                   # no such row: zero polynomial
+                assert not op.Encode(i, j).any()
+                continue
+            exp = [to_int(v[s0 + s]) if s0 + s < length else 0 for s in range(p.slots)]
+        assert got == exp, ("decode", i, j)
+    # rows past len(v) stay zero polynomials (prover.go:118-125)
+    if last_data + 1 < p.rows - 1:
+        assert not op.Encode(0, last_data + 1).any()
+    short = [i for i in range(p.cols) if col_rows[i] < len(data_rows)]
+    if short:
+        assert not op.Encode(short[-1], last_data).any()
+
+    # (2) inner commitment of one column, one output index, from the downloaded Opening
+    i_col, o_idx = 5, 3
+    prv = J.Prover.__new__(J.Prover)                      # only cut_pipeline's state is needed
+    prv.p = p; prv.rns_out = J.RNSReconstructor(p.ringQOut)
+    acc = ring.new_poly()
+    for k in range(p.rows):
+        e = op.Encode(i_col, k)
+        if e.any():
+            acc = ring.mul_mont_then_add(ck_in[o_idx, k].tolist(), e.tolist(), acc)
+    for k in range(p.mlwe):
+        acc = ring.mul_mont_then_add(ck_mlwe[o_idx, k].tolist(), op.MLWE(i_col, k).tolist(), acc)
+    acc = ring.add(op.MLWE(i_col, p.mlwe + o_idx).tolist(), acc)
+    expect = prv.cut_pipeline(ring, rec, acc, p.log_in_cut)
+    assert np.array_equal(op.InCommit(i_col * p.in_msis + o_idx), polys_array(expect))
+
+    # (3) determinism
+    com2, _ = gp.Commit(B, 0, length, tape)
+    assert np.array_equal(com, com2)
