@@ -221,9 +221,8 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
     tape_bytes = sum(t.numel() * 8 for t in pin.values())
 
     def timed_e2e(T):
-        def one():
-            rs.check(L.rs_batch_upload(B.h, 0, 1, ctypes.c_void_p(v_host.data_ptr())))
-            gp.CommitInto(B, 0, N, T, op, com)
+        def one():                                  # v and the tape start in pinned host memory
+            gp.CommitHostInto(v_host.data_ptr(), N, T, op, com)
         one()
         barrier()
         t0 = time.perf_counter()
@@ -255,7 +254,8 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
         "gpu_launches_per_commit": int(launches), "deterministic": deterministic,
         "e2e": {"value": world * 1e3 / e2e_ms, "unit": "polys/s", "ms_per_commit": e2e_ms,
                 "h2d_bytes_per_step": nb + tape_bytes - twin_bytes, "d2h_bytes_per_step": int(com.nbytes),
-                "sampler": "TwinCDT uniforms drawn on the device (AES-256-CTR stream, rs_jindo_set_twin_stream)"},
+                "sampler": "TwinCDT uniforms drawn on the device (AES-256-CTR stream, rs_jindo_set_twin_stream)",
+                "call": "rs_jindo_commit_host: v uploaded in 8 pieces behind the encode kernels"},
         "e2e_host_tape": {"value": world * 1e3 / host_tape_ms, "unit": "polys/s", "ms_per_commit": host_tape_ms,
                           "h2d_bytes_per_step": nb + tape_bytes, "d2h_bytes_per_step": int(com.nbytes),
                           "sampler": "one u64 per TwinCDT sample uploaded from pinned host memory"},

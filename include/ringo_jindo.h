@@ -93,6 +93,11 @@ typedef struct rs_jindo_tape {
  * *open: NULL on entry -> a new Opening is allocated; otherwise the given Opening is overwritten. */
 int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
                     rs_opening **open, uint64_t *commitment_out);
+/* Same Commit with v in host memory (len elements, L64 limbs each, Montgomery form; pinned memory for
+ * overlap): v is uploaded in pieces on a copy stream while earlier pieces are already being encoded, so
+ * the upload hides behind the encode kernels.  The tape must be host resident too. */
+int rs_jindo_commit_host(rs_jindo *j, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
+                         rs_opening **open, uint64_t *commitment_out);
 void rs_opening_free(rs_opening *o);
 /* accessors (tests / the Go shim's Opening view): kind 0 = Encode[col][row] (ringQ),
  * 1 = MLWE[col][idx] (ringQ), 2 = InCommit[idx] (ringQOut, col ignored) */

@@ -135,7 +135,11 @@ struct UniformStream {
     u64 pos;             // samples handed out so far
     u64 *d_state;        // 1024 words: current contents of the sampler's 8 KiB buffer
     cudaStream_t side;   // generation runs here, so it overlaps the caller's uploads on the main stream
-    cudaEvent_t ready;
+    cudaEvent_t ready, consumed;
+    u64 *d_out;          // output buffer, reused by every draw (grown on demand)
+    size_t out_words;
+    u64 *d_tot;          // segment totals of the scan
+    size_t tot_words;
 };
 
 static bool g_sbox_uploaded = false;
@@ -150,6 +154,8 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
     RS_CUDA_CHECK(cudaMemset(s->d_state, 0, CH_WORDS * 8));
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
     RS_CUDA_CHECK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&s->consumed, cudaEventDisableTiming));
+    s->d_out = s->d_tot = nullptr; s->out_words = s->tot_words = 0;
     if (!g_sbox_uploaded) { RS_CUDA_CHECK(cudaMemcpyToSymbol(c_sbox, h_sbox, 256)); g_sbox_uploaded = true; }
     *out = s;
     return RS_OK;
@@ -157,49 +163,59 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
 void uniform_stream_free(UniformStream *s) {
     if (!s) return;
     cudaStreamSynchronize(s->side);
-    cudaFree(s->d_state); cudaEventDestroy(s->ready); cudaStreamDestroy(s->side);
+    cudaFree(s->d_state); cudaFree(s->d_out); cudaFree(s->d_tot);
+    cudaEventDestroy(s->ready); cudaEventDestroy(s->consumed); cudaStreamDestroy(s->side);
     delete s;
 }
 
 // Produces the next n Sample() values of the stream in HBM and advances it.  The kernels run on the
 // stream's own side stream; the current stream is made to wait for them before this returns.
-// *d_buf is the allocation (cudaFreeAsync it on the current stream when done), *d_samples points at sample 0.
-// Layout of the allocation: [ current 8 KiB buffer of the sampler | every chunk refilled by this call ].
-int uniform_stream_draw(UniformStream *s, size_t n, u64 **d_buf, const u64 **d_samples) {
-    *d_buf = nullptr; *d_samples = nullptr;
+// *d_samples points at sample 0 inside the stream's reusable output buffer: call uniform_stream_release on
+// the consuming stream once the kernels reading it have been launched (the next draw waits for that).
+// Layout of the buffer: [ current 8 KiB buffer of the sampler | every chunk refilled by this call ].
+int uniform_stream_draw(UniformStream *s, size_t n, const u64 **d_samples) {
+    *d_samples = nullptr;
     if (n == 0) return RS_OK;
     cudaStream_t st = s->side;
     const u64 off = s->pos % CH_WORDS;
     const u64 c_start = s->pos / CH_WORDS + (off ? 1 : 0);                  // first chunk not yet refilled
     const u64 c_end = (s->pos + n + CH_WORDS - 1) / CH_WORDS;
     const size_t n_chunks = c_end > c_start ? (size_t)(c_end - c_start) : 0;
-    u64 *buf = nullptr;
-    RS_CUDA_CHECK(cudaMallocAsync((void **)&buf, (n_chunks + 1) * CH_WORDS * 8, st));
+    const int seg = n_chunks > 4096 ? 256 : (n_chunks > 64 ? 16 : 1);
+    const size_t n_seg = n_chunks ? (n_chunks + seg - 1) / seg : 0;
+    RS_CUDA_CHECK(cudaStreamWaitEvent(st, s->consumed, 0));                 // previous consumer is done with d_out
+    if ((n_chunks + 1) * CH_WORDS > s->out_words || n_seg * CH_WORDS > s->tot_words) {
+        RS_CUDA_CHECK(cudaStreamSynchronize(st));
+        if ((n_chunks + 1) * CH_WORDS > s->out_words) {
+            cudaFree(s->d_out); s->d_out = nullptr; s->out_words = 0;
+            RS_CUDA_CHECK(cudaMalloc((void **)&s->d_out, (n_chunks + 1) * CH_WORDS * 8));
+            s->out_words = (n_chunks + 1) * CH_WORDS;
+        }
+        if (n_seg * CH_WORDS > s->tot_words) {
+            cudaFree(s->d_tot); s->d_tot = nullptr; s->tot_words = 0;
+            RS_CUDA_CHECK(cudaMalloc((void **)&s->d_tot, n_seg * CH_WORDS * 8));
+            s->tot_words = n_seg * CH_WORDS;
+        }
+    }
+    u64 *buf = s->d_out;
     RS_CUDA_CHECK(cudaMemcpyAsync(buf, s->d_state, CH_WORDS * 8, cudaMemcpyDeviceToDevice, st));
     if (n_chunks) {
         u64 *ks = buf + CH_WORDS;
         aes_keystream_kernel<<<148 * 4, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
-        const int seg = n_chunks > 4096 ? 256 : (n_chunks > 64 ? 16 : 1);
-        const size_t n_seg = (n_chunks + seg - 1) / seg;
-        u64 *d_tot = nullptr;
-        if (cudaMallocAsync((void **)&d_tot, n_seg * CH_WORDS * 8, st) != cudaSuccess) {
-            cudaFreeAsync(buf, st);
-            return set_error(RS_ERR_CUDA, "uniform_stream_draw: cudaMallocAsync failed");
-        }
         dim3 grid(CH_WORDS / 256, (unsigned)n_seg);
-        xor_scan_totals<<<grid, 256, 0, st>>>(d_tot, ks, n_chunks, seg);
-        xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(d_tot, s->d_state, n_seg);
-        xor_scan_apply<<<grid, 256, 0, st>>>(ks, d_tot, n_chunks, seg);
+        xor_scan_totals<<<grid, 256, 0, st>>>(s->d_tot, ks, n_chunks, seg);
+        xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, s->d_state, n_seg);
+        xor_scan_apply<<<grid, 256, 0, st>>>(ks, s->d_tot, n_chunks, seg);
         count_launch(4);
-        cudaFreeAsync(d_tot, st);
-        if (cudaGetLastError() != cudaSuccess) { cudaFreeAsync(buf, st); return set_error(RS_ERR_CUDA, "uniform_stream_draw: launch failed"); }
+        RS_CUDA_CHECK(cudaGetLastError());
     }
     RS_CUDA_CHECK(cudaEventRecord(s->ready, st));
     RS_CUDA_CHECK(cudaStreamWaitEvent(current_stream(), s->ready, 0));
     s->pos += n;
-    *d_buf = buf;
     *d_samples = buf + (off ? off : CH_WORDS);
     return RS_OK;
 }
+
+void uniform_stream_release(UniformStream *s) { cudaEventRecord(s->consumed, current_stream()); }
 
 }  // namespace rs

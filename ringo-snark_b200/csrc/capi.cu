@@ -147,6 +147,15 @@ int rs_init(int device) {
     cudaDeviceProp p;
     RS_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
     if (p.major != 10) return set_error(RS_ERR_CUDA, "device %s is sm_%d%d; kernels are built for sm_100a only", p.name, p.major, p.minor);
+    // per-call scratch (tapes, partial sums, sampler output: hundreds of MB per Commit) comes from the
+    // stream-ordered pool; keep it cached across synchronisations instead of returning it to the driver
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     return RS_OK;
 }
 

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/ringo_jindo.h"
@@ -48,17 +49,23 @@ struct CrtDev {             // RNSReconstructor constants of the *source* ring (
 };
 
 namespace rs { struct EncDesc; }
+constexpr int RS_VCHUNKS = 8;
 struct DescCache {            // encode descriptors of one committed length, resident on the device
     size_t len;
     rs::EncDesc *d_descs;
     size_t n_descs, twin, cosac, mask;
+    // descriptors are ordered by row of the committed matrix, i.e. by ascending offset into v: chunk k
+    // (descriptors [chunk_desc[k], chunk_desc[k+1])) needs v[0, chunk_vhi[k]) -- lets a host-resident v
+    // upload in pieces while earlier pieces are already being encoded (rs_jindo_commit_host)
+    size_t chunk_desc[RS_VCHUNKS + 1], chunk_vhi[RS_VCHUNKS];
 };
 
 namespace rs {
 struct UniformStream;
 int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_t iv[16]);
 void uniform_stream_free(UniformStream *s);
-int uniform_stream_draw(UniformStream *s, size_t n, u64 **d_buf, const u64 **d_samples);
+int uniform_stream_draw(UniformStream *s, size_t n, const u64 **d_samples);
+void uniform_stream_release(UniformStream *s);
 }  // namespace rs
 
 struct rs_jindo {
@@ -74,6 +81,8 @@ struct rs_jindo {
     uint8_t *d_cdt_guide;   // [128][257]: number of table entries below b << 56 (search window per top byte of u)
     u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
     rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
+    cudaStream_t copy_stream;         // rs_jindo_commit_host: uploads of v pieces
+    cudaEvent_t ev_alloc, ev_piece[RS_VCHUNKS];
 };
 
 struct rs_opening {
@@ -1072,12 +1081,20 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
     j->rqo.roots_inv = j->rqo.roots + (size_t)p->n_qout * JD;
     j->rqo.roots_plain = j->rqo.roots + (size_t)2 * p->n_qout * JD;
     j->rqo.roots_shoup = j->rqo.roots + (size_t)3 * p->n_qout * JD;
+    cudaStreamCreateWithFlags(&j->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&j->ev_alloc, cudaEventDisableTiming);
+    for (int k = 0; k < RS_VCHUNKS; k++) cudaEventCreateWithFlags(&j->ev_piece[k], cudaEventDisableTiming);
     *out = j;
     return RS_OK;
 }
 
 void rs_jindo_destroy(rs_jindo *j) {
     if (!j) return;
+    if (j->copy_stream) {
+        cudaStreamSynchronize(j->copy_stream);
+        cudaStreamDestroy(j->copy_stream); cudaEventDestroy(j->ev_alloc);
+        for (int k = 0; k < RS_VCHUNKS; k++) cudaEventDestroy(j->ev_piece[k]);
+    }
     cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt); cudaFree(j->d_cdt_guide);
     if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
     cudaFree(j->d_ndescs);
@@ -1094,12 +1111,12 @@ int rs_jindo_set_twin_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *i
 
 int rs_jindo_twin_stream_draw(rs_jindo *j, size_t n, uint64_t *out) {
     RS_REQUIRE(j && j->twin_stream && (out || n == 0), RS_ERR_ARG, "rs_jindo_twin_stream_draw: no stream / null argument");
-    u64 *buf = nullptr; const u64 *smp = nullptr;
-    int rc = rs::uniform_stream_draw(j->twin_stream, n, &buf, &smp);
+    const u64 *smp = nullptr;
+    int rc = rs::uniform_stream_draw(j->twin_stream, n, &smp);
     if (rc || n == 0) return rc;
     cudaError_t e = cudaMemcpyAsync(out, smp, n * 8, cudaMemcpyDeviceToHost, rs::current_stream());
+    rs::uniform_stream_release(j->twin_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(rs::current_stream());
-    cudaFreeAsync(buf, rs::current_stream());
     if (e != cudaSuccess) return rs::set_error(RS_ERR_CUDA, "rs_jindo_twin_stream_draw: %s", cudaGetErrorString(e));
     return RS_OK;
 }
@@ -1137,14 +1154,13 @@ int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, u
     return RS_OK;
 }
 
-int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
-                    rs_opening **open, uint64_t *commitment_out) {
-    RS_REQUIRE(j && v && tape && open && commitment_out, RS_ERR_ARG, "rs_jindo_commit: null argument");
+// vec: the committed vector in HBM, or nullptr with v_host set (then it is uploaded piecewise, see DescCache)
+static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
+                       rs_opening **open, uint64_t *commitment_out) {
     const rs_jindo_params &p = j->p;
     const size_t rank = (size_t)p.cols * (p.rows - 1) * p.slots;
     RS_REQUIRE(len <= rank, RS_ERR_SHAPE, "len(v) > params.rank");                    // prover.go:47-49
-    RS_REQUIRE(len >= 1 && v_poly < v->n_polys && len <= v->rank, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
-    RS_REQUIRE(v->f->NL == j->f->NL, RS_ERR_SHAPE, "rs_jindo_commit: field mismatch");
+    RS_REQUIRE(len >= 1, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
     RS_REQUIRE(tape->first_row && tape->last_row && tape->mask_rows && tape->cosac_g && tape->mlwe, RS_ERR_ARG, "rs_jindo_commit: incomplete tape");
     const int NL = j->f->NL, d = JD, slots = p.slots, rows = p.rows, cols = p.cols;
     const size_t cs = (size_t)cols * slots;
@@ -1176,7 +1192,25 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
             add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, r);
         }
         add(1, 2 * cs + (mask++) * slots, slots, 1, cosac++, cols, rows - 1);
-        DescCache nc{len, nullptr, descs.size(), twin, cosac, mask};
+        // row-major order (every descriptor is independent: sources, noise offsets and the output slot are
+        // explicit), so that consecutive descriptors read consecutive pieces of v
+        std::stable_sort(descs.begin(), descs.end(), [rows](const EncDesc &a, const EncDesc &b) {
+            const i64 ra = a.out_poly % rows, rb = b.out_poly % rows;
+            return ra != rb ? ra < rb : a.out_poly < b.out_poly;
+        });
+        DescCache nc{};
+        nc.len = len; nc.d_descs = nullptr; nc.n_descs = descs.size(); nc.twin = twin; nc.cosac = cosac; nc.mask = mask;
+        {
+            size_t hi = 0;
+            for (int k = 0; k < RS_VCHUNKS; k++) {
+                nc.chunk_desc[k] = descs.size() * k / RS_VCHUNKS;
+                const size_t e = descs.size() * (k + 1) / RS_VCHUNKS;
+                for (size_t t = nc.chunk_desc[k]; t < e; t++)
+                    if (descs[t].src_kind == 0 && (size_t)(descs[t].src_off + descs[t].cnt) > hi) hi = (size_t)(descs[t].src_off + descs[t].cnt);
+                nc.chunk_vhi[k] = hi;
+            }
+            nc.chunk_desc[RS_VCHUNKS] = descs.size();
+        }
         RS_CUDA_CHECK(cudaMalloc((void **)&nc.d_descs, descs.size() * sizeof(EncDesc)));
         RS_CUDA_CHECK(cudaMemcpy(nc.d_descs, descs.data(), descs.size() * sizeof(EncDesc), cudaMemcpyHostToDevice));
         if (j->cache->size() >= 64) { cudaFree(j->cache->front().d_descs); j->cache->erase(j->cache->begin()); }
@@ -1213,9 +1247,9 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
 
     // ---- uploads (skipped when the tape is already device resident)
     const bool dev = tape->on_device != 0;
-    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr, *d_twin_buf = nullptr; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
+    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; bool twin_drawn = false; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
     u64 *d_com = nullptr, *d_com2 = nullptr, *d_value = nullptr, *d_part = nullptr;
-    const uint32_t *vec = v->d + v_poly * v->rank * NL;
+    uint32_t *d_v = nullptr;          // device copy of a host-resident v
 #define RS_TRY(x) do { rc = (x); if (rc) goto fail; } while (0)
     {
         const size_t aux_words = (2 * cs + mask * slots) * NL;
@@ -1234,7 +1268,8 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
     }
     if (gen_twin) {       // draws come from the prover's own AES-CTR stream, generated in HBM
         const u64 *smp = nullptr;
-        RS_TRY(uniform_stream_draw(j->twin_stream, twin * d, &d_twin_buf, &smp));
+        RS_TRY(uniform_stream_draw(j->twin_stream, twin * d, &smp));
+        twin_drawn = true;
         d_twin = (u64 *)smp;
     }
     {
@@ -1247,7 +1282,27 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
             goto fail;
         }
         // ---- encodes + noise polynomials
-        RS_TRY(encode_dispatch(j, o->d_encode, dc->d_descs, n_descs, vec, d_aux, d_twin, d_cosac));
+        if (v_host) {
+            // upload v in RS_VCHUNKS pieces on the copy stream; piece k is encoded as soon as it has landed
+            if (cudaMallocAsync((void **)&d_v, len * NL * 4, current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit_host: cudaMallocAsync failed"); goto fail; }
+            cudaEventRecord(j->ev_alloc, current_stream());
+            cudaStreamWaitEvent(j->copy_stream, j->ev_alloc, 0);
+            size_t lo = 0;
+            for (int k = 0; k < RS_VCHUNKS; k++) {
+                const size_t hi = dc->chunk_vhi[k];
+                if (hi > lo) cudaMemcpyAsync(d_v + lo * NL, (const uint32_t *)v_host + lo * NL, (hi - lo) * NL * 4, cudaMemcpyHostToDevice, j->copy_stream);
+                if (hi > lo) lo = hi;
+                cudaEventRecord(j->ev_piece[k], j->copy_stream);
+            }
+            for (int k = 0; k < RS_VCHUNKS; k++) {
+                cudaStreamWaitEvent(current_stream(), j->ev_piece[k], 0);
+                const size_t c0 = dc->chunk_desc[k], c1 = dc->chunk_desc[k + 1];
+                if (c1 > c0) RS_TRY(encode_dispatch(j, o->d_encode, dc->d_descs + c0, c1 - c0, d_v, d_aux, d_twin, d_cosac));
+            }
+            vec = d_v;
+        } else {
+            RS_TRY(encode_dispatch(j, o->d_encode, dc->d_descs, n_descs, vec, d_aux, d_twin, d_cosac));
+        }
         RS_TRY(encode_dispatch(j, o->d_mlwe, j->d_ndescs, n_noise, vec, d_aux, d_twin, d_mlwe_s));
         // ---- inner commit (prover.go:144-157)
         MatvecGeom G;
@@ -1285,13 +1340,29 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
 fail:
 #undef RS_TRY
     cudaFreeAsync(d_aux, current_stream());
+    if (d_v) cudaFreeAsync(d_v, current_stream());
     if (!dev) { if (!gen_twin) cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); cudaFreeAsync(d_mlwe_s, current_stream()); }
-    if (d_twin_buf) cudaFreeAsync(d_twin_buf, current_stream());
+    if (twin_drawn) uniform_stream_release(j->twin_stream);      // every reader of the draws has been launched
     cudaFreeAsync(d_part, current_stream());
     cudaFreeAsync(d_com, current_stream()); cudaFreeAsync(d_com2, current_stream()); cudaFreeAsync(d_value, current_stream());
     if (rc) { if (!reuse) rs_opening_free(o); return rc; }
     *open = o;
     return RS_OK;
+}
+
+int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
+                    rs_opening **open, uint64_t *commitment_out) {
+    RS_REQUIRE(j && v && tape && open && commitment_out, RS_ERR_ARG, "rs_jindo_commit: null argument");
+    RS_REQUIRE(len >= 1 && v_poly < v->n_polys && len <= v->rank, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
+    RS_REQUIRE(v->f->NL == j->f->NL, RS_ERR_SHAPE, "rs_jindo_commit: field mismatch");
+    return commit_impl(j, v->d + v_poly * v->rank * j->f->NL, nullptr, len, tape, open, commitment_out);
+}
+
+int rs_jindo_commit_host(rs_jindo *j, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
+                         rs_opening **open, uint64_t *commitment_out) {
+    RS_REQUIRE(j && v_host && tape && open && commitment_out, RS_ERR_ARG, "rs_jindo_commit_host: null argument");
+    RS_REQUIRE(!tape->on_device, RS_ERR_ARG, "rs_jindo_commit_host: the tape must be host resident like v");
+    return commit_impl(j, nullptr, v_host, len, tape, open, commitment_out);
 }
 
 int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out) {

@@ -116,6 +116,11 @@ class Prover:
         oh = c_vp(opening.h.value)
         check(lib().rs_jindo_commit(self.h, batch.h, poly, length, ctypes.byref(tape_struct), ctypes.byref(oh), _vp(com_out)))
 
+    def CommitHostInto(self, v_host_ptr, length, tape_struct, opening, com_out):
+        """rs_jindo_commit_host: v in (pinned) host memory, uploaded piecewise behind the encode kernels."""
+        oh = c_vp(opening.h.value)
+        check(lib().rs_jindo_commit_host(self.h, c_vp(v_host_ptr), length, ctypes.byref(tape_struct), ctypes.byref(oh), _vp(com_out)))
+
     def Partial(self, opening, left):
         """prover.go:281-289: returns [cols+1, n_q, 256]; index cols is PartialMask."""
         left = np.ascontiguousarray(left, dtype=np.uint64)

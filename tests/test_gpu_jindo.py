@@ -317,3 +317,31 @@ def test_commit_full_size_properties(rs):
     # (3) determinism
     com2, _ = gp.Commit(B, 0, length, tape)
     assert np.array_equal(com, com2)
+
+
+@pytest.mark.parametrize("name,N,batch,length", [("zp255", 1024, 1, 700), ("zp220", 2049, 9, 2049), ("zp128", 700, 2, 1)])
+def test_commit_host_matches_commit(rs, name, N, batch, length):
+    """rs_jindo_commit_host (v uploaded piecewise behind the encode kernels) == rs_jindo_commit == oracle."""
+    import ctypes
+    q, fo, fg, p, tape, prv, gp = _prover_pair(rs, name, N, batch, b"host-v-" + name.encode())
+    v = [J.field_set_random(tape, q) for _ in range(length)]
+    com_o, open_o = prv.commit(v)
+    t = tape_arrays(fo, p, prv.trace)
+    vm = np.ascontiguousarray(fo.to_mont(v), dtype=np.uint64)
+    keep = {k: np.ascontiguousarray(t[k], dtype=(np.int64 if k in ("cosac_g", "mlwe") else np.uint64)) for k in t}
+    T = rs.capi.JindoTape()
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    T.first_row, T.last_row, T.mask_rows = vp(keep["first_row"]), vp(keep["last_row"]), vp(keep["mask_rows"])
+    T.n_mask_rows = keep["mask_rows"].size // (fo.L * p.slots)
+    T.twin_u, T.n_twin_u = vp(keep["twin_u"]), keep["twin_u"].size
+    T.cosac_g, T.n_cosac_polys = vp(keep["cosac_g"]), keep["cosac_g"].size // p.d
+    T.mlwe = vp(keep["mlwe"])
+    op = gp.NewOpening()
+    com = np.zeros((p.out_msis, len(p.qout_primes), p.d), dtype=np.uint64)
+    gp.CommitHostInto(vm.ctypes.data, length, T, op, com)
+    assert np.array_equal(com, polys_array(com_o))
+    for i in range(p.cols + 1):
+        for j in range(p.rows):
+            assert np.array_equal(op.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", i, j)
+    for k in range(p.in_com_dcmp_len):
+        assert np.array_equal(op.InCommit(k), polys_array(open_o.InCommit[k])), ("InCommit", k)
