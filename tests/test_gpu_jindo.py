@@ -345,3 +345,56 @@ def test_commit_host_matches_commit(rs, name, N, batch, length):
             assert np.array_equal(op.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", i, j)
     for k in range(p.in_com_dcmp_len):
         assert np.array_equal(op.InCommit(k), polys_array(open_o.InCommit[k])), ("InCommit", k)
+
+
+@pytest.mark.parametrize("name,logn,length_off", [("zp255", 16, 0), ("zp255", 18, 4321), ("zp128", 14, 77), ("zp220", 15, 1)])
+def test_commit_mid_size_bit_exact_vs_c_oracle(rs, name, logn, length_off):
+    """Sizes the Python restatement cannot reach: the whole Opening and the Commitment against the C
+    restatement (oracle/jindo_oracle.c, pinned to the Python one by tests/test_oracle_jindo_c.py) on a
+    synthetic key / tape, including ragged lengths and 3-limb rings."""
+    from oracle import jindo_c
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    N = 1 << logn
+    length = N - length_off
+    p = J.new_parameters(q, N, 1)
+    ecd = J.Encoder(p, J.Tape(b"mid-" + name.encode()))
+    rng = np.random.default_rng(logn)
+
+    def rpolys(shape, primes):
+        a = np.empty(shape + (len(primes), p.d), dtype=np.uint64)
+        for l, pr in enumerate(primes):
+            a[..., l, :] = rng.integers(0, pr, size=shape + (p.d,), dtype=np.uint64)
+        return a
+
+    top_bits = (q.bit_length() - 1) % 64          # canonical Montgomery limbs: top limb below q's top limb
+    def felems(n):
+        a = rng.integers(0, 1 << 63, size=(n, fo.L), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, fo.L), dtype=np.uint64)
+        a[:, fo.L - 1] &= np.uint64((1 << top_bits) - 1)
+        return a
+    cs = p.cols * p.slots
+    col_rows = [sum(1 for r in range(1, p.rows - 1) if r * cs + i * p.slots <= length) for i in range(p.cols)]
+    n_mask = 2 + sum(1 for r in range(1, p.rows - 1) if r * cs <= length)
+    n_twin = sum(col_rows) + p.cols; n_cosac = p.cols + n_mask; n_noise = (p.cols + 1) * (p.in_msis + p.mlwe)
+    ck_in, ck_mlwe = rpolys((p.in_msis, p.rows), p.q_primes), rpolys((p.in_msis, p.mlwe), p.q_primes)
+    ck_out = rpolys((p.out_msis, p.in_com_dcmp_len), p.qout_primes)
+    tape = {"first_row": felems(cs), "last_row": felems(cs), "mask_rows": felems(n_mask * p.slots),
+            "twin_u": rng.integers(0, 1 << 63, size=n_twin * p.d, dtype=np.int64).view(np.uint64) * np.uint64(2),
+            "cosac_g": rng.integers(-5000, 5000, size=n_cosac * p.d, dtype=np.int64),
+            "mlwe": rng.integers(-20, 20, size=n_noise * p.d, dtype=np.int64)}
+    v = felems(length)
+    pd = params_dict(p, ecd)
+    exp = jindo_c.commit(fo, pd, ck_in, ck_mlwe, ck_out, cdt_array(ecd), v, tape, threads=8)
+    gp = rs.jindo.Prover(fg, pd, ck_in, ck_mlwe, ck_out, cdt_array(ecd))
+    B = rs.Batch(fg, 1, N)
+    host = np.zeros((1, N, fo.L), dtype=np.uint64); host[0, :length] = v
+    B.upload(host)
+    com, op = gp.Commit(B, 0, length, tape)
+    assert np.array_equal(com, exp["commitment"])
+    for k in range(p.in_com_dcmp_len):
+        assert np.array_equal(op.InCommit(k), exp["incommit"][k]), ("InCommit", k)
+    for i in range(p.cols + 1):
+        for j in range(p.rows):
+            assert np.array_equal(op.Encode(i, j), exp["encode"][i, j]), ("Encode", i, j)
+        for j in range(p.mlwe + p.in_msis):
+            assert np.array_equal(op.MLWE(i, j), exp["mlwe"][i, j]), ("MLWE", i, j)
