@@ -910,10 +910,113 @@ static void fill_geom_ring(MatvecGeom &G, const RingDev &R) {
     G.fold_every = (G.K < cap) ? 0 : (int)(cap > 1 ? cap - 1 : 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// rowsum_kernel: the O == 1 products of Evaluate (Partial: prover.go:281-289, responses: :304-316):
+//   out[cc] (+ addend[cc]) = sum_k key[k] (.) x[cc * x_cs + k * x_ks]
+// A pure stream over the Opening: one thread per slot of one output polynomial, 8 rows in flight per thread,
+// the K range optionally split over blockIdx.z into partial sums (reduced mod q, added up by
+// rowsum_reduce_kernel).  Same lazy accumulation and final REDC as matvec_kernel.
+// ---------------------------------------------------------------------------------------------
+template <bool FOLD>
+__global__ void __launch_bounds__(256) rowsum_kernel(u64 *__restrict__ out, const u64 *__restrict__ key, const u64 *__restrict__ x,
+                                                     const u64 *__restrict__ addend, const __grid_constant__ MatvecGeom G, int ksplit) {
+    const int slot = blockIdx.x * 256 + threadIdx.x;
+    const int cc = blockIdx.y, part = blockIdx.z;
+    const int n_slots = G.n_limbs * JD;
+    if (slot >= n_slots) return;
+    const int limb = slot / JD;
+    const u64 q = G.q[limb], qi = G.qinvneg[limb];
+    const size_t pw = (size_t)n_slots;
+    const int per = (G.K + ksplit - 1) / ksplit;
+    const int k0 = part * per, k1 = (k0 + per < G.K) ? k0 + per : G.K;
+    uint32_t s0a = 0, s0b = 0, s0c = 0;
+    u64 s1 = 0, s2 = 0, s1h = 0, s2h = 0;
+    int since = 0;
+    const u64 *xp = x + ((size_t)cc * G.x_cs + (size_t)k0 * G.x_ks) * pw + slot;
+    const u64 *kp = key + (size_t)k0 * G.key_ks * pw + slot;
+    const size_t x_step = (size_t)G.x_ks * pw, k_step = (size_t)G.key_ks * pw;
+    constexpr int U = 8;
+    for (int k = k0; k < k1; k += U) {
+        u64 kv[U], xv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const bool ok = k + u < k1;
+            xv[u] = ok ? __ldg(xp + (size_t)u * x_step) : 0;
+            kv[u] = ok ? __ldg(kp + (size_t)u * k_step) : 0;
+        }
+        xp += (size_t)U * x_step; kp += (size_t)U * k_step;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t a0 = (uint32_t)kv[u], a1 = (uint32_t)(kv[u] >> 32);
+            const uint32_t b0 = (uint32_t)xv[u], b1 = (uint32_t)(xv[u] >> 32);
+            asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+                : "+r"(s0a), "+r"(s0b), "+r"(s0c) : "r"(a0), "r"(b0));
+            s1 += (u64)a0 * b1;
+            s1 += (u64)a1 * b0;
+            s2 += (u64)a1 * b1;
+            if (FOLD && ++since == G.fold_every) {
+                since = 0;
+                s1h += s1 >> 32; s1 &= 0xffffffffull;
+                s2h += s2 >> 32; s2 &= 0xffffffffull;
+            }
+        }
+    }
+    u64 w0 = ((u64)s0b << 32) | s0a, w1 = s0c, w2 = 0;
+    auto add_at32 = [&](u64 v) {
+        const u64 lo = v << 32, hi = v >> 32;
+        const u64 n0 = w0 + lo; const u64 cy = n0 < lo; w0 = n0;
+        const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
+    };
+    auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
+    add_at32(s1);
+    add_at64(s2);
+    if (FOLD) { add_at64(s1h); const u64 v = s2h; add_at64(v << 32); w2 += v >> 32; }
+    u64 h = w1 >= q ? w1 % q : w1;
+    if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
+    u64 r = redc128(h, w0, q, qi);
+    if (ksplit == 1 && G.has_addend) r = addmod(r, __ldg(addend + (size_t)cc * G.add_cs * pw + slot), q);
+    out[((size_t)part * G.C + cc) * pw + slot] = r;       // ksplit == 1: out[cc]
+}
+
+__global__ void rowsum_reduce_kernel(u64 *__restrict__ out, const u64 *__restrict__ parts, const u64 *__restrict__ addend,
+                                     const __grid_constant__ MatvecGeom G, int ksplit) {
+    const size_t pw = (size_t)G.n_limbs * JD;
+    const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (idx >= (size_t)G.C * pw) return;
+    const int slot = (int)(idx % pw), cc = (int)(idx / pw);
+    const u64 q = G.q[slot / JD];
+    u64 r = 0;
+    for (int s = 0; s < ksplit; s++) r = addmod(r, parts[(size_t)s * G.C * pw + idx], q);
+    if (G.has_addend) r = addmod(r, __ldg(addend + (size_t)cc * G.add_cs * pw + slot), q);
+    out[idx] = r;
+}
+
 static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *addend, MatvecGeom G, const RingDev &R) {
     fill_geom_ring(G, R);
     const int n_slots = R.n * JD;
-    // large products (inner commit, Partial, responses): shared-memory ring version
+    // single-output products (Evaluate): streaming row sums
+    if (G.O == 1 && G.key_cs == 0 && G.out_cs == 1 && !G.accumulate && !getenv("RS_MV_NOROWSUM")) {
+        // enough CTAs for >= 4 per SM; K is split when there are few output polynomials
+        const int bx = (n_slots + 255) / 256;
+        int ksplit = 1;
+        while ((long long)bx * G.C * ksplit < 148 * 4 && ksplit * 64 < G.K) ksplit *= 2;
+        u64 *d_parts = nullptr;
+        if (ksplit > 1) RS_CUDA_CHECK(cudaMallocAsync((void **)&d_parts, (size_t)ksplit * G.C * n_slots * 8, current_stream()));
+        dim3 grid(bx, G.C, ksplit);
+        u64 *dst = ksplit > 1 ? d_parts : out;
+        if (G.fold_every) rowsum_kernel<true><<<grid, 256, 0, current_stream()>>>(dst, key, x, addend, G, ksplit);
+        else rowsum_kernel<false><<<grid, 256, 0, current_stream()>>>(dst, key, x, addend, G, ksplit);
+        count_launch();
+        if (ksplit > 1) {
+            const size_t tot = (size_t)G.C * n_slots;
+            rowsum_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, current_stream()>>>(out, d_parts, addend, G, ksplit);
+            count_launch();
+            cudaFreeAsync(d_parts, current_stream());
+        }
+        RS_CUDA_CHECK(cudaGetLastError());
+        return RS_OK;
+    }
+    // large products (inner commit): shared-memory ring version
     if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !getenv("RS_MV_NOPIPE")) {
         static bool configured = false;
         if (!configured) {

@@ -56,3 +56,11 @@ torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / reps
 print(f"commit 2^{logN}: {dt*1e3:.3f} ms/commit  {1/dt:.1f} polys/s  {N/dt/1e6:.1f} Mcoeff/s  launches/commit={(L.rs_launch_count()-l0)//reps}")
 com2 = com.copy(); gp.CommitInto(B, 0, N, T, op, com); assert np.array_equal(com, com2)
+# ---- Evaluate inner loops (prover.go:281-316) on the same opening
+left = rpolys((p.rows,), p.q_primes); chals = rpolys((p.cols,), p.q_primes)
+for fn, name in ((lambda: gp.Partial(op, left), "Partial"), (lambda: gp.Respond(op, chals), "Respond")):
+    fn(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5): fn()
+    torch.cuda.synchronize()
+    print(f"{name}: {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms", flush=True)
