@@ -245,6 +245,24 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
     ms = e0.elapsed_time(e1) / steps
     launches = (L.rs_launch_count() - l0) // steps
     com_ref = com.copy()
+    # "open" (Prover.Evaluate's two passes over the Opening, prover.go:281-316) through the C ABI: left vector /
+    # challenges from the host, partial sums / responses back to the host
+    def rp(n):
+        a = np.empty((n, len(p.q_primes), p.d), dtype=np.uint64)
+        for l, pr in enumerate(p.q_primes):
+            a[:, l, :] = rng.integers(0, pr, size=(n, p.d), dtype=np.uint64)
+        return a
+    left_h, chal_h = rp(p.rows), rp(p.cols)
+
+    def wall(fn):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) * 1e3 / steps
+    partial_ms = wall(lambda: gp.Partial(op, left_h))
+    respond_ms = wall(lambda: gp.Respond(op, chal_h))
     # e2e: committed vector + the whole tape start in pinned host memory
     nb = v_host.numel() * 8
     tape_bytes = sum(t.numel() * 8 for t in pin.values())
@@ -280,6 +298,9 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
                    "qout_limbs": len(p.qout_primes), "in_msis": p.in_msis, "mlwe": p.mlwe, "out_msis": p.out_msis},
         "ring_polys_encoded": (p.cols + 1) * p.rows + (p.cols + 1) * (p.in_msis + p.mlwe),
         "mod_mul_adds": macs, "gmac_per_s": world * macs / ms / 1e6,
+        "open": {"partial_ms": partial_ms, "respond_ms": respond_ms,
+                 "commit_plus_open_polys_per_s": world * 1e3 / (ms + partial_ms + respond_ms),
+                 "note": "Evaluate's two passes over the 1.08 GB Opening (rs_jindo_partial, rs_jindo_respond), host vectors in, host results out"},
         "gpu_launches_per_commit": int(launches), "deterministic": deterministic,
         "e2e": {"value": world * 1e3 / e2e_ms, "unit": "polys/s", "ms_per_commit": e2e_ms,
                 "h2d_bytes_per_step": nb + tape_bytes - twin_bytes, "d2h_bytes_per_step": int(com.nbytes),
