@@ -98,6 +98,17 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
  * the upload hides behind the encode kernels.  The tape must be host resident too. */
 int rs_jindo_commit_host(rs_jindo *j, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
                          rs_opening **open, uint64_t *commitment_out);
+/* Column-sharded Commit (SURVEY 8e iii): the cols+1 columns of the committed matrix are independent until
+ * the outer commit (prover.go:89-177 vs :180-202).  A rank runs commitColTo for columns [col_begin, col_end)
+ * (the mask column is index cols) with the WHOLE tape -- offsets into it are global, so every shard consumes
+ * exactly the draws the single-GPU Commit gives those columns -- which fills Opening.Encode / MLWE for these
+ * columns and InCommit[col*in_msis, (col+1)*in_msis).  After the shards' InCommit slices have been gathered
+ * into rs_opening_incommit_device() (n_qout*d words per polynomial, (cols+1)*in_msis polynomials; e.g. an NCCL
+ * all-gather on that device pointer), rs_jindo_outer_commit produces Commitment.Value. */
+int rs_jindo_commit_columns(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
+                            int col_begin, int col_end, rs_opening **open);
+int rs_jindo_outer_commit(rs_jindo *j, const rs_opening *open, uint64_t *commitment_out);
+void *rs_opening_incommit_device(rs_opening *open);
 void rs_opening_free(rs_opening *o);
 /* accessors (tests / the Go shim's Opening view): kind 0 = Encode[col][row] (ringQ),
  * 1 = MLWE[col][idx] (ringQ), 2 = InCommit[idx] (ringQOut, col ignored) */

@@ -105,6 +105,9 @@ _SIGS = {
     "rs_jindo_twin_stream_draw": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_commit": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
     "rs_jindo_commit_host": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
+    "rs_jindo_commit_columns": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "rs_jindo_outer_commit": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "rs_opening_incommit_device": (c_vp, [c_vp]),
     "rs_opening_free": (None, [c_vp]),
     "rs_opening_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_size, c_size, c_vp]),
     "rs_jindo_partial": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),

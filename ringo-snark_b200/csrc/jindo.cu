@@ -52,6 +52,7 @@ namespace rs { struct EncDesc; }
 constexpr int RS_VCHUNKS = 8;
 struct DescCache {            // encode descriptors of one committed length, resident on the device
     size_t len;
+    int c0, c1;               // column range [c0, c1) the descriptors cover (0 .. cols+1 for a whole Commit)
     rs::EncDesc *d_descs;
     size_t n_descs, twin, cosac, mask;
     // descriptors are ordered by row of the committed matrix, i.e. by ascending offset into v: chunk k
@@ -1258,9 +1259,15 @@ int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, u
 }
 
 // vec: the committed vector in HBM, or nullptr with v_host set (then it is uploaded piecewise, see DescCache)
+static int outer_commit(rs_jindo *j, const rs_opening *o, uint64_t *commitment_out);
+
+// col0/col1: the columns of the committed matrix to process (the mask column is index cols); a whole Commit
+// is [0, cols+1) and ends with the outer commit, a partial one leaves InCommit[col0*in_msis, col1*in_msis) filled
 static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
-                       rs_opening **open, uint64_t *commitment_out) {
+                       rs_opening **open, uint64_t *commitment_out, int col0, int col1) {
     const rs_jindo_params &p = j->p;
+    RS_REQUIRE(col0 >= 0 && col0 < col1 && col1 <= p.cols + 1, RS_ERR_ARG, "rs_jindo_commit: bad column range");
+    const bool whole = (commitment_out != nullptr);       // rs_jindo_commit_columns never runs the outer commit
     const size_t rank = (size_t)p.cols * (p.rows - 1) * p.slots;
     RS_REQUIRE(len <= rank, RS_ERR_SHAPE, "len(v) > params.rank");                    // prover.go:47-49
     RS_REQUIRE(len >= 1, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
@@ -1270,11 +1277,14 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
 
     // ---- descriptors, in the order of commitColTo (prover.go:89-128); cached per committed length
     const DescCache *dc = nullptr;
-    for (auto &c : *j->cache) if (c.len == len) dc = &c;
+    for (auto &c : *j->cache) if (c.len == len && c.c0 == col0 && c.c1 == col1) dc = &c;
     if (!dc) {
         std::vector<EncDesc> descs;
         size_t twin = 0, cosac = 0, mask = 0;
         auto add = [&](int kind, size_t off, int cnt, int nk, size_t noff, size_t col, size_t row) {
+            // tape offsets are global (the counters advance for every column): a column shard consumes exactly
+            // the draws the whole Commit would give it
+            if ((int)col < col0 || (int)col >= col1) return;
             descs.push_back(EncDesc{kind, cnt, (i64)off, nk, (i64)(noff * d), (i64)(col * rows + row)});
         };
         for (int i = 0; i < cols; i++) add(1, (size_t)i * slots, slots, 1, (size_t)i, i, 0);   // firstRow, COSAC (ecdBlindStdDev)
@@ -1302,7 +1312,7 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
             return ra != rb ? ra < rb : a.out_poly < b.out_poly;
         });
         DescCache nc{};
-        nc.len = len; nc.d_descs = nullptr; nc.n_descs = descs.size(); nc.twin = twin; nc.cosac = cosac; nc.mask = mask;
+        nc.len = len; nc.c0 = col0; nc.c1 = col1; nc.d_descs = nullptr; nc.n_descs = descs.size(); nc.twin = twin; nc.cosac = cosac; nc.mask = mask;
         {
             size_t hi = 0;
             for (int k = 0; k < RS_VCHUNKS; k++) {
@@ -1344,14 +1354,14 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         if (rc) return rc;
     } else {
         RS_REQUIRE(o->j == j, RS_ERR_ARG, "rs_jindo_commit: opening belongs to another prover");
-        if (n_descs < (size_t)(cols + 1) * rows)           // rows past len(v) must read as zero polynomials
-            RS_CUDA_CHECK(cudaMemsetAsync(o->d_encode, 0, (size_t)(cols + 1) * rows * pq(j) * 8, current_stream()));
+        if (n_descs < (size_t)(col1 - col0) * rows)          // rows past len(v) must read as zero polynomials
+            RS_CUDA_CHECK(cudaMemsetAsync(o->d_encode + (size_t)col0 * rows * pq(j), 0, (size_t)(col1 - col0) * rows * pq(j) * 8, current_stream()));
     }
 
     // ---- uploads (skipped when the tape is already device resident)
     const bool dev = tape->on_device != 0;
     uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; bool twin_drawn = false; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
-    u64 *d_com = nullptr, *d_com2 = nullptr, *d_value = nullptr, *d_part = nullptr;
+    u64 *d_com = nullptr;
     uint32_t *d_v = nullptr;          // device copy of a host-resident v
 #define RS_TRY(x) do { rc = (x); if (rc) goto fail; } while (0)
     {
@@ -1377,10 +1387,8 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
     }
     {
         const size_t n_com = (size_t)(cols + 1) * p.in_msis;
-        if (cudaMallocAsync((void **)&d_com, n_com * pq(j) * 8, current_stream()) != cudaSuccess ||
-            cudaMallocAsync((void **)&d_com2, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess ||
-            cudaMallocAsync((void **)&d_part, (size_t)(cols + 1) * p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess ||
-            cudaMallocAsync((void **)&d_value, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess) {
+        const int nc = col1 - col0, nm = p.mlwe + p.in_msis;
+        if (cudaMallocAsync((void **)&d_com, n_com * pq(j) * 8, current_stream()) != cudaSuccess) {
             rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: cudaMallocAsync failed");
             goto fail;
         }
@@ -1406,39 +1414,24 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         } else {
             RS_TRY(encode_dispatch(j, o->d_encode, dc->d_descs, n_descs, vec, d_aux, d_twin, d_cosac));
         }
-        RS_TRY(encode_dispatch(j, o->d_mlwe, j->d_ndescs, n_noise, vec, d_aux, d_twin, d_mlwe_s));
-        // ---- inner commit (prover.go:144-157)
+        RS_TRY(encode_dispatch(j, o->d_mlwe, j->d_ndescs + (size_t)col0 * nm, (size_t)nc * nm, vec, d_aux, d_twin, d_mlwe_s));
+        // ---- inner commit (prover.go:144-157) of the columns [col0, col1)
         MatvecGeom G;
         memset(&G, 0, sizeof(G));
-        G.O = p.in_msis; G.C = cols + 1; G.K = rows;
+        G.O = p.in_msis; G.C = nc; G.K = rows;
         G.key_os = rows; G.key_ks = 1; G.x_cs = rows; G.x_ks = 1; G.out_cs = p.in_msis; G.out_os = 1;
-        RS_TRY(launch_matvec(d_com, j->d_ck_in, o->d_encode, nullptr, G, j->rq));
-        G.K = p.mlwe; G.key_os = p.mlwe; G.x_cs = p.mlwe + p.in_msis; G.accumulate = 1;
-        G.has_addend = 1; G.add_cs = p.mlwe + p.in_msis; G.add_os = 1;
-        RS_TRY(launch_matvec(d_com, j->d_ck_mlwe, o->d_mlwe, o->d_mlwe + (size_t)p.mlwe * pq(j), G, j->rq));
-        // ---- cut-off pipeline (prover.go:164-176)
-        RS_TRY(launch_cut(j, o->d_incommit, d_com, n_com, false));
-        // ---- outer commit (prover.go:180-202): split over the cols+1 column blocks of InCommit,
-        //      partial sums reduced mod q afterwards (same field element as the sequential sum)
-        memset(&G, 0, sizeof(G));
-        G.O = p.out_msis; G.C = cols + 1; G.K = p.in_msis;
-        G.key_os = (i64)n_com; G.key_cs = p.in_msis; G.key_ks = 1; G.x_cs = p.in_msis; G.x_ks = 1;
-        G.out_cs = p.out_msis; G.out_os = 1;
-        RS_TRY(launch_matvec(d_part, j->d_ck_out, o->d_incommit, nullptr, G, j->rqo));
+        u64 *com0 = d_com + (size_t)col0 * p.in_msis * pq(j);
+        RS_TRY(launch_matvec(com0, j->d_ck_in, o->d_encode + (size_t)col0 * rows * pq(j), nullptr, G, j->rq));
+        G.K = p.mlwe; G.key_os = p.mlwe; G.x_cs = nm; G.accumulate = 1;
+        G.has_addend = 1; G.add_cs = nm; G.add_os = 1;
         {
-            MatvecGeom Gr;
-            memset(&Gr, 0, sizeof(Gr));
-            fill_geom_ring(Gr, j->rqo);
-            const size_t tot = (size_t)p.out_msis * pqo(j);
-            reduce_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, current_stream()>>>(d_com2, d_part, cols + 1, p.out_msis, Gr);
-            count_launch();
+            const u64 *ml0 = o->d_mlwe + (size_t)col0 * nm * pq(j);
+            RS_TRY(launch_matvec(com0, j->d_ck_mlwe, ml0, ml0 + (size_t)p.mlwe * pq(j), G, j->rq));
         }
-        RS_TRY(launch_cut(j, d_value, d_com2, p.out_msis, true));
-        if (cudaMemcpyAsync(commitment_out, d_value, (size_t)p.out_msis * pqo(j) * 8, cudaMemcpyDeviceToHost, current_stream()) != cudaSuccess ||
-            cudaStreamSynchronize(current_stream()) != cudaSuccess) {
-            rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: %s", cudaGetErrorString(cudaGetLastError()));
-            goto fail;
-        }
+        // ---- cut-off pipeline (prover.go:164-176)
+        RS_TRY(launch_cut(j, o->d_incommit + (size_t)col0 * p.in_msis * pqo(j), com0, (size_t)nc * p.in_msis, false));
+        if (whole) RS_TRY(outer_commit(j, o, commitment_out));
+        else if (cudaStreamSynchronize(current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit_columns: %s", cudaGetErrorString(cudaGetLastError())); goto fail; }
     }
 fail:
 #undef RS_TRY
@@ -1446,11 +1439,47 @@ fail:
     if (d_v) cudaFreeAsync(d_v, current_stream());
     if (!dev) { if (!gen_twin) cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); cudaFreeAsync(d_mlwe_s, current_stream()); }
     if (twin_drawn) uniform_stream_release(j->twin_stream);      // every reader of the draws has been launched
-    cudaFreeAsync(d_part, current_stream());
-    cudaFreeAsync(d_com, current_stream()); cudaFreeAsync(d_com2, current_stream()); cudaFreeAsync(d_value, current_stream());
+    cudaFreeAsync(d_com, current_stream());
     if (rc) { if (!reuse) rs_opening_free(o); return rc; }
     *open = o;
     return RS_OK;
+}
+
+// outer commit (prover.go:180-202) from Opening.InCommit: split over the cols+1 column blocks, partial sums
+// reduced mod q afterwards (same field element as the sequential sum), then the cut-off pipeline
+static int outer_commit(rs_jindo *j, const rs_opening *o, uint64_t *commitment_out) {
+    const rs_jindo_params &p = j->p;
+    const int cols = p.cols;
+    const size_t n_com = (size_t)(cols + 1) * p.in_msis;
+    u64 *d_com2 = nullptr, *d_value = nullptr, *d_part = nullptr;
+    int rc = RS_OK;
+    if (cudaMallocAsync((void **)&d_com2, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess ||
+        cudaMallocAsync((void **)&d_part, (size_t)(cols + 1) * p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess ||
+        cudaMallocAsync((void **)&d_value, (size_t)p.out_msis * pqo(j) * 8, current_stream()) != cudaSuccess)
+        rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: cudaMallocAsync failed");
+    if (rc == RS_OK) {
+        MatvecGeom G;
+        memset(&G, 0, sizeof(G));
+        G.O = p.out_msis; G.C = cols + 1; G.K = p.in_msis;
+        G.key_os = (i64)n_com; G.key_cs = p.in_msis; G.key_ks = 1; G.x_cs = p.in_msis; G.x_ks = 1;
+        G.out_cs = p.out_msis; G.out_os = 1;
+        rc = launch_matvec(d_part, j->d_ck_out, o->d_incommit, nullptr, G, j->rqo);
+    }
+    if (rc == RS_OK) {
+        MatvecGeom Gr;
+        memset(&Gr, 0, sizeof(Gr));
+        fill_geom_ring(Gr, j->rqo);
+        const size_t tot = (size_t)p.out_msis * pqo(j);
+        reduce_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, current_stream()>>>(d_com2, d_part, cols + 1, p.out_msis, Gr);
+        count_launch();
+        rc = launch_cut(j, d_value, d_com2, p.out_msis, true);
+    }
+    if (rc == RS_OK &&
+        (cudaMemcpyAsync(commitment_out, d_value, (size_t)p.out_msis * pqo(j) * 8, cudaMemcpyDeviceToHost, current_stream()) != cudaSuccess ||
+         cudaStreamSynchronize(current_stream()) != cudaSuccess))
+        rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFreeAsync(d_part, current_stream()); cudaFreeAsync(d_com2, current_stream()); cudaFreeAsync(d_value, current_stream());
+    return rc;
 }
 
 int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
@@ -1458,14 +1487,30 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
     RS_REQUIRE(j && v && tape && open && commitment_out, RS_ERR_ARG, "rs_jindo_commit: null argument");
     RS_REQUIRE(len >= 1 && v_poly < v->n_polys && len <= v->rank, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
     RS_REQUIRE(v->f->NL == j->f->NL, RS_ERR_SHAPE, "rs_jindo_commit: field mismatch");
-    return commit_impl(j, v->d + v_poly * v->rank * j->f->NL, nullptr, len, tape, open, commitment_out);
+    return commit_impl(j, v->d + v_poly * v->rank * j->f->NL, nullptr, len, tape, open, commitment_out, 0, j->p.cols + 1);
 }
+
+int rs_jindo_commit_columns(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
+                            int col_begin, int col_end, rs_opening **open) {
+    RS_REQUIRE(j && v && tape && open, RS_ERR_ARG, "rs_jindo_commit_columns: null argument");
+    RS_REQUIRE(len >= 1 && v_poly < v->n_polys && len <= v->rank, RS_ERR_SHAPE, "rs_jindo_commit_columns: vector range out of bounds");
+    RS_REQUIRE(v->f->NL == j->f->NL, RS_ERR_SHAPE, "rs_jindo_commit_columns: field mismatch");
+    return commit_impl(j, v->d + v_poly * v->rank * j->f->NL, nullptr, len, tape, open, nullptr, col_begin, col_end);
+}
+
+int rs_jindo_outer_commit(rs_jindo *j, const rs_opening *open, uint64_t *commitment_out) {
+    RS_REQUIRE(j && open && commitment_out, RS_ERR_ARG, "rs_jindo_outer_commit: null argument");
+    RS_REQUIRE(open->j == j, RS_ERR_ARG, "rs_jindo_outer_commit: opening belongs to another prover");
+    return outer_commit(j, open, commitment_out);
+}
+
+void *rs_opening_incommit_device(rs_opening *open) { return open ? (void *)open->d_incommit : nullptr; }
 
 int rs_jindo_commit_host(rs_jindo *j, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
                          rs_opening **open, uint64_t *commitment_out) {
     RS_REQUIRE(j && v_host && tape && open && commitment_out, RS_ERR_ARG, "rs_jindo_commit_host: null argument");
     RS_REQUIRE(!tape->on_device, RS_ERR_ARG, "rs_jindo_commit_host: the tape must be host resident like v");
-    return commit_impl(j, nullptr, v_host, len, tape, open, commitment_out);
+    return commit_impl(j, nullptr, v_host, len, tape, open, commitment_out, 0, j->p.cols + 1);
 }
 
 int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out) {

@@ -38,6 +38,11 @@ class Opening:
     def MLWE(self, col, idx): return self._get(1, col, idx, self.prover.n_q)
     def InCommit(self, idx): return self._get(2, 0, idx, self.prover.n_qout)
 
+    def incommit_device_ptr(self):
+        """Device address of Opening.InCommit: (cols+1)*in_msis polynomials of n_qout*256 uint64 (for the
+        all-gather of a column-sharded Commit)."""
+        return int(lib().rs_opening_incommit_device(self.h) or 0)
+
 
 class Prover:
     """jindo.NewProver (prover.go:28-40).  `p` is a dict with the jindo.Parameters fields, the
@@ -115,6 +120,34 @@ class Prover:
         Opening -- the allocation-free form used by bench.py."""
         oh = c_vp(opening.h.value)
         check(lib().rs_jindo_commit(self.h, batch.h, poly, length, ctypes.byref(tape_struct), ctypes.byref(oh), _vp(com_out)))
+
+    def tape_struct(self, tape):
+        """rs_jindo_tape over host numpy arrays (returns the struct and the arrays that must stay alive)."""
+        keep = {k: np.ascontiguousarray(tape[k], dtype=(np.int64 if k in ("cosac_g", "mlwe") else np.uint64))
+                for k in ("first_row", "last_row", "mask_rows", "twin_u", "cosac_g", "mlwe") if tape.get(k) is not None}
+        L = self.field.L
+        T = capi.JindoTape()
+        T.first_row, T.last_row, T.mask_rows = _vp(keep["first_row"]), _vp(keep["last_row"]), _vp(keep["mask_rows"])
+        T.n_mask_rows = keep["mask_rows"].size // (L * self.p["slots"])
+        if "twin_u" in keep:
+            T.twin_u, T.n_twin_u = _vp(keep["twin_u"]), keep["twin_u"].size
+        T.cosac_g, T.n_cosac_polys = _vp(keep["cosac_g"]), keep["cosac_g"].size // self.d
+        T.mlwe = _vp(keep["mlwe"])
+        return T, keep
+
+    def CommitColumns(self, batch, poly, length, tape, col_begin, col_end, opening=None):
+        """rs_jindo_commit_columns: commitColTo (prover.go:89-177) for the columns [col_begin, col_end) only,
+        with the whole tape.  Returns the Opening (its other columns are untouched / zero)."""
+        T, keep = self.tape_struct(tape) if isinstance(tape, dict) else (tape, None)
+        oh = c_vp(opening.h.value) if opening is not None else c_vp()
+        check(lib().rs_jindo_commit_columns(self.h, batch.h, poly, length, ctypes.byref(T), col_begin, col_end, ctypes.byref(oh)))
+        return opening if opening is not None else Opening(self, oh)
+
+    def OuterCommit(self, opening):
+        """rs_jindo_outer_commit: Commitment.Value from the (gathered) Opening.InCommit (prover.go:180-202)."""
+        com = np.zeros((self.p["out_msis"], self.n_qout, self.d), dtype=np.uint64)
+        check(lib().rs_jindo_outer_commit(self.h, opening.h, _vp(com)))
+        return com
 
     def CommitHostInto(self, v_host_ptr, length, tape_struct, opening, com_out):
         """rs_jindo_commit_host: v in (pinned) host memory, uploaded piecewise behind the encode kernels."""

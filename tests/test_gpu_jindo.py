@@ -398,3 +398,30 @@ def test_commit_mid_size_bit_exact_vs_c_oracle(rs, name, logn, length_off):
             assert np.array_equal(op.Encode(i, j), exp["encode"][i, j]), ("Encode", i, j)
         for j in range(p.mlwe + p.in_msis):
             assert np.array_equal(op.MLWE(i, j), exp["mlwe"][i, j]), ("MLWE", i, j)
+
+
+@pytest.mark.parametrize("name,N,batch,length,cuts", [("zp255", 1024, 1, 700, (0, 1, 2)), ("zp128", 700, 2, 700, (0, 2)), ("zp220", 2049, 9, 2049, (0, 1, 4))])
+def test_column_sharded_commit_equals_commit(rs, name, N, batch, length, cuts):
+    """rs_jindo_commit_columns over a partition of the columns (what the ranks of a sharded Commit run, here one
+    after the other into one Opening) + rs_jindo_outer_commit == rs_jindo_commit == oracle, incl. the tape offsets."""
+    q, fo, fg, p, tape, prv, gp = _prover_pair(rs, name, N, batch, b"shard-" + name.encode())
+    v = [J.field_set_random(tape, q) for _ in range(length)]
+    com_o, open_o = prv.commit(v)
+    t = tape_arrays(fo, p, prv.trace)
+    B = rs.Batch(fg, 1, max(length, 8))
+    host = np.zeros((1, max(length, 8), fo.L), dtype=np.uint64); host[0, :length] = fo.to_mont(v)
+    B.upload(host)
+    bounds = [c for c in cuts if c <= p.cols] + [p.cols + 1]
+    op = None
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if b > a:
+            op = gp.CommitColumns(B, 0, length, t, a, b, op)
+    com = gp.OuterCommit(op)
+    assert np.array_equal(com, polys_array(com_o))
+    for i in range(p.cols + 1):
+        for j in range(p.rows):
+            assert np.array_equal(op.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", i, j)
+    for k in range(p.in_com_dcmp_len):
+        assert np.array_equal(op.InCommit(k), polys_array(open_o.InCommit[k])), ("InCommit", k)
+    with pytest.raises(rs.RingoError):
+        gp.CommitColumns(B, 0, length, t, 2, 2)

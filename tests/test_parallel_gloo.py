@@ -58,3 +58,38 @@ def test_shard_range_partition(product):
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def _slice_worker(rank, world, n_cols, words, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from conftest import load_product
+    par = load_product().parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    full = torch.arange(n_cols * words, dtype=torch.int64) * 7 + 3
+    buf = torch.zeros_like(full)
+    a, b = par.shard_range(n_cols, rank, world)
+    buf[a * words:b * words] = full[a * words:b * words]          # this rank's columns only
+    par.gather_column_slices(buf, n_cols, words, world)
+    q.put((rank, bool(torch.equal(buf, full))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_cols", [129, 3, 1])
+def test_column_slices_exchange(n_cols, product):
+    """The InCommit exchange of a column-sharded Commit (parallel.gather_column_slices), world 2 on gloo."""
+    world, words = 2, 40
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + n_cols) % 2000
+    procs = [ctx.Process(target=_slice_worker, args=(r, world, n_cols, words, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
