@@ -146,7 +146,7 @@ def run_reference(args):
     key, tape, _ = synthetic_commit_inputs(p, f.L, rng)
     v = rng.integers(0, 1 << 62, size=(1 << COMMIT_LOGN, f.L), dtype=np.uint64)
     _, commit_cpu = commit_cpu_baseline(q, key, tape, v, params_dict(p, ecd), cdt_array(ecd))
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64x4 (255-bit Montgomery)", "data": "synthetic",
@@ -504,7 +504,7 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": f"{n_polys} polys x 2^{LOGN} ({dt * 1e3:.0f} ms per sample); C restatement of "
                                              f"math/bigpoly/ntt.go, batch-parallel over {threads} pthreads"}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -517,10 +517,26 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (e.g. NCCL's version
+    # banner) is sent to stderr, and the real stdout is put back just before the line is printed
+    sys.stdout.flush()
+    global _REAL_STDOUT
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(line, flush=True)
 
 
 if __name__ == "__main__":
