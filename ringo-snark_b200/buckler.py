@@ -94,6 +94,16 @@ class Prover:
         L = lib()
         tapes = iter(rand["tapes"])
         tr = Transcript(CHAL_NAMES)
+        # wall-time split of the last Prove (ms; the stream is synchronised at every mark)
+        import time as _time
+        self.timing = {}
+        _t = [_time.perf_counter()]
+
+        def mark(name):
+            check(L.rs_sync())
+            now = _time.perf_counter()
+            self.timing[name] = self.timing.get(name, 0.0) + (now - _t[0]) * 1e3
+            _t[0] = now
         # ---- Encode + NTT of all (public) witnesses: 1 upload, 2 batched transforms
         vals = Batch(f, wc + pc, N).upload(np.concatenate([w_mont, pw_mont]))
         ecd = Batch(f, wc + pc, E)
@@ -111,6 +121,7 @@ class Prover:
         pw_ntt = Batch(f, max(pc, 1), E)
         for k in range(pc):
             check(L.rs_batch_copy(pw_ntt.h, k, 0, ntt.h, wc + k, 0, E))
+        mark("encode_ntt")
         n_com = wc + (1 if c["arith_terms"] else 0) + (4 if c["lin"] else 0)
         coms, opens, views = [None] * n_com, [None] * n_com, [None] * n_com
         for i in range(wc):                              # first-round witnesses (no second-round witnesses here)
@@ -118,6 +129,7 @@ class Prover:
             views[i] = (ecd, i, N + 1)
             tr.bind("projConst", JH.commitment_write_raw(self.jp, coms[i].tolist()))
         tr.compute_challenge("projConst")
+        mark("commit")
         idx = wc
         work = Batch(f, 8, E)                            # 0 mask, 1 eval, 2 quo, 3 rem, 4 term, 5 linEcd, 6 linEcdTr, 7 scratch
         lin_mask_sum = None
@@ -131,6 +143,7 @@ class Prover:
             tr.bind("arithBatchConst", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
             tr.bind("arithBatchConst", lin_mask_sum.to_bytes(8 * self.L, "big"))
             idx += 1
+        mark("commit")
         arith_bc = int.from_bytes(tr.compute_challenge("arithBatchConst"), "big") % q
         keep = []                                        # committed polynomials must stay alive until Evaluate
         if c["arith_terms"]:
@@ -145,9 +158,11 @@ class Prover:
             quo_b = Batch(f, 2, E)
             check(L.rs_quorem_vanishing(quo_b.h, 0, quo_b.h, 1, work.h, 1, N))
             keep.append(quo_b)
+            mark("arith_check")
             coms[idx], opens[idx] = self._commit(quo_b, 0, c["arith_max_rank"] - N, next(tapes)); views[idx] = (quo_b, 0, c["arith_max_rank"] - N)
             tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
             idx += 1
+        mark("commit")
         lin_bc = int.from_bytes(tr.compute_challenge("linCheckBatchConst"), "big") % q
         lin_c = int.from_bytes(tr.compute_challenge("linCheckConst"), "big") % q
         if c["lin"]:
@@ -182,13 +197,16 @@ class Prover:
             check(L.rs_batch_copy(rem.h, 0, 0, qr.h, 1, 1, N - 1))
             check(L.rs_batch_copy(rem.h, 1, Rk - (N - 1), qr.h, 1, 1, N - 1))
             keep += [qr, rem]
+            mark("lin_check")
             for (b, p, ln) in ((qr, 0, N), (rem, 0, N - 1), (rem, 1, Rk)):
                 coms[idx], opens[idx] = self._commit(b, p, ln, next(tapes)); views[idx] = (b, p, ln)
                 tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
                 idx += 1
         tr.compute_challenge("sumCheckBatchConst")
         x = int.from_bytes(tr.compute_challenge("evalPoint"), "big") % q
+        mark("commit")
         evals, pf = self.evaluate(x, views, coms, opens)
+        mark("evaluate")
         return {"Witness": [cm.tolist() for cm in coms], "LinCheckMaskSum": lin_mask_sum, "SumCheckMaskSum": None,
                 "Evals": evals, "EvalProof": pf, "_eval_point": x}
 
