@@ -482,7 +482,10 @@ def run_ours(args):
                    "l2": f"input+output {2 * nbytes >> 20} MiB per step, larger than the 126 MB L2 (no flush needed)",
                    "sharding": "independent polynomials per rank, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                     "traffic": None, "kernel": f"ntt_pass_kernel pass {dom} of {len(passes)}",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the ncu --set full capture
+                     # profiles/ntt_r1h_ncu_batch512_summary.csv (same command, batch 512): 1.076 + 1.016 GB
+                     "traffic": 2.092e9 if (BATCH, LOGN, FIELD) == (512, 16, "zp255") else None,
+                     "algorithmic_bytes": alg_bytes, "kernel": f"ntt_pass_kernel pass {dom} of {len(passes)}",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "note": "kernel is integer-pipe bound, see roofline_imad"},
         "roofline_imad": {"bound": "imad", "achieved": imad_ach, "peak": imad_peak, "unit": "G IMAD.WIDE/s",
