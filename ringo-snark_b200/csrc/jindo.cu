@@ -464,6 +464,18 @@ struct MatvecGeom {
 // FOLD: spill the high words of S1/S2 every fold_every terms (only needed for primes > ~50 bits and
 // long sums).  One Montgomery reduction per output at the end: the result is the same field element
 // as the reference's chain of MulCoeffsMontgomeryThenAdd.
+// one lazy multiply-accumulate of two 64-bit residues k = k1 2^32 + k0, x = x1 2^32 + x0:
+//   S0 (96 bit) += k0 x0 ;  S1 += k0 x1 + k1 x0 ;  S2 += k1 x1       -- 5 instructions (IMAD.WIDE + IADD3.X, 3 x IMAD.WIDE)
+__device__ __forceinline__ void mac_lazy(uint32_t &s0a, uint32_t &s0b, uint32_t &s0c, u64 &s1, u64 &s2, u64 kv, u64 xv) {
+    const uint32_t k0 = (uint32_t)kv, k1 = (uint32_t)(kv >> 32);
+    const uint32_t x0 = (uint32_t)xv, x1 = (uint32_t)(xv >> 32);
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(s0a), "+r"(s0b), "+r"(s0c) : "r"(k0), "r"(x0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s1) : "r"(k0), "r"(x1));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s1) : "r"(k1), "r"(x0));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s2) : "r"(k1), "r"(x1));
+}
+
 template <int OT, int CT, int WARPS, bool FOLD>
 __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
                                                            const u64 *__restrict__ x, const u64 *__restrict__ addend,
@@ -514,13 +526,7 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
         for (int a = 0; a < OT; a++)
 #pragma unroll
             for (int b = 0; b < CT; b++) {
-                const uint32_t k0 = (uint32_t)kv[a][b], k1 = (uint32_t)(kv[a][b] >> 32);
-                const uint32_t x0 = (uint32_t)xv[b], x1 = (uint32_t)(xv[b] >> 32);
-                asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
-                    : "+r"(s0a[a][b]), "+r"(s0b[a][b]), "+r"(s0c[a][b]) : "r"(k0), "r"(x0));
-                s1[a][b] += (u64)k0 * x1;
-                s1[a][b] += (u64)k1 * x0;
-                s2[a][b] += (u64)k1 * x1;
+                mac_lazy(s0a[a][b], s0b[a][b], s0c[a][b], s1[a][b], s2[a][b], kv[a][b], xv[b]);
             }
         if (FOLD && ++since == G.fold_every) {
             since = 0;
@@ -587,27 +593,42 @@ __global__ void __launch_bounds__(MP_THREADS, 1) matvec_pipe_kernel(u64 *__restr
     const int limb = (slot0 + tx) / JD;
     const u64 q = G.q[limb], qi = G.qinvneg[limb];
 
-    // ---- loader: chunk id -> (k_local, row, 16-byte piece); rows 0..OT-1 are key rows, the rest x columns
+    // ---- loader.  A stage is MP_KS k-steps x MP_ROWS polynomial rows (OT key rows, then CTC x columns) x
+    //      PIECES 16-byte pieces.  Per CTA the rows' base pointers and per-k strides are fixed: they sit in a
+    //      small shared table, and a thread's chunk list (row, k_local) is static, so one chunk costs a table
+    //      read, a 32x32+64 multiply-add for the address and the cp.async.
     constexpr int PIECES = MP_MS / 2;                               // 16-byte pieces per row
-    constexpr int CHUNKS = MP_KS * MP_ROWS * PIECES;
+    constexpr int PAIRS = MP_KS * MP_ROWS;                          // (k_local, row) pairs per stage
+    constexpr int PAIRS_PER_ROUND = MP_THREADS / PIECES;
+    __shared__ unsigned long long row_base[MP_ROWS];                // global address of (row, k = 0, this tile's first slot)
+    __shared__ unsigned row_step[MP_ROWS];                          // bytes per k-step
+    if (threadIdx.x < MP_ROWS) {
+        const int row = threadIdx.x;
+        const u64 *src; size_t step;
+        if (row < MP_OT) {
+            const int oo = (o0 + row < G.O) ? o0 + row : G.O - 1;
+            src = key + (size_t)(oo * G.key_os) * pw; step = (size_t)G.key_ks * pw * 8;
+        } else {
+            const int cc = (cb + row - MP_OT < G.C) ? cb + row - MP_OT : G.C - 1;
+            src = x + (size_t)(cc * G.x_cs) * pw; step = (size_t)G.x_ks * pw * 8;
+        }
+        row_base[row] = (unsigned long long)(src + slot0);
+        row_step[row] = (unsigned)step;                             // < 2^32: launch_matvec checks
+    }
+    __syncthreads();
+    const int piece = threadIdx.x % PIECES, pair0 = threadIdx.x / PIECES;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     auto load_stage = [&](int it, int buf) {
-        u64 *dst = ring + (size_t)buf * MP_STAGE_WORDS;
-        for (int ch = threadIdx.x; ch < CHUNKS; ch += MP_THREADS) {
-            const int piece = ch % PIECES, row = (ch / PIECES) % MP_ROWS, kl = ch / (PIECES * MP_ROWS);
+        const unsigned dst = ring_s + (unsigned)buf * (MP_STAGE_WORDS * 8) + piece * 16;
+#pragma unroll
+        for (int r = 0; r < (PAIRS + PAIRS_PER_ROUND - 1) / PAIRS_PER_ROUND; r++) {
+            const int pair = pair0 + r * PAIRS_PER_ROUND;
+            if (pair >= PAIRS) break;
+            const int kl = pair / MP_ROWS, row = pair - kl * MP_ROWS;
             int k = it * MP_KS + kl;
             if (k >= G.K) k = G.K - 1;                              // tail: harmless duplicate, not accumulated
-            const u64 *src;
-            if (row < MP_OT) {
-                const int oo = (o0 + row < G.O) ? o0 + row : G.O - 1;
-                // key may depend on the column block (outer commit: key_cs != 0 requires CTC == 1 handling -> host uses matvec_kernel)
-                src = key + (size_t)(oo * G.key_os + k * G.key_ks) * pw;
-            } else {
-                const int cc = (cb + row - MP_OT < G.C) ? cb + row - MP_OT : G.C - 1;
-                src = x + (size_t)(cc * G.x_cs + k * G.x_ks) * pw;
-            }
-            src += slot0 + piece * 2;
-            const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + ((size_t)kl * MP_ROWS + row) * MP_MS + piece * 2);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src));
+            const unsigned long long src = row_base[row] + (unsigned long long)(unsigned)k * row_step[row] + piece * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)pair * (MP_MS * 8)), "l"(src));
         }
         asm volatile("cp.async.commit_group;");
     };
@@ -644,13 +665,7 @@ __global__ void __launch_bounds__(MP_THREADS, 1) matvec_pipe_kernel(u64 *__restr
             for (int a = 0; a < MP_OT; a++)
 #pragma unroll
                 for (int b = 0; b < 2; b++) {
-                    const uint32_t k0 = (uint32_t)kv[a], k1 = (uint32_t)(kv[a] >> 32);
-                    const uint32_t x0 = (uint32_t)xv[b], x1 = (uint32_t)(xv[b] >> 32);
-                    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
-                        : "+r"(s0a[a][b]), "+r"(s0b[a][b]), "+r"(s0c[a][b]) : "r"(k0), "r"(x0));
-                    s1[a][b] += (u64)k0 * x1;
-                    s1[a][b] += (u64)k1 * x0;
-                    s2[a][b] += (u64)k1 * x1;
+                    mac_lazy(s0a[a][b], s0b[a][b], s0c[a][b], s1[a][b], s2[a][b], kv[a], xv[b]);
                 }
             if (FOLD && ++since == G.fold_every) {
                 since = 0;
@@ -948,13 +963,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(u64 *__restrict__ out, cons
         xp += (size_t)U * x_step; kp += (size_t)U * k_step;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint32_t a0 = (uint32_t)kv[u], a1 = (uint32_t)(kv[u] >> 32);
-            const uint32_t b0 = (uint32_t)xv[u], b1 = (uint32_t)(xv[u] >> 32);
-            asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
-                : "+r"(s0a), "+r"(s0b), "+r"(s0c) : "r"(a0), "r"(b0));
-            s1 += (u64)a0 * b1;
-            s1 += (u64)a1 * b0;
-            s2 += (u64)a1 * b1;
+            mac_lazy(s0a, s0b, s0c, s1, s2, kv[u], xv[u]);
             if (FOLD && ++since == G.fold_every) {
                 since = 0;
                 s1h += s1 >> 32; s1 &= 0xffffffffull;
@@ -1018,7 +1027,8 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         return RS_OK;
     }
     // large products (inner commit): shared-memory ring version
-    if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !getenv("RS_MV_NOPIPE")) {
+    if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !getenv("RS_MV_NOPIPE") &&
+        (unsigned long long)G.key_ks * n_slots * 8 < (1ull << 32) && (unsigned long long)G.x_ks * n_slots * 8 < (1ull << 32)) {
         static bool configured = false;
         if (!configured) {
             RS_CUDA_CHECK(cudaFuncSetAttribute(matvec_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_SMEM_BYTES));
