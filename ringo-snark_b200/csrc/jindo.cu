@@ -464,16 +464,27 @@ struct MatvecGeom {
 // FOLD: spill the high words of S1/S2 every fold_every terms (only needed for primes > ~50 bits and
 // long sums).  One Montgomery reduction per output at the end: the result is the same field element
 // as the reference's chain of MulCoeffsMontgomeryThenAdd.
+// 64-bit accumulator; the multiply-add is written as a mad.lo.cc / madc.hi pair on its halves so that ptxas
+// emits ONE IMAD.WIDE.U32 with the 64-bit addend (it splits a plain mad.wide.u32 into a multiply and a
+// two-instruction add)
+struct Acc64 {
+    u64 v;
+    __device__ __forceinline__ u64 value() const { return v; }
+};
+__device__ __forceinline__ void acc_mad(Acc64 &s, uint32_t a, uint32_t b) {
+    asm("{\n\t.reg .u32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmad.lo.cc.u32 lo, %1, %2, lo;\n\tmadc.hi.u32 hi, %1, %2, hi;\n\tmov.b64 %0, {lo, hi};\n\t}"
+        : "+l"(s.v) : "r"(a), "r"(b));
+}
 // one lazy multiply-accumulate of two 64-bit residues k = k1 2^32 + k0, x = x1 2^32 + x0:
 //   S0 (96 bit) += k0 x0 ;  S1 += k0 x1 + k1 x0 ;  S2 += k1 x1       -- 5 instructions (IMAD.WIDE + IADD3.X, 3 x IMAD.WIDE)
-__device__ __forceinline__ void mac_lazy(uint32_t &s0a, uint32_t &s0b, uint32_t &s0c, u64 &s1, u64 &s2, u64 kv, u64 xv) {
+__device__ __forceinline__ void mac_lazy(uint32_t &s0a, uint32_t &s0b, uint32_t &s0c, Acc64 &s1, Acc64 &s2, u64 kv, u64 xv) {
     const uint32_t k0 = (uint32_t)kv, k1 = (uint32_t)(kv >> 32);
     const uint32_t x0 = (uint32_t)xv, x1 = (uint32_t)(xv >> 32);
     asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
         : "+r"(s0a), "+r"(s0b), "+r"(s0c) : "r"(k0), "r"(x0));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s1) : "r"(k0), "r"(x1));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s1) : "r"(k1), "r"(x0));
-    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(s2) : "r"(k1), "r"(x1));
+    acc_mad(s1, k0, x1);
+    acc_mad(s1, k1, x0);
+    acc_mad(s2, k1, x1);
 }
 
 template <int OT, int CT, int WARPS, bool FOLD>
@@ -489,11 +500,11 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
     const u64 q = G.q[limb], qi = G.qinvneg[limb];
     const size_t pw = (size_t)n_slots;                                // words per polynomial
     uint32_t s0a[OT][CT], s0b[OT][CT], s0c[OT][CT];
-    u64 s1[OT][CT], s2[OT][CT], s1h[OT][CT], s2h[OT][CT];
+    Acc64 s1[OT][CT], s2[OT][CT]; u64 s1h[OT][CT], s2h[OT][CT];
 #pragma unroll
     for (int a = 0; a < OT; a++)
 #pragma unroll
-        for (int b = 0; b < CT; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = 0; s1h[a][b] = s2h[a][b] = 0; }
+        for (int b = 0; b < CT; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = Acc64{0}; s1h[a][b] = s2h[a][b] = 0; }
     int since = 0;
     // running pointers (ragged tiles clamp to the last valid row / column; their results are not stored)
     const u64 *xp[CT], *kp[OT][CT];
@@ -534,8 +545,8 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
             for (int a = 0; a < OT; a++)
 #pragma unroll
                 for (int b = 0; b < CT; b++) {
-                    s1h[a][b] += s1[a][b] >> 32; s1[a][b] &= 0xffffffffull;
-                    s2h[a][b] += s2[a][b] >> 32; s2[a][b] &= 0xffffffffull;
+                    s1h[a][b] += s1[a][b].v >> 32; s1[a][b].v &= 0xffffffffull;
+                    s2h[a][b] += s2[a][b].v >> 32; s2[a][b].v &= 0xffffffffull;
                 }
         }
     }
@@ -552,8 +563,8 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
                 const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
             };
             auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
-            add_at32(s1[a][b]);
-            add_at64(s2[a][b]);
+            add_at32(s1[a][b].value());
+            add_at64(s2[a][b].value());
             if (FOLD) { add_at64(s1h[a][b]); const u64 v = s2h[a][b]; add_at64(v << 32); w2 += v >> 32; }
             // h = (w2 2^64 + w1) mod q ;  result = (h 2^64 + w0) 2^-64 mod q
             u64 h = w1 >= q ? w1 % q : w1;
@@ -634,11 +645,11 @@ __global__ void __launch_bounds__(MP_THREADS, 1) matvec_pipe_kernel(u64 *__restr
     };
 
     uint32_t s0a[MP_OT][2], s0b[MP_OT][2], s0c[MP_OT][2];
-    u64 s1[MP_OT][2], s2[MP_OT][2], s1h[MP_OT][2], s2h[MP_OT][2];
+    Acc64 s1[MP_OT][2], s2[MP_OT][2]; u64 s1h[MP_OT][2], s2h[MP_OT][2];
 #pragma unroll
     for (int a = 0; a < MP_OT; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = 0; s1h[a][b] = s2h[a][b] = 0; }
+        for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = Acc64{0}; s1h[a][b] = s2h[a][b] = 0; }
 
     const int n_it = (G.K + MP_KS - 1) / MP_KS;
     for (int st = 0; st < MP_STAGES - 1; st++) {
@@ -673,8 +684,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) matvec_pipe_kernel(u64 *__restr
                 for (int a = 0; a < MP_OT; a++)
 #pragma unroll
                     for (int b = 0; b < 2; b++) {
-                        s1h[a][b] += s1[a][b] >> 32; s1[a][b] &= 0xffffffffull;
-                        s2h[a][b] += s2[a][b] >> 32; s2[a][b] &= 0xffffffffull;
+                        s1h[a][b] += s1[a][b].v >> 32; s1[a][b].v &= 0xffffffffull;
+                        s2h[a][b] += s2[a][b].v >> 32; s2[a][b].v &= 0xffffffffull;
                     }
             }
         }
@@ -694,8 +705,8 @@ __global__ void __launch_bounds__(MP_THREADS, 1) matvec_pipe_kernel(u64 *__restr
                 const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
             };
             auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
-            add_at32(s1[a][b]);
-            add_at64(s2[a][b]);
+            add_at32(s1[a][b].value());
+            add_at64(s2[a][b].value());
             if (FOLD) { add_at64(s1h[a][b]); const u64 v = s2h[a][b]; add_at64(v << 32); w2 += v >> 32; }
             u64 h = w1 >= q ? w1 % q : w1;
             if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
@@ -946,7 +957,7 @@ __global__ void __launch_bounds__(256) rowsum_kernel(u64 *__restrict__ out, cons
     const int per = (G.K + ksplit - 1) / ksplit;
     const int k0 = part * per, k1 = (k0 + per < G.K) ? k0 + per : G.K;
     uint32_t s0a = 0, s0b = 0, s0c = 0;
-    u64 s1 = 0, s2 = 0, s1h = 0, s2h = 0;
+    Acc64 s1{0}, s2{0}; u64 s1h = 0, s2h = 0;
     int since = 0;
     const u64 *xp = x + ((size_t)cc * G.x_cs + (size_t)k0 * G.x_ks) * pw + slot;
     const u64 *kp = key + (size_t)k0 * G.key_ks * pw + slot;
@@ -966,8 +977,8 @@ __global__ void __launch_bounds__(256) rowsum_kernel(u64 *__restrict__ out, cons
             mac_lazy(s0a, s0b, s0c, s1, s2, kv[u], xv[u]);
             if (FOLD && ++since == G.fold_every) {
                 since = 0;
-                s1h += s1 >> 32; s1 &= 0xffffffffull;
-                s2h += s2 >> 32; s2 &= 0xffffffffull;
+                s1h += s1.v >> 32; s1.v &= 0xffffffffull;
+                s2h += s2.v >> 32; s2.v &= 0xffffffffull;
             }
         }
     }
@@ -978,8 +989,8 @@ __global__ void __launch_bounds__(256) rowsum_kernel(u64 *__restrict__ out, cons
         const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
     };
     auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
-    add_at32(s1);
-    add_at64(s2);
+    add_at32(s1.value());
+    add_at64(s2.value());
     if (FOLD) { add_at64(s1h); const u64 v = s2h; add_at64(v << 32); w2 += v >> 32; }
     u64 h = w1 >= q ? w1 % q : w1;
     if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
