@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *__res
         const int lb = INV ? full * R : 0;
         if (R >= 2 && rem == 1) run_round<NL, QS, 1, INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
         if (R >= 3 && rem == 2) run_round<NL, QS, (R >= 3 ? 2 : 1), INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
+        if (R >= 4 && rem == 3) run_round<NL, QS, (R >= 4 ? 3 : 1), INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
         __syncthreads();
     }
     move_tile<NL, THREADS, TS, true>(sm, in, out, G, tile);

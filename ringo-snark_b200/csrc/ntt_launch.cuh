@@ -8,13 +8,16 @@ namespace rs {
 #ifndef RS_NTT_R_SMALL
 #define RS_NTT_R_SMALL 3      // radix-2^R rounds for <= 8 limbs (tuning knob)
 #endif
+#ifndef RS_NTT_R_L4
+#define RS_NTT_R_L4 3         // same knob for the 4-limb (128-bit) fields
+#endif
 #ifndef RS_NTT_MINB_SMALL
 #define RS_NTT_MINB_SMALL 2   // resident CTAs per SM the register allocation is capped for
 #endif
 
 template <int NL> struct NttTuning {
     // 2^R elements per thread between shared-memory exchanges
-    static constexpr int R = (NL <= 8) ? RS_NTT_R_SMALL : (NL <= 14 ? 2 : 1);
+    static constexpr int R = (NL <= 4) ? RS_NTT_R_L4 : ((NL <= 8) ? RS_NTT_R_SMALL : (NL <= 14 ? 2 : 1));
     static constexpr int THREADS = 256;
     static constexpr int TS = THREADS << R;
     static constexpr int LOG_TS = 8 + R;
