@@ -244,7 +244,9 @@ struct EncConsts {
     u64 base, base_magic;       // base_magic = floor(2^64 / base) + 1  (base is not a power of two)
     i64 tail_lo;
     double sigma;
-    double delta_inv[RS_JINDO_MAX_EXP];
+    double delta_inv[RS_JINDO_MAX_EXP];   // non-zero entries of Encoder.deltaInv, ascending i (encoder.go:152-164 skips zeros)
+    int delta_w[RS_JINDO_MAX_EXP];        // (i + 1) * slots of the same entries
+    int n_delta;
     u64 base_mont[JMAXL];
 };
 
@@ -321,10 +323,9 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
         } else {
             // float64 centre (encoder.go:152-164), unfused multiply-add in the reference's order
             double fp = 0.0;
-            for (int i = 0; i < E.exp; i++) {
+            for (int i = 0; i < E.n_delta; i++) {          // the non-zero deltaInv terms, ascending i
                 const double di = E.delta_inv[i];
-                if (di == 0.0) continue;
-                const int w = (i + 1) * E.slots;           // N - d
+                const int w = E.delta_w[i];                // N - d
                 if (c >= JD - w) fp = __dadd_rn(fp, __dmul_rn(di, (double)dig[c - (JD - w)]));
                 else fp = __dsub_rn(fp, __dmul_rn(di, (double)dig[c + w]));
             }
@@ -333,7 +334,8 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             const double cfloor = floor(center);
             const double cfrac = __dsub_rn(center, cfloor);
             const double sc = __dmul_rn(128.0, cfrac);
-            const int c0 = (int)(((i64)floor(sc)) % 128), c1 = (int)(((i64)ceil(sc)) % 128);
+            // 0 <= sc < 128 (cfrac in [0, 1)): floor / ceil fit an int, "% BLOCK" only matters for ceil == 128
+            const int c0 = __double2int_rd(sc) & 127, c1 = __double2int_ru(sc) & 127;
             const u64 u = __ldg(twin_u + D.noise_off + c);
             // slices.BinarySearch on both tables at once (branch-free lower bound: number of entries < u),
             // minus one on an exact hit (gaussian_twin_cdt.go:86-93)
@@ -1075,7 +1077,9 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
     E.slots = j->p.slots; E.exp = j->p.exp; E.cdt_len = j->p.cdt_len;
     E.base = j->p.base; E.base_magic = (u64)((((u128)1) << 64) / j->p.base) + 1;
     E.tail_lo = j->p.cdt_tail_lo; E.sigma = j->p.cdt_sigma;
-    for (int i = 0; i < j->p.exp; i++) E.delta_inv[i] = j->p.delta_inv[i];
+    E.n_delta = 0;
+    for (int i = 0; i < j->p.exp; i++)
+        if (j->p.delta_inv[i] != 0.0) { E.delta_inv[E.n_delta] = j->p.delta_inv[i]; E.delta_w[E.n_delta] = (i + 1) * j->p.slots; E.n_delta++; }
     for (int l = 0; l < j->rq.n; l++) E.base_mont[l] = j->base_mont_q[l];
     FieldParams<NL> F = make_params<NL>(j->f);
     int G = JD / j->p.slots;
