@@ -342,7 +342,6 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from oracle import pyref
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -359,7 +358,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     rs.check(L.rs_set_stream(ctypes.c_void_p(stream.cuda_stream)))
 
-    q = pyref.modulus(FIELD)
+    q = product().modulus(FIELD)
     f = rs.Field(q)
     N = 1 << LOGN
     ntt = rs.CyclotomicTransformer(f, N)

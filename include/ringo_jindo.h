@@ -60,6 +60,15 @@ typedef struct rs_jindo_params {
  * 128 x cdt_len TwinCDT tables. */
 int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in, const uint64_t *ck_mlwe,
                     const uint64_t *ck_out, const uint64_t *cdt_tables, rs_jindo **out);
+/* NewProver with NewCommitKey(params, crs) evaluated in HBM (jindo/entities.go:21-61): the key is
+ * the SampleN stream (math/csprng/uniform.go:87-95, rejection included) of a UniformSampler seeded with the CRS, in
+ * the reference's draw order (In, MLWE, Out; polynomial -> coefficient -> limb).  key32 || iv16 = SHA-384(crs)
+ * (uniform.go:38-46), hashed by the caller like rs_jindo_set_twin_stream's.  No key bytes cross PCIe.
+ * rs_jindo_commit_key_download copies ck.In (which = 0), ck.MLWE (1) or ck.Out (2) back (tests; the shim's
+ * CommitKey view), layout as rs_jindo_create's inputs. */
+int rs_jindo_create_crs(rs_field *f, const rs_jindo_params *p, const uint8_t *key32, const uint8_t *iv16,
+                        const uint64_t *cdt_tables, rs_jindo **out);
+int rs_jindo_commit_key_download(const rs_jindo *j, int which, uint64_t *out);
 void rs_jindo_destroy(rs_jindo *j);
 
 /* GPU-resident uniform source of the encoder's TwinCDT sampler.
@@ -122,9 +131,22 @@ int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, u
  *            chals: cols polys over ringQ (host); enc_out: rows polys, mlwe_out: mlwe+in_msis polys */
 int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out);
 int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, uint64_t *enc_out, uint64_t *mlwe_out);
-/* batch > 1 (prover.go:251-265): acc += open (.) challenge, over every polynomial of the opening */
+/* The same two phases with Evaluate's host-side vectors produced on the device, so that only the evaluation point
+ * and the transcript's challenge bytes cross the boundary:
+ *   rs_jindo_partial_at    left = Encoder.EncodeTo of leftVec(x) (jindo/utils.go:63-73, encoder.go:113-117); x_mont: the
+ *                          evaluation point, L64 Montgomery limbs (host)
+ *   rs_jindo_respond_bytes chals = encodeChallengeTo (utils.go:21-46) of cols 16-byte SHAKE outputs (host)
+ *   rs_jindo_left_vec / rs_jindo_encode_challenges  hand the encoded vectors back (tests; the verifier-side shim):
+ *                          rows polys over ringQ / n polys over ringQ (ring_out = 0) or ringQOut (1) */
+int rs_jindo_partial_at(rs_jindo *j, const rs_opening *o, const uint64_t *x_mont, uint64_t *partial_out);
+int rs_jindo_respond_bytes(rs_jindo *j, const rs_opening *o, const uint8_t *chal_bytes, uint64_t *enc_out, uint64_t *mlwe_out);
+int rs_jindo_left_vec(rs_jindo *j, const uint64_t *x_mont, uint64_t *left_out);
+int rs_jindo_encode_challenges(rs_jindo *j, const uint8_t *chal_bytes, size_t n, int ring_out, uint64_t *polys_out);
+/* batch > 1 (prover.go:251-265): acc += open (.) challenge, over every polynomial of the opening;
+ * _bytes: the challenge polynomial of both rings is encoded on the device from its 16 bytes (prover.go:230-249) */
 int rs_opening_alloc_zero(rs_jindo *j, rs_opening **out);
 int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout);
+int rs_opening_mul_add_bytes(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint8_t *chal16);
 
 #ifdef __cplusplus
 }

@@ -481,3 +481,22 @@ def public_key_circuit(rank):
         ctx.add_inf_norm_constraint(0, 1)
         ctx.add_inf_norm_constraint(2, 1)
     return define, 2, 4
+
+
+def ciphertext_circuit(rank, delta, plaintext_modulus, err_bound):
+    """examples/bfv/main.go:30-68 (CiphertextCircuit).  public: CiphertextNTT[0], CiphertextNTT[1];
+    witnesses in declaration order: SecretKeyNTT(0) MessageNTT(1) MessageCoeffs(2) ErrorNTT(3) ErrorCoeffs(4).
+    Body + Mask*sk - Delta*Message - Error = 0 (:56-62), |m| <= t - 1 (:65), |e| <= ErrBound (:67)."""
+    def define(ctx, f):
+        chk = NTTChecker(f, rank)
+        ctx.add_linear_constraint(1, 2, chk)
+        ctx.add_linear_constraint(3, 4, chk)
+        c = ArithmeticConstraint()
+        c.add_term_with_const(1, 0)
+        c.add_term_with_const(1, 1, 0)
+        c.add_term_with_const((-delta) % ctx.q, None, 1)
+        c.add_term_with_const(ctx.q - 1, None, 3)
+        ctx.add_arithmetic_constraint(c)
+        ctx.add_inf_norm_constraint(2, plaintext_modulus - 1)
+        ctx.add_inf_norm_constraint(4, err_bound)
+    return define, 2, 5

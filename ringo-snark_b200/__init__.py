@@ -11,4 +11,4 @@ from . import capi            # noqa: F401
 from .capi import RingoError, lib, load, check  # noqa: F401
 from . import jindo, jindo_host, parallel, buckler  # noqa: F401
 from .bigpoly import (Field, Batch, Poly, CyclicTransformer, CyclotomicTransformer,  # noqa: F401
-                      CyclicEvaluator, CyclotomicEvaluator)
+                      CyclicEvaluator, CyclotomicEvaluator, MODULI, modulus)

@@ -18,6 +18,24 @@ from . import capi
 from .capi import check, lib, c_vp, c_u64p
 
 
+# The moduli the reference ships (jindo-modulus output, q = b^k + 1): package -> (b, k).  SURVEY.md Appendix A2;
+# q itself is what the Go shim reads from the element type (SetInt64(-1).BigInt() + 1, ntt.go:31-38).
+MODULI = {
+    "zp110": (12640, 8),      # buckler/internal/zp110
+    "zp128": (60256, 8),      # examples/mult/zp
+    "zp220": (13216, 16),     # buckler/internal/zp220
+    "zp240": (31432, 16),     # examples/bfv/zp
+    "zp255": (60272, 16),     # jindo/internal/zp
+    "zp440": (13512, 32),     # buckler/internal/zp440
+    "zp880": (13694, 64),     # buckler/internal/zp880
+}
+
+
+def modulus(name):
+    b, k = MODULI[name]
+    return b ** k + 1
+
+
 def _u64p(a):
     return a.ctypes.data_as(c_u64p)
 

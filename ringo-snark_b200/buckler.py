@@ -219,20 +219,16 @@ class Prover:
             bb = hashlib.shake_128(prefix).digest(16 * batch)
             prefix += bb
             ob = gp.NewOpening()
-            for i in range(batch):
-                cq = JH.encode_challenge(jp, self.ringQ, bb[16 * i:16 * i + 16])
-                co = JH.encode_challenge(jp, self.ringQOut, bb[16 * i:16 * i + 16])
-                gp.OpeningMulAdd(ob, opens[i], np.array(cq, dtype=np.uint64), np.array(co, dtype=np.uint64))
+            for i in range(batch):                       # challenge polynomials are encoded on the device from their bytes
+                gp.OpeningMulAddBytes(ob, opens[i], bb[16 * i:16 * i + 16])
         else:
             ob = opens[0]
-        left = np.array([JH.encode_elements(jp, self.ringQ, q, [le]) for le in JH.left_vec(jp, q, x)], dtype=np.uint64)
-        part = gp.Partial(ob, left)
+        part = gp.PartialAt(ob, self.mont(x))            # leftVec(x) + Encoder.EncodeTo on the device
         pf = {"Partial": part[:jp.cols].tolist(), "PartialMask": part[jp.cols].tolist(),
               "InCommit": [ob.InCommit(k).tolist() for k in range(jp.in_com_dcmp_len)]}
         tr = prefix + b"".join(JH.poly_write_to(c) for c in pf["Partial"]) + JH.poly_write_to(pf["PartialMask"])
         cs = hashlib.shake_128(tr).digest(16 * jp.cols)
-        chals = np.array([JH.encode_challenge(jp, self.ringQ, cs[16 * i:16 * i + 16]) for i in range(jp.cols)], dtype=np.uint64)
-        enc, ml = gp.Respond(ob, chals)
+        enc, ml = gp.RespondBytes(ob, cs)
         pf["Encode"], pf["MLWE"] = enc.tolist(), ml.tolist()
         xm = self.mont(x)
         evals = []

@@ -100,6 +100,8 @@ _SIGS = {
     "rs_poly_evaluate": (ctypes.c_int, [c_vp, c_size, c_size, c_u64p, c_u64p]),
     # ringo_jindo.h
     "rs_jindo_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "rs_jindo_create_crs": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "rs_jindo_commit_key_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
     "rs_jindo_destroy": (None, [c_vp]),
     "rs_jindo_set_twin_stream": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "rs_jindo_twin_stream_draw": (ctypes.c_int, [c_vp, c_size, c_vp]),
@@ -112,6 +114,11 @@ _SIGS = {
     "rs_opening_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_size, c_size, c_vp]),
     "rs_jindo_partial": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "rs_jindo_respond": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rs_jindo_partial_at": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "rs_jindo_respond_bytes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "rs_jindo_left_vec": (ctypes.c_int, [c_vp, c_vp, c_vp]),
+    "rs_jindo_encode_challenges": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.c_int, c_vp]),
+    "rs_opening_mul_add_bytes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "rs_opening_alloc_zero": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "rs_opening_mul_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }

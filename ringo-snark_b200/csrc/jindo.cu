@@ -72,6 +72,8 @@ void uniform_stream_release(UniformStream *s);
 struct rs_jindo {
     std::vector<DescCache> *cache;
     rs::EncDesc *d_ndescs;    // descriptors of the MLWE noise polynomials
+    rs::EncDesc *d_ldescs;    // descriptors of the encoded leftVec (rs_jindo_partial_at)
+    long long *d_zero_g;      // 256 zero "noise" samples (deterministic Encoder.EncodeTo through encode_kernel)
     rs_field *f;
     rs_jindo_params p;
     RingDev rq, rqo;
@@ -83,6 +85,7 @@ struct rs_jindo {
     u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
     rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
     cudaStream_t copy_stream;         // rs_jindo_commit_host: uploads of v pieces
+    size_t ck_rejected;               // rs_jindo_create_crs: draws SampleN threw away while generating the key
     cudaEvent_t ev_alloc, ev_piece[RS_VCHUNKS];
 };
 
@@ -1155,9 +1158,227 @@ static int opening_alloc(rs_jindo *j, rs_opening **out) {
 extern "C" {
 #pragma GCC visibility push(default)
 
+// ---------------------------------------------------------------------------------------------
+// Evaluate's host-side vectors on the device (jindo/utils.go).
+//   leftVec (utils.go:63-73): left[i] = (x^(cols*slots))^i, except left[rows-1] = x.  One thread per entry,
+//   square-and-multiply on Montgomery elements (exact field arithmetic: the same canonical values as the
+//   reference's running product).  The entries are then encoded by encode_kernel as Encoder.EncodeTo does
+//   (encoder.go:113-117: one element in slot 0, no noise).
+//   encodeChallengeTo (utils.go:21-46): 16 bytes -> two big-endian words, read as a little-endian 128-bit number
+//   (bytes 8..15 are the HIGH limb), exp balanced digits in base B = ChallengeBound() at coefficients i*slots,
+//   MForm, NTT.  One CTA per (challenge, RNS limb).
+// ---------------------------------------------------------------------------------------------
+extern "C++" {
+namespace rs {
+template <int NL>
+__global__ void left_vec_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ xin, int rows, unsigned skip_exp,
+                                const __grid_constant__ FieldParams<NL> F) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    uint32_t b[NL], skip[NL], r[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) { b[l] = xin[l]; skip[l] = F.one[l]; r[l] = F.one[l]; }
+    if (i == rows - 1) {                                    // utils.go:71
+#pragma unroll
+        for (int l = 0; l < NL; l++) out[(size_t)i * NL + l] = b[l];
+        return;
+    }
+    for (unsigned e = skip_exp; e; e >>= 1) {               // skip = x^(cols*slots)
+        if (e & 1) mont_mul<NL, 0>(skip, skip, b, F);
+        mont_mul<NL, 0>(b, b, b, F);
+    }
+    for (unsigned e = (unsigned)i; e; e >>= 1) {            // left[i] = skip^i
+        if (e & 1) mont_mul<NL, 0>(r, r, skip, F);
+        mont_mul<NL, 0>(skip, skip, skip, F);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) out[(size_t)i * NL + l] = r[l];
+}
+
+__global__ void __launch_bounds__(128) challenge_kernel(u64 *__restrict__ out, const uint8_t *__restrict__ bytes, int exp, int slots,
+                                                        uint32_t bound, const __grid_constant__ RingDev R) {
+    __shared__ u64 a[JD];
+    __shared__ uint32_t dig[RS_JINDO_MAX_EXP];
+    const int ch = blockIdx.x, l = blockIdx.y, t = threadIdx.x;
+    const u64 q = R.q[l], qi = R.qinvneg[l];
+    if (t == 0) {
+        const uint8_t *b = bytes + (size_t)ch * 16;
+        uint32_t w[4];                                      // little-endian 32-bit limbs of c = [BE64(b[0:8]), BE64(b[8:16])]
+        w[1] = (uint32_t)b[0] << 24 | (uint32_t)b[1] << 16 | (uint32_t)b[2] << 8 | b[3];
+        w[0] = (uint32_t)b[4] << 24 | (uint32_t)b[5] << 16 | (uint32_t)b[6] << 8 | b[7];
+        w[3] = (uint32_t)b[8] << 24 | (uint32_t)b[9] << 16 | (uint32_t)b[10] << 8 | b[11];
+        w[2] = (uint32_t)b[12] << 24 | (uint32_t)b[13] << 16 | (uint32_t)b[14] << 8 | b[15];
+        for (int i = 0; i < exp; i++) {                     // divMod64 (utils.go:12-18)
+            uint32_t r = 0;
+            for (int k = 3; k >= 0; k--) {
+                const u64 cur = ((u64)r << 32) | w[k];
+                w[k] = (uint32_t)(cur / bound);
+                r = (uint32_t)(cur % bound);
+            }
+            dig[i] = r;
+        }
+    }
+    a[t] = 0; a[t + 128] = 0;
+    __syncthreads();
+    if (t < exp) {
+        const uint32_t r = dig[t];
+        const u64 val = (r > bound / 2) ? q - (u64)(bound - r) : (u64)r;
+        a[t * slots] = mont64(val, R.r2[l], q, qi);         // MForm
+    }
+    __syncthreads();
+    ntt256(a, R.roots + (size_t)l * JD, q, qi, t, 1, 128);
+    u64 *dst = out + ((size_t)ch * R.n + l) * JD;
+    dst[t] = a[t]; dst[t + 128] = a[t + 128];
+}
+}  // namespace rs
+}  // extern "C++"
+
+// ---------------------------------------------------------------------------------------------
+// NewCommitKey on the device (jindo/entities.go:21-61).  The key is the SampleN stream of one
+// csprng.UniformSampler seeded with the CRS: polynomial -> coefficient k -> limb l, each value the first draw below
+// bound_l = MaxUint64 - MaxUint64 % q_l, reduced mod q_l (uniform.go:87-95).  Draws come from aes_ctr.cu (same XOR-
+// accumulated keystream).  A rejected draw shifts every later sample by one stream position, and whether a draw is
+// rejected depends on the limb it lands on, so: (1) flag the draws that ANY limb would reject (rare: < q_max / 2^64),
+// (2) the host walks that short sorted list once, deciding each with the shift accumulated so far, (3) one kernel
+// writes every polynomial, finding its shift by binary search in the list of rejected positions.
+// ---------------------------------------------------------------------------------------------
+struct KeyGeom {
+    u64 n_in, n_ml, n_out;          // samples of ck.In, ck.MLWE (ringQ) and ck.Out (ringQOut)
+    int nq, nqo;
+    u64 q[JMAXL], qo[JMAXL];
+};
+
+namespace rs {
+__global__ void key_candidates_kernel(const u64 *__restrict__ smp, u64 n, u64 min_bound, u64 *__restrict__ list, unsigned *count, unsigned cap) {
+    for (u64 s = blockIdx.x * (u64)blockDim.x + threadIdx.x; s < n; s += (u64)gridDim.x * blockDim.x)
+        if (smp[s] >= min_bound) { const unsigned at = atomicAdd(count, 1u); if (at < cap) { list[2 * at] = s; list[2 * at + 1] = smp[s]; } }
+}
+
+__global__ void key_sample_kernel(u64 *__restrict__ ck_in, u64 *__restrict__ ck_mlwe, u64 *__restrict__ ck_out, const u64 *__restrict__ smp,
+                                  const u64 *__restrict__ rejected, unsigned n_rej, const __grid_constant__ KeyGeom G) {
+    const u64 total = G.n_in + G.n_ml + G.n_out;
+    for (u64 s = blockIdx.x * (u64)blockDim.x + threadIdx.x; s < total + n_rej; s += (u64)gridDim.x * blockDim.x) {
+        unsigned lo = 0, hi = n_rej;                       // lo = #{ rejected positions <= s }
+        while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (rejected[mid] <= s) lo = mid + 1; else hi = mid; }
+        if (lo && rejected[lo - 1] == s) continue;         // this draw was thrown away
+        u64 o = s - lo;
+        u64 *dst; int nl; const u64 *mod;
+        if (o < G.n_in) { dst = ck_in; nl = G.nq; mod = G.q; }
+        else if (o < G.n_in + G.n_ml) { o -= G.n_in; dst = ck_mlwe; nl = G.nq; mod = G.q; }
+        else { o -= G.n_in + G.n_ml; dst = ck_out; nl = G.nqo; mod = G.qo; }
+        const u64 poly = o / ((u64)JD * nl), rem = o % ((u64)JD * nl);
+        const int k = (int)(rem / nl), l = (int)(rem % nl);
+        dst[(poly * nl + l) * JD + k] = smp[s] % mod[l];
+    }
+}
+}  // namespace rs
+
+static u64 sample_bound(u64 n) { return ~0ull - (~0ull % n); }
+
+// fills j->d_ck_* from the CRS stream; returns the number of rejected draws through *n_rejected
+static int generate_commit_key(rs_jindo *j, const uint8_t *key32, const uint8_t *iv16, size_t *n_rejected) {
+    using namespace rs;
+    const rs_jindo_params &p = j->p;
+    KeyGeom G;
+    memset(&G, 0, sizeof(G));
+    G.nq = p.n_q; G.nqo = p.n_qout;
+    G.n_in = (u64)p.in_msis * p.rows * pq(j); G.n_ml = (u64)p.in_msis * p.mlwe * pq(j);
+    G.n_out = (u64)p.out_msis * (p.cols + 1) * p.in_msis * pqo(j);
+    u64 min_bound = ~0ull;
+    for (int l = 0; l < p.n_q; l++) { G.q[l] = p.q[l]; if (sample_bound(p.q[l]) < min_bound) min_bound = sample_bound(p.q[l]); }
+    for (int l = 0; l < p.n_qout; l++) { G.qo[l] = p.qout[l]; if (sample_bound(p.qout[l]) < min_bound) min_bound = sample_bound(p.qout[l]); }
+    const u64 total = G.n_in + G.n_ml + G.n_out;
+    const u64 slack = total / 64 + 4096;                    // rejection rate < q_max / 2^64 <= 2^-4 at the 60-bit limit; typically 2^-9 .. 2^-26
+    UniformStream *us = nullptr;
+    int rc = uniform_stream_init(&us, key32, iv16);
+    if (rc) return rc;
+    const u64 *smp = nullptr;
+    u64 *d_list = nullptr; unsigned *d_count = nullptr;
+    std::vector<u64> cand, vals, rej;
+    unsigned n_cand = 0;
+    const unsigned cap = (unsigned)slack;
+    rc = uniform_stream_draw(us, total + slack, &smp);
+    cudaError_t e = cudaSuccess;
+    if (rc == RS_OK) {
+        e = cudaMalloc((void **)&d_list, (size_t)cap * 16);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d_count, 4);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, 4, current_stream());
+    }
+    if (rc == RS_OK && e == cudaSuccess) {
+        key_candidates_kernel<<<148 * 8, 256, 0, current_stream()>>>(smp, total + slack, min_bound, d_list, d_count, cap);
+        count_launch();
+        e = cudaMemcpyAsync(&n_cand, d_count, 4, cudaMemcpyDeviceToHost, current_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+    }
+    if (rc == RS_OK && e == cudaSuccess && n_cand > cap) rc = set_error(RS_ERR_UNSUPPORTED, "rs_jindo_create_crs: %u rejection candidates exceed the slack of %llu draws", n_cand, (unsigned long long)slack);
+    if (rc == RS_OK && e == cudaSuccess && n_cand) {
+        std::vector<u64> pairs((size_t)2 * n_cand);
+        e = cudaMemcpy(pairs.data(), d_list, pairs.size() * 8, cudaMemcpyDeviceToHost);
+        std::vector<std::pair<u64, u64>> pv(n_cand);
+        for (unsigned i = 0; i < n_cand; i++) pv[i] = {pairs[2 * i], pairs[2 * i + 1]};
+        std::sort(pv.begin(), pv.end());
+        cand.resize(n_cand); vals.resize(n_cand);
+        for (unsigned i = 0; i < n_cand; i++) { cand[i] = pv[i].first; vals[i] = pv[i].second; }
+        if (e == cudaSuccess) {
+            for (unsigned i = 0; i < n_cand; i++) {
+                const u64 s = cand[i];
+                if (s >= total + rej.size()) break;          // past the last draw the key consumes
+                u64 o = s - rej.size();
+                int nl; const u64 *mod;
+                if (o < G.n_in) { nl = G.nq; mod = G.q; }
+                else if (o < G.n_in + G.n_ml) { o -= G.n_in; nl = G.nq; mod = G.q; }
+                else { o -= G.n_in + G.n_ml; nl = G.nqo; mod = G.qo; }
+                const int l = (int)(o % (u64)nl);
+                if (vals[i] >= sample_bound(mod[l])) rej.push_back(s);
+            }
+        }
+    }
+    if (rc == RS_OK && e == cudaSuccess && rej.size() > slack) rc = set_error(RS_ERR_UNSUPPORTED, "rs_jindo_create_crs: more rejected draws than slack");
+    if (rc == RS_OK && e == cudaSuccess) {
+        if (!rej.empty()) e = cudaMemcpyAsync(d_list, rej.data(), rej.size() * 8, cudaMemcpyHostToDevice, current_stream());
+        if (e == cudaSuccess) {
+            key_sample_kernel<<<148 * 8, 256, 0, current_stream()>>>(j->d_ck_in, j->d_ck_mlwe, j->d_ck_out, smp, d_list, (unsigned)rej.size(), G);
+            count_launch();
+            uniform_stream_release(us);
+            e = cudaStreamSynchronize(current_stream());
+            if (e == cudaSuccess) e = cudaGetLastError();
+        }
+    }
+    cudaFree(d_list); cudaFree(d_count);
+    uniform_stream_free(us);
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_error(RS_ERR_CUDA, "rs_jindo_create_crs: %s", cudaGetErrorString(e));
+    if (n_rejected) *n_rejected = rej.size();
+    return RS_OK;
+}
+
+static int jindo_create_impl(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in, const uint64_t *ck_mlwe,
+                             const uint64_t *ck_out, const uint64_t *cdt_tables, const uint8_t *key32, const uint8_t *iv16, rs_jindo **out);
+
 int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in, const uint64_t *ck_mlwe,
                     const uint64_t *ck_out, const uint64_t *cdt_tables, rs_jindo **out) {
     RS_REQUIRE(f && p && ck_in && ck_mlwe && ck_out && cdt_tables && out, RS_ERR_ARG, "rs_jindo_create: null argument");
+    return jindo_create_impl(f, p, ck_in, ck_mlwe, ck_out, cdt_tables, nullptr, nullptr, out);
+}
+
+int rs_jindo_create_crs(rs_field *f, const rs_jindo_params *p, const uint8_t *key32, const uint8_t *iv16,
+                        const uint64_t *cdt_tables, rs_jindo **out) {
+    RS_REQUIRE(f && p && key32 && iv16 && cdt_tables && out, RS_ERR_ARG, "rs_jindo_create_crs: null argument");
+    return jindo_create_impl(f, p, nullptr, nullptr, nullptr, cdt_tables, key32, iv16, out);
+}
+
+int rs_jindo_commit_key_download(const rs_jindo *j, int which, uint64_t *out) {
+    RS_REQUIRE(j && out && which >= 0 && which <= 2, RS_ERR_ARG, "rs_jindo_commit_key_download: bad argument");
+    const rs_jindo_params &p = j->p;
+    const size_t n = which == 0 ? (size_t)p.in_msis * p.rows * pq(j) : which == 1 ? (size_t)p.in_msis * p.mlwe * pq(j)
+                                : (size_t)p.out_msis * (p.cols + 1) * p.in_msis * pqo(j);
+    const u64 *src = which == 0 ? j->d_ck_in : which == 1 ? j->d_ck_mlwe : j->d_ck_out;
+    RS_CUDA_CHECK(cudaMemcpy(out, src, n * 8, cudaMemcpyDeviceToHost));
+    return RS_OK;
+}
+
+static int jindo_create_impl(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in, const uint64_t *ck_mlwe,
+                             const uint64_t *ck_out, const uint64_t *cdt_tables, const uint8_t *key32, const uint8_t *iv16, rs_jindo **out) {
     RS_REQUIRE(p->d == JD, RS_ERR_UNSUPPORTED, "rs_jindo_create: ring degree must be 256");
     RS_REQUIRE(p->n_q >= 1 && p->n_q <= JMAXL && p->n_qout >= 1 && p->n_qout <= JMAXL, RS_ERR_UNSUPPORTED, "rs_jindo_create: 1..4 RNS limbs");
     RS_REQUIRE(p->exp >= 1 && p->exp <= RS_JINDO_MAX_EXP && p->slots * p->exp == JD, RS_ERR_ARG, "rs_jindo_create: slots*exp != d");
@@ -1183,9 +1404,14 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
     if (e == cudaSuccess) e = cudaMalloc((void **)&j->d_ck_out, n_out * 8);
     if (e == cudaSuccess) e = cudaMalloc((void **)&j->d_cdt, n_cdt * 8);
     if (e == cudaSuccess) e = cudaMemcpy(j->d_roots, roots.data(), roots.size() * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_in, ck_in, n_in * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_mlwe, ck_mlwe, n_ml * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_out, ck_out, n_out * 8, cudaMemcpyHostToDevice);
+    if (ck_in) {
+        if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_in, ck_in, n_in * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_mlwe, ck_mlwe, n_ml * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(j->d_ck_out, ck_out, n_out * 8, cudaMemcpyHostToDevice);
+    } else if (e == cudaSuccess) {
+        rc = generate_commit_key(j, key32, iv16, &j->ck_rejected);
+        if (rc != RS_OK) { rs_jindo_destroy(j); return rc; }
+    }
     if (e == cudaSuccess) e = cudaMemcpy(j->d_cdt, cdt_tables, n_cdt * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && p->cdt_len <= 255 && !getenv("RS_JINDO_NOGUIDE")) {
         // guide[t][b] = #{ i : table_t[i] < b << 56 }, b = 0..256 (tables are sorted: gaussian_twin_cdt.go:13-35)
@@ -1226,7 +1452,7 @@ void rs_jindo_destroy(rs_jindo *j) {
     }
     cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt); cudaFree(j->d_cdt_guide);
     if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
-    cudaFree(j->d_ndescs);
+    cudaFree(j->d_ndescs); cudaFree(j->d_ldescs); cudaFree(j->d_zero_g);
     rs::uniform_stream_free(j->twin_stream);
     delete j;
 }
@@ -1538,34 +1764,130 @@ int rs_jindo_commit_host(rs_jindo *j, const uint64_t *v_host, size_t len, const 
     return commit_impl(j, nullptr, v_host, len, tape, open, commitment_out, 0, j->p.cols + 1);
 }
 
-int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out) {
-    RS_REQUIRE(j && o && left && partial_out, RS_ERR_ARG, "rs_jindo_partial: null argument");
+static int partial_impl(rs_jindo *j, const rs_opening *o, const u64 *d_left, uint64_t *partial_out) {
     const rs_jindo_params &p = j->p;
-    u64 *d_left = nullptr, *d_out = nullptr;
-    int rc = upload(&d_left, (const u64 *)left, (size_t)p.rows * pq(j));
-    if (rc) return rc;
+    u64 *d_out = nullptr;
     RS_CUDA_CHECK(cudaMallocAsync((void **)&d_out, (size_t)(p.cols + 1) * pq(j) * 8, current_stream()));
     MatvecGeom G;
     memset(&G, 0, sizeof(G));
     G.O = 1; G.C = p.cols + 1; G.K = p.rows;
     G.key_os = 0; G.key_ks = 1; G.x_cs = p.rows; G.x_ks = 1; G.out_cs = 1; G.out_os = 0;
-    rc = launch_matvec(d_out, d_left, o->d_encode, nullptr, G, j->rq);
+    int rc = launch_matvec(d_out, d_left, o->d_encode, nullptr, G, j->rq);
     if (rc == RS_OK) {
         cudaError_t e = cudaMemcpyAsync(partial_out, d_out, (size_t)(p.cols + 1) * pq(j) * 8, cudaMemcpyDeviceToHost, current_stream());
         if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
         if (e != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_partial: %s", cudaGetErrorString(e));
     }
-    cudaFreeAsync(d_left, current_stream()); cudaFreeAsync(d_out, current_stream());
+    cudaFreeAsync(d_out, current_stream());
     return rc;
 }
 
-int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, uint64_t *enc_out, uint64_t *mlwe_out) {
-    RS_REQUIRE(j && o && chals && enc_out && mlwe_out, RS_ERR_ARG, "rs_jindo_respond: null argument");
+int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out) {
+    RS_REQUIRE(j && o && left && partial_out, RS_ERR_ARG, "rs_jindo_partial: null argument");
+    u64 *d_left = nullptr;
+    int rc = upload(&d_left, (const u64 *)left, (size_t)j->p.rows * pq(j));
+    if (rc == RS_OK) rc = partial_impl(j, o, d_left, partial_out);
+    cudaFreeAsync(d_left, current_stream());
+    return rc;
+}
+
+extern "C++" {
+template <int NL>
+static int launch_left_vec(rs_jindo *j, uint32_t *d_elems, const uint32_t *d_x) {
+    const rs_jindo_params &p = j->p;
+    FieldParams<NL> F = make_params<NL>(j->f);
+    left_vec_kernel<NL><<<(p.rows + 127) / 128, 128, 0, current_stream()>>>(d_elems, d_x, p.rows, (unsigned)(p.cols * p.slots), F);
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+}  // extern "C++"
+
+// leftVec(x) encoded into rows polynomials over ringQ at *d_left (cudaMallocAsync'ed here)
+static int encode_left_vec(rs_jindo *j, const uint64_t *x_mont, u64 **d_left) {
+    const rs_jindo_params &p = j->p;
+    const int NL = j->f->NL;
+    *d_left = nullptr;
+    if (!j->d_ldescs) {                                     // one descriptor per row: aux element i -> polynomial i, no noise
+        std::vector<EncDesc> ld((size_t)p.rows);
+        for (int i = 0; i < p.rows; i++) ld[i] = EncDesc{1, 1, (i64)i, 1, 0, (i64)i};
+        RS_CUDA_CHECK(cudaMalloc((void **)&j->d_ldescs, ld.size() * sizeof(EncDesc)));
+        RS_CUDA_CHECK(cudaMemcpy(j->d_ldescs, ld.data(), ld.size() * sizeof(EncDesc), cudaMemcpyHostToDevice));
+        RS_CUDA_CHECK(cudaMalloc((void **)&j->d_zero_g, JD * sizeof(i64)));
+        RS_CUDA_CHECK(cudaMemset(j->d_zero_g, 0, JD * sizeof(i64)));
+    }
+    uint32_t *d_elems = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_elems, ((size_t)p.rows + 1) * NL * 4, current_stream()));
+    uint32_t *d_x = d_elems + (size_t)p.rows * NL;
+    int rc = RS_OK;
+    if (cudaMemcpyAsync(d_x, x_mont, (size_t)NL * 4, cudaMemcpyHostToDevice, current_stream()) != cudaSuccess)
+        rc = set_error(RS_ERR_CUDA, "rs_jindo_partial_at: upload failed");
+    if (rc == RS_OK) {
+        switch (NL) {
+            case 4: rc = launch_left_vec<4>(j, d_elems, d_x); break;
+            case 8: rc = launch_left_vec<8>(j, d_elems, d_x); break;
+            case 14: rc = launch_left_vec<14>(j, d_elems, d_x); break;
+            case 28: rc = launch_left_vec<28>(j, d_elems, d_x); break;
+            default: rc = set_error(RS_ERR_UNSUPPORTED, "unsupported limb count");
+        }
+    }
+    if (rc == RS_OK && cudaMallocAsync((void **)d_left, (size_t)p.rows * pq(j) * 8, current_stream()) != cudaSuccess)
+        rc = set_error(RS_ERR_CUDA, "rs_jindo_partial_at: cudaMallocAsync failed");
+    if (rc == RS_OK) rc = encode_dispatch(j, *d_left, j->d_ldescs, (size_t)p.rows, nullptr, d_elems, nullptr, j->d_zero_g);
+    cudaFreeAsync(d_elems, current_stream());
+    return rc;
+}
+
+int rs_jindo_partial_at(rs_jindo *j, const rs_opening *o, const uint64_t *x_mont, uint64_t *partial_out) {
+    RS_REQUIRE(j && o && x_mont && partial_out, RS_ERR_ARG, "rs_jindo_partial_at: null argument");
+    u64 *d_left = nullptr;
+    int rc = encode_left_vec(j, x_mont, &d_left);
+    if (rc == RS_OK) rc = partial_impl(j, o, d_left, partial_out);
+    if (d_left) cudaFreeAsync(d_left, current_stream());
+    return rc;
+}
+
+int rs_jindo_left_vec(rs_jindo *j, const uint64_t *x_mont, uint64_t *left_out) {
+    RS_REQUIRE(j && x_mont && left_out, RS_ERR_ARG, "rs_jindo_left_vec: null argument");
+    u64 *d_left = nullptr;
+    int rc = encode_left_vec(j, x_mont, &d_left);
+    if (rc == RS_OK) {
+        cudaError_t e = cudaMemcpyAsync(left_out, d_left, (size_t)j->p.rows * pq(j) * 8, cudaMemcpyDeviceToHost, current_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+        if (e != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_left_vec: %s", cudaGetErrorString(e));
+    }
+    if (d_left) cudaFreeAsync(d_left, current_stream());
+    return rc;
+}
+
+static uint32_t challenge_bound(const rs_jindo_params &p) {              // params.go:358-361
+    const int sh = 120 / p.exp;
+    const u64 cap = sh >= 63 ? ~0ull : (1ull << sh);
+    return (uint32_t)((p.base < cap ? p.base : cap) / 2);
+}
+
+// n challenges of 16 bytes (host) -> n polynomials over `ring` at *d_out (cudaMallocAsync'ed here)
+static int encode_challenges(rs_jindo *j, const uint8_t *bytes, size_t n, const RingDev &ring, u64 **d_out) {
+    *d_out = nullptr;
+    uint8_t *d_b = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_b, n * 16, current_stream()));
+    int rc = RS_OK;
+    if (cudaMemcpyAsync(d_b, bytes, n * 16, cudaMemcpyHostToDevice, current_stream()) != cudaSuccess ||
+        cudaMallocAsync((void **)d_out, n * (size_t)ring.n * JD * 8, current_stream()) != cudaSuccess)
+        rc = set_error(RS_ERR_CUDA, "encode_challenges: allocation / upload failed");
+    if (rc == RS_OK) {
+        challenge_kernel<<<dim3((unsigned)n, (unsigned)ring.n), 128, 0, current_stream()>>>(*d_out, d_b, j->p.exp, j->p.slots, challenge_bound(j->p), ring);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) rc = set_error(RS_ERR_CUDA, "challenge_kernel launch failed");
+    }
+    cudaFreeAsync(d_b, current_stream());
+    return rc;
+}
+
+static int respond_impl(rs_jindo *j, const rs_opening *o, const u64 *d_ch, uint64_t *enc_out, uint64_t *mlwe_out) {
     const rs_jindo_params &p = j->p;
     const int nm = p.mlwe + p.in_msis;
-    u64 *d_ch = nullptr, *d_e = nullptr, *d_m = nullptr;
-    int rc = upload(&d_ch, (const u64 *)chals, (size_t)p.cols * pq(j));
-    if (rc) return rc;
+    u64 *d_e = nullptr, *d_m = nullptr;
     RS_CUDA_CHECK(cudaMallocAsync((void **)&d_e, (size_t)p.rows * pq(j) * 8, current_stream()));
     RS_CUDA_CHECK(cudaMallocAsync((void **)&d_m, (size_t)nm * pq(j) * 8, current_stream()));
     MatvecGeom G;
@@ -1574,7 +1896,7 @@ int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, ui
     G.O = 1; G.C = p.rows; G.K = p.cols;
     G.key_os = 0; G.key_ks = 1; G.x_cs = 1; G.x_ks = p.rows; G.out_cs = 1; G.out_os = 0;
     G.has_addend = 1; G.add_cs = 1; G.add_os = 0;
-    rc = launch_matvec(d_e, d_ch, o->d_encode, o->d_encode + (size_t)p.cols * p.rows * pq(j), G, j->rq);
+    int rc = launch_matvec(d_e, d_ch, o->d_encode, o->d_encode + (size_t)p.cols * p.rows * pq(j), G, j->rq);
     if (rc == RS_OK) {
         G.C = nm; G.x_ks = nm;
         rc = launch_matvec(d_m, d_ch, o->d_mlwe, o->d_mlwe + (size_t)p.cols * nm * pq(j), G, j->rq);
@@ -1585,17 +1907,44 @@ int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, ui
         if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
         if (e != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_respond: %s", cudaGetErrorString(e));
     }
-    cudaFreeAsync(d_ch, current_stream()); cudaFreeAsync(d_e, current_stream()); cudaFreeAsync(d_m, current_stream());
+    cudaFreeAsync(d_e, current_stream()); cudaFreeAsync(d_m, current_stream());
     return rc;
 }
 
-int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout) {
-    RS_REQUIRE(j && acc && o && chal_q && chal_qout, RS_ERR_ARG, "rs_opening_mul_add: null argument");
+int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, uint64_t *enc_out, uint64_t *mlwe_out) {
+    RS_REQUIRE(j && o && chals && enc_out && mlwe_out, RS_ERR_ARG, "rs_jindo_respond: null argument");
+    u64 *d_ch = nullptr;
+    int rc = upload(&d_ch, (const u64 *)chals, (size_t)j->p.cols * pq(j));
+    if (rc == RS_OK) rc = respond_impl(j, o, d_ch, enc_out, mlwe_out);
+    cudaFreeAsync(d_ch, current_stream());
+    return rc;
+}
+
+int rs_jindo_respond_bytes(rs_jindo *j, const rs_opening *o, const uint8_t *chal_bytes, uint64_t *enc_out, uint64_t *mlwe_out) {
+    RS_REQUIRE(j && o && chal_bytes && enc_out && mlwe_out, RS_ERR_ARG, "rs_jindo_respond_bytes: null argument");
+    u64 *d_ch = nullptr;
+    int rc = encode_challenges(j, chal_bytes, (size_t)j->p.cols, j->rq, &d_ch);
+    if (rc == RS_OK) rc = respond_impl(j, o, d_ch, enc_out, mlwe_out);
+    if (d_ch) cudaFreeAsync(d_ch, current_stream());
+    return rc;
+}
+
+int rs_jindo_encode_challenges(rs_jindo *j, const uint8_t *chal_bytes, size_t n, int ring_out, uint64_t *polys_out) {
+    RS_REQUIRE(j && chal_bytes && polys_out && n >= 1, RS_ERR_ARG, "rs_jindo_encode_challenges: bad argument");
+    const RingDev &ring = ring_out ? j->rqo : j->rq;
+    u64 *d_ch = nullptr;
+    int rc = encode_challenges(j, chal_bytes, n, ring, &d_ch);
+    if (rc == RS_OK) {
+        cudaError_t e = cudaMemcpyAsync(polys_out, d_ch, n * (size_t)ring.n * JD * 8, cudaMemcpyDeviceToHost, current_stream());
+        if (e == cudaSuccess) e = cudaStreamSynchronize(current_stream());
+        if (e != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_encode_challenges: %s", cudaGetErrorString(e));
+    }
+    if (d_ch) cudaFreeAsync(d_ch, current_stream());
+    return rc;
+}
+
+static int opening_mul_add_impl(rs_jindo *j, rs_opening *acc, const rs_opening *o, const u64 *d_cq, const u64 *d_co) {
     const rs_jindo_params &p = j->p;
-    u64 *d_cq = nullptr, *d_co = nullptr;
-    int rc = upload(&d_cq, (const u64 *)chal_q, pq(j));
-    if (rc == RS_OK) rc = upload(&d_co, (const u64 *)chal_qout, pqo(j));
-    if (rc) return rc;
     MatvecGeom Gq, Go;
     memset(&Gq, 0, sizeof(Gq)); memset(&Go, 0, sizeof(Go));
     fill_geom_ring(Gq, j->rq); fill_geom_ring(Go, j->rqo);
@@ -1605,9 +1954,29 @@ int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const 
     muladd_bcast_kernel<<<148 * 2, 256, 0, current_stream()>>>(acc->d_incommit, o->d_incommit, d_co, ni, j->rqo.n, Go);
     count_launch(3);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(d_cq, current_stream()); cudaFreeAsync(d_co, current_stream());
     if (e != cudaSuccess) return set_error(RS_ERR_CUDA, "rs_opening_mul_add: %s", cudaGetErrorString(e));
     return RS_OK;
+}
+
+int rs_opening_mul_add_bytes(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint8_t *chal16) {
+    RS_REQUIRE(j && acc && o && chal16, RS_ERR_ARG, "rs_opening_mul_add_bytes: null argument");
+    u64 *d_cq = nullptr, *d_co = nullptr;
+    int rc = encode_challenges(j, chal16, 1, j->rq, &d_cq);
+    if (rc == RS_OK) rc = encode_challenges(j, chal16, 1, j->rqo, &d_co);
+    if (rc == RS_OK) rc = opening_mul_add_impl(j, acc, o, d_cq, d_co);
+    if (d_cq) cudaFreeAsync(d_cq, current_stream());
+    if (d_co) cudaFreeAsync(d_co, current_stream());
+    return rc;
+}
+
+int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout) {
+    RS_REQUIRE(j && acc && o && chal_q && chal_qout, RS_ERR_ARG, "rs_opening_mul_add: null argument");
+    u64 *d_cq = nullptr, *d_co = nullptr;
+    int rc = upload(&d_cq, (const u64 *)chal_q, pq(j));
+    if (rc == RS_OK) rc = upload(&d_co, (const u64 *)chal_qout, pqo(j));
+    if (rc == RS_OK) rc = opening_mul_add_impl(j, acc, o, d_cq, d_co);
+    cudaFreeAsync(d_cq, current_stream()); cudaFreeAsync(d_co, current_stream());
+    return rc;
 }
 
 #pragma GCC visibility pop

@@ -49,7 +49,8 @@ class Prover:
     RNS primes / psi, deltaInv and the TwinCDT tables; `ck_*` are the commit-key polynomials as
     uint64 arrays [.., limb, 256]."""
 
-    def __init__(self, field, p, ck_in, ck_mlwe, ck_out, cdt_tables, crs=b""):
+    def __init__(self, field, p, ck_in, ck_mlwe, ck_out, cdt_tables, crs=b"", key_from_crs=False):
+        """key_from_crs: ignore ck_* and evaluate NewCommitKey(params, crs) on the device (rs_jindo_create_crs)."""
         self.field = field
         self.crs = bytes(crs)           # CommitKey.WriteRawTo (entities.go:75-77): bound into the Evaluate transcript
         self.p = dict(p)
@@ -69,10 +70,28 @@ class Prover:
         P.cdt_tail_lo = int(p["cdt_tail_lo"])
         P.cdt_sigma = float(p["cdt_sigma"])
         h = c_vp()
-        ck_in = np.ascontiguousarray(ck_in, dtype=np.uint64); ck_mlwe = np.ascontiguousarray(ck_mlwe, dtype=np.uint64)
-        ck_out = np.ascontiguousarray(ck_out, dtype=np.uint64)
-        check(lib().rs_jindo_create(field.h, ctypes.byref(P), _vp(ck_in), _vp(ck_mlwe), _vp(ck_out), _vp(cdt), ctypes.byref(h)))
+        if key_from_crs:
+            import hashlib
+            dg = hashlib.sha384(self.crs).digest()                     # uniform.go:38-46: key = h[:32], iv = h[32:48]
+            check(lib().rs_jindo_create_crs(field.h, ctypes.byref(P), ctypes.c_char_p(dg[:32]), ctypes.c_char_p(dg[32:48]),
+                                            _vp(cdt), ctypes.byref(h)))
+        else:
+            ck_in = np.ascontiguousarray(ck_in, dtype=np.uint64); ck_mlwe = np.ascontiguousarray(ck_mlwe, dtype=np.uint64)
+            ck_out = np.ascontiguousarray(ck_out, dtype=np.uint64)
+            check(lib().rs_jindo_create(field.h, ctypes.byref(P), _vp(ck_in), _vp(ck_mlwe), _vp(ck_out), _vp(cdt), ctypes.byref(h)))
         self.h = h
+
+    def CommitKey(self):
+        """(In, MLWE, Out) as uint64 arrays [i][j][limb][256] (jindo.CommitKey, entities.go:15-19), read back from HBM."""
+        p = self.p
+        shapes = [(p["in_msis"], p["rows"], self.n_q, self.d), (p["in_msis"], p["mlwe"], self.n_q, self.d),
+                  (p["out_msis"], (p["cols"] + 1) * p["in_msis"], self.n_qout, self.d)]
+        out = []
+        for which, shp in enumerate(shapes):
+            a = np.zeros(shp, dtype=np.uint64)
+            check(lib().rs_jindo_commit_key_download(self.h, which, _vp(a)))
+            out.append(a)
+        return tuple(out)
 
     def __del__(self):
         try:
@@ -168,6 +187,37 @@ class Prover:
         ml = np.zeros((self.p["mlwe"] + self.p["in_msis"], self.n_q, self.d), dtype=np.uint64)
         check(lib().rs_jindo_respond(self.h, opening.h, _vp(chals), _vp(enc), _vp(ml)))
         return enc, ml
+
+    def PartialAt(self, opening, x_mont):
+        """prover.go:267-289 with leftVec(x) encoded on the device; x_mont: L64 Montgomery limbs of the evaluation point."""
+        xm = np.ascontiguousarray(x_mont, dtype=np.uint64)
+        out = np.zeros((self.p["cols"] + 1, self.n_q, self.d), dtype=np.uint64)
+        check(lib().rs_jindo_partial_at(self.h, opening.h, _vp(xm), _vp(out)))
+        return out
+
+    def RespondBytes(self, opening, chal_bytes):
+        """prover.go:296-316 with encodeChallengeTo on the device; chal_bytes: 16 * cols bytes of the SHAKE output."""
+        assert len(chal_bytes) == 16 * self.p["cols"]
+        enc = np.zeros((self.p["rows"], self.n_q, self.d), dtype=np.uint64)
+        ml = np.zeros((self.p["mlwe"] + self.p["in_msis"], self.n_q, self.d), dtype=np.uint64)
+        check(lib().rs_jindo_respond_bytes(self.h, opening.h, ctypes.c_char_p(bytes(chal_bytes)), _vp(enc), _vp(ml)))
+        return enc, ml
+
+    def LeftVec(self, x_mont):
+        xm = np.ascontiguousarray(x_mont, dtype=np.uint64)
+        out = np.zeros((self.p["rows"], self.n_q, self.d), dtype=np.uint64)
+        check(lib().rs_jindo_left_vec(self.h, _vp(xm), _vp(out)))
+        return out
+
+    def EncodeChallenges(self, chal_bytes, ring_out=False):
+        n = len(chal_bytes) // 16
+        out = np.zeros((n, self.n_qout if ring_out else self.n_q, self.d), dtype=np.uint64)
+        check(lib().rs_jindo_encode_challenges(self.h, ctypes.c_char_p(bytes(chal_bytes)), n, 1 if ring_out else 0, _vp(out)))
+        return out
+
+    def OpeningMulAddBytes(self, acc, opening, chal16):
+        """prover.go:230-265: acc += opening (.) encodeChallenge(16 bytes), both rings, encoded on the device."""
+        check(lib().rs_opening_mul_add_bytes(self.h, acc.h, opening.h, ctypes.c_char_p(bytes(chal16))))
 
     def NewOpening(self):
         oh = c_vp()

@@ -1,37 +1,58 @@
-"""Buckler Prove on the GPU at the reference's own example size (BASELINE configs[0] / SURVEY 8d cfg1:
+"""[tests/perf: measurement harness that checks against / times the oracle, hence under tests/ -- the product never imports oracle/]
+Buckler Prove on the GPU at the reference's own example size (BASELINE configs[0] / SURVEY 8d cfg1:
 examples/mult MultCircuit, N = 2^13, 128-bit field): wall time with its split, checked bit for bit against the
 Python restatement of buckler.Prover.Prove on the same witness / CRS / randomness tape and accepted by the
 restated Verifier.  The oracle's own time is printed for context only (pure Python, not a performance baseline).
 
-  python tools/bench_buckler.py [logN] [circuit: mult|pk] [field]  ->  one JSON line"""
+  python tests/perf/bench_buckler.py [logN] [circuit: mult|pk|ct] [field]  ->  one JSON line"""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_product
 import oracle
 from oracle import buckler_ref as B, jindo_ref as J, pyref
 from jindo_util import cdt_array, params_dict, polys_array, tape_arrays
-from test_oracle_buckler import mult_witness, pk_witness
+from test_oracle_buckler import circuit_and_witness
 
-logn = int(sys.argv[1]) if len(sys.argv) > 1 else 13
-circuit = sys.argv[2] if len(sys.argv) > 2 else "mult"
-name = sys.argv[3] if len(sys.argv) > 3 else ("zp128" if circuit == "mult" else "zp220")
+import pickle
+pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+# --trace=FILE: the oracle's proof and randomness trace are cached there (the pure-Python oracle takes minutes at the bfv
+# sizes; it can run once on a CPU-only machine and the GPU box then only loads it).  --oracle-only: stop after writing it.
+trace_path = next((a[8:] for a in sys.argv[1:] if a.startswith("--trace=")), None)
+oracle_only = "--oracle-only" in sys.argv
+logn = int(pos[0]) if len(pos) > 0 else 13
+circuit = pos[1] if len(pos) > 1 else "mult"
+name = pos[2] if len(pos) > 2 else {"mult": "zp128", "pk": "zp220", "ct": "zp240"}[circuit]
 N = 1 << logn
-rs = load_product(); L = rs.load()
-assert L.rs_init(0) == 0, L.rs_last_error()
 q = pyref.modulus(name)
-fo = oracle.Field(q); fg = rs.Field(q)
-define, n_pw, n_w = (B.public_key_circuit if circuit == "pk" else B.mult_circuit)(N)
+fo = oracle.Field(q)
+(define, n_pw, n_w), (pw, w) = circuit_and_witness(circuit, q, N, 11)
 tape = J.Tape(b"buckler-bench-" + circuit.encode())
 t0 = time.perf_counter()
 C = B.compile_circuit(q, N, define, n_pw, n_w, b"Buckler!", tape)
 t_compile = time.perf_counter() - t0
-pw, w = (pk_witness if circuit == "pk" else mult_witness)(q, N, 11)
-op = B.Prover(C, tape)
-t0 = time.perf_counter()
-pf_o = op.prove(pw, w)
-t_oracle = time.perf_counter() - t0
+KEEP = ("blind", "mask", "mask_sum", "commit_traces", "pw_full", "w_full")
+if trace_path and os.path.exists(trace_path):
+    with open(trace_path, "rb") as fh:
+        saved = pickle.load(fh)
+    assert saved["key"] == (logn, circuit, name), "trace file belongs to another workload"
+    pf_o, trace, t_oracle = saved["proof"], saved["trace"], saved["t_oracle"]
+else:
+    op = B.Prover(C, tape)
+    t0 = time.perf_counter()
+    pf_o = op.prove(pw, w)
+    t_oracle = time.perf_counter() - t0
+    trace = {k: op.trace[k] for k in KEEP}
+    if trace_path:
+        os.makedirs(os.path.dirname(os.path.abspath(trace_path)), exist_ok=True)
+        with open(trace_path, "wb") as fh:
+            pickle.dump({"key": (logn, circuit, name), "proof": pf_o, "trace": trace, "t_oracle": t_oracle}, fh, protocol=4)
+if oracle_only:
+    print(json.dumps({"oracle_python_prove_s": t_oracle, "trace": trace_path})); sys.exit(0)
+rs = load_product(); L = rs.load()
+assert L.rs_init(0) == 0, L.rs_last_error()
+fg = rs.Field(q)
 ctx = C.ctx
 terms, coeffs = ctx.terms(ctx.arith_constraints)
 desc = {"rank": N, "emb_rank": C.emb_rank, "w_cnt": ctx.w_cnt, "pw_cnt": ctx.pw_cnt, "arith_max_rank": ctx.arith_max_rank,
@@ -40,10 +61,10 @@ desc = {"rank": N, "emb_rank": C.emb_rank, "w_cnt": ctx.w_cnt, "pw_cnt": ctx.pw_
 prv = C.poly_prover
 gp = rs.jindo.Prover(fg, params_dict(C.jp, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
                      polys_array(prv.ck.Out), cdt_array(prv.ecd), crs=b"Buckler!")
-rand = {"blind": op.trace["blind"], "mask": op.trace["mask"], "mask_sum": op.trace["mask_sum"],
-        "tapes": [tape_arrays(fo, C.jp, t) for t in op.trace["commit_traces"]]}
+rand = {"blind": trace["blind"], "mask": trace["mask"], "mask_sum": trace["mask_sum"],
+        "tapes": [tape_arrays(fo, C.jp, t) for t in trace["commit_traces"]]}
 gprv = rs.buckler.Prover(fg, q, desc, C.jp, gp)
-pwm = np.stack([fo.to_mont(v) for v in op.trace["pw_full"]]); wm = np.stack([fo.to_mont(v) for v in op.trace["w_full"]])
+pwm = np.stack([fo.to_mont(v) for v in trace["pw_full"]]); wm = np.stack([fo.to_mont(v) for v in trace["w_full"]])
 gprv.prove(pwm, wm, rand)                                  # warm-up (twiddle tables, descriptor caches)
 times, split = [], None
 for _ in range(3):

