@@ -77,8 +77,16 @@ class Prover:
         return sum(int(v) << (64 * i) for i, v in enumerate(a)) * rinv % self.q
 
     def _set_elem(self, batch, poly, off, value):
-        one = Batch(self.f, 1, 1).upload(self.mont(value).reshape(1, 1, self.L))
-        check(lib().rs_batch_copy(batch.h, poly, off, one.h, 0, 0, 1))
+        if getattr(self, "_one", None) is None:
+            self._one = Batch(self.f, 1, 1)
+        self._one.upload(self.mont(value).reshape(1, 1, self.L))
+        check(lib().rs_batch_copy(batch.h, poly, off, self._one.h, 0, 0, 1))
+
+    def mont_many(self, values):
+        """canonical ints -> [n, L] Montgomery limbs (one big-int product each; limbs split by numpy)"""
+        R, q, nb = self.R, self.q, 8 * self.L
+        buf = b"".join(((v % q) * R % q).to_bytes(nb, "little") for v in values)
+        return np.frombuffer(buf, dtype="<u8").reshape(len(values), self.L).copy()
 
     # ---- Jindo commit of coefficients [0, length) of batch[poly] ---------------------------------
     def _commit(self, batch, poly, length, tape):
@@ -127,7 +135,7 @@ class Prover:
         for i in range(wc):                              # first-round witnesses (no second-round witnesses here)
             coms[i], opens[i] = self._commit(ecd, i, N + 1, next(tapes))
             views[i] = (ecd, i, N + 1)
-            tr.bind("projConst", JH.commitment_write_raw(self.jp, coms[i].tolist()))
+            tr.bind("projConst", JH.commitment_write_raw(self.jp, coms[i]))
         tr.compute_challenge("projConst")
         mark("commit")
         idx = wc
@@ -136,11 +144,11 @@ class Prover:
         if c["lin"]:
             mask = rand["mask"][0]
             host = np.zeros((1, E, self.L), dtype=np.uint64)
-            host[0, :2 * N] = np.stack([self.mont(v) for v in mask])
+            host[0, :2 * N] = self.mont_many(mask)
             work.upload(host, 0)
             lin_mask_sum = rand["mask_sum"][0]
             coms[idx], opens[idx] = self._commit(work, 0, 2 * N, next(tapes)); views[idx] = (work, 0, 2 * N)
-            tr.bind("arithBatchConst", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
+            tr.bind("arithBatchConst", JH.commitment_write_raw(self.jp, coms[idx]))
             tr.bind("arithBatchConst", lin_mask_sum.to_bytes(8 * self.L, "big"))
             idx += 1
         mark("commit")
@@ -152,7 +160,7 @@ class Prover:
                 T[k].constraint, T[k].coeff, T[k].pw, T[k].n_w = ci, co, pw, len(ws)
                 for j, x in enumerate(ws):
                     T[k].w[j] = x
-            coeffs = np.stack([self.mont(v) for v in c["arith_coeffs"]])
+            coeffs = self.mont_many(c["arith_coeffs"])
             check(L.rs_eval_circuit(work.h, 1, pw_ntt.h, w_ntt.h, T, len(c["arith_terms"]), _p(coeffs), len(coeffs), _p(self.mont(arith_bc))))
             check(L.rs_ntt_inverse(self.emb.h, work.h, 1, work.h, 1, 1))
             quo_b = Batch(f, 2, E)
@@ -160,7 +168,7 @@ class Prover:
             keep.append(quo_b)
             mark("arith_check")
             coms[idx], opens[idx] = self._commit(quo_b, 0, c["arith_max_rank"] - N, next(tapes)); views[idx] = (quo_b, 0, c["arith_max_rank"] - N)
-            tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
+            tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx]))
             idx += 1
         mark("commit")
         lin_bc = int.from_bytes(tr.compute_challenge("linCheckBatchConst"), "big") % q
@@ -169,7 +177,8 @@ class Prover:
             vec = [1]
             for _ in range(1, N):
                 vec.append(vec[-1] * lin_c % q)
-            lv = Batch(f, 2, N).upload(np.stack([np.stack([self.mont(v) for v in vec])] * 2))
+            lvm = self.mont_many(vec)
+            lv = Batch(f, 2, N).upload(np.stack([lvm, lvm]))
             le = Batch(f, 2, E)
             check(L.rs_ntt_inverse_embed(self.enc.h, le.h, 0, lv.h, 0, 1, 1))
             check(L.rs_ntt_forward(self.emb.h, le.h, 0, le.h, 0, 1))                     # linCheckEcd (NTT form)
@@ -200,7 +209,7 @@ class Prover:
             mark("lin_check")
             for (b, p, ln) in ((qr, 0, N), (rem, 0, N - 1), (rem, 1, Rk)):
                 coms[idx], opens[idx] = self._commit(b, p, ln, next(tapes)); views[idx] = (b, p, ln)
-                tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx].tolist()))
+                tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx]))
                 idx += 1
         tr.compute_challenge("sumCheckBatchConst")
         x = int.from_bytes(tr.compute_challenge("evalPoint"), "big") % q
@@ -214,7 +223,7 @@ class Prover:
         """jindo.Prover.Evaluate (jindo/prover.go:205-324); views: (batch, poly, length) of each committed vector."""
         jp, gp, q = self.jp, self.gp, self.q
         batch = len(coms)
-        prefix = gp.crs + b"".join(JH.commitment_write_raw(jp, cm.tolist()) for cm in coms) + x.to_bytes(8 * self.L, "big")
+        prefix = gp.crs + b"".join(JH.commitment_write_raw(jp, cm) for cm in coms) + x.to_bytes(8 * self.L, "big")
         if batch > 1:
             bb = hashlib.shake_128(prefix).digest(16 * batch)
             prefix += bb

@@ -1144,9 +1144,10 @@ static int opening_alloc(rs_jindo *j, rs_opening **out) {
     const rs_jindo_params &p = j->p;
     const size_t ne = (size_t)(p.cols + 1) * p.rows * pq(j), nm = (size_t)(p.cols + 1) * (p.mlwe + p.in_msis) * pq(j),
                  ni = (size_t)(p.cols + 1) * p.in_msis * pqo(j);
-    cudaError_t e = cudaMalloc((void **)&o->d_encode, ne * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_mlwe, nm * 8);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&o->d_incommit, ni * 8);
+    // stream-ordered pool (rs_init keeps it cached): a Buckler proof allocates and frees 12-43 Openings
+    cudaError_t e = cudaMallocAsync((void **)&o->d_encode, ne * 8, current_stream());
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&o->d_mlwe, nm * 8, current_stream());
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&o->d_incommit, ni * 8, current_stream());
     if (e == cudaSuccess) e = cudaMemsetAsync(o->d_encode, 0, ne * 8, current_stream());
     if (e == cudaSuccess) e = cudaMemsetAsync(o->d_mlwe, 0, nm * 8, current_stream());
     if (e == cudaSuccess) e = cudaMemsetAsync(o->d_incommit, 0, ni * 8, current_stream());
@@ -1478,7 +1479,9 @@ int rs_jindo_twin_stream_draw(rs_jindo *j, size_t n, uint64_t *out) {
 
 void rs_opening_free(rs_opening *o) {
     if (!o) return;
-    cudaFree(o->d_encode); cudaFree(o->d_mlwe); cudaFree(o->d_incommit);
+    if (o->d_encode) cudaFreeAsync(o->d_encode, rs::current_stream());
+    if (o->d_mlwe) cudaFreeAsync(o->d_mlwe, rs::current_stream());
+    if (o->d_incommit) cudaFreeAsync(o->d_incommit, rs::current_stream());
     delete o;
 }
 

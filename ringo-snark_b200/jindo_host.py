@@ -5,6 +5,8 @@ see DESIGN.md "unpinned"), the encoder constants deltaInv (jindo/encoder.go:50-6
 tables (math/csprng/gaussian_twin_cdt.go:13-35).  In a Go deployment these values come from the
 reference's own host code; bench.py and examples use this module.  No device work happens here."""
 import math
+
+import numpy as np
 from fractions import Fraction
 
 MASK64 = (1 << 64) - 1
@@ -410,6 +412,15 @@ def commitment_write_raw(p, value):
     """Commitment.WriteRawTo (jindo/entities.go:85-100): polys allocated with ringQ's limb count."""
     nl = len(p.q_primes)
     out = []
+    if isinstance(value, np.ndarray):                      # [out_msis, n_qout, d] uint64: same bytes without int lists
+        import struct
+        head, lim = struct.pack("<Q", max(nl, value.shape[1])), struct.pack("<Q", p.d)
+        for v in value:
+            out.append(head)
+            for l in range(max(nl, value.shape[1])):
+                out.append(lim)
+                out.append(np.ascontiguousarray(v[l], dtype="<u8").tobytes() if l < value.shape[1] else bytes(8 * p.d))
+        return b"".join(out)
     for v in value:
         limbs = [list(c) for c in v] + [[0] * p.d for _ in range(nl - len(v))]
         out.append(poly_write_to(limbs))

@@ -32,22 +32,37 @@ tape = J.Tape(b"buckler-bench-" + circuit.encode())
 t0 = time.perf_counter()
 C = B.compile_circuit(q, N, define, n_pw, n_w, b"Buckler!", tape)
 t_compile = time.perf_counter() - t0
-KEEP = ("blind", "mask", "mask_sum", "commit_traces", "pw_full", "w_full")
+def slim(pf):
+    """the proof without the oracle's debugging attachments (whole Openings)"""
+    return {k: v for k, v in pf.items() if not k.startswith("_") or k == "_eval_point"}
+
+
+def pack(trace):
+    """the oracle's randomness trace as the plain arrays the GPU prover takes (numpy: ~5x smaller than the int lists)"""
+    rand = {"blind": trace["blind"], "mask": trace["mask"], "mask_sum": trace["mask_sum"],
+            "tapes": [tape_arrays(fo, C.jp, t) for t in trace["commit_traces"]]}
+    return rand, np.stack([fo.to_mont(v) for v in trace["pw_full"]]), np.stack([fo.to_mont(v) for v in trace["w_full"]])
+
+
 if trace_path and os.path.exists(trace_path):
     with open(trace_path, "rb") as fh:
         saved = pickle.load(fh)
     assert saved["key"] == (logn, circuit, name), "trace file belongs to another workload"
-    pf_o, trace, t_oracle = saved["proof"], saved["trace"], saved["t_oracle"]
+    pf_o, t_oracle = slim(saved["proof"]), saved["t_oracle"]
+    rand, pwm, wm = saved["packed"] if "packed" in saved else pack(saved["trace"])
+    if "packed" not in saved or len(pf_o) != len(saved["proof"]):      # rewrite an old-format file compactly
+        with open(trace_path, "wb") as fh:
+            pickle.dump({"key": saved["key"], "proof": pf_o, "packed": (rand, pwm, wm), "t_oracle": t_oracle}, fh, protocol=4)
 else:
     op = B.Prover(C, tape)
     t0 = time.perf_counter()
-    pf_o = op.prove(pw, w)
+    pf_o = slim(op.prove(pw, w))
     t_oracle = time.perf_counter() - t0
-    trace = {k: op.trace[k] for k in KEEP}
+    rand, pwm, wm = pack(op.trace)
     if trace_path:
         os.makedirs(os.path.dirname(os.path.abspath(trace_path)), exist_ok=True)
         with open(trace_path, "wb") as fh:
-            pickle.dump({"key": (logn, circuit, name), "proof": pf_o, "trace": trace, "t_oracle": t_oracle}, fh, protocol=4)
+            pickle.dump({"key": (logn, circuit, name), "proof": pf_o, "packed": (rand, pwm, wm), "t_oracle": t_oracle}, fh, protocol=4)
 if oracle_only:
     print(json.dumps({"oracle_python_prove_s": t_oracle, "trace": trace_path})); sys.exit(0)
 rs = load_product(); L = rs.load()
@@ -59,12 +74,9 @@ desc = {"rank": N, "emb_rank": C.emb_rank, "w_cnt": ctx.w_cnt, "pw_cnt": ctx.pw_
         "arith_terms": terms, "arith_coeffs": coeffs,
         "lin": [("ntt", ctx.lin_constraints[id(chk)]) for chk in ctx.lin_checkers]}
 prv = C.poly_prover
-gp = rs.jindo.Prover(fg, params_dict(C.jp, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
-                     polys_array(prv.ck.Out), cdt_array(prv.ecd), crs=b"Buckler!")
-rand = {"blind": trace["blind"], "mask": trace["mask"], "mask_sum": trace["mask_sum"],
-        "tapes": [tape_arrays(fo, C.jp, t) for t in trace["commit_traces"]]}
+# commit key: NewCommitKey(params, crs) evaluated on the device (rs_jindo_create_crs); the oracle's key only sizes nothing here
+gp = rs.jindo.Prover(fg, params_dict(C.jp, prv.ecd), None, None, None, cdt_array(prv.ecd), crs=b"Buckler!", key_from_crs=True)
 gprv = rs.buckler.Prover(fg, q, desc, C.jp, gp)
-pwm = np.stack([fo.to_mont(v) for v in trace["pw_full"]]); wm = np.stack([fo.to_mont(v) for v in trace["w_full"]])
 gprv.prove(pwm, wm, rand)                                  # warm-up (twiddle tables, descriptor caches)
 times, split = [], None
 for _ in range(3):

@@ -45,14 +45,17 @@ def ct_params(q, N):
 
 
 def ct_witness(q, N, seed):
-    """Synthetic BFV ciphertext over zp: c1 uniform, sk ternary, |m| <= t - 1, |e| <= N + t,
-    c0 = -c1*s + Delta*m + e (examples/bfv/main.go:22-28); all relations hold in the NTT domain."""
+    """Synthetic BFV ciphertext over zp: c1 uniform, sk ternary, m centred mod t (ringT.PolyToBigintCentered,
+    main.go:143: |m| <= t/2), |e| <= N + t, c0 = -c1*s + Delta*m + e (examples/bfv/main.go:22-28); all relations
+    hold in the NTT domain.  (Quirk kept by the restatement: for a power-of-two bound such as t - 1 = 2^16,
+    decomposeBase (buckler/utils.go:7-32) drops one digit and the digits sum to bound - 1, so a coefficient equal
+    to +-(t - 1) itself has no decomposition and the proof is rejected; centred plaintexts never reach it.)"""
     f = oracle.Field(q)
     rng = random.Random(seed)
     ntt = oracle.NTT(f, N.bit_length() - 1, True)
     delta, err_bound = ct_params(q, N)
     sk = [rng.randrange(3) - 1 for _ in range(N)]
-    m = [rng.randrange(-(BFV_T - 1), BFV_T) for _ in range(N)]
+    m = [rng.randrange(-(BFV_T // 2), BFV_T // 2 + 1) for _ in range(N)]
     e = [rng.randrange(-err_bound, err_bound + 1) for _ in range(N)]
     skn = ntt.fwd(f.to_mont(sk)); mn = ntt.fwd(f.to_mont(m)); en = ntt.fwd(f.to_mont(e))
     c1 = f.to_mont([rng.randrange(q) for _ in range(N)])
