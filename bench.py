@@ -349,6 +349,31 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
     return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank's host threads -- and therefore place its pinned staging buffers (first touch) -- on the CPUs of
+    the NUMA node the GPU's PCIe root port hangs off.  On an 8-GPU box the e2e leg moves 2 GiB per step per rank
+    through host memory; with unpinned ranks half of that crosses the socket interconnect.  Returns what was done."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if node < 0 or not use or use == allowed:
+            return {"node": node, "bound": False, "cpus": len(allowed)}
+        os.sched_setaffinity(0, use)
+        return {"node": node, "bound": True, "cpus": len(use)}
+    except Exception as e:                                 # no sysfs / not permitted: run unbound
+        return {"bound": False, "why": type(e).__name__}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -360,6 +385,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback; use --impl reference)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -490,7 +516,8 @@ def run_ours(args):
         "config": {"workload": f"bigpoly negacyclic forward NTT, {FIELD} (jindo/internal/zp), rank 2^{LOGN}, "
                                f"batch {BATCH} polys per GPU (BASELINE configs[1] headline)",
                    "l2": f"input+output {2 * nbytes >> 20} MiB per step, larger than the 126 MB L2 (no flush needed)",
-                   "sharding": "independent polynomials per rank, no data-path collective"},
+                   "sharding": "independent polynomials per rank, no data-path collective",
+                   "host_numa": numa},
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the ncu --set full capture
                      # profiles/ntt_r1h_ncu_batch512_summary.csv (same command, batch 512): 1.076 + 1.016 GB

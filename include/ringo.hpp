@@ -254,6 +254,11 @@ class Prover {
         : p_(p) {
         check(rs_jindo_create(f.handle(), &p, ck_in, ck_mlwe, ck_out, cdt_tables, &h_));
     }
+    // NewProver with NewCommitKey(params, crs) evaluated on the device (entities.go:21-61); key || iv = SHA-384(crs)
+    Prover(const bigpoly::Field &f, const rs_jindo_params &p, const uint8_t key[32], const uint8_t iv[16], const uint64_t *cdt_tables)
+        : p_(p) {
+        check(rs_jindo_create_crs(f.handle(), &p, key, iv, cdt_tables, &h_));
+    }
     ~Prover() { rs_jindo_destroy(h_); }
     Prover(const Prover &) = delete;
     Prover &operator=(const Prover &) = delete;
@@ -286,6 +291,34 @@ class Prover {
         enc.assign((size_t)p_.rows * p_.n_q * p_.d, 0);
         mlwe.assign((size_t)(p_.mlwe + p_.in_msis) * p_.n_q * p_.d, 0);
         check(rs_jindo_respond(h_, open.h, chals, enc.data(), mlwe.data()));
+    }
+    // the same two phases from the transcript's raw inputs: leftVec(x) (utils.go:63-73) and encodeChallengeTo
+    // (utils.go:21-46) are evaluated on the device
+    std::vector<uint64_t> PartialAt(const Opening &open, const uint64_t *x_mont) {         // prover.go:267-289
+        std::vector<uint64_t> out((size_t)(p_.cols + 1) * p_.n_q * p_.d);
+        check(rs_jindo_partial_at(h_, open.h, x_mont, out.data()));
+        return out;
+    }
+    void RespondBytes(const Opening &open, const uint8_t *chal_bytes, std::vector<uint64_t> &enc, std::vector<uint64_t> &mlwe) {   // :296-316
+        enc.assign((size_t)p_.rows * p_.n_q * p_.d, 0);
+        mlwe.assign((size_t)(p_.mlwe + p_.in_msis) * p_.n_q * p_.d, 0);
+        check(rs_jindo_respond_bytes(h_, open.h, chal_bytes, enc.data(), mlwe.data()));
+    }
+    void OpeningMulAddBytes(Opening &acc, const Opening &open, const uint8_t chal16[16]) {   // :230-265
+        check(rs_opening_mul_add_bytes(h_, acc.h, open.h, chal16));
+    }
+    std::vector<uint64_t> LeftVec(const uint64_t *x_mont) {
+        std::vector<uint64_t> out((size_t)p_.rows * p_.n_q * p_.d);
+        check(rs_jindo_left_vec(h_, x_mont, out.data()));
+        return out;
+    }
+    // ck.In (0) / ck.MLWE (1) / ck.Out (2) as the device holds them
+    std::vector<uint64_t> CommitKey(int which) const {
+        const size_t n = which == 0 ? (size_t)p_.in_msis * p_.rows * p_.n_q : which == 1 ? (size_t)p_.in_msis * p_.mlwe * p_.n_q
+                                    : (size_t)p_.out_msis * (p_.cols + 1) * p_.in_msis * p_.n_qout;
+        std::vector<uint64_t> out(n * p_.d);
+        check(rs_jindo_commit_key_download(h_, which, out.data()));
+        return out;
     }
     const rs_jindo_params &Parameters() const { return p_; }
     rs_jindo *handle() const { return h_; }

@@ -1087,6 +1087,9 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
     FieldParams<NL> F = make_params<NL>(j->f);
     int G = JD / j->p.slots;
     if (G > 16) G = 16;
+    // small commits (the 12-43 per Buckler proof: 650-2300 encodes): a CTA walks its G polynomials in sequence, so with
+    // fewer than ~4 CTAs per SM the launch lasts as long as one CTA.  Shrink G until the grid covers the chip.
+    while (G > 1 && (n + G - 1) / G < (size_t)148 * 4) G >>= 1;
     E.group = G;
     E.subgroup = 8 / j->rq.n > 0 ? 8 / j->rq.n : 1;
     if (E.subgroup > G) E.subgroup = G;
