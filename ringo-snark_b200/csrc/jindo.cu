@@ -272,6 +272,15 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
     u64 *s_poly = reinterpret_cast<u64 *>(smem_raw + (size_t)G * JD * 4 + (size_t)E.subgroup * JD * 8);
     const int c = threadIdx.x;
     const int d0 = blockIdx.x * G;
+    // TwinCDT slow-path samples (~1 %) are parked here and served by all eight warps after the fast pass, one sample
+    // per warp at a time, instead of stalling the warp that happened to draw them (the barrier after phase 2a waits for
+    // the unluckiest warp otherwise).  Overflowing samples fall back to the in-warp loop; results do not depend on which.
+    constexpr int QCAP = 48;
+    __shared__ double q_cfrac[QCAP];
+    __shared__ u64 q_u[QCAP];
+    __shared__ int q_v0[QCAP], q_v1[QCAP], q_idx[QCAP];
+    __shared__ int q_n;
+    if (c == 0) q_n = 0;
 
     // ---- phase 1: baseEncodeTo (encoder.go:120-146) for G polynomials at once
     for (int k = c; k < G * JD; k += 256) s_dig[k] = 0;
@@ -377,7 +386,15 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             // take it; the warp serves its slow lanes one at a time, all 32 lanes evaluating the terms
             // rho(x), x = tail_lo .. v0, in parallel (lane-strided partial sums, then a shuffle tree).
             int pick = v[0];
-            unsigned slow = __ballot_sync(0xffffffffu, v[0] != v[1]);
+            bool is_slow = v[0] != v[1];
+            if (is_slow) {
+                const int slot = atomicAdd(&q_n, 1);
+                if (slot < QCAP) {
+                    q_cfrac[slot] = cfrac; q_u[slot] = u; q_v0[slot] = v[0]; q_v1[slot] = v[1]; q_idx[slot] = (g - g0) * JD + c;
+                    is_slow = false;                       // decided after the barrier; s_g holds the v0 guess until then
+                }
+            }
+            unsigned slow = __ballot_sync(0xffffffffu, is_slow);
             const int lane = c & 31;
             const double norm = __dmul_rn(sqrt(6.283185307179586), E.sigma);
             const double den = __dmul_rn(__dmul_rn(2.0, E.sigma), E.sigma);
@@ -403,6 +420,30 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
         s_g[c] = gv;
     }
     __syncthreads();
+    {
+        // parked slow samples: the CDF at v0 for the exact centre, 32 lanes per sample (same sums as the in-warp loop)
+        const int nq = q_n < QCAP ? q_n : QCAP;
+        const int warp = c >> 5, lane = c & 31;
+        const double norm = __dmul_rn(sqrt(6.283185307179586), E.sigma);
+        const double den = __dmul_rn(__dmul_rn(2.0, E.sigma), E.sigma);
+        for (int e = warp; e < nq; e += 8) {
+            const double cf = q_cfrac[e];
+            const int top = q_v0[e];
+            double part = 0.0;
+            for (i64 x = E.tail_lo + lane; x <= (i64)top; x += 32) {
+                const double t = __dsub_rn((double)x, cf);
+                part = __dadd_rn(part, __ddiv_rn(exp(__ddiv_rn(__dmul_rn(-t, t), den)), norm));
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+            if (lane == 0) {
+                const double p = __dmul_rn(__ull2double_rn(q_u[e]), 5.421010862427522e-20);   // u / 2^64
+                if (!(p < part)) s_gbuf[q_idx[e]] += (i64)(q_v1[e] - top);                     // the guess was v0
+            }
+        }
+    }
+    __syncthreads();
+    if (c == 0) q_n = 0;                                   // (the barriers of phase 2b order this before the next pushes)
     for (int g = g0; g < g1; g++) {
         const EncDesc D = descs[d0 + g];
         const uint32_t *dig = s_dig + g * JD;
