@@ -35,6 +35,8 @@ struct RingDev {
     u64 qinvneg[JMAXL];     // -q^-1 mod 2^64
     u64 r2[JMAXL];          // 2^128 mod q  (MForm multiplier)
     u64 ninv[JMAXL];        // d^-1 mod q, plain (INTT scale that also leaves Montgomery form)
+    u64 r1[JMAXL];          // 2^64 mod q, and its Shoup constant floor(r1 2^64 / q): MForm of an unreduced 64-bit value
+    u64 r1s[JMAXL];         //   x * r1 - hi(x * r1s) * q  in [0, 2q)  for any x < 2^64
     const u64 *roots;       // [limb][d]  psi^brv(j) * 2^64 mod q   (forward twiddles)
     const u64 *roots_inv;   // [limb][d]  psi^-brv(j) * 2^64 mod q
     const u64 *roots_plain; // [limb][d]  psi^brv(j) mod q             (Shoup butterflies of the warp NTT)
@@ -119,6 +121,15 @@ __host__ __device__ __forceinline__ u64 mont64(u64 a, u64 b, u64 q, u64 qinvneg)
 }
 __host__ __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { u64 s = a + b; return s >= q ? s - q : s; }
 __host__ __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+
+// MForm of a signed 64-bit integer: (c mod q) * 2^64 mod q, canonical -- setCoeffSigned + MForm in one Shoup product
+// (valid for every |c| < 2^64: x r1 - hi(x r1s) q < 2q).  The same ring element as mont64(signed_res(c, q), r2).
+__device__ __forceinline__ u64 mform_signed(i64 c, u64 q, u64 r1, u64 r1s) {
+    const u64 m = (u64)(c < 0 ? -c : c);
+    u64 t = m * r1 - __umul64hi(m, r1s) * q;
+    t = t >= q ? t - q : t;
+    return (c < 0 && t) ? q - t : t;
+}
 
 // signed 64-bit value -> canonical residue (setCoeffSigned utils.go:49-60 followed by MForm's reduction)
 __device__ __forceinline__ u64 signed_res(i64 c, u64 q) {
@@ -251,6 +262,7 @@ struct EncConsts {
     int delta_w[RS_JINDO_MAX_EXP];        // (i + 1) * slots of the same entries
     int n_delta;
     u64 base_mont[JMAXL];
+    i64 g_lim;                  // |g| below this: digits + X^slots g - base g fits an int64 with room (2^62 / base)
 };
 
 // One CTA handles G = 256 / slots consecutive descriptors.  Phase 1 (all 256 threads, one field
@@ -406,12 +418,13 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                 double part = 0.0;
                 for (i64 x = E.tail_lo + lane; x <= (i64)top; x += 32) {
                     const double t = __dsub_rn((double)x, cf);
-                    part = __dadd_rn(part, __ddiv_rn(exp(__ddiv_rn(__dmul_rn(-t, t), den)), norm));
+                    part = __dadd_rn(part, exp(__ddiv_rn(__dmul_rn(-t, t), den)));
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
                 if (lane == src) {
-                    const double p = __dmul_rn(__ull2double_rn(u), 5.421010862427522e-20);   // u / 2^64
+                    // u / 2^64 < sum rho(x) / norm, with the division by norm moved to the other side
+                    const double p = __dmul_rn(__dmul_rn(__ull2double_rn(u), 5.421010862427522e-20), norm);
                     pick = (p < part) ? v[0] : v[1];
                 }
             }
@@ -432,12 +445,12 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             double part = 0.0;
             for (i64 x = E.tail_lo + lane; x <= (i64)top; x += 32) {
                 const double t = __dsub_rn((double)x, cf);
-                part = __dadd_rn(part, __ddiv_rn(exp(__ddiv_rn(__dmul_rn(-t, t), den)), norm));
+                part = __dadd_rn(part, exp(__ddiv_rn(__dmul_rn(-t, t), den)));
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) part = __dadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
             if (lane == 0) {
-                const double p = __dmul_rn(__ull2double_rn(q_u[e]), 5.421010862427522e-20);   // u / 2^64
+                const double p = __dmul_rn(__dmul_rn(__ull2double_rn(q_u[e]), 5.421010862427522e-20), norm);   // u / 2^64 * norm
                 if (!(p < part)) s_gbuf[q_idx[e]] += (i64)(q_v1[e] - top);                     // the guess was v0
             }
         }
@@ -445,24 +458,30 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
     __syncthreads();
     if (c == 0) q_n = 0;                                   // (the barriers of phase 2b order this before the next pushes)
     for (int g = g0; g < g1; g++) {
-        const EncDesc D = descs[d0 + g];
+        const int kind = descs[d0 + g].src_kind;
         const uint32_t *dig = s_dig + g * JD;
         const i64 *s_g = s_gbuf + (g - g0) * JD;
         const i64 gv = s_g[c];
-        // MForm(digits) + MForm(X^slots g - base g)  (encoder.go:166-199), per RNS limb
+        // MForm(digits) + MForm(X^slots g - base g)  (encoder.go:166-199), per RNS limb.  The three terms are small
+        // integers, so they are combined in int64 first and reduced once per limb (same ring element: every step of
+        // the reference is exact arithmetic mod q); values too large for that keep the term-by-term path.
+        const bool wrap = c < E.slots;
+        const i64 gnb = (kind == 2) ? 0 : (wrap ? s_g[c + JD - E.slots] : s_g[c - E.slots]);
+        const bool small = gv > -E.g_lim && gv < E.g_lim && gnb > -(1ll << 61) && gnb < (1ll << 61);
+        const i64 comb = (kind == 2) ? gv : (i64)dig[c] + (wrap ? -gnb : gnb) - (i64)E.base * gv;
         for (int l = 0; l < R.n; l++) {
             const u64 q = R.q[l], qi = R.qinvneg[l];
-            u64 val;
-            if (D.src_kind == 2) {
-                val = signed_res(gv, q);                   // noise polynomial: setCoeffSigned (prover.go:130-139)
+            u64 mf;
+            if (kind == 2 || small) {
+                mf = mform_signed(comb, q, R.r1[l], R.r1s[l]);      // noise polynomial: setCoeffSigned (prover.go:130-139)
             } else {
                 const u64 gm = signed_res(gv, q);
-                const u64 gs = (c >= E.slots) ? signed_res(s_g[c - E.slots], q)
-                                              : submod(0, signed_res(s_g[c + JD - E.slots], q), q);
+                const u64 gs = wrap ? submod(0, signed_res(gnb, q), q) : signed_res(gnb, q);
                 const u64 bg = mont64(E.base_mont[l], gm, q, qi);        // base * g mod q
-                val = submod(addmod((u64)dig[c], gs, q), bg, q);          // digits <= base < 2^31 < q
+                const u64 val = submod(addmod((u64)dig[c], gs, q), bg, q);   // digits <= base < 2^31 < q
+                mf = mont64(val, R.r2[l], q, qi);                        // MForm
             }
-            s_poly[(size_t)((g - g0) * R.n + l) * NTTW_STRIDE + nttw_idx(c)] = mont64(val, R.r2[l], q, qi);    // MForm
+            s_poly[(size_t)((g - g0) * R.n + l) * NTTW_STRIDE + nttw_idx(c)] = mf;
         }
     }
     __syncthreads();
@@ -944,6 +963,8 @@ static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi
         R.qinvneg[l] = 0 - inv;
         const u64 r1 = (u64)((((u128)1) << 64) % ql);
         R.r2[l] = h_mulmod(r1, r1, ql);
+        R.r1[l] = r1;
+        R.r1s[l] = (u64)((((u128)r1) << 64) / ql);
         R.ninv[l] = h_powmod(JD, ql - 2, ql);
         if (h_powmod(psi[l], JD, ql) != ql - 1) return set_error(RS_ERR_ARG, "jindo: psi is not a primitive 2d-th root of unity");
         const u64 psi_inv = h_powmod(psi[l], ql - 2, ql);
@@ -1125,6 +1146,7 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
     for (int i = 0; i < j->p.exp; i++)
         if (j->p.delta_inv[i] != 0.0) { E.delta_inv[E.n_delta] = j->p.delta_inv[i]; E.delta_w[E.n_delta] = (i + 1) * j->p.slots; E.n_delta++; }
     for (int l = 0; l < j->rq.n; l++) E.base_mont[l] = j->base_mont_q[l];
+    E.g_lim = (i64)((1ull << 62) / j->p.base);
     FieldParams<NL> F = make_params<NL>(j->f);
     int G = JD / j->p.slots;
     if (G > 16) G = 16;
