@@ -41,6 +41,10 @@ struct RingDev {
     const u64 *roots_inv;   // [limb][d]  psi^-brv(j) * 2^64 mod q
     const u64 *roots_plain; // [limb][d]  psi^brv(j) mod q             (Shoup butterflies of the warp NTT)
     const u64 *roots_shoup; // [limb][d]  floor(psi^brv(j) * 2^64 / q)
+    // float64 butterflies (primes below 2^44: the 35-38 bit rings of the 255-bit field): psi^brv(j), q and 1/q as doubles
+    const double *roots_f64;
+    double qf[JMAXL], qinvf[JMAXL];
+    int f64_ok;
 };
 
 struct CrtDev {             // RNSReconstructor constants of the *source* ring (rns.go:33-55)
@@ -236,6 +240,69 @@ __device__ __forceinline__ void ntt256_warp(u64 *a, const u64 *__restrict__ rp, 
         x = x >= q2 ? x - q2 : x;
         x = x >= q ? x - q : x;
         a[nttw_idx(lane * 8 + u)] = x;
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same warp-level transform on the FP64 pipe, for primes below 2^44.  Values are integer-valued doubles; a
+// product x*w mod q is h = rn(x*w), l = fma(x, w, -h) (the exact rounding error), b = rint(h / q), r = fma(-b, q, h) + l:
+// every step is exact (|x| < 9q < 2^48, h - b q and l are integers far below 2^53), r == x*w (mod q) with |r| < q.
+// No reduction is needed between the 8 stages (|value| < (stage + 1) q); the last loop maps to the canonical [0, q).
+// Exact modular arithmetic throughout, so the output equals ntt256_warp's / ntt256's bit for bit -- 9 DFMA-class
+// instructions per butterfly instead of ~27 integer ones, on a pipe the rest of the kernel leaves idle.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void f64_bfly(double &X, double &Y, double w, double q, double qinv) {
+    const double h = __dmul_rn(Y, w);
+    const double l = __fma_rn(Y, w, -h);
+    const double b = __dadd_rn(__dadd_rn(__dmul_rn(h, qinv), 6755399441055744.0), -6755399441055744.0);   // rint, |h/q| < 2^51
+    const double r = __dadd_rn(__fma_rn(-b, q, h), l);
+    Y = __dsub_rn(X, r);
+    X = __dadd_rn(X, r);
+}
+
+__device__ __forceinline__ void ntt256_warp_f64(double *a, const double *__restrict__ rf, double q, double qinv, int lane) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = a[nttw_idx(u * 32 + lane)];
+#pragma unroll
+    for (int u = 0; u < 4; u++) f64_bfly(v[u], v[u + 4], __ldg(rf + 1), q, qinv);
+#pragma unroll
+    for (int u = 0; u < 8; u++) if ((u & 2) == 0) f64_bfly(v[u], v[u + 2], __ldg(rf + 2 + (u >> 2)), q, qinv);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) f64_bfly(v[u], v[u + 1], __ldg(rf + 4 + (u >> 1)), q, qinv);
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[nttw_idx(u * 32 + lane)] = v[u];
+    __syncwarp();
+    const int hi = lane >> 2, lo = lane & 3;
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = a[nttw_idx(hi * 32 + u * 4 + lo)];
+    {
+        const double w = __ldg(rf + 8 + hi);
+#pragma unroll
+        for (int u = 0; u < 4; u++) f64_bfly(v[u], v[u + 4], w, q, qinv);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) if ((u & 2) == 0) f64_bfly(v[u], v[u + 2], __ldg(rf + 16 + hi * 2 + (u >> 2)), q, qinv);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) f64_bfly(v[u], v[u + 1], __ldg(rf + 32 + hi * 4 + (u >> 1)), q, qinv);
+#pragma unroll
+    for (int u = 0; u < 8; u++) a[nttw_idx(hi * 32 + u * 4 + lo)] = v[u];
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; u++) v[u] = a[nttw_idx(lane * 8 + u)];
+#pragma unroll
+    for (int u = 0; u < 8; u++) if ((u & 2) == 0) f64_bfly(v[u], v[u + 2], __ldg(rf + 64 + lane * 2 + (u >> 2)), q, qinv);
+#pragma unroll
+    for (int u = 0; u < 8; u += 2) f64_bfly(v[u], v[u + 1], __ldg(rf + 128 + lane * 4 + (u >> 1)), q, qinv);
+    u64 *au = reinterpret_cast<u64 *>(a);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        const double x = v[u];                             // integer, |x| < 9q
+        const double b = __dadd_rn(__dadd_rn(__dmul_rn(x, qinv), 6755399441055744.0), -6755399441055744.0);
+        double r = __fma_rn(-b, q, x);                     // [-q/2, q/2]
+        r = r < 0.0 ? __dadd_rn(r, q) : r;
+        au[nttw_idx(lane * 8 + u)] = (u64)__double2ll_rn(r);
     }
     __syncwarp();
 }
@@ -481,7 +548,7 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                 const u64 val = submod(addmod((u64)dig[c], gs, q), bg, q);   // digits <= base < 2^31 < q
                 mf = mont64(val, R.r2[l], q, qi);                        // MForm
             }
-            s_poly[(size_t)((g - g0) * R.n + l) * NTTW_STRIDE + nttw_idx(c)] = mf;
+            s_poly[(size_t)((g - g0) * R.n + l) * NTTW_STRIDE + nttw_idx(c)] = R.f64_ok ? (u64)__double_as_longlong(__ull2double_rn(mf)) : mf;
         }
     }
     __syncthreads();
@@ -491,7 +558,8 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
         for (int task = warp; task < (g1 - g0) * R.n; task += 8) {
             const int g = g0 + task / R.n, l = task % R.n;
             u64 *a = s_poly + (size_t)task * NTTW_STRIDE;
-            ntt256_warp(a, R.roots_plain + (size_t)l * JD, R.roots_shoup + (size_t)l * JD, R.q[l], lane);
+            if (R.f64_ok) ntt256_warp_f64(reinterpret_cast<double *>(a), R.roots_f64 + (size_t)l * JD, R.qf[l], R.qinvf[l], lane);
+            else ntt256_warp(a, R.roots_plain + (size_t)l * JD, R.roots_shoup + (size_t)l * JD, R.q[l], lane);
             u64 *dst = out + ((size_t)descs[d0 + g].out_poly * R.n + l) * JD;
 #pragma unroll
             for (int u = 0; u < 8; u++) dst[u * 32 + lane] = a[nttw_idx(u * 32 + lane)];
@@ -950,12 +1018,15 @@ static u64 mw_mod_word(const u64 *a, u64 q) {
     return (u64)r;
 }
 
-static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi, u64 *h_roots /* 4*n*JD */) {
+static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi, u64 *h_roots /* 5*n*JD */) {
     memset(&R, 0, sizeof(R));
     memset(&C, 0, sizeof(C));
     R.n = n;
+    R.f64_ok = getenv("RS_JINDO_NOF64") ? 0 : 1;
     for (int l = 0; l < n; l++) {
         const u64 ql = q[l];
+        if (ql >= (1ull << 44)) R.f64_ok = 0;
+        R.qf[l] = (double)ql; R.qinvf[l] = 1.0 / (double)ql;
         if (!(ql & 1) || ql >= (1ull << 62) || ql < (1ull << 33)) return set_error(RS_ERR_UNSUPPORTED, "jindo: RNS prime out of the supported range (2^33, 2^62)");
         R.q[l] = ql;
         u64 inv = 1;
@@ -975,6 +1046,7 @@ static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi
             h_roots[(size_t)(n + l) * JD + b] = h_mulmod(pwi, r1, ql);
             h_roots[(size_t)(2 * n + l) * JD + b] = pw;
             h_roots[(size_t)(3 * n + l) * JD + b] = (u64)((((u128)pw) << 64) / ql);
+            { const double pf = (double)pw; memcpy(&h_roots[(size_t)(4 * n + l) * JD + b], &pf, 8); }
             pw = h_mulmod(pw, psi[l], ql);
             pwi = h_mulmod(pwi, psi_inv, ql);
         }
@@ -1457,8 +1529,8 @@ static int jindo_create_impl(rs_field *f, const rs_jindo_params *p, const uint64
     j->cache = new std::vector<DescCache>();
     j->f = f;
     j->p = *p;
-    std::vector<u64> roots((size_t)4 * (p->n_q + p->n_qout) * JD);
-    u64 *rq_h = roots.data(), *rqo_h = roots.data() + (size_t)4 * p->n_q * JD;
+    std::vector<u64> roots((size_t)5 * (p->n_q + p->n_qout) * JD);
+    u64 *rq_h = roots.data(), *rqo_h = roots.data() + (size_t)5 * p->n_q * JD;
     int rc = ring_setup(j->rq, j->crt_q, p->n_q, (const u64 *)p->q, (const u64 *)p->psi_q, rq_h);
     if (rc == RS_OK) rc = ring_setup(j->rqo, j->crt_qo, p->n_qout, (const u64 *)p->qout, (const u64 *)p->psi_qout, rqo_h);
     if (rc != RS_OK) { delete j; return rc; }
@@ -1499,10 +1571,12 @@ static int jindo_create_impl(rs_field *f, const rs_jindo_params *p, const uint64
     j->rq.roots_inv = j->d_roots + (size_t)p->n_q * JD;
     j->rq.roots_plain = j->d_roots + (size_t)2 * p->n_q * JD;
     j->rq.roots_shoup = j->d_roots + (size_t)3 * p->n_q * JD;
-    j->rqo.roots = j->d_roots + (size_t)4 * p->n_q * JD;
+    j->rq.roots_f64 = reinterpret_cast<const double *>(j->d_roots + (size_t)4 * p->n_q * JD);
+    j->rqo.roots = j->d_roots + (size_t)5 * p->n_q * JD;
     j->rqo.roots_inv = j->rqo.roots + (size_t)p->n_qout * JD;
     j->rqo.roots_plain = j->rqo.roots + (size_t)2 * p->n_qout * JD;
     j->rqo.roots_shoup = j->rqo.roots + (size_t)3 * p->n_qout * JD;
+    j->rqo.roots_f64 = reinterpret_cast<const double *>(j->rqo.roots + (size_t)4 * p->n_qout * JD);
     cudaStreamCreateWithFlags(&j->copy_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&j->ev_alloc, cudaEventDisableTiming);
     for (int k = 0; k < RS_VCHUNKS; k++) cudaEventCreateWithFlags(&j->ev_piece[k], cudaEventDisableTiming);
