@@ -88,6 +88,7 @@ struct rs_jindo {
     u64 *d_ck_in, *d_ck_mlwe, *d_ck_out;
     u64 *d_cdt;
     uint8_t *d_cdt_guide;   // [128][257]: number of table entries below b << 56 (search window per top byte of u)
+    double *d_slow_lb;      // [16][cdt_len]: rigorous lower bounds of the slow path's CDF sum (see encode_kernel)
     u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
     rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
     cudaStream_t copy_stream;         // rs_jindo_commit_host: uploads of v pieces
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                                                      const uint32_t *__restrict__ vec, const uint32_t *__restrict__ aux,
                                                      const u64 *__restrict__ twin_u, const i64 *__restrict__ given,
                                                      const u64 *__restrict__ cdt, const uint8_t *__restrict__ guide,
+                                                     const double *__restrict__ slow_lb,
                                                      const __grid_constant__ RingDev R,
                                                      const __grid_constant__ EncConsts E,
                                                      const __grid_constant__ FieldParams<NL> F) {
@@ -466,6 +468,15 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             // rho(x), x = tail_lo .. v0, in parallel (lane-strided partial sums, then a shuffle tree).
             int pick = v[0];
             bool is_slow = v[0] != v[1];
+            if (is_slow && slow_lb && v[0] >= 0 && v[0] < E.cdt_len) {
+                // The slow path keeps v0 iff u / 2^64 < sum_{x = tail_lo .. v0} rho(x - cfrac) / norm.  slow_lb[k][v0] bounds
+                // that sum from below, term by term, for every cfrac in [k/16, (k+1)/16) (minus a 1e-9 margin): below it
+                // the outcome is v0 without evaluating the sum.  (x runs up to the table INDEX v0, as in the reference,
+                // so the sum is close to 1 and this settles ~99 % of the slow samples.)
+                int kc = (int)(cfrac * 16.0); kc = kc > 15 ? 15 : kc;
+                const double p = __dmul_rn(__ull2double_rn(u), 5.421010862427522e-20);
+                if (p < __ldg(slow_lb + kc * E.cdt_len + v[0])) is_slow = false;
+            }
             if (is_slow) {
                 const int slot = atomicAdd(&q_n, 1);
                 if (slot < QCAP) {
@@ -1237,7 +1248,7 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
         configured = true;
     }
     encode_kernel<NL><<<(unsigned)((n + G - 1) / G), 256, smem, current_stream()>>>(out, d_descs, (int)n, vec, aux, twin_u, given,
-                                                                                   j->d_cdt, j->d_cdt_guide, j->rq, E, F);
+                                                                                   j->d_cdt, j->d_cdt_guide, j->d_slow_lb, j->rq, E, F);
     count_launch();
     RS_CUDA_CHECK(cudaGetLastError());
     return RS_OK;
@@ -1566,6 +1577,25 @@ static int jindo_create_impl(rs_field *f, const rs_jindo_params *p, const uint64
         e = cudaMalloc((void **)&j->d_cdt_guide, guide.size());
         if (e == cudaSuccess) e = cudaMemcpy(j->d_cdt_guide, guide.data(), guide.size(), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && !getenv("RS_JINDO_NOSLOWLB")) {
+        // lower bounds for the TwinCDT slow path (gaussian_twin_cdt.go:95-110): for cfrac in [a, b) = [k/16, (k+1)/16),
+        // rho(x - cfrac) >= rho(x - b) for x <= 0 and >= rho(x - a) for x >= 1, so
+        //   sum_{x = tail_lo .. v0} rho(x - cfrac) >= sum_{x = tail_lo .. min(v0, 0)} rho(x - b) + sum_{x = 1 .. v0} rho(x - a)
+        const double sg = p->cdt_sigma, den = 2.0 * sg * sg, norm = sqrt(6.283185307179586) * sg;
+        std::vector<double> lb((size_t)16 * p->cdt_len);
+        for (int k = 0; k < 16; k++) {
+            const double a = k / 16.0, b = (k + 1) / 16.0;
+            double neg = 0.0;                                   // x <= 0 part, accumulated up to min(v0, 0); v0 >= 0 so it is complete
+            for (long long x = p->cdt_tail_lo; x <= 0; x++) neg += exp(-((double)x - b) * ((double)x - b) / den);
+            double pos = 0.0;
+            for (int v0 = 0; v0 < p->cdt_len; v0++) {
+                if (v0 >= 1) pos += exp(-((double)v0 - a) * ((double)v0 - a) / den);
+                lb[(size_t)k * p->cdt_len + v0] = (neg + pos) / norm - 1e-9;
+            }
+        }
+        e = cudaMalloc((void **)&j->d_slow_lb, lb.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(j->d_slow_lb, lb.data(), lb.size() * 8, cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) { rs_jindo_destroy(j); return set_error(RS_ERR_CUDA, "rs_jindo_create: %s", cudaGetErrorString(e)); }
     j->rq.roots = j->d_roots;
     j->rq.roots_inv = j->d_roots + (size_t)p->n_q * JD;
@@ -1591,7 +1621,7 @@ void rs_jindo_destroy(rs_jindo *j) {
         cudaStreamDestroy(j->copy_stream); cudaEventDestroy(j->ev_alloc);
         for (int k = 0; k < RS_VCHUNKS; k++) cudaEventDestroy(j->ev_piece[k]);
     }
-    cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt); cudaFree(j->d_cdt_guide);
+    cudaFree(j->d_roots); cudaFree(j->d_ck_in); cudaFree(j->d_ck_mlwe); cudaFree(j->d_ck_out); cudaFree(j->d_cdt); cudaFree(j->d_cdt_guide); cudaFree(j->d_slow_lb);
     if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
     cudaFree(j->d_ndescs); cudaFree(j->d_ldescs); cudaFree(j->d_zero_g);
     rs::uniform_stream_free(j->twin_stream);
