@@ -127,6 +127,11 @@ __host__ __device__ __forceinline__ u64 mont64(u64 a, u64 b, u64 q, u64 qinvneg)
 __host__ __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { u64 s = a + b; return s >= q ? s - q : s; }
 __host__ __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
 
+// exact uint32 -> double without a conversion instruction: (2^52 + x) - 2^52
+__device__ __forceinline__ double u32_to_f64(uint32_t x) {
+    return __dsub_rn(__hiloint2double(0x43300000, (int)x), 4503599627370496.0);
+}
+
 // MForm of a signed 64-bit integer: (c mod q) * 2^64 mod q, canonical -- setCoeffSigned + MForm in one Shoup product
 // (valid for every |c| < 2^64: x r1 - hi(x r1s) q < 2q).  The same ring element as mont64(signed_res(c, q), r2).
 __device__ __forceinline__ u64 mform_signed(i64 c, u64 q, u64 r1, u64 r1s) {
@@ -330,6 +335,8 @@ struct EncConsts {
     int delta_w[RS_JINDO_MAX_EXP];        // (i + 1) * slots of the same entries
     int n_delta;
     u64 base_mont[JMAXL];
+    uint32_t base2, base_magic32;   // base^2 when it fits 32 bits (else 0); floor(2^32 / base) + 1
+    u64 base2_magic;                // floor(2^64 / base^2) + 1
     i64 g_lim;                  // |g| below this: digits + X^slots g - base g fits an int64 with room (2^62 / base)
 };
 
@@ -379,7 +386,33 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                 mont_mul<NL, 0>(y, x, one, F);                 // Slice(): fromMont (element.go:1769-1773)
                 const uint32_t b = (uint32_t)E.base;
                 uint32_t *dst = s_dig + g * JD + i;
-                for (int j = 0; j < E.exp - 1; j++) {
+                int j = 0;
+                if (E.base2) {
+                    // two digits per long division: divide by base^2 (< 2^32), then split the remainder; limbs that have
+                    // become zero are skipped (the quotient loses ~one limb per pass)
+                    const uint32_t b2 = E.base2;
+                    int top = NL - 1;
+                    for (; j + 1 < E.exp - 1; j += 2) {
+                        while (top > 0 && y[top] == 0) top--;
+                        uint32_t r = 0;
+#pragma unroll
+                        for (int l = NL - 1; l >= 0; l--) {
+                            if (l > top) continue;
+                            const u64 cur = ((u64)r << 32) | y[l];
+                            u64 qd = hmulhi(cur, E.base2_magic);   // floor(cur / b2) or one more (cur < b2 * 2^32)
+                            i64 rem = (i64)(cur - qd * b2);
+                            if (rem < 0) { rem += b2; qd--; }
+                            y[l] = (uint32_t)qd;
+                            r = (uint32_t)rem;
+                        }
+                        uint32_t hi = __umulhi(r, E.base_magic32);  // floor(r / b) or one more (r < 2^32)
+                        int lo = (int)(r - hi * b);
+                        if (lo < 0) { lo += (int)b; hi--; }
+                        dst[j * E.slots] = (uint32_t)lo;
+                        dst[(j + 1) * E.slots] = hi;
+                    }
+                }
+                for (; j < E.exp - 1; j++) {
                     uint32_t r = 0;                            // divMod64 (utils.go:12-18) on 32-bit limbs
 #pragma unroll
                     for (int l = NL - 1; l >= 0; l--) {
@@ -414,13 +447,14 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
         if (D.noise_kind == 1) {
             gv = given[D.noise_off + c];
         } else {
+            const u64 u = __ldg(twin_u + D.noise_off + c);     // issued first: its HBM latency hides behind the centre sum
             // float64 centre (encoder.go:152-164), unfused multiply-add in the reference's order
             double fp = 0.0;
             for (int i = 0; i < E.n_delta; i++) {          // the non-zero deltaInv terms, ascending i
                 const double di = E.delta_inv[i];
                 const int w = E.delta_w[i];                // N - d
-                if (c >= JD - w) fp = __dadd_rn(fp, __dmul_rn(di, (double)dig[c - (JD - w)]));
-                else fp = __dsub_rn(fp, __dmul_rn(di, (double)dig[c + w]));
+                if (c >= JD - w) fp = __dadd_rn(fp, __dmul_rn(di, u32_to_f64(dig[c - (JD - w)])));
+                else fp = __dsub_rn(fp, __dmul_rn(di, u32_to_f64(dig[c + w])));
             }
             // TwinCDT (gaussian_twin_cdt.go:77-111)
             const double center = -fp;
@@ -429,13 +463,13 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             const double sc = __dmul_rn(128.0, cfrac);
             // 0 <= sc < 128 (cfrac in [0, 1)): floor / ceil fit an int, "% BLOCK" only matters for ceil == 128
             const int c0 = __double2int_rd(sc) & 127, c1 = __double2int_ru(sc) & 127;
-            const u64 u = __ldg(twin_u + D.noise_off + c);
             // slices.BinarySearch on both tables at once (branch-free lower bound: number of entries < u),
             // minus one on an exact hit (gaussian_twin_cdt.go:86-93)
             int v[2];
             {
                 const u64 *t0 = cdt + (size_t)c0 * E.cdt_len, *t1 = cdt + (size_t)c1 * E.cdt_len;
                 int l0 = 0, l1 = 0;
+                int e0 = E.cdt_len, e1 = E.cdt_len;            // an exact hit can only sit below these indices
                 if (guide) {
                     // the top byte of u narrows the lower bound to [guide[b], guide[b+1]]: 0-1 probes for the
                     // bulk of the distribution, log2(tail length) for the two tail buckets
@@ -443,6 +477,7 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                     const uint8_t *g0p = guide + c0 * 257 + b, *g1p = guide + c1 * 257 + b;
                     int h0 = g0p[1], h1 = g1p[1];
                     l0 = g0p[0]; l1 = g1p[0];
+                    e0 = h0; e1 = h1;                          // entries sharing u's top byte end here: beyond, table > u
                     while (l0 < h0 || l1 < h1) {
                         const int m0 = (l0 + h0) >> 1, m1 = (l1 + h1) >> 1;
                         const u64 a0 = (l0 < h0) ? __ldg(t0 + m0) : ~0ull;
@@ -459,8 +494,8 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
                         if (p1 <= E.cdt_len && a1 < u) l1 = p1;
                     }
                 }
-                if (l0 < E.cdt_len && __ldg(t0 + l0) == u) l0 -= 1;
-                if (l1 < E.cdt_len && __ldg(t1 + l1) == u) l1 -= 1;
+                if (l0 < e0 && __ldg(t0 + l0) == u) l0 -= 1;
+                if (l1 < e1 && __ldg(t1 + l1) == u) l1 -= 1;
                 v[0] = l0; v[1] = l1;
             }
             // Slow path (gaussian_twin_cdt.go:95-110): CDF at v0 for the exact centre.  ~1% of the samples
@@ -1230,6 +1265,11 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
         if (j->p.delta_inv[i] != 0.0) { E.delta_inv[E.n_delta] = j->p.delta_inv[i]; E.delta_w[E.n_delta] = (i + 1) * j->p.slots; E.n_delta++; }
     for (int l = 0; l < j->rq.n; l++) E.base_mont[l] = j->base_mont_q[l];
     E.g_lim = (i64)((1ull << 62) / j->p.base);
+    if (j->p.base < 65536 && !getenv("RS_JINDO_NOPAIR")) {
+        E.base2 = (uint32_t)(j->p.base * j->p.base);
+        E.base2_magic = (u64)((((u128)1) << 64) / E.base2) + 1;
+        E.base_magic32 = (uint32_t)((1ull << 32) / j->p.base) + 1;
+    }
     FieldParams<NL> F = make_params<NL>(j->f);
     int G = JD / j->p.slots;
     if (G > 16) G = 16;
