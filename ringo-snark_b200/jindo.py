@@ -195,11 +195,18 @@ class Prover:
         check(lib().rs_jindo_partial_at(self.h, opening.h, _vp(xm), _vp(out)))
         return out
 
-    def RespondBytes(self, opening, chal_bytes):
-        """prover.go:296-316 with encodeChallengeTo on the device; chal_bytes: 16 * cols bytes of the SHAKE output."""
+    def RespondBytes(self, opening, chal_bytes, out=None):
+        """prover.go:296-316 with encodeChallengeTo on the device; chal_bytes: 16 * cols bytes of the SHAKE output.
+        out: optional (enc, mlwe) uint64 arrays to fill (e.g. views of pinned memory: the 8 MB of responses at 2^22
+        then come back at PCIe speed instead of through the driver's pageable staging)."""
         assert len(chal_bytes) == 16 * self.p["cols"]
-        enc = np.zeros((self.p["rows"], self.n_q, self.d), dtype=np.uint64)
-        ml = np.zeros((self.p["mlwe"] + self.p["in_msis"], self.n_q, self.d), dtype=np.uint64)
+        if out is not None:
+            enc, ml = out
+            assert enc.shape == (self.p["rows"], self.n_q, self.d) and ml.shape == (self.p["mlwe"] + self.p["in_msis"], self.n_q, self.d)
+            assert enc.dtype == np.uint64 and ml.dtype == np.uint64 and enc.flags.c_contiguous and ml.flags.c_contiguous
+        else:
+            enc = np.zeros((self.p["rows"], self.n_q, self.d), dtype=np.uint64)
+            ml = np.zeros((self.p["mlwe"] + self.p["in_msis"], self.n_q, self.d), dtype=np.uint64)
         check(lib().rs_jindo_respond_bytes(self.h, opening.h, ctypes.c_char_p(bytes(chal_bytes)), _vp(enc), _vp(ml)))
         return enc, ml
 
