@@ -1843,6 +1843,21 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
         RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
     }
+    if (v_host) {
+        // upload v in RS_VCHUNKS pieces on the copy stream; piece k is encoded as soon as it has landed.  Enqueued right behind
+        // the (small) tape uploads and BEFORE the main stream starts waiting for the sampler's AES kernels: the 134 MB of v
+        // must not queue up behind that wait.
+        if (cudaMallocAsync((void **)&d_v, len * NL * 4, current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit_host: cudaMallocAsync failed"); goto fail; }
+        cudaEventRecord(j->ev_alloc, current_stream());
+        cudaStreamWaitEvent(j->copy_stream, j->ev_alloc, 0);
+        size_t lo = 0;
+        for (int k = 0; k < RS_VCHUNKS; k++) {
+            const size_t hi = dc->chunk_vhi[k];
+            if (hi > lo) cudaMemcpyAsync(d_v + lo * NL, (const uint32_t *)v_host + lo * NL, (hi - lo) * NL * 4, cudaMemcpyHostToDevice, j->copy_stream);
+            if (hi > lo) lo = hi;
+            cudaEventRecord(j->ev_piece[k], j->copy_stream);
+        }
+    }
     if (gen_twin) {       // draws come from the prover's own AES-CTR stream, generated in HBM
         const u64 *smp = nullptr;
         RS_TRY(uniform_stream_draw(j->twin_stream, twin * d, &smp));
@@ -1858,17 +1873,6 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         }
         // ---- encodes + noise polynomials
         if (v_host) {
-            // upload v in RS_VCHUNKS pieces on the copy stream; piece k is encoded as soon as it has landed
-            if (cudaMallocAsync((void **)&d_v, len * NL * 4, current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit_host: cudaMallocAsync failed"); goto fail; }
-            cudaEventRecord(j->ev_alloc, current_stream());
-            cudaStreamWaitEvent(j->copy_stream, j->ev_alloc, 0);
-            size_t lo = 0;
-            for (int k = 0; k < RS_VCHUNKS; k++) {
-                const size_t hi = dc->chunk_vhi[k];
-                if (hi > lo) cudaMemcpyAsync(d_v + lo * NL, (const uint32_t *)v_host + lo * NL, (hi - lo) * NL * 4, cudaMemcpyHostToDevice, j->copy_stream);
-                if (hi > lo) lo = hi;
-                cudaEventRecord(j->ev_piece[k], j->copy_stream);
-            }
             for (int k = 0; k < RS_VCHUNKS; k++) {
                 cudaStreamWaitEvent(current_stream(), j->ev_piece[k], 0);
                 const size_t c0 = dc->chunk_desc[k], c1 = dc->chunk_desc[k + 1];
