@@ -133,11 +133,17 @@ struct UniformStream {
     AesKey key;
     u64 iv_hi, iv_lo;
     u64 pos;             // samples handed out so far
-    u64 *d_state;        // 1024 words: current contents of the sampler's 8 KiB buffer
-    cudaStream_t side;   // generation runs here, so it overlaps the caller's uploads on the main stream
-    cudaEvent_t ready, consumed;
-    u64 *d_out;          // output buffer, reused by every draw (grown on demand)
-    size_t out_words;
+    u64 *d_state[2];     // 1024 words each: contents of the sampler's 8 KiB buffer; d_state[cur] is the live one
+    int cur;
+    cudaStream_t side;   // generation runs here, so it overlaps the caller's uploads / kernels on the main stream
+    // two output buffers: the one handed out last may still be read by the consumer's kernels while the other one is
+    // being filled for the next draw (uniform_stream_prefetch)
+    u64 *d_buf[2];
+    size_t buf_words[2];
+    cudaEvent_t ready[2], consumed[2];
+    int last;            // buffer handed out by the last draw
+    bool pre_valid;      // d_buf[last ^ 1] / d_state[cur ^ 1] hold the draws [pre_pos, pre_pos + pre_n) and the state after them
+    u64 pre_pos; size_t pre_n;
     u64 *d_tot;          // segment totals of the scan
     size_t tot_words;
 };
@@ -149,13 +155,16 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
     aes256_expand(key, s->key);
     s->iv_hi = s->iv_lo = 0;
     for (int i = 0; i < 8; i++) { s->iv_hi = (s->iv_hi << 8) | iv[i]; s->iv_lo = (s->iv_lo << 8) | iv[8 + i]; }
-    s->pos = 0;
-    RS_CUDA_CHECK(cudaMalloc((void **)&s->d_state, CH_WORDS * 8));
-    RS_CUDA_CHECK(cudaMemset(s->d_state, 0, CH_WORDS * 8));
+    s->pos = 0; s->cur = 0; s->last = 0; s->pre_valid = false; s->pre_pos = 0; s->pre_n = 0;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
-    RS_CUDA_CHECK(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
-    RS_CUDA_CHECK(cudaEventCreateWithFlags(&s->consumed, cudaEventDisableTiming));
-    s->d_out = s->d_tot = nullptr; s->out_words = s->tot_words = 0;
+    for (int k = 0; k < 2; k++) {
+        RS_CUDA_CHECK(cudaMalloc((void **)&s->d_state[k], CH_WORDS * 8));
+        RS_CUDA_CHECK(cudaMemset(s->d_state[k], 0, CH_WORDS * 8));
+        RS_CUDA_CHECK(cudaEventCreateWithFlags(&s->ready[k], cudaEventDisableTiming));
+        RS_CUDA_CHECK(cudaEventCreateWithFlags(&s->consumed[k], cudaEventDisableTiming));
+        s->d_buf[k] = nullptr; s->buf_words[k] = 0;
+    }
+    s->d_tot = nullptr; s->tot_words = 0;
     if (!g_sbox_uploaded) { RS_CUDA_CHECK(cudaMemcpyToSymbol(c_sbox, h_sbox, 256)); g_sbox_uploaded = true; }
     *out = s;
     return RS_OK;
@@ -163,33 +172,31 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
 void uniform_stream_free(UniformStream *s) {
     if (!s) return;
     cudaStreamSynchronize(s->side);
-    cudaFree(s->d_state); cudaFree(s->d_out); cudaFree(s->d_tot);
-    cudaEventDestroy(s->ready); cudaEventDestroy(s->consumed); cudaStreamDestroy(s->side);
+    for (int k = 0; k < 2; k++) { cudaFree(s->d_state[k]); cudaFree(s->d_buf[k]); cudaEventDestroy(s->ready[k]); cudaEventDestroy(s->consumed[k]); }
+    cudaFree(s->d_tot);
+    cudaStreamDestroy(s->side);
     delete s;
 }
 
-// Produces the next n Sample() values of the stream in HBM and advances it.  The kernels run on the
-// stream's own side stream; the current stream is made to wait for them before this returns.
-// *d_samples points at sample 0 inside the stream's reusable output buffer: call uniform_stream_release on
-// the consuming stream once the kernels reading it have been launched (the next draw waits for that).
+// Enqueues, on the side stream, the generation of the n Sample() values that follow position `pos` into d_buf[b], from the
+// sampler state d_state[cur] into d_state[cur ^ 1] (the live state is not touched); records ready[b].
 // Layout of the buffer: [ current 8 KiB buffer of the sampler | every chunk refilled by this call ].
-int uniform_stream_draw(UniformStream *s, size_t n, const u64 **d_samples) {
-    *d_samples = nullptr;
-    if (n == 0) return RS_OK;
+static int generate(UniformStream *s, u64 pos, size_t n, int b) {
     cudaStream_t st = s->side;
-    const u64 off = s->pos % CH_WORDS;
-    const u64 c_start = s->pos / CH_WORDS + (off ? 1 : 0);                  // first chunk not yet refilled
-    const u64 c_end = (s->pos + n + CH_WORDS - 1) / CH_WORDS;
+    const u64 off = pos % CH_WORDS;
+    const u64 c_start = pos / CH_WORDS + (off ? 1 : 0);                     // first chunk not yet refilled
+    const u64 c_end = (pos + n + CH_WORDS - 1) / CH_WORDS;
     const size_t n_chunks = c_end > c_start ? (size_t)(c_end - c_start) : 0;
     const int seg = n_chunks > 4096 ? 256 : (n_chunks > 64 ? 16 : 1);
     const size_t n_seg = n_chunks ? (n_chunks + seg - 1) / seg : 0;
-    RS_CUDA_CHECK(cudaStreamWaitEvent(st, s->consumed, 0));                 // previous consumer is done with d_out
-    if ((n_chunks + 1) * CH_WORDS > s->out_words || n_seg * CH_WORDS > s->tot_words) {
+    RS_CUDA_CHECK(cudaStreamWaitEvent(st, s->consumed[b], 0));              // the last consumer of this buffer is done
+    if ((n_chunks + 1) * CH_WORDS > s->buf_words[b] || n_seg * CH_WORDS > s->tot_words) {
         RS_CUDA_CHECK(cudaStreamSynchronize(st));
-        if ((n_chunks + 1) * CH_WORDS > s->out_words) {
-            cudaFree(s->d_out); s->d_out = nullptr; s->out_words = 0;
-            RS_CUDA_CHECK(cudaMalloc((void **)&s->d_out, (n_chunks + 1) * CH_WORDS * 8));
-            s->out_words = (n_chunks + 1) * CH_WORDS;
+        if ((n_chunks + 1) * CH_WORDS > s->buf_words[b]) {
+            RS_CUDA_CHECK(cudaEventSynchronize(s->consumed[b]));
+            cudaFree(s->d_buf[b]); s->d_buf[b] = nullptr; s->buf_words[b] = 0;
+            RS_CUDA_CHECK(cudaMalloc((void **)&s->d_buf[b], (n_chunks + 1) * CH_WORDS * 8));
+            s->buf_words[b] = (n_chunks + 1) * CH_WORDS;
         }
         if (n_seg * CH_WORDS > s->tot_words) {
             cudaFree(s->d_tot); s->d_tot = nullptr; s->tot_words = 0;
@@ -197,25 +204,59 @@ int uniform_stream_draw(UniformStream *s, size_t n, const u64 **d_samples) {
             s->tot_words = n_seg * CH_WORDS;
         }
     }
-    u64 *buf = s->d_out;
-    RS_CUDA_CHECK(cudaMemcpyAsync(buf, s->d_state, CH_WORDS * 8, cudaMemcpyDeviceToDevice, st));
+    u64 *buf = s->d_buf[b];
+    const u64 *state_in = s->d_state[s->cur];
+    u64 *state_out = s->d_state[s->cur ^ 1];
+    RS_CUDA_CHECK(cudaMemcpyAsync(buf, state_in, CH_WORDS * 8, cudaMemcpyDeviceToDevice, st));
+    RS_CUDA_CHECK(cudaMemcpyAsync(state_out, state_in, CH_WORDS * 8, cudaMemcpyDeviceToDevice, st));
     if (n_chunks) {
         u64 *ks = buf + CH_WORDS;
         aes_keystream_kernel<<<148 * 4, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
         dim3 grid(CH_WORDS / 256, (unsigned)n_seg);
         xor_scan_totals<<<grid, 256, 0, st>>>(s->d_tot, ks, n_chunks, seg);
-        xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, s->d_state, n_seg);
+        xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, state_out, n_seg);
         xor_scan_apply<<<grid, 256, 0, st>>>(ks, s->d_tot, n_chunks, seg);
         count_launch(4);
         RS_CUDA_CHECK(cudaGetLastError());
     }
-    RS_CUDA_CHECK(cudaEventRecord(s->ready, st));
-    RS_CUDA_CHECK(cudaStreamWaitEvent(current_stream(), s->ready, 0));
-    s->pos += n;
-    *d_samples = buf + (off ? off : CH_WORDS);
+    RS_CUDA_CHECK(cudaEventRecord(s->ready[b], st));
     return RS_OK;
 }
 
-void uniform_stream_release(UniformStream *s) { cudaEventRecord(s->consumed, current_stream()); }
+// Produces the next n Sample() values of the stream in HBM and advances it.  The kernels run on the stream's own side
+// stream; the current stream is made to wait for them before this returns.  *d_samples points at sample 0 inside one of
+// the stream's two reusable output buffers: call uniform_stream_release on the consuming stream once the kernels reading
+// it have been launched.  If the draws were generated ahead by uniform_stream_prefetch they are handed out as they are.
+int uniform_stream_draw(UniformStream *s, size_t n, const u64 **d_samples) {
+    *d_samples = nullptr;
+    if (n == 0) return RS_OK;
+    const int b = s->last ^ 1;
+    if (!(s->pre_valid && s->pre_pos == s->pos && s->pre_n == n)) {
+        const int rc = generate(s, s->pos, n, b);                           // (a stale prefetch in d_buf[b] is simply overwritten)
+        if (rc) { s->pre_valid = false; return rc; }
+    }
+    s->pre_valid = false;
+    s->cur ^= 1;                                                            // the state written by generate() becomes live
+    RS_CUDA_CHECK(cudaStreamWaitEvent(current_stream(), s->ready[b], 0));
+    const u64 off = s->pos % CH_WORDS;
+    s->pos += n;
+    s->last = b;
+    *d_samples = s->d_buf[b] + (off ? off : CH_WORDS);
+    return RS_OK;
+}
+
+void uniform_stream_release(UniformStream *s) { cudaEventRecord(s->consumed[s->last], current_stream()); }
+
+// Generates the NEXT n draws ahead of time into the idle buffer (the stream's position does not move: this is a cache of
+// what the next uniform_stream_draw(n) would compute).  Called after the consumer of the current draws has been launched, so
+// the AES kernels of Commit k+1 run next to the mat-vec / cut-off kernels of Commit k instead of in front of its encodes.
+int uniform_stream_prefetch(UniformStream *s, size_t n) {
+    if (n == 0 || (s->pre_valid && s->pre_pos == s->pos && s->pre_n == n)) return RS_OK;
+    s->pre_valid = false;
+    const int rc = generate(s, s->pos, n, s->last ^ 1);
+    if (rc) return rc;
+    s->pre_valid = true; s->pre_pos = s->pos; s->pre_n = n;
+    return RS_OK;
+}
 
 }  // namespace rs

@@ -73,6 +73,7 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
 void uniform_stream_free(UniformStream *s);
 int uniform_stream_draw(UniformStream *s, size_t n, const u64 **d_samples);
 void uniform_stream_release(UniformStream *s);
+int uniform_stream_prefetch(UniformStream *s, size_t n);
 }  // namespace rs
 
 struct rs_jindo {
@@ -1906,7 +1907,13 @@ fail:
     cudaFreeAsync(d_aux, current_stream());
     if (d_v) cudaFreeAsync(d_v, current_stream());
     if (!dev) { if (!gen_twin) cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); cudaFreeAsync(d_mlwe_s, current_stream()); }
-    if (twin_drawn) uniform_stream_release(j->twin_stream);      // every reader of the draws has been launched
+    if (twin_drawn) {
+        uniform_stream_release(j->twin_stream);                  // every reader of the draws has been launched
+        // optional (RS_JINDO_PREFETCH=1): generate the next Commit's draws now, behind this Commit's remaining kernels.
+        // Measured neutral at 2^22 (5.9 ms e2e either way: the AES kernels take the same SM time wherever they run), so
+        // it is off by default; it pays when the host leaves gaps between Commits.
+        if (rc == RS_OK && getenv("RS_JINDO_PREFETCH")) uniform_stream_prefetch(j->twin_stream, twin * d);
+    }
     cudaFreeAsync(d_com, current_stream());
     if (rc) { if (!reuse) rs_opening_free(o); return rc; }
     *open = o;

@@ -191,12 +191,17 @@ def test_device_uniform_stream_matches_csprng(rs):
             assert np.array_equal(got, ref.sample_many(n)), (seed, n)
 
 
-def test_commit_with_device_twin_stream(rs):
-    """Two consecutive Commits drawing the TwinCDT uniforms on the device (tape.twin_u = NULL) give the
-    same Opening / Commitment as the oracle, whose encoder owns one stateful sampler (encoder.go:56-62)."""
+def test_commit_with_device_twin_stream(rs, monkeypatch):
+    """Consecutive Commits drawing the TwinCDT uniforms on the device (tape.twin_u = NULL) give the same Opening /
+    Commitment as the oracle, whose encoder owns one stateful sampler (encoder.go:56-62).  With RS_JINDO_PREFETCH every Commit pre-generates
+    the next Commit's draws (uniform_stream_prefetch): the lengths below make the prefetch miss (different number of
+    rows), hit twice, and miss again, and a host-side draw in between moves the stream under a pending prefetch."""
     q, fo, fg, p, tape, prv, gp = _prover_pair(rs, "zp128", 700, 2, b"dev-twin")
     gp.SetTwinSeed(prv.ecd.twin.base.seed)
-    for length in (700, 333):
+    monkeypatch.setenv("RS_JINDO_PREFETCH", "1")       # (read by the library at every Commit)
+    for step, length in enumerate((700, 333, 333, 333, 40, 700)):
+        if step == 4:                                  # the oracle's sampler hands 777 draws to somebody else
+            assert np.array_equal(gp.TwinStreamDraw(777), prv.ecd.twin.base.sample_many(777))
         v = [J.field_set_random(tape, q) for _ in range(length)]
         com_o, open_o = prv.commit(v)
         B = rs.Batch(fg, 1, 1024)
