@@ -454,8 +454,9 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
             for (int i = 0; i < E.n_delta; i++) {          // the non-zero deltaInv terms, ascending i
                 const double di = E.delta_inv[i];
                 const int w = E.delta_w[i];                // N - d
-                if (c >= JD - w) fp = __dadd_rn(fp, __dmul_rn(di, u32_to_f64(dig[c - (JD - w)])));
-                else fp = __dsub_rn(fp, __dmul_rn(di, u32_to_f64(dig[c + w])));
+                // fp[c] += di * dig[c + w - N] for c >= N - w, fp[c] -= di * dig[c + w] below: one load, sign by select
+                const double t = __dmul_rn(di, u32_to_f64(dig[(c + w) & (JD - 1)]));
+                fp = __dadd_rn(fp, (c >= JD - w) ? t : -t);
             }
             // TwinCDT (gaussian_twin_cdt.go:77-111)
             const double center = -fp;
@@ -582,7 +583,9 @@ __global__ void __launch_bounds__(256) encode_kernel(u64 *__restrict__ out, cons
         const bool wrap = c < E.slots;
         const i64 gnb = (kind == 2) ? 0 : (wrap ? s_g[c + JD - E.slots] : s_g[c - E.slots]);
         const bool small = gv > -E.g_lim && gv < E.g_lim && gnb > -(1ll << 61) && gnb < (1ll << 61);
-        const i64 comb = (kind == 2) ? gv : (i64)dig[c] + (wrap ? -gnb : gnb) - (i64)E.base * gv;
+        // (base * g: one signed 32x32 -> 64 multiply when g fits 32 bits, as every Gaussian sample does)
+        const i64 bg = (gv == (i64)(int)gv) ? (i64)(int)gv * (i64)(int)E.base : (i64)E.base * gv;
+        const i64 comb = (kind == 2) ? gv : (i64)dig[c] + (wrap ? -gnb : gnb) - bg;
         for (int l = 0; l < R.n; l++) {
             const u64 q = R.q[l], qi = R.qinvneg[l];
             u64 mf;

@@ -106,6 +106,31 @@ __global__ void __launch_bounds__(256) mixed_kernel(unsigned long long *out, uin
     if (s == 0x1234567ull) out[0] = s;
 }
 
+// IMAD.WIDE.U32 with a 64-bit addend and operands that change every iteration (mode 1's multiplicands are loop
+// invariant: ptxas hoists the product and the loop degenerates into IADD3 pairs).  The multiply-add is written the
+// way the kernels write it (mad.lo.cc + madc.hi on a packed 64-bit register -> ONE IMAD.WIDE.U32 R, a, b, R), and one
+// factor is the low word of a neighbouring accumulator, so nothing can be hoisted; 8 independent chains per thread.
+__global__ void __launch_bounds__(256) imad_wide_acc_kernel(unsigned long long *out, uint32_t b, int iters) {
+    unsigned long long acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = (unsigned long long)(threadIdx.x * 2654435761u + k) * 0x9e3779b97f4a7c15ull;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t f = (uint32_t)acc[(k + 3) & 7];
+                asm volatile("{\n\t.reg .u32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmad.lo.cc.u32 lo, %1, %2, lo;\n\tmadc.hi.u32 hi, %1, %2, hi;\n\tmov.b64 %0, {lo, hi};\n\t}"
+                             : "+l"(acc[k]) : "r"(f), "r"(b));
+            }
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += acc[k];
+    if (s == 0x1234567ull) out[0] = s;
+}
+
 }  // namespace rs
 
 extern "C" {
@@ -113,6 +138,8 @@ extern "C" {
 // Returns sustained G op/s.  wide: 0 = 32-bit IMAD, 1 = IMAD.WIDE.U32 (32x32+64, no carry),
 // 2 = carry-chained IMAD.WIDE.U32.X (the Montgomery inner loop), 3 = IADD3.X carry chains,
 // 4 = 1:1 mix of independent IMAD.WIDE.U32 and LOP3 (counts both): can the two pipes run concurrently?
+// 5 = IMAD.WIDE.U32 with a 64-bit addend and changing operands (what the kernels' multiply-adds are; mode 1's loop-invariant
+//     product is hoisted by ptxas, so mode 1 really measures IADD3 pairs)
 int rs_bench_imad_peak(int wide, double *gops) {
     using namespace rs;
     RS_REQUIRE(gops, RS_ERR_ARG, "rs_bench_imad_peak: null argument");
@@ -129,6 +156,7 @@ int rs_bench_imad_peak(int wide, double *gops) {
         else if (wide == 2) imad_chain_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
         else if (wide == 3) iadd_chain_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, iters);
         else if (wide == 4) mixed_kernel<<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
+        else if (wide == 5) imad_wide_acc_kernel<<<blocks, threads, 0, current_stream()>>>(d, 0x9e3779b1u, iters);
         else imad_kernel<false><<<blocks, threads, 0, current_stream()>>>(d, 12345u, 6789u, iters);
         count_launch();
         RS_CUDA_CHECK(cudaEventRecord(e1, current_stream()));
