@@ -142,6 +142,8 @@ struct UniformStream {
     size_t buf_words[2];
     cudaEvent_t ready[2], consumed[2];
     int last;            // buffer handed out by the last draw
+    bool two;            // alternate between the two buffers (only once uniform_stream_prefetch has been used: the second
+                         // buffer costs as much HBM again -- 537 MB at 2^22 -- and its first use a cudaMalloc)
     bool pre_valid;      // d_buf[last ^ 1] / d_state[cur ^ 1] hold the draws [pre_pos, pre_pos + pre_n) and the state after them
     u64 pre_pos; size_t pre_n;
     u64 *d_tot;          // segment totals of the scan
@@ -155,7 +157,7 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
     aes256_expand(key, s->key);
     s->iv_hi = s->iv_lo = 0;
     for (int i = 0; i < 8; i++) { s->iv_hi = (s->iv_hi << 8) | iv[i]; s->iv_lo = (s->iv_lo << 8) | iv[8 + i]; }
-    s->pos = 0; s->cur = 0; s->last = 0; s->pre_valid = false; s->pre_pos = 0; s->pre_n = 0;
+    s->pos = 0; s->cur = 0; s->last = 0; s->two = false; s->pre_valid = false; s->pre_pos = 0; s->pre_n = 0;
     RS_CUDA_CHECK(cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking));
     for (int k = 0; k < 2; k++) {
         RS_CUDA_CHECK(cudaMalloc((void **)&s->d_state[k], CH_WORDS * 8));
@@ -230,7 +232,7 @@ static int generate(UniformStream *s, u64 pos, size_t n, int b) {
 int uniform_stream_draw(UniformStream *s, size_t n, const u64 **d_samples) {
     *d_samples = nullptr;
     if (n == 0) return RS_OK;
-    const int b = s->last ^ 1;
+    const int b = s->two ? s->last ^ 1 : 0;
     if (!(s->pre_valid && s->pre_pos == s->pos && s->pre_n == n)) {
         const int rc = generate(s, s->pos, n, b);                           // (a stale prefetch in d_buf[b] is simply overwritten)
         if (rc) { s->pre_valid = false; return rc; }
@@ -253,6 +255,7 @@ void uniform_stream_release(UniformStream *s) { cudaEventRecord(s->consumed[s->l
 int uniform_stream_prefetch(UniformStream *s, size_t n) {
     if (n == 0 || (s->pre_valid && s->pre_pos == s->pos && s->pre_n == n)) return RS_OK;
     s->pre_valid = false;
+    s->two = true;
     const int rc = generate(s, s->pos, n, s->last ^ 1);
     if (rc) return rc;
     s->pre_valid = true; s->pre_pos = s->pos; s->pre_n = n;
