@@ -14,6 +14,9 @@ namespace rs {
 #ifndef RS_NTT_MINB_SMALL
 #define RS_NTT_MINB_SMALL 4   // resident CTAs per SM the register allocation is capped for (<= 8 limbs)
 #endif
+#ifndef RS_NTT_MINB_FWD
+#define RS_NTT_MINB_FWD 5     // forward passes of the 8-limb fields: 102 registers (8 bytes of spill), 20 warps per SM: +3-5 %;
+#endif                        // the inverse passes (multiply after the add/sub pair, N^-1 folded in) lose 3 % there and keep 4
 #ifndef RS_NTT_MINB_L4
 #define RS_NTT_MINB_L4 8        // 4-limb (128-bit) fields: 64 registers suffice, 8 CTAs of 128 threads per SM (+4 %)
 #endif
@@ -38,7 +41,8 @@ template <int NL, int QS, bool INV, bool LAST, bool LAZY>
 int launch_pass(const rs_ntt *t, uint32_t *out, const uint32_t *in, const NttConsts<NL> &C, const PassGeom &G,
                 unsigned long long tiles) {
     using T = NttTuning<NL>;
-    auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, T::MINB, INV, (INV && LAST), LAZY, LAST>;
+    constexpr int MINB = (!INV && NL > 4 && NL <= 8) ? RS_NTT_MINB_FWD : T::MINB;
+    auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, MINB, INV, (INV && LAST), LAZY, LAST>;
     constexpr int smem = SmemLayout<NL, T::TS>::BYTES;
     static bool configured = false;
     if (!configured) {
