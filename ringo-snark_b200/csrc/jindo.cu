@@ -769,13 +769,17 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
 //   Per k-step a thread reads 5 key values (broadcast across the 8 column-pair groups) and 2 x values
 //   from shared memory and issues 10 lazy multiply-accumulates.
 // ---------------------------------------------------------------------------------------------
-constexpr int MP_MS = 64, MP_OT = 5, MP_CTC = 16, MP_KS = 4, MP_STAGES = 3, MP_THREADS = 512;
+#ifndef RS_MP_CTC
+#define RS_MP_CTC 8           // columns per CTA tile: 8 -> 256 threads, two CTAs per SM (their barrier / load phases interleave);
+#endif                        // 16 -> 512 threads, one CTA per SM (the first version)
+constexpr int MP_MS = 64, MP_OT = 5, MP_CTC = RS_MP_CTC, MP_KS = 4, MP_STAGES = 3, MP_THREADS = MP_MS * MP_CTC / 2;
+constexpr int MP_MINB = (MP_CTC <= 8) ? 2 : 1;
 constexpr int MP_ROWS = MP_OT + MP_CTC;                         // polynomial rows per k-step
 constexpr int MP_STAGE_WORDS = MP_KS * MP_ROWS * MP_MS;         // u64 words per stage
 constexpr int MP_SMEM_BYTES = MP_STAGES * MP_STAGE_WORDS * 8;
 
 template <bool FOLD>
-__global__ void __launch_bounds__(MP_THREADS, 1) matvec_pipe_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
+__global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
                                                                    const u64 *__restrict__ x, const u64 *__restrict__ addend,
                                                                    const __grid_constant__ MatvecGeom G) {
     extern __shared__ __align__(16) u64 ring[];

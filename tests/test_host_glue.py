@@ -1,0 +1,37 @@
+"""CPU tests of the product-side host helpers (no GPU, no compute through the library)."""
+import numpy as np
+
+from oracle import jindo_ref as J, pyref
+
+
+def test_product_modulus_table_matches_reference_constants(product):
+    """bigpoly.MODULI (product side) lists the same b^k + 1 moduli as the oracle's table, which is pinned to the
+    reference's zp packages by tests/golden/field_constants.json."""
+    assert product.MODULI == pyref.MODULI
+    for name in pyref.MODULI:
+        assert product.modulus(name) == pyref.modulus(name)
+
+
+def test_commitment_serialisation_numpy_equals_lists(product):
+    """jindo_host.commitment_write_raw: the numpy fast path writes the bytes of the list path, which restates
+    Commitment.WriteRawTo (jindo/entities.go:85-100) -- including the zero limbs of polynomials allocated in ringQ."""
+    JH = product.jindo_host
+    rng = np.random.default_rng(3)
+    for name, n, batch in (("zp255", 1024, 1), ("zp220", 2049, 9), ("zp128", 700, 2)):
+        p = JH.new_parameters(pyref.modulus(name), n, batch)
+        com = np.stack([np.stack([rng.integers(0, pr, size=p.d, dtype=np.uint64) for pr in p.qout_primes]) for _ in range(p.out_msis)])
+        a = JH.commitment_write_raw(p, com)
+        assert a == JH.commitment_write_raw(p, com.tolist())
+        po = J.new_parameters(pyref.modulus(name), n, batch)
+        assert a == J.commitment_write_raw(po, com.tolist())
+
+
+def test_host_parameters_match_oracle(product):
+    """jindo_host.new_parameters (product side) against the oracle's restatement of jindo.NewParameters for the shapes of
+    SURVEY section 8 (they are independent implementations of params.go:126-321)."""
+    JH = product.jindo_host
+    for name, n, batch in (("zp255", 1 << 22, 1), ("zp128", 16385, 12), ("zp240", 32769, 43), ("zp220", 2049, 9), ("zp255", 1024, 8)):
+        a = JH.new_parameters(pyref.modulus(name), n, batch); b = J.new_parameters(pyref.modulus(name), n, batch)
+        for f in ("rows", "cols", "slots", "in_msis", "mlwe", "out_msis", "log_in_cut", "log_out_cut", "d", "exp", "base"):
+            assert getattr(a, f) == getattr(b, f), (name, f)
+        assert list(a.q_primes) == list(b.q_primes) and list(a.qout_primes) == list(b.qout_primes)
