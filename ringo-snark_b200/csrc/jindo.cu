@@ -770,8 +770,8 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
 //   from shared memory and issues 10 lazy multiply-accumulates.
 // ---------------------------------------------------------------------------------------------
 #ifndef RS_MP_CTC
-#define RS_MP_CTC 8           // columns per CTA tile: 8 -> 256 threads, two CTAs per SM (their barrier / load phases interleave);
-#endif                        // 16 -> 512 threads, one CTA per SM (the first version)
+#define RS_MP_CTC 16          // columns per CTA tile: 16 -> 512 threads, one CTA per SM.  8 -> 256 threads, two CTAs per SM was
+#endif                        // measured slower (Commit 2^22: 3.29 -> 3.53 ms: twice the key traffic, half the reuse per key load)
 constexpr int MP_MS = 64, MP_OT = 5, MP_CTC = RS_MP_CTC, MP_KS = 4, MP_STAGES = 3, MP_THREADS = MP_MS * MP_CTC / 2;
 constexpr int MP_MINB = (MP_CTC <= 8) ? 2 : 1;
 constexpr int MP_ROWS = MP_OT + MP_CTC;                         // polynomial rows per k-step
