@@ -844,11 +844,12 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
     }
     int since = 0;
     for (int it = 0; it < n_it; it++) {
-        // keep STAGES-1 groups in flight: issue the load for iteration it + STAGES - 1 into the buffer freed last round
+        // groups it and it+1 are in flight: wait for group it, then ONE barrier per iteration -- it publishes stage it and, since
+        // every thread has finished iteration it-1 by now, frees that buffer for the load of iteration it + STAGES - 1
+        asm volatile("cp.async.wait_group %0;" ::"n"(MP_STAGES - 2));
+        __syncthreads();
         if (it + MP_STAGES - 1 < n_it) load_stage(it + MP_STAGES - 1, (it + MP_STAGES - 1) % MP_STAGES);
         else asm volatile("cp.async.commit_group;");
-        asm volatile("cp.async.wait_group %0;" ::"n"(MP_STAGES - 1));
-        __syncthreads();
         const u64 *buf = ring + (size_t)(it % MP_STAGES) * MP_STAGE_WORDS;
 #pragma unroll
         for (int kl = 0; kl < MP_KS; kl++) {
@@ -876,7 +877,6 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
                     }
             }
         }
-        __syncthreads();                                            // the buffer may be overwritten next round
     }
     const int slot = slot0 + tx;
 #pragma unroll
