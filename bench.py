@@ -533,7 +533,7 @@ def run_ours(args):
                    "host_numa": numa},
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the ncu --set full capture
-                     # profiles/ntt_r1h_ncu_batch512_summary.csv (same command, batch 512): 1.076 + 1.016 GB
+                     # profiles/ntt_r1f_ncu_batch512_summary.csv (tools/profile_ntt.py zp255 16 512, final kernel shape): 1.076 + 1.016 GB
                      "traffic": 2.092e9 if (BATCH, LOGN, FIELD) == (512, 16, "zp255") else None,
                      "algorithmic_bytes": alg_bytes, "kernel": f"ntt_pass_kernel pass {dom} of {len(passes)}",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
