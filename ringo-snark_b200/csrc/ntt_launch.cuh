@@ -27,14 +27,27 @@ namespace rs {
 #define RS_NTT_LOG_THREADS 7
 #endif
 
+#ifndef RS_NTT_LOG_THREADS_L14
+#define RS_NTT_LOG_THREADS_L14 7   // 14-limb (440-bit) fields: 128 threads x 3 CTAs per SM instead of 256 x 1: +35 %
+#endif
+#ifndef RS_NTT_MINB_L14
+#define RS_NTT_MINB_L14 3
+#endif
+#ifndef RS_NTT_LOG_THREADS_L28
+#define RS_NTT_LOG_THREADS_L28 7   // 28-limb (880-bit) fields: 128 threads x 3 CTAs per SM: +8 % forward, +21 % inverse
+#endif
+#ifndef RS_NTT_MINB_L28
+#define RS_NTT_MINB_L28 3
+#endif
+
 template <int NL> struct NttTuning {
     // 2^R elements per thread between shared-memory exchanges
     static constexpr int R = (NL <= 4) ? RS_NTT_R_L4 : ((NL <= 8) ? RS_NTT_R_SMALL : (NL <= 14 ? 2 : 1));
-    static constexpr int LOG_THREADS = (NL <= 8) ? RS_NTT_LOG_THREADS : 8;
+    static constexpr int LOG_THREADS = (NL <= 8) ? RS_NTT_LOG_THREADS : (NL <= 14 ? RS_NTT_LOG_THREADS_L14 : RS_NTT_LOG_THREADS_L28);
     static constexpr int THREADS = 1 << LOG_THREADS;
     static constexpr int TS = THREADS << R;
     static constexpr int LOG_TS = LOG_THREADS + R;
-    static constexpr int MINB = (NL <= 4) ? RS_NTT_MINB_L4 : ((NL <= 8) ? RS_NTT_MINB_SMALL : 1);
+    static constexpr int MINB = (NL <= 4) ? RS_NTT_MINB_L4 : ((NL <= 8) ? RS_NTT_MINB_SMALL : (NL <= 14 ? RS_NTT_MINB_L14 : RS_NTT_MINB_L28));
 };
 
 template <int NL, int QS, bool INV, bool LAST, bool LAZY>
