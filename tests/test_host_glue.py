@@ -35,3 +35,34 @@ def test_host_parameters_match_oracle(product):
         for f in ("rows", "cols", "slots", "in_msis", "mlwe", "out_msis", "log_in_cut", "log_out_cut", "d", "exp", "base"):
             assert getattr(a, f) == getattr(b, f), (name, f)
         assert list(a.q_primes) == list(b.q_primes) and list(a.qout_primes) == list(b.qout_primes)
+
+
+def test_twin_cdt_slow_path_lower_bound_is_a_lower_bound(product):
+    """The shortcut of encode_kernel's TwinCDT slow path (csrc/jindo.cu, rs_jindo_create): lb[k][v0] must not exceed
+    sum_{x = tail_lo .. v0} rho(x - c) / norm for ANY c in [k/16, (k+1)/16) -- the quantity the reference compares u / 2^64
+    with (math/csprng/gaussian_twin_cdt.go:95-110).  Restated here term by term and checked on a fine grid of c,
+    interval end points included, for the sigma / tail of the parameter sets the tests and the bench use."""
+    import math
+    JH = product.jindo_host
+    for name, n, batch in (("zp255", 1 << 22, 1), ("zp128", 700, 2), ("zp220", 2049, 9)):
+        p = JH.new_parameters(pyref.modulus(name), n, batch)
+        pd, tables = JH.prover_inputs(p)
+        sg, tail_lo, cdt_len = pd["cdt_sigma"], pd["cdt_tail_lo"], len(tables[0])
+        den, norm = 2.0 * sg * sg, math.sqrt(2.0 * math.pi) * sg
+        for k in range(16):
+            a, b = k / 16.0, (k + 1) / 16.0
+            neg = sum(math.exp(-((x - b) ** 2) / den) for x in range(tail_lo, 1))
+            pos, lb = 0.0, []
+            for v0 in range(cdt_len):
+                if v0 >= 1:
+                    pos += math.exp(-((v0 - a) ** 2) / den)
+                lb.append((neg + pos) / norm - 1e-9)
+            for c in [a, math.nextafter(b, 0.0)] + [a + (b - a) * t / 7.0 for t in range(1, 7)]:
+                run = 0.0
+                x = tail_lo
+                for v0 in range(cdt_len):
+                    while x <= v0:
+                        run += math.exp(-((x - c) ** 2) / den)
+                        x += 1
+                    assert lb[v0] <= run / norm, (name, k, v0, c)
+            assert lb[-1] > 0.9                      # and it is tight enough to settle almost every slow sample
