@@ -352,11 +352,14 @@ def test_commit_host_matches_commit(rs, name, N, batch, length):
         assert np.array_equal(op.InCommit(k), polys_array(open_o.InCommit[k])), ("InCommit", k)
 
 
-@pytest.mark.parametrize("name,logn,length_off", [("zp255", 16, 0), ("zp255", 18, 4321), ("zp128", 14, 77), ("zp220", 15, 1)])
-def test_commit_mid_size_bit_exact_vs_c_oracle(rs, name, logn, length_off):
+@pytest.mark.parametrize("name,logn,length_off,huge", [("zp255", 16, 0, False), ("zp255", 18, 4321, False), ("zp128", 14, 77, False),
+                                                       ("zp220", 15, 1, False), ("zp255", 14, 5, True), ("zp220", 13, 0, True)])
+def test_commit_mid_size_bit_exact_vs_c_oracle(rs, name, logn, length_off, huge):
     """Sizes the Python restatement cannot reach: the whole Opening and the Commitment against the C
     restatement (oracle/jindo_oracle.c, pinned to the Python one by tests/test_oracle_jindo_c.py) on a
-    synthetic key / tape, including ragged lengths and 3-limb rings."""
+    synthetic key / tape, including ragged lengths and 3-limb rings.  `huge`: half of the supplied noise integers span
+    +-2^62, far beyond what a sampler produces -- setCoeffSigned (jindo/utils.go:49-60) is defined for any int64, and this
+    is what drives encode_kernel's term-by-term fallback instead of its combined int64 path."""
     from oracle import jindo_c
     q = pyref.modulus(name)
     fo = oracle.Field(q); fg = rs.Field(q)
@@ -387,6 +390,11 @@ def test_commit_mid_size_bit_exact_vs_c_oracle(rs, name, logn, length_off):
             "twin_u": rng.integers(0, 1 << 63, size=n_twin * p.d, dtype=np.int64).view(np.uint64) * np.uint64(2),
             "cosac_g": rng.integers(-5000, 5000, size=n_cosac * p.d, dtype=np.int64),
             "mlwe": rng.integers(-20, 20, size=n_noise * p.d, dtype=np.int64)}
+    if huge:
+        for key in ("cosac_g", "mlwe"):
+            big = rng.integers(-(1 << 62), 1 << 62, size=tape[key].size, dtype=np.int64)
+            tape[key] = np.where(rng.integers(0, 2, size=tape[key].size) == 1, big, tape[key])
+        tape["cosac_g"][:4] = [np.iinfo(np.int64).max, np.iinfo(np.int64).min + 1, -int(p.q_primes[0]), int(p.q_primes[0])]
     v = felems(length)
     pd = params_dict(p, ecd)
     exp = jindo_c.commit(fo, pd, ck_in, ck_mlwe, ck_out, cdt_array(ecd), v, tape, threads=8)
@@ -490,3 +498,13 @@ def test_evaluate_vectors_encoded_on_device(rs, name, N, batch):
         want = polys_array([J.encode_challenge(p, ring, cb) for cb in chal])
         got = gp.EncodeChallenges(blob, ring_out)
         assert np.array_equal(got, want), ("challenge", ring_out)
+
+
+@pytest.mark.parametrize("env", ["RS_JINDO_NOSLOWLB", "RS_JINDO_NOF64", "RS_JINDO_NOPAIR", "RS_JINDO_NOGUIDE"])
+def test_commit_parity_with_alternative_kernel_paths(rs, monkeypatch, env):
+    """encode_kernel keeps its earlier code paths behind environment switches (read when the prover is created / at every
+    launch): no slow-path lower bound (every slow sample takes the CDF sum), integer instead of FP64 warp NTT, one digit per
+    long division, plain binary search instead of the guide table.  Each must give the oracle's Opening as well."""
+    monkeypatch.setenv(env, "1")
+    test_commit_and_evaluate_parity(rs, "zp255", 1024, 1, 1024)
+    test_commit_and_evaluate_parity(rs, "zp220", 2049, 9, 2049)
