@@ -150,7 +150,6 @@ struct UniformStream {
     size_t tot_words;
 };
 
-static bool g_sbox_uploaded = false;
 
 int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_t iv[16]) {
     UniformStream *s = new UniformStream();
@@ -167,7 +166,8 @@ int uniform_stream_init(UniformStream **out, const uint8_t key[32], const uint8_
         s->d_buf[k] = nullptr; s->buf_words[k] = 0;
     }
     s->d_tot = nullptr; s->tot_words = 0;
-    if (!g_sbox_uploaded) { RS_CUDA_CHECK(cudaMemcpyToSymbol(c_sbox, h_sbox, 256)); g_sbox_uploaded = true; }
+    // __constant__ memory is per device: upload once on every device a stream is created on
+    if (first_use_on_device((const void *)h_sbox)) RS_CUDA_CHECK(cudaMemcpyToSymbol(c_sbox, h_sbox, 256));
     *out = s;
     return RS_OK;
 }

@@ -3,7 +3,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <set>
+#include <utility>
 
 #include "common.cuh"
 
@@ -23,6 +26,27 @@ int set_error(int code, const char *fmt, ...) {
 }
 cudaStream_t current_stream() { return g_stream; }
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::mutex g_once_mu;
+static std::map<std::pair<int, const void *>, int> g_smem_attr;      // (device, kernel) -> bytes opted in
+static std::set<std::pair<int, const void *>> g_first_use;
+cudaError_t ensure_smem_attr(const void *func, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_once_mu);
+    auto it = g_smem_attr.find({dev, func});
+    if (it != g_smem_attr.end() && it->second >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) g_smem_attr[{dev, func}] = bytes;
+    return e;
+}
+bool first_use_on_device(const void *tag) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_once_mu);
+    return g_first_use.insert({dev, tag}).second;
+}
 
 // implemented in pointwise.cu
 int pointwise(int op, const rs_field *f, uint32_t *out, const uint32_t *a, const uint32_t *b, const uint32_t *c, size_t n);
@@ -109,9 +133,12 @@ static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 static int ilog2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
 static int ntt_dispatch(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse) {
-    if (!inverse && t->rr_W && 1 + 3 * t->logN <= t->rr_max_bound) {
-        const int rc = ntt_rr_run_l8(const_cast<rs_ntt *>(t), out, in, n_polys);
+    if (t->has52 && t->mix_pf) {
+        const int rc = ntt_mix_run_l8(t, out, in, n_polys, inverse);
         if (rc != RS_ERR_UNSUPPORTED) return rc;
+    }
+    if (t->has52 && t->variant52 >= 0 && t->logN >= 1) {
+        return ntt52_run_v2(t, out, in, n_polys, inverse);
     }
     switch (t->f->NL) {
         case 4: return ntt_run_l4(t, out, in, n_polys, inverse);
@@ -365,66 +392,47 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
     host_inverse(f, t->ninv, nm);
     if (N >= 2) host_mul(f, t->ninv_w1, t->ninv, &t->h_twinv[1 * n]);
     else memcpy(t->ninv_w1, t->ninv, 4 * n);
-    // ---- reduced-radix lazy forward path (8-limb fields with q == 1 mod 2^29)
-    t->rr_W = 0; t->d_tw_rr = nullptr; t->d_scratch = nullptr; t->scratch_words = 0;
-    std::vector<uint32_t> tw_rr;
-    if (n == 8 && (f->q[0] & ((1u << 29) - 1)) == 1 && N >= 2 && getenv("RS_NTT_RR")) {   // experimental, slower than the lazy full-radix kernels
-        int bits = 0;
-        for (int i = n - 1; i >= 0; i--) if (f->q[i]) { bits = 32 * i + (32 - __builtin_clz(f->q[i])); break; }
-        const int W = (bits + 33) / 29;
-        if (W == 8 || W == 9) {
-            auto limbs29 = [&](const uint32_t *w, int nw, uint32_t *out) {     // slice nw 32-bit words into W 29-bit limbs
-                for (int j = 0; j < W; j++) {
-                    const int bit = 29 * j, wi = bit / 32, sh = bit % 32;
-                    const uint64_t lo = wi < nw ? w[wi] : 0, hi = wi + 1 < nw ? w[wi + 1] : 0;
-                    const uint64_t v = ((hi << 32) | lo) >> sh;
-                    out[j] = (j == W - 1) ? (uint32_t)v : (uint32_t)(v & ((1u << 29) - 1));
-                }
-            };
-            uint32_t q1[10] = {0}, q2w[10] = {0}, q3[10] = {0};
-            memcpy(q1, f->q, 4 * n);
-            uint64_t c = 0;
-            for (int i = 0; i < 10; i++) { c += (uint64_t)q1[i] * 2; q2w[i] = (uint32_t)c; c >>= 32; }
-            c = 0;
-            for (int i = 0; i < 10; i++) { c += (uint64_t)q1[i] * 3; q3[i] = (uint32_t)c; c >>= 32; }
-            uint32_t m3[12];
-            limbs29(q1, 10, t->rr_q); limbs29(q2w, 10, t->rr_q2); limbs29(q3, 10, m3);
-            // 3q in limb-dominating form (rr_sub): every limb >= 2^29 - 1, same integer
-            t->rr_c3q[0] = m3[0] + (1u << 29);
-            for (int j = 1; j < W - 1; j++) t->rr_c3q[j] = m3[j] + (1u << 29) - 1;
-            t->rr_c3q[W - 1] = m3[W - 1] - 1;
-            // R' = 2^(29 W) mod q by doubling
-            uint32_t rp[RS_MAX_NL] = {1};
-            for (int i = 0; i < 29 * W; i++) {
-                uint32_t cy = 0;
-                for (int k = 0; k < n; k++) { const uint32_t nc = rp[k] >> 31; rp[k] = (rp[k] << 1) | cy; cy = nc; }
-                if (cy || geq(rp, f->q, n)) {
-                    uint64_t br = 0;
-                    for (int k = 0; k < n; k++) { const uint64_t d = (uint64_t)rp[k] - f->q[k] - br; rp[k] = (uint32_t)d; br = (d >> 63) & 1; }
-                }
-            }
-            limbs29(rp, n, t->rr_one);
-            t->rr_QZ = (t->rr_q[1] == 0) ? 1 : 0;
-            // largest lazy bound B with B * q < 2^(29 W): from the headroom bits (conservative)
-            t->rr_max_bound = 1 << (29 * W - bits);
-            t->rr_W = W;
-            tw_rr.assign(N * 12, 0);
-            for (size_t i = 1; i < N; i++) {
-                uint32_t w[RS_MAX_NL];
-                host_mul(f, w, &t->h_tw[i * n], rp);             // omega 2^256 * R' * 2^-256 = omega R' mod q
-                limbs29(w, n, &tw_rr[i * 12]);
-            }
+    // ---- FP64-pipe paths (ntt52.cuh), 8-word fields with 2^260 >= 36 q.  Both are bit-exact and both measured no faster than
+    // the integer kernels on B200 (a DFMA costs two dispatch cycles, and half-rate instructions of different
+    // pipes barely overlap), so they are opt-in: RS_NTT52=1 runs the FP64 kernels alone, RS_NTT_MIX=pf/p the two-pipe kernels.
+    // RS_NTT52_VARIANT=k: FP64 kernels alone (tuning variant k); RS_NTT_MIX=pf/p: share of FP64 CTAs in the two-pipe kernels
+    t->has52 = 0; t->d_tw52 = t->d_twinv52 = nullptr; t->variant52 = -1; t->mix_pf = 0; t->mix_p = 4;
+    std::vector<double> tw52, twinv52;
+    if (n == 8 && N >= 2 && (getenv("RS_NTT52") || getenv("RS_NTT_MIX")) && f52_setup<8, 5>(t->c52.F, f->q)) {
+        if (const char *v = getenv("RS_NTT52")) { t->variant52 = atoi(v) ? 2 : -1; }
+        if (const char *v = getenv("RS_NTT_MIX")) {
+            unsigned a = 0, b = 1;
+            if (sscanf(v, "%u/%u", &a, &b) >= 1 && b > a) { t->mix_pf = a; t->mix_p = b; }
         }
+        // x R -> x R' = x R 2^(260 - 256): four modular doublings
+        auto to52 = [&](const uint32_t *w, double *out) {
+            uint32_t x[RS_MAX_NL];
+            memcpy(x, w, 4 * n);
+            for (int d = 0; d < 52 * 5 - 32 * 8; d++) host_add(f, x, x, x);
+            long long l[5];
+            f52_from_words<8, 5>(l, x);
+            for (int k = 0; k < 5; k++) out[k] = (double)l[k];
+        };
+        tw52.assign(N * TW52_STRIDE, 0.0); twinv52.assign(N * TW52_STRIDE, 0.0);
+        for (size_t i = 0; i < N; i++) { to52(&t->h_tw[i * n], &tw52[i * TW52_STRIDE]); to52(&t->h_twinv[i * n], &twinv52[i * TW52_STRIDE]); }
+        to52(t->ninv, t->c52.ninv);
+        to52(t->ninv_w1, t->c52.ninv_w1);
+        memcpy(t->c52.qw, f->q, 32);
+        t->has52 = 1;
     }
     const size_t bytes = N * n * 4;
     cudaError_t e1 = cudaMalloc((void **)&t->d_tw, bytes), e2 = cudaMalloc((void **)&t->d_twinv, bytes);
-    if (e1 == cudaSuccess && e2 == cudaSuccess && t->rr_W) {
-        e1 = cudaMalloc((void **)&t->d_tw_rr, tw_rr.size() * 4);
-        if (e1 == cudaSuccess) e1 = cudaMemcpy(t->d_tw_rr, tw_rr.data(), tw_rr.size() * 4, cudaMemcpyHostToDevice);
+    if (e1 == cudaSuccess && e2 == cudaSuccess && t->has52) {
+        e1 = cudaMalloc((void **)&t->d_tw52, tw52.size() * 8);
+        e2 = cudaMalloc((void **)&t->d_twinv52, twinv52.size() * 8);
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(t->d_tw52, tw52.data(), tw52.size() * 8, cudaMemcpyHostToDevice);
+        if (e2 == cudaSuccess) e2 = cudaMemcpy(t->d_twinv52, twinv52.data(), twinv52.size() * 8, cudaMemcpyHostToDevice);
     }
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
         if (t->d_tw) cudaFree(t->d_tw);
         if (t->d_twinv) cudaFree(t->d_twinv);
+        if (t->d_tw52) cudaFree(t->d_tw52);
+        if (t->d_twinv52) cudaFree(t->d_twinv52);
         delete t;
         return set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     }
@@ -437,8 +445,8 @@ void rs_ntt_destroy(rs_ntt *t) {
     if (!t) return;
     if (t->d_tw) cudaFree(t->d_tw);
     if (t->d_twinv) cudaFree(t->d_twinv);
-    if (t->d_tw_rr) cudaFree(t->d_tw_rr);
-    if (t->d_scratch) cudaFree(t->d_scratch);
+    if (t->d_tw52) cudaFree(t->d_tw52);
+    if (t->d_twinv52) cudaFree(t->d_twinv52);
     delete t;
 }
 int rs_ntt_rank_log2(const rs_ntt *t) { return t ? t->logN : RS_ERR_ARG; }

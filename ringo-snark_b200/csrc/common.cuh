@@ -10,6 +10,7 @@
 
 #include "../../include/ringo_cuda.h"
 #include "field.cuh"
+#include "ntt52.cuh"
 
 #define RS_MAX_NL 28
 
@@ -34,12 +35,12 @@ struct rs_ntt {
     std::vector<uint32_t> h_tw, h_twinv;
     uint32_t ninv[RS_MAX_NL];
     uint32_t ninv_w1[RS_MAX_NL];
-    // reduced-radix lazy forward path (rr_field.cuh / ntt_rr.cuh); rr_W == 0: not available
-    int rr_W, rr_QZ, rr_max_bound;
-    uint32_t rr_q[12], rr_c3q[12], rr_q2[12], rr_one[12];
-    uint32_t *d_tw_rr;       // N x 12 words: omega * 2^(29 W) mod q in 29-bit limbs
-    uint32_t *d_scratch;     // lazy elements between passes (planes)
-    size_t scratch_words;
+    // FP64-pipe path (ntt52.cuh), 8-word fields only: twiddles re-scaled to the 2^260 Montgomery radix, 52-bit limbs
+    // as doubles, TW52_STRIDE doubles per entry; has52 == 0: not available for this field
+    int has52, variant52;
+    unsigned mix_pf, mix_p;   // share of the CTAs that take FP64 tiles in the two-pipe kernels (0: off)
+    double *d_tw52, *d_twinv52;
+    rs::Ntt52Consts<8, 5> c52;
 };
 
 struct rs_batch {
@@ -59,6 +60,11 @@ extern thread_local PassProfile *g_pass_profile;
 int set_error(int code, const char *fmt, ...);
 cudaStream_t current_stream();
 void count_launch(unsigned n = 1);
+// One-time per (device, kernel) opt-in to more than 48 KB of dynamic shared memory.  The attribute is per device, so
+// the cache is keyed by the current device (rs_init may bind different threads to different GPUs); mutex-guarded.
+cudaError_t ensure_smem_attr(const void *func, int bytes);
+// true exactly once per (current device, tag): per-device uploads such as __constant__ tables
+bool first_use_on_device(const void *tag);
 
 template <int NL>
 inline FieldParams<NL> make_params(const rs_field *f) {
@@ -80,8 +86,10 @@ int ntt_run_l4(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_poly
 int ntt_run_l8(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 int ntt_run_l14(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 int ntt_run_l28(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
-// forward transform on the reduced-radix lazy kernels (8-limb fields); RS_ERR_UNSUPPORTED if not applicable
-int ntt_rr_run_l8(rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys);
+// FP64-pipe kernels for the 8-word fields, one translation unit per tuning variant (ntt52_v*.cu)
+int ntt52_run_v2(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
+// both pipes in one launch (ntt_mix_l8.cu); RS_ERR_UNSUPPORTED: use the single-pipe kernels
+int ntt_mix_run_l8(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 
 }  // namespace rs
 

@@ -1233,12 +1233,8 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
     // large products (inner commit): shared-memory ring version
     if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !getenv("RS_MV_NOPIPE") &&
         (unsigned long long)G.key_ks * n_slots * 8 < (1ull << 32) && (unsigned long long)G.x_ks * n_slots * 8 < (1ull << 32)) {
-        static bool configured = false;
-        if (!configured) {
-            RS_CUDA_CHECK(cudaFuncSetAttribute(matvec_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_SMEM_BYTES));
-            RS_CUDA_CHECK(cudaFuncSetAttribute(matvec_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_SMEM_BYTES));
-            configured = true;
-        }
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true>, MP_SMEM_BYTES));
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false>, MP_SMEM_BYTES));
         dim3 grid(n_slots / MP_MS, (G.O + MP_OT - 1) / MP_OT, (G.C + MP_CTC - 1) / MP_CTC);
         if (G.fold_every) matvec_pipe_kernel<true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(out, key, x, addend, G);
         else matvec_pipe_kernel<false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(out, key, x, addend, G);
@@ -1290,11 +1286,7 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
     E.cdt_pow2 = 1;
     while (E.cdt_pow2 * 2 <= E.cdt_len) E.cdt_pow2 *= 2;
     const size_t smem = (size_t)G * JD * 4 + (size_t)E.subgroup * JD * 8 + (size_t)E.subgroup * j->rq.n * NTTW_STRIDE * 8;
-    static bool configured = false;
-    if (!configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(encode_kernel<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    RS_CUDA_CHECK(ensure_smem_attr((const void *)encode_kernel<NL>, 200 * 1024));
     encode_kernel<NL><<<(unsigned)((n + G - 1) / G), 256, smem, current_stream()>>>(out, d_descs, (int)n, vec, aux, twin_u, given,
                                                                                    j->d_cdt, j->d_cdt_guide, j->d_slow_lb, j->rq, E, F);
     count_launch();

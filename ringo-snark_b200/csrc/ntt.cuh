@@ -242,26 +242,23 @@ __device__ __forceinline__ void move_tile(uint32_t *sm, const uint32_t *gin, uin
         uint32_t *s = sm + h * L::PLANE_STRIDE + pad_idx(e) * PW;
         if (PW == 4) {
             if (STORE) reinterpret_cast<uint4 *>(gout + flat * NL)[h] = *reinterpret_cast<const uint4 *>(s);
-            else *reinterpret_cast<uint4 *>(s) = __ldg(reinterpret_cast<const uint4 *>(gin + flat * NL) + h);
+            else *reinterpret_cast<uint4 *>(s) = reinterpret_cast<const uint4 *>(gin + flat * NL)[h];
         } else {
             if (STORE) reinterpret_cast<uint2 *>(gout + flat * NL)[h] = *reinterpret_cast<const uint2 *>(s);
-            else *reinterpret_cast<uint2 *>(s) = __ldg(reinterpret_cast<const uint2 *>(gin + flat * NL) + h);
+            else *reinterpret_cast<uint2 *>(s) = reinterpret_cast<const uint2 *>(gin + flat * NL)[h];
         }
     }
 }
 
 // LAST: this pass ends the transform (forward: owns stage logN-1; inverse: owns stage 0, == SCALE)
-template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE, bool LAZY, bool LAST>
-__global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *__restrict__ out, const uint32_t *__restrict__ in,
-                                                           const uint32_t *__restrict__ tw,
-                                                           const __grid_constant__ NttConsts<NL> C,
-                                                           const __grid_constant__ PassGeom G) {
-    constexpr int TS = THREADS << R;
-    extern __shared__ __align__(16) uint32_t sm[];
-    const unsigned long long tile = blockIdx.x;
-
+// (in == out for every pass after the first: plain loads on the data, no __restrict__)
+// TS: tile size in elements (THREADS << R in the single-pipe kernels: one group of 2^R elements per thread and round;
+// a larger TS makes every thread walk several groups per round)
+template <int NL, int QS, int R, int THREADS, int TS, bool INV, bool SCALE, bool LAZY, bool LAST, class SYNC>
+__device__ __forceinline__ void ntt_pass_body(uint32_t *sm, uint32_t *out, const uint32_t *in, const uint32_t *__restrict__ tw,
+                                              const NttConsts<NL> &C, const PassGeom &G, unsigned long long tile, SYNC sync) {
     move_tile<NL, THREADS, TS, false>(sm, in, out, G, tile);
-    __syncthreads();
+    sync();
 
     // rounds: forward walks the local bit field from the top, inverse from the bottom;
     // the one partial round (K mod R stages) comes last in both directions.
@@ -277,16 +274,27 @@ __global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *__res
             else run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS>(sm, tw, G, lb, tile, C);
         } else if (!INV && r == 0 && G.s0 == 0 && G.triv) run_round<NL, QS, R, false, false, LAZY, false, THREADS, TS, true>(sm, tw, G, lb, tile, C);
         else run_round<NL, QS, R, INV, false, LAZY, false, THREADS, TS>(sm, tw, G, lb, tile, C);
-        __syncthreads();
+        sync();
     }
     if (rem) {
         const int lb = INV ? full * R : 0;
         if (R >= 2 && rem == 1) run_round<NL, QS, 1, INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
         if (R >= 3 && rem == 2) run_round<NL, QS, (R >= 3 ? 2 : 1), INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
         if (R >= 4 && rem == 3) run_round<NL, QS, (R >= 4 ? 3 : 1), INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
-        __syncthreads();
+        sync();
     }
     move_tile<NL, THREADS, TS, true>(sm, in, out, G, tile);
+}
+
+struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+
+template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE, bool LAZY, bool LAST>
+__global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *out, const uint32_t *in,
+                                                           const uint32_t *__restrict__ tw,
+                                                           const __grid_constant__ NttConsts<NL> C,
+                                                           const __grid_constant__ PassGeom G) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    ntt_pass_body<NL, QS, R, THREADS, (THREADS << R), INV, SCALE, LAZY, LAST>(sm, out, in, tw, C, G, blockIdx.x, CtaSync());
 }
 
 #endif  // __CUDACC__

@@ -57,11 +57,7 @@ int launch_pass(const rs_ntt *t, uint32_t *out, const uint32_t *in, const NttCon
     constexpr int MINB = (!INV && NL > 4 && NL <= 8) ? RS_NTT_MINB_FWD : T::MINB;
     auto kern = ntt_pass_kernel<NL, QS, T::R, T::THREADS, MINB, INV, (INV && LAST), LAZY, LAST>;
     constexpr int smem = SmemLayout<NL, T::TS>::BYTES;
-    static bool configured = false;
-    if (!configured) {
-        RS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    RS_CUDA_CHECK(ensure_smem_attr((const void *)kern, smem));
     RS_REQUIRE(tiles <= 0x7fffffffull, RS_ERR_UNSUPPORTED, "ntt: batch too large for one launch");
     kern<<<(unsigned)tiles, T::THREADS, smem, current_stream()>>>(out, in, INV ? t->d_twinv : t->d_tw, C, G);
     count_launch();

@@ -236,3 +236,37 @@ def test_shape_errors(rs):
         t.FwdNTTTo(small, ok)
     with pytest.raises(ValueError):
         rs.CyclicTransformer(fg, 100)          # "rank must be a power of two" (ntt.go:27-29)
+
+
+@pytest.mark.parametrize("env", [{"RS_NTT52": "1"}, {"RS_NTT_MIX": "1/4"}, {"RS_NTT_MIX": "2/5"}])
+@pytest.mark.parametrize("name", ["zp255", "zp240", "zp220"])
+def test_fp64_pipe_paths_equal_integer_path(rs, name, env, monkeypatch):
+    """The opt-in FP64-pipe kernels (ntt52.cuh: 52-bit limbs in doubles, lazy reduction) and the two-pipe kernels that
+    share a batch between integer and FP64 tiles give the integer kernels' bytes: every kind of transform, ranks with
+    one and two passes, partial tiles, unit-twiddle rounds, q == 1 mod 2^52 (zp255, zp220) and the generic modulus (zp240)."""
+    q = pyref.modulus(name)
+    fg = rs.Field(q); fo = oracle.Field(q)
+    cases = [(1, 3), (4, 5), (9, 3), (10, 2), (11, 3), (13, 2), (16, 8)]
+    for logN, n_polys in cases:
+        N = 1 << logN
+        rng = np.random.default_rng(logN * 31 + n_polys)
+        raw = rng.integers(0, 1 << 63, size=(n_polys, N, fo.L), dtype=np.uint64)
+        raw[..., fo.L - 1] &= np.uint64((1 << ((q.bit_length() - 1) % 64)) - 1)
+        raw[0, :4] = fo.to_mont([0, 1, q - 1, q - 2])          # edge values
+        for neg in (False, True):
+            cls = rs.CyclotomicTransformer if neg else rs.CyclicTransformer
+            ref_t = cls(fg, N)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            alt_t = cls(fg, N)                                     # the path is chosen when the tables are built
+            for k in env:
+                monkeypatch.delenv(k)
+            for inv in (False, True):
+                A = rs.Batch(fg, n_polys, N).upload(raw)
+                Bt = rs.Batch(fg, n_polys, N).upload(raw)
+                (ref_t.InvNTTTo if inv else ref_t.FwdNTTTo)(A, A)
+                (alt_t.InvNTTTo if inv else alt_t.FwdNTTTo)(Bt, Bt)
+                assert np.array_equal(A.download(), Bt.download()), (name, env, logN, neg, inv)
+        if logN == 9:
+            to = oracle.NTT(fo, logN, True)
+            assert np.array_equal(Bt.download()[1], to.inv(raw[1]))   # and the oracle itself once
