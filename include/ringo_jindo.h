@@ -80,6 +80,16 @@ void rs_jindo_destroy(rs_jindo *j);
 int rs_jindo_set_twin_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *iv16);
 int rs_jindo_twin_stream_draw(rs_jindo *j, size_t n, uint64_t *out);
 
+/* GPU-resident Prover.mlweSampler (jindo/prover.go:38, :136-138): a TwinCDTGaussianSampler that is only ever asked for
+ * centre 0, i.e. exactly one uniform draw and one binary search in table 0 per sample (gaussian_twin_cdt.go:77-97: c0 == c1,
+ * so the slow path is unreachable).  key32 || iv16 = SHA-384(seed) of that sampler's UniformSampler; table0 = computeCDT(0,
+ * mlweStdDev) (len entries, gaussian_twin_cdt.go:13-35; rs_compute_cdt), tail_lo = -ceil(9 mlweStdDev).  Stateful like the Go
+ * object: every Commit whose tape has mlwe_mask_only set consumes the next cols*(in_msis+mlwe)*d draws, column-major in the
+ * reference's call order. */
+int rs_jindo_set_mlwe_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *iv16, const uint64_t *table0, int len, int64_t tail_lo);
+/* the next n samples of that sampler (tests) */
+int rs_jindo_mlwe_stream_sample(rs_jindo *j, size_t n, int64_t *out);
+
 /* Randomness / noise inputs of one Commit, in the reference's consumption order. */
 typedef struct rs_jindo_tape {
     const uint64_t *first_row;   /* cols*slots field elements (Montgomery)       prover.go:65-86 */
@@ -92,8 +102,12 @@ typedef struct rs_jindo_tape {
     const int64_t *cosac_g;      /* sampled g for the COSAC rows: data columns' row 0 (col order), then
                                     the mask column's rows in encode order; d values each */
     size_t n_cosac_polys;
-    const int64_t *mlwe;         /* (cols+1)*(in_msis+mlwe)*d noise samples          prover.go:130-139 */
+    const int64_t *mlwe;         /* (cols+1)*(in_msis+mlwe)*d noise samples          prover.go:130-139;
+                                    with mlwe_mask_only: just the mask column's (in_msis+mlwe)*d samples */
     int32_t on_device;           /* != 0: every pointer above is a device pointer (tape already resident in HBM) */
+    int32_t mlwe_mask_only;      /* != 0: the data columns' MLWE noise (mlweSampler.Sample(0), prover.go:136-138) is drawn on the
+                                    device from the stream set by rs_jindo_set_mlwe_stream; `mlwe` holds the mask column only
+                                    (roundedSampler, host) */
 } rs_jindo_tape;
 
 /* Prover.Commit (jindo/prover.go:45-62).  v: device batch holding the committed vector

@@ -37,7 +37,7 @@ def build(force=False, verbose=False, defines=(), tag=""):
     FLAGS.extend("-D" + d for d in defines)
     os.makedirs(OBJ, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(HERE, "..", "include", "ringo_cuda.h")]
+    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(HERE, "..", "include", "*.h")))
     jobs = []
     objs = []
     for s in srcs:
@@ -45,6 +45,13 @@ def build(force=False, verbose=False, defines=(), tag=""):
         objs.append(o)
         if force or not _newer(o, [s] + hdrs):
             jobs.append([NVCC] + ARCH + FLAGS + ["-c", s, "-o", o])
+    # host-only sources (the csprng restatement): g++, no FMA contraction (Go on amd64 never fuses a*b+c)
+    for s in sorted(glob.glob(os.path.join(CSRC, "*.cpp"))):
+        o = os.path.join(OBJ, os.path.basename(s)[:-4] + ".host.o")
+        objs.append(o)
+        if force or not _newer(o, [s] + hdrs):
+            jobs.append(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-pthread"]
+                        + ["-D" + d for d in defines] + ["-c", s, "-o", o])
     if jobs:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             for cmd, res in zip(jobs, ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs)):
@@ -53,7 +60,7 @@ def build(force=False, verbose=False, defines=(), tag=""):
                 if res.returncode:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
     if jobs or not _newer(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart", "-Xcompiler", "-pthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             sys.stderr.write(res.stdout + res.stderr)

@@ -46,7 +46,13 @@ class JindoTape(ctypes.Structure):
     """rs_jindo_tape (include/ringo_jindo.h)"""
     _fields_ = [("first_row", c_vp), ("last_row", c_vp), ("mask_rows", c_vp), ("n_mask_rows", c_size),
                 ("twin_u", c_vp), ("n_twin_u", c_size), ("cosac_g", c_vp), ("n_cosac_polys", c_size), ("mlwe", c_vp),
-                ("on_device", ctypes.c_int32)]
+                ("on_device", ctypes.c_int32), ("mlwe_mask_only", ctypes.c_int32)]
+
+
+class JindoNoise(ctypes.Structure):
+    """rs_jindo_noise (include/ringo_sampler.h)"""
+    _fields_ = [("ecd_blind_std", ctypes.c_double), ("mask_blind_std", ctypes.c_double), ("mask_std", ctypes.c_double),
+                ("mask_mlwe_std", ctypes.c_double)]
 
 
 # name -> (restype, argtypes); mirrors include/ringo_cuda.h and include/ringo_jindo.h one to one
@@ -105,6 +111,8 @@ _SIGS = {
     "rs_jindo_destroy": (None, [c_vp]),
     "rs_jindo_set_twin_stream": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "rs_jindo_twin_stream_draw": (ctypes.c_int, [c_vp, c_size, c_vp]),
+    "rs_jindo_set_mlwe_stream": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int64]),
+    "rs_jindo_mlwe_stream_sample": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_commit": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
     "rs_jindo_commit_host": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
     "rs_jindo_commit_columns": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
@@ -121,6 +129,28 @@ _SIGS = {
     "rs_opening_mul_add_bytes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "rs_opening_alloc_zero": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "rs_opening_mul_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    # ringo_sampler.h
+    "rs_uniform_create": (c_vp, [c_vp]),
+    "rs_uniform_destroy": (None, [c_vp]),
+    "rs_uniform_sample": (ctypes.c_uint64, [c_vp]),
+    "rs_uniform_sample_many": (None, [c_vp, c_vp, c_size]),
+    "rs_uniform_sample_n": (ctypes.c_uint64, [c_vp, ctypes.c_uint64]),
+    "rs_uniform_sample_float": (ctypes.c_double, [c_vp]),
+    "rs_uniform_read": (None, [c_vp, c_vp, c_size]),
+    "rs_rounded_create": (c_vp, [c_vp]),
+    "rs_rounded_destroy": (None, [c_vp]),
+    "rs_rounded_norm_float": (ctypes.c_double, [c_vp]),
+    "rs_rounded_sample": (ctypes.c_int64, [c_vp, ctypes.c_double, ctypes.c_double]),
+    "rs_cosac_create": (c_vp, [c_vp, c_vp]),
+    "rs_cosac_destroy": (None, [c_vp]),
+    "rs_cosac_sample": (ctypes.c_int64, [c_vp, ctypes.c_double, ctypes.c_double]),
+    "rs_compute_cdt": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]),
+    "rs_tape_builder_create": (ctypes.c_int, [ctypes.POINTER(JindoParams), ctypes.POINTER(JindoNoise), c_u64p, ctypes.c_int, ctypes.c_int,
+                                              c_vp, ctypes.POINTER(c_vp)]),
+    "rs_tape_builder_destroy": (None, [c_vp]),
+    "rs_tape_builder_set_random_bytes": (ctypes.c_int, [c_vp, c_vp, c_size]),
+    "rs_tape_builder_start": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.c_int]),
+    "rs_tape_builder_wait": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(JindoTape), ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None

@@ -92,6 +92,8 @@ struct rs_jindo {
     double *d_slow_lb;      // [16][cdt_len]: rigorous lower bounds of the slow path's CDF sum (see encode_kernel)
     u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
     rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
+    rs::UniformStream *mlwe_stream;   // same for Prover.mlweSampler (centre 0: table 0 only)
+    u64 *d_mlwe_cdt; int mlwe_cdt_len; long long mlwe_tail_lo;
     cudaStream_t copy_stream;         // rs_jindo_commit_host: uploads of v pieces
     size_t ck_rejected;               // rs_jindo_create_crs: draws SampleN threw away while generating the key
     cudaEvent_t ev_alloc, ev_piece[RS_VCHUNKS];
@@ -1665,6 +1667,8 @@ void rs_jindo_destroy(rs_jindo *j) {
     if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
     cudaFree(j->d_ndescs); cudaFree(j->d_ldescs); cudaFree(j->d_zero_g);
     rs::uniform_stream_free(j->twin_stream);
+    rs::uniform_stream_free(j->mlwe_stream);
+    cudaFree(j->d_mlwe_cdt);
     delete j;
 }
 
@@ -1684,6 +1688,64 @@ int rs_jindo_twin_stream_draw(rs_jindo *j, size_t n, uint64_t *out) {
     rs::uniform_stream_release(j->twin_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(rs::current_stream());
     if (e != cudaSuccess) return rs::set_error(RS_ERR_CUDA, "rs_jindo_twin_stream_draw: %s", cudaGetErrorString(e));
+    return RS_OK;
+}
+
+namespace rs {
+// TwinCDTGaussianSampler.Sample(0) (gaussian_twin_cdt.go:77-97): v0 = slices.BinarySearch(table0, u), minus one on an exact
+// hit; c0 == c1 == 0, so v0 == v1 and the result is v0 + tailLo.  One thread per sample, table in shared memory.
+__global__ void __launch_bounds__(256) cdt0_sample_kernel(i64 *__restrict__ out, const u64 *__restrict__ draws, const u64 *__restrict__ table,
+                                                         int len, i64 tail_lo, size_t n) {
+    extern __shared__ u64 s_tab[];
+    for (int i = threadIdx.x; i < len; i += blockDim.x) s_tab[i] = table[i];
+    __syncthreads();
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 u = draws[i];
+        int lo = 0, hi = len;                       // first index with table[idx] >= u
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tab[mid] < u) lo = mid + 1; else hi = mid; }
+        const int v0 = (lo < len && s_tab[lo] == u) ? lo - 1 : lo;
+        out[i] = (i64)v0 + tail_lo;
+    }
+}
+static int mlwe_stream_sample(rs_jindo *j, size_t n, i64 *d_out) {
+    if (n == 0) return RS_OK;
+    const u64 *smp = nullptr;
+    int rc = uniform_stream_draw(j->mlwe_stream, n, &smp);
+    if (rc) return rc;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cdt0_sample_kernel<<<(unsigned)blocks, 256, (size_t)j->mlwe_cdt_len * 8, current_stream()>>>(d_out, smp, j->d_mlwe_cdt, j->mlwe_cdt_len,
+                                                                                             (i64)j->mlwe_tail_lo, n);
+    count_launch();
+    uniform_stream_release(j->mlwe_stream);
+    if (cudaGetLastError() != cudaSuccess) return set_error(RS_ERR_CUDA, "cdt0_sample_kernel launch failed");
+    return RS_OK;
+}
+}  // namespace rs
+
+int rs_jindo_set_mlwe_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *iv16, const uint64_t *table0, int len, int64_t tail_lo) {
+    RS_REQUIRE(j && key32 && iv16 && table0 && len > 0 && len <= 4096, RS_ERR_ARG, "rs_jindo_set_mlwe_stream: bad argument");
+    rs::uniform_stream_free(j->mlwe_stream);
+    j->mlwe_stream = nullptr;
+    cudaFree(j->d_mlwe_cdt); j->d_mlwe_cdt = nullptr;
+    RS_CUDA_CHECK(cudaMalloc((void **)&j->d_mlwe_cdt, (size_t)len * 8));
+    RS_CUDA_CHECK(cudaMemcpy(j->d_mlwe_cdt, table0, (size_t)len * 8, cudaMemcpyHostToDevice));
+    j->mlwe_cdt_len = len; j->mlwe_tail_lo = tail_lo;
+    return rs::uniform_stream_init(&j->mlwe_stream, key32, iv16);
+}
+
+int rs_jindo_mlwe_stream_sample(rs_jindo *j, size_t n, int64_t *out) {
+    RS_REQUIRE(j && j->mlwe_stream && (out || n == 0), RS_ERR_ARG, "rs_jindo_mlwe_stream_sample: no stream / null argument");
+    if (n == 0) return RS_OK;
+    i64 *d = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d, n * 8, rs::current_stream()));
+    int rc = rs::mlwe_stream_sample(j, n, d);
+    cudaError_t e = cudaSuccess;
+    if (rc == RS_OK) e = cudaMemcpyAsync(out, d, n * 8, cudaMemcpyDeviceToHost, rs::current_stream());
+    cudaFreeAsync(d, rs::current_stream());
+    if (rc) return rc;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rs::current_stream());
+    if (e != cudaSuccess) return rs::set_error(RS_ERR_CUDA, "rs_jindo_mlwe_stream_sample: %s", cudaGetErrorString(e));
     return RS_OK;
 }
 
@@ -1804,6 +1866,8 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
     }
     RS_REQUIRE(tape->n_mask_rows == mask, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of mask rows");
     RS_REQUIRE(tape->n_cosac_polys == cosac, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of COSAC polynomials");
+    const bool gen_mlwe = tape->mlwe_mask_only != 0;
+    if (gen_mlwe) RS_REQUIRE(j->mlwe_stream, RS_ERR_ARG, "rs_jindo_commit: tape has mlwe_mask_only set and no stream was set (rs_jindo_set_mlwe_stream)");
     const bool gen_twin = (tape->twin_u == nullptr && twin != 0);
     if (gen_twin)
         RS_REQUIRE(j->twin_stream, RS_ERR_ARG, "rs_jindo_commit: tape carries no TwinCDT draws and no stream was set (rs_jindo_set_twin_stream)");
@@ -1824,7 +1888,7 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
 
     // ---- uploads (skipped when the tape is already device resident)
     const bool dev = tape->on_device != 0;
-    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; bool twin_drawn = false; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
+    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; bool twin_drawn = false, mlwe_owned = false; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
     u64 *d_com = nullptr;
     uint32_t *d_v = nullptr;          // device copy of a host-resident v
 #define RS_TRY(x) do { rc = (x); if (rc) goto fail; } while (0)
@@ -1836,12 +1900,26 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         cudaMemcpyAsync(d_aux + cs * NL, tape->last_row, cs * NL * 4, kind, current_stream());
         cudaMemcpyAsync(d_aux + 2 * cs * NL, tape->mask_rows, mask * slots * NL * 4, kind, current_stream());
     }
-    if (dev) {
+    if (dev && !gen_mlwe) {
         d_twin = (u64 *)tape->twin_u; d_cosac = (i64 *)tape->cosac_g; d_mlwe_s = (i64 *)tape->mlwe;
     } else {
-        if (!gen_twin) RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
-        RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
-        RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
+        if (dev) { d_twin = (u64 *)tape->twin_u; d_cosac = (i64 *)tape->cosac_g; }
+        else {
+            if (!gen_twin) RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
+            RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
+        }
+        if (gen_mlwe) {
+            // data columns: Prover.mlweSampler on the device (the whole Commit's draws, so that a column shard sees the
+            // stream positions the unsharded Commit gives its columns); mask column: the host's roundedSampler samples
+            const size_t nmd = (size_t)(p.in_msis + p.mlwe) * d;
+            if (cudaMallocAsync((void **)&d_mlwe_s, n_noise * d * 8, current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: cudaMallocAsync failed"); goto fail; }
+            mlwe_owned = true;
+            cudaMemcpyAsync(d_mlwe_s + (size_t)cols * nmd, tape->mlwe, nmd * 8, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, current_stream());
+            RS_TRY(mlwe_stream_sample(j, (size_t)cols * nmd, d_mlwe_s));
+        } else {
+            RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
+            mlwe_owned = true;
+        }
     }
     if (v_host) {
         // upload v in RS_VCHUNKS pieces on the copy stream; piece k is encoded as soon as it has landed.  Enqueued right behind
@@ -1905,7 +1983,8 @@ fail:
 #undef RS_TRY
     cudaFreeAsync(d_aux, current_stream());
     if (d_v) cudaFreeAsync(d_v, current_stream());
-    if (!dev) { if (!gen_twin) cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); cudaFreeAsync(d_mlwe_s, current_stream()); }
+    if (!dev) { if (!gen_twin) cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); }
+    if (mlwe_owned) cudaFreeAsync(d_mlwe_s, current_stream());
     if (twin_drawn) {
         uniform_stream_release(j->twin_stream);                  // every reader of the draws has been launched
         // optional (RS_JINDO_PREFETCH=1): generate the next Commit's draws now, behind this Commit's remaining kernels.

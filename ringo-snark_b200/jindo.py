@@ -17,6 +17,104 @@ def _vp(a):
     return a.ctypes.data_as(c_vp)
 
 
+def params_struct(p, cdt_len):
+    """rs_jindo_params from the plain dict the host glue / the tests carry around"""
+    P = capi.JindoParams()
+    for k in ("d", "slots", "exp", "base", "rows", "cols", "in_msis", "mlwe", "out_msis", "log_in_cut", "log_out_cut"):
+        setattr(P, k, int(p[k]))
+    P.n_q, P.n_qout = len(p["q"]), len(p["qout"])
+    for i, v in enumerate(p["q"]): P.q[i] = v
+    for i, v in enumerate(p["qout"]): P.qout[i] = v
+    for i, v in enumerate(p["psi_q"]): P.psi_q[i] = v
+    for i, v in enumerate(p["psi_qout"]): P.psi_qout[i] = v
+    for i, v in enumerate(p["delta_inv"]): P.delta_inv[i] = v
+    P.cdt_len = int(cdt_len)
+    P.cdt_tail_lo = int(p["cdt_tail_lo"])
+    P.cdt_sigma = float(p["cdt_sigma"])
+    return P
+
+
+def key48(seed):
+    """SHA-384(seed) = AES key || IV of a csprng.UniformSampler (math/csprng/uniform.go:38-46)"""
+    import hashlib
+    return hashlib.sha384(bytes(seed)).digest()
+
+
+def compute_cdt(center, sigma):
+    """computeCDT (gaussian_twin_cdt.go:13-35) through the library: (table, tail_lo)"""
+    import math
+    cap = 2 * int(math.ceil(9 * sigma)) + 1
+    tab = np.zeros(cap, dtype=np.uint64)
+    lo = ctypes.c_int64()
+    n = lib().rs_compute_cdt(float(center), float(sigma), _vp(tab), cap, ctypes.byref(lo))
+    if n < 0:
+        raise capi.RingoError(n, "rs_compute_cdt")
+    return tab[:n], lo.value
+
+
+class TapeBuilder:
+    """rs_tape_builder (include/ringo_sampler.h): the host half of a Commit's randomness tape -- COSAC rows, the mask
+    column's rounded-Gaussian MLWE noise and the MustSetRandom elements -- produced on worker threads.
+    noise: dict with ecd_blind_std, mask_blind_std, mask_std, mask_mlwe_std (jindo/params.go:303-309).
+    seeds: None (OS randomness, any number of threads) or three 32-byte sampler seeds in NewProver's order
+    (encoder COSAC base, COSAC rounded, prover rounded; one thread: the reference's sequential streams)."""
+
+    def __init__(self, p, cdt_len, noise, q_field, threads=1, seeds=None):
+        self.p = p
+        self.L = (q_field.bit_length() + 63) // 64
+        P = params_struct(p, cdt_len)
+        Nz = capi.JindoNoise()
+        for k in ("ecd_blind_std", "mask_blind_std", "mask_std", "mask_mlwe_std"):
+            setattr(Nz, k, float(noise[k]))
+        qa = np.array([(q_field >> (64 * i)) & ((1 << 64) - 1) for i in range(self.L)], dtype=np.uint64)
+        kb = b"".join(key48(s) for s in seeds) if seeds is not None else None
+        h = c_vp()
+        check(lib().rs_tape_builder_create(ctypes.byref(P), ctypes.byref(Nz), qa.ctypes.data_as(capi.c_u64p), self.L, int(threads),
+                                           ctypes.c_char_p(kb) if kb else None, ctypes.byref(h)))
+        self.h = h
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().rs_tape_builder_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    def set_random_bytes(self, data):
+        self._rand = ctypes.create_string_buffer(bytes(data), len(data))
+        check(lib().rs_tape_builder_set_random_bytes(self.h, ctypes.cast(self._rand, c_vp), len(data)))
+
+    def start(self, v_host, length, slot=0):
+        """v_host: numpy uint64 array [>= length, L] (kept alive until wait) or a raw host pointer"""
+        if isinstance(v_host, np.ndarray):
+            self._keep = np.ascontiguousarray(v_host, dtype=np.uint64)
+            ptr = _vp(self._keep)
+        else:
+            ptr = c_vp(int(v_host))
+        check(lib().rs_tape_builder_start(self.h, ptr, int(length), int(slot)))
+
+    def wait(self, slot=0):
+        """-> (rs_jindo_tape struct pointing into the builder's staging buffers, host milliseconds)"""
+        T = capi.JindoTape()
+        ms = ctypes.c_double()
+        check(lib().rs_tape_builder_wait(self.h, int(slot), ctypes.byref(T), ctypes.byref(ms)))
+        return T, ms.value
+
+    def arrays(self, T):
+        """numpy copies of a finished tape (tests)"""
+        d, L, slots = self.p["d"], self.L, self.p["slots"]
+        cs = self.p["cols"] * slots
+        nm = self.p["in_msis"] + self.p["mlwe"]
+
+        def arr(ptr, n, dt):
+            return np.frombuffer((ctypes.c_uint64 * n).from_address(ptr), dtype=dt).copy()
+        return {"first_row": arr(T.first_row, cs * L, np.uint64).reshape(cs, L), "last_row": arr(T.last_row, cs * L, np.uint64).reshape(cs, L),
+                "mask_rows": arr(T.mask_rows, T.n_mask_rows * slots * L, np.uint64).reshape(-1, L),
+                "cosac_g": arr(T.cosac_g, T.n_cosac_polys * d, np.int64).reshape(-1, d),
+                "mlwe_mask": arr(T.mlwe, nm * d, np.int64).reshape(nm, d)}
+
+
 class Opening:
     def __init__(self, prover, handle):
         self.prover = prover
@@ -56,19 +154,8 @@ class Prover:
         self.p = dict(p)
         self.d = p["d"]
         self.n_q, self.n_qout = len(p["q"]), len(p["qout"])
-        P = capi.JindoParams()
-        for k in ("d", "slots", "exp", "base", "rows", "cols", "in_msis", "mlwe", "out_msis", "log_in_cut", "log_out_cut"):
-            setattr(P, k, int(p[k]))
-        P.n_q, P.n_qout = self.n_q, self.n_qout
-        for i, v in enumerate(p["q"]): P.q[i] = v
-        for i, v in enumerate(p["qout"]): P.qout[i] = v
-        for i, v in enumerate(p["psi_q"]): P.psi_q[i] = v
-        for i, v in enumerate(p["psi_qout"]): P.psi_qout[i] = v
-        for i, v in enumerate(p["delta_inv"]): P.delta_inv[i] = v
         cdt = np.ascontiguousarray(cdt_tables, dtype=np.uint64)
-        P.cdt_len = cdt.shape[1]
-        P.cdt_tail_lo = int(p["cdt_tail_lo"])
-        P.cdt_sigma = float(p["cdt_sigma"])
+        P = params_struct(p, cdt.shape[1])
         h = c_vp()
         if key_from_crs:
             import hashlib
@@ -109,6 +196,17 @@ class Prover:
         key = np.frombuffer(h[:32], dtype=np.uint8).copy(); iv = np.frombuffer(h[32:48], dtype=np.uint8).copy()
         check(lib().rs_jindo_set_twin_stream(self.h, _vp(key), _vp(iv)))
 
+    def SetMlweSeed(self, seed, mlwe_std):
+        """Prover.mlweSampler on the device (rs_jindo_set_mlwe_stream): seed of its UniformSampler, sigma = params.mlweStdDev"""
+        tab, lo = compute_cdt(0.0, mlwe_std)
+        dg = key48(seed)
+        check(lib().rs_jindo_set_mlwe_stream(self.h, ctypes.c_char_p(dg[:32]), ctypes.c_char_p(dg[32:48]), _vp(tab), len(tab), lo))
+
+    def MlweStreamSample(self, n):
+        out = np.zeros(n, dtype=np.int64)
+        check(lib().rs_jindo_mlwe_stream_sample(self.h, n, _vp(out)))
+        return out
+
     def TwinStreamDraw(self, n):
         """The next n Sample() values of the device stream (advances it)."""
         out = np.zeros(n, dtype=np.uint64)
@@ -119,16 +217,10 @@ class Prover:
         """prover.go:45-62.  batch/poly/length: device-resident committed vector; tape: dict of
         numpy arrays first_row, last_row, mask_rows (uint64 Montgomery limbs), twin_u (uint64),
         cosac_g, mlwe (int64).  Returns (commitment [out_msis, n_qout, 256], Opening)."""
-        keep = {k: np.ascontiguousarray(tape[k], dtype=(np.int64 if k in ("cosac_g", "mlwe") else np.uint64))
-                for k in ("first_row", "last_row", "mask_rows", "twin_u", "cosac_g", "mlwe") if tape.get(k) is not None}
-        L = self.field.L
-        T = capi.JindoTape()
-        T.first_row, T.last_row, T.mask_rows = _vp(keep["first_row"]), _vp(keep["last_row"]), _vp(keep["mask_rows"])
-        T.n_mask_rows = keep["mask_rows"].size // (L * self.p["slots"])
-        if "twin_u" in keep:        # else: drawn on the device from the stream set by SetTwinSeed
-            T.twin_u, T.n_twin_u = _vp(keep["twin_u"]), keep["twin_u"].size
-        T.cosac_g, T.n_cosac_polys = _vp(keep["cosac_g"]), keep["cosac_g"].size // self.d
-        T.mlwe = _vp(keep["mlwe"])
+        if isinstance(tape, capi.JindoTape):       # e.g. straight from TapeBuilder.wait()
+            T = tape
+        else:
+            T, keep = self.tape_struct(tape)
         com = np.zeros((self.p["out_msis"], self.n_qout, self.d), dtype=np.uint64)
         oh = c_vp()
         check(lib().rs_jindo_commit(self.h, batch.h, poly, length, ctypes.byref(T), ctypes.byref(oh), _vp(com)))
@@ -152,6 +244,7 @@ class Prover:
             T.twin_u, T.n_twin_u = _vp(keep["twin_u"]), keep["twin_u"].size
         T.cosac_g, T.n_cosac_polys = _vp(keep["cosac_g"]), keep["cosac_g"].size // self.d
         T.mlwe = _vp(keep["mlwe"])
+        T.mlwe_mask_only = 1 if tape.get("mlwe_mask_only") else 0
         return T, keep
 
     def CommitColumns(self, batch, poly, length, tape, col_begin, col_end, opening=None):

@@ -15,7 +15,11 @@ BLOCK = 128
 
 def _go_round(x):
     """math.Round: half away from zero."""
-    return math.floor(x + 0.5) if x >= 0 else math.ceil(x - 0.5)
+    # (not floor(x + 0.5): that sum rounds to even above 2^52 and turns 0.49999999999999994 into 1)
+    t = float(math.trunc(x))
+    if abs(x - t) >= 0.5:
+        t += math.copysign(1.0, x)
+    return t
 
 
 def compute_cdt(center, sigma):

@@ -508,3 +508,66 @@ def test_commit_parity_with_alternative_kernel_paths(rs, monkeypatch, env):
     monkeypatch.setenv(env, "1")
     test_commit_and_evaluate_parity(rs, "zp255", 1024, 1, 1024)
     test_commit_and_evaluate_parity(rs, "zp220", 2049, 9, 2049)
+
+
+def test_device_mlwe_sampler_matches_oracle(rs):
+    """Prover.mlweSampler (TwinCDT, centre 0) on the device: the AES-CTR stream keyed by the sampler's seed and the
+    binary search in table 0 give the oracle's Sample(0) sequence, across calls (the stream is stateful)."""
+    q = pyref.modulus("zp255")
+    fg = rs.Field(q)
+    p = J.new_parameters(q, 1024, 1)
+    tape = J.Tape(b"mlwe-stream")
+    prv = J.Prover(p, b"Jindo!", tape)
+    gp = rs.jindo.Prover(fg, params_dict(p, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
+                         polys_array(prv.ck.Out), cdt_array(prv.ecd))
+    seed = prv.mlwe.base.seed
+    gp.SetMlweSeed(seed, p.mlwe_std)
+    ref = J.TwinCDTGaussianSampler(p.mlwe_std, seed)
+    for n in (1, 1023, 5000, 3 * 8192 + 5):
+        got = gp.MlweStreamSample(n)
+        assert got.tolist() == [ref.sample(0) for _ in range(n)], n
+    # exact-hit rule of slices.BinarySearch (gaussian_twin_cdt.go:86-89): a draw equal to a table entry steps one back;
+    # checked on the table itself through a host-built sampler with the same table
+    tab, lo = rs.jindo.compute_cdt(0.0, p.mlwe_std)
+    assert [int(x) for x in tab] == ref.tables[0] and lo == ref.tail_lo
+
+
+@pytest.mark.parametrize("name,N,batch,length", [("zp255", 1024, 1, 1024), ("zp255", 1024, 1, 600), ("zp128", 700, 2, 700), ("zp240", 600, 3, 513)])
+def test_commit_from_seeds_only(rs, name, N, batch, length):
+    """The end-to-end form of Commit: nothing but the vector, the sampler seeds and the crypto/rand bytes go in.  The
+    host half of the tape comes from the product's tape builder (COSAC rows, mask MLWE, MustSetRandom elements), the two
+    TwinCDT samplers (encoder rows, mlweSampler) run on the device from their seeds -- and the Opening and Commitment
+    are the oracle's, bit for bit, for two Commits in a row (every stream continues where it stopped)."""
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    sd = b"seeds-only-" + name.encode()
+    p = J.new_parameters(q, N, batch)
+    tape = J.Tape(sd)
+    prv = J.Prover(p, b"Jindo!", tape)
+    pd = params_dict(p, prv.ecd)
+    gp = rs.jindo.Prover(fg, pd, polys_array(prv.ck.In), polys_array(prv.ck.MLWE), polys_array(prv.ck.Out), cdt_array(prv.ecd))
+    gp.SetTwinSeed(prv.ecd.twin.base.seed)
+    gp.SetMlweSeed(prv.mlwe.base.seed, p.mlwe_std)
+    noise = {"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std, "mask_mlwe_std": p.mask_mlwe_std}
+    tb = rs.jindo.TapeBuilder(pd, len(prv.ecd.twin.tables[0]), noise, q, threads=1,
+                              seeds=[prv.ecd.cosac.base.seed, prv.ecd.cosac.rounded.base.seed, prv.rounded.base.seed])
+    rng = np.random.default_rng(N + length)
+    for it in range(2):
+        v = [int.from_bytes(rng.bytes(40), "little") % q for _ in range(length)]
+        pos0 = tape._pos
+        com_o, open_o = prv.commit(v)
+        clone = J.Tape(sd); clone.read(pos0)
+        tb.set_random_bytes(clone.read(tape._pos - pos0))
+        vm = fo.to_mont(v)
+        tb.start(vm, length, it)
+        T, _ = tb.wait(it)
+        B = rs.Batch(fg, 1, max(length, 8))
+        host = np.zeros((1, max(length, 8), fo.L), dtype=np.uint64); host[0, :length] = vm
+        B.upload(host)
+        com_g, open_g = gp.Commit(B, 0, length, T)
+        assert np.array_equal(com_g, polys_array(com_o)), it
+        for i in range(p.cols + 1):
+            for j in range(p.rows):
+                assert np.array_equal(open_g.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", it, i, j)
+            for j in range(p.mlwe + p.in_msis):
+                assert np.array_equal(open_g.MLWE(i, j), polys_array(open_o.MLWE[i][j])), ("MLWE", it, i, j)
