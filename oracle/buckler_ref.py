@@ -122,6 +122,34 @@ class NTTChecker:
         return self.ntt.inv(self.f.vec_scalar_mul(np.ascontiguousarray(v[::-1]), self.scale))
 
 
+def mod_inverse(x, m):
+    """linear.go:75-92 (extended Euclid on uint64; the result is reduced mod m)"""
+    x %= m
+    a, b, u, v = x, m, 1, 0
+    while b != 0:
+        qq = a // b
+        a, b = b, a - qq * b
+        u, v = v, (u - qq * v) % (1 << 64)          # uint64 wrap-around as in the reference
+    if a != 1:
+        raise ValueError("modular inverse does not exist")
+    return u % m
+
+
+class AutChecker:
+    """linear.go:46-73: X -> X^idx on coefficient (is_ntt False) or NTT-slot (True) vectors; the transpose is the
+    automorphism with idx^-1 mod 2N (cyclotomic.go:29-82)."""
+
+    def __init__(self, field, rank, idx, is_ntt):
+        self.f, self.rank, self.idx, self.is_ntt = field, rank, idx, is_ntt
+        self.idx_inv = mod_inverse(idx, 2 * rank)
+
+    def transform(self, v):
+        return self.f.aut(np.ascontiguousarray(v), self.idx, self.is_ntt)
+
+    def transpose(self, v):
+        return self.f.aut(np.ascontiguousarray(v), self.idx_inv, self.is_ntt)
+
+
 class Context:
     def __init__(self, q, rank, pw_cnt, w_cnt):
         self.q, self.rank, self.pw_cnt, self.w_cnt = q, rank, pw_cnt, w_cnt
@@ -132,6 +160,27 @@ class Context:
         self.sumcheck_constraints, self.sumcheck_sums = [], []
         self.lin_checkers, self.lin_constraints = [], {}
         self.inf_dcmp_bound, self.inf_dcmp_witness = {}, {}
+        self.two_dcmp_bound, self.two_dcmp_base, self.two_dcmp_mask, self.two_dcmp_witness = {}, {}, {}, {}
+
+    def add_sumcheck_constraint(self, c, total):
+        """context.go:84-94"""
+        self.sumcheck_constraints.append(c)
+        self.sumcheck_sums.append(total)
+        self.sumcheck_max_rank = max(self.sumcheck_max_rank, c.max_rank(self.rank))
+
+    def add_sq_two_norm_constraint(self, w, bound):
+        """context.go:165-196: one decomposition witness, two public witnesses (base, mask), a binary constraint
+        wDcmp^2 - mask * wDcmp = 0 and the sum-check constraint sum(w^2 - base * wDcmp) = 0."""
+        q = self.q
+        wd = self.w_cnt; self.w_cnt += 1
+        pw_base, pw_mask = self.pw_cnt, self.pw_cnt + 1; self.pw_cnt += 2
+        self.two_dcmp_bound[w], self.two_dcmp_base[w], self.two_dcmp_mask[w], self.two_dcmp_witness[w] = bound, pw_base, pw_mask, wd
+        c = ArithmeticConstraint()
+        c.add_term_with_const(1, None, wd, wd); c.add_term_with_const(q - 1, pw_mask, wd)
+        self.add_arithmetic_constraint(c)
+        c = ArithmeticConstraint()
+        c.add_term_with_const(1, None, w, w); c.add_term_with_const(q - 1, pw_base, wd)
+        self.add_sumcheck_constraint(c, 0)
 
     def add_arithmetic_constraint(self, c):
         self.arith_constraints.append(c)
@@ -294,6 +343,19 @@ class Prover:
                 d = decompose_big(w[wid][i], base, q)
                 for j, x in enumerate(wds):
                     w[x][i] = d[j] % q
+        sq_nm = 0                                     # (not reset between constraints, like the reference: prover.go:88)
+        for wid, bound in ctx.two_dcmp_bound.items():
+            base = decompose_base(bound)                # prover.go:88-110
+            pb, pm = ctx.two_dcmp_base[wid], ctx.two_dcmp_mask[wid]
+            for i, b in enumerate(base):
+                pw[pb][i] = b % q
+                pw[pm][i] = 1
+            for i in range(N):
+                sq_nm += w[wid][i] * w[wid][i]
+            sq_nm %= q
+            d = decompose_big(sq_nm, base, q)
+            for i, x in enumerate(d):
+                w[ctx.two_dcmp_witness[wid]][i] = x % q
         self.trace["w_full"], self.trace["pw_full"] = w, pw
         tr = Transcript(CHAL_NAMES)
         pw_ecd_ntt = [C.emb_ntt.fwd(encode(C, f.to_mont(v))) for v in pw]
@@ -316,8 +378,13 @@ class Prover:
             tr.bind("arithBatchConst", J.commitment_write_raw(C.jp, coms[idx]))
             tr.bind("arithBatchConst", _marshal(lin_mask_sum, q))
             idx += 1
-        if ctx.has_sum():
-            raise NotImplementedError("sumcheck constraints are not part of the restated circuits")
+        sum_mask = sum_mask_sum = None
+        if ctx.has_sum():                              # prover.go:223-238
+            sum_mask, sum_mask_sum = self._sum_check_mask(ctx.sumcheck_max_rank)
+            com_polys[idx], coms[idx], opens[idx] = self._commit(sum_mask[:ctx.sumcheck_max_rank])
+            tr.bind("arithBatchConst", J.commitment_write_raw(C.jp, coms[idx]))
+            tr.bind("arithBatchConst", _marshal(sum_mask_sum, q))
+            idx += 1
         arith_bc = _set_bytes(tr.compute_challenge("arithBatchConst"), q)
         if ctx.has_arith():
             terms, coeffs = ctx.terms(ctx.arith_constraints)
@@ -334,12 +401,27 @@ class Prover:
                 com_polys[idx], coms[idx], opens[idx] = self._commit(poly)
                 tr.bind("evalPoint", J.commitment_write_raw(C.jp, coms[idx]))
                 idx += 1
-        tr.compute_challenge("sumCheckBatchConst")
+        sum_bc = _set_bytes(tr.compute_challenge("sumCheckBatchConst"), q)
+        if ctx.has_sum():                              # prover.go:307-331, :461-485
+            terms, coeffs = ctx.terms(ctx.sumcheck_constraints)
+            bcm = self._mont(sum_bc)
+            ev = f.eval_circuit(pw_ecd_ntt, w_ntt, terms, f.to_mont(coeffs), bcm, C.emb_rank)
+            ev = f.vec_scalar_mul(ev, bcm)
+            ev = f.vec_add(C.emb_ntt.inv(ev), sum_mask)
+            quo, rem = f.quorem_vanishing(ev, N)
+            rem_lo = rem[1:N].copy()
+            R = C.jp.rank
+            rem_hi = np.zeros((R, f.L), dtype=np.uint64)
+            rem_hi[R - (N - 1):] = rem_lo
+            for poly in (quo[:ctx.sumcheck_max_rank - N].copy(), rem_lo, rem_hi):
+                com_polys[idx], coms[idx], opens[idx] = self._commit(poly)
+                tr.bind("evalPoint", J.commitment_write_raw(C.jp, coms[idx]))
+                idx += 1
         x = _set_bytes(tr.compute_challenge("evalPoint"), q)
         evals, pf = C.poly_prover.evaluate(x, com_polys, coms, opens)
-        return {"Witness": coms, "LinCheckMaskSum": lin_mask_sum, "SumCheckMaskSum": None, "Evals": evals,
+        return {"Witness": coms, "LinCheckMaskSum": lin_mask_sum, "SumCheckMaskSum": sum_mask_sum, "Evals": evals,
                 "EvalProof": pf, "_eval_point": x, "_opens": opens, "_com_polys": com_polys,
-                "_chal": {"arith": arith_bc, "lin_bc": lin_bc, "lin_c": lin_c}}
+                "_chal": {"arith": arith_bc, "lin_bc": lin_bc, "lin_c": lin_c, "sum_bc": sum_bc}}
 
     def _lin_check(self, bc, lin_c, mask, w_ntt):
         """prover.go:406-459"""
@@ -397,6 +479,10 @@ class Verifier:
         """Verifier.Verify (verifier.go:29-189)"""
         C = self.C; ctx = C.ctx; f = C.f; q = C.q; N = ctx.rank
         pw = [list(v) for v in pw_vals] + [[0] * N for _ in range(ctx.pw_cnt - len(pw_vals))]
+        for wid, bound in ctx.two_dcmp_bound.items():          # verifier.go:48-57
+            for i, b in enumerate(decompose_base(bound)):
+                pw[ctx.two_dcmp_base[wid]][i] = b % q
+                pw[ctx.two_dcmp_mask[wid]][i] = 1
         tr = Transcript(CHAL_NAMES)
         for i in range(ctx.w_cnt):
             if i not in ctx.w_second:
@@ -409,10 +495,16 @@ class Verifier:
             tr.bind("arithBatchConst", J.commitment_write_raw(C.jp, pf["Witness"][idx]))
             tr.bind("arithBatchConst", _marshal(pf["LinCheckMaskSum"], q))
             idx += 1
+        sum_mask_eval = None
+        if ctx.has_sum():                              # verifier.go:128-136
+            sum_mask_eval = pf["Evals"][idx]
+            tr.bind("arithBatchConst", J.commitment_write_raw(C.jp, pf["Witness"][idx]))
+            tr.bind("arithBatchConst", _marshal(pf["SumCheckMaskSum"], q))
+            idx += 1
         arith_bc = _set_bytes(tr.compute_challenge("arithBatchConst"), q)
         lin_bc = _set_bytes(tr.compute_challenge("linCheckBatchConst"), q)
         lin_c = _set_bytes(tr.compute_challenge("linCheckConst"), q)
-        tr.compute_challenge("sumCheckBatchConst")
+        sum_bc = _set_bytes(tr.compute_challenge("sumCheckBatchConst"), q)
         for i in range(idx, len(pf["Witness"])):
             tr.bind("evalPoint", J.commitment_write_raw(C.jp, pf["Witness"][i]))
         x = _set_bytes(tr.compute_challenge("evalPoint"), q)
@@ -444,6 +536,16 @@ class Verifier:
                     ev = (ev * lin_bc + term) % q
             ev = (ev * lin_bc + lin_mask_eval) % q
             test = (quo_e * vanish + lo_e * x + pf["LinCheckMaskSum"]) % q
+            if ev != test:
+                return False
+            idx += 3
+        if ctx.has_sum():                              # verifier.go:295-315
+            quo_e, lo_e, hi_e = evals[idx], evals[idx + 1], evals[idx + 2]
+            if hi_e != pow(x, C.jp.rank - (N - 1), q) * lo_e % q:
+                return False
+            ev = self._eval_circuit(sum_bc, ctx.sumcheck_constraints, evals, pw_evals)
+            ev = (ev * sum_bc + sum_mask_eval) % q
+            test = (quo_e * vanish + lo_e * x + pf["SumCheckMaskSum"]) % q
             if ev != test:
                 return False
             idx += 3
@@ -481,6 +583,24 @@ def public_key_circuit(rank):
         ctx.add_inf_norm_constraint(0, 1)
         ctx.add_inf_norm_constraint(2, 1)
     return define, 2, 4
+
+
+def norm_aut_circuit(rank, aut_idx, sq_bound):
+    """A circuit over the remaining constraint kinds of buckler (none of the shipped examples uses them; BASELINE
+    configs[3] names them): an automorphism linear constraint in the coefficient domain and one in the NTT domain
+    (NewAutChecker, linear.go:54-73), a squared two-norm constraint (AddSqTwoNormConstraint, context.go:165-196: binary
+    decomposition + sum-check) and an explicit sum-check constraint (AddSumCheckConstraint, context.go:84-94).
+    witnesses: S(0) SAut(1) SNTT(2) SNTTAut(3); no declared public witness."""
+    def define(ctx, f):
+        ctx.add_linear_constraint(1, 0, AutChecker(f, rank, aut_idx, False))      # SAut = Aut(S)
+        ctx.add_linear_constraint(2, 0, NTTChecker(f, rank))                      # SNTT = NTT(S)
+        ctx.add_linear_constraint(3, 2, AutChecker(f, rank, aut_idx, True))       # SNTTAut = AutNTT(SNTT)
+        ctx.add_inf_norm_constraint(0, 1)                                         # ternary S
+        ctx.add_sq_two_norm_constraint(0, sq_bound)                               # |S|_2^2 <= bound
+        c = ArithmeticConstraint()                                                # sum_i (S_i^3 - S_i) = 0  (true for ternary S)
+        c.add_term_with_const(1, None, 0, 0, 0); c.add_term_with_const(ctx.q - 1, None, 0)
+        ctx.add_sumcheck_constraint(c, 0)
+    return define, 0, 4
 
 
 def ciphertext_circuit(rank, delta, plaintext_modulus, err_bound):

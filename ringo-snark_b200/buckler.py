@@ -18,7 +18,10 @@ in call order) exactly like the tapes of include/ringo_jindo.h.
 
 `circuit` is the compiled description a Go caller gets from buckler.Compile (plain data):
   rank, emb_rank, w_cnt, pw_cnt, arith_max_rank, arith_terms [(constraint, coeff_idx, pw|-1, [w..])],
-  arith_coeffs [ints], lin [(checker_kind, [(w_out, w_in), ...])] with checker_kind == "ntt".
+  arith_coeffs [ints], lin [(checker, [(w_out, w_in), ...])] with checker == "ntt" (nttChecker, linear.go:20-43) or
+  ("aut", idx_inv, is_ntt) (autChecker, linear.go:46-73: TransposeTo is AutTo with idx^-1 mod 2N),
+  and, when the circuit has sum-check constraints (context.go:84-94; AddSqTwoNormConstraint adds one, :165-196),
+  sum_terms / sum_coeffs in the same flattened form plus sum_max_rank.
 """
 import ctypes
 import hashlib
@@ -130,7 +133,8 @@ class Prover:
         for k in range(pc):
             check(L.rs_batch_copy(pw_ntt.h, k, 0, ntt.h, wc + k, 0, E))
         mark("encode_ntt")
-        n_com = wc + (1 if c["arith_terms"] else 0) + (4 if c["lin"] else 0)
+        has_sum = bool(c.get("sum_terms"))
+        n_com = wc + (1 if c["arith_terms"] else 0) + (4 if c["lin"] else 0) + (4 if has_sum else 0)
         coms, opens, views = [None] * n_com, [None] * n_com, [None] * n_com
         for i in range(wc):                              # first-round witnesses (no second-round witnesses here)
             coms[i], opens[i] = self._commit(ecd, i, N + 1, next(tapes))
@@ -139,17 +143,27 @@ class Prover:
         tr.compute_challenge("projConst")
         mark("commit")
         idx = wc
-        work = Batch(f, 8, E)                            # 0 mask, 1 eval, 2 quo, 3 rem, 4 term, 5 linEcd, 6 linEcdTr, 7 scratch
-        lin_mask_sum = None
+        work = Batch(f, 8, E)                            # 0 linCheckMask, 1 eval, 2 quo, 3 rem, 4 term, 5 sumCheckMask, 6-7 scratch
+        lin_mask_sum = sum_mask_sum = None
+        masks = iter(zip(rand["mask"], rand.get("mask_sum", [])))
         if c["lin"]:
-            mask = rand["mask"][0]
+            mask, lin_mask_sum = next(masks)
             host = np.zeros((1, E, self.L), dtype=np.uint64)
             host[0, :2 * N] = self.mont_many(mask)
             work.upload(host, 0)
-            lin_mask_sum = rand["mask_sum"][0]
             coms[idx], opens[idx] = self._commit(work, 0, 2 * N, next(tapes)); views[idx] = (work, 0, 2 * N)
             tr.bind("arithBatchConst", JH.commitment_write_raw(self.jp, coms[idx]))
             tr.bind("arithBatchConst", lin_mask_sum.to_bytes(8 * self.L, "big"))
+            idx += 1
+        if has_sum:                                      # sumCheckMask (prover.go:223-238, :381-397)
+            mask, sum_mask_sum = next(masks)
+            SR = c["sum_max_rank"]
+            host = np.zeros((1, E, self.L), dtype=np.uint64)
+            host[0, :SR] = self.mont_many(mask)
+            work.upload(host, 5)
+            coms[idx], opens[idx] = self._commit(work, 5, SR, next(tapes)); views[idx] = (work, 5, SR)
+            tr.bind("arithBatchConst", JH.commitment_write_raw(self.jp, coms[idx]))
+            tr.bind("arithBatchConst", sum_mask_sum.to_bytes(8 * self.L, "big"))
             idx += 1
         mark("commit")
         arith_bc = int.from_bytes(tr.compute_challenge("arithBatchConst"), "big") % q
@@ -185,9 +199,12 @@ class Prover:
             check(L.rs_batch_zero(work.h, 1, 0, E))                                      # eval = 0
             bcm = self.mont(lin_bc)
             for kind, pairs in c["lin"]:
-                assert kind == "ntt"
-                check(L.rs_reverse_scale(lv.h, 1, lv.h, 0, _p(self.mont(N))))            # TransposeTo (linear.go:38-43)
-                check(L.rs_ntt_inverse(self.neg.h, lv.h, 1, lv.h, 1, 1))
+                if kind == "ntt":
+                    check(L.rs_reverse_scale(lv.h, 1, lv.h, 0, _p(self.mont(N))))        # nttChecker.TransposeTo (linear.go:38-43)
+                    check(L.rs_ntt_inverse(self.neg.h, lv.h, 1, lv.h, 1, 1))
+                else:
+                    _, idx_inv, is_ntt = kind                                            # autChecker.TransposeTo (linear.go:69-73)
+                    check(L.rs_aut(lv.h, 1, lv.h, 0, 1, int(idx_inv), 1 if is_ntt else 0))
                 check(L.rs_ntt_inverse_embed(self.enc.h, le.h, 1, lv.h, 1, 1, 1))
                 check(L.rs_ntt_forward(self.emb.h, le.h, 1, le.h, 1, 1))                 # linCheckEcdTr
                 for (w_out, w_in) in pairs:
@@ -211,12 +228,37 @@ class Prover:
                 coms[idx], opens[idx] = self._commit(b, p, ln, next(tapes)); views[idx] = (b, p, ln)
                 tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx]))
                 idx += 1
-        tr.compute_challenge("sumCheckBatchConst")
+        sum_bc = int.from_bytes(tr.compute_challenge("sumCheckBatchConst"), "big") % q
+        if has_sum:                                      # sumCheck (prover.go:307-331, :461-485)
+            T = (capi.Term * len(c["sum_terms"]))()
+            for k, (ci, co, pw, ws) in enumerate(c["sum_terms"]):
+                T[k].constraint, T[k].coeff, T[k].pw, T[k].n_w = ci, co, pw, len(ws)
+                for j, xw in enumerate(ws):
+                    T[k].w[j] = xw
+            coeffs = self.mont_many(c["sum_coeffs"])
+            bcm = self.mont(sum_bc)
+            check(L.rs_eval_circuit(work.h, 1, pw_ntt.h, w_ntt.h, T, len(c["sum_terms"]), _p(coeffs), len(coeffs), _p(bcm)))
+            check(L.rs_vec_scalar_mul(work.h, 1, work.h, 1, _p(bcm), 1))
+            check(L.rs_ntt_inverse(self.emb.h, work.h, 1, work.h, 1, 1))
+            check(L.rs_vec_add(work.h, 1, work.h, 1, work.h, 5, 1))                      # + sumCheckMask
+            qs = Batch(f, 2, E)
+            check(L.rs_quorem_vanishing(qs.h, 0, qs.h, 1, work.h, 1, N))
+            Rk = self.jp.rank
+            rems = Batch(f, 2, max(Rk, N))
+            check(L.rs_batch_zero(rems.h, 0, 0, rems.rank)); check(L.rs_batch_zero(rems.h, 1, 0, rems.rank))
+            check(L.rs_batch_copy(rems.h, 0, 0, qs.h, 1, 1, N - 1))
+            check(L.rs_batch_copy(rems.h, 1, Rk - (N - 1), qs.h, 1, 1, N - 1))
+            keep += [qs, rems]
+            mark("sum_check")
+            for (b, p, ln) in ((qs, 0, c["sum_max_rank"] - N), (rems, 0, N - 1), (rems, 1, Rk)):
+                coms[idx], opens[idx] = self._commit(b, p, ln, next(tapes)); views[idx] = (b, p, ln)
+                tr.bind("evalPoint", JH.commitment_write_raw(self.jp, coms[idx]))
+                idx += 1
         x = int.from_bytes(tr.compute_challenge("evalPoint"), "big") % q
         mark("commit")
         evals, pf = self.evaluate(x, views, coms, opens)
         mark("evaluate")
-        return {"Witness": [cm.tolist() for cm in coms], "LinCheckMaskSum": lin_mask_sum, "SumCheckMaskSum": None,
+        return {"Witness": [cm.tolist() for cm in coms], "LinCheckMaskSum": lin_mask_sum, "SumCheckMaskSum": sum_mask_sum,
                 "Evals": evals, "EvalProof": pf, "_eval_point": x}
 
     def evaluate(self, x, views, coms, opens):

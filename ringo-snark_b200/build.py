@@ -50,7 +50,7 @@ def build(force=False, verbose=False, defines=(), tag=""):
         o = os.path.join(OBJ, os.path.basename(s)[:-4] + ".host.o")
         objs.append(o)
         if force or not _newer(o, [s] + hdrs):
-            jobs.append(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-pthread"]
+            jobs.append(["/usr/bin/g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off", "-pthread"]
                         + ["-D" + d for d in defines] + ["-c", s, "-o", o])
     if jobs:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

@@ -98,16 +98,46 @@ struct Aes256 {
         memcpy(out, s, 16);
     }
 #if defined(__x86_64__)
+    // 8 blocks at a time keeps the AES units' pipelines full (AESENC: latency 4, throughput 1-2 per cycle)
     __attribute__((target("aes,sse4.1"))) void encrypt8_ni(const uint8_t *in /* 8 blocks */, uint8_t *out) const {
-        __m128i b[8];
-        const __m128i k0 = _mm_load_si128((const __m128i *)rk[0]);
-        for (int i = 0; i < 8; i++) b[i] = _mm_xor_si128(_mm_loadu_si128((const __m128i *)(in + 16 * i)), k0);
-        for (int r = 1; r < 14; r++) {
-            const __m128i k = _mm_load_si128((const __m128i *)rk[r]);
-            for (int i = 0; i < 8; i++) b[i] = _mm_aesenc_si128(b[i], k);
+        const __m128i *k = (const __m128i *)rk;
+        __m128i b0 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 0), k[0]), b1 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 1), k[0]);
+        __m128i b2 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 2), k[0]), b3 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 3), k[0]);
+        __m128i b4 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 4), k[0]), b5 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 5), k[0]);
+        __m128i b6 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 6), k[0]), b7 = _mm_xor_si128(_mm_loadu_si128((const __m128i *)in + 7), k[0]);
+#define RS_AES_ROUND(r)                                                                                               \
+        b0 = _mm_aesenc_si128(b0, k[r]); b1 = _mm_aesenc_si128(b1, k[r]); b2 = _mm_aesenc_si128(b2, k[r]); b3 = _mm_aesenc_si128(b3, k[r]); \
+        b4 = _mm_aesenc_si128(b4, k[r]); b5 = _mm_aesenc_si128(b5, k[r]); b6 = _mm_aesenc_si128(b6, k[r]); b7 = _mm_aesenc_si128(b7, k[r]);
+        RS_AES_ROUND(1) RS_AES_ROUND(2) RS_AES_ROUND(3) RS_AES_ROUND(4) RS_AES_ROUND(5) RS_AES_ROUND(6) RS_AES_ROUND(7)
+        RS_AES_ROUND(8) RS_AES_ROUND(9) RS_AES_ROUND(10) RS_AES_ROUND(11) RS_AES_ROUND(12) RS_AES_ROUND(13)
+#undef RS_AES_ROUND
+        __m128i *o = (__m128i *)out;
+        _mm_storeu_si128(o + 0, _mm_aesenclast_si128(b0, k[14])); _mm_storeu_si128(o + 1, _mm_aesenclast_si128(b1, k[14]));
+        _mm_storeu_si128(o + 2, _mm_aesenclast_si128(b2, k[14])); _mm_storeu_si128(o + 3, _mm_aesenclast_si128(b3, k[14]));
+        _mm_storeu_si128(o + 4, _mm_aesenclast_si128(b4, k[14])); _mm_storeu_si128(o + 5, _mm_aesenclast_si128(b5, k[14]));
+        _mm_storeu_si128(o + 6, _mm_aesenclast_si128(b6, k[14])); _mm_storeu_si128(o + 7, _mm_aesenclast_si128(b7, k[14]));
+    }
+#endif
+#if defined(__x86_64__)
+    // p[0 .. 16 n) ^= keystream for the counters ctr, ctr+1, ... (128-bit big endian), n a multiple of 8; returns through
+    // hi/lo the counter after the last block
+    __attribute__((target("aes,sse4.1,ssse3"))) void ctr_xor8_ni(uint8_t *p, size_t n, uint64_t &hi, uint64_t &lo) const {
+        const __m128i *k = (const __m128i *)rk;
+        const __m128i bswap = _mm_set_epi8(8, 9, 10, 11, 12, 13, 14, 15, 0, 1, 2, 3, 4, 5, 6, 7);   // two u64 -> big-endian bytes (hi first)
+        for (size_t i = 0; i < n; i += 8, p += 128) {
+            __m128i b[8];
+            for (int j = 0; j < 8; j++) {
+                const uint64_t l = lo + (uint64_t)j, h = hi + (l < lo);
+                b[j] = _mm_xor_si128(_mm_shuffle_epi8(_mm_set_epi64x((long long)l, (long long)h), bswap), k[0]);
+            }
+            { const uint64_t l = lo + 8; hi += (l < lo); lo = l; }
+            for (int r = 1; r < 14; r++)
+                for (int j = 0; j < 8; j++) b[j] = _mm_aesenc_si128(b[j], k[r]);
+            for (int j = 0; j < 8; j++) {
+                const __m128i ks = _mm_aesenclast_si128(b[j], k[14]);
+                _mm_storeu_si128((__m128i *)p + j, _mm_xor_si128(_mm_loadu_si128((const __m128i *)p + j), ks));
+            }
         }
-        const __m128i kl = _mm_load_si128((const __m128i *)rk[14]);
-        for (int i = 0; i < 8; i++) _mm_storeu_si128((__m128i *)(out + 16 * i), _mm_aesenclast_si128(b[i], kl));
     }
 #endif
     // n blocks
@@ -160,20 +190,36 @@ struct Uniform {
         ptr = BUF;
         ks_pos = 16;
     }
-    void bump() {
-        for (int i = 15; i >= 0; i--) if (++ctr[i]) break;
+    inline void bump() {                 // 128-bit big-endian increment
+        if (__builtin_expect(++ctr[15] != 0, 1)) return;
+        for (int i = 14; i >= 0; i--) if (++ctr[i]) break;
     }
     // XORKeyStream(p, p)
     void xor_stream(uint8_t *p, size_t n) {
         size_t i = 0;
         while (i < n && ks_pos < 16) p[i++] ^= ks[ks_pos++];
+#if defined(__x86_64__)
+        if (aes.ni && n - i >= 128) {
+            uint64_t hi = 0, lo = 0;
+            for (int b = 0; b < 8; b++) { hi = (hi << 8) | ctr[b]; lo = (lo << 8) | ctr[8 + b]; }
+            const size_t blocks = ((n - i) / 128) * 8;
+            aes.ctr_xor8_ni(p + i, blocks, hi, lo);
+            for (int b = 7; b >= 0; b--) { ctr[b] = (uint8_t)hi; hi >>= 8; ctr[8 + b] = (uint8_t)lo; lo >>= 8; }
+            i += 16 * blocks;
+        }
+#endif
         alignas(16) uint8_t cb[128 * 16], kb[128 * 16];
         while (n - i >= 16) {
             size_t blocks = (n - i) / 16;
             if (blocks > 128) blocks = 128;
             for (size_t b = 0; b < blocks; b++) { memcpy(cb + 16 * b, ctr, 16); bump(); }
             aes.encrypt_blocks(cb, kb, blocks);
-            for (size_t b = 0; b < 16 * blocks; b++) p[i + b] ^= kb[b];
+            for (size_t b = 0; b < 2 * blocks; b++) {           // 8 bytes at a time (p may be unaligned)
+                uint64_t x, y;
+                memcpy(&x, p + i + 8 * b, 8); memcpy(&y, kb + 8 * b, 8);
+                x ^= y;
+                memcpy(p + i + 8 * b, &x, 8);
+            }
             i += 16 * blocks;
         }
         if (i < n) {
@@ -279,7 +325,11 @@ struct Cosac {
             else { y_round = round(y) + 1; cmp = y_round >= -0.5; }
             if (cmp) {
                 const double r = base.sample_float();
-                if (r < exp(-((y_round + c_frac) * (y_round + c_frac) - y * y) / (2 * std_dev * std_dev))) return (int64_t)y_round;
+                const double z = ((y_round + c_frac) * (y_round + c_frac) - y * y) / (2 * std_dev * std_dev);   // test: r < exp(-z)
+                // same decision without the exponential when it cannot matter: r < 1 <= exp(-z) for z <= 0, and
+                // exp(-z) >= 1 - z, with a margin far above the rounding errors of both sides
+                if (z <= 0 || r < (1 - z) - 1e-12) return (int64_t)y_round;
+                if (r < exp(-z)) return (int64_t)y_round;
             }
         }
     }
@@ -287,7 +337,9 @@ struct Cosac {
         const double c_int = round(center);
         const double c_frac = c_int - center;
         const double r = base.sample_float();
-        if (r < exp(-(c_frac * c_frac) / (2 * std_dev * std_dev)) / (sqrt(2 * M_PI) * std_dev)) return (int64_t)c_int;
+        const double norm = sqrt(2 * M_PI) * std_dev;
+        // exp(.) <= 1 and the division is monotone: r >= 1 / norm decides the test below without the exponential
+        if (r < 1.0 / norm && r < exp(-(c_frac * c_frac) / (2 * std_dev * std_dev)) / norm) return (int64_t)c_int;
         return sample_round(c_frac, std_dev) + (int64_t)c_int;
     }
 };
@@ -380,6 +432,20 @@ bool set_random(const FieldHost &f, ByteSource &src, uint64_t *out) {
 }
 
 inline uint64_t div_mod64(uint64_t *x, int n, uint64_t y) {      // jindo/utils.go:12-18
+    if (y < (1ull << 32)) {
+        // the encoder's base is below 2^25: two 64-bit hardware divisions per limb instead of a 128-bit one
+        uint64_t r = 0;
+        for (int i = n - 1; i >= 0; i--) {
+            const uint64_t t1 = (r << 32) | (x[i] >> 32);
+            const uint64_t q1 = t1 / y;
+            r = t1 - q1 * y;
+            const uint64_t t0 = (r << 32) | (x[i] & 0xffffffffull);
+            const uint64_t q0 = t0 / y;
+            r = t0 - q0 * y;
+            x[i] = (q1 << 32) | q0;
+        }
+        return r;
+    }
     unsigned __int128 r = 0;
     for (int i = n - 1; i >= 0; i--) {
         const unsigned __int128 cur = (r << 64) | x[i];
@@ -467,7 +533,11 @@ void cosac_poly(const rs_tape_builder *b, Cosac &cs, const uint64_t *elems, int 
     for (int i = 0; i < cnt; i++) {
         uint64_t c[RS_MAX_NL_HOST / 2];
         from_mont(b->f, (uint32_t *)c, (const uint32_t *)(elems + (size_t)i * L));     // Slice(): canonical limbs
-        for (int j = 0; j < p.exp - 1; j++) digits[j * slots + i] = div_mod64(c, L, p.base);
+        int top = L;                                             // limbs above `top` are zero: the quotient shrinks
+        for (int j = 0; j < p.exp - 1; j++) {
+            while (top > 1 && c[top - 1] == 0) top--;
+            digits[j * slots + i] = div_mod64(c, top, p.base);
+        }
         digits[(p.exp - 1) * slots + i] = c[0];
     }
     for (int i = 0; i < p.exp; i++) {

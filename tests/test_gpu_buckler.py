@@ -125,7 +125,7 @@ def test_prover_pipeline(rs, name, logN):
     assert np.array_equal(P[1].Coeffs, eval_o)
 
 
-@pytest.mark.parametrize("circuit,name,N", [("mult", "zp128", 256), ("pk", "zp220", 256), ("ct", "zp240", 256)])
+@pytest.mark.parametrize("circuit,name,N", [("mult", "zp128", 256), ("pk", "zp220", 256), ("ct", "zp240", 256), ("norm", "zp220", 256)])
 def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N):
     """buckler.Prover.Prove end to end on the GPU (ringo-snark_b200/buckler.py: host transcript, device
     polynomials, Jindo commits/evaluation through the C ABI) against the oracle's Prove on the same
@@ -148,7 +148,11 @@ def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N):
     terms, coeffs = ctx.terms(ctx.arith_constraints)
     desc = {"rank": N, "emb_rank": C.emb_rank, "w_cnt": ctx.w_cnt, "pw_cnt": ctx.pw_cnt, "arith_max_rank": ctx.arith_max_rank,
             "arith_terms": terms, "arith_coeffs": coeffs,
-            "lin": [("ntt", ctx.lin_constraints[id(chk)]) for chk in ctx.lin_checkers]}
+            "lin": [("ntt" if isinstance(chk, B.NTTChecker) else ("aut", chk.idx_inv, chk.is_ntt), ctx.lin_constraints[id(chk)])
+                    for chk in ctx.lin_checkers]}
+    if ctx.has_sum():                                # sum-check rounds ("norm": automorphism + two-norm + explicit sum-check)
+        desc["sum_terms"], desc["sum_coeffs"] = ctx.terms(ctx.sumcheck_constraints)
+        desc["sum_max_rank"] = ctx.sumcheck_max_rank
     prv = C.poly_prover
     gp = rs.jindo.Prover(fg, params_dict(C.jp, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
                          polys_array(prv.ck.Out), cdt_array(prv.ecd), crs=b"Buckler!")
@@ -160,6 +164,7 @@ def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N):
     assert pf_g["_eval_point"] == pf_o["_eval_point"]
     assert pf_g["Witness"] == [[[list(map(int, l)) for l in poly] for poly in cm] for cm in pf_o["Witness"]]
     assert pf_g["Evals"] == pf_o["Evals"] and pf_g["LinCheckMaskSum"] == pf_o["LinCheckMaskSum"]
+    assert pf_g["SumCheckMaskSum"] == pf_o["SumCheckMaskSum"]
     for k in ("Partial", "Encode", "MLWE", "InCommit"):
         assert pf_g["EvalProof"][k] == [[list(map(int, l)) for l in poly] for poly in pf_o["EvalProof"][k]], k
     assert pf_g["EvalProof"]["PartialMask"] == [list(map(int, l)) for l in pf_o["EvalProof"]["PartialMask"]]

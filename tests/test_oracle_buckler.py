@@ -65,7 +65,25 @@ def ct_witness(q, N, seed):
     return [g(c0), g(c1)], [g(skn), g(mn), [x % q for x in m], g(en), [x % q for x in e]]
 
 
+AUT_IDX = 5                              # the Galois element of the automorphism constraints (odd, generates rotations)
+
+
+def norm_aut_witness(q, N, seed):
+    """S ternary; SAut = S(X^idx) on coefficients (cyclotomic.go:49-64), SNTT = NTT(S), SNTTAut = the same automorphism on
+    NTT slots (:66-82).  Returns the declared witnesses; the two-norm decomposition witness is filled by Prove."""
+    f = oracle.Field(q)
+    rng = random.Random(seed)
+    ntt = oracle.NTT(f, N.bit_length() - 1, True)
+    S = [rng.randrange(3) - 1 for _ in range(N)]
+    Sm = f.to_mont(S)
+    g = lambda a: f.from_mont(a)
+    Sn = ntt.fwd(Sm)
+    return [], [[x % q for x in S], g(f.aut(Sm, AUT_IDX, False)), g(Sn), g(f.aut(Sn, AUT_IDX, True))]
+
+
 def circuit_and_witness(circuit, q, N, seed):
+    if circuit == "norm":
+        return B.norm_aut_circuit(N, AUT_IDX, N), norm_aut_witness(q, N, seed)
     if circuit == "ct":
         delta, err_bound = ct_params(q, N)
         return B.ciphertext_circuit(N, delta, BFV_T, err_bound), ct_witness(q, N, seed)
@@ -74,7 +92,36 @@ def circuit_and_witness(circuit, q, N, seed):
     return B.mult_circuit(N), mult_witness(q, N, seed)
 
 
-@pytest.mark.parametrize("circuit,name,N", [("pk", "zp220", 256), ("mult", "zp128", 256), ("ct", "zp240", 256)])
+def test_aut_checker_is_the_adjoint():
+    """autChecker.TransposeTo is the transpose of TransformTo (what linCheck relies on, linear.go:63-73):
+    <u, Aut(v)> == <Aut^T(u), v> in both domains, and the NTT-domain automorphism commutes with the NTT."""
+    q = pyref.modulus("zp220"); N = 64
+    f = oracle.Field(q)
+    rng = random.Random(1)
+    u = [rng.randrange(q) for _ in range(N)]; v = [rng.randrange(q) for _ in range(N)]
+    ntt = oracle.NTT(f, 6, True)
+    for is_ntt in (False, True):
+        chk = B.AutChecker(f, N, AUT_IDX, is_ntt)
+        assert chk.idx * chk.idx_inv % (2 * N) == 1
+        a = f.from_mont(chk.transform(f.to_mont(v))); b = f.from_mont(chk.transpose(f.to_mont(u)))
+        assert sum(x * y for x, y in zip(u, a)) % q == sum(x * y for x, y in zip(b, v)) % q
+    vm = f.to_mont(v)
+    assert np.array_equal(ntt.fwd(f.aut(vm, AUT_IDX, False)), f.aut(ntt.fwd(vm), AUT_IDX, True))
+
+
+def test_norm_aut_circuit_metadata():
+    N = 256
+    q = pyref.modulus("zp220")
+    define, n_pw, n_w = B.norm_aut_circuit(N, AUT_IDX, N)
+    ctx = B.Context(q, N, n_pw, n_w)
+    define(ctx, oracle.Field(q))
+    # 4 declared + 1 two-norm decomposition witness; 2 public (base, mask); sum-check adds 4 commitments
+    assert (ctx.w_cnt, ctx.pw_cnt) == (5, 2) and len(ctx.lin_checkers) == 3 and len(ctx.sumcheck_constraints) == 2
+    assert ctx.batch() == 5 + 1 + 4 + 4
+    assert ctx.sumcheck_max_rank == 3 * N + 1 and ctx.commit_rank() == 3 * N + 1 + N + 1
+
+
+@pytest.mark.parametrize("circuit,name,N", [("pk", "zp220", 256), ("mult", "zp128", 256), ("ct", "zp240", 256), ("norm", "zp220", 256)])
 def test_prove_verify(circuit, name, N):
     q = pyref.modulus(name)
     (define, n_pw, n_w), (pw, w) = circuit_and_witness(circuit, q, N, 3)
@@ -84,6 +131,17 @@ def test_prove_verify(circuit, name, N):
     assert len(pf["Witness"]) == C.ctx.batch() == len(pf["Evals"])
     assert B.Verifier(C).verify(pw, pf)
     if circuit == "ct":                              # (43 commits per proof: the negative cases run on the two smaller circuits)
+        return
+    if circuit == "norm":
+        assert pf["SumCheckMaskSum"] is not None
+        # a non-ternary coefficient breaks the explicit sum-check (and the ternary constraint); a wrong automorphism image the linear check
+        for wi, pos in ((0, 7), (1, 3), (3, 9)):
+            w_bad = [list(v) for v in w]
+            w_bad[wi][pos] = (w_bad[wi][pos] + 2) % q
+            assert not B.Verifier(C).verify(pw, B.Prover(C, tape).prove(pw, w_bad)), wi
+        # a tampered sum-check mask sum is rejected
+        pf2 = dict(pf); pf2["SumCheckMaskSum"] = (pf["SumCheckMaskSum"] + 1) % q
+        assert not B.Verifier(C).verify(pw, pf2)
         return
     # a witness violating the arithmetic constraint is rejected
     w_bad = [list(v) for v in w]
