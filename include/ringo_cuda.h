@@ -153,6 +153,17 @@ int rs_reverse_scale(rs_batch *out, size_t out_poly, const rs_batch *v, size_t v
 /* Poly.Evaluate (math/bigpoly/poly.go:64-76) of the first n_elems coefficients at x; result to host */
 int rs_poly_evaluate(const rs_batch *p, size_t poly, size_t n_elems, const uint64_t *x, uint64_t *result);
 
+/* ---- multi-GPU plumbing (SURVEY 8b "rs_allgather_commitments", 8e) ---------------------------------------------------
+ * One process per GPU.  The only exchanges of the path are tiny: per-shard commitments / evaluations into the host
+ * Fiat-Shamir transcript, and the InCommit slices of a column-sharded Commit (ringo_jindo.h).  NCCL is loaded at run time.
+ * A communicator can come from the caller (any ncclComm_t) or be made here: rank 0 calls rs_nccl_unique_id, ships the 128
+ * bytes to the other ranks over its own control plane, and every rank calls rs_nccl_comm_create after rs_init(device). */
+int rs_nccl_unique_id(uint8_t *id128);
+int rs_nccl_comm_create(const uint8_t *id128, int rank, int world, void **comm_out);
+void rs_nccl_comm_destroy(void *comm);
+/* every rank contributes n words and receives world * n words, rank-major (host buffers) */
+int rs_allgather_u64(void *comm, int rank, int world, const uint64_t *host_in, size_t n, uint64_t *host_out);
+
 #ifdef __cplusplus
 }
 #endif

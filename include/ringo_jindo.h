@@ -132,6 +132,17 @@ int rs_jindo_commit_columns(rs_jindo *j, const rs_batch *v, size_t v_poly, size_
                             int col_begin, int col_end, rs_opening **open);
 int rs_jindo_outer_commit(rs_jindo *j, const rs_opening *open, uint64_t *commitment_out);
 void *rs_opening_incommit_device(rs_opening *open);
+/* The same split with the exchange inside the library (NCCL on the library's stream, no host synchronisation; nccl_comm is an
+ * ncclComm_t -- the caller's, or one made by rs_nccl_comm_create):
+ *   rs_jindo_shard_columns         rank r of world owns columns [r*per, min((r+1)*per, cols+1)), per = ceil((cols+1)/world)
+ *   rs_jindo_outer_commit_sharded  Commitment.Value from the shards WITHOUT gathering InCommit: every rank multiplies ck.Out
+ *                                  by its own columns' InCommit, the out_msis partial sums (KiB) are all-reduced, the cut-off
+ *                                  pipeline runs replicated; bit-identical to the unsharded Commit on every rank
+ *   rs_jindo_allgather_incommit    all InCommit polynomials into every rank's Opening (Proof.InCommit, Evaluate), one in-place
+ *                                  ncclAllGather; may be issued after the commitment is out, it is not on Commit's critical path */
+int rs_jindo_shard_columns(const rs_jindo *j, int rank, int world, int *col_begin, int *col_end);
+int rs_jindo_outer_commit_sharded(rs_jindo *j, const rs_opening *open, int rank, int world, void *nccl_comm, uint64_t *commitment_out);
+int rs_jindo_allgather_incommit(rs_jindo *j, rs_opening *open, int rank, int world, void *nccl_comm);
 void rs_opening_free(rs_opening *o);
 /* accessors (tests / the Go shim's Opening view): kind 0 = Encode[col][row] (ringQ),
  * 1 = MLWE[col][idx] (ringQ), 2 = InCommit[idx] (ringQOut, col ignored) */

@@ -60,7 +60,7 @@ def build(force=False, verbose=False, defines=(), tag=""):
                 if res.returncode:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
     if jobs or not _newer(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart", "-Xcompiler", "-pthread"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart", "-ldl", "-Xcompiler", "-pthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode:
             sys.stderr.write(res.stdout + res.stderr)

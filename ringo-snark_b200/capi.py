@@ -118,6 +118,13 @@ _SIGS = {
     "rs_jindo_commit_columns": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "rs_jindo_outer_commit": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "rs_opening_incommit_device": (c_vp, [c_vp]),
+    "rs_jindo_shard_columns": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "rs_jindo_outer_commit_sharded": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "rs_jindo_allgather_incommit": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
+    "rs_nccl_unique_id": (ctypes.c_int, [c_vp]),
+    "rs_nccl_comm_create": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "rs_nccl_comm_destroy": (None, [c_vp]),
+    "rs_allgather_u64": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_size, c_vp]),
     "rs_opening_free": (None, [c_vp]),
     "rs_opening_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_size, c_size, c_vp]),
     "rs_jindo_partial": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),

@@ -66,6 +66,10 @@ cudaError_t ensure_smem_attr(const void *func, int bytes);
 // true exactly once per (current device, tag): per-device uploads such as __constant__ tables
 bool first_use_on_device(const void *tag);
 
+// NCCL collectives on the current stream (nccl_glue.cu; libnccl is loaded at run time)
+int nccl_allgather_inplace_u64(void *comm, uint64_t *d_buf, size_t count, int rank);
+int nccl_allreduce_sum_u64(void *comm, uint64_t *d_buf, size_t count);
+
 template <int NL>
 inline FieldParams<NL> make_params(const rs_field *f) {
     FieldParams<NL> F;

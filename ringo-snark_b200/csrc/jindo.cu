@@ -99,6 +99,8 @@ struct rs_jindo {
     cudaEvent_t ev_alloc, ev_piece[RS_VCHUNKS];
 };
 
+#define RS_MAX_SHARDS 64      // ranks a Commit can be split over (rs_jindo_shard_columns)
+
 struct rs_opening {
     rs_jindo *j;
     u64 *d_encode;          // (cols+1)*rows polys over ringQ
@@ -632,6 +634,8 @@ struct MatvecGeom {
     int accumulate;      // add the reduced sum to the existing out value
     int has_addend;
     int fold_every;      // reduce the high word mod q every this many terms (0 = never)
+    int k_split;         // matvec_pipe_kernel: the K range is cut into k_split pieces (grid.y carries the piece); piece s writes its
+    i64 split_stride;    // reduced partial sums at out + s * split_stride words, summed afterwards by reduce_split_kernel (0/1: off)
     u64 q[JMAXL], qinvneg[JMAXL], r2[JMAXL];
 };
 
@@ -788,10 +792,16 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
     const int tx = threadIdx.x & (MP_MS - 1), ty = threadIdx.x / MP_MS;     // slot in tile, column pair
     const int slot0 = blockIdx.x * MP_MS;
     const int n_slots = G.n_limbs * JD;
-    const int o0 = blockIdx.y * MP_OT, cb = blockIdx.z * MP_CTC;
+    // split-K (a column shard of a Commit has too few column tiles to fill the chip): grid.y = o-tiles x pieces
+    const int n_ot = (G.O + MP_OT - 1) / MP_OT;
+    const int ksp = G.k_split > 1 ? (int)blockIdx.y / n_ot : 0;
+    const int k_per = G.k_split > 1 ? (G.K + G.k_split - 1) / G.k_split : G.K;
+    const int k_begin = ksp * k_per, k_cnt = (k_begin + k_per <= G.K ? k_per : (G.K > k_begin ? G.K - k_begin : 0));
+    const int o0 = ((int)blockIdx.y - ksp * n_ot) * MP_OT, cb = blockIdx.z * MP_CTC;
     const size_t pw = (size_t)n_slots;
     const int limb = (slot0 + tx) / JD;
     const u64 q = G.q[limb], qi = G.qinvneg[limb];
+    out += (size_t)ksp * (size_t)G.split_stride;
 
     // ---- loader.  A stage is MP_KS k-steps x MP_ROWS polynomial rows (OT key rows, then CTC x columns) x
     //      PIECES 16-byte pieces.  Per CTA the rows' base pointers and per-k strides are fixed: they sit in a
@@ -812,7 +822,7 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
             const int cc = (cb + row - MP_OT < G.C) ? cb + row - MP_OT : G.C - 1;
             src = x + (size_t)(cc * G.x_cs) * pw; step = (size_t)G.x_ks * pw * 8;
         }
-        row_base[row] = (unsigned long long)(src + slot0);
+        row_base[row] = (unsigned long long)(src + slot0) + (unsigned long long)k_begin * step;
         row_step[row] = (unsigned)step;                             // < 2^32: launch_matvec checks
     }
     __syncthreads();
@@ -826,7 +836,7 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
             if (pair >= PAIRS) break;
             const int kl = pair / MP_ROWS, row = pair - kl * MP_ROWS;
             int k = it * MP_KS + kl;
-            if (k >= G.K) k = G.K - 1;                              // tail: harmless duplicate, not accumulated
+            if (k >= k_cnt) k = k_cnt > 0 ? k_cnt - 1 : 0;          // tail: harmless duplicate, not accumulated
             const unsigned long long src = row_base[row] + (unsigned long long)(unsigned)k * row_step[row] + piece * 16;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)pair * (MP_MS * 8)), "l"(src));
         }
@@ -840,7 +850,7 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
 #pragma unroll
         for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = Acc64{0}; s1h[a][b] = s2h[a][b] = 0; }
 
-    const int n_it = (G.K + MP_KS - 1) / MP_KS;
+    const int n_it = (k_cnt + MP_KS - 1) / MP_KS;
     for (int st = 0; st < MP_STAGES - 1; st++) {
         if (st < n_it) load_stage(st, st); else asm volatile("cp.async.commit_group;");
     }
@@ -855,7 +865,7 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
         const u64 *buf = ring + (size_t)(it % MP_STAGES) * MP_STAGE_WORDS;
 #pragma unroll
         for (int kl = 0; kl < MP_KS; kl++) {
-            if (it * MP_KS + kl >= G.K) break;
+            if (it * MP_KS + kl >= k_cnt) break;
             const u64 *rowp = buf + (size_t)kl * MP_ROWS * MP_MS + tx;
             u64 kv[MP_OT], xv[2];
 #pragma unroll
@@ -917,6 +927,18 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(u64 *__restrict__ out,
     const u64 q = G.q[slot / JD];
     u64 acc = 0;
     for (int c = 0; c < C; c++) acc = addmod(acc, part[((size_t)c * O + o) * pw + slot], q);
+    out[i] = acc;
+}
+
+// out[i] = sum_s part[s][i] mod q   (split-K reduction of matvec_pipe_kernel; out and part share the [C][O] polynomial layout)
+__global__ void __launch_bounds__(256) reduce_split_kernel(u64 *__restrict__ out, const u64 *__restrict__ part, int S, size_t n,
+                                                           const __grid_constant__ MatvecGeom G) {
+    const size_t pw = (size_t)G.n_limbs * JD;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 q = G.q[(i % pw) / JD];
+    u64 acc = 0;
+    for (int s = 0; s < S; s++) acc = addmod(acc, part[(size_t)s * n + i], q);
     out[i] = acc;
 }
 
@@ -1238,9 +1260,31 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true>, MP_SMEM_BYTES));
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false>, MP_SMEM_BYTES));
         dim3 grid(n_slots / MP_MS, (G.O + MP_OT - 1) / MP_OT, (G.C + MP_CTC - 1) / MP_CTC);
-        if (G.fold_every) matvec_pipe_kernel<true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(out, key, x, addend, G);
-        else matvec_pipe_kernel<false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(out, key, x, addend, G);
+        // few column tiles (a column shard of a Commit, a short Commit): cut K so that the grid still covers the chip
+        const unsigned ctas = grid.x * grid.y * grid.z;
+        int S = 1;
+        if (ctas * 2 <= 148 && !G.accumulate && !G.has_addend && G.out_os == 1 && G.out_cs == G.O && !getenv("RS_MV_NOSPLIT")) {
+            S = (int)(148 / ctas);
+            if (S > 16) S = 16;
+            while (S > 1 && G.K / S < 64) S--;
+        }
+        u64 *d_parts = nullptr;
+        const size_t n_out = (size_t)G.C * G.O * n_slots;
+        if (S > 1) {
+            if (cudaMallocAsync((void **)&d_parts, (size_t)S * n_out * 8, current_stream()) != cudaSuccess)
+                return set_error(RS_ERR_CUDA, "matvec: cudaMallocAsync failed");
+            G.k_split = S; G.split_stride = (i64)n_out;
+            grid.y *= S;
+        }
+        u64 *dst = S > 1 ? d_parts : out;
+        if (G.fold_every) matvec_pipe_kernel<true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
+        else matvec_pipe_kernel<false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         count_launch();
+        if (S > 1) {
+            reduce_split_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, current_stream()>>>(out, d_parts, S, n_out, G);
+            count_launch();
+            cudaFreeAsync(d_parts, current_stream());
+        }
         RS_CUDA_CHECK(cudaGetLastError());
         return RS_OK;
     }
@@ -1334,7 +1378,7 @@ static int opening_alloc(rs_jindo *j, rs_opening **out) {
     rs_opening *o = new rs_opening{j, nullptr, nullptr, nullptr};
     const rs_jindo_params &p = j->p;
     const size_t ne = (size_t)(p.cols + 1) * p.rows * pq(j), nm = (size_t)(p.cols + 1) * (p.mlwe + p.in_msis) * pq(j),
-                 ni = (size_t)(p.cols + 1) * p.in_msis * pqo(j);
+                 ni = (size_t)(p.cols + 1 + RS_MAX_SHARDS) * p.in_msis * pqo(j);   // + slack: padded in-place all-gather of column shards
     // stream-ordered pool (rs_init keeps it cached): a Buckler proof allocates and frees 12-43 Openings
     cudaError_t e = cudaMallocAsync((void **)&o->d_encode, ne * 8, current_stream());
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&o->d_mlwe, nm * 8, current_stream());
@@ -1977,7 +2021,9 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         // ---- cut-off pipeline (prover.go:164-176)
         RS_TRY(launch_cut(j, o->d_incommit + (size_t)col0 * p.in_msis * pqo(j), com0, (size_t)nc * p.in_msis, false));
         if (whole) RS_TRY(outer_commit(j, o, commitment_out));
-        else if (cudaStreamSynchronize(current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit_columns: %s", cudaGetErrorString(cudaGetLastError())); goto fail; }
+        // a column shard ends without the outer commit: host-resident tape buffers must have been consumed before the caller
+        // may reuse them; with a device-resident tape nothing needs the host to wait (the exchange runs on the same stream)
+        else if (!dev && cudaStreamSynchronize(current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit_columns: %s", cudaGetErrorString(cudaGetLastError())); goto fail; }
     }
 fail:
 #undef RS_TRY
@@ -2058,6 +2104,87 @@ int rs_jindo_outer_commit(rs_jindo *j, const rs_opening *open, uint64_t *commitm
 }
 
 void *rs_opening_incommit_device(rs_opening *open) { return open ? (void *)open->d_incommit : nullptr; }
+
+// ---- one Commit over several GPUs (SURVEY 8e iii) ------------------------------------------------------------------
+// Columns are dealt in equal contiguous blocks of ceil((cols+1) / world): every rank except possibly the last owns a full
+// block, so the ranks' InCommit slices, laid end to end, ARE the InCommit array and the exchange is one in-place all-gather.
+int rs_jindo_shard_columns(const rs_jindo *j, int rank, int world, int *col_begin, int *col_end) {
+    RS_REQUIRE(j && col_begin && col_end && world >= 1 && world <= RS_MAX_SHARDS && rank >= 0 && rank < world, RS_ERR_ARG,
+               "rs_jindo_shard_columns: bad argument");
+    const int n = j->p.cols + 1, per = (n + world - 1) / world;
+    const int b = rank * per < n ? rank * per : n, e = (rank + 1) * per < n ? (rank + 1) * per : n;
+    *col_begin = b; *col_end = e;
+    return RS_OK;
+}
+
+namespace rs {
+__global__ void mod_reduce_kernel(u64 *__restrict__ x, size_t n, const __grid_constant__ MatvecGeom G) {
+    const size_t pw = (size_t)G.n_limbs * JD;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] %= G.q[(i % pw) / JD];
+}
+}  // namespace rs
+
+// Outer commit of a column-sharded Commit without gathering InCommit first: every rank multiplies ck.Out by ITS columns'
+// InCommit polynomials (prover.go:186-189 is a sum over j, split here by column block), the out_msis partial sums (a few
+// KiB) are all-reduced as plain uint64 sums (world * q < 2^64) and reduced mod q, and the cut-off pipeline (:190-200) runs
+// replicated.  The same field elements as the sequential sum, so Commitment.Value is bit-identical to the unsharded one.
+int rs_jindo_outer_commit_sharded(rs_jindo *j, const rs_opening *o, int rank, int world, void *nccl_comm, uint64_t *commitment_out) {
+    RS_REQUIRE(j && o && o->j == j && nccl_comm && commitment_out, RS_ERR_ARG, "rs_jindo_outer_commit_sharded: bad argument");
+    int c0 = 0, c1 = 0;
+    int rc = rs_jindo_shard_columns(j, rank, world, &c0, &c1);
+    if (rc) return rc;
+    const rs_jindo_params &p = j->p;
+    for (int l = 0; l < j->rqo.n; l++)
+        RS_REQUIRE(j->rqo.q[l] < (~0ull) / (u64)world, RS_ERR_UNSUPPORTED, "rs_jindo_outer_commit_sharded: world * q overflows 64 bits");
+    const size_t n_com = (size_t)(p.cols + 1) * p.in_msis, tot = (size_t)p.out_msis * pqo(j);
+    const int nc = c1 - c0;
+    u64 *d_part = nullptr, *d_sum = nullptr, *d_value = nullptr;
+    if (cudaMallocAsync((void **)&d_sum, tot * 8, current_stream()) != cudaSuccess ||
+        cudaMallocAsync((void **)&d_value, tot * 8, current_stream()) != cudaSuccess ||
+        (nc > 0 && cudaMallocAsync((void **)&d_part, (size_t)nc * tot * 8, current_stream()) != cudaSuccess))
+        rc = set_error(RS_ERR_CUDA, "rs_jindo_outer_commit_sharded: cudaMallocAsync failed");
+    MatvecGeom Gr;
+    memset(&Gr, 0, sizeof(Gr));
+    fill_geom_ring(Gr, j->rqo);
+    if (rc == RS_OK) {
+        if (nc > 0) {
+            MatvecGeom G;
+            memset(&G, 0, sizeof(G));
+            G.O = p.out_msis; G.C = nc; G.K = p.in_msis;
+            G.key_os = (i64)n_com; G.key_cs = p.in_msis; G.key_ks = 1; G.x_cs = p.in_msis; G.x_ks = 1;
+            G.out_cs = p.out_msis; G.out_os = 1;
+            rc = launch_matvec(d_part, j->d_ck_out + (size_t)c0 * p.in_msis * pqo(j), o->d_incommit + (size_t)c0 * p.in_msis * pqo(j), nullptr, G, j->rqo);
+            if (rc == RS_OK) {
+                reduce_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, current_stream()>>>(d_sum, d_part, nc, p.out_msis, Gr);
+                count_launch();
+            }
+        } else if (cudaMemsetAsync(d_sum, 0, tot * 8, current_stream()) != cudaSuccess) {
+            rc = set_error(RS_ERR_CUDA, "rs_jindo_outer_commit_sharded: memset failed");
+        }
+    }
+    if (rc == RS_OK) rc = nccl_allreduce_sum_u64(nccl_comm, (uint64_t *)d_sum, tot);
+    if (rc == RS_OK) {
+        mod_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, current_stream()>>>(d_sum, tot, Gr);
+        count_launch();
+        rc = launch_cut(j, d_value, d_sum, p.out_msis, true);
+    }
+    if (rc == RS_OK && (cudaMemcpyAsync(commitment_out, d_value, tot * 8, cudaMemcpyDeviceToHost, current_stream()) != cudaSuccess ||
+                        cudaStreamSynchronize(current_stream()) != cudaSuccess))
+        rc = set_error(RS_ERR_CUDA, "rs_jindo_outer_commit_sharded: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFreeAsync(d_part, current_stream()); cudaFreeAsync(d_sum, current_stream()); cudaFreeAsync(d_value, current_stream());
+    return rc;
+}
+
+// The InCommit polynomials of every shard, gathered in place in the Opening (Proof.InCommit / Evaluate need all of them):
+// one ncclAllGather on the compute stream, no host synchronisation.
+int rs_jindo_allgather_incommit(rs_jindo *j, rs_opening *o, int rank, int world, void *nccl_comm) {
+    RS_REQUIRE(j && o && o->j == j && nccl_comm && world >= 1 && world <= RS_MAX_SHARDS && rank >= 0 && rank < world, RS_ERR_ARG,
+               "rs_jindo_allgather_incommit: bad argument");
+    const int per = (j->p.cols + 1 + world - 1) / world;
+    return nccl_allgather_inplace_u64(nccl_comm, (uint64_t *)o->d_incommit, (size_t)per * j->p.in_msis * pqo(j), rank);
+}
 
 int rs_jindo_commit_host(rs_jindo *j, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
                          rs_opening **open, uint64_t *commitment_out) {

@@ -57,24 +57,71 @@ def gather_column_slices(buf, n_cols, words_per_col, world, group=None):
     return buf
 
 
-def sharded_commit(prover, batch, poly, length, tape, rank, world, opening=None):
-    """One Commit split over `world` GPUs by columns of the committed matrix (SURVEY 8e iii): each rank encodes
-    and inner-commits its columns, the InCommit slices are exchanged over NCCL directly in the Opening's device
-    buffer, and every rank finishes with the same outer commit.  Returns (commitment, opening); the Opening
-    stays sharded by column (Partial is per column; the responses need a modular all-reduce)."""
-    import torch
-    p = prover.p
-    n_cols = p["cols"] + 1
+def block_range(n_units, rank, world):
+    """Equal contiguous blocks of ceil(n / world) units (the last ranks may own fewer or none): the split of
+    rs_jindo_shard_columns.  Laid end to end the blocks are the whole array, so ONE in-place all-gather of
+    equal-sized slices exchanges them."""
+    per = -(-n_units // world)
+    return min(rank * per, n_units), min((rank + 1) * per, n_units)
+
+
+class NcclComm:
+    """An NCCL communicator owned by the library (rs_nccl_comm_create): rank 0 makes the unique id, the other ranks get
+    it over the host's own control plane -- here a torch.distributed object broadcast, in a Go host any RPC."""
+
+    def __init__(self, rank, world):
+        import ctypes
+        import torch.distributed as dist
+        from .capi import check, lib, c_vp
+        self.rank, self.world = rank, world
+        ident = [None]
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            check(lib().rs_nccl_unique_id(ctypes.cast(buf, c_vp)))
+            ident[0] = buf.raw
+        dist.broadcast_object_list(ident, src=0)
+        self.h = c_vp()
+        check(lib().rs_nccl_comm_create(ctypes.c_char_p(ident[0]), rank, world, ctypes.byref(self.h)))
+
+    def all_gather_u64(self, local):
+        """local: uint64 array of n words -> [world, n] on every rank (rs_allgather_u64)"""
+        import ctypes
+        from .capi import check, lib
+        local = np.ascontiguousarray(local, dtype=np.uint64).reshape(-1)
+        out = np.zeros((self.world, local.size), dtype=np.uint64)
+        check(lib().rs_allgather_u64(self.h, self.rank, self.world, local.ctypes.data_as(ctypes.c_void_p), local.size,
+                                     out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def close(self):
+        from .capi import lib
+        if self.h:
+            lib().rs_nccl_comm_destroy(self.h)
+            self.h = None
+
+
+def sharded_commit(prover, batch, poly, length, tape, rank, world, opening=None, comm=None, gather_incommit=True):
+    """One Commit split over `world` GPUs by columns of the committed matrix (SURVEY 8e iii), the exchange inside the
+    library: each rank encodes and inner-commits its block of columns (rs_jindo_commit_columns), multiplies ck.Out by its
+    own InCommit polynomials, the out_msis partial sums are all-reduced over NCCL and the cut-off pipeline runs replicated
+    (rs_jindo_outer_commit_sharded) -- nothing but a few KiB is on Commit's critical path.  The InCommit slices that
+    Evaluate / the proof need are all-gathered in place afterwards (rs_jindo_allgather_incommit, asynchronous).
+    Returns (commitment, opening); Encode / MLWE stay sharded by column."""
+    import ctypes
+    from .capi import check, lib
     if world == 1:
         return prover.Commit(batch, poly, length, tape)
-    c0, c1 = shard_range(n_cols, rank, world)
-    opening = prover.CommitColumns(batch, poly, length, tape, c0, c1, opening)
-    words = p["in_msis"] * prover.n_qout * prover.d
-    view = torch.as_tensor(_DevView(opening.incommit_device_ptr(), n_cols * words), device="cuda")
-    torch.cuda.synchronize()
-    gather_column_slices(view, n_cols, words, world)
-    torch.cuda.synchronize()
-    return prover.OuterCommit(opening), opening
+    c0, c1 = ctypes.c_int(), ctypes.c_int()
+    check(lib().rs_jindo_shard_columns(prover.h, rank, world, ctypes.byref(c0), ctypes.byref(c1)))
+    if c1.value > c0.value:
+        opening = prover.CommitColumns(batch, poly, length, tape, c0.value, c1.value, opening)
+    elif opening is None:
+        opening = prover.NewOpening()
+    com = np.zeros((prover.p["out_msis"], prover.n_qout, prover.d), dtype=np.uint64)
+    check(lib().rs_jindo_outer_commit_sharded(prover.h, opening.h, rank, world, comm.h, com.ctypes.data_as(ctypes.c_void_p)))
+    if gather_incommit:
+        check(lib().rs_jindo_allgather_incommit(prover.h, opening.h, rank, world, comm.h))
+    return com, opening
 
 
 def transcript_digest(commitments):

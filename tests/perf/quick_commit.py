@@ -65,3 +65,18 @@ for fn, name in ((lambda: gp.Partial(op, left), "Partial"), (lambda: gp.Respond(
     for _ in range(5): fn()
     torch.cuda.synchronize()
     print(f"{name}: {(time.perf_counter() - t0) / 5 * 1e3:.3f} ms", flush=True)
+# ---- column shards on one GPU: how the per-rank share of a sharded Commit scales (no exchange here)
+if "--shards" in sys.argv:
+    for world in (1, 2, 4, 8):
+        per = -(-(p.cols + 1) // world)
+        for r in sorted({0, world - 1}):
+            c0, c1 = min(r * per, p.cols + 1), min((r + 1) * per, p.cols + 1)
+            for _ in range(2):
+                gp.CommitColumns(B, 0, N, T, c0, c1, op)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter(); e0.record()
+            for _ in range(reps):
+                gp.CommitColumns(B, 0, N, T, c0, c1, op)
+            e1.record(); torch.cuda.synchronize()
+            print(f"world {world} rank {r}: columns [{c0},{c1})  wall {(time.perf_counter() - t0) / reps * 1e3:.3f} ms  device {e0.elapsed_time(e1) / reps:.3f} ms", flush=True)
