@@ -169,6 +169,37 @@ int rs_jindo_left_vec(rs_jindo *j, const uint64_t *x_mont, uint64_t *left_out);
 int rs_jindo_encode_challenges(rs_jindo *j, const uint8_t *chal_bytes, size_t n, int ring_out, uint64_t *polys_out);
 /* batch > 1 (prover.go:251-265): acc += open (.) challenge, over every polynomial of the opening;
  * _bytes: the challenge polynomial of both rings is encoded on the device from its 16 bytes (prover.go:230-249) */
+/* Verifier.Verify (jindo/verifier.go:50-282) with the proof's arithmetic on the device: IMForm / INTT of every proof
+ * polynomial, the outer and inner commitment equations (MulCoeffsMontgomeryThenSub against ck.Out / ck.In / ck.MLWE, the
+ * cut-off scalars, BasisExtender.ModUpQtoP as a centred lift), CRT reconstruction and the two-norms of verifyNorm, the
+ * consistency equation, and the reconstruction of the Partial polynomials that verifyEval decodes.  The transcript stays with
+ * the caller, as in Evaluate: batch_bytes (16 per commitment, NULL when batch == 1) and chal_bytes (16 per column) are the
+ * SHAKE128 outputs of verifier.go:61-94.  The proof polynomials are host arrays in the form Evaluate returns them.
+ * *checks: bit 0 verifyOuterCommitment, bit 1 verifyInnerCommitment, bit 2 verifyConsistency, bit 3 verifyEval; the proof is
+ * accepted iff *checks == 15.  in_com_dcmp_two_nm / res_two_nm: Parameters.inComDcmpTwoNm / resTwoNm (params.go). */
+typedef struct rs_jindo_proof {
+    const uint64_t *partial;       /* cols polys over ringQ          Proof.Partial */
+    const uint64_t *partial_mask;  /* 1 poly over ringQ              Proof.PartialMask */
+    const uint64_t *encode;        /* rows polys over ringQ          Proof.Encode */
+    const uint64_t *mlwe;          /* mlwe + in_msis polys, ringQ    Proof.MLWE */
+    const uint64_t *incommit;      /* (cols+1)*in_msis polys, ringQOut  Proof.InCommit */
+} rs_jindo_proof;
+int rs_jindo_verify(rs_jindo *j, const uint64_t *x_mont, const uint64_t *commitments, int batch, const uint8_t *batch_bytes,
+                    const uint8_t *chal_bytes, const uint64_t *ys_mont, const rs_jindo_proof *pf, double in_com_dcmp_two_nm,
+                    double res_two_nm, int *checks);
+
+/* Wire format of the transcript inputs, for hosts that do not have lattigo at hand:
+ *   rs_jindo_poly_write_to          [lattigo] ring.Poly.WriteTo framing of one polynomial given as n_limbs x d words: u64 LE
+ *                                   limb count, then per limb u64 LE length d and d coefficients as u64 LE.
+ *   rs_jindo_commitment_write_raw   Commitment.WriteRawTo (jindo/entities.go:96-100): the out_msis polynomials of
+ *                                   Commitment.Value one after the other.  NewCommitment allocates them in ringQ
+ *                                   (entities.go:85-94) although their data live in ringQOut, so every polynomial is
+ *                                   framed with max(n_q, n_qout) limbs, the limbs beyond n_qout all zero.
+ * Both return the number of bytes written, or a negative error code (RS_ERR_ARG when cap is too small); with out == NULL
+ * they only return the size. */
+long long rs_jindo_poly_write_to(const uint64_t *poly, int n_limbs, int d, uint8_t *out, size_t cap);
+long long rs_jindo_commitment_write_raw(const rs_jindo *j, const uint64_t *commitment, uint8_t *out, size_t cap);
+
 int rs_opening_alloc_zero(rs_jindo *j, rs_opening **out);
 int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout);
 int rs_opening_mul_add_bytes(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint8_t *chal16);

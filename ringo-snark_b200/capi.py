@@ -49,6 +49,11 @@ class JindoTape(ctypes.Structure):
                 ("on_device", ctypes.c_int32), ("mlwe_mask_only", ctypes.c_int32)]
 
 
+class JindoProof(ctypes.Structure):
+    """rs_jindo_proof (include/ringo_jindo.h)"""
+    _fields_ = [("partial", c_vp), ("partial_mask", c_vp), ("encode", c_vp), ("mlwe", c_vp), ("incommit", c_vp)]
+
+
 class JindoNoise(ctypes.Structure):
     """rs_jindo_noise (include/ringo_sampler.h)"""
     _fields_ = [("ecd_blind_std", ctypes.c_double), ("mask_blind_std", ctypes.c_double), ("mask_std", ctypes.c_double),
@@ -134,6 +139,10 @@ _SIGS = {
     "rs_jindo_left_vec": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "rs_jindo_encode_challenges": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.c_int, c_vp]),
     "rs_opening_mul_add_bytes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "rs_jindo_verify": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.POINTER(JindoProof), ctypes.c_double,
+                                       ctypes.c_double, ctypes.POINTER(ctypes.c_int)]),
+    "rs_jindo_poly_write_to": (ctypes.c_longlong, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_size]),
+    "rs_jindo_commitment_write_raw": (ctypes.c_longlong, [c_vp, c_vp, c_vp, c_size]),
     "rs_opening_alloc_zero": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "rs_opening_mul_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     # ringo_sampler.h

@@ -51,7 +51,7 @@ bool first_use_on_device(const void *tag) {
 // implemented in pointwise.cu
 int pointwise(int op, const rs_field *f, uint32_t *out, const uint32_t *a, const uint32_t *b, const uint32_t *c, size_t n);
 int eval_circuit(const rs_field *f, uint32_t *out, const uint32_t *pw, const uint32_t *w, const rs_term *d_terms,
-                 int n_terms, const uint32_t *d_coeffs, const uint32_t *bc, size_t rank);
+                 int n_terms, const uint32_t *d_coeffs, int n_coeffs, const uint32_t *bc, size_t rank);
 int quorem(const rs_field *f, uint32_t *quo, uint32_t *rem, const uint32_t *p, size_t rank, size_t N);
 int aut(const rs_field *f, uint32_t *out, const uint32_t *p, int logN, unsigned long long idx,
         unsigned long long idx_inv, int is_ntt, size_t n_polys);
@@ -509,7 +509,26 @@ int rs_ntt_inverse_embed(rs_ntt *t, rs_batch *dst, size_t dp, const rs_batch *sr
     RS_REQUIRE(t && dst && src, RS_ERR_ARG, "ntt: null argument");
     const size_t N = (size_t)1 << t->logN;
     RS_REQUIRE(dst->rank >= N && src->rank >= N, RS_ERR_SHAPE, "inconsistent input(s)");
+    RS_REQUIRE(dst->f->NL == t->f->NL && src->f->NL == t->f->NL, RS_ERR_SHAPE, "ntt: field mismatch");
     RS_REQUIRE(dp + n <= dst->n_polys && sp + n <= src->n_polys, RS_ERR_SHAPE, "ntt: poly range out of bounds");
+    if (n == 0) return RS_OK;
+    if (src->rank == N && dst->rank == N) return ntt_dispatch(t, elem_ptr(dst, dp), elem_ptr(src, sp), n, true);
+    if (src->rank == N && dst != src) {
+        // Encoder.EncodeTo for a whole batch of witnesses (buckler/encoder.go:32-38): ONE batched transform of the packed
+        // source into a stream-ordered temporary, then one strided copy into the low N coefficients of the wider
+        // polynomials and one strided zero-fill of their tails -- `passes` + 2 launches instead of (passes + 1) per witness
+        const size_t eb = (size_t)t->f->NL * 4;
+        uint32_t *tmp = nullptr;
+        RS_CUDA_CHECK(cudaMallocAsync((void **)&tmp, n * N * eb, g_stream));
+        int rc = ntt_dispatch(t, tmp, elem_ptr(src, sp), n, true);
+        if (rc == RS_OK && cudaMemcpy2DAsync(elem_ptr(dst, dp), dst->rank * eb, tmp, N * eb, N * eb, n, cudaMemcpyDeviceToDevice, g_stream) != cudaSuccess)
+            rc = set_error(RS_ERR_CUDA, "rs_ntt_inverse_embed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc == RS_OK && zero_pad && dst->rank > N &&
+            cudaMemset2DAsync(elem_ptr(dst, dp, N), dst->rank * eb, 0, (dst->rank - N) * eb, n, g_stream) != cudaSuccess)
+            rc = set_error(RS_ERR_CUDA, "rs_ntt_inverse_embed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFreeAsync(tmp, g_stream);
+        return rc;
+    }
     for (size_t i = 0; i < n; i++) {
         int rc = ntt_dispatch(t, elem_ptr(dst, dp + i), elem_ptr(src, sp + i), 1, true);
         if (rc) return rc;
@@ -574,16 +593,20 @@ int rs_eval_circuit(rs_batch *out, size_t out_poly, const rs_batch *pw, const rs
             RS_REQUIRE(t.w[x] >= 0 && (size_t)t.w[x] < w->n_polys, RS_ERR_ARG, "rs_eval_circuit: witness index out of range");
         RS_REQUIRE(k == 0 || t.constraint >= terms[k - 1].constraint, RS_ERR_ARG, "rs_eval_circuit: terms must be grouped by constraint");
     }
-    rs_term *d_terms = nullptr;
-    uint32_t *d_coeffs = nullptr;
-    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_terms, (n_terms ? n_terms : 1) * sizeof(rs_term), g_stream));
-    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_coeffs, (n_coeffs ? n_coeffs : 1) * NL * 4, g_stream));
-    RS_CUDA_CHECK(cudaMemcpyAsync(d_terms, terms, n_terms * sizeof(rs_term), cudaMemcpyHostToDevice, g_stream));
-    RS_CUDA_CHECK(cudaMemcpyAsync(d_coeffs, coeffs, n_coeffs * NL * 4, cudaMemcpyHostToDevice, g_stream));
-    int rc = eval_circuit(out->f, elem_ptr(out, out_poly), pw ? pw->d : nullptr, w->d, d_terms, (int)n_terms, d_coeffs,
+    // one stream-ordered temporary for both tables; freed on every path
+    const size_t tbytes = ((n_terms ? n_terms : 1) * sizeof(rs_term) + 15) & ~(size_t)15;
+    char *d_tmp = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_tmp, tbytes + (n_coeffs ? n_coeffs : 1) * NL * 4, g_stream));
+    rs_term *d_terms = (rs_term *)d_tmp;
+    uint32_t *d_coeffs = (uint32_t *)(d_tmp + tbytes);
+    int rc = RS_OK;
+    if (cudaMemcpyAsync(d_terms, terms, n_terms * sizeof(rs_term), cudaMemcpyHostToDevice, g_stream) != cudaSuccess ||
+        cudaMemcpyAsync(d_coeffs, coeffs, n_coeffs * NL * 4, cudaMemcpyHostToDevice, g_stream) != cudaSuccess)
+        rc = set_error(RS_ERR_CUDA, "rs_eval_circuit: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == RS_OK)
+        rc = eval_circuit(out->f, elem_ptr(out, out_poly), pw ? pw->d : nullptr, w->d, d_terms, (int)n_terms, d_coeffs, (int)n_coeffs,
                           (const uint32_t *)batch_const, out->rank);
-    cudaFreeAsync(d_terms, g_stream);
-    cudaFreeAsync(d_coeffs, g_stream);
+    cudaFreeAsync(d_tmp, g_stream);
     return rc;
 }
 

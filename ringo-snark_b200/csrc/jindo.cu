@@ -45,6 +45,9 @@ struct RingDev {
     const double *roots_f64;
     double qf[JMAXL], qinvf[JMAXL];
     int f64_ok;
+    // kernel-path switches (tuning / the parity tests of the alternative paths): read from the environment ONCE, when the
+    // prover handle is created, never on the Commit path
+    int no_rowsum, no_pipe, no_split;
 };
 
 struct CrtDev {             // RNSReconstructor constants of the *source* ring (rns.go:33-55)
@@ -94,6 +97,7 @@ struct rs_jindo {
     rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
     rs::UniformStream *mlwe_stream;   // same for Prover.mlweSampler (centre 0: table 0 only)
     u64 *d_mlwe_cdt; int mlwe_cdt_len; long long mlwe_tail_lo;
+    int no_pair, prefetch;            // RS_JINDO_NOPAIR / RS_JINDO_PREFETCH, read when the handle is created
     cudaStream_t copy_stream;         // rs_jindo_commit_host: uploads of v pieces
     size_t ck_rejected;               // rs_jindo_create_crs: draws SampleN threw away while generating the key
     cudaEvent_t ev_alloc, ev_piece[RS_VCHUNKS];
@@ -964,8 +968,11 @@ __device__ __forceinline__ void mw_sub(u64 *a, const u64 *b) {
     }
 }
 
+// Verifier side (jindo/verifier.go:100-113, :262-282): with ints_out / sq_out set the kernel also hands back the reconstructed
+// centred integers (JW two's-complement words per coefficient) and, per polynomial, the sum of their squares (2 JW words,
+// what verifyNorm accumulates); out == NULL stops after the reconstruction.
 __global__ void __launch_bounds__(256) cut_kernel(u64 *__restrict__ out, const u64 *__restrict__ in,
-                                                  const __grid_constant__ CutConsts K) {
+                                                  const __grid_constant__ CutConsts K, u64 *__restrict__ ints_out, u64 *__restrict__ sq_out) {
     __shared__ u64 s[JMAXL][JD];
     const int c = threadIdx.x;
     const RingDev &A = K.in, &B = K.outr;
@@ -1014,6 +1021,45 @@ __global__ void __launch_bounds__(256) cut_kernel(u64 *__restrict__ out, const u
             if (mw_geq(V, K.crt.Qhalf)) { mw_sub(V, K.crt.Q); neg = true; }             // acc >= Q>>1 -> acc - Q
         }
     }
+    if (ints_out) {
+        u64 *dst = ints_out + ((size_t)blockIdx.x * JD + c) * JW;
+        for (int i = 0; i < JW; i++) dst[i] = V[i];
+    }
+    if (sq_out) {
+        __shared__ u64 s_sq[JD][2 * JW + 1];
+        u64 M[JW];
+        if (neg) { u64 cy = 1; for (int i = 0; i < JW; i++) { const u64 t = ~V[i] + cy; cy = (cy && t == 0); M[i] = t; } }
+        else for (int i = 0; i < JW; i++) M[i] = V[i];
+        u64 P[2 * JW];
+        for (int i = 0; i < 2 * JW; i++) P[i] = 0;
+        for (int a = 0; a < JW; a++) {
+            u64 carry = 0;
+            for (int b = 0; b < JW; b++) {
+                const u64 lo = M[a] * M[b], hi = __umul64hi(M[a], M[b]);
+                u64 t = P[a + b] + lo; u64 cy = t < lo;
+                const u64 t2 = t + carry; cy += t2 < t;
+                P[a + b] = t2;
+                carry = hi + cy;
+            }
+            P[a + JW] += carry;
+        }
+        for (int i = 0; i < 2 * JW; i++) s_sq[c][i] = P[i];
+        __syncthreads();
+        for (int st = JD / 2; st >= 1; st >>= 1) {
+            if (c < st) {
+                u64 cy = 0;
+                for (int i = 0; i < 2 * JW; i++) {
+                    const u64 a = s_sq[c][i], b = s_sq[c + st][i];
+                    const u64 t = a + b; u64 c1 = t < b;
+                    const u64 t2 = t + cy; c1 += t2 < t;
+                    s_sq[c][i] = t2; cy = c1;
+                }
+            }
+            __syncthreads();
+        }
+        if (c < 2 * JW) sq_out[(size_t)blockIdx.x * 2 * JW + c] = s_sq[0][c];
+    }
+    if (!out) return;
     // Rsh(log_cut): arithmetic shift (floor for negatives, like big.Int.Rsh)
     {
         const int ws = K.log_cut / 64, bs = K.log_cut % 64;
@@ -1068,6 +1114,31 @@ __global__ void __launch_bounds__(256) muladd_bcast_kernel(u64 *__restrict__ acc
     }
 }
 
+// out = a * s - b [- c]  (mod q), s a per-limb Montgomery scalar: the verifier's  commitment * 2^cut - key (.) proof  lines
+// (MulRNSScalarMontgomery + MulCoeffsMontgomeryThenSub + Sub, verifier.go:146-157, :183-196)
+__global__ void __launch_bounds__(256) scale_sub_kernel(u64 *__restrict__ out, const u64 *__restrict__ a, const u64 *__restrict__ b,
+                                                        const u64 *__restrict__ c, size_t n_polys, const __grid_constant__ MatvecGeom G,
+                                                        const __grid_constant__ MatvecGeom S /* S.q[l] = scalar in Montgomery form */) {
+    const size_t pw = (size_t)G.n_limbs * JD;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_polys * pw; i += (size_t)gridDim.x * blockDim.x) {
+        const int limb = (int)((i % pw) / JD);
+        const u64 q = G.q[limb];
+        u64 r = mont64(a[i], S.q[limb], q, G.qinvneg[limb]);
+        r = submod(r, b[i], q);
+        if (c) r = submod(r, c[i], q);
+        out[i] = r;
+    }
+}
+// flag |= (a - b - c != 0) anywhere
+__global__ void __launch_bounds__(256) nonzero_kernel(unsigned *__restrict__ flag, const u64 *__restrict__ a, const u64 *__restrict__ b,
+                                                      const u64 *__restrict__ c, size_t n, const __grid_constant__ MatvecGeom G) {
+    const size_t pw = (size_t)G.n_limbs * JD;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 q = G.q[(i % pw) / JD];
+        if (submod(submod(a[i], b[i], q), c[i], q) != 0) atomicOr(flag, 1u);
+    }
+}
+
 }  // namespace rs
 
 // =============================================================================================
@@ -1101,6 +1172,7 @@ static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi
     memset(&C, 0, sizeof(C));
     R.n = n;
     R.f64_ok = getenv("RS_JINDO_NOF64") ? 0 : 1;
+    R.no_rowsum = getenv("RS_MV_NOROWSUM") ? 1 : 0; R.no_pipe = getenv("RS_MV_NOPIPE") ? 1 : 0; R.no_split = getenv("RS_MV_NOSPLIT") ? 1 : 0;
     for (int l = 0; l < n; l++) {
         const u64 ql = q[l];
         if (ql >= (1ull << 44)) R.f64_ok = 0;
@@ -1233,7 +1305,7 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
     fill_geom_ring(G, R);
     const int n_slots = R.n * JD;
     // single-output products (Evaluate): streaming row sums
-    if (G.O == 1 && G.key_cs == 0 && G.out_cs == 1 && !G.accumulate && !getenv("RS_MV_NOROWSUM")) {
+    if (G.O == 1 && G.key_cs == 0 && G.out_cs == 1 && !G.accumulate && !R.no_rowsum) {
         // enough CTAs for >= 4 per SM; K is split when there are few output polynomials
         const int bx = (n_slots + 255) / 256;
         int ksplit = 1;
@@ -1255,7 +1327,7 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         return RS_OK;
     }
     // large products (inner commit): shared-memory ring version
-    if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !getenv("RS_MV_NOPIPE") &&
+    if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !R.no_pipe &&
         (unsigned long long)G.key_ks * n_slots * 8 < (1ull << 32) && (unsigned long long)G.x_ks * n_slots * 8 < (1ull << 32)) {
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true>, MP_SMEM_BYTES));
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false>, MP_SMEM_BYTES));
@@ -1263,7 +1335,7 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         // few column tiles (a column shard of a Commit, a short Commit): cut K so that the grid still covers the chip
         const unsigned ctas = grid.x * grid.y * grid.z;
         int S = 1;
-        if (ctas * 2 <= 148 && !G.accumulate && !G.has_addend && G.out_os == 1 && G.out_cs == G.O && !getenv("RS_MV_NOSPLIT")) {
+        if (ctas * 2 <= 148 && !G.accumulate && !G.has_addend && G.out_os == 1 && G.out_cs == G.O && !R.no_split) {
             S = (int)(148 / ctas);
             if (S > 16) S = 16;
             while (S > 1 && G.K / S < 64) S--;
@@ -1315,7 +1387,7 @@ static int launch_encode(rs_jindo *j, u64 *out, const EncDesc *d_descs, size_t n
         if (j->p.delta_inv[i] != 0.0) { E.delta_inv[E.n_delta] = j->p.delta_inv[i]; E.delta_w[E.n_delta] = (i + 1) * j->p.slots; E.n_delta++; }
     for (int l = 0; l < j->rq.n; l++) E.base_mont[l] = j->base_mont_q[l];
     E.g_lim = (i64)((1ull << 62) / j->p.base);
-    if (j->p.base < 65536 && !getenv("RS_JINDO_NOPAIR")) {
+    if (j->p.base < 65536 && !j->no_pair) {
         E.base2 = (uint32_t)(j->p.base * j->p.base);
         E.base2_magic = (u64)((((u128)1) << 64) / E.base2) + 1;
         E.base_magic32 = (uint32_t)((1ull << 32) / j->p.base) + 1;
@@ -1357,7 +1429,22 @@ static int launch_cut(rs_jindo *j, u64 *out, const u64 *in, size_t n_polys, bool
     K.in = outer ? j->rqo : j->rq;
     K.outr = j->rqo;
     K.crt = outer ? j->crt_qo : j->crt_q;
-    cut_kernel<<<(unsigned)n_polys, 256, 0, current_stream()>>>(out, in, K);
+    cut_kernel<<<(unsigned)n_polys, 256, 0, current_stream()>>>(out, in, K, nullptr, nullptr);
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// verifier forms: src ring -> (optional) re-RNS into dst ring with no shift (BasisExtender.ModUpQtoP of a centred lift),
+// (optional) centred integers, (optional) per-polynomial sums of squares
+static int launch_recon(rs_jindo *j, bool src_out, bool dst_q, u64 *out, const u64 *in, size_t n_polys, u64 *ints_out, u64 *sq_out) {
+    if (n_polys == 0) return RS_OK;
+    CutConsts K;
+    K.log_cut = 0;
+    K.in = src_out ? j->rqo : j->rq;
+    K.outr = dst_q ? j->rq : j->rqo;
+    K.crt = src_out ? j->crt_qo : j->crt_q;
+    cut_kernel<<<(unsigned)n_polys, 256, 0, current_stream()>>>(out, in, K, ints_out, sq_out);
     count_launch();
     RS_CUDA_CHECK(cudaGetLastError());
     return RS_OK;
@@ -1623,6 +1710,7 @@ static int jindo_create_impl(rs_field *f, const rs_jindo_params *p, const uint64
     RS_REQUIRE(p->cdt_len >= 1, RS_ERR_ARG, "rs_jindo_create: bad CDT");
     rs_jindo *j = new rs_jindo();
     memset(j, 0, sizeof(*j));
+    j->no_pair = getenv("RS_JINDO_NOPAIR") ? 1 : 0; j->prefetch = getenv("RS_JINDO_PREFETCH") ? 1 : 0;
     j->cache = new std::vector<DescCache>();
     j->f = f;
     j->p = *p;
@@ -1799,6 +1887,282 @@ void rs_opening_free(rs_opening *o) {
     if (o->d_mlwe) cudaFreeAsync(o->d_mlwe, rs::current_stream());
     if (o->d_incommit) cudaFreeAsync(o->d_incommit, rs::current_stream());
     delete o;
+}
+
+// =============================================================================================
+// Verifier.Verify on the device (jindo/verifier.go:50-282)
+// =============================================================================================
+static int encode_left_vec(rs_jindo *j, const uint64_t *x_mont, u64 **d_left);
+static int encode_challenges(rs_jindo *j, const uint8_t *bytes, size_t n, const RingDev &ring, u64 **d_out);
+namespace {
+// sum of n_parts numbers of 2 JW words -> total (2 JW + 2 words)
+void sq_total(const u64 *parts, size_t n_parts, u64 *tot /* 2*JW+2 */) {
+    for (int i = 0; i < 2 * JW + 2; i++) tot[i] = 0;
+    for (size_t k = 0; k < n_parts; k++) {
+        u64 cy = 0;
+        for (int i = 0; i < 2 * JW + 2; i++) {
+            const u64 b = i < 2 * JW ? parts[k * 2 * JW + i] : 0;
+            const u64 t = tot[i] + b; u64 c1 = t < b;
+            const u64 t2 = t + cy; c1 += t2 < t;
+            tot[i] = t2; cy = c1;
+        }
+    }
+}
+// float64(isqrt(S)) < nm, as verifyNorm does (big.Int.Sqrt then Float64, verifier.go:278-281).  S: W little-endian words.
+bool isqrt_lt(const u64 *S, int W, double nm) {
+    const int HW = (W + 1) / 2;
+    std::vector<u64> r(HW, 0), cand(HW), sq(2 * HW + 1);
+    for (int bit = 64 * HW - 1; bit >= 0; bit--) {
+        cand = r;
+        cand[bit / 64] |= 1ull << (bit % 64);
+        std::fill(sq.begin(), sq.end(), 0);
+        for (int a = 0; a < HW; a++) {
+            u64 carry = 0;
+            for (int b = 0; b < HW; b++) {
+                const u128 t = (u128)cand[a] * cand[b] + sq[a + b] + carry;
+                sq[a + b] = (u64)t; carry = (u64)(t >> 64);
+            }
+            sq[a + HW] += carry;
+        }
+        bool le = true;                                              // cand^2 <= S ?
+        for (int i = 2 * HW; i >= 0; i--) {
+            const u64 sv = i < W ? S[i] : 0;
+            if (sq[i] != sv) { le = sq[i] < sv; break; }
+        }
+        if (le) r = cand;
+    }
+    // big.Int.Float64: nearest, ties to even
+    int top = HW - 1;
+    while (top > 0 && r[top] == 0) top--;
+    if (top == 0 && r[0] < (1ull << 53)) return (double)r[0] < nm;
+    const int hb = 63 - __builtin_clzll(r[top]);                      // highest set bit of the top word
+    const int total_bits = 64 * top + hb + 1;
+    const int shift = total_bits - 53;                                // bits dropped
+    auto bit_at = [&](int b) { return b < 0 ? 0ull : (r[b / 64] >> (b % 64)) & 1ull; };
+    u64 mant = 0;
+    for (int b = 0; b < 53; b++) mant |= bit_at(shift + b) << b;
+    bool sticky = false;
+    for (int b = 0; b < shift - 1 && !sticky; b++) sticky = bit_at(b);
+    const u64 half = bit_at(shift - 1);
+    if (half && (sticky || (mant & 1))) mant++;
+    return ldexp((double)mant, shift) < nm;
+}
+}  // namespace
+
+int rs_jindo_verify(rs_jindo *j, const uint64_t *x_mont, const uint64_t *commitments, int batch, const uint8_t *batch_bytes,
+                    const uint8_t *chal_bytes, const uint64_t *ys_mont, const rs_jindo_proof *pf, double in_com_dcmp_two_nm,
+                    double res_two_nm, int *checks) {
+    RS_REQUIRE(j && x_mont && commitments && chal_bytes && ys_mont && pf && checks && batch >= 1, RS_ERR_ARG, "rs_jindo_verify: null argument");
+    RS_REQUIRE(pf->partial && pf->partial_mask && pf->encode && pf->mlwe && pf->incommit, RS_ERR_ARG, "rs_jindo_verify: incomplete proof");
+    RS_REQUIRE(batch == 1 || batch_bytes, RS_ERR_ARG, "rs_jindo_verify: batch challenges missing");
+    const rs_jindo_params &p = j->p;
+    const int cols = p.cols, rows = p.rows, nm = p.mlwe + p.in_msis, NL = j->f->NL;
+    const size_t n_com = (size_t)(cols + 1) * p.in_msis, wq = pq(j), wo = pqo(j);
+    *checks = 0;
+    int rc = RS_OK;
+    cudaStream_t st = current_stream();
+    // ---- device copies of the proof and of the commitments
+    u64 *d_part = nullptr, *d_enc = nullptr, *d_ml = nullptr, *d_inc = nullptr, *d_coms = nullptr, *d_chal = nullptr, *d_bq = nullptr, *d_bo = nullptr;
+    u64 *d_left = nullptr, *d_tmp = nullptr, *d_sq = nullptr, *d_ints = nullptr;
+    unsigned *d_flag = nullptr;
+    std::vector<u64> h_sq, h_ints;
+    MatvecGeom Gq, Go, Sq, So;
+    memset(&Gq, 0, sizeof(Gq)); memset(&Go, 0, sizeof(Go)); memset(&Sq, 0, sizeof(Sq)); memset(&So, 0, sizeof(So));
+    fill_geom_ring(Gq, j->rq); fill_geom_ring(Go, j->rqo);
+    for (int l = 0; l < j->rq.n; l++) {       // MForm(2^log_in_cut mod q_l): the RNS scalar of verifier.go:28-37
+        const u64 q = j->rq.q[l];
+        Sq.q[l] = h_mulmod(h_powmod(2, (u64)p.log_in_cut, q), h_powmod(2, 64, q), q);
+    }
+    for (int l = 0; l < j->rqo.n; l++) {
+        const u64 q = j->rqo.q[l];
+        So.q[l] = h_mulmod(h_powmod(2, (u64)p.log_out_cut, q), h_powmod(2, 64, q), q);
+    }
+#define RS_V(x) do { if (rc == RS_OK) { rc = (x); } } while (0)
+#define RS_VA(ptr, words) do { if (rc == RS_OK && cudaMallocAsync((void **)&(ptr), (size_t)(words) * 8, st) != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_verify: cudaMallocAsync failed"); } while (0)
+#define RS_VU(dst, src, words) do { if (rc == RS_OK && cudaMemcpyAsync(dst, src, (size_t)(words) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_verify: upload failed"); } while (0)
+    RS_VA(d_part, (size_t)(cols + 1) * wq); RS_VA(d_enc, (size_t)rows * wq); RS_VA(d_ml, (size_t)nm * wq); RS_VA(d_inc, n_com * wo);
+    RS_VA(d_coms, (size_t)batch * p.out_msis * wo);
+    RS_VU(d_part, pf->partial, (size_t)cols * wq); RS_VU(d_part + (size_t)cols * wq, pf->partial_mask, wq);
+    RS_VU(d_enc, pf->encode, (size_t)rows * wq); RS_VU(d_ml, pf->mlwe, (size_t)nm * wq); RS_VU(d_inc, pf->incommit, n_com * wo);
+    RS_VU(d_coms, commitments, (size_t)batch * p.out_msis * wo);
+    // challenge polynomials (encodeChallengeTo, utils.go:21-46) and the encoded leftVec, on the device
+    RS_V(encode_challenges(j, chal_bytes, (size_t)cols, j->rq, &d_chal));
+    if (batch > 1) { RS_V(encode_challenges(j, batch_bytes, (size_t)batch, j->rq, &d_bq)); RS_V(encode_challenges(j, batch_bytes, (size_t)batch, j->rqo, &d_bo)); }
+    RS_V(encode_left_vec(j, x_mont, &d_left));
+    // scratch: cut-off polynomials, mod-up images, partial sums
+    const size_t tmp_q = (size_t)(3 * p.in_msis + 2) * wq + n_com * wq, tmp_o = (size_t)(3 * p.out_msis) * wo + (size_t)(cols + 1) * p.out_msis * wo;
+    RS_VA(d_tmp, tmp_q + tmp_o);
+    const size_t n_sq_polys = n_com + p.out_msis + rows + nm + p.in_msis;
+    RS_VA(d_sq, n_sq_polys * 2 * JW);
+    RS_VA(d_ints, (size_t)(cols + batch) * JD * JW);
+    if (rc == RS_OK && cudaMallocAsync((void **)&d_flag, 4, st) != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_jindo_verify: cudaMallocAsync failed");
+    if (rc == RS_OK) cudaMemsetAsync(d_flag, 0, 4, st);
+    if (rc == RS_OK) {
+        u64 *q_acc = d_tmp, *q_T = q_acc + (size_t)p.in_msis * wq, *q_cut = q_T + (size_t)p.in_msis * wq, *q_t1 = q_cut + (size_t)p.in_msis * wq,
+            *q_t2 = q_t1 + wq, *q_up = q_t2 + wq;
+        u64 *o_comb = d_tmp + tmp_q, *o_S = o_comb + (size_t)p.out_msis * wo, *o_cut = o_S + (size_t)p.out_msis * wo, *o_part = o_cut + (size_t)p.out_msis * wo;
+        u64 *sq_o = d_sq, *sq_q = d_sq + (n_com + p.out_msis) * 2 * JW;
+        MatvecGeom G;
+        // ---- outer commitment (verifier.go:135-163)
+        if (batch > 1) {         // cutoff_i = sum_b com[b][i] (.) batchOut[b]
+            memset(&G, 0, sizeof(G));
+            G.O = 1; G.C = p.out_msis; G.K = batch; G.key_os = 0; G.key_ks = 1; G.x_cs = 1; G.x_ks = p.out_msis; G.out_cs = 1; G.out_os = 0;
+            RS_V(launch_matvec(o_comb, d_bo, d_coms, nullptr, G, j->rqo));
+        } else if (cudaMemcpyAsync(o_comb, d_coms, (size_t)p.out_msis * wo * 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+            rc = set_error(RS_ERR_CUDA, "rs_jindo_verify: copy failed");
+        }
+        memset(&G, 0, sizeof(G));
+        G.O = p.out_msis; G.C = cols + 1; G.K = p.in_msis;
+        G.key_os = (i64)n_com; G.key_cs = p.in_msis; G.key_ks = 1; G.x_cs = p.in_msis; G.x_ks = 1; G.out_cs = p.out_msis; G.out_os = 1;
+        RS_V(launch_matvec(o_part, j->d_ck_out, d_inc, nullptr, G, j->rqo));
+        if (rc == RS_OK) {
+            const size_t tot = (size_t)p.out_msis * wo;
+            reduce_cols_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(o_S, o_part, cols + 1, p.out_msis, Go);
+            scale_sub_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(o_cut, o_comb, o_S, nullptr, (size_t)p.out_msis, Go, So);
+            count_launch(2);
+        }
+        RS_V(launch_recon(j, true, false, nullptr, d_inc, n_com, nullptr, sq_o));
+        RS_V(launch_recon(j, true, false, nullptr, o_cut, (size_t)p.out_msis, nullptr, sq_o + n_com * 2 * JW));
+        // ---- inner commitment (verifier.go:165-205)
+        RS_V(launch_recon(j, true, true, q_up, d_inc, n_com, nullptr, nullptr));                 // ModUpQtoP + MForm + NTT
+        memset(&G, 0, sizeof(G));
+        G.O = 1; G.C = p.in_msis; G.K = cols; G.key_os = 0; G.key_ks = 1; G.x_cs = 1; G.x_ks = p.in_msis; G.out_cs = 1; G.out_os = 0;
+        G.has_addend = 1; G.add_cs = 1; G.add_os = 0;
+        RS_V(launch_matvec(q_acc, d_chal, q_up, q_up + (size_t)cols * p.in_msis * wq, G, j->rq));
+        memset(&G, 0, sizeof(G));
+        G.O = p.in_msis; G.C = 1; G.K = rows; G.key_os = rows; G.key_ks = 1; G.x_cs = rows; G.x_ks = 1; G.out_cs = p.in_msis; G.out_os = 1;
+        RS_V(launch_matvec(q_T, j->d_ck_in, d_enc, nullptr, G, j->rq));
+        G.K = p.mlwe; G.key_os = p.mlwe; G.x_cs = nm; G.accumulate = 1; G.has_addend = 1; G.add_cs = nm; G.add_os = 1;
+        RS_V(launch_matvec(q_T, j->d_ck_mlwe, d_ml, d_ml + (size_t)p.mlwe * wq, G, j->rq));
+        if (rc == RS_OK) {
+            const size_t tot = (size_t)p.in_msis * wq;
+            scale_sub_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(q_cut, q_acc, q_T, nullptr, (size_t)p.in_msis, Gq, Sq);
+            count_launch();
+        }
+        RS_V(launch_recon(j, false, false, nullptr, d_enc, (size_t)rows, nullptr, sq_q));
+        RS_V(launch_recon(j, false, false, nullptr, d_ml, (size_t)nm, nullptr, sq_q + (size_t)rows * 2 * JW));
+        RS_V(launch_recon(j, false, false, nullptr, q_cut, (size_t)p.in_msis, nullptr, sq_q + (size_t)(rows + nm) * 2 * JW));
+        // ---- consistency (verifier.go:207-227): sum_i left_i (.) Encode_i - sum_i chal_i (.) Partial_i - PartialMask == 0
+        memset(&G, 0, sizeof(G));
+        G.O = 1; G.C = 1; G.K = rows; G.key_os = 0; G.key_ks = 1; G.x_cs = rows; G.x_ks = 1; G.out_cs = 1; G.out_os = 0;
+        RS_V(launch_matvec(q_t1, d_left, d_enc, nullptr, G, j->rq));
+        G.K = cols; G.x_cs = cols;
+        RS_V(launch_matvec(q_t2, d_chal, d_part, nullptr, G, j->rq));
+        if (rc == RS_OK) {
+            nonzero_kernel<<<(unsigned)((wq + 255) / 256), 256, 0, st>>>(d_flag, q_t1, q_t2, d_part + (size_t)cols * wq, wq, Gq);
+            count_launch();
+        }
+        // ---- evaluation (verifier.go:229-260): centred coefficients of the Partial (and batch challenge) polynomials
+        RS_V(launch_recon(j, false, false, nullptr, d_part, (size_t)cols, d_ints, nullptr));
+        if (batch > 1) RS_V(launch_recon(j, false, false, nullptr, d_bq, (size_t)batch, d_ints + (size_t)cols * JD * JW, nullptr));
+    }
+    unsigned h_flag = 1;
+    if (rc == RS_OK) {
+        h_sq.resize(n_sq_polys * 2 * JW); h_ints.resize((size_t)(cols + batch) * JD * JW);
+        if (cudaMemcpyAsync(h_sq.data(), d_sq, h_sq.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(h_ints.data(), d_ints, (size_t)(cols + (batch > 1 ? batch : 0)) * JD * JW * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            rc = set_error(RS_ERR_CUDA, "rs_jindo_verify: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    for (u64 *ptr : {d_part, d_enc, d_ml, d_inc, d_coms, d_chal, d_bq, d_bo, d_left, d_tmp, d_sq, d_ints}) if (ptr) cudaFreeAsync(ptr, st);
+    if (d_flag) cudaFreeAsync(d_flag, st);
+#undef RS_V
+#undef RS_VA
+#undef RS_VU
+    if (rc) return rc;
+    // ---- host tail: norms, and the decode + inner product of verifyEval in the committed field
+    u64 tot[2 * JW + 2];
+    sq_total(h_sq.data(), n_com + p.out_msis, tot);
+    if (isqrt_lt(tot, 2 * JW + 2, in_com_dcmp_two_nm)) *checks |= 1;                  // verifyOuterCommitment
+    sq_total(h_sq.data() + (n_com + p.out_msis) * 2 * JW, (size_t)rows + nm + p.in_msis, tot);
+    if (isqrt_lt(tot, 2 * JW + 2, res_two_nm)) *checks |= 2;                          // verifyInnerCommitment
+    if (h_flag == 0) *checks |= 4;                                                     // verifyConsistency
+    {
+        const rs_field *f = j->f;
+        const int L64 = f->L64;
+        auto to_field = [&](const u64 *V, uint32_t *out /* Montgomery */) {          // SetBigInt of a centred JW-word integer
+            const bool neg = (V[JW - 1] >> 63) != 0;
+            u64 M[JW];
+            if (neg) { u64 cy = 1; for (int i = 0; i < JW; i++) { const u64 t = ~V[i] + cy; cy = (cy && t == 0); M[i] = t; } }
+            else for (int i = 0; i < JW; i++) M[i] = V[i];
+            uint32_t acc[RS_MAX_NL] = {0}, chunk[RS_MAX_NL], t[RS_MAX_NL];
+            const int n_chunks = (JW + L64 - 1) / L64;
+            for (int ch = n_chunks - 1; ch >= 0; ch--) {                               // value = sum chunk_k R^k, Horner in Montgomery form
+                host_mul(f, acc, acc, f->r2);                                          // acc * R
+                memset(chunk, 0, sizeof(chunk));
+                for (int w = 0; w < L64 && ch * L64 + w < JW; w++) { chunk[2 * w] = (uint32_t)M[ch * L64 + w]; chunk[2 * w + 1] = (uint32_t)(M[ch * L64 + w] >> 32); }
+                host_mul(f, t, chunk, f->r2);                                          // to Montgomery (chunk < R; result canonical)
+                host_add(f, acc, acc, t);
+            }
+            if (neg) { uint32_t z[RS_MAX_NL] = {0}; bool any = false; for (int i = 0; i < NL; i++) any |= acc[i] != 0;
+                       if (any) { u64 br = 0; for (int i = 0; i < NL; i++) { const u64 dd = (u64)f->q[i] - acc[i] - br; z[i] = (uint32_t)dd; br = (dd >> 63) & 1; } memcpy(acc, z, 4 * NL); } }
+            memcpy(out, acc, 4 * NL);
+        };
+        uint32_t base_m[RS_MAX_NL];
+        host_set_u64(f, base_m, p.base);
+        auto decode_slot = [&](const u64 *poly_ints, int slot, uint32_t *out) {       // Encoder.DecodeTo (encoder.go:204-219)
+            uint32_t acc[RS_MAX_NL] = {0}, c[RS_MAX_NL];
+            for (int e = p.exp - 1; e >= 0; e--) {
+                host_mul(f, acc, acc, base_m);
+                to_field(poly_ints + (size_t)(e * p.slots + slot) * JW, c);
+                host_add(f, acc, acc, c);
+            }
+            memcpy(out, acc, 4 * NL);
+        };
+        uint32_t yb[RS_MAX_NL] = {0}, t[RS_MAX_NL], dc[RS_MAX_NL];
+        if (batch > 1) {
+            for (int b = 0; b < batch; b++) {
+                decode_slot(h_ints.data() + (size_t)(cols + b) * JD * JW, 0, dc);
+                host_mul(f, t, dc, (const uint32_t *)(ys_mont + (size_t)b * L64));
+                host_add(f, yb, yb, t);
+            }
+        } else memcpy(yb, ys_mont, 4 * NL);
+        uint32_t test[RS_MAX_NL] = {0}, xp[RS_MAX_NL];
+        memcpy(xp, f->one, 4 * NL);                                                    // rightVec[k] = x^k (utils.go:75-82)
+        for (int i = 0; i < cols; i++)
+            for (int s2 = 0; s2 < p.slots; s2++) {
+                decode_slot(h_ints.data() + (size_t)i * JD * JW, s2, dc);
+                host_mul(f, t, xp, dc);
+                host_add(f, test, test, t);
+                host_mul(f, xp, xp, (const uint32_t *)x_mont);
+            }
+        if (memcmp(test, yb, 4 * NL) == 0) *checks |= 8;                                // verifyEval
+    }
+    return RS_OK;
+}
+
+static void put_u64le(uint8_t *&o, uint64_t v) { for (int i = 0; i < 8; i++) *o++ = (uint8_t)(v >> (8 * i)); }
+
+long long rs_jindo_poly_write_to(const uint64_t *poly, int n_limbs, int d, uint8_t *out, size_t cap) {
+    if ((!poly && out) || n_limbs < 0 || d < 0) return rs::set_error(RS_ERR_ARG, "rs_jindo_poly_write_to: bad argument");
+    const size_t need = 8 + (size_t)n_limbs * (8 + (size_t)d * 8);
+    if (!out) return (long long)need;
+    if (cap < need) return rs::set_error(RS_ERR_ARG, "rs_jindo_poly_write_to: buffer too small");
+    uint8_t *o = out;
+    put_u64le(o, (uint64_t)n_limbs);
+    for (int l = 0; l < n_limbs; l++) {
+        put_u64le(o, (uint64_t)d);
+        for (int c = 0; c < d; c++) put_u64le(o, poly[(size_t)l * d + c]);
+    }
+    return (long long)need;
+}
+
+long long rs_jindo_commitment_write_raw(const rs_jindo *j, const uint64_t *commitment, uint8_t *out, size_t cap) {
+    if (!j || (!commitment && out)) return rs::set_error(RS_ERR_ARG, "rs_jindo_commitment_write_raw: null argument");
+    const rs_jindo_params &p = j->p;
+    const int nl = p.n_q > p.n_qout ? p.n_q : p.n_qout, d = JD;
+    const size_t per = 8 + (size_t)nl * (8 + (size_t)d * 8), need = per * p.out_msis;
+    if (!out) return (long long)need;
+    if (cap < need) return rs::set_error(RS_ERR_ARG, "rs_jindo_commitment_write_raw: buffer too small");
+    uint8_t *o = out;
+    for (int i = 0; i < p.out_msis; i++) {
+        put_u64le(o, (uint64_t)nl);
+        for (int l = 0; l < nl; l++) {
+            put_u64le(o, (uint64_t)d);
+            for (int c = 0; c < d; c++) put_u64le(o, l < p.n_qout ? commitment[((size_t)i * p.n_qout + l) * d + c] : 0);
+        }
+    }
+    return (long long)need;
 }
 
 int rs_opening_alloc_zero(rs_jindo *j, rs_opening **out) {
@@ -2036,7 +2400,7 @@ fail:
         // optional (RS_JINDO_PREFETCH=1): generate the next Commit's draws now, behind this Commit's remaining kernels.
         // Measured neutral at 2^22 (5.9 ms e2e either way: the AES kernels take the same SM time wherever they run), so
         // it is off by default; it pays when the host leaves gaps between Commits.
-        if (rc == RS_OK && getenv("RS_JINDO_PREFETCH")) uniform_stream_prefetch(j->twin_stream, twin * d);
+        if (rc == RS_OK && j->prefetch) uniform_stream_prefetch(j->twin_stream, twin * d);
     }
     cudaFreeAsync(d_com, current_stream());
     if (rc) { if (!reuse) rs_opening_free(o); return rc; }
@@ -2213,6 +2577,7 @@ static int partial_impl(rs_jindo *j, const rs_opening *o, const u64 *d_left, uin
 
 int rs_jindo_partial(rs_jindo *j, const rs_opening *o, const uint64_t *left, uint64_t *partial_out) {
     RS_REQUIRE(j && o && left && partial_out, RS_ERR_ARG, "rs_jindo_partial: null argument");
+    RS_REQUIRE(o->j == j, RS_ERR_ARG, "rs_jindo_partial: opening belongs to another prover");
     u64 *d_left = nullptr;
     int rc = upload(&d_left, (const u64 *)left, (size_t)j->p.rows * pq(j));
     if (rc == RS_OK) rc = partial_impl(j, o, d_left, partial_out);
@@ -2269,6 +2634,7 @@ static int encode_left_vec(rs_jindo *j, const uint64_t *x_mont, u64 **d_left) {
 
 int rs_jindo_partial_at(rs_jindo *j, const rs_opening *o, const uint64_t *x_mont, uint64_t *partial_out) {
     RS_REQUIRE(j && o && x_mont && partial_out, RS_ERR_ARG, "rs_jindo_partial_at: null argument");
+    RS_REQUIRE(o->j == j, RS_ERR_ARG, "rs_jindo_partial_at: opening belongs to another prover");
     u64 *d_left = nullptr;
     int rc = encode_left_vec(j, x_mont, &d_left);
     if (rc == RS_OK) rc = partial_impl(j, o, d_left, partial_out);
@@ -2342,6 +2708,7 @@ static int respond_impl(rs_jindo *j, const rs_opening *o, const u64 *d_ch, uint6
 
 int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, uint64_t *enc_out, uint64_t *mlwe_out) {
     RS_REQUIRE(j && o && chals && enc_out && mlwe_out, RS_ERR_ARG, "rs_jindo_respond: null argument");
+    RS_REQUIRE(o->j == j, RS_ERR_ARG, "rs_jindo_respond: opening belongs to another prover");
     u64 *d_ch = nullptr;
     int rc = upload(&d_ch, (const u64 *)chals, (size_t)j->p.cols * pq(j));
     if (rc == RS_OK) rc = respond_impl(j, o, d_ch, enc_out, mlwe_out);
@@ -2351,6 +2718,7 @@ int rs_jindo_respond(rs_jindo *j, const rs_opening *o, const uint64_t *chals, ui
 
 int rs_jindo_respond_bytes(rs_jindo *j, const rs_opening *o, const uint8_t *chal_bytes, uint64_t *enc_out, uint64_t *mlwe_out) {
     RS_REQUIRE(j && o && chal_bytes && enc_out && mlwe_out, RS_ERR_ARG, "rs_jindo_respond_bytes: null argument");
+    RS_REQUIRE(o->j == j, RS_ERR_ARG, "rs_jindo_respond_bytes: opening belongs to another prover");
     u64 *d_ch = nullptr;
     int rc = encode_challenges(j, chal_bytes, (size_t)j->p.cols, j->rq, &d_ch);
     if (rc == RS_OK) rc = respond_impl(j, o, d_ch, enc_out, mlwe_out);
@@ -2389,6 +2757,7 @@ static int opening_mul_add_impl(rs_jindo *j, rs_opening *acc, const rs_opening *
 
 int rs_opening_mul_add_bytes(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint8_t *chal16) {
     RS_REQUIRE(j && acc && o && chal16, RS_ERR_ARG, "rs_opening_mul_add_bytes: null argument");
+    RS_REQUIRE(o->j == j && acc->j == j, RS_ERR_ARG, "rs_opening_mul_add_bytes: opening belongs to another prover");
     u64 *d_cq = nullptr, *d_co = nullptr;
     int rc = encode_challenges(j, chal16, 1, j->rq, &d_cq);
     if (rc == RS_OK) rc = encode_challenges(j, chal16, 1, j->rqo, &d_co);
@@ -2400,6 +2769,7 @@ int rs_opening_mul_add_bytes(rs_jindo *j, rs_opening *acc, const rs_opening *o, 
 
 int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout) {
     RS_REQUIRE(j && acc && o && chal_q && chal_qout, RS_ERR_ARG, "rs_opening_mul_add: null argument");
+    RS_REQUIRE(o->j == j && acc->j == j, RS_ERR_ARG, "rs_opening_mul_add: opening belongs to another prover");
     u64 *d_cq = nullptr, *d_co = nullptr;
     int rc = upload(&d_cq, (const u64 *)chal_q, pq(j));
     if (rc == RS_OK) rc = upload(&d_co, (const u64 *)chal_qout, pqo(j));

@@ -110,18 +110,32 @@ int pointwise(int op, const rs_field *f, uint32_t *out, const uint32_t *a, const
 // ---------------------------------------------------------------------------
 // evalCircuit (buckler/prover.go:355-379), fused: one pass over the witnesses
 // ---------------------------------------------------------------------------
+// The term list and the constraint coefficients are the same for every coefficient of the polynomial: each CTA stages
+// them in shared memory once (a few KB), so the per-coefficient loop reads witnesses from HBM / L1 and nothing else.
 template <int NL, int QS>
-__global__ void __launch_bounds__(256) eval_circuit_kernel(uint32_t *out, const uint32_t *pw, const uint32_t *w,
-                                                           const rs_term *terms, int n_terms, const uint32_t *coeffs,
+__global__ void __launch_bounds__(128) eval_circuit_kernel(uint32_t *out, const uint32_t *pw, const uint32_t *w,
+                                                           const rs_term *terms, int n_terms, const uint32_t *coeffs, int n_coeffs,
                                                            const __grid_constant__ Scalar<NL> bc,
-                                                           const __grid_constant__ FieldParams<NL> F, size_t rank) {
+                                                           const __grid_constant__ FieldParams<NL> F, size_t rank, int staged) {
+    extern __shared__ __align__(16) uint32_t ec_smem[];
+    const rs_term *T = terms;
+    const uint32_t *CO = coeffs;
+    if (staged) {
+        constexpr int TW = sizeof(rs_term) / 4;
+        uint32_t *st = ec_smem, *sc = ec_smem + n_terms * TW;
+        for (int i = threadIdx.x; i < n_terms * TW; i += blockDim.x) st[i] = reinterpret_cast<const uint32_t *>(terms)[i];
+        for (int i = threadIdx.x; i < n_coeffs * NL; i += blockDim.x) sc[i] = coeffs[i];
+        __syncthreads();
+        T = reinterpret_cast<const rs_term *>(st);
+        CO = sc;
+    }
     for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < rank; j += (size_t)gridDim.x * blockDim.x) {
         uint32_t acc[NL], ev[NL];
 #pragma unroll
         for (int l = 0; l < NL; l++) { acc[l] = 0; ev[l] = 0; }
-        int cur = n_terms ? terms[0].constraint : -1;
+        int cur = n_terms ? T[0].constraint : -1;
         for (int k = 0; k <= n_terms; k++) {
-            if (k == n_terms || terms[k].constraint != cur) {
+            if (k == n_terms || T[k].constraint != cur) {
                 // eval *= batchConst ; pOut += eval   (prover.go:374-375)
                 uint32_t t[NL];
                 mont_mul<NL, QS>(t, ev, bc.v, F);
@@ -129,18 +143,20 @@ __global__ void __launch_bounds__(256) eval_circuit_kernel(uint32_t *out, const 
 #pragma unroll
                 for (int l = 0; l < NL; l++) ev[l] = 0;
                 if (k == n_terms) break;
-                cur = terms[k].constraint;
+                cur = T[k].constraint;
             }
-            const rs_term tm = terms[k];
+            const rs_term &tm = T[k];
             uint32_t term[NL], fac[NL], t[NL];
-            ld_elem<NL>(term, coeffs + (size_t)tm.coeff * NL);
+#pragma unroll
+            for (int l = 0; l < NL; l++) term[l] = CO[(size_t)tm.coeff * NL + l];
             if (tm.pw >= 0) {
                 ld_elem<NL>(fac, pw + ((size_t)tm.pw * rank + j) * NL);
                 mont_mul<NL, QS>(t, term, fac, F);
 #pragma unroll
                 for (int l = 0; l < NL; l++) term[l] = t[l];
             }
-            for (int x = 0; x < tm.n_w; x++) {
+            const int nw = tm.n_w;
+            for (int x = 0; x < nw; x++) {
                 ld_elem<NL>(fac, w + ((size_t)tm.w[x] * rank + j) * NL);
                 mont_mul<NL, QS>(t, term, fac, F);
 #pragma unroll
@@ -153,14 +169,16 @@ __global__ void __launch_bounds__(256) eval_circuit_kernel(uint32_t *out, const 
 }
 
 int eval_circuit(const rs_field *f, uint32_t *out, const uint32_t *pw, const uint32_t *w, const rs_term *d_terms,
-                 int n_terms, const uint32_t *d_coeffs, const uint32_t *bc, size_t rank) {
+                 int n_terms, const uint32_t *d_coeffs, int n_coeffs, const uint32_t *bc, size_t rank) {
 #define CALL(NL, QS)                                                                                       \
     {                                                                                                      \
         FieldParams<NL> F = make_params<NL>(f);                                                            \
         Scalar<NL> s;                                                                                      \
         for (int i = 0; i < NL; i++) s.v[i] = bc[i];                                                       \
-        eval_circuit_kernel<NL, QS><<<grid_for(rank, 128), 128, 0, current_stream()>>>(out, pw, w, d_terms, n_terms, \
-                                                                                  d_coeffs, s, F, rank);   \
+        const size_t smem = (size_t)n_terms * sizeof(rs_term) + (size_t)n_coeffs * NL * 4;                 \
+        const int staged = smem <= 40 * 1024;                                                              \
+        eval_circuit_kernel<NL, QS><<<grid_for(rank, 128), 128, staged ? smem : 0, current_stream()>>>(out, pw, w, d_terms, n_terms, \
+                                                                                  d_coeffs, n_coeffs, s, F, rank, staged);   \
     }
     RS_FIELD_DISPATCH(f, CALL)
 #undef CALL

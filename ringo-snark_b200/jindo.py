@@ -196,6 +196,32 @@ class Prover:
         key = np.frombuffer(h[:32], dtype=np.uint8).copy(); iv = np.frombuffer(h[32:48], dtype=np.uint8).copy()
         check(lib().rs_jindo_set_twin_stream(self.h, _vp(key), _vp(iv)))
 
+    def Verify(self, x_mont, coms, batch_bytes, chal_bytes, ys_mont, pf, in_com_dcmp_two_nm, res_two_nm):
+        """Verifier.Verify's arithmetic on the device (rs_jindo_verify; jindo/verifier.go:50-282).  coms: [batch, out_msis,
+        n_qout, 256]; pf: dict Partial / PartialMask / Encode / MLWE / InCommit (as Evaluate returns them); the SHAKE128
+        challenge bytes come from the caller's transcript.  Returns the check bits (15 = accepted)."""
+        arr = lambda a: np.ascontiguousarray(a, dtype=np.uint64)
+        keep = [arr(pf["Partial"]), arr(pf["PartialMask"]), arr(pf["Encode"]), arr(pf["MLWE"]), arr(pf["InCommit"]), arr(coms),
+                arr(x_mont), arr(ys_mont)]
+        P = capi.JindoProof()
+        P.partial, P.partial_mask, P.encode, P.mlwe, P.incommit = (_vp(a) for a in keep[:5])
+        out = ctypes.c_int(0)
+        batch = keep[5].shape[0]
+        check(lib().rs_jindo_verify(self.h, _vp(keep[6]), _vp(keep[5]), batch, ctypes.c_char_p(bytes(batch_bytes)) if batch > 1 else None,
+                                    ctypes.c_char_p(bytes(chal_bytes)), _vp(keep[7]), ctypes.byref(P), float(in_com_dcmp_two_nm),
+                                    float(res_two_nm), ctypes.byref(out)))
+        return out.value
+
+    def CommitmentWriteRaw(self, com):
+        """Commitment.WriteRawTo bytes (jindo/entities.go:96-100) through the C ABI (rs_jindo_commitment_write_raw)"""
+        com = np.ascontiguousarray(com, dtype=np.uint64)
+        n = lib().rs_jindo_commitment_write_raw(self.h, _vp(com), None, 0)
+        buf = ctypes.create_string_buffer(int(n))
+        got = lib().rs_jindo_commitment_write_raw(self.h, _vp(com), ctypes.cast(buf, c_vp), int(n))
+        if got != n:
+            raise capi.RingoError(int(got), "rs_jindo_commitment_write_raw")
+        return buf.raw
+
     def SetMlweSeed(self, seed, mlwe_std):
         """Prover.mlweSampler on the device (rs_jindo_set_mlwe_stream): seed of its UniformSampler, sigma = params.mlweStdDev"""
         tab, lo = compute_cdt(0.0, mlwe_std)

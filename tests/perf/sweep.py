@@ -21,6 +21,7 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 out_path = next((a[6:] for a in sys.argv[1:] if a.startswith("--out=")), None)
 do_ntt = not args or "ntt" in args
 do_commit = not args or "commit" in args
+do_k3 = not args or "k3" in args
 
 import torch
 rs = bench.product(); L = rs.load()
@@ -134,8 +135,85 @@ def commit_sweep():
     return rows
 
 
+def k3_sweep():
+    """SURVEY 8d "pointwise ops": single element-wise ops (HBM bound), the fused evalCircuit of the two example circuits
+    (integer bound), QuoRemByVanishing (HBM) -- both fractions for each, at the circuits' own embedding ranks."""
+    from oracle import buckler_ref as B
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_buckler import ct_params, BFV_T
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    g = ctypes.c_double(); rs.check(L.rs_bench_imad_peak(5, ctypes.byref(g))); imad = g.value
+    rows = []
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    for name, circuit, N in (("zp128", "mult", 1 << 13), ("zp240", "ct", 1 << 14)):
+        q = pyref.modulus(name); f = rs.Field(q); fo = oracle.Field(q)
+        if circuit == "mult":
+            define, n_pw, n_w = B.mult_circuit(N)
+        else:
+            delta, eb = ct_params(q, N)
+            define, n_pw, n_w = B.ciphertext_circuit(N, delta, BFV_T, eb)
+        ctx = B.Context(q, N, n_pw, n_w); define(ctx, fo)
+        E = 1 << (ctx.arith_max_rank - 1).bit_length()
+        terms, coeffs = ctx.terms(ctx.arith_constraints)
+        nl = 2 * f.L; mul_imad = 2 * nl * nl + nl
+        n_mul = sum((1 if pw >= 0 else 0) + len(ws) for (_, _, pw, ws) in terms) + len(ctx.arith_constraints)   # MulTo + ScalarMulTo
+        inputs = len({("w", x) for (_, _, _, ws) in terms for x in ws} | {("pw", pw) for (_, _, pw, _) in terms if pw >= 0})
+        rng = np.random.default_rng(3)
+        wb = rs.Batch(f, ctx.w_cnt, E).upload(bench.synthetic_polys(q, f.L, ctx.w_cnt, E, 1))
+        pwb = rs.Batch(f, ctx.pw_cnt, E).upload(bench.synthetic_polys(q, f.L, ctx.pw_cnt, E, 2))
+        out = rs.Batch(f, 4, E)
+        T = (rs.capi.Term * len(terms))()
+        for k, (ci, co, pw, ws) in enumerate(terms):
+            T[k].constraint, T[k].coeff, T[k].pw, T[k].n_w = ci, co, pw, len(ws)
+            for j, x in enumerate(ws):
+                T[k].w[j] = x
+        cm = fo.to_mont(coeffs); bc = fo.to_mont([12345])[0]
+        u64p = rs.capi.c_u64p
+        ms = timed(lambda: rs.check(L.rs_eval_circuit(out.h, 0, pwb.h, wb.h, T, len(terms), cm.ctypes.data_as(u64p), len(coeffs), bc.ctypes.data_as(u64p))))
+        byts = (inputs + 1) * 8 * f.L * E
+        rows.append({"op": f"evalCircuit ({circuit}, {len(ctx.arith_constraints)} constraints, {len(terms)} terms)", "field": name, "rank": E, "ms": round(ms, 4),
+                     "alg_gbs": round(byts / ms / 1e6, 1), "hbm_frac": round(byts / ms / 1e6 / hbm, 3),
+                     "alg_gimad_s": round(n_mul * mul_imad * E / ms / 1e6, 1), "imad_frac": round(n_mul * mul_imad * E / ms / 1e6 / imad, 3),
+                     "bound": "integer", "unfused_passes": 2 * n_mul + len(terms)})
+        for opname, fn, reads, muls in (("MulTo", lambda: rs.check(L.rs_vec_mul(out.h, 1, wb.h, 0, wb.h, 1, 1)), 2, 1),
+                                        ("MulAddTo", lambda: rs.check(L.rs_vec_mul_add(out.h, 1, wb.h, 0, wb.h, 1, 1)), 3, 1),
+                                        ("AddTo", lambda: rs.check(L.rs_vec_add(out.h, 1, wb.h, 0, wb.h, 1, 1)), 2, 0),
+                                        ("QuoRemByVanishing", lambda: rs.check(L.rs_quorem_vanishing(out.h, 2, out.h, 3, wb.h, 0, N)), 1, 0)):
+            ms = timed(fn, 50)
+            writes = 2 if opname.startswith("QuoRem") else 1
+            byts = (reads + writes) * 8 * f.L * E
+            rows.append({"op": opname, "field": name, "rank": E, "ms": round(ms, 4), "alg_gbs": round(byts / ms / 1e6, 1),
+                         "hbm_frac": round(byts / ms / 1e6 / hbm, 3), "alg_gimad_s": round(muls * mul_imad * E / ms / 1e6, 1),
+                         "imad_frac": round(muls * mul_imad * E / ms / 1e6 / imad, 3), "bound": "hbm (one polynomial = %.1f MB: launch latency at this size)" % (8 * f.L * E / 1e6)})
+        # the same single ops on a batch large enough to leave L2 and hide the launch (64 polynomials)
+        big = rs.Batch(f, 192, E).upload(np.resize(bench.synthetic_polys(q, f.L, 8, E, 5), (192, E, f.L)))
+        for opname, fn, reads, muls in (("MulTo x64", lambda: rs.check(L.rs_vec_mul(big.h, 128, big.h, 0, big.h, 64, 64)), 2, 1),
+                                        ("AddTo x64", lambda: rs.check(L.rs_vec_add(big.h, 128, big.h, 0, big.h, 64, 64)), 2, 0)):
+            ms = timed(fn, 20)
+            byts = (reads + 1) * 8 * f.L * E * 64
+            rows.append({"op": opname, "field": name, "rank": E, "ms": round(ms, 4), "alg_gbs": round(byts / ms / 1e6, 1),
+                         "hbm_frac": round(byts / ms / 1e6 / hbm, 3), "alg_gimad_s": round(muls * mul_imad * E * 64 / ms / 1e6, 1),
+                         "imad_frac": round(muls * mul_imad * E * 64 / ms / 1e6 / imad, 3), "bound": "hbm"})
+        del wb, pwb, out, big
+        torch.cuda.empty_cache()
+    return {"hbm_peak_gbs": hbm, "imad_wide_peak_g_s": round(imad, 1), "rows": rows}
+
+
 if do_ntt:
     doc["ntt_sweep"] = ntt_sweep()
+if do_k3:
+    doc["k3_sweep"] = k3_sweep()
 if do_commit:
     doc["commit_sweep"] = commit_sweep()
 s = json.dumps(doc)

@@ -166,6 +166,24 @@ def test_gpu_proof_verifies(rs, batch):
     assert vrf.verify(x, coms, ys, pf)
     bad = list(ys); bad[0] = (bad[0] + 1) % q
     assert not vrf.verify(x, coms, bad, pf)
+    # ---- the same decisions from the device verifier (rs_jindo_verify), check by check
+    ymont = lambda vals: fo.to_mont(vals)
+    bbytes = bb if batch > 1 else b""
+    dv = lambda ys_, pf_, coms_=coms: gp.Verify(xm, coms_, bbytes, cs, ymont(ys_), pf_, p.in_com_dcmp_two_nm, p.res_two_nm)
+    assert dv(ys, pf) == 15
+    assert dv(bad, pf) == 7                                   # only verifyEval fails
+    import copy
+    t1 = copy.deepcopy(pf); t1["Encode"][1][0][5] = (t1["Encode"][1][0][5] + 1) % p.q_primes[0]
+    assert not vrf.verify(x, coms, ys, t1)
+    c1 = dv(ys, t1); assert c1 != 15 and not (c1 & 4)         # breaks the consistency equation (and the inner norm)
+    t2 = copy.deepcopy(pf); t2["InCommit"][3][0][7] = (t2["InCommit"][3][0][7] + 12345) % p.qout_primes[0]
+    assert not vrf.verify(x, coms, ys, t2)
+    c2 = dv(ys, t2); assert not (c2 & 1) or not (c2 & 2)      # outer / inner commitment equations leave the norm ball
+    t3 = copy.deepcopy(pf); t3["Partial"][0][0][0] = (t3["Partial"][0][0][0] + 1) % p.q_primes[0]
+    assert not vrf.verify(x, coms, ys, t3)
+    c3 = dv(ys, t3); assert c3 != 15
+    coms_bad = copy.deepcopy(coms); coms_bad[0][0][0][1] = (coms_bad[0][0][0][1] + 1) % p.qout_primes[0]
+    assert not vrf.verify(x, coms_bad, ys, pf) and not (dv(ys, pf, coms_bad) & 1)
 
 
 def _prover_pair(rs, name, N, batch, seed):
@@ -196,9 +214,9 @@ def test_commit_with_device_twin_stream(rs, monkeypatch):
     Commitment as the oracle, whose encoder owns one stateful sampler (encoder.go:56-62).  With RS_JINDO_PREFETCH every Commit pre-generates
     the next Commit's draws (uniform_stream_prefetch): the lengths below make the prefetch miss (different number of
     rows), hit twice, and miss again, and a host-side draw in between moves the stream under a pending prefetch."""
+    monkeypatch.setenv("RS_JINDO_PREFETCH", "1")       # (read by the library when the prover handle is created)
     q, fo, fg, p, tape, prv, gp = _prover_pair(rs, "zp128", 700, 2, b"dev-twin")
     gp.SetTwinSeed(prv.ecd.twin.base.seed)
-    monkeypatch.setenv("RS_JINDO_PREFETCH", "1")       # (read by the library at every Commit)
     for step, length in enumerate((700, 333, 333, 333, 40, 700)):
         if step == 4:                                  # the oracle's sampler hands 777 draws to somebody else
             assert np.array_equal(gp.TwinStreamDraw(777), prv.ecd.twin.base.sample_many(777))
@@ -571,3 +589,24 @@ def test_commit_from_seeds_only(rs, name, N, batch, length):
                 assert np.array_equal(open_g.Encode(i, j), polys_array(open_o.Encode[i][j])), ("Encode", it, i, j)
             for j in range(p.mlwe + p.in_msis):
                 assert np.array_equal(open_g.MLWE(i, j), polys_array(open_o.MLWE[i][j])), ("MLWE", it, i, j)
+
+
+def test_wire_format_through_the_abi(rs):
+    """rs_jindo_commitment_write_raw / rs_jindo_poly_write_to give the bytes of the restated Commitment.WriteRawTo /
+    ring.Poly.WriteTo (entities.go:96-100; the ringQ limb-count quirk of NewCommitment included: zp255 at N = 1024 has
+    2 ringQ limbs and 1 ringQOut limb)."""
+    import ctypes
+    q, fo, fg, p, tape, prv, gp = _prover_pair(rs, "zp255", 1024, 1, b"wire")
+    assert len(p.q_primes) == 2 and len(p.qout_primes) == 1
+    v = [J.field_set_random(tape, q) for _ in range(100)]
+    com_o, _ = prv.commit(v)
+    B = rs.Batch(fg, 1, 128)
+    host = np.zeros((1, 128, fo.L), dtype=np.uint64); host[0, :100] = fo.to_mont(v)
+    B.upload(host)
+    com_g, _ = gp.Commit(B, 0, 100, tape_arrays(fo, p, prv.trace))
+    assert gp.CommitmentWriteRaw(com_g) == J.commitment_write_raw(p, com_o)
+    poly = np.ascontiguousarray(polys_array(prv.ck.In[0][0]))
+    n = rs.lib().rs_jindo_poly_write_to(poly.ctypes.data_as(ctypes.c_void_p), poly.shape[0], poly.shape[1], None, 0)
+    buf = ctypes.create_string_buffer(int(n))
+    assert rs.lib().rs_jindo_poly_write_to(poly.ctypes.data_as(ctypes.c_void_p), poly.shape[0], poly.shape[1], ctypes.cast(buf, ctypes.c_void_p), int(n)) == n
+    assert buf.raw == J.poly_write_to(prv.ck.In[0][0])
