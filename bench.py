@@ -303,6 +303,16 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
     ml_pin = torch.empty((p.mlwe + p.in_msis, nq, p.d), dtype=torch.int64).pin_memory()
     resp_out = (enc_pin.numpy().view(np.uint64), ml_pin.numpy().view(np.uint64))
     respond_bytes_ms = wall(lambda: gp.RespondBytes(op, chal_bytes, out=resp_out))
+    # prove -> verify: Verifier.Verify's arithmetic on the device (rs_jindo_verify) for the proof just produced
+    # (batch 1: the transcript bytes are the ones the responses were computed with, y = v(x) by the Horner kernel)
+    part_v = gp.PartialAt(op, x_mont)
+    enc_v, ml_v = gp.RespondBytes(op, chal_bytes)
+    pf_v = {"Partial": part_v[:p.cols], "PartialMask": part_v[p.cols], "Encode": enc_v, "MLWE": ml_v,
+            "InCommit": np.stack([op.InCommit(k) for k in range(p.in_com_dcmp_len)])}
+    y_mont = np.zeros(f.L, dtype=np.uint64)
+    rs.check(L.rs_poly_evaluate(B.h, 0, N, x_mont.ctypes.data_as(rs.capi.c_u64p), y_mont.ctypes.data_as(rs.capi.c_u64p)))
+    verify_checks = gp.Verify(x_mont, com_ref[None], b"", chal_bytes, y_mont[None], pf_v, p.in_com_dcmp_two_nm, p.res_two_nm)
+    verify_ms = wall(lambda: gp.Verify(x_mont, com_ref[None], b"", chal_bytes, y_mont[None], pf_v, p.in_com_dcmp_two_nm, p.res_two_nm))
     # e2e: committed vector + the whole tape start in pinned host memory
     nb = v_host.numel() * 8
     tape_bytes = sum(t.numel() * 8 for t in pin.values())
@@ -382,6 +392,9 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
                                              "cold (includes table setup of the prover handle); no key bytes cross PCIe"},
         "open": {"partial_ms": partial_ms, "respond_ms": respond_ms, "partial_at_ms": partial_at_ms, "respond_bytes_ms": respond_bytes_ms,
                  "commit_plus_open_polys_per_s": world * 1e3 / (ms + partial_at_ms + respond_bytes_ms),
+                 "verify_ms": verify_ms, "verify_checks": int(verify_checks),
+                 "verify_note": "rs_jindo_verify on the proof of this Commit + open (host proof arrays in, 4 check bits out; 15 = accepted; "
+                                "consistency + evaluation are exact statements, the two norm checks depend on the synthetic noise tape)",
                  "note": "Evaluate's two passes over the 1.08 GB Opening: partial/respond = host-encoded vectors in, pageable results out; "
                          "partial_at/respond_bytes = x and SHAKE bytes in (vectors encoded on the device), results into pinned memory"},
         "sharded": sharded,

@@ -138,6 +138,10 @@ typedef struct rs_term {
     int32_t n_w;                 /* number of witness factors (<= RS_TERM_MAX_W) */
     int32_t w[RS_TERM_MAX_W];    /* witness poly indices in `w` batch */
 } rs_term;
+/* Encoder.RandEncodeTo's blinding step (buckler/encoder.go:50-54) for n polynomials of a batch at once, after
+ * rs_ntt_inverse_embed: coefficient N <- blind[i] (a MustSetRandom element, Montgomery limbs, host), coefficient 0 -= it. */
+int rs_rand_encode_blind(rs_batch *b, size_t poly0, size_t n, size_t N, const uint64_t *blind_mont);
+
 /* Prover.evalCircuit (buckler/prover.go:355-379) fused into one pass:
  * out[j] = sum_c batch_const * sum_{terms of c} coeff * pw[j] * prod w[j]. */
 int rs_eval_circuit(rs_batch *out, size_t out_poly, const rs_batch *pw, const rs_batch *w,

@@ -119,13 +119,8 @@ class Prover:
         vals = Batch(f, wc + pc, N).upload(np.concatenate([w_mont, pw_mont]))
         ecd = Batch(f, wc + pc, E)
         check(L.rs_ntt_inverse_embed(self.enc.h, ecd.h, 0, vals.h, 0, wc + pc, 1))
-        tmp = Batch(f, 2, 1)
-        for i in range(wc):                              # RandEncodeTo: c[N] <- r ; c[0] -= c[N]
-            self._set_elem(ecd, i, N, rand["blind"][i])
-            check(L.rs_batch_copy(tmp.h, 0, 0, ecd.h, i, 0, 1))
-            check(L.rs_batch_copy(tmp.h, 1, 0, ecd.h, i, N, 1))
-            check(L.rs_vec_sub(tmp.h, 0, tmp.h, 0, tmp.h, 1, 1))
-            check(L.rs_batch_copy(ecd.h, i, 0, tmp.h, 0, 0, 1))
+        bl = self.mont_many(rand["blind"][:wc])            # RandEncodeTo: c[N] <- r ; c[0] -= c[N], all witnesses in one launch
+        check(L.rs_rand_encode_blind(ecd.h, 0, wc, N, _p(bl)))
         ntt = Batch(f, wc + pc, E)
         self.emb.FwdNTTTo(ntt, ecd)
         w_ntt = Batch(f, wc, E, device_ptr=L.rs_batch_device_ptr(ntt.h), keepalive=ntt)

@@ -104,6 +104,7 @@ _SIGS = {
     "rs_vec_scalar_mul": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p, c_size]),
     "rs_vec_scalar_mul_add": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p, c_size]),
     "rs_vec_scalar_mul_sub": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p, c_size]),
+    "rs_rand_encode_blind": (ctypes.c_int, [c_vp, c_size, c_size, c_size, c_u64p]),
     "rs_eval_circuit": (ctypes.c_int, [c_vp, c_size, c_vp, c_vp, ctypes.POINTER(Term), c_size, c_u64p, c_size, c_u64p]),
     "rs_quorem_vanishing": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_vp, c_size, c_size]),
     "rs_aut": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_size, ctypes.c_long, ctypes.c_int]),

@@ -58,6 +58,7 @@ int aut(const rs_field *f, uint32_t *out, const uint32_t *p, int logN, unsigned 
 int reverse_scale(const rs_field *f, uint32_t *out, const uint32_t *v, const uint32_t *scale, size_t N);
 int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uint32_t *coeffs, size_t n,
            const uint32_t *x, const uint32_t *x_pow_ch, int CH);
+int blind(const rs_field *f, uint32_t *polys, const uint32_t *d_blind, size_t n, size_t rank, size_t N);
 enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
 
 // ---- host-side field helpers (setup only) -------------------------------------------------
@@ -607,6 +608,21 @@ int rs_eval_circuit(rs_batch *out, size_t out_poly, const rs_batch *pw, const rs
         rc = eval_circuit(out->f, elem_ptr(out, out_poly), pw ? pw->d : nullptr, w->d, d_terms, (int)n_terms, d_coeffs, (int)n_coeffs,
                           (const uint32_t *)batch_const, out->rank);
     cudaFreeAsync(d_tmp, g_stream);
+    return rc;
+}
+
+int rs_rand_encode_blind(rs_batch *b, size_t poly0, size_t n, size_t N, const uint64_t *blind_mont) {
+    RS_REQUIRE(b && blind_mont, RS_ERR_ARG, "rs_rand_encode_blind: null argument");
+    RS_REQUIRE(poly0 + n <= b->n_polys && N < b->rank, RS_ERR_SHAPE, "rs_rand_encode_blind: range out of bounds");
+    if (n == 0) return RS_OK;
+    const int NL = b->f->NL;
+    uint32_t *d = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d, n * NL * 4, g_stream));
+    int rc = RS_OK;
+    if (cudaMemcpyAsync(d, blind_mont, n * NL * 4, cudaMemcpyHostToDevice, g_stream) != cudaSuccess)
+        rc = set_error(RS_ERR_CUDA, "rs_rand_encode_blind: upload failed");
+    if (rc == RS_OK) rc = blind(b->f, elem_ptr(b, poly0), d, n, b->rank, N);
+    cudaFreeAsync(d, g_stream);
     return rc;
 }
 

@@ -310,6 +310,36 @@ int reverse_scale(const rs_field *f, uint32_t *out, const uint32_t *v, const uin
 }
 
 // ---------------------------------------------------------------------------
+// Encoder.RandEncodeTo's blinding (buckler/encoder.go:50-54) for a batch of witnesses: c[N] <- r ; c[0] <- c[0] - c[N].
+// One thread per witness polynomial.
+// ---------------------------------------------------------------------------
+template <int NL>
+__global__ void blind_kernel(uint32_t *polys, const uint32_t *blind, size_t n, size_t rank, size_t N, const __grid_constant__ FieldParams<NL> F) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r[NL], c0[NL], d[NL];
+    ld_elem<NL>(r, blind + i * NL);
+    uint32_t *p = polys + i * rank * NL;
+    ld_elem<NL>(c0, p);
+    mod_sub<NL>(d, c0, r, F);
+    st_elem<NL>(p + N * NL, r);
+    st_elem<NL>(p, d);
+}
+
+int blind(const rs_field *f, uint32_t *polys, const uint32_t *d_blind, size_t n, size_t rank, size_t N) {
+#define CALL(NL, QS)                                                                                      \
+    {                                                                                                     \
+        FieldParams<NL> F = make_params<NL>(f);                                                           \
+        blind_kernel<NL><<<(unsigned)((n + 63) / 64), 64, 0, current_stream()>>>(polys, d_blind, n, rank, N, F); \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Poly.Evaluate (poly.go:64-76): Horner is N sequential products on the CPU; here each
 // thread Horner-evaluates a contiguous chunk of CH coefficients and the partial values are
 // combined as  sum_t part_t * x^(t*CH)  by a second tiny kernel (exact field arithmetic, so
