@@ -72,6 +72,11 @@ int rs_field_limbs(const rs_field *f);                        /* Limb() element.
  * identical to SetUint64 / Mul / toMont / fromMont of element.go:94-99, :470-479, :604-653) */
 int rs_field_to_mont(const rs_field *f, uint64_t *out, const uint64_t *canonical_le);
 int rs_field_from_mont(const rs_field *f, uint64_t *out, const uint64_t *mont_le);
+/* SetBytes (element.go:891-915): len <= 128 bytes read as a big-endian integer, reduced mod q, Montgomery form out --
+ * how buckler turns its 32-byte SHA-256 challenges into field elements (prover.go:248, :273-274, :308, :340);
+ * Marshal (element.go:873-883): the canonical value as 8 L64 big-endian bytes (transcript bindings, prover.go:220, :236). */
+int rs_field_set_bytes(const rs_field *f, const uint8_t *be_bytes, size_t len, uint64_t *out_mont);
+int rs_field_marshal(const rs_field *f, const uint64_t *mont, uint8_t *out_be);
 
 /* ---- device batches: []*bigpoly.Poly (math/bigpoly/poly.go:11-28) ----------------------- */
 int rs_batch_alloc(rs_field *f, size_t n_polys, size_t rank, rs_batch **out);
@@ -138,6 +143,8 @@ typedef struct rs_term {
     int32_t n_w;                 /* number of witness factors (<= RS_TERM_MAX_W) */
     int32_t w[RS_TERM_MAX_W];    /* witness poly indices in `w` batch */
 } rs_term;
+/* linCheckVec (buckler/prover.go:409-413): out[poly][i] = c^i for i < n, c a Montgomery element (host) */
+int rs_vec_powers(rs_batch *out, size_t poly, size_t n, const uint64_t *c_mont);
 /* Encoder.RandEncodeTo's blinding step (buckler/encoder.go:50-54) for n polynomials of a batch at once, after
  * rs_ntt_inverse_embed: coefficient N <- blind[i] (a MustSetRandom element, Montgomery limbs, host), coefficient 0 -= it. */
 int rs_rand_encode_blind(rs_batch *b, size_t poly0, size_t n, size_t N, const uint64_t *blind_mont);

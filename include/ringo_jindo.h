@@ -69,6 +69,8 @@ int rs_jindo_create(rs_field *f, const rs_jindo_params *p, const uint64_t *ck_in
 int rs_jindo_create_crs(rs_field *f, const rs_jindo_params *p, const uint8_t *key32, const uint8_t *iv16,
                         const uint64_t *cdt_tables, rs_jindo **out);
 int rs_jindo_commit_key_download(const rs_jindo *j, int which, uint64_t *out);
+/* the parameter block the prover was created with (the compiled Buckler prover sizes its proof buffers from it) */
+int rs_jindo_get_params(const rs_jindo *j, rs_jindo_params *out);
 void rs_jindo_destroy(rs_jindo *j);
 
 /* GPU-resident uniform source of the encoder's TwinCDT sampler.
@@ -147,6 +149,8 @@ void rs_opening_free(rs_opening *o);
 /* accessors (tests / the Go shim's Opening view): kind 0 = Encode[col][row] (ringQ),
  * 1 = MLWE[col][idx] (ringQ), 2 = InCommit[idx] (ringQOut, col ignored) */
 int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, uint64_t *poly_out);
+/* all polynomials of one kind in one copy; kind 2 (InCommit, (cols+1)*in_msis polys over ringQOut) is what Proof.InCommit carries */
+int rs_opening_download_all(const rs_opening *o, int kind, uint64_t *out);
 
 /* Prover.Evaluate (jindo/prover.go:205-324), split around the host transcript:
  *   phase 1: Partial[i] = sum_j left[j] (.) Encode[i][j]  for i <= cols  (prover.go:281-289)

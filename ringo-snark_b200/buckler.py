@@ -283,3 +283,124 @@ class Prover:
             check(lib().rs_poly_evaluate(b.h, p, ln, _p(xm), _p(out)))
             evals.append(self.from_mont_arr(out))
         return evals, pf
+
+
+class NativeProver:
+    """The same Prove as ONE C-ABI call: rs_buckler_prove (include/ringo_buckler.h) runs the round structure, both transcripts
+    and the launch sequence in compiled code inside the library.  Same constructor and `prove` arguments / result as `Prover`
+    (which stays as the readable mirror and as the second implementation the tests compare against)."""
+
+    def __init__(self, field, q, circuit, jindo_params, jindo_prover):
+        self.f, self.q, self.c, self.jp, self.gp = field, q, circuit, jindo_params, jindo_prover
+        self.L = field.L
+        self.R = 1 << (64 * self.L)
+        c = circuit
+        self._keep = []
+
+        def terms(ts):
+            T = (capi.Term * max(len(ts), 1))()
+            for k, (ci, co, pw, ws) in enumerate(ts):
+                T[k].constraint, T[k].coeff, T[k].pw, T[k].n_w = ci, co, pw, len(ws)
+                for j, x in enumerate(ws):
+                    T[k].w[j] = x
+            self._keep.append(T)
+            return ctypes.cast(T, capi.c_vp), len(ts)
+
+        def elems(vals):
+            a = self.mont_many(vals) if len(vals) else np.zeros((1, self.L), dtype=np.uint64)
+            self._keep.append(a)
+            return a.ctypes.data_as(capi.c_vp), len(vals)
+        C = capi.BucklerCircuit()
+        C.rank, C.emb_rank, C.w_cnt, C.pw_cnt = c["rank"], c["emb_rank"], c["w_cnt"], c["pw_cnt"]
+        C.arith_max_rank, C.sum_max_rank = c.get("arith_max_rank", 0), c.get("sum_max_rank", 0) if c.get("sum_terms") else 0
+        C.arith_terms, C.n_arith_terms = terms(c["arith_terms"])
+        C.arith_coeffs, C.n_arith_coeffs = elems(c["arith_coeffs"])
+        C.sum_terms, C.n_sum_terms = terms(c.get("sum_terms") or [])
+        C.sum_coeffs, C.n_sum_coeffs = elems(c.get("sum_coeffs") or [])
+        lin = (capi.LinChecker * max(len(c["lin"]), 1))()
+        for k, (kind, pairs) in enumerate(c["lin"]):
+            pa = np.ascontiguousarray(np.array(pairs, dtype=np.int32).reshape(-1, 2))
+            self._keep.append(pa)
+            lin[k].pairs, lin[k].n_pairs = pa.ctypes.data_as(capi.c_vp), len(pairs)
+            if kind == "ntt":
+                lin[k].kind = 0
+            else:
+                lin[k].kind, lin[k].idx_inv, lin[k].is_ntt = 1, int(kind[1]), 1 if kind[2] else 0
+        self._keep.append(lin)
+        C.lin, C.n_lin = ctypes.cast(lin, capi.c_vp), len(c["lin"])
+        h = capi.c_vp()
+        crs = bytes(jindo_prover.crs)
+        check(lib().rs_buckler_create(field.h, jindo_prover.h, ctypes.byref(C), ctypes.c_char_p(crs), len(crs), ctypes.byref(h)))
+        self.h = h
+        self.batch = lib().rs_buckler_batch(h)
+        self.timing = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().rs_buckler_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+    mont_many = Prover.mont_many
+
+    def from_mont_arr(self, a):
+        return sum(int(v) << (64 * i) for i, v in enumerate(a)) * pow(self.R, -1, self.q) % self.q
+
+    def rand_struct(self, rand):
+        """rs_buckler_rand over host arrays (kept alive in the returned list)"""
+        keep = []
+        R = capi.BucklerRand()
+
+        def el(vals):
+            a = self.mont_many(vals)
+            keep.append(a)
+            return a.ctypes.data_as(capi.c_vp)
+        R.blind = el(rand["blind"][:self.c["w_cnt"]])
+        masks = list(zip(rand["mask"], rand.get("mask_sum", [])))
+        if self.c["lin"]:
+            m, s = masks.pop(0)
+            R.lin_mask, R.lin_mask_sum = el(m), el([s])
+        if self.c.get("sum_terms"):
+            m, s = masks.pop(0)
+            R.sum_mask, R.sum_mask_sum = el(m), el([s])
+        T = (capi.JindoTape * len(rand["tapes"]))()
+        for k, t in enumerate(rand["tapes"]):
+            if isinstance(t, capi.JindoTape):
+                T[k] = t
+            else:
+                T[k], kp = self.gp.tape_struct(t)
+                keep.append(kp)
+        keep.append(T)
+        R.tapes, R.n_tapes = ctypes.cast(T, capi.c_vp), len(rand["tapes"])
+        return R, keep
+
+    def prove_raw(self, pw_mont, w_mont, R):
+        """rs_buckler_prove on prepared inputs; returns the proof as numpy arrays (no Python-object conversion)"""
+        p, d, L = self.gp.p, self.gp.d, self.L
+        nq, nqo, B = self.gp.n_q, self.gp.n_qout, self.batch
+        out = {"Witness": np.zeros((B, p["out_msis"], nqo, d), dtype=np.uint64), "Evals": np.zeros((B, L), dtype=np.uint64),
+               "Partial": np.zeros((p["cols"], nq, d), dtype=np.uint64), "PartialMask": np.zeros((nq, d), dtype=np.uint64),
+               "Encode": np.zeros((p["rows"], nq, d), dtype=np.uint64), "MLWE": np.zeros((p["mlwe"] + p["in_msis"], nq, d), dtype=np.uint64),
+               "InCommit": np.zeros(((p["cols"] + 1) * p["in_msis"], nqo, d), dtype=np.uint64),
+               "lin_mask_sum": np.zeros(L, dtype=np.uint64), "sum_mask_sum": np.zeros(L, dtype=np.uint64), "eval_point": np.zeros(L, dtype=np.uint64)}
+        P = capi.BucklerProof()
+        vp = lambda a: a.ctypes.data_as(capi.c_vp)
+        P.witness, P.evals, P.partial, P.partial_mask = vp(out["Witness"]), vp(out["Evals"]), vp(out["Partial"]), vp(out["PartialMask"])
+        P.encode, P.mlwe, P.incommit = vp(out["Encode"]), vp(out["MLWE"]), vp(out["InCommit"])
+        P.lin_mask_sum, P.sum_mask_sum, P.eval_point = vp(out["lin_mask_sum"]), vp(out["sum_mask_sum"]), vp(out["eval_point"])
+        ms = (ctypes.c_double * 8)()
+        pw = np.ascontiguousarray(pw_mont, dtype=np.uint64); w = np.ascontiguousarray(w_mont, dtype=np.uint64)
+        check(lib().rs_buckler_prove(self.h, vp(pw) if pw.size else None, vp(w), ctypes.byref(R), ctypes.byref(P), ms))
+        self.timing = dict(zip(("encode_ntt", "commit", "arith_check", "lin_check", "sum_check", "evaluate", "_", "total"), ms))
+        return out
+
+    def prove(self, pw_mont, w_mont, rand):
+        R, keep = self.rand_struct(rand)
+        o = self.prove_raw(pw_mont, w_mont, R)
+        has_lin, has_sum = bool(self.c["lin"]), bool(self.c.get("sum_terms"))
+        return {"Witness": o["Witness"].tolist(), "LinCheckMaskSum": self.from_mont_arr(o["lin_mask_sum"]) if has_lin else None,
+                "SumCheckMaskSum": self.from_mont_arr(o["sum_mask_sum"]) if has_sum else None,
+                "Evals": [self.from_mont_arr(e) for e in o["Evals"]],
+                "EvalProof": {k: o[k].tolist() for k in ("Partial", "PartialMask", "InCommit", "Encode", "MLWE")},
+                "_eval_point": self.from_mont_arr(o["eval_point"])}

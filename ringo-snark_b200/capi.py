@@ -60,7 +60,33 @@ class JindoNoise(ctypes.Structure):
                 ("mask_mlwe_std", ctypes.c_double)]
 
 
-# name -> (restype, argtypes); mirrors include/ringo_cuda.h and include/ringo_jindo.h one to one
+class LinChecker(ctypes.Structure):
+    """rs_lin_checker (include/ringo_buckler.h)"""
+    _fields_ = [("kind", ctypes.c_int32), ("is_ntt", ctypes.c_int32), ("idx_inv", ctypes.c_int64), ("pairs", c_vp), ("n_pairs", c_size)]
+
+
+class BucklerCircuit(ctypes.Structure):
+    """rs_buckler_circuit (include/ringo_buckler.h)"""
+    _fields_ = [("rank", c_size), ("emb_rank", c_size), ("w_cnt", c_size), ("pw_cnt", c_size),
+                ("arith_max_rank", c_size), ("sum_max_rank", c_size),
+                ("arith_terms", c_vp), ("n_arith_terms", c_size), ("arith_coeffs", c_vp), ("n_arith_coeffs", c_size),
+                ("sum_terms", c_vp), ("n_sum_terms", c_size), ("sum_coeffs", c_vp), ("n_sum_coeffs", c_size),
+                ("lin", c_vp), ("n_lin", c_size)]
+
+
+class BucklerRand(ctypes.Structure):
+    """rs_buckler_rand (include/ringo_buckler.h)"""
+    _fields_ = [("blind", c_vp), ("lin_mask", c_vp), ("lin_mask_sum", c_vp), ("sum_mask", c_vp), ("sum_mask_sum", c_vp),
+                ("tapes", c_vp), ("n_tapes", c_size)]
+
+
+class BucklerProof(ctypes.Structure):
+    """rs_buckler_proof (include/ringo_buckler.h)"""
+    _fields_ = [("witness", c_vp), ("lin_mask_sum", c_vp), ("sum_mask_sum", c_vp), ("evals", c_vp), ("partial", c_vp),
+                ("partial_mask", c_vp), ("encode", c_vp), ("mlwe", c_vp), ("incommit", c_vp), ("eval_point", c_vp)]
+
+
+# name -> (restype, argtypes); mirrors include/ringo_cuda.h, ringo_jindo.h, ringo_buckler.h and ringo_sampler.h one to one
 _SIGS = {
     "rs_init": (ctypes.c_int, [ctypes.c_int]),
     "rs_set_stream": (ctypes.c_int, [c_vp]),
@@ -104,6 +130,10 @@ _SIGS = {
     "rs_vec_scalar_mul": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p, c_size]),
     "rs_vec_scalar_mul_add": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p, c_size]),
     "rs_vec_scalar_mul_sub": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p, c_size]),
+    "rs_vec_powers": (ctypes.c_int, [c_vp, c_size, c_size, c_u64p]),
+    "rs_field_set_bytes": (ctypes.c_int, [c_vp, c_vp, c_size, c_u64p]),
+    "rs_field_marshal": (ctypes.c_int, [c_vp, c_u64p, c_vp]),
+    "rs_opening_download_all": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
     "rs_rand_encode_blind": (ctypes.c_int, [c_vp, c_size, c_size, c_size, c_u64p]),
     "rs_eval_circuit": (ctypes.c_int, [c_vp, c_size, c_vp, c_vp, ctypes.POINTER(Term), c_size, c_u64p, c_size, c_u64p]),
     "rs_quorem_vanishing": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_vp, c_size, c_size]),
@@ -113,6 +143,7 @@ _SIGS = {
     # ringo_jindo.h
     "rs_jindo_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "rs_jindo_create_crs": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "rs_jindo_get_params": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams)]),
     "rs_jindo_commit_key_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
     "rs_jindo_destroy": (None, [c_vp]),
     "rs_jindo_set_twin_stream": (ctypes.c_int, [c_vp, c_vp, c_vp]),
@@ -146,6 +177,13 @@ _SIGS = {
     "rs_jindo_commitment_write_raw": (ctypes.c_longlong, [c_vp, c_vp, c_vp, c_size]),
     "rs_opening_alloc_zero": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp)]),
     "rs_opening_mul_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    # ringo_buckler.h
+    "rs_buckler_create": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(BucklerCircuit), c_vp, c_size, ctypes.POINTER(c_vp)]),
+    "rs_buckler_destroy": (None, [c_vp]),
+    "rs_buckler_batch": (c_size, [c_vp]),
+    "rs_buckler_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(BucklerRand), ctypes.POINTER(BucklerProof), ctypes.POINTER(ctypes.c_double)]),
+    "rs_sha256": (None, [c_vp, c_size, c_vp]),
+    "rs_shake128": (None, [c_vp, c_size, c_vp, c_size]),
     # ringo_sampler.h
     "rs_uniform_create": (c_vp, [c_vp]),
     "rs_uniform_destroy": (None, [c_vp]),

@@ -59,6 +59,7 @@ int reverse_scale(const rs_field *f, uint32_t *out, const uint32_t *v, const uin
 int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uint32_t *coeffs, size_t n,
            const uint32_t *x, const uint32_t *x_pow_ch, int CH);
 int blind(const rs_field *f, uint32_t *polys, const uint32_t *d_blind, size_t n, size_t rank, size_t N);
+int powers(const rs_field *f, uint32_t *out, const uint32_t *c, size_t n);
 enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
 
 // ---- host-side field helpers (setup only) -------------------------------------------------
@@ -253,6 +254,38 @@ int rs_field_from_mont(const rs_field *f, uint64_t *out, const uint64_t *mont) {
     uint32_t z[RS_MAX_NL], one[RS_MAX_NL] = {1};
     host_mul(f, z, (const uint32_t *)mont, one);
     memcpy(out, z, 4 * f->NL);
+    return RS_OK;
+}
+
+// SetBytes (zp element.go:891-915): the bytes as a big-endian integer, reduced mod q (any length up to 128 bytes), in
+// Montgomery form.  Horner over chunks of L64 words, each step a multiplication by R = 2^(64 L64) done as a Montgomery
+// product with R^2.
+int rs_field_set_bytes(const rs_field *f, const uint8_t *be, size_t len, uint64_t *out_mont) {
+    RS_REQUIRE(f && (be || len == 0) && out_mont && len <= 128, RS_ERR_ARG, "rs_field_set_bytes: bad argument");
+    const int L = f->L64, NL = f->NL;
+    uint64_t words[16] = {0};
+    for (size_t i = 0; i < len; i++) words[i / 8] |= (uint64_t)be[len - 1 - i] << (8 * (i % 8));
+    const int n_words = (int)((len + 7) / 8), n_chunks = (n_words + L - 1) / L;
+    uint32_t acc[RS_MAX_NL] = {0}, chunk[RS_MAX_NL], t[RS_MAX_NL];
+    for (int ch = n_chunks - 1; ch >= 0; ch--) {
+        host_mul(f, acc, acc, f->r2);
+        memset(chunk, 0, sizeof(chunk));
+        for (int w = 0; w < L && ch * L + w < n_words; w++) { chunk[2 * w] = (uint32_t)words[ch * L + w]; chunk[2 * w + 1] = (uint32_t)(words[ch * L + w] >> 32); }
+        host_mul(f, t, chunk, f->r2);
+        host_add(f, acc, acc, t);
+    }
+    memcpy(out_mont, acc, 4 * NL);
+    return RS_OK;
+}
+// Marshal (element.go:873-883): the canonical value as 8 L64 big-endian bytes
+int rs_field_marshal(const rs_field *f, const uint64_t *mont, uint8_t *out_be) {
+    RS_REQUIRE(f && mont && out_be, RS_ERR_ARG, "rs_field_marshal: null argument");
+    uint64_t c[RS_MAX_NL / 2];
+    int rc = rs_field_from_mont(f, c, mont);
+    if (rc) return rc;
+    const int L = f->L64;
+    for (int i = 0; i < L; i++)
+        for (int b = 0; b < 8; b++) out_be[8 * (L - 1 - i) + (7 - b)] = (uint8_t)(c[i] >> (8 * b));
     return RS_OK;
 }
 
@@ -609,6 +642,13 @@ int rs_eval_circuit(rs_batch *out, size_t out_poly, const rs_batch *pw, const rs
                           (const uint32_t *)batch_const, out->rank);
     cudaFreeAsync(d_tmp, g_stream);
     return rc;
+}
+
+int rs_vec_powers(rs_batch *out, size_t poly, size_t n, const uint64_t *c_mont) {
+    RS_REQUIRE(out && c_mont, RS_ERR_ARG, "rs_vec_powers: null argument");
+    RS_REQUIRE(poly < out->n_polys && n <= out->rank, RS_ERR_SHAPE, "rs_vec_powers: range out of bounds");
+    if (n == 0) return RS_OK;
+    return powers(out->f, elem_ptr(out, poly), (const uint32_t *)c_mont, n);
 }
 
 int rs_rand_encode_blind(rs_batch *b, size_t poly0, size_t n, size_t N, const uint64_t *blind_mont) {

@@ -1690,6 +1690,12 @@ int rs_jindo_create_crs(rs_field *f, const rs_jindo_params *p, const uint8_t *ke
     return jindo_create_impl(f, p, nullptr, nullptr, nullptr, cdt_tables, key32, iv16, out);
 }
 
+int rs_jindo_get_params(const rs_jindo *j, rs_jindo_params *out) {
+    RS_REQUIRE(j && out, RS_ERR_ARG, "rs_jindo_get_params: null argument");
+    *out = j->p;
+    return RS_OK;
+}
+
 int rs_jindo_commit_key_download(const rs_jindo *j, int which, uint64_t *out) {
     RS_REQUIRE(j && out && which >= 0 && which <= 2, RS_ERR_ARG, "rs_jindo_commit_key_download: bad argument");
     const rs_jindo_params &p = j->p;
@@ -2168,6 +2174,17 @@ long long rs_jindo_commitment_write_raw(const rs_jindo *j, const uint64_t *commi
 int rs_opening_alloc_zero(rs_jindo *j, rs_opening **out) {
     RS_REQUIRE(j && out, RS_ERR_ARG, "rs_opening_alloc_zero: null argument");
     return opening_alloc(j, out);
+}
+
+// every polynomial of one kind in one copy: kind 2 = InCommit[(cols+1)*in_msis] (what Proof.InCommit carries)
+int rs_opening_download_all(const rs_opening *o, int kind, uint64_t *out) {
+    RS_REQUIRE(o && out && kind == 2, RS_ERR_ARG, "rs_opening_download_all: bad argument");
+    const rs_jindo *j = o->j;
+    const size_t words = (size_t)(j->p.cols + 1) * j->p.in_msis * pqo(j);
+    cudaError_t e = cudaMemcpyAsync(out, o->d_incommit, words * 8, cudaMemcpyDeviceToHost, rs::current_stream());
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rs::current_stream());
+    if (e != cudaSuccess) return rs::set_error(RS_ERR_CUDA, "rs_opening_download_all: %s", cudaGetErrorString(e));
+    return RS_OK;
 }
 
 int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, uint64_t *poly_out) {

@@ -310,6 +310,46 @@ int reverse_scale(const rs_field *f, uint32_t *out, const uint32_t *v, const uin
 }
 
 // ---------------------------------------------------------------------------
+// linCheckVec (buckler/prover.go:409-413): out[i] = c^i.  The reference runs N sequential products; here thread i
+// computes its power by square-and-multiply (exact field arithmetic: the same canonical elements).
+// ---------------------------------------------------------------------------
+template <int NL, int QS>
+__global__ void __launch_bounds__(128) powers_kernel(uint32_t *out, const __grid_constant__ Scalar<NL> c,
+                                                     const __grid_constant__ FieldParams<NL> F, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r[NL], b[NL], t[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) { r[l] = F.one[l]; b[l] = c.v[l]; }
+    for (size_t e = i; e; e >>= 1) {
+        if (e & 1) {
+            mont_mul<NL, QS>(t, r, b, F);
+#pragma unroll
+            for (int l = 0; l < NL; l++) r[l] = t[l];
+        }
+        mont_mul<NL, QS>(t, b, b, F);
+#pragma unroll
+        for (int l = 0; l < NL; l++) b[l] = t[l];
+    }
+    st_elem<NL>(out + i * NL, r);
+}
+
+int powers(const rs_field *f, uint32_t *out, const uint32_t *c, size_t n) {
+#define CALL(NL, QS)                                                                                      \
+    {                                                                                                     \
+        FieldParams<NL> F = make_params<NL>(f);                                                           \
+        Scalar<NL> s;                                                                                     \
+        for (int i = 0; i < NL; i++) s.v[i] = c[i];                                                       \
+        powers_kernel<NL, QS><<<(unsigned)((n + 127) / 128), 128, 0, current_stream()>>>(out, s, F, n);    \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Encoder.RandEncodeTo's blinding (buckler/encoder.go:50-54) for a batch of witnesses: c[N] <- r ; c[0] <- c[0] - c[N].
 // One thread per witness polynomial.
 // ---------------------------------------------------------------------------

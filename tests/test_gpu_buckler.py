@@ -125,12 +125,14 @@ def test_prover_pipeline(rs, name, logN):
     assert np.array_equal(P[1].Coeffs, eval_o)
 
 
+@pytest.mark.parametrize("native", [False, True], ids=["python-mirror", "compiled"])
 @pytest.mark.parametrize("circuit,name,N", [("mult", "zp128", 256), ("pk", "zp220", 256), ("ct", "zp240", 256), ("norm", "zp220", 256)])
-def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N):
+def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N, native):
     """buckler.Prover.Prove end to end on the GPU (ringo-snark_b200/buckler.py: host transcript, device
     polynomials, Jindo commits/evaluation through the C ABI) against the oracle's Prove on the same
     circuit, witness, CRS and randomness tape: every commitment, evaluation and proof polynomial is
-    bit-identical, and the restated buckler.Verifier accepts the GPU proof (buckler_test.go:82-99)."""
+    bit-identical, and the restated buckler.Verifier accepts the GPU proof (buckler_test.go:82-99).
+    native: the same Prove as one call into the compiled prover (rs_buckler_prove, include/ringo_buckler.h)."""
     import sys, os
     sys.path.insert(0, os.path.dirname(__file__))
     from test_oracle_buckler import circuit_and_witness
@@ -158,7 +160,7 @@ def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N):
                          polys_array(prv.ck.Out), cdt_array(prv.ecd), crs=b"Buckler!")
     rand = {"blind": op.trace["blind"], "mask": op.trace["mask"], "mask_sum": op.trace["mask_sum"],
             "tapes": [tape_arrays(fo, C.jp, t) for t in op.trace["commit_traces"]]}
-    gprv = rs.buckler.Prover(fg, q, desc, C.jp, gp)
+    gprv = (rs.buckler.NativeProver if native else rs.buckler.Prover)(fg, q, desc, C.jp, gp)
     pf_g = gprv.prove(np.stack([fo.to_mont(v) for v in op.trace["pw_full"]]),
                       np.stack([fo.to_mont(v) for v in op.trace["w_full"]]), rand)
     assert pf_g["_eval_point"] == pf_o["_eval_point"]
