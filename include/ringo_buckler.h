@@ -52,6 +52,8 @@ typedef struct rs_buckler_rand {
     const uint64_t *sum_mask_sum;
     const rs_jindo_tape *tapes;     /* one tape per polyProver.Commit, in call order */
     size_t n_tapes;
+    int32_t tapes_pinned;           /* != 0: the tapes' host arrays are pinned memory (rs_pinned_alloc, rs_tape_builder) and are read in
+                                       place; otherwise they are staged through the prover's own pinned arena first */
 } rs_buckler_rand;
 
 /* buckler.Proof (buckler/entities.go) as caller-owned host buffers; sizes follow from the circuit and the Jindo
@@ -76,7 +78,9 @@ void rs_buckler_destroy(rs_buckler *b);
 /* number of commitments of a proof = Context.batch() (context.go) */
 size_t rs_buckler_batch(const rs_buckler *b);
 /* Prover.Prove.  pw / w: pw_cnt x rank and w_cnt x rank Montgomery elements (host), decomposition witnesses filled in.
- * phase_ms (optional, 8 doubles): wall milliseconds of encode+NTT, commits, arithCheck, linCheck, sumCheck, Evaluate, 0, total. */
+ * phase_ms (optional, 16 doubles): wall milliseconds of [0] encode+NTT, [1] commits, [2] arithCheck, [3] linCheck, [4] sumCheck, [5] Evaluate,
+ * [6] tape staging, [7] total; Evaluate's parts: [8] batch combination of the openings, [9] Partial, [10] InCommit download + transcript, [11] responses,
+ * [12] Poly.Evaluate of the committed vectors.  The stream is synchronised at every boundary when phase_ms is given. */
 int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const rs_buckler_rand *rand,
                      rs_buckler_proof *proof, double *phase_ms);
 

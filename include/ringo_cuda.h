@@ -163,6 +163,10 @@ int rs_aut(rs_batch *out, size_t out_poly, const rs_batch *p, size_t p_poly, siz
 int rs_reverse_scale(rs_batch *out, size_t out_poly, const rs_batch *v, size_t v_poly, const uint64_t *scale);
 /* Poly.Evaluate (math/bigpoly/poly.go:64-76) of the first n_elems coefficients at x; result to host */
 int rs_poly_evaluate(const rs_batch *p, size_t poly, size_t n_elems, const uint64_t *x, uint64_t *result);
+/* the closing loop of jindo.Prover.Evaluate (jindo/prover.go:318-321): n polynomials (batches[i], polys[i], first lens[i]
+ * coefficients) at the same point in one launch and one copy; results: n x L64 Montgomery limbs (host) */
+int rs_poly_evaluate_many(const rs_batch *const *batches, const size_t *polys, const size_t *lens, size_t n, const uint64_t *x,
+                          uint64_t *results);
 
 /* ---- multi-GPU plumbing (SURVEY 8b "rs_allgather_commitments", 8e) ---------------------------------------------------
  * One process per GPU.  The only exchanges of the path are tiny: per-shard commitments / evaluations into the host

@@ -118,6 +118,12 @@ typedef struct rs_jindo_tape {
  * *open: NULL on entry -> a new Opening is allocated; otherwise the given Opening is overwritten. */
 int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
                     rs_opening **open, uint64_t *commitment_out);
+/* Same Commit without the trailing synchronisation: every copy and kernel is enqueued on the library's stream and the call
+ * returns.  commitment_out_pinned and every host buffer of the tape must be pinned memory (rs_pinned_alloc) and stay untouched
+ * until the caller has synchronised (rs_sync).  Lets a proof's 12-43 small Commits run back to back while the host hashes the
+ * commitments that are already out (the compiled Buckler prover, ringo_buckler.h). */
+int rs_jindo_commit_async(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
+                          rs_opening **open, uint64_t *commitment_out_pinned);
 /* Same Commit with v in host memory (len elements, L64 limbs each, Montgomery form; pinned memory for
  * overlap): v is uploaded in pieces on a copy stream while earlier pieces are already being encoded, so
  * the upload hides behind the encode kernels.  The tape must be host resident too. */
@@ -207,6 +213,9 @@ long long rs_jindo_commitment_write_raw(const rs_jindo *j, const uint64_t *commi
 int rs_opening_alloc_zero(rs_jindo *j, rs_opening **out);
 int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout);
 int rs_opening_mul_add_bytes(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint8_t *chal16);
+/* the whole loop of prover.go:230-265 in one pass: *out = sum_i opens[i] (.) encodeChallenge(chal_bytes[16 i .. 16 i + 16)); n
+ * challenge polynomials per ring are encoded in one launch each, every opening is read once and the new Opening written once */
+int rs_opening_combine_bytes(rs_jindo *j, const rs_opening *const *opens, size_t n, const uint8_t *chal_bytes, rs_opening **out);
 
 #ifdef __cplusplus
 }

@@ -285,6 +285,21 @@ class Prover:
         return evals, pf
 
 
+class _PinnedArray:
+    """a numpy copy of `src` living in rs_pinned_alloc memory"""
+    _live = []
+
+    def __init__(self, src):
+        n = max(src.nbytes, 8)
+        self.ptr = lib().rs_pinned_alloc(n)
+        if not self.ptr:
+            raise capi.RingoError(-5, "rs_pinned_alloc failed")
+        buf = (ctypes.c_uint8 * n).from_address(self.ptr)
+        self.a = np.frombuffer(buf, dtype=src.dtype, count=src.size).reshape(src.shape)
+        self.a[...] = src
+        _PinnedArray._live.append(self)      # pinned for the life of the process (benchmark helper)
+
+
 class NativeProver:
     """The same Prove as ONE C-ABI call: rs_buckler_prove (include/ringo_buckler.h) runs the round structure, both transcripts
     and the launch sequence in compiled code inside the library.  Same constructor and `prove` arguments / result as `Prover`
@@ -347,8 +362,10 @@ class NativeProver:
     def from_mont_arr(self, a):
         return sum(int(v) << (64 * i) for i, v in enumerate(a)) * pow(self.R, -1, self.q) % self.q
 
-    def rand_struct(self, rand):
-        """rs_buckler_rand over host arrays (kept alive in the returned list)"""
+    def rand_struct(self, rand, pinned=False):
+        """rs_buckler_rand over host arrays (kept alive in the returned list).  pinned: the tapes' arrays are copied into
+        pinned memory once here (what a Go caller holding its tapes in rs_pinned_alloc / rs_tape_builder buffers passes) and
+        rs_buckler_prove reads them in place instead of staging them on every call."""
         keep = []
         R = capi.BucklerRand()
 
@@ -368,15 +385,21 @@ class NativeProver:
         for k, t in enumerate(rand["tapes"]):
             if isinstance(t, capi.JindoTape):
                 T[k] = t
-            else:
-                T[k], kp = self.gp.tape_struct(t)
-                keep.append(kp)
+                continue
+            if pinned:
+                t = {kk: (_PinnedArray(v).a if isinstance(v, np.ndarray) else v) for kk, v in
+                     ((kk, (np.ascontiguousarray(v, dtype=(np.int64 if kk in ("cosac_g", "mlwe") else np.uint64)) if v is not None and kk in
+                            ("first_row", "last_row", "mask_rows", "twin_u", "cosac_g", "mlwe") else v)) for kk, v in t.items())}
+            T[k], kp = self.gp.tape_struct(t)
+            keep.append(kp)
         keep.append(T)
+        R.tapes_pinned = 1 if pinned else 0
         R.tapes, R.n_tapes = ctypes.cast(T, capi.c_vp), len(rand["tapes"])
         return R, keep
 
-    def prove_raw(self, pw_mont, w_mont, R):
-        """rs_buckler_prove on prepared inputs; returns the proof as numpy arrays (no Python-object conversion)"""
+    def prove_raw(self, pw_mont, w_mont, R, phases=True):
+        """rs_buckler_prove on prepared inputs; returns the proof as numpy arrays (no Python-object conversion).
+        phases: also fill self.timing (the library synchronises the stream at every phase boundary to do so)"""
         p, d, L = self.gp.p, self.gp.d, self.L
         nq, nqo, B = self.gp.n_q, self.gp.n_qout, self.batch
         out = {"Witness": np.zeros((B, p["out_msis"], nqo, d), dtype=np.uint64), "Evals": np.zeros((B, L), dtype=np.uint64),
@@ -389,10 +412,11 @@ class NativeProver:
         P.witness, P.evals, P.partial, P.partial_mask = vp(out["Witness"]), vp(out["Evals"]), vp(out["Partial"]), vp(out["PartialMask"])
         P.encode, P.mlwe, P.incommit = vp(out["Encode"]), vp(out["MLWE"]), vp(out["InCommit"])
         P.lin_mask_sum, P.sum_mask_sum, P.eval_point = vp(out["lin_mask_sum"]), vp(out["sum_mask_sum"]), vp(out["eval_point"])
-        ms = (ctypes.c_double * 8)()
+        ms = (ctypes.c_double * 16)()
         pw = np.ascontiguousarray(pw_mont, dtype=np.uint64); w = np.ascontiguousarray(w_mont, dtype=np.uint64)
-        check(lib().rs_buckler_prove(self.h, vp(pw) if pw.size else None, vp(w), ctypes.byref(R), ctypes.byref(P), ms))
-        self.timing = dict(zip(("encode_ntt", "commit", "arith_check", "lin_check", "sum_check", "evaluate", "_", "total"), ms))
+        check(lib().rs_buckler_prove(self.h, vp(pw) if pw.size else None, vp(w), ctypes.byref(R), ctypes.byref(P), ms if phases else None))
+        self.timing = dict(zip(("encode_ntt", "commit", "arith_check", "lin_check", "sum_check", "evaluate", "tape_staging", "total", "ev_combine", "ev_partial",
+                                "ev_incommit", "ev_respond", "ev_poly_eval"), ms))
         return out
 
     def prove(self, pw_mont, w_mont, rand):

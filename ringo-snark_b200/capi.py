@@ -77,7 +77,7 @@ class BucklerCircuit(ctypes.Structure):
 class BucklerRand(ctypes.Structure):
     """rs_buckler_rand (include/ringo_buckler.h)"""
     _fields_ = [("blind", c_vp), ("lin_mask", c_vp), ("lin_mask_sum", c_vp), ("sum_mask", c_vp), ("sum_mask_sum", c_vp),
-                ("tapes", c_vp), ("n_tapes", c_size)]
+                ("tapes", c_vp), ("n_tapes", c_size), ("tapes_pinned", ctypes.c_int32)]
 
 
 class BucklerProof(ctypes.Structure):
@@ -140,6 +140,7 @@ _SIGS = {
     "rs_aut": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_size, ctypes.c_long, ctypes.c_int]),
     "rs_reverse_scale": (ctypes.c_int, [c_vp, c_size, c_vp, c_size, c_u64p]),
     "rs_poly_evaluate": (ctypes.c_int, [c_vp, c_size, c_size, c_u64p, c_u64p]),
+    "rs_poly_evaluate_many": (ctypes.c_int, [c_vp, c_vp, c_vp, c_size, c_u64p, c_u64p]),
     # ringo_jindo.h
     "rs_jindo_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "rs_jindo_create_crs": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
@@ -151,6 +152,7 @@ _SIGS = {
     "rs_jindo_set_mlwe_stream": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int64]),
     "rs_jindo_mlwe_stream_sample": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_commit": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
+    "rs_jindo_commit_async": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
     "rs_jindo_commit_host": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
     "rs_jindo_commit_columns": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
     "rs_jindo_outer_commit": (ctypes.c_int, [c_vp, c_vp, c_vp]),
@@ -171,6 +173,7 @@ _SIGS = {
     "rs_jindo_left_vec": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "rs_jindo_encode_challenges": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.c_int, c_vp]),
     "rs_opening_mul_add_bytes": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "rs_opening_combine_bytes": (ctypes.c_int, [c_vp, c_vp, c_size, c_vp, ctypes.POINTER(c_vp)]),
     "rs_jindo_verify": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.POINTER(JindoProof), ctypes.c_double,
                                        ctypes.c_double, ctypes.POINTER(ctypes.c_int)]),
     "rs_jindo_poly_write_to": (ctypes.c_longlong, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_size]),

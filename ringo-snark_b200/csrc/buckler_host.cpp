@@ -6,8 +6,17 @@
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>
+#endif
 
 #include "../../include/ringo_buckler.h"
 
@@ -27,6 +36,58 @@ const uint32_t K256[64] = {
     0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
 
 inline uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+#if defined(__x86_64__)
+bool have_sha_ni() {
+    static const bool ok = [] {
+        unsigned a, b, c, d;
+        if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
+        const bool sha = (b >> 29) & 1;
+        if (!__get_cpuid(1, &a, &b, &c, &d)) return false;
+        return sha && ((c >> 19) & 1) && ((c >> 9) & 1);      // SHA, SSE4.1, SSSE3
+    }();
+    return ok;
+}
+
+// the compression function on the SHA extensions (two rounds per SHA256RNDS2, message schedule by SHA256MSG1/2)
+__attribute__((target("sha,sse4.1,ssse3"))) void sha256_blocks_ni(uint32_t state[8], const uint8_t *p, size_t n_blocks) {
+    const __m128i shuf = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i tmp = _mm_loadu_si128((const __m128i *)&state[0]);        // DCBA
+    __m128i st1 = _mm_loadu_si128((const __m128i *)&state[4]);        // HGFE
+    tmp = _mm_shuffle_epi32(tmp, 0xB1);                               // CDAB
+    st1 = _mm_shuffle_epi32(st1, 0x1B);                               // EFGH
+    __m128i st0 = _mm_alignr_epi8(tmp, st1, 8);                       // ABEF
+    st1 = _mm_blend_epi16(st1, tmp, 0xF0);                            // CDGH
+    for (; n_blocks; n_blocks--, p += 64) {
+        const __m128i save0 = st0, save1 = st1;
+        __m128i m[4];
+        for (int i = 0; i < 4; i++) m[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *)(p + 16 * i)), shuf);
+        for (int r = 0; r < 16; r++) {
+            __m128i w;
+            if (r < 4) {
+                w = m[r];
+            } else {                                                  // W[4r .. 4r+3] from the previous sixteen words
+                __m128i t = _mm_sha256msg1_epu32(m[0], m[1]);
+                t = _mm_add_epi32(t, _mm_alignr_epi8(m[3], m[2], 4));
+                w = _mm_sha256msg2_epu32(t, m[3]);
+                m[0] = m[1]; m[1] = m[2]; m[2] = m[3]; m[3] = w;
+            }
+            __m128i wk = _mm_add_epi32(w, _mm_loadu_si128((const __m128i *)&K256[4 * r]));
+            st1 = _mm_sha256rnds2_epu32(st1, st0, wk);
+            wk = _mm_shuffle_epi32(wk, 0x0E);
+            st0 = _mm_sha256rnds2_epu32(st0, st1, wk);
+        }
+        st0 = _mm_add_epi32(st0, save0);
+        st1 = _mm_add_epi32(st1, save1);
+    }
+    tmp = _mm_shuffle_epi32(st0, 0x1B);                               // FEBA
+    st1 = _mm_shuffle_epi32(st1, 0xB1);                               // DCHG
+    st0 = _mm_blend_epi16(tmp, st1, 0xF0);                            // DCBA
+    st1 = _mm_alignr_epi8(st1, tmp, 8);                               // HGFE
+    _mm_storeu_si128((__m128i *)&state[0], st0);
+    _mm_storeu_si128((__m128i *)&state[4], st1);
+}
+#endif
 
 struct Sha256 {
     uint32_t h[8];
@@ -63,6 +124,12 @@ struct Sha256 {
             fill += take; p += take; n -= take;
             if (fill == 64) { block(buf); fill = 0; }
         }
+#if defined(__x86_64__)
+        if (n >= 64 && have_sha_ni()) {
+            sha256_blocks_ni(h, p, n / 64);
+            p += n & ~(size_t)63; n &= 63;
+        }
+#endif
         for (; n >= 64; p += 64, n -= 64) block(p);
         if (n) { memcpy(buf, p, n); fill = n; }
     }
@@ -81,7 +148,27 @@ struct Sha256 {
 // ---------------------------------------------------------------------------------------------------------------
 // SHAKE128 (FIPS 202): Keccak-f[1600], rate 168, domain byte 0x1f; absorb then squeeze, both incremental
 // ---------------------------------------------------------------------------------------------------------------
-inline uint64_t rotl64(uint64_t x, int n) { return n ? (x << n) | (x >> (64 - n)) : x; }
+#define RS_ROL(x, n) (((x) << (n)) | ((x) >> (64 - (n))))
+// one round from lanes a** into lanes e** (theta, rho, pi, chi, iota), lanes named a[y][x] = a<y><x>
+#define RS_KROUND(A, E, rc)                                                                                           \
+    do {                                                                                                              \
+        const uint64_t c0 = A##00 ^ A##10 ^ A##20 ^ A##30 ^ A##40, c1 = A##01 ^ A##11 ^ A##21 ^ A##31 ^ A##41,         \
+                       c2 = A##02 ^ A##12 ^ A##22 ^ A##32 ^ A##42, c3 = A##03 ^ A##13 ^ A##23 ^ A##33 ^ A##43,         \
+                       c4 = A##04 ^ A##14 ^ A##24 ^ A##34 ^ A##44;                                                     \
+        const uint64_t d0 = c4 ^ RS_ROL(c1, 1), d1 = c0 ^ RS_ROL(c2, 1), d2 = c1 ^ RS_ROL(c3, 1), d3 = c2 ^ RS_ROL(c4, 1), \
+                       d4 = c3 ^ RS_ROL(c0, 1);                                                                        \
+        uint64_t b0, b1, b2, b3, b4;                                                                                  \
+        b0 = A##00 ^ d0; b1 = RS_ROL(A##11 ^ d1, 44); b2 = RS_ROL(A##22 ^ d2, 43); b3 = RS_ROL(A##33 ^ d3, 21); b4 = RS_ROL(A##44 ^ d4, 14); \
+        E##00 = b0 ^ (~b1 & b2) ^ (rc); E##01 = b1 ^ (~b2 & b3); E##02 = b2 ^ (~b3 & b4); E##03 = b3 ^ (~b4 & b0); E##04 = b4 ^ (~b0 & b1); \
+        b0 = RS_ROL(A##03 ^ d3, 28); b1 = RS_ROL(A##14 ^ d4, 20); b2 = RS_ROL(A##20 ^ d0, 3); b3 = RS_ROL(A##31 ^ d1, 45); b4 = RS_ROL(A##42 ^ d2, 61); \
+        E##10 = b0 ^ (~b1 & b2); E##11 = b1 ^ (~b2 & b3); E##12 = b2 ^ (~b3 & b4); E##13 = b3 ^ (~b4 & b0); E##14 = b4 ^ (~b0 & b1); \
+        b0 = RS_ROL(A##01 ^ d1, 1); b1 = RS_ROL(A##12 ^ d2, 6); b2 = RS_ROL(A##23 ^ d3, 25); b3 = RS_ROL(A##34 ^ d4, 8); b4 = RS_ROL(A##40 ^ d0, 18); \
+        E##20 = b0 ^ (~b1 & b2); E##21 = b1 ^ (~b2 & b3); E##22 = b2 ^ (~b3 & b4); E##23 = b3 ^ (~b4 & b0); E##24 = b4 ^ (~b0 & b1); \
+        b0 = RS_ROL(A##04 ^ d4, 27); b1 = RS_ROL(A##10 ^ d0, 36); b2 = RS_ROL(A##21 ^ d1, 10); b3 = RS_ROL(A##32 ^ d2, 15); b4 = RS_ROL(A##43 ^ d3, 56); \
+        E##30 = b0 ^ (~b1 & b2); E##31 = b1 ^ (~b2 & b3); E##32 = b2 ^ (~b3 & b4); E##33 = b3 ^ (~b4 & b0); E##34 = b4 ^ (~b0 & b1); \
+        b0 = RS_ROL(A##02 ^ d2, 62); b1 = RS_ROL(A##13 ^ d3, 55); b2 = RS_ROL(A##24 ^ d4, 39); b3 = RS_ROL(A##30 ^ d0, 41); b4 = RS_ROL(A##41 ^ d1, 2); \
+        E##40 = b0 ^ (~b1 & b2); E##41 = b1 ^ (~b2 & b3); E##42 = b2 ^ (~b3 & b4); E##43 = b3 ^ (~b4 & b0); E##44 = b4 ^ (~b0 & b1); \
+    } while (0)
 
 void keccak_f(uint64_t s[25]) {
     static const uint64_t RC[24] = {0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL,
@@ -89,18 +176,18 @@ void keccak_f(uint64_t s[25]) {
                                     0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
                                     0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
                                     0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-    static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};   // [x + 5y]
-    for (int r = 0; r < 24; r++) {
-        uint64_t c[5], d[5], b[25];
-        for (int x = 0; x < 5; x++) c[x] = s[x] ^ s[x + 5] ^ s[x + 10] ^ s[x + 15] ^ s[x + 20];
-        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
-        for (int i = 0; i < 25; i++) s[i] ^= d[i % 5];
-        for (int x = 0; x < 5; x++)
-            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(s[x + 5 * y], ROT[x + 5 * y]);   // rho + pi
-        for (int y = 0; y < 5; y++)
-            for (int x = 0; x < 5; x++) s[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
-        s[0] ^= RC[r];
+    // lane [x + 5y] of the state is a<y><x>
+    uint64_t a00 = s[0], a01 = s[1], a02 = s[2], a03 = s[3], a04 = s[4], a10 = s[5], a11 = s[6], a12 = s[7], a13 = s[8], a14 = s[9],
+             a20 = s[10], a21 = s[11], a22 = s[12], a23 = s[13], a24 = s[14], a30 = s[15], a31 = s[16], a32 = s[17], a33 = s[18], a34 = s[19],
+             a40 = s[20], a41 = s[21], a42 = s[22], a43 = s[23], a44 = s[24];
+    uint64_t e00, e01, e02, e03, e04, e10, e11, e12, e13, e14, e20, e21, e22, e23, e24, e30, e31, e32, e33, e34, e40, e41, e42, e43, e44;
+    for (int r = 0; r < 24; r += 2) {
+        RS_KROUND(a, e, RC[r]);
+        RS_KROUND(e, a, RC[r + 1]);
     }
+    s[0] = a00; s[1] = a01; s[2] = a02; s[3] = a03; s[4] = a04; s[5] = a10; s[6] = a11; s[7] = a12; s[8] = a13; s[9] = a14;
+    s[10] = a20; s[11] = a21; s[12] = a22; s[13] = a23; s[14] = a24; s[15] = a30; s[16] = a31; s[17] = a32; s[18] = a33; s[19] = a34;
+    s[20] = a40; s[21] = a41; s[22] = a42; s[23] = a43; s[24] = a44;
 }
 
 struct Shake128 {
@@ -161,6 +248,44 @@ struct Transcript {
 
 struct Lin { int kind, is_ntt; long idx_inv; std::vector<int32_t> pairs; };
 
+// Evaluate's SHAKE128 transcript starts with the commit key and every commitment (jindo/prover.go:221-226) -- hundreds of KB
+// at ~0.3 GB/s.  None of it depends on the evaluation point, so a worker thread absorbs each commitment as soon as it is
+// out while the main thread keeps the GPU busy with the next rounds.
+struct ShakeWorker {
+    Shake128 xof;
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::vector<uint8_t>> q;
+    bool closing = false, running = false;
+    void start() {
+        running = true;
+        th = std::thread([this] {
+            for (;;) {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return !q.empty() || closing; });
+                if (q.empty()) return;
+                std::vector<uint8_t> v = std::move(q.front());
+                q.pop_front();
+                lk.unlock();
+                xof.absorb(v.data(), v.size());
+            }
+        });
+    }
+    void post(const uint8_t *p, size_t n) {
+        { std::lock_guard<std::mutex> lk(m); q.emplace_back(p, p + n); }
+        cv.notify_one();
+    }
+    void finish() {
+        if (!running) return;
+        { std::lock_guard<std::mutex> lk(m); closing = true; }
+        cv.notify_one();
+        th.join();
+        running = false;
+    }
+    ~ShakeWorker() { finish(); }
+};
+
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -181,8 +306,10 @@ struct rs_buckler {
     // persistent device batches
     rs_batch *vals = nullptr, *ecd = nullptr, *ntt = nullptr, *w_ntt = nullptr, *pw_ntt = nullptr, *work = nullptr, *quo = nullptr, *lv = nullptr,
              *le = nullptr, *qr = nullptr, *rem = nullptr, *qs = nullptr, *rems = nullptr;
-    uint64_t *pin = nullptr;        // pinned staging: witnesses in, commitments out
-    size_t pin_words = 0;
+    uint64_t *pin = nullptr;        // pinned staging: witnesses and masks in, commitments out
+    size_t pin_words = 0, off_lin_mask = 0, off_sum_mask = 0, off_coms = 0;
+    uint64_t *tape_pin = nullptr;   // pinned staging of the tapes' host arrays (grown on demand)
+    size_t tape_pin_words = 0;
     uint64_t n_mont[32];            // N as a Montgomery element (nttChecker.TransposeTo's scale)
     size_t batch() const { return wc + (arith_terms.empty() ? 0 : 1) + (lin.empty() ? 0 : 4) + (sum_terms.empty() ? 0 : 4); }
 };
@@ -215,6 +342,7 @@ void rs_buckler_destroy(rs_buckler *b) {
     for (rs_ntt *t : {b->enc, b->emb, b->neg})
         if (t) rs_ntt_destroy(t);
     if (b->pin) rs_pinned_free(b->pin);
+    if (b->tape_pin) rs_pinned_free(b->tape_pin);
     delete b;
 }
 
@@ -281,9 +409,10 @@ int rs_buckler_create(rs_field *f, rs_jindo *j, const rs_buckler_circuit *c, con
         rc = rs_field_to_mont(f, b->n_mont, n_can);
     }
     if (rc == RS_OK) {
-        b->pin_words = np * N * b->L;
-        const size_t mask_words = (2 * N > b->sum_max_rank ? 2 * N : b->sum_max_rank) * b->L;
-        if (b->pin_words < mask_words) b->pin_words = mask_words;
+        b->off_lin_mask = np * N * b->L;
+        b->off_sum_mask = b->off_lin_mask + 2 * N * b->L;
+        b->off_coms = b->off_sum_mask + b->sum_max_rank * b->L;
+        b->pin_words = b->off_coms + b->batch() * (size_t)b->jp.out_msis * b->jp.n_qout * b->jp.d;
         b->pin = (uint64_t *)rs_pinned_alloc(b->pin_words * 8);
         if (!b->pin) rc = rs::set_error(RS_ERR_CUDA, "rs_buckler_create: pinned allocation failed");
     }
@@ -303,7 +432,7 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     if (rd->n_tapes != n_com || !rd->tapes || !rd->blind) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: one tape per commitment and the blinding elements are required");
     if ((has_lin && (!rd->lin_mask || !rd->lin_mask_sum)) || (has_sum && (!rd->sum_mask || !rd->sum_mask_sum)))
         return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: mask polynomial missing");
-    double t_phase[8] = {0};
+    double t_phase[16] = {0};
     double t_last = now_ms();
     const double t_start = t_last;
     auto mark = [&](int k) {
@@ -314,12 +443,52 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
         t_last = t;
     };
     const size_t com_words = (size_t)jp.out_msis * jp.n_qout * jp.d;
+    uint64_t *coms_pin = b->pin + b->off_coms;
+
+    // ---- tapes: the Commits are enqueued without waiting for each other, so their host arrays must be pinned (a copy from
+    // pageable memory would make every cudaMemcpyAsync wait for the stream).  Pageable tapes are staged here first.
+    std::vector<rs_jindo_tape> tapes(rd->tapes, rd->tapes + n_com);
+    if (!rd->tapes_pinned) {
+        const size_t cs = (size_t)jp.cols * jp.slots, nmd = (size_t)(jp.in_msis + jp.mlwe) * jp.d;
+        auto tape_words = [&](const rs_jindo_tape &t) {
+            return 2 * cs * L + t.n_mask_rows * jp.slots * L + (t.twin_u ? t.n_twin_u : 0) + t.n_cosac_polys * jp.d +
+                   (t.mlwe_mask_only ? nmd : (size_t)(jp.cols + 1) * nmd);
+        };
+        size_t total = 0;
+        for (const rs_jindo_tape &t : tapes) if (!t.on_device) total += tape_words(t);
+        if (total > b->tape_pin_words) {
+            rs_sync();
+            if (b->tape_pin) rs_pinned_free(b->tape_pin);
+            b->tape_pin_words = total + total / 8;
+            b->tape_pin = (uint64_t *)rs_pinned_alloc(b->tape_pin_words * 8);
+            if (!b->tape_pin) { b->tape_pin_words = 0; return rs::set_error(RS_ERR_CUDA, "rs_buckler_prove: pinned allocation failed"); }
+        }
+        uint64_t *o = b->tape_pin;
+        auto stage = [&](const void *src, size_t words) -> uint64_t * {
+            uint64_t *dst = o;
+            memcpy(dst, src, words * 8);
+            o += words;
+            return dst;
+        };
+        for (rs_jindo_tape &t : tapes) {
+            if (t.on_device) continue;
+            if (!t.first_row || !t.last_row || !t.mask_rows || !t.cosac_g || !t.mlwe) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: incomplete tape");
+            t.first_row = stage(t.first_row, cs * L);
+            t.last_row = stage(t.last_row, cs * L);
+            t.mask_rows = stage(t.mask_rows, t.n_mask_rows * jp.slots * L);
+            if (t.twin_u) t.twin_u = stage(t.twin_u, t.n_twin_u);
+            t.cosac_g = (const int64_t *)stage(t.cosac_g, t.n_cosac_polys * jp.d);
+            t.mlwe = (const int64_t *)stage(t.mlwe, t.mlwe_mask_only ? nmd : (size_t)(jp.cols + 1) * nmd);
+        }
+    }
+    mark(6);
+
     std::vector<uint8_t> raw;
     auto raw_of = [&](size_t idx) -> int {
-        const long long n = rs_jindo_commitment_write_raw(b->j, pf->witness + idx * com_words, nullptr, 0);
+        const long long n = rs_jindo_commitment_write_raw(b->j, coms_pin + idx * com_words, nullptr, 0);
         if (n < 0) return (int)n;
         raw.resize((size_t)n);
-        const long long got = rs_jindo_commitment_write_raw(b->j, pf->witness + idx * com_words, raw.data(), raw.size());
+        const long long got = rs_jindo_commitment_write_raw(b->j, coms_pin + idx * com_words, raw.data(), raw.size());
         return got == n ? RS_OK : (int)(got < 0 ? got : RS_ERR_ARG);
     };
     struct View { rs_batch *bt; size_t poly, len; };
@@ -327,15 +496,42 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     std::vector<rs_opening *> opens(n_com, nullptr);
     struct Cleanup {
         std::vector<rs_opening *> &o; rs_opening *extra = nullptr;
-        ~Cleanup() { for (rs_opening *x : o) if (x) rs_opening_free(x); if (extra) rs_opening_free(extra); }
+        ~Cleanup() { rs_sync(); for (rs_opening *x : o) if (x) rs_opening_free(x); if (extra) rs_opening_free(extra); }
     } cleanup{opens};
     Transcript tr;
-    size_t tape_i = 0;
-    auto commit = [&](size_t idx, rs_batch *bt, size_t poly, size_t len, int bind_to) -> int {
+    ShakeWorker shake;
+    shake.xof.absorb((const uint8_t *)b->crs.data(), b->crs.size());             // ck.WriteRawTo (jindo/prover.go:222)
+    shake.start();
+    size_t n_issued = 0, n_bound = 0;
+    std::vector<int> bind_of(n_com);
+    // polyProver.Commit, enqueued only; the commitment lands in pinned memory
+    auto commit = [&](size_t idx, rs_batch *bt, size_t poly, size_t len, int bind) -> int {
+        if (idx != n_issued) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: commit order");
         views[idx] = View{bt, poly, len};
-        RS_B(rs_jindo_commit(b->j, bt, poly, len, &rd->tapes[tape_i++], &opens[idx], pf->witness + idx * com_words));
-        RS_B(raw_of(idx));
-        tr.bind(bind_to, raw.data(), raw.size());
+        bind_of[idx] = bind;
+        RS_B(rs_jindo_commit_async(b->j, bt, poly, len, &tapes[idx], &opens[idx], coms_pin + idx * com_words));
+        n_issued++;
+        return RS_OK;
+    };
+    // wait for the commitments issued so far, bind them into the fiat-shamir transcript in order (coms[i].WriteRawTo,
+    // oracle.Bind) and hand their bytes to the SHAKE worker; `extra` runs right after commitment `extra_after` is bound
+    uint8_t el[8 * 32];
+    auto bind_ready = [&](long extra_after_a, const uint64_t *sum_a, long extra_after_b, const uint64_t *sum_b) -> int {
+        RS_B(rs_sync());
+        for (; n_bound < n_issued; n_bound++) {
+            RS_B(raw_of(n_bound));
+            tr.bind(bind_of[n_bound], raw.data(), raw.size());
+            shake.post(raw.data(), raw.size());
+            memcpy(pf->witness + n_bound * com_words, coms_pin + n_bound * com_words, com_words * 8);
+            for (int k = 0; k < 2; k++) {
+                const long after = k ? extra_after_b : extra_after_a;
+                const uint64_t *sum = k ? sum_b : sum_a;
+                if (after == (long)n_bound && sum) {                                  // oracle.Bind("arithBatchConst", maskSum.Marshal())
+                    RS_B(rs_field_marshal(b->f, sum, el));
+                    tr.bind(ARITH_BC, el, 8 * L);
+                }
+            }
+        }
         return RS_OK;
     };
 
@@ -349,53 +545,45 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     for (size_t k = 0; k < pc; k++) RS_B(rs_batch_copy(b->pw_ntt, k, 0, b->ntt, wc + k, 0, E));
     mark(0);
     for (size_t i = 0; i < wc; i++) RS_B(commit(i, b->ecd, i, N + 1, PROJ));
-    tr.compute(PROJ);
     size_t idx = wc;
-    uint8_t el[8 * 32];
+    long lin_mask_idx = -1, sum_mask_idx = -1;
+    auto upload_mask = [&](size_t work_poly, const uint64_t *mask, size_t words_off, size_t len) -> int {
+        RS_B(rs_batch_zero(b->work, work_poly, 0, E));
+        memcpy(b->pin + words_off, mask, len * L * 8);
+        rs_batch *view = nullptr;      // the mask occupies the first `len` coefficients of an emb_rank polynomial
+        RS_B(rs_batch_wrap(b->f, (uint8_t *)rs_batch_device_ptr(b->work) + work_poly * E * L * 8, 1, len, &view));
+        const int rc = rs_batch_upload(view, 0, 1, b->pin + words_off);
+        rs_batch_free(view);
+        return rc;
+    };
     if (has_lin) {      // linCheckMask (prover.go:209-224)
-        RS_B(rs_batch_zero(b->work, 0, 0, E));
-        memcpy(b->pin, rd->lin_mask, 2 * N * L * 8);
-        {   // the mask occupies the first 2N coefficients of an emb_rank polynomial
-            rs_batch *view = nullptr;
-            RS_B(rs_batch_wrap(b->f, rs_batch_device_ptr(b->work), 1, 2 * N, &view));
-            const int rc = rs_batch_upload(view, 0, 1, b->pin);
-            rs_batch_free(view);
-            RS_B(rc);
-        }
-        RS_B(commit(idx, b->work, 0, 2 * N, ARITH_BC));
-        RS_B(rs_field_marshal(b->f, rd->lin_mask_sum, el));
-        tr.bind(ARITH_BC, el, 8 * L);
+        RS_B(upload_mask(0, rd->lin_mask, b->off_lin_mask, 2 * N));
+        lin_mask_idx = (long)idx;
+        RS_B(commit(idx++, b->work, 0, 2 * N, ARITH_BC));
         if (pf->lin_mask_sum) memcpy(pf->lin_mask_sum, rd->lin_mask_sum, 8 * L);
-        idx++;
     }
     if (has_sum) {      // sumCheckMask (prover.go:226-241)
-        const size_t SR = b->sum_max_rank;
-        RS_B(rs_batch_zero(b->work, 5, 0, E));
-        memcpy(b->pin, rd->sum_mask, SR * L * 8);
-        {
-            rs_batch *view = nullptr;
-            RS_B(rs_batch_wrap(b->f, (uint8_t *)rs_batch_device_ptr(b->work) + 5 * E * L * 8, 1, SR, &view));
-            const int rc = rs_batch_upload(view, 0, 1, b->pin);
-            rs_batch_free(view);
-            RS_B(rc);
-        }
-        RS_B(commit(idx, b->work, 5, SR, ARITH_BC));
-        RS_B(rs_field_marshal(b->f, rd->sum_mask_sum, el));
-        tr.bind(ARITH_BC, el, 8 * L);
+        RS_B(upload_mask(5, rd->sum_mask, b->off_sum_mask, b->sum_max_rank));
+        sum_mask_idx = (long)idx;
+        RS_B(commit(idx++, b->work, 5, b->sum_max_rank, ARITH_BC));
         if (pf->sum_mask_sum) memcpy(pf->sum_mask_sum, rd->sum_mask_sum, 8 * L);
-        idx++;
     }
+    // projConst only feeds the projection checker; its digest is needed as the prefix of arithBatchConst.  Bindings are per
+    // challenge name, so binding the masks' commitments before computing projConst changes nothing.
+    RS_B(bind_ready(lin_mask_idx, rd->lin_mask_sum, sum_mask_idx, rd->sum_mask_sum));
+    tr.compute(PROJ);
     mark(1);
     uint64_t bc[32], lc[32];
     RS_B(rs_field_set_bytes(b->f, tr.compute(ARITH_BC), 32, bc));
+    // From here to evalPoint no challenge depends on a new commitment (linCheckBatchConst, linCheckConst and
+    // sumCheckBatchConst have no bindings, prover.go:262-304): every remaining round is enqueued back to back.
     if (has_arith) {    // arithCheck (prover.go:399-404)
         RS_B(rs_eval_circuit(b->work, 1, b->pw_ntt, b->w_ntt, b->arith_terms.data(), b->arith_terms.size(), b->arith_coeffs.data(),
                              b->arith_coeffs.size() / L, bc));
         RS_B(rs_ntt_inverse(b->emb, b->work, 1, b->work, 1, 1));
         RS_B(rs_quorem_vanishing(b->quo, 0, b->quo, 1, b->work, 1, N));
         mark(2);
-        RS_B(commit(idx, b->quo, 0, b->arith_max_rank - N, EVAL_PT));
-        idx++;
+        RS_B(commit(idx++, b->quo, 0, b->arith_max_rank - N, EVAL_PT));
         mark(1);
     }
     RS_B(rs_field_set_bytes(b->f, tr.compute(LIN_BC), 32, bc));
@@ -459,17 +647,15 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
         idx += 3;
         mark(1);
     }
+    RS_B(bind_ready(-1, nullptr, -1, nullptr));
+    mark(1);
     uint64_t x[32];
     RS_B(rs_field_set_bytes(b->f, tr.compute(EVAL_PT), 32, x));
     if (pf->eval_point) memcpy(pf->eval_point, x, 8 * L);
 
     // ---- polyProver.Evaluate (jindo/prover.go:205-324)
-    Shake128 xof;
-    xof.absorb((const uint8_t *)b->crs.data(), b->crs.size());                   // ck.WriteRawTo
-    for (size_t i = 0; i < n_com; i++) {
-        RS_B(raw_of(i));
-        xof.absorb(raw.data(), raw.size());
-    }
+    shake.finish();                                                               // ck and every commitment absorbed
+    Shake128 &xof = shake.xof;
     RS_B(rs_field_marshal(b->f, x, el));
     xof.absorb(el, 8 * L);
     rs_opening *ob = opens[0];
@@ -478,16 +664,16 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
         Shake128 fork = xof;                                                      // Read, Reset, re-absorb the same prefix (prover.go:232-248)
         fork.squeeze(bb.data(), bb.size());
         xof.absorb(bb.data(), bb.size());
-        RS_B(rs_opening_alloc_zero(b->j, &cleanup.extra));
+        RS_B(rs_opening_combine_bytes(b->j, opens.data(), n_com, bb.data(), &cleanup.extra));
         ob = cleanup.extra;
-        for (size_t i = 0; i < n_com; i++) RS_B(rs_opening_mul_add_bytes(b->j, ob, opens[i], bb.data() + 16 * i));
     }
+    mark(8);
     const size_t pq = (size_t)jp.n_q * jp.d;
     std::vector<uint64_t> part((size_t)(jp.cols + 1) * pq);
     RS_B(rs_jindo_partial_at(b->j, ob, x, part.data()));                          // leftVec(x) encoded on the device
+    mark(9);
     memcpy(pf->partial, part.data(), (size_t)jp.cols * pq * 8);
     memcpy(pf->partial_mask, part.data() + (size_t)jp.cols * pq, pq * 8);
-    RS_B(rs_opening_download_all(ob, 2, pf->incommit));
     {
         const long long n = rs_jindo_poly_write_to(part.data(), jp.n_q, jp.d, nullptr, 0);
         if (n < 0) return (int)n;
@@ -500,11 +686,19 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     }
     std::vector<uint8_t> cs(16 * (size_t)jp.cols);
     xof.squeeze(cs.data(), cs.size());
+    mark(10);
     RS_B(rs_jindo_respond_bytes(b->j, ob, cs.data(), pf->encode, pf->mlwe));
-    for (size_t i = 0; i < n_com; i++)                                            // Poly.Evaluate of every committed vector
-        RS_B(rs_poly_evaluate(views[i].bt, views[i].poly, views[i].len, x, pf->evals + i * L));
-    mark(5);
+    RS_B(rs_opening_download_all(ob, 2, pf->incommit));
+    mark(11);
+    {                                                                             // Poly.Evaluate of every committed vector
+        std::vector<const rs_batch *> bs(n_com);
+        std::vector<size_t> ps(n_com), ls(n_com);
+        for (size_t i = 0; i < n_com; i++) { bs[i] = views[i].bt; ps[i] = views[i].poly; ls[i] = views[i].len; }
+        RS_B(rs_poly_evaluate_many(bs.data(), ps.data(), ls.data(), n_com, x, pf->evals));
+    }
+    mark(12);
     if (phase_ms) {
+        t_phase[5] = t_phase[8] + t_phase[9] + t_phase[10] + t_phase[11] + t_phase[12];
         t_phase[7] = now_ms() - t_start;
         memcpy(phase_ms, t_phase, sizeof(t_phase));
     }

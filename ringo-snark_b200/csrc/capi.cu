@@ -60,6 +60,7 @@ int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uin
            const uint32_t *x, const uint32_t *x_pow_ch, int CH);
 int blind(const rs_field *f, uint32_t *polys, const uint32_t *d_blind, size_t n, size_t rank, size_t N);
 int powers(const rs_field *f, uint32_t *out, const uint32_t *c, size_t n);
+int evaluate_many(const rs_field *f, uint32_t *d_results, const void *d_descs, size_t n_polys, const uint32_t *x);
 enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
 
 // ---- host-side field helpers (setup only) -------------------------------------------------
@@ -721,6 +722,32 @@ int rs_poly_evaluate(const rs_batch *p, size_t poly, size_t n_elems, const uint6
         if (e2 != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_poly_evaluate: %s", cudaGetErrorString(e2));
     }
     cudaFreeAsync(d_partial, g_stream);
+    return rc;
+}
+
+int rs_poly_evaluate_many(const rs_batch *const *batches, const size_t *polys, const size_t *lens, size_t n, const uint64_t *x, uint64_t *results) {
+    RS_REQUIRE(batches && polys && lens && x && results, RS_ERR_ARG, "rs_poly_evaluate_many: null argument");
+    if (n == 0) return RS_OK;
+    const rs_field *f = batches[0]->f;
+    const int NL = f->NL;
+    struct Desc { const uint32_t *coeffs; size_t n; };
+    std::vector<Desc> h(n);
+    for (size_t i = 0; i < n; i++) {
+        RS_REQUIRE(batches[i] && batches[i]->f->NL == NL, RS_ERR_SHAPE, "rs_poly_evaluate_many: field mismatch");
+        RS_REQUIRE(polys[i] < batches[i]->n_polys && lens[i] <= batches[i]->rank, RS_ERR_SHAPE, "rs_poly_evaluate_many: range out of bounds");
+        h[i] = Desc{elem_ptr(batches[i], polys[i]), lens[i]};
+    }
+    uint8_t *d_buf = nullptr;
+    const size_t desc_bytes = (n * sizeof(Desc) + 15) & ~(size_t)15;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_buf, desc_bytes + n * NL * 4, g_stream));
+    cudaError_t e = cudaMemcpyAsync(d_buf, h.data(), n * sizeof(Desc), cudaMemcpyHostToDevice, g_stream);   // pageable: staged before the call returns
+    int rc = e == cudaSuccess ? evaluate_many(f, (uint32_t *)(d_buf + desc_bytes), d_buf, n, (const uint32_t *)x) : set_error(RS_ERR_CUDA, "rs_poly_evaluate_many: %s", cudaGetErrorString(e));
+    if (rc == RS_OK) {
+        e = cudaMemcpyAsync(results, d_buf + desc_bytes, n * NL * 4, cudaMemcpyDeviceToHost, g_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g_stream);
+        if (e != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_poly_evaluate_many: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(d_buf, g_stream);
     return rc;
 }
 

@@ -47,7 +47,7 @@ struct RingDev {
     int f64_ok;
     // kernel-path switches (tuning / the parity tests of the alternative paths): read from the environment ONCE, when the
     // prover handle is created, never on the Commit path
-    int no_rowsum, no_pipe, no_split;
+    int no_rowsum, no_pipe, no_split, no_small;
 };
 
 struct CrtDev {             // RNSReconstructor constants of the *source* ring (rns.go:33-55)
@@ -680,7 +680,7 @@ __device__ __forceinline__ void mac_lazy(uint32_t &s0a, uint32_t &s0b, uint32_t 
     acc_mad(s2, k1, x1);
 }
 
-template <int OT, int CT, int WARPS, bool FOLD>
+template <int OT, int CT, int WARPS, bool FOLD, int UNR = 2>
 __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
                                                            const u64 *__restrict__ x, const u64 *__restrict__ addend,
                                                            const __grid_constant__ MatvecGeom G) {
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ ou
     }
     const size_t x_step = (size_t)G.x_ks * pw, k_step = (size_t)G.key_ks * pw;
     const bool key_per_col = (G.key_cs != 0);
-#pragma unroll 2
+#pragma unroll(UNR)
     for (int k = 0; k < G.K; k++) {
         u64 kv[OT][CT], xv[CT];
 #pragma unroll
@@ -1114,6 +1114,22 @@ __global__ void __launch_bounds__(256) muladd_bcast_kernel(u64 *__restrict__ acc
     }
 }
 
+// acc[p] = sum_k srcs[k][p] (.) chal[k]   -- the whole batch combination of Evaluate (prover.go:251-265) in one pass: every
+// opening is read once and the accumulator written once (the reference adds the products one opening at a time; the sum of
+// canonical residues mod q does not depend on the order)
+__global__ void __launch_bounds__(256) combine_kernel(u64 *__restrict__ acc, const u64 *const *__restrict__ srcs, const u64 *__restrict__ chals,
+                                                      int n, size_t n_polys, int n_limbs, const __grid_constant__ MatvecGeom G) {
+    const size_t pw = (size_t)n_limbs * JD;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_polys * pw; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t slot = i % pw;
+        const int limb = (int)(slot / JD);
+        const u64 q = G.q[limb], qi = G.qinvneg[limb];
+        u64 a = 0;
+        for (int k = 0; k < n; k++) a = addmod(a, mont64(__ldg(srcs[k] + i), __ldg(chals + (size_t)k * pw + slot), q, qi), q);
+        acc[i] = a;
+    }
+}
+
 // out = a * s - b [- c]  (mod q), s a per-limb Montgomery scalar: the verifier's  commitment * 2^cut - key (.) proof  lines
 // (MulRNSScalarMontgomery + MulCoeffsMontgomeryThenSub + Sub, verifier.go:146-157, :183-196)
 __global__ void __launch_bounds__(256) scale_sub_kernel(u64 *__restrict__ out, const u64 *__restrict__ a, const u64 *__restrict__ b,
@@ -1173,6 +1189,7 @@ static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi
     R.n = n;
     R.f64_ok = getenv("RS_JINDO_NOF64") ? 0 : 1;
     R.no_rowsum = getenv("RS_MV_NOROWSUM") ? 1 : 0; R.no_pipe = getenv("RS_MV_NOPIPE") ? 1 : 0; R.no_split = getenv("RS_MV_NOSPLIT") ? 1 : 0;
+    R.no_small = getenv("RS_MV_NOSMALL") ? 1 : 0;
     for (int l = 0; l < n; l++) {
         const u64 ql = q[l];
         if (ql >= (1ull << 44)) R.f64_ok = 0;
@@ -1366,7 +1383,14 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         if (G.fold_every) matvec_kernel<OT, CT, WARPS, true><<<grid, dim3(32, WARPS), 0, current_stream()>>>(out, key, x, addend, G); \
         else matvec_kernel<OT, CT, WARPS, false><<<grid, dim3(32, WARPS), 0, current_stream()>>>(out, key, x, addend, G);             \
     }
-    RS_MV(5, 2, 4)
+    // a small product (the Commits of a Buckler proof: K*C in the hundreds) would leave two thirds of the SMs without a CTA
+    // with the 5 x 2 register tile and spends its time waiting for loads: one output per thread, eight loads in flight
+    if ((long long)((n_slots + 31) / 32) * ((G.O + 4) / 5) * ((G.C + 7) / 8) < 148 * 2 && !R.no_small) {
+        dim3 grid((n_slots + 31) / 32, G.O, (G.C + 3) / 4);
+        if (G.fold_every) matvec_kernel<1, 1, 4, true, 8><<<grid, dim3(32, 4), 0, current_stream()>>>(out, key, x, addend, G);
+        else matvec_kernel<1, 1, 4, false, 8><<<grid, dim3(32, 4), 0, current_stream()>>>(out, key, x, addend, G);
+    } else
+        RS_MV(5, 2, 4)
 #undef RS_MV
     count_launch();
     RS_CUDA_CHECK(cudaGetLastError());
@@ -1461,7 +1485,7 @@ static int upload(T **d, const T *h, size_t count) {
     return RS_OK;
 }
 
-static int opening_alloc(rs_jindo *j, rs_opening **out) {
+static int opening_alloc(rs_jindo *j, rs_opening **out, bool zero = true) {
     rs_opening *o = new rs_opening{j, nullptr, nullptr, nullptr};
     const rs_jindo_params &p = j->p;
     const size_t ne = (size_t)(p.cols + 1) * p.rows * pq(j), nm = (size_t)(p.cols + 1) * (p.mlwe + p.in_msis) * pq(j),
@@ -1470,9 +1494,9 @@ static int opening_alloc(rs_jindo *j, rs_opening **out) {
     cudaError_t e = cudaMallocAsync((void **)&o->d_encode, ne * 8, current_stream());
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&o->d_mlwe, nm * 8, current_stream());
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&o->d_incommit, ni * 8, current_stream());
-    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_encode, 0, ne * 8, current_stream());
-    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_mlwe, 0, nm * 8, current_stream());
-    if (e == cudaSuccess) e = cudaMemsetAsync(o->d_incommit, 0, ni * 8, current_stream());
+    if (zero && e == cudaSuccess) e = cudaMemsetAsync(o->d_encode, 0, ne * 8, current_stream());
+    if (zero && e == cudaSuccess) e = cudaMemsetAsync(o->d_mlwe, 0, nm * 8, current_stream());
+    if (zero && e == cudaSuccess) e = cudaMemsetAsync(o->d_incommit, 0, ni * 8, current_stream());
     if (e != cudaSuccess) { rs_opening_free(o); return set_error(RS_ERR_CUDA, "opening alloc: %s", cudaGetErrorString(e)); }
     *out = o;
     return RS_OK;
@@ -2210,12 +2234,14 @@ int rs_opening_download(const rs_opening *o, int kind, size_t col, size_t idx, u
 }
 
 // vec: the committed vector in HBM, or nullptr with v_host set (then it is uploaded piecewise, see DescCache)
-static int outer_commit(rs_jindo *j, const rs_opening *o, uint64_t *commitment_out);
+static int outer_commit(rs_jindo *j, const rs_opening *o, uint64_t *commitment_out, bool sync = true);
 
 // col0/col1: the columns of the committed matrix to process (the mask column is index cols); a whole Commit
 // is [0, cols+1) and ends with the outer commit, a partial one leaves InCommit[col0*in_msis, col1*in_msis) filled
+// sync == false (rs_jindo_commit_async): nothing waits for the stream; commitment_out must be pinned and, like a host-resident
+// tape, stay untouched until the caller has synchronised
 static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host, size_t len, const rs_jindo_tape *tape,
-                       rs_opening **open, uint64_t *commitment_out, int col0, int col1) {
+                       rs_opening **open, uint64_t *commitment_out, int col0, int col1, bool sync = true) {
     const rs_jindo_params &p = j->p;
     RS_REQUIRE(col0 >= 0 && col0 < col1 && col1 <= p.cols + 1, RS_ERR_ARG, "rs_jindo_commit: bad column range");
     const bool whole = (commitment_out != nullptr);       // rs_jindo_commit_columns never runs the outer commit
@@ -2401,7 +2427,7 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         }
         // ---- cut-off pipeline (prover.go:164-176)
         RS_TRY(launch_cut(j, o->d_incommit + (size_t)col0 * p.in_msis * pqo(j), com0, (size_t)nc * p.in_msis, false));
-        if (whole) RS_TRY(outer_commit(j, o, commitment_out));
+        if (whole) RS_TRY(outer_commit(j, o, commitment_out, sync));
         // a column shard ends without the outer commit: host-resident tape buffers must have been consumed before the caller
         // may reuse them; with a device-resident tape nothing needs the host to wait (the exchange runs on the same stream)
         else if (!dev && cudaStreamSynchronize(current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit_columns: %s", cudaGetErrorString(cudaGetLastError())); goto fail; }
@@ -2427,7 +2453,7 @@ fail:
 
 // outer commit (prover.go:180-202) from Opening.InCommit: split over the cols+1 column blocks, partial sums
 // reduced mod q afterwards (same field element as the sequential sum), then the cut-off pipeline
-static int outer_commit(rs_jindo *j, const rs_opening *o, uint64_t *commitment_out) {
+static int outer_commit(rs_jindo *j, const rs_opening *o, uint64_t *commitment_out, bool sync) {
     const rs_jindo_params &p = j->p;
     const int cols = p.cols;
     const size_t n_com = (size_t)(cols + 1) * p.in_msis;
@@ -2456,7 +2482,7 @@ static int outer_commit(rs_jindo *j, const rs_opening *o, uint64_t *commitment_o
     }
     if (rc == RS_OK &&
         (cudaMemcpyAsync(commitment_out, d_value, (size_t)p.out_msis * pqo(j) * 8, cudaMemcpyDeviceToHost, current_stream()) != cudaSuccess ||
-         cudaStreamSynchronize(current_stream()) != cudaSuccess))
+         (sync && cudaStreamSynchronize(current_stream()) != cudaSuccess)))
         rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFreeAsync(d_part, current_stream()); cudaFreeAsync(d_com2, current_stream()); cudaFreeAsync(d_value, current_stream());
     return rc;
@@ -2468,6 +2494,14 @@ int rs_jindo_commit(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, c
     RS_REQUIRE(len >= 1 && v_poly < v->n_polys && len <= v->rank, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
     RS_REQUIRE(v->f->NL == j->f->NL, RS_ERR_SHAPE, "rs_jindo_commit: field mismatch");
     return commit_impl(j, v->d + v_poly * v->rank * j->f->NL, nullptr, len, tape, open, commitment_out, 0, j->p.cols + 1);
+}
+
+int rs_jindo_commit_async(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
+                          rs_opening **open, uint64_t *commitment_out_pinned) {
+    RS_REQUIRE(j && v && tape && open && commitment_out_pinned, RS_ERR_ARG, "rs_jindo_commit_async: null argument");
+    RS_REQUIRE(len >= 1 && v_poly < v->n_polys && len <= v->rank, RS_ERR_SHAPE, "rs_jindo_commit_async: vector range out of bounds");
+    RS_REQUIRE(v->f->NL == j->f->NL, RS_ERR_SHAPE, "rs_jindo_commit_async: field mismatch");
+    return commit_impl(j, v->d + v_poly * v->rank * j->f->NL, nullptr, len, tape, open, commitment_out_pinned, 0, j->p.cols + 1, false);
 }
 
 int rs_jindo_commit_columns(rs_jindo *j, const rs_batch *v, size_t v_poly, size_t len, const rs_jindo_tape *tape,
@@ -2782,6 +2816,41 @@ int rs_opening_mul_add_bytes(rs_jindo *j, rs_opening *acc, const rs_opening *o, 
     if (d_cq) cudaFreeAsync(d_cq, current_stream());
     if (d_co) cudaFreeAsync(d_co, current_stream());
     return rc;
+}
+
+int rs_opening_combine_bytes(rs_jindo *j, const rs_opening *const *opens, size_t n, const uint8_t *chal_bytes, rs_opening **out) {
+    RS_REQUIRE(j && opens && chal_bytes && out && n >= 1, RS_ERR_ARG, "rs_opening_combine_bytes: bad argument");
+    for (size_t k = 0; k < n; k++) RS_REQUIRE(opens[k] && opens[k]->j == j, RS_ERR_ARG, "rs_opening_combine_bytes: opening belongs to another prover");
+    const rs_jindo_params &p = j->p;
+    rs_opening *acc = nullptr;
+    int rc = opening_alloc(j, &acc, false);
+    if (rc) return rc;
+    u64 *d_cq = nullptr, *d_co = nullptr;
+    const u64 **d_ptrs = nullptr;
+    std::vector<const u64 *> h(3 * n);
+    for (size_t k = 0; k < n; k++) { h[k] = opens[k]->d_encode; h[n + k] = opens[k]->d_mlwe; h[2 * n + k] = opens[k]->d_incommit; }
+    rc = encode_challenges(j, chal_bytes, n, j->rq, &d_cq);
+    if (rc == RS_OK) rc = encode_challenges(j, chal_bytes, n, j->rqo, &d_co);
+    if (rc == RS_OK && (cudaMallocAsync((void **)&d_ptrs, 3 * n * sizeof(u64 *), current_stream()) != cudaSuccess ||
+                        cudaMemcpyAsync(d_ptrs, h.data(), 3 * n * sizeof(u64 *), cudaMemcpyHostToDevice, current_stream()) != cudaSuccess))
+        rc = set_error(RS_ERR_CUDA, "rs_opening_combine_bytes: upload failed");      // pageable source: staged before the call returns
+    if (rc == RS_OK) {
+        MatvecGeom Gq, Go;
+        memset(&Gq, 0, sizeof(Gq)); memset(&Go, 0, sizeof(Go));
+        fill_geom_ring(Gq, j->rq); fill_geom_ring(Go, j->rqo);
+        const size_t ne = (size_t)(p.cols + 1) * p.rows, nm = (size_t)(p.cols + 1) * (p.mlwe + p.in_msis), ni = (size_t)(p.cols + 1) * p.in_msis;
+        combine_kernel<<<148 * 8, 256, 0, current_stream()>>>(acc->d_encode, d_ptrs, d_cq, (int)n, ne, j->rq.n, Gq);
+        combine_kernel<<<148 * 2, 256, 0, current_stream()>>>(acc->d_mlwe, d_ptrs + n, d_cq, (int)n, nm, j->rq.n, Gq);
+        combine_kernel<<<148 * 2, 256, 0, current_stream()>>>(acc->d_incommit, d_ptrs + 2 * n, d_co, (int)n, ni, j->rqo.n, Go);
+        count_launch(3);
+        if (cudaGetLastError() != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_opening_combine_bytes: launch failed");
+    }
+    if (d_cq) cudaFreeAsync(d_cq, current_stream());
+    if (d_co) cudaFreeAsync(d_co, current_stream());
+    if (d_ptrs) cudaFreeAsync(d_ptrs, current_stream());
+    if (rc) { rs_opening_free(acc); return rc; }
+    *out = acc;
+    return RS_OK;
 }
 
 int rs_opening_mul_add(rs_jindo *j, rs_opening *acc, const rs_opening *o, const uint64_t *chal_q, const uint64_t *chal_qout) {

@@ -439,4 +439,87 @@ int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uin
     return RS_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Poly.Evaluate of many polynomials at one point (jindo.Prover.Evaluate's closing loop, jindo/prover.go:318-321: one
+// evaluation per committed vector of the batch).  One CTA per polynomial: thread t Horner-evaluates a contiguous chunk
+// of CH = ceil(n / 256) coefficients, scales it by x^(t CH) (square-and-multiply on its own), and the 256 terms are
+// summed in shared memory.  Exact field arithmetic: the same element as the reference's sequential Horner.
+// ---------------------------------------------------------------------------
+struct EvalDesc { const uint32_t *coeffs; size_t n; };
+
+template <int NL, int QS>
+__device__ __forceinline__ void pow_small(uint32_t *r, const uint32_t *base, size_t e, const FieldParams<NL> &F) {
+    uint32_t b[NL], t[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) { r[l] = F.one[l]; b[l] = base[l]; }
+    for (; e; e >>= 1) {
+        if (e & 1) {
+            mont_mul<NL, QS>(t, r, b, F);
+#pragma unroll
+            for (int l = 0; l < NL; l++) r[l] = t[l];
+        }
+        if (e > 1) {
+            mont_mul<NL, QS>(t, b, b, F);
+#pragma unroll
+            for (int l = 0; l < NL; l++) b[l] = t[l];
+        }
+    }
+}
+
+template <int NL, int QS>
+__global__ void __launch_bounds__(256) evaluate_many_kernel(uint32_t *results, const EvalDesc *descs, const __grid_constant__ Scalar<NL> x,
+                                                            const __grid_constant__ FieldParams<NL> F) {
+    __shared__ uint32_t sh[256 * NL];
+    const EvalDesc D = descs[blockIdx.x];
+    const int t = threadIdx.x;
+    const size_t CH = (D.n + 255) / 256;
+    const size_t lo = (size_t)t * CH, hi = lo + CH < D.n ? lo + CH : D.n;
+    uint32_t acc[NL], c[NL], tmp[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) acc[l] = 0;
+    if (lo < D.n) {
+        for (size_t i = hi; i-- > lo;) {
+            mont_mul<NL, QS>(tmp, acc, x.v, F);
+            ld_elem<NL>(c, D.coeffs + i * NL);
+            mod_add<NL>(acc, tmp, c, F);
+        }
+        if (t) {
+            pow_small<NL, QS>(c, x.v, CH, F);         // x^CH
+            pow_small<NL, QS>(tmp, c, (size_t)t, F);  // x^(t CH)
+            mont_mul<NL, QS>(c, acc, tmp, F);
+#pragma unroll
+            for (int l = 0; l < NL; l++) acc[l] = c[l];
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) sh[t * NL + l] = acc[l];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s) {
+#pragma unroll
+            for (int l = 0; l < NL; l++) { acc[l] = sh[t * NL + l]; c[l] = sh[(t + s) * NL + l]; }
+            mod_add<NL>(tmp, acc, c, F);
+#pragma unroll
+            for (int l = 0; l < NL; l++) sh[t * NL + l] = tmp[l];
+        }
+        __syncthreads();
+    }
+    if (t < NL) results[(size_t)blockIdx.x * NL + t] = sh[t];
+}
+
+int evaluate_many(const rs_field *f, uint32_t *d_results, const void *d_descs, size_t n_polys, const uint32_t *x) {
+#define CALL(NL, QS)                                                                                          \
+    {                                                                                                         \
+        FieldParams<NL> F = make_params<NL>(f);                                                               \
+        Scalar<NL> sx;                                                                                        \
+        for (int i = 0; i < NL; i++) sx.v[i] = x[i];                                                          \
+        evaluate_many_kernel<NL, QS><<<(unsigned)n_polys, 256, 0, current_stream()>>>(d_results, (const EvalDesc *)d_descs, sx, F); \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
+}
+
 }  // namespace rs

@@ -345,6 +345,14 @@ class Prover:
         """prover.go:230-265: acc += opening (.) encodeChallenge(16 bytes), both rings, encoded on the device."""
         check(lib().rs_opening_mul_add_bytes(self.h, acc.h, opening.h, ctypes.c_char_p(bytes(chal16))))
 
+    def OpeningCombineBytes(self, openings, chal_bytes):
+        """prover.go:230-265 in one pass (rs_opening_combine_bytes): sum_i openings[i] (.) encodeChallenge(16 bytes each)."""
+        assert len(chal_bytes) == 16 * len(openings)
+        hs = (c_vp * len(openings))(*[o.h.value for o in openings])
+        oh = c_vp()
+        check(lib().rs_opening_combine_bytes(self.h, hs, len(openings), ctypes.c_char_p(bytes(chal_bytes)), ctypes.byref(oh)))
+        return Opening(self, oh)
+
     def NewOpening(self):
         oh = c_vp()
         check(lib().rs_opening_alloc_zero(self.h, ctypes.byref(oh)))

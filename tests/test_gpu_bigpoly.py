@@ -193,6 +193,17 @@ def test_quorem_aut_reverse_evaluate(rs):
     x = rand_mont(fo, 1, 9)[0]
     for cnt in (n, n - 1, 1, 65, 64, 63):
         assert np.array_equal(B.poly(0).Evaluate(x, cnt), fo.poly_evaluate(a[:cnt], x)), cnt
+    # the batched form (jindo.Prover.Evaluate's closing loop): ragged lengths incl. 1, < 256 and non-multiples of 256
+    import ctypes
+    lens = [n, n - 1, 1, 255, 256, 257, 1000, 3]
+    hs = (ctypes.c_void_p * len(lens))(*[B.h.value] * len(lens))
+    ps = (ctypes.c_size_t * len(lens))(*[k % 2 for k in range(len(lens))])
+    ls = (ctypes.c_size_t * len(lens))(*lens)
+    out = np.zeros((len(lens), fo.L), dtype=np.uint64)
+    a1 = B.download(1, 1)[0]
+    assert rs.lib().rs_poly_evaluate_many(hs, ps, ls, len(lens), x.ctypes.data_as(rs.capi.c_u64p), out.ctypes.data_as(rs.capi.c_u64p)) == 0, rs.lib().rs_last_error()
+    for k, cnt in enumerate(lens):
+        assert np.array_equal(out[k], fo.poly_evaluate((a if k % 2 == 0 else a1)[:cnt], x)), ("many", cnt)
 
 
 @pytest.mark.parametrize("name", ["zp128", "zp240"])

@@ -92,6 +92,18 @@ def test_commit_and_evaluate_parity(rs, name, N, batch, length):
     zo = p.ringQOut.new_poly()
     e = p.ringQOut.mul_mont_then_add(open_o.InCommit[3], co, p.ringQOut.mul_mont_then_add(open_o.InCommit[3], co, zo))
     assert np.array_equal(acc_g.InCommit(3), polys_array(e))
+    # the same loop in one pass (rs_opening_combine_bytes): two openings, two different challenges
+    b2 = b"\x05" * 16 + bytes(range(16))
+    seq = gp.NewOpening()
+    gp.OpeningMulAddBytes(seq, open_g, b2[:16]); gp.OpeningMulAddBytes(seq, acc_g, b2[16:])
+    one = gp.OpeningCombineBytes([open_g, acc_g], b2)
+    for k in range((p.cols + 1) * p.in_msis):
+        assert np.array_equal(one.InCommit(k), seq.InCommit(k)), ("combine InCommit", k)
+    for c in range(p.cols + 1):
+        for r in (0, 1, p.rows - 1):
+            assert np.array_equal(one.Encode(c, r), seq.Encode(c, r)), ("combine Encode", c, r)
+        for r in (0, p.mlwe + p.in_msis - 1):
+            assert np.array_equal(one.MLWE(c, r), seq.MLWE(c, r)), ("combine MLWE", c, r)
 
 
 def test_commit_shape_errors(rs):
