@@ -15,6 +15,7 @@
 #define RINGO_BUCKLER_H
 
 #include "ringo_jindo.h"
+#include "ringo_sampler.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -77,10 +78,17 @@ int rs_buckler_create(rs_field *f, rs_jindo *j, const rs_buckler_circuit *c, con
 void rs_buckler_destroy(rs_buckler *b);
 /* number of commitments of a proof = Context.batch() (context.go) */
 size_t rs_buckler_batch(const rs_buckler *b);
+/* Lets the prover draw its own randomness, as the reference's Prove does: an rs_tape_builder (ringo_sampler.h) with n_threads
+ * worker threads and one slot per Commit samples the COSAC rows, the mask column's noise and every MustSetRandom element from OS
+ * randomness; the encoder's TwinCDT rows and the data columns' MLWE noise come from the Jindo prover's device streams, which the
+ * caller must have set (rs_jindo_set_twin_stream, rs_jindo_set_mlwe_stream).  q_le: the field modulus, L64 limbs.  After this,
+ * rs_buckler_prove accepts rand == NULL. */
+int rs_buckler_enable_sampling(rs_buckler *b, const rs_jindo_noise *noise, const uint64_t *q_le, int n_threads);
 /* Prover.Prove.  pw / w: pw_cnt x rank and w_cnt x rank Montgomery elements (host), decomposition witnesses filled in.
  * phase_ms (optional, 16 doubles): wall milliseconds of [0] encode+NTT, [1] commits, [2] arithCheck, [3] linCheck, [4] sumCheck, [5] Evaluate,
  * [6] tape staging, [7] total; Evaluate's parts: [8] batch combination of the openings, [9] Partial, [10] InCommit download + transcript, [11] responses,
  * [12] Poly.Evaluate of the committed vectors.  The stream is synchronised at every boundary when phase_ms is given. */
+/* rand == NULL: self-sampled (see rs_buckler_enable_sampling). */
 int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const rs_buckler_rand *rand,
                      rs_buckler_proof *proof, double *phase_ms);
 

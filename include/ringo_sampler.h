@@ -72,7 +72,15 @@ typedef struct rs_tape_builder rs_tape_builder;
  * concurrency model (Prover.SafeCopy hands every goroutine fresh samplers, prover.go:327-338). */
 int rs_tape_builder_create(const rs_jindo_params *p, const rs_jindo_noise *noise, const uint64_t *q, int L64,
                            int n_threads, const uint8_t *seeds, rs_tape_builder **out);
+/* same with n_slots >= 1 buffer sets instead of two (slot index 0 .. n_slots-1 in start / wait): the compiled Buckler prover
+ * keeps one tape per Commit of a proof alive until the proof's last kernel has run */
+int rs_tape_builder_create_slots(const rs_jindo_params *p, const rs_jindo_noise *noise, const uint64_t *q, int L64,
+                                 int n_threads, int n_slots, const uint8_t *seeds, rs_tape_builder **out);
 void rs_tape_builder_destroy(rs_tape_builder *b);
+/* n MustSetRandom field elements (rejection sampling over the builder's crypto/rand stand-in), Montgomery limbs */
+int rs_tape_builder_random_elements(rs_tape_builder *b, uint64_t *out_mont, size_t n);
+/* Prover.sumCheckMask (buckler/prover.go:381-397): mask_rank coefficients and maskSum */
+int rs_tape_builder_sum_check_mask(rs_tape_builder *b, size_t rank, size_t mask_rank, uint64_t *mask_out, uint64_t *mask_sum_out);
 /* crypto/rand stand-in for the MustSetRandom draws of the NEXT rs_tape_builder_start (tests): the bytes a
  * crypto/rand.Reader would return, consumed in the reference's order (last row, then the mask rows).  Without it
  * the elements come from an AES-CTR generator keyed from the OS. */

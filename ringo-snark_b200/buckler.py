@@ -359,6 +359,15 @@ class NativeProver:
 
     mont_many = Prover.mont_many
 
+    def enable_sampling(self, noise, threads=4):
+        """rs_buckler_enable_sampling: prove_raw(pw, w, None) then draws every random value inside the library (host samplers on
+        `threads` worker threads + the Jindo prover's device streams, which must have been seeded: SetTwinSeed / SetMlweSeed)."""
+        Nz = capi.JindoNoise()
+        for k in ("ecd_blind_std", "mask_blind_std", "mask_std", "mask_mlwe_std"):
+            setattr(Nz, k, float(noise[k]))
+        qa = np.array([(self.q >> (64 * i)) & ((1 << 64) - 1) for i in range(self.L)], dtype=np.uint64)
+        check(lib().rs_buckler_enable_sampling(self.h, ctypes.byref(Nz), qa.ctypes.data_as(capi.c_u64p), int(threads)))
+
     def from_mont_arr(self, a):
         return sum(int(v) << (64 * i) for i, v in enumerate(a)) * pow(self.R, -1, self.q) % self.q
 
@@ -414,13 +423,15 @@ class NativeProver:
         P.lin_mask_sum, P.sum_mask_sum, P.eval_point = vp(out["lin_mask_sum"]), vp(out["sum_mask_sum"]), vp(out["eval_point"])
         ms = (ctypes.c_double * 16)()
         pw = np.ascontiguousarray(pw_mont, dtype=np.uint64); w = np.ascontiguousarray(w_mont, dtype=np.uint64)
-        check(lib().rs_buckler_prove(self.h, vp(pw) if pw.size else None, vp(w), ctypes.byref(R), ctypes.byref(P), ms if phases else None))
+        check(lib().rs_buckler_prove(self.h, vp(pw) if pw.size else None, vp(w), ctypes.byref(R) if R is not None else None, ctypes.byref(P),
+                                     ms if phases else None))
         self.timing = dict(zip(("encode_ntt", "commit", "arith_check", "lin_check", "sum_check", "evaluate", "tape_staging", "total", "ev_combine", "ev_partial",
                                 "ev_incommit", "ev_respond", "ev_poly_eval"), ms))
         return out
 
     def prove(self, pw_mont, w_mont, rand):
-        R, keep = self.rand_struct(rand)
+        """rand = None: self-sampled (enable_sampling first)"""
+        R, keep = self.rand_struct(rand) if rand is not None else (None, None)
         o = self.prove_raw(pw_mont, w_mont, R)
         has_lin, has_sum = bool(self.c["lin"]), bool(self.c.get("sum_terms"))
         return {"Witness": o["Witness"].tolist(), "LinCheckMaskSum": self.from_mont_arr(o["lin_mask_sum"]) if has_lin else None,

@@ -182,6 +182,7 @@ _SIGS = {
     "rs_opening_mul_add": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     # ringo_buckler.h
     "rs_buckler_create": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(BucklerCircuit), c_vp, c_size, ctypes.POINTER(c_vp)]),
+    "rs_buckler_enable_sampling": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoNoise), c_u64p, ctypes.c_int]),
     "rs_buckler_destroy": (None, [c_vp]),
     "rs_buckler_batch": (c_size, [c_vp]),
     "rs_buckler_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(BucklerRand), ctypes.POINTER(BucklerProof), ctypes.POINTER(ctypes.c_double)]),
@@ -205,6 +206,10 @@ _SIGS = {
     "rs_compute_cdt": (ctypes.c_int, [ctypes.c_double, ctypes.c_double, c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]),
     "rs_tape_builder_create": (ctypes.c_int, [ctypes.POINTER(JindoParams), ctypes.POINTER(JindoNoise), c_u64p, ctypes.c_int, ctypes.c_int,
                                               c_vp, ctypes.POINTER(c_vp)]),
+    "rs_tape_builder_create_slots": (ctypes.c_int, [ctypes.POINTER(JindoParams), ctypes.POINTER(JindoNoise), c_u64p, ctypes.c_int, ctypes.c_int,
+                                                    ctypes.c_int, c_vp, ctypes.POINTER(c_vp)]),
+    "rs_tape_builder_random_elements": (ctypes.c_int, [c_vp, c_vp, c_size]),
+    "rs_tape_builder_sum_check_mask": (ctypes.c_int, [c_vp, c_size, c_size, c_vp, c_vp]),
     "rs_tape_builder_destroy": (None, [c_vp]),
     "rs_tape_builder_set_random_bytes": (ctypes.c_int, [c_vp, c_vp, c_size]),
     "rs_tape_builder_start": (ctypes.c_int, [c_vp, c_vp, c_size, ctypes.c_int]),

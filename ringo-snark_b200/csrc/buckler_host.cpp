@@ -19,6 +19,7 @@
 #endif
 
 #include "../../include/ringo_buckler.h"
+#include "../../include/ringo_sampler.h"
 
 namespace rs { int set_error(int code, const char *fmt, ...); }
 
@@ -310,6 +311,11 @@ struct rs_buckler {
     size_t pin_words = 0, off_lin_mask = 0, off_sum_mask = 0, off_coms = 0;
     uint64_t *tape_pin = nullptr;   // pinned staging of the tapes' host arrays (grown on demand)
     size_t tape_pin_words = 0;
+    // self-sampled proofs (rs_buckler_enable_sampling): host samplers on worker threads, one tape slot per Commit
+    rs_tape_builder *tb = nullptr;
+    uint64_t *heads = nullptr;      // pinned: the first cols*slots coefficients of every committed vector (genFirstLastRow's input)
+    std::vector<uint64_t> r_blind, r_lin_mask, r_sum_mask;
+    uint64_t r_lin_sum[32], r_sum_sum[32];
     uint64_t n_mont[32];            // N as a Montgomery element (nttChecker.TransposeTo's scale)
     size_t batch() const { return wc + (arith_terms.empty() ? 0 : 1) + (lin.empty() ? 0 : 4) + (sum_terms.empty() ? 0 : 4); }
 };
@@ -343,6 +349,8 @@ void rs_buckler_destroy(rs_buckler *b) {
         if (t) rs_ntt_destroy(t);
     if (b->pin) rs_pinned_free(b->pin);
     if (b->tape_pin) rs_pinned_free(b->tape_pin);
+    if (b->heads) rs_pinned_free(b->heads);
+    if (b->tb) rs_tape_builder_destroy(b->tb);
     delete b;
 }
 
@@ -421,17 +429,52 @@ int rs_buckler_create(rs_field *f, rs_jindo *j, const rs_buckler_circuit *c, con
     return RS_OK;
 }
 
+int rs_buckler_enable_sampling(rs_buckler *b, const rs_jindo_noise *noise, const uint64_t *q_le, int n_threads) {
+    if (!b || !noise || !q_le || n_threads < 1) return rs::set_error(RS_ERR_ARG, "rs_buckler_enable_sampling: bad argument");
+    if (b->tb) { rs_tape_builder_destroy(b->tb); b->tb = nullptr; }
+    int rc = rs_tape_builder_create_slots(&b->jp, noise, q_le, b->L, n_threads, (int)b->batch(), nullptr, &b->tb);
+    if (rc != RS_OK) return rs::set_error(rc, "rs_buckler_enable_sampling: tape builder creation failed");
+    if (!b->heads) {
+        b->heads = (uint64_t *)rs_pinned_alloc(b->batch() * (size_t)b->jp.cols * b->jp.slots * b->L * 8);
+        if (!b->heads) return rs::set_error(RS_ERR_CUDA, "rs_buckler_enable_sampling: pinned allocation failed");
+    }
+    return RS_OK;
+}
+
 int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const rs_buckler_rand *rd, rs_buckler_proof *pf, double *phase_ms) {
-    if (!b || !w || !rd || !pf || (b->pc && !pw)) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: null argument");
+    if (!b || !w || !pf || (b->pc && !pw)) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: null argument");
+    const bool sampling = (rd == nullptr);       // the prover draws its own randomness, like the reference's Prove
+    rs_buckler_rand own;
+    if (sampling) {
+        if (!b->tb) return rs::set_error(RS_ERR_STATE, "rs_buckler_prove: no randomness given and rs_buckler_enable_sampling was not called");
+        memset(&own, 0, sizeof(own));
+        rd = &own;
+    }
     const size_t N = b->N, E = b->E, wc = b->wc, pc = b->pc, n_com = b->batch();
     const int L = b->L;
     const rs_jindo_params &jp = b->jp;
     const bool has_arith = !b->arith_terms.empty(), has_lin = !b->lin.empty(), has_sum = !b->sum_terms.empty();
     if (!pf->witness || !pf->evals || !pf->partial || !pf->partial_mask || !pf->encode || !pf->mlwe || !pf->incommit)
         return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: proof buffers missing");
-    if (rd->n_tapes != n_com || !rd->tapes || !rd->blind) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: one tape per commitment and the blinding elements are required");
-    if ((has_lin && (!rd->lin_mask || !rd->lin_mask_sum)) || (has_sum && (!rd->sum_mask || !rd->sum_mask_sum)))
-        return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: mask polynomial missing");
+    if (sampling) {      // RandEncode's blinding elements and the two sumCheckMask polynomials (encoder.go:50-54, prover.go:381-397)
+        b->r_blind.resize(b->wc * L);
+        RS_B(rs_tape_builder_random_elements(b->tb, b->r_blind.data(), b->wc));
+        own.blind = b->r_blind.data();
+        if (has_lin) {
+            b->r_lin_mask.resize(2 * b->N * L);
+            RS_B(rs_tape_builder_sum_check_mask(b->tb, b->N, 2 * b->N, b->r_lin_mask.data(), b->r_lin_sum));
+            own.lin_mask = b->r_lin_mask.data(); own.lin_mask_sum = b->r_lin_sum;
+        }
+        if (has_sum) {
+            b->r_sum_mask.resize(b->sum_max_rank * L);
+            RS_B(rs_tape_builder_sum_check_mask(b->tb, b->N, b->sum_max_rank, b->r_sum_mask.data(), b->r_sum_sum));
+            own.sum_mask = b->r_sum_mask.data(); own.sum_mask_sum = b->r_sum_sum;
+        }
+    } else {
+        if (rd->n_tapes != n_com || !rd->tapes || !rd->blind) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: one tape per commitment and the blinding elements are required");
+        if ((has_lin && (!rd->lin_mask || !rd->lin_mask_sum)) || (has_sum && (!rd->sum_mask || !rd->sum_mask_sum)))
+            return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: mask polynomial missing");
+    }
     double t_phase[16] = {0};
     double t_last = now_ms();
     const double t_start = t_last;
@@ -447,8 +490,9 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
 
     // ---- tapes: the Commits are enqueued without waiting for each other, so their host arrays must be pinned (a copy from
     // pageable memory would make every cudaMemcpyAsync wait for the stream).  Pageable tapes are staged here first.
-    std::vector<rs_jindo_tape> tapes(rd->tapes, rd->tapes + n_com);
-    if (!rd->tapes_pinned) {
+    std::vector<rs_jindo_tape> tapes(n_com);
+    if (!sampling) tapes.assign(rd->tapes, rd->tapes + n_com);
+    if (!sampling && !rd->tapes_pinned) {
         const size_t cs = (size_t)jp.cols * jp.slots, nmd = (size_t)(jp.in_msis + jp.mlwe) * jp.d;
         auto tape_words = [&](const rs_jindo_tape &t) {
             return 2 * cs * L + t.n_mask_rows * jp.slots * L + (t.twin_u ? t.n_twin_u : 0) + t.n_cosac_polys * jp.d +
@@ -503,20 +547,44 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     shake.xof.absorb((const uint8_t *)b->crs.data(), b->crs.size());             // ck.WriteRawTo (jindo/prover.go:222)
     shake.start();
     size_t n_issued = 0, n_bound = 0;
+    const size_t head_cap = (size_t)jp.cols * jp.slots;
+    std::vector<size_t> pending;
     std::vector<int> bind_of(n_com);
     // polyProver.Commit, enqueued only; the commitment lands in pinned memory
     auto commit = [&](size_t idx, rs_batch *bt, size_t poly, size_t len, int bind) -> int {
         if (idx != n_issued) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: commit order");
         views[idx] = View{bt, poly, len};
         bind_of[idx] = bind;
-        RS_B(rs_jindo_commit_async(b->j, bt, poly, len, &tapes[idx], &opens[idx], coms_pin + idx * com_words));
         n_issued++;
+        if (!sampling) return rs_jindo_commit_async(b->j, bt, poly, len, &tapes[idx], &opens[idx], coms_pin + idx * com_words);
+        // genFirstLastRow (jindo/prover.go:65-86) and the first rows' COSAC centres need the head of the vector on the host
+        const size_t head = len < head_cap ? len : head_cap;
+        rs_batch *view = nullptr;
+        RS_B(rs_batch_wrap(b->f, (uint8_t *)rs_batch_device_ptr(bt) + poly * rs_batch_rank(bt) * L * 8, 1, head, &view));
+        const int rc = rs_batch_download_async(view, 0, 1, b->heads + idx * head_cap * L);
+        rs_batch_free(view);
+        pending.push_back(idx);
+        return rc;
+    };
+    // self-sampled mode: sample the pending Commits' tapes on the worker threads and enqueue each Commit as its tape completes
+    auto flush = [&]() -> int {
+        if (pending.empty()) return RS_OK;
+        RS_B(rs_sync());
+        for (size_t i : pending)
+            if (rs_tape_builder_start(b->tb, b->heads + i * head_cap * L, views[i].len, (int)i) != RS_OK)
+                return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: tape builder start failed");
+        for (size_t i : pending) {
+            if (rs_tape_builder_wait(b->tb, (int)i, &tapes[i], nullptr) != RS_OK) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: tape builder failed");
+            RS_B(rs_jindo_commit_async(b->j, views[i].bt, views[i].poly, views[i].len, &tapes[i], &opens[i], coms_pin + i * com_words));
+        }
+        pending.clear();
         return RS_OK;
     };
     // wait for the commitments issued so far, bind them into the fiat-shamir transcript in order (coms[i].WriteRawTo,
     // oracle.Bind) and hand their bytes to the SHAKE worker; `extra` runs right after commitment `extra_after` is bound
     uint8_t el[8 * 32];
     auto bind_ready = [&](long extra_after_a, const uint64_t *sum_a, long extra_after_b, const uint64_t *sum_b) -> int {
+        RS_B(flush());
         RS_B(rs_sync());
         for (; n_bound < n_issued; n_bound++) {
             RS_B(raw_of(n_bound));

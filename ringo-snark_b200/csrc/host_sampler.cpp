@@ -485,7 +485,7 @@ struct rs_tape_builder {
     int T;
     std::vector<Samplers *> smp;                  // one set per worker
     bool deterministic;
-    // pinned buffers, two slots
+    // pinned buffers, n_slots slots (two for the double-buffered Commit loop; one per Commit of a proof for the Buckler prover)
     struct Slot {
         uint64_t *first = nullptr, *last = nullptr, *mask = nullptr;
         int64_t *cosac = nullptr, *mlwe = nullptr;
@@ -494,7 +494,9 @@ struct rs_tape_builder {
         std::chrono::steady_clock::time_point t0;
         double ms = 0;
         std::atomic<int> error{0};
-    } slot[2];
+    };
+    std::deque<Slot> slot;
+    int n_slots = 2;
     ByteSource main_rnd;                          // genFirstLastRow's draws when the workers own their own generators
     std::vector<Staging> staging;
     size_t cap_mask_rows;
@@ -606,11 +608,18 @@ int rs_compute_cdt(double center, double sigma, uint64_t *table, int cap, int64_
 
 int rs_tape_builder_create(const rs_jindo_params *p, const rs_jindo_noise *noise, const uint64_t *q, int L64, int n_threads,
                            const uint8_t *seeds, rs_tape_builder **out) {
-    if (!p || !noise || !q || !out || n_threads < 1 || p->d != 256) return RS_ERR_ARG;
+    return rs_tape_builder_create_slots(p, noise, q, L64, n_threads, 2, seeds, out);
+}
+
+int rs_tape_builder_create_slots(const rs_jindo_params *p, const rs_jindo_noise *noise, const uint64_t *q, int L64, int n_threads,
+                                 int n_slots, const uint8_t *seeds, rs_tape_builder **out) {
+    if (!p || !noise || !q || !out || n_threads < 1 || n_slots < 1 || n_slots > 4096 || p->d != 256) return RS_ERR_ARG;
     if (L64 != 2 && L64 != 4 && L64 != 7 && L64 != 14) return RS_ERR_UNSUPPORTED;
     if (seeds && n_threads != 1) return RS_ERR_ARG;
     rs_tape_builder *b = new rs_tape_builder();
     b->p = *p; b->nz = *noise; b->T = n_threads; b->deterministic = seeds != nullptr;
+    b->n_slots = n_slots;
+    b->slot.resize((size_t)n_slots);
     b->f.L64 = L64; b->f.NL = 2 * L64;
     for (int i = 0; i < L64; i++) { b->f.q[2 * i] = (uint32_t)q[i]; b->f.q[2 * i + 1] = (uint32_t)(q[i] >> 32); }
     uint32_t inv = 1;
@@ -627,7 +636,7 @@ int rs_tape_builder_create(const rs_jindo_params *p, const rs_jindo_noise *noise
     const size_t cs = (size_t)p->cols * p->slots, L = (size_t)L64;
     b->cap_mask_rows = (size_t)p->rows;
     const size_t nm = (size_t)(p->in_msis + p->mlwe);
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < n_slots; k++) {
         auto &s = b->slot[k];
         s.first = (uint64_t *)stage_alloc(cs * L * 8, b->staging);
         s.last = (uint64_t *)stage_alloc(cs * L * 8, b->staging);
@@ -661,16 +670,16 @@ int rs_tape_builder_set_random_bytes(rs_tape_builder *b, const uint8_t *bytes, s
 }
 
 int rs_tape_builder_start(rs_tape_builder *b, const uint64_t *v_host, size_t len, int k) {
-    if (!b || !v_host || k < 0 || k > 1 || len < 1) return RS_ERR_ARG;
+    if (!b || !v_host || k < 0 || k >= b->n_slots || len < 1) return RS_ERR_ARG;
     const rs_jindo_params &p = b->p;
     const size_t cs = (size_t)p.cols * p.slots, L = (size_t)b->f.L64;
     if (len > cs * (size_t)(p.rows - 1)) return RS_ERR_SHAPE;                         // prover.go:47-49
     auto &s = b->slot[k];
     if (s.pending.load() != 0) return RS_ERR_STATE;
     if (b->deterministic) {
-        // one sequential crypto/rand stream shared with worker 0: wait until the other slot's jobs have drained
+        // one sequential crypto/rand stream shared with worker 0: wait until the other slots' jobs have drained
         std::unique_lock<std::mutex> lk(b->mu);
-        b->cv_done.wait(lk, [&] { return b->slot[k ^ 1].pending.load() == 0; });
+        b->cv_done.wait(lk, [&] { for (auto &o : b->slot) if (o.pending.load() != 0) return false; return true; });
     }
     s.t0 = std::chrono::steady_clock::now();
     s.error = 0;
@@ -727,8 +736,33 @@ int rs_tape_builder_start(rs_tape_builder *b, const uint64_t *v_host, size_t len
     return RS_OK;
 }
 
+// MustSetRandom (jindo-modulus element.go, rejection sampling over crypto/rand bytes) for n elements, Montgomery limbs out
+int rs_tape_builder_random_elements(rs_tape_builder *b, uint64_t *out_mont, size_t n) {
+    if (!b || (!out_mont && n)) return RS_ERR_ARG;
+    ByteSource &r0 = b->deterministic ? b->smp[0]->rnd : b->main_rnd;
+    for (size_t i = 0; i < n; i++)
+        if (!set_random(b->f, r0, out_mont + i * (size_t)b->f.L64)) return RS_ERR_ARG;
+    return RS_OK;
+}
+
+// Prover.sumCheckMask (buckler/prover.go:381-397): rank random coefficients, maskSum = the first one, then every further
+// coefficient is random and folded back: mask[i - rank] -= mask[i]
+int rs_tape_builder_sum_check_mask(rs_tape_builder *b, size_t rank, size_t mask_rank, uint64_t *mask_out, uint64_t *mask_sum_out) {
+    if (!b || !mask_out || !mask_sum_out || rank < 1 || mask_rank < rank) return RS_ERR_ARG;
+    const size_t L = (size_t)b->f.L64;
+    int rc = rs_tape_builder_random_elements(b, mask_out, rank);
+    if (rc) return rc;
+    memcpy(mask_sum_out, mask_out, L * 8);
+    for (size_t i = rank; i < mask_rank; i++) {
+        rc = rs_tape_builder_random_elements(b, mask_out + i * L, 1);
+        if (rc) return rc;
+        field_sub(b->f, (uint32_t *)(mask_out + (i - rank) * L), (const uint32_t *)(mask_out + (i - rank) * L), (const uint32_t *)(mask_out + i * L));
+    }
+    return RS_OK;
+}
+
 int rs_tape_builder_wait(rs_tape_builder *b, int k, rs_jindo_tape *tape, double *host_ms) {
-    if (!b || !tape || k < 0 || k > 1) return RS_ERR_ARG;
+    if (!b || !tape || k < 0 || k >= b->n_slots) return RS_ERR_ARG;
     auto &s = b->slot[k];
     {
         std::unique_lock<std::mutex> lk(b->mu);

@@ -171,3 +171,51 @@ def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N, native):
         assert pf_g["EvalProof"][k] == [[list(map(int, l)) for l in poly] for poly in pf_o["EvalProof"][k]], k
     assert pf_g["EvalProof"]["PartialMask"] == [list(map(int, l)) for l in pf_o["EvalProof"]["PartialMask"]]
     assert B.Verifier(C).verify(pw, pf_g)
+
+
+@pytest.mark.parametrize("circuit,name,N", [("mult", "zp128", 256), ("norm", "zp220", 256)])
+def test_self_sampled_prove_verifies(rs, circuit, name, N):
+    """rs_buckler_prove with rand == NULL: every random value is drawn inside the library (host samplers on worker threads +
+    the device TwinCDT / MLWE streams), as the reference's Prove does with crypto/rand.  No trace to compare with, so the
+    check is the reference's own (buckler_test.go:82-99): the restated Verifier accepts, two proofs of the same statement
+    differ, and a proof for a wrong witness is rejected."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_oracle_buckler import circuit_and_witness
+    from oracle import buckler_ref as B, jindo_ref as J
+    from jindo_util import cdt_array, params_dict, polys_array
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    (define, n_pw, n_w), (pw, w) = circuit_and_witness(circuit, q, N, 23)
+    tape = J.Tape(b"buckler-self-" + circuit.encode())
+    C = B.compile_circuit(q, N, define, n_pw, n_w, b"Buckler!", tape)
+    op = B.Prover(C, tape)
+    op.prove(pw, w)                                   # only for the completed witness vectors (decomposition witnesses)
+    ctx = C.ctx
+    terms, coeffs = ctx.terms(ctx.arith_constraints)
+    desc = {"rank": N, "emb_rank": C.emb_rank, "w_cnt": ctx.w_cnt, "pw_cnt": ctx.pw_cnt, "arith_max_rank": ctx.arith_max_rank,
+            "arith_terms": terms, "arith_coeffs": coeffs,
+            "lin": [("ntt" if isinstance(chk, B.NTTChecker) else ("aut", chk.idx_inv, chk.is_ntt), ctx.lin_constraints[id(chk)])
+                    for chk in ctx.lin_checkers]}
+    if ctx.has_sum():
+        desc["sum_terms"], desc["sum_coeffs"] = ctx.terms(ctx.sumcheck_constraints)
+        desc["sum_max_rank"] = ctx.sumcheck_max_rank
+    prv = C.poly_prover
+    p = C.jp
+    gp = rs.jindo.Prover(fg, params_dict(p, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE),
+                         polys_array(prv.ck.Out), cdt_array(prv.ecd), crs=b"Buckler!")
+    gp.SetTwinSeed(os.urandom(32))
+    gp.SetMlweSeed(os.urandom(32), p.mlwe_std)
+    nprv = rs.buckler.NativeProver(fg, q, desc, p, gp)
+    nprv.enable_sampling({"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std,
+                          "mask_mlwe_std": p.mask_mlwe_std}, threads=3)
+    pwm = np.stack([fo.to_mont(v) for v in op.trace["pw_full"]])
+    wm = np.stack([fo.to_mont(v) for v in op.trace["w_full"]])
+    pf1 = nprv.prove(pwm, wm, None)
+    pf2 = nprv.prove(pwm, wm, None)
+    V = B.Verifier(C)
+    assert V.verify(pw, pf1) and V.verify(pw, pf2)
+    assert pf1["Witness"] != pf2["Witness"] and pf1["_eval_point"] != pf2["_eval_point"]
+    bad = wm.copy()
+    bad[0, 3] = fo.to_mont([12345])[0]                # breaks the arithmetic constraint on one coefficient
+    assert not V.verify(pw, nprv.prove(pwm, bad, None))
