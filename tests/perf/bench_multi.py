@@ -1,17 +1,20 @@
-"""[tests/perf: measurement harness that takes its inputs from the oracle, hence under tests/ -- the product never imports oracle/]
+"""[tests/perf: measurement harness that checks a sample of its proofs with the oracle's Verifier, hence under tests/ -- the product never imports oracle/]
 BASELINE configs[4]: Buckler multi-circuit batched proving, whole circuits sharded across the GPUs of one box
 (SURVEY 8e ii: circuits are independent; every Prove is sequential inside through its Fiat-Shamir rounds), with the
-NCCL all-gather of the per-circuit first-round commitments that the host transcripts bind.
+NCCL all-gather of the per-circuit first-round commitments that the host transcripts bind (rs_allgather_u64, C ABI).
 
-    python tests/perf/bench_multi.py [--instances=256] [--logn=13] [--circuit=mult] --trace=oracle_trace/mult13.pkl
+    python tests/perf/bench_multi.py [--instances=256] [--logn=13] [--threads=4] [--verify=2]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tests/perf/bench_multi.py ...
 
-256 MultCircuit instances at N = 2^13 are 256 * 8 * 2^13 = 2^24 witness coefficients.  The oracle
-produces ONE witness / randomness trace (minutes of pure Python per instance), so every instance replays that trace:
-the device work and the host glue per instance are those of distinct instances, the data are not.  Rank r proves the
-instances shard_range(instances, r, world); weak/strong: total work is fixed (strong scaling).  One JSON line on rank 0.
+256 examples/mult MultCircuit instances at N = 2^13 are 256 * 8 * 2^13 = 2^24 witness coefficients.
+Every instance is DISTINCT: its own X (|X| <= 5), Y (63 bit), Z = X * Y in R_q (computed with the library's negacyclic NTT
+before the timed region, like the user of the reference fills the circuit before Prove), and its own randomness -- the compiled
+prover (rs_buckler_prove with rand = NULL) draws it inside the timed region: COSAC rows, mask noise and MustSetRandom
+elements on `threads` host worker threads per rank, TwinCDT / MLWE rows from the device streams.  Rank r proves the
+instances shard_range(instances, r, world); total work is fixed (strong scaling).  `verify` proofs of rank 0 are checked
+by the restated buckler.Verifier after the timed region.  One JSON line on rank 0.
 """
-import json, os, pickle, sys, time
+import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -19,7 +22,6 @@ from conftest import load_product
 import oracle
 from oracle import buckler_ref as B, jindo_ref as J, pyref
 from jindo_util import cdt_array, params_dict
-from test_oracle_buckler import ct_params, BFV_T
 import torch
 import torch.distributed as dist
 
@@ -28,9 +30,9 @@ def opt(name, default):
     return next((a[len(name) + 3:] for a in sys.argv[1:] if a.startswith("--" + name + "=")), default)
 
 
-instances = int(opt("instances", "256")); logn = int(opt("logn", "13")); circuit = opt("circuit", "mult")
-name = {"mult": "zp128", "pk": "zp220", "ct": "zp240"}[circuit]
-trace_path = opt("trace", os.path.join(ROOT, "oracle_trace", f"{circuit}{logn}.pkl"))
+instances = int(opt("instances", "256")); logn = int(opt("logn", "13")); threads = int(opt("threads", "4")); n_verify = int(opt("verify", "2"))
+n_streams = int(opt("streams", "1"))     # concurrent provers per GPU: one host thread + CUDA stream + prover handle each
+circuit, name = "mult", "zp128"
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 if world > 1:
@@ -38,17 +40,8 @@ if world > 1:
 N = 1 << logn
 q = pyref.modulus(name)
 fo = oracle.Field(q)
-if circuit == "ct":                                            # (the witness itself comes from the trace)
-    delta, eb = ct_params(q, N)
-    define, n_pw, n_w = B.ciphertext_circuit(N, delta, BFV_T, eb)
-else:
-    define, n_pw, n_w = {"mult": B.mult_circuit, "pk": B.public_key_circuit}[circuit](N)
+define, n_pw, n_w = B.mult_circuit(N)
 C = B.compile_circuit(q, N, define, n_pw, n_w, b"Buckler!", J.Tape(b"buckler-bench-" + circuit.encode()))
-with open(trace_path, "rb") as fh:
-    saved = pickle.load(fh)
-assert saved["key"] == (logn, circuit, name)
-rand, pwm, wm = saved["packed"]
-pf_o = saved["proof"]
 
 rs = load_product(); L = rs.load()
 rs.check(L.rs_init(local))
@@ -58,10 +51,55 @@ terms, coeffs = ctx.terms(ctx.arith_constraints)
 desc = {"rank": N, "emb_rank": C.emb_rank, "w_cnt": ctx.w_cnt, "pw_cnt": ctx.pw_cnt, "arith_max_rank": ctx.arith_max_rank,
         "arith_terms": terms, "arith_coeffs": coeffs,
         "lin": [("ntt", ctx.lin_constraints[id(chk)]) for chk in ctx.lin_checkers]}
-gp = rs.jindo.Prover(fg, params_dict(C.jp, C.poly_prover.ecd), None, None, None, cdt_array(C.poly_prover.ecd), crs=b"Buckler!", key_from_crs=True)
-gprv = rs.buckler.Prover(fg, q, desc, C.jp, gp)
+p = C.jp
+
+
+def make_prover():
+    """one jindo.Prover + buckler.Prover pair, like Prover.SafeCopy hands every goroutine (jindo/prover.go:327-338)"""
+    gp = rs.jindo.Prover(fg, params_dict(p, C.poly_prover.ecd), None, None, None, cdt_array(C.poly_prover.ecd), crs=b"Buckler!", key_from_crs=True)
+    gp.SetTwinSeed(os.urandom(32)); gp.SetMlweSeed(os.urandom(32), p.mlwe_std)
+    pr = rs.buckler.NativeProver(fg, q, desc, p, gp)
+    pr.enable_sampling({"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std,
+                        "mask_mlwe_std": p.mask_mlwe_std}, threads=threads)
+    return pr
+
+
+provers = [make_prover() for _ in range(n_streams)]
+nprv = provers[0]
 par = rs.parallel
 a, b = par.shard_range(instances, rank, world)
+
+# ---- distinct instances (outside the timed region: the reference's user fills the circuit before calling Prove)
+# witnesses of examples/mult: XCoeffs, ZCoeffs, XNTT, ZNTT + the ternary digits of X (inf-norm bound 5: base [3, 1, 1],
+# prover.go:77-86); public: YNTT.  Small values go to Montgomery form with one device product by R^2.
+DIG = np.array([(0, 0, 0), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 1, 0), (1, 1, 1)], dtype=np.uint64)
+neg = rs.CyclotomicTransformer(fg, N)
+r2 = fo.to_mont([pow(2, 64 * fo.L, q)])[0]
+one_m = fo.to_mont([1])[0]
+
+
+def make_instance(seed):
+    rng = np.random.default_rng(seed)
+    X = rng.integers(0, 6, size=N, dtype=np.uint64)
+    Y = rng.integers(0, 1 << 63, size=N, dtype=np.uint64)
+    raw = np.zeros((5, N, fo.L), dtype=np.uint64)
+    raw[0, :, 0] = X; raw[1, :, 0] = Y
+    for k in range(3):
+        raw[2 + k, :, 0] = DIG[X, k]
+    bt = rs.Batch(fg, 8, N).upload(np.concatenate([raw, np.zeros((3, N, fo.L), dtype=np.uint64)]))
+    u64p = rs.capi.c_u64p
+    rs.check(L.rs_vec_scalar_mul(bt.h, 0, bt.h, 0, r2.ctypes.data_as(u64p), 5))        # canonical small ints -> Montgomery
+    neg.FwdNTTTo(bt, bt, dst_poly=5, src_poly=0, n_polys=2)                            # 5: XNTT, 6: YNTT
+    rs.check(L.rs_vec_mul(bt.h, 7, bt.h, 5, bt.h, 6, 1))                               # 7: ZNTT
+    out = bt.download()
+    zb = rs.Batch(fg, 1, N).upload(out[7:8])
+    neg.InvNTTTo(zb, zb)
+    Z = zb.download()[0]
+    w = np.stack([out[0], Z, out[5], out[7], out[2], out[3], out[4]])                  # X, Z, XNTT, ZNTT, digits
+    return out[6:7].copy(), w
+
+
+inst = [make_instance(1000 + i) for i in range(a, b)]
 
 
 def barrier():
@@ -70,20 +108,43 @@ def barrier():
         dist.barrier()
 
 
-pf = gprv.prove(pwm, wm, rand)                                  # warm-up
-ok = pf["_eval_point"] == pf_o["_eval_point"] and pf["Evals"] == pf_o["Evals"]
+comm = par.NcclComm(rank, world) if world > 1 else None
+for pr in provers:
+    pr.prove_raw(inst[0][0], inst[0][1], None)                 # warm-up (twiddle tables, descriptor caches, pinned arenas)
+streams = [torch.cuda.Stream() for _ in range(n_streams)]
+firsts, proofs = [None] * len(inst), [None] * len(inst)
+
+
+def run(s):
+    """prover s on its own CUDA stream (the library's current stream is per host thread; ctypes drops the GIL during calls)"""
+    rs.check(L.rs_init(local)); rs.check(L.rs_set_stream(streams[s].cuda_stream))
+    for k in range(s, len(inst), n_streams):
+        o = provers[s].prove_raw(inst[k][0], inst[k][1], None, phases=False)
+        firsts[k] = o["Witness"][0].reshape(-1).copy()
+        if k < n_verify:
+            proofs[k] = o
+
+
 barrier()
 t0 = time.perf_counter()
-firsts = []
-split = {}
-for _ in range(a, b):
-    pf = gprv.prove(pwm, wm, rand)
-    firsts.append(np.array(pf["Witness"][0], dtype=np.uint64).reshape(-1))
-    for k, v in gprv.timing.items():
-        split[k] = split.get(k, 0.0) + v
-# the per-circuit commitments every rank's transcript would bind (prover.go:155-157): one all-gather
-allc = par.all_gather_commitments(np.stack(firsts) if firsts else np.zeros((0, 1), dtype=np.uint64), instances, rank, world,
-                                  device=torch.device("cuda", local) if world > 1 else None)
+if n_streams == 1:
+    run(0)
+else:
+    import threading
+    ths = [threading.Thread(target=run, args=(s,)) for s in range(n_streams)]
+    for th in ths: th.start()
+    for th in ths: th.join()
+    rs.check(L.rs_set_stream(None))
+proofs = [o for o in proofs if o is not None]
+# the per-circuit commitments every rank's transcript would bind (prover.go:155-157): one all-gather through the C ABI
+local_c = np.stack(firsts)
+if world > 1:
+    per = max(bb - aa for aa, bb in (par.shard_range(instances, r, world) for r in range(world)))
+    pad = np.zeros((per, local_c.shape[1]), dtype=np.uint64); pad[:len(firsts)] = local_c
+    g = comm.all_gather_u64(pad).reshape(world, per, -1)
+    allc = np.concatenate([g[r, :bb - aa] for r, (aa, bb) in enumerate(par.shard_range(instances, r, world) for r in range(world))])
+else:
+    allc = local_c
 barrier()
 dt = time.perf_counter() - t0
 t = torch.tensor([dt], device="cuda")
@@ -91,17 +152,30 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 dt = float(t[0])
 if rank == 0:
+    # a sample of the proofs through the restated Verifier (pure Python, ~1.5 s each; outside the timed region)
+    V = B.Verifier(C)
+    accepted = []
+    for k, o in enumerate(proofs):
+        pf = {"Witness": o["Witness"].tolist(), "LinCheckMaskSum": nprv.from_mont_arr(o["lin_mask_sum"]), "SumCheckMaskSum": None,
+              "Evals": [nprv.from_mont_arr(e) for e in o["Evals"]],
+              "EvalProof": {kk: o[kk].tolist() for kk in ("Partial", "PartialMask", "InCommit", "Encode", "MLWE")}}
+        pw_ints = [fo.from_mont(inst[k][0][0])]
+        accepted.append(bool(V.verify(pw_ints, pf)))
+    distinct = len({c.tobytes() for c in allc}) == len(allc)
     coeffs_total = instances * (ctx.w_cnt + ctx.pw_cnt) * N
     print(json.dumps({
-        "workload": f"buckler multi-circuit proving: {instances} x {circuit} circuit, N = 2^{logn}, field {name} "
-                    f"({ctx.w_cnt}+{ctx.pw_cnt} witnesses, {len(rand['tapes'])} Jindo commits each) = 2^{np.log2(coeffs_total):.2f} witness coefficients",
+        "workload": f"buckler multi-circuit proving: {instances} distinct {circuit} circuits, N = 2^{logn}, field {name} "
+                    f"({ctx.w_cnt}+{ctx.pw_cnt} witnesses, {ctx.batch()} Jindo commits each) = 2^{np.log2(coeffs_total):.2f} witness coefficients",
         "n_gpus": world, "scaling": "strong", "seconds": dt, "proofs_per_s": instances / dt,
         "witness_mcoeff_per_s": coeffs_total / dt / 1e6, "ms_per_proof_per_gpu": dt * 1e3 / max(1, b - a),
-        "rank0_split_ms_per_proof": {k: v / max(1, b - a) for k, v in split.items()},
-        "gathered_commitments": list(allc.shape), "transcript_digest": par.transcript_digest(allc),
-        "first_proof_matches_oracle": bool(ok),
-        "data": "one oracle witness / randomness trace replayed for every instance (distinct instances would take minutes of pure-Python oracle each)",
-        "note": "wall time incl. the Python rendering of the Go shim (ringo-snark_b200/buckler.py); commit key generated on the device from the CRS",
+        "concurrent_provers_per_gpu": n_streams, "host_sampler_threads_per_prover": threads, "host_cpus": os.cpu_count(),
+        "gathered_commitments": list(allc.shape), "all_commitments_distinct": bool(distinct), "transcript_digest": par.transcript_digest(allc),
+        "verified_sample": accepted,
+        "prover": "rs_buckler_prove (compiled, include/ringo_buckler.h), rand = NULL: randomness drawn inside the timed region",
+        "exchange": "rs_allgather_u64 (NCCL behind the C ABI)" if world > 1 else "none (1 GPU)",
+        "data": "distinct synthetic instances: X uniform in [0,5], Y uniform 63-bit, Z = X*Y in R_q (library NTT), ternary digits of X",
     }))
+if comm is not None:
+    comm.close()
 if world > 1:
     dist.destroy_process_group()
