@@ -94,6 +94,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def bench_config():
+    """The workload both arms are quoted on (identical dict in the product line and the --impl reference line; the reference arm
+    says in cpu_baseline.sample how much of it one of its steps covers)."""
+    nbytes = BATCH * (1 << LOGN) * 32
+    return {"workload": f"bigpoly negacyclic forward NTT, {FIELD} (jindo/internal/zp), rank 2^{LOGN}, "
+                        f"batch {BATCH} polys per GPU (BASELINE configs[1] headline)",
+            "l2": f"input+output {2 * nbytes >> 20} MiB per step, larger than the 126 MB L2 (no flush needed)",
+            "sharding": "independent polynomials per rank, no data-path collective"}
+
+
 def cpu_reference_rate(threads, seconds_target=12.0):
     """The restated reference (oracle C) on a bounded sample of the same workload."""
     import numpy as np
@@ -150,11 +160,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64x4 (255-bit Montgomery)", "data": "synthetic",
-        "config": {"workload": f"bigpoly negacyclic forward NTT, {FIELD}, rank 2^{LOGN}, sample of {n_polys} polys per step "
-                               f"(of the {BATCH}-poly batch)"},
+        "config": bench_config(),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n_polys} polys x 2^{LOGN} per step; C restatement of math/bigpoly/ntt.go "
-                                   f"(Go toolchain unavailable), batch-parallel over {threads} pthreads"},
+                         "sample": f"{n_polys} of the {BATCH} polys x 2^{LOGN} per step (throughput is per coefficient, so the sample "
+                                   f"size does not change it); C restatement of math/bigpoly/ntt.go (Go toolchain unavailable), "
+                                   f"batch-parallel over {threads} pthreads -- the reference itself is single-threaded "
+                                   f"(1 thread: ~1/{threads} of this figure), so the ratio against it is conservative"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "commit": {"metric": "Jindo Commit throughput (one 2^22-coefficient polynomial, 255-bit field, NewParameters(2^22, 1))",
                    "value": commit_cpu["value"], "unit": "polys/s", "cpu_baseline": commit_cpu},
@@ -561,7 +572,7 @@ def run_ours(args):
     hin = torch.from_numpy(host.view(np.int64).reshape(-1)).pin_memory()
     hout = torch.empty_like(hin).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
-    n_chunks, n_streams = 8, 3
+    n_chunks, n_streams = 16, 4        # tools/e2e_probe.py: 8x3 24.5 ms, 16x4 23.5 ms, 64x4 25.1 ms; duplex copies alone 21.6 ms
     cp = BATCH // n_chunks
     cw = cp * N * f.L                      # words per chunk
     streams = [torch.cuda.Stream() for _ in range(n_streams)]
@@ -589,6 +600,18 @@ def run_ours(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_val = world * BATCH * N / (float(t2.item()) * 1e-3) / 1e6
     e2e_ok = bool(np.array_equal(hout.numpy()[:cw], dst_t[:cw].cpu().numpy()))
+    # the leg's own roof: the same bytes as pinned copies in both directions at once, no kernel (PCIe full duplex)
+    def duplex():
+        with torch.cuda.stream(streams[0]):
+            src_t.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(streams[1]):
+            hout.copy_(dst_t, non_blocking=True)
+        streams[0].synchronize(); streams[1].synchronize()
+    duplex()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        duplex()
+    duplex_ms = (time.perf_counter() - t0) * 1e3 / 2
 
     commit = commit_leg(rs, L, f, q, args, world, rank, barrier, dist if world > 1 else None)
 
@@ -596,11 +619,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64x4 (255-bit Montgomery, IMAD.WIDE on 32-bit limbs)", "data": "synthetic",
-        "config": {"workload": f"bigpoly negacyclic forward NTT, {FIELD} (jindo/internal/zp), rank 2^{LOGN}, "
-                               f"batch {BATCH} polys per GPU (BASELINE configs[1] headline)",
-                   "l2": f"input+output {2 * nbytes >> 20} MiB per step, larger than the 126 MB L2 (no flush needed)",
-                   "sharding": "independent polynomials per rank, no data-path collective",
-                   "host_numa": numa},
+        "config": bench_config(), "host_numa": numa,
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the ncu --set full capture
                      # profiles/ntt_r1f_ncu_batch512_summary.csv (tools/profile_ntt.py zp255 16 512, final kernel shape): 1.076 + 1.016 GB
@@ -617,7 +636,11 @@ def run_ours(args):
                                   "(nominal 64 lanes/clk/SM each): the same roof either way"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": float(t2.item()), "pipeline": f"{n_chunks} chunks on {n_streams} streams (pinned host memory)",
-                "result_checked": e2e_ok},
+                "result_checked": e2e_ok,
+                "pcie_roof": {"duplex_copy_ms": duplex_ms, "gbs_each_way": nbytes / duplex_ms / 1e6,
+                              "frac": duplex_ms / e2e_ms,
+                              "note": "the step's 2 x 1 GiB as plain pinned copies in both directions at once on this rank, no kernel: "
+                                      "the host-buffer leg is PCIe bound, a field element is 255 bits in 32 bytes (nothing to compress)"}},
         "ntt_variants": variants,
         "commit": commit,
         "gpu_launches": int(launches),

@@ -8,7 +8,8 @@
 //   ringo::bigpoly::Poly / CyclicTransformer / CyclotomicTransformer   math/bigpoly/poly.go, ntt.go:26-244
 //   ringo::bigpoly::CyclicEvaluator / CyclotomicEvaluator              math/bigpoly/base_op.go:42-207,
 //                                                                      cyclic.go:9-37, cyclotomic.go:14-82
-//   ringo::jindo::Prover                                               jindo/prover.go:28-324
+//   ringo::jindo::Prover                                               jindo/prover.go:28-324, verifier.go:50-282
+//   ringo::buckler::Prover                                             buckler/prover.go:42-353
 //
 // Differences that follow from the boundary: polynomials live in device-resident
 // batches (`Batch`), a `Poly` is a (batch, index, IsNTT) view, scalars are L64-limb Montgomery values on
@@ -24,6 +25,7 @@
 #include <utility>
 #include <vector>
 
+#include "ringo_buckler.h"
 #include "ringo_cuda.h"
 #include "ringo_jindo.h"
 
@@ -307,6 +309,25 @@ class Prover {
     void OpeningMulAddBytes(Opening &acc, const Opening &open, const uint8_t chal16[16]) {   // :230-265
         check(rs_opening_mul_add_bytes(h_, acc.h, open.h, chal16));
     }
+    // the whole batch combination of prover.go:230-265 in one pass
+    Opening CombineBytes(const std::vector<const Opening *> &opens, const uint8_t *chal_bytes) {
+        std::vector<const rs_opening *> hs;
+        for (const Opening *o : opens) hs.push_back(o->h);
+        Opening out;
+        check(rs_opening_combine_bytes(h_, hs.data(), hs.size(), chal_bytes, &out.h));
+        return out;
+    }
+    // Verifier.Verify's arithmetic on the device (verifier.go:50-282): the four check bits, 15 = accepted
+    int Verify(const uint64_t *x_mont, const uint64_t *commitments, int batch, const uint8_t *batch_bytes, const uint8_t *chal_bytes,
+               const uint64_t *ys_mont, const rs_jindo_proof &pf, double in_com_dcmp_two_nm, double res_two_nm) {
+        int checks = 0;
+        check(rs_jindo_verify(h_, x_mont, commitments, batch, batch_bytes, chal_bytes, ys_mont, &pf, in_com_dcmp_two_nm, res_two_nm, &checks));
+        return checks;
+    }
+    // Prover.mlweSampler on the device (prover.go:38, :136-138)
+    void SetMlweStream(const uint8_t key[32], const uint8_t iv[16], const uint64_t *table0, int len, int64_t tail_lo) {
+        check(rs_jindo_set_mlwe_stream(h_, key, iv, table0, len, tail_lo));
+    }
     std::vector<uint64_t> LeftVec(const uint64_t *x_mont) {
         std::vector<uint64_t> out((size_t)p_.rows * p_.n_q * p_.d);
         check(rs_jindo_left_vec(h_, x_mont, out.data()));
@@ -329,6 +350,54 @@ class Prover {
 };
 
 }  // namespace jindo
+
+namespace buckler {
+
+// buckler.Proof (buckler/entities.go) in host vectors
+struct Proof {
+    std::vector<uint64_t> Witness;                    // batch x out_msis polys over ringQOut
+    std::vector<uint64_t> LinCheckMaskSum, SumCheckMaskSum, EvalPoint;   // L64 Montgomery limbs each
+    std::vector<uint64_t> Evals;                      // batch x L64 Montgomery limbs
+    std::vector<uint64_t> Partial, PartialMask, Encode, MLWE, InCommit;  // jindo.Proof
+    double phase_ms[16] = {0};
+};
+
+// buckler.Prover (prover.go:16-40): Prove is one call into the compiled prover (ringo_buckler.h)
+class Prover {
+  public:
+    Prover(const bigpoly::Field &f, jindo::Prover &poly_prover, const rs_buckler_circuit &c, const std::string &crs)
+        : L_(f.Limb()), jp_(poly_prover.Parameters()) {
+        check(rs_buckler_create(f.handle(), poly_prover.handle(), &c, (const uint8_t *)crs.data(), crs.size(), &h_));
+    }
+    ~Prover() { rs_buckler_destroy(h_); }
+    Prover(const Prover &) = delete;
+    Prover &operator=(const Prover &) = delete;
+    size_t Batch() const { return rs_buckler_batch(h_); }
+    // draw all randomness inside the library, as the reference's Prove does (crypto/rand + the device streams)
+    void EnableSampling(const rs_jindo_noise &noise, const uint64_t *q_le, int n_threads) {
+        check(rs_buckler_enable_sampling(h_, &noise, q_le, n_threads));
+    }
+    // Prove (prover.go:42-353).  pw / w: pw_cnt x rank and w_cnt x rank Montgomery elements; rand == nullptr: self-sampled
+    Proof Prove(const uint64_t *pw, const uint64_t *w, const rs_buckler_rand *rand = nullptr, bool phases = false) {
+        Proof pf;
+        const size_t B = Batch(), pq = (size_t)jp_.n_q * jp_.d, pqo = (size_t)jp_.n_qout * jp_.d;
+        pf.Witness.resize(B * jp_.out_msis * pqo); pf.Evals.resize(B * L_);
+        pf.LinCheckMaskSum.resize(L_); pf.SumCheckMaskSum.resize(L_); pf.EvalPoint.resize(L_);
+        pf.Partial.resize((size_t)jp_.cols * pq); pf.PartialMask.resize(pq); pf.Encode.resize((size_t)jp_.rows * pq);
+        pf.MLWE.resize((size_t)(jp_.mlwe + jp_.in_msis) * pq); pf.InCommit.resize((size_t)(jp_.cols + 1) * jp_.in_msis * pqo);
+        rs_buckler_proof out{pf.Witness.data(), pf.LinCheckMaskSum.data(), pf.SumCheckMaskSum.data(), pf.Evals.data(), pf.Partial.data(),
+                             pf.PartialMask.data(), pf.Encode.data(), pf.MLWE.data(), pf.InCommit.data(), pf.EvalPoint.data()};
+        check(rs_buckler_prove(h_, pw, w, rand, &out, phases ? pf.phase_ms : nullptr));
+        return pf;
+    }
+
+  private:
+    int L_;
+    rs_jindo_params jp_;
+    rs_buckler *h_ = nullptr;
+};
+
+}  // namespace buckler
 }  // namespace ringo
 
 #endif  // RINGO_HPP

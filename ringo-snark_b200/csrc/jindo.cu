@@ -1352,10 +1352,14 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         // few column tiles (a column shard of a Commit, a short Commit): cut K so that the grid still covers the chip
         const unsigned ctas = grid.x * grid.y * grid.z;
         int S = 1;
-        if (ctas * 2 <= 148 && !G.accumulate && !G.has_addend && G.out_os == 1 && G.out_cs == G.O && !R.no_split) {
-            S = (int)(148 / ctas);
-            if (S > 16) S = 16;
-            while (S > 1 && G.K / S < 64) S--;
+        if (ctas < 148 && !G.accumulate && !G.has_addend && G.out_os == 1 && G.out_cs == G.O && !R.no_split) {
+            // one 512-thread CTA per SM: the launch lasts ceil(ctas S / 148) waves of K / S steps.  Pick the S with the shortest
+            // launch (80 CTAs: S = 1 and S = 2 both take K steps, S = 3 two waves of K / 3), smaller S on near ties.
+            double best = 1.0;
+            for (int s = 2; s <= 16 && G.K / s >= 64; s++) {
+                const double cost = (double)((ctas * s + 147) / 148) / s;
+                if (cost < best * 0.97) { best = cost; S = s; }
+            }
         }
         u64 *d_parts = nullptr;
         const size_t n_out = (size_t)G.C * G.O * n_slots;

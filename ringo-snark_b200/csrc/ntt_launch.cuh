@@ -1,5 +1,7 @@
 // ntt_launch.cuh -- host-side pass planning + launches for ntt_pass_kernel (see ntt.cuh).
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ntt.cuh"
 
@@ -83,6 +85,25 @@ int ntt_run(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, 
     C.F = make_params<NL>(t->f);
     for (int i = 0; i < NL; i++) { C.ninv[i] = t->ninv[i]; C.ninv_w1[i] = t->ninv_w1[i]; }
 
+    // L2-resident sub-batches (RS_NTT_CHUNK_MB, off by default): a multi-pass transform re-reads what the previous pass wrote;
+    // run over sub-batches whose output fits the 126 MB L2, the later passes hit L2 instead of HBM (one HBM round trip per
+    // coefficient instead of one per pass).  The kernels are integer bound, so this changes DRAM traffic, not time.
+    {
+        static const long chunk_mb = [] { const char *e = getenv("RS_NTT_CHUNK_MB"); return e ? atol(e) : 0L; }();
+        const size_t poly_bytes = ((size_t)NL * 4) << logN;
+        if (chunk_mb > 0 && logN > T::LOG_TS && !g_pass_profile && n_polys * poly_bytes > (size_t)chunk_mb << 20) {
+            size_t per = ((size_t)chunk_mb << 20) / poly_bytes;
+            if (per < 1) per = 1;
+            for (size_t p0 = 0; p0 < n_polys; p0 += per) {
+                const size_t n = n_polys - p0 < per ? n_polys - p0 : per;
+                const size_t off = (p0 << logN) * NL;
+                // (the recursion sees n * poly_bytes <= chunk and runs the passes)
+                const int rc = ntt_run<NL, QS>(t, out + off, in + off, n, inverse);
+                if (rc) return rc;
+            }
+            return RS_OK;
+        }
+    }
     const unsigned long long total = (unsigned long long)n_polys << logN;
     const int KB = logN < T::LOG_TS ? logN : T::LOG_TS;   // stages of the contiguous pass
     const int top = logN - KB;                              // stages left for column passes
