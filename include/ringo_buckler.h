@@ -92,6 +92,14 @@ int rs_buckler_enable_sampling(rs_buckler *b, const rs_jindo_noise *noise, const
 int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const rs_buckler_rand *rand,
                      rs_buckler_proof *proof, double *phase_ms);
 
+/* Verifier.Verify (buckler/verifier.go:29-315) for a proof in the layout rs_buckler_prove writes.  pw: the pw_cnt x rank public
+ * witnesses (Montgomery, the two-norm base / mask rows filled in as Prove's caller fills them); in_com_dcmp_two_nm / res_two_nm:
+ * Parameters.inComDcmpTwoNm / resTwoNm of the Jindo parameters.  Both transcripts are recomputed from the proof; the Jindo evaluation
+ * proof is checked by rs_jindo_verify; Encode(.).Evaluate(x) of the public witnesses and the linear-check vectors runs on the device.
+ * *result: 0 = accepted, otherwise the first failing check (1 polyVerifier.Verify, 2 arithmetic, 3 / 4 linear, 5 / 6 sum check). */
+int rs_buckler_verify(rs_buckler *b, const uint64_t *pw, const rs_buckler_proof *proof, double in_com_dcmp_two_nm, double res_two_nm,
+                      int *result);
+
 /* the two hash functions of the transcripts, exported for the shim's tests (FIPS 180-4 / FIPS 202) */
 void rs_sha256(const uint8_t *data, size_t len, uint8_t out32[32]);
 void rs_shake128(const uint8_t *data, size_t len, uint8_t *out, size_t out_len);

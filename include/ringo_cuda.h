@@ -72,6 +72,10 @@ int rs_field_limbs(const rs_field *f);                        /* Limb() element.
  * identical to SetUint64 / Mul / toMont / fromMont of element.go:94-99, :470-479, :604-653) */
 int rs_field_to_mont(const rs_field *f, uint64_t *out, const uint64_t *canonical_le);
 int rs_field_from_mont(const rs_field *f, uint64_t *out, const uint64_t *mont_le);
+/* Mul / Add / Sub (element.go:470-479, :400-445) on single Montgomery elements; out may alias an input */
+int rs_field_mul(const rs_field *f, uint64_t *out, const uint64_t *a, const uint64_t *b);
+int rs_field_add(const rs_field *f, uint64_t *out, const uint64_t *a, const uint64_t *b);
+int rs_field_sub(const rs_field *f, uint64_t *out, const uint64_t *a, const uint64_t *b);
 /* SetBytes (element.go:891-915): len <= 128 bytes read as a big-endian integer, reduced mod q, Montgomery form out --
  * how buckler turns its 32-byte SHA-256 challenges into field elements (prover.go:248, :273-274, :308, :340);
  * Marshal (element.go:873-883): the canonical value as 8 L64 big-endian bytes (transcript bindings, prover.go:220, :236). */

@@ -425,9 +425,27 @@ class NativeProver:
         pw = np.ascontiguousarray(pw_mont, dtype=np.uint64); w = np.ascontiguousarray(w_mont, dtype=np.uint64)
         check(lib().rs_buckler_prove(self.h, vp(pw) if pw.size else None, vp(w), ctypes.byref(R) if R is not None else None, ctypes.byref(P),
                                      ms if phases else None))
+        self.last_raw = out
         self.timing = dict(zip(("encode_ntt", "commit", "arith_check", "lin_check", "sum_check", "evaluate", "tape_staging", "total", "ev_combine", "ev_partial",
                                 "ev_incommit", "ev_respond", "ev_poly_eval"), ms))
         return out
+
+    def verify_raw(self, pw_mont, o, in_com_dcmp_two_nm=None, res_two_nm=None):
+        """rs_buckler_verify on a proof in prove_raw's layout: 0 = accepted, else the first failing check
+        (1 polyVerifier.Verify, 2 arithmetic, 3 / 4 linear, 5 / 6 sum check)"""
+        P = capi.BucklerProof()
+        vp = lambda a: np.ascontiguousarray(a, dtype=np.uint64).ctypes.data_as(capi.c_vp)
+        keep = {k: np.ascontiguousarray(o[k], dtype=np.uint64) for k in ("Witness", "Evals", "Partial", "PartialMask", "Encode", "MLWE", "InCommit",
+                                                                         "lin_mask_sum", "sum_mask_sum")}
+        P.witness, P.evals, P.partial, P.partial_mask = vp(keep["Witness"]), vp(keep["Evals"]), vp(keep["Partial"]), vp(keep["PartialMask"])
+        P.encode, P.mlwe, P.incommit = vp(keep["Encode"]), vp(keep["MLWE"]), vp(keep["InCommit"])
+        P.lin_mask_sum, P.sum_mask_sum = vp(keep["lin_mask_sum"]), vp(keep["sum_mask_sum"])
+        pw = np.ascontiguousarray(pw_mont, dtype=np.uint64)
+        res = ctypes.c_int(-1)
+        a = self.jp.in_com_dcmp_two_nm if in_com_dcmp_two_nm is None else in_com_dcmp_two_nm
+        b = self.jp.res_two_nm if res_two_nm is None else res_two_nm
+        check(lib().rs_buckler_verify(self.h, vp(pw) if pw.size else None, ctypes.byref(P), float(a), float(b), ctypes.byref(res)))
+        return res.value
 
     def prove(self, pw_mont, w_mont, rand):
         """rand = None: self-sampled (enable_sampling first)"""

@@ -102,6 +102,9 @@ _SIGS = {
     "rs_field_limbs": (ctypes.c_int, [c_vp]),
     "rs_field_to_mont": (ctypes.c_int, [c_vp, c_u64p, c_u64p]),
     "rs_field_from_mont": (ctypes.c_int, [c_vp, c_u64p, c_u64p]),
+    "rs_field_mul": (ctypes.c_int, [c_vp, c_u64p, c_u64p, c_u64p]),
+    "rs_field_add": (ctypes.c_int, [c_vp, c_u64p, c_u64p, c_u64p]),
+    "rs_field_sub": (ctypes.c_int, [c_vp, c_u64p, c_u64p, c_u64p]),
     "rs_batch_alloc": (ctypes.c_int, [c_vp, c_size, c_size, ctypes.POINTER(c_vp)]),
     "rs_batch_wrap": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(c_vp)]),
     "rs_batch_free": (None, [c_vp]),
@@ -186,6 +189,7 @@ _SIGS = {
     "rs_buckler_destroy": (None, [c_vp]),
     "rs_buckler_batch": (c_size, [c_vp]),
     "rs_buckler_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(BucklerRand), ctypes.POINTER(BucklerProof), ctypes.POINTER(ctypes.c_double)]),
+    "rs_buckler_verify": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(BucklerProof), ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_int)]),
     "rs_sha256": (None, [c_vp, c_size, c_vp]),
     "rs_shake128": (None, [c_vp, c_size, c_vp, c_size]),
     # ringo_sampler.h

@@ -314,6 +314,7 @@ struct rs_buckler {
     // self-sampled proofs (rs_buckler_enable_sampling): host samplers on worker threads, one tape slot per Commit
     rs_tape_builder *tb = nullptr;
     uint64_t *heads = nullptr;      // pinned: the first cols*slots coefficients of every committed vector (genFirstLastRow's input)
+    rs_batch *vs = nullptr;         // verifier scratch: Encode(linCheckVec) and one Encode(transposed vec) per checker, rank N
     std::vector<uint64_t> r_blind, r_lin_mask, r_sum_mask;
     uint64_t r_lin_sum[32], r_sum_sum[32];
     uint64_t n_mont[32];            // N as a Montgomery element (nttChecker.TransposeTo's scale)
@@ -343,7 +344,7 @@ void rs_shake128(const uint8_t *data, size_t len, uint8_t *out, size_t out_len) 
 
 void rs_buckler_destroy(rs_buckler *b) {
     if (!b) return;
-    for (rs_batch *x : {b->vals, b->ecd, b->ntt, b->w_ntt, b->pw_ntt, b->work, b->quo, b->lv, b->le, b->qr, b->rem, b->qs, b->rems})
+    for (rs_batch *x : {b->vals, b->ecd, b->ntt, b->w_ntt, b->pw_ntt, b->work, b->quo, b->lv, b->le, b->qr, b->rem, b->qs, b->rems, b->vs})
         if (x) rs_batch_free(x);
     for (rs_ntt *t : {b->enc, b->emb, b->neg})
         if (t) rs_ntt_destroy(t);
@@ -770,6 +771,198 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
         t_phase[7] = now_ms() - t_start;
         memcpy(phase_ms, t_phase, sizeof(t_phase));
     }
+    return RS_OK;
+}
+
+// Verifier.Verify (buckler/verifier.go:29-315).  The transcripts are recomputed from the proof, the Jindo evaluation proof is
+// checked on the device (rs_jindo_verify), Encode(.).Evaluate(x) of the public witnesses and of the linear-check vectors runs
+// on the device (INTT + one batched evaluation), and the closing equations are a few dozen field operations on the host.
+// *result: 0 accepted; 1 polyVerifier.Verify failed, 2 arithmetic check, 3 / 5 remHi != x^k remLo (linear / sum check),
+// 4 linear check, 6 sum check.
+int rs_buckler_verify(rs_buckler *b, const uint64_t *pw, const rs_buckler_proof *pf, double in_com_dcmp_two_nm, double res_two_nm, int *result) {
+    if (!b || !pf || !result || (b->pc && !pw)) return rs::set_error(RS_ERR_ARG, "rs_buckler_verify: null argument");
+    if (!pf->witness || !pf->evals || !pf->partial || !pf->partial_mask || !pf->encode || !pf->mlwe || !pf->incommit)
+        return rs::set_error(RS_ERR_ARG, "rs_buckler_verify: proof buffers missing");
+    const size_t N = b->N, wc = b->wc, pc = b->pc, n_com = b->batch();
+    const int L = b->L;
+    const rs_jindo_params &jp = b->jp;
+    const bool has_arith = !b->arith_terms.empty(), has_lin = !b->lin.empty(), has_sum = !b->sum_terms.empty();
+    if ((has_lin && !pf->lin_mask_sum) || (has_sum && !pf->sum_mask_sum)) return rs::set_error(RS_ERR_ARG, "rs_buckler_verify: mask sum missing");
+    *result = -1;
+    const size_t com_words = (size_t)jp.out_msis * jp.n_qout * jp.d;
+    std::vector<uint8_t> raw;
+    auto raw_of = [&](size_t idx) -> int {
+        const long long n = rs_jindo_commitment_write_raw(b->j, pf->witness + idx * com_words, nullptr, 0);
+        if (n < 0) return (int)n;
+        raw.resize((size_t)n);
+        const long long got = rs_jindo_commitment_write_raw(b->j, pf->witness + idx * com_words, raw.data(), raw.size());
+        return got == n ? RS_OK : (int)(got < 0 ? got : RS_ERR_ARG);
+    };
+    // ---- the fiat-shamir transcript, bound as Prove binds it (verifier.go:70-160), and Evaluate's SHAKE prefix
+    Transcript tr;
+    Shake128 xof;
+    xof.absorb((const uint8_t *)b->crs.data(), b->crs.size());
+    uint8_t el[8 * 32];
+    size_t idx = wc;
+    const size_t lin_mask_idx = idx;
+    if (has_lin) idx++;
+    const size_t sum_mask_idx = idx;
+    if (has_sum) idx++;
+    const size_t first_late = idx;
+    for (size_t i = 0; i < n_com; i++) {
+        RS_B(raw_of(i));
+        xof.absorb(raw.data(), raw.size());
+        const int which = i < wc ? PROJ : (i < first_late ? ARITH_BC : EVAL_PT);
+        tr.bind(which, raw.data(), raw.size());
+        if ((has_lin && i == lin_mask_idx) || (has_sum && i == sum_mask_idx)) {
+            RS_B(rs_field_marshal(b->f, (has_lin && i == lin_mask_idx) ? pf->lin_mask_sum : pf->sum_mask_sum, el));
+            tr.bind(ARITH_BC, el, 8 * L);
+        }
+    }
+    uint64_t arith_bc[32], lin_bc[32], lin_c[32], sum_bc[32], x[32];
+    tr.compute(PROJ);
+    RS_B(rs_field_set_bytes(b->f, tr.compute(ARITH_BC), 32, arith_bc));
+    RS_B(rs_field_set_bytes(b->f, tr.compute(LIN_BC), 32, lin_bc));
+    RS_B(rs_field_set_bytes(b->f, tr.compute(LIN_C), 32, lin_c));
+    RS_B(rs_field_set_bytes(b->f, tr.compute(SUM_BC), 32, sum_bc));
+    RS_B(rs_field_set_bytes(b->f, tr.compute(EVAL_PT), 32, x));
+    // ---- polyVerifier.Verify (jindo/verifier.go:50-282): SHAKE bytes here, arithmetic on the device
+    RS_B(rs_field_marshal(b->f, x, el));
+    xof.absorb(el, 8 * L);
+    std::vector<uint8_t> bb(16 * n_com);
+    if (n_com > 1) {
+        Shake128 fork = xof;
+        fork.squeeze(bb.data(), bb.size());
+        xof.absorb(bb.data(), bb.size());
+    }
+    {
+        const size_t pq = (size_t)jp.n_q * jp.d;
+        const long long n = rs_jindo_poly_write_to(pf->partial, jp.n_q, jp.d, nullptr, 0);
+        if (n < 0) return (int)n;
+        raw.resize((size_t)n);
+        for (int i = 0; i <= jp.cols; i++) {
+            const uint64_t *poly = i < jp.cols ? pf->partial + (size_t)i * pq : pf->partial_mask;
+            if (rs_jindo_poly_write_to(poly, jp.n_q, jp.d, raw.data(), raw.size()) != n) return rs::set_error(RS_ERR_ARG, "rs_buckler_verify: poly_write_to failed");
+            xof.absorb(raw.data(), raw.size());
+        }
+    }
+    std::vector<uint8_t> cs(16 * (size_t)jp.cols);
+    xof.squeeze(cs.data(), cs.size());
+    rs_jindo_proof jpf{pf->partial, pf->partial_mask, pf->encode, pf->mlwe, pf->incommit};
+    int checks = 0;
+    RS_B(rs_jindo_verify(b->j, x, pf->witness, (int)n_com, n_com > 1 ? bb.data() : nullptr, cs.data(), pf->evals, &jpf, in_com_dcmp_two_nm, res_two_nm, &checks));
+    if (checks != 15) { *result = 1; return RS_OK; }
+    // ---- Encode(v).Evaluate(x) for the public witnesses, linCheckVec and its transposes (verifier.go:191-193, :244-262)
+    const size_t n_lin = b->lin.size();
+    if (has_lin && !b->vs) RS_B(rs_batch_alloc(b->f, 1 + n_lin, N, &b->vs));
+    std::vector<const rs_batch *> bs;
+    std::vector<size_t> ps, ls;
+    if (pc) {
+        memcpy(b->pin + wc * N * L, pw, pc * N * L * 8);
+        RS_B(rs_batch_upload(b->vals, wc, pc, b->pin + wc * N * L));
+        RS_B(rs_ntt_inverse(b->enc, b->vals, wc, b->vals, wc, pc));
+        for (size_t k = 0; k < pc; k++) { bs.push_back(b->vals); ps.push_back(wc + k); ls.push_back(N); }
+    }
+    if (has_lin) {
+        RS_B(rs_vec_powers(b->lv, 0, N, lin_c));
+        RS_B(rs_ntt_inverse(b->enc, b->vs, 0, b->lv, 0, 1));
+        bs.push_back(b->vs); ps.push_back(0); ls.push_back(N);
+        for (size_t k = 0; k < n_lin; k++) {
+            const Lin &l = b->lin[k];
+            if (l.kind == 0) {
+                RS_B(rs_reverse_scale(b->lv, 1, b->lv, 0, b->n_mont));
+                RS_B(rs_ntt_inverse(b->neg, b->lv, 1, b->lv, 1, 1));
+            } else {
+                RS_B(rs_aut(b->lv, 1, b->lv, 0, 1, l.idx_inv, l.is_ntt));
+            }
+            RS_B(rs_ntt_inverse(b->enc, b->vs, 1 + k, b->lv, 1, 1));
+            bs.push_back(b->vs); ps.push_back(1 + k); ls.push_back(N);
+        }
+    }
+    std::vector<uint64_t> dev_evals(bs.size() * L + 1);
+    if (!bs.empty()) RS_B(rs_poly_evaluate_many(bs.data(), ps.data(), ls.data(), bs.size(), x, dev_evals.data()));
+    const uint64_t *pw_evals = dev_evals.data();
+    const uint64_t *lin_eval = dev_evals.data() + pc * L, *tr_evals = lin_eval + L;
+    // ---- host scalars
+    rs_field *f = b->f;
+    auto E = [&](size_t i) { return pf->evals + i * L; };
+    uint64_t one[32] = {0}, one_c[32] = {0};
+    one_c[0] = 1;
+    RS_B(rs_field_to_mont(f, one, one_c));
+    auto fpow = [&](uint64_t *out, const uint64_t *base, size_t e) {
+        uint64_t r[32], bsq[32];
+        memcpy(r, one, 8 * L); memcpy(bsq, base, 8 * L);
+        for (; e; e >>= 1) {
+            if (e & 1) rs_field_mul(f, r, r, bsq);
+            rs_field_mul(f, bsq, bsq, bsq);
+        }
+        memcpy(out, r, 8 * L);
+    };
+    auto eq = [&](const uint64_t *a, const uint64_t *c) { return memcmp(a, c, 8 * L) == 0; };
+    uint64_t vanish[32], t0[32], t1[32], ev[32], test[32];
+    fpow(vanish, x, N);
+    rs_field_sub(f, vanish, vanish, one);                              // x^N - 1
+    // evalCircuit at the point (verifier.go:191-215): sum_c bc * sum_terms coeff * pw(x) * prod w(x)
+    auto eval_circuit = [&](uint64_t *out, const uint64_t *bc, const std::vector<rs_term> &terms, const std::vector<uint64_t> &coeffs) {
+        uint64_t acc[32] = {0}, cur[32] = {0}, t[32];
+        int cur_c = terms.empty() ? 0 : terms[0].constraint;
+        auto close = [&]() { rs_field_mul(f, cur, cur, bc); rs_field_add(f, acc, acc, cur); memset(cur, 0, sizeof(cur)); };
+        for (const rs_term &tm : terms) {
+            if (tm.constraint != cur_c) { close(); cur_c = tm.constraint; }
+            memcpy(t, coeffs.data() + (size_t)tm.coeff * L, 8 * L);
+            if (tm.pw >= 0) rs_field_mul(f, t, t, pw_evals + (size_t)tm.pw * L);
+            for (int k = 0; k < tm.n_w; k++) rs_field_mul(f, t, t, E((size_t)tm.w[k]));
+            rs_field_add(f, cur, cur, t);
+        }
+        if (!terms.empty()) close();
+        memcpy(out, acc, 8 * L);
+    };
+    idx = first_late;
+    if (has_arith) {                                                   // verifier.go:217-225
+        eval_circuit(ev, arith_bc, b->arith_terms, b->arith_coeffs);
+        rs_field_mul(f, test, E(idx), vanish);
+        if (!eq(ev, test)) { *result = 2; return RS_OK; }
+        idx++;
+    }
+    uint64_t xk[32];
+    if (has_lin || has_sum) fpow(xk, x, b->jrank - (N - 1));
+    // quo * (x^N - 1) + remLo * x + maskSum, and remHi == x^(rank - (N - 1)) remLo (verifier.go:227-242, :264-293)
+    auto closing = [&](size_t i0, const uint64_t *mask_sum, int fail_hi) -> int {
+        rs_field_mul(f, t0, xk, E(i0 + 1));
+        if (!eq(t0, E(i0 + 2))) return fail_hi;
+        rs_field_mul(f, test, E(i0), vanish);
+        rs_field_mul(f, t0, E(i0 + 1), x);
+        rs_field_add(f, test, test, t0);
+        rs_field_add(f, test, test, mask_sum);
+        return 0;
+    };
+    if (has_lin) {
+        if (int r = closing(idx, pf->lin_mask_sum, 3)) { *result = r; return RS_OK; }
+        memset(ev, 0, sizeof(ev));
+        for (size_t k = 0; k < n_lin; k++) {
+            const Lin &l = b->lin[k];
+            for (size_t j = 0; j < l.pairs.size(); j += 2) {
+                rs_field_mul(f, t0, tr_evals + k * L, E((size_t)l.pairs[j + 1]));      // trEval * wIn(x)
+                rs_field_mul(f, t1, lin_eval, E((size_t)l.pairs[j]));                  // linEval * wOut(x)
+                rs_field_sub(f, t0, t0, t1);
+                rs_field_mul(f, ev, ev, lin_bc);
+                rs_field_add(f, ev, ev, t0);
+            }
+        }
+        rs_field_mul(f, ev, ev, lin_bc);
+        rs_field_add(f, ev, ev, E(lin_mask_idx));
+        if (!eq(ev, test)) { *result = 4; return RS_OK; }
+        idx += 3;
+    }
+    if (has_sum) {
+        if (int r = closing(idx, pf->sum_mask_sum, 5)) { *result = r; return RS_OK; }
+        eval_circuit(ev, sum_bc, b->sum_terms, b->sum_coeffs);
+        rs_field_mul(f, ev, ev, sum_bc);
+        rs_field_add(f, ev, ev, E(sum_mask_idx));
+        if (!eq(ev, test)) { *result = 6; return RS_OK; }
+        idx += 3;
+    }
+    *result = 0;
     return RS_OK;
 }
 

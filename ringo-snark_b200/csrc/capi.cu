@@ -76,6 +76,20 @@ template <int NL> static void host_add_t(const rs_field *f, uint32_t *z, const u
     mod_add<NL>(t, x, y, F);
     memcpy(z, t, 4 * NL);
 }
+template <int NL> static void host_sub_t(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *y) {
+    FieldParams<NL> F = make_params<NL>(f);
+    uint32_t t[NL];
+    mod_sub<NL>(t, x, y, F);
+    memcpy(z, t, 4 * NL);
+}
+void host_sub(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *y) {
+    switch (f->NL) {
+        case 4: host_sub_t<4>(f, z, x, y); break;
+        case 8: host_sub_t<8>(f, z, x, y); break;
+        case 14: host_sub_t<14>(f, z, x, y); break;
+        case 28: host_sub_t<28>(f, z, x, y); break;
+    }
+}
 void host_mul(const rs_field *f, uint32_t *z, const uint32_t *x, const uint32_t *y) {
     switch (f->NL) {
         case 4: host_mul_t<4>(f, z, x, y); break;
@@ -255,6 +269,23 @@ int rs_field_from_mont(const rs_field *f, uint64_t *out, const uint64_t *mont) {
     uint32_t z[RS_MAX_NL], one[RS_MAX_NL] = {1};
     host_mul(f, z, (const uint32_t *)mont, one);
     memcpy(out, z, 4 * f->NL);
+    return RS_OK;
+}
+
+// scalar arithmetic on Montgomery elements (host): what a verifier-side caller needs for a handful of field elements
+int rs_field_mul(const rs_field *f, uint64_t *out, const uint64_t *a, const uint64_t *b) {
+    RS_REQUIRE(f && out && a && b, RS_ERR_ARG, "rs_field_mul: null argument");
+    host_mul(f, (uint32_t *)out, (const uint32_t *)a, (const uint32_t *)b);
+    return RS_OK;
+}
+int rs_field_add(const rs_field *f, uint64_t *out, const uint64_t *a, const uint64_t *b) {
+    RS_REQUIRE(f && out && a && b, RS_ERR_ARG, "rs_field_add: null argument");
+    host_add(f, (uint32_t *)out, (const uint32_t *)a, (const uint32_t *)b);
+    return RS_OK;
+}
+int rs_field_sub(const rs_field *f, uint64_t *out, const uint64_t *a, const uint64_t *b) {
+    RS_REQUIRE(f && out && a && b, RS_ERR_ARG, "rs_field_sub: null argument");
+    host_sub(f, (uint32_t *)out, (const uint32_t *)a, (const uint32_t *)b);
     return RS_OK;
 }
 

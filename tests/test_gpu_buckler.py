@@ -171,6 +171,22 @@ def test_full_prove_bit_exact_and_verifies(rs, circuit, name, N, native):
         assert pf_g["EvalProof"][k] == [[list(map(int, l)) for l in poly] for poly in pf_o["EvalProof"][k]], k
     assert pf_g["EvalProof"]["PartialMask"] == [list(map(int, l)) for l in pf_o["EvalProof"]["PartialMask"]]
     assert B.Verifier(C).verify(pw, pf_g)
+    if native:
+        # the compiled Verifier (rs_buckler_verify) takes the same decisions as the restated one
+        pwm = np.stack([fo.to_mont(v) for v in op.trace["pw_full"]]) if ctx.pw_cnt else np.zeros((0, N, fo.L), dtype=np.uint64)
+        raw = gprv.last_raw
+        assert gprv.verify_raw(pwm, raw) == 0
+        import copy
+        t1 = copy.deepcopy(raw); t1["Evals"][0, 0] ^= np.uint64(1)                 # a wrong evaluation: polyVerifier.Verify rejects
+        assert gprv.verify_raw(pwm, t1) == 1
+        t2 = copy.deepcopy(raw); t2["Encode"][1, 0, 5] = (int(t2["Encode"][1, 0, 5]) + 1) % C.jp.q_primes[0]
+        assert gprv.verify_raw(pwm, t2) == 1
+        if ctx.has_lin():
+            t3 = copy.deepcopy(raw); t3["lin_mask_sum"][0] ^= np.uint64(1)         # re-derives every later challenge
+            assert gprv.verify_raw(pwm, t3) != 0
+        if ctx.pw_cnt:
+            bad_pw = pwm.copy(); bad_pw[0, 2] = fo.to_mont([777])[0]               # a different statement
+            assert gprv.verify_raw(bad_pw, raw) in (2, 4, 6)
 
 
 @pytest.mark.parametrize("circuit,name,N", [("mult", "zp128", 256), ("norm", "zp220", 256)])
@@ -212,10 +228,14 @@ def test_self_sampled_prove_verifies(rs, circuit, name, N):
     pwm = np.stack([fo.to_mont(v) for v in op.trace["pw_full"]])
     wm = np.stack([fo.to_mont(v) for v in op.trace["w_full"]])
     pf1 = nprv.prove(pwm, wm, None)
+    raw1 = nprv.last_raw
     pf2 = nprv.prove(pwm, wm, None)
     V = B.Verifier(C)
     assert V.verify(pw, pf1) and V.verify(pw, pf2)
+    assert nprv.verify_raw(pwm, raw1) == 0 and nprv.verify_raw(pwm, nprv.last_raw) == 0     # the compiled Verifier agrees
     assert pf1["Witness"] != pf2["Witness"] and pf1["_eval_point"] != pf2["_eval_point"]
     bad = wm.copy()
-    bad[0, 3] = fo.to_mont([12345])[0]                # breaks the arithmetic constraint on one coefficient
-    assert not V.verify(pw, nprv.prove(pwm, bad, None))
+    bad[0, 3] = fo.to_mont([12345])[0]                # breaks a constraint on one coefficient
+    pf_bad = nprv.prove(pwm, bad, None)
+    assert not V.verify(pw, pf_bad)
+    assert nprv.verify_raw(pwm, nprv.last_raw) != 0
