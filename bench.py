@@ -452,6 +452,52 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
     return out
 
 
+def buckler_leg(rs, L, args):
+    """BASELINE configs[0]: buckler Prove (and Verify) of examples/mult's MultCircuit at its default rank N = 2^13 over the
+    128-bit field, through the compiled prover (rs_buckler_prove, include/ringo_buckler.h) with every random value drawn inside
+    the timed region (host samplers on worker threads + the device TwinCDT / MLWE streams), as the reference's Prove does.
+    Product side only: circuit description, Jindo parameters and the witness come from the package."""
+    import numpy as np
+    N = 1 << 13
+    q = rs.modulus("zp128")
+    f = rs.Field(q)
+    JH = rs.jindo_host
+    desc, commit_rank, batch = rs.circuits.mult_circuit(q, N)
+    p = JH.new_parameters(q, commit_rank, batch)
+    pdict, cdt = JH.prover_inputs(p)
+    gp = rs.jindo.Prover(f, pdict, None, None, None, np.array(cdt, dtype=np.uint64), crs=b"Buckler!", key_from_crs=True)
+    gp.SetTwinSeed(os.urandom(32)); gp.SetMlweSeed(os.urandom(32), p.mlwe_std)
+    threads = max(1, min((os.cpu_count() or 2) - 1, 15))
+    pr = rs.buckler.NativeProver(f, q, desc, p, gp)
+    pr.enable_sampling({"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std,
+                        "mask_mlwe_std": p.mask_mlwe_std}, threads=threads)
+    insts = [rs.circuits.mult_witness(f, q, N, 77 + k) for k in range(4)]
+    pr.prove_raw(insts[0][0], insts[0][1], None)
+    steps = max(4, min(args.steps, 10))
+    l0 = L.rs_launch_count()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        raw = pr.prove_raw(insts[k % 4][0], insts[k % 4][1], None, phases=False)
+    prove_ms = (time.perf_counter() - t0) * 1e3 / steps
+    launches = (L.rs_launch_count() - l0) // steps
+    res = pr.verify_raw(insts[(steps - 1) % 4][0], raw)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        pr.verify_raw(insts[(steps - 1) % 4][0], raw)
+    verify_ms = (time.perf_counter() - t0) * 1e3 / 3
+    wrong = pr.verify_raw(insts[steps % 4][0], raw)            # the proof against another instance's public witness
+    pr.prove_raw(insts[0][0], insts[0][1], None, phases=True)
+    return {"workload": f"buckler.Prove + Verify, examples/mult MultCircuit, N = 2^13, zp128, {desc['w_cnt']}+{desc['pw_cnt']} witnesses, "
+                        f"{batch} Jindo commits (rows {p.rows}, cols {p.cols}, slots {p.slots}) (BASELINE configs[0])",
+            "prove_ms": prove_ms, "proofs_per_s": 1e3 / prove_ms, "verify_ms": verify_ms, "verifier_accepts": res == 0,
+            "verifier_rejects_other_statement": wrong != 0, "gpu_launches_per_proof": int(launches),
+            "host_sampler_threads": threads,
+            "phases_ms_with_syncs": {k: round(v, 3) for k, v in pr.timing.items() if k != "_"},
+            "randomness": "drawn inside the timed region (rs_buckler_prove with rand = NULL)",
+            "parity": "the same prover with explicit randomness is bit-identical to the restated reference prover "
+                      "(tests/test_gpu_buckler.py; tests/perf/bench_buckler.py at this size: 6.0 ms)"}
+
+
 def bind_to_gpu_numa_node(local):
     """Run this rank's host threads -- and therefore place its pinned staging buffers (first touch) -- on the CPUs of
     the NUMA node the GPU's PCIe root port hangs off.  On an 8-GPU box the e2e leg moves 2 GiB per step per rank
@@ -632,6 +678,8 @@ def run_ours(args):
     duplex_ms = (time.perf_counter() - t0) * 1e3 / 2
 
     commit = commit_leg(rs, L, f, q, args, world, rank, barrier, dist if world > 1 else None)
+    buckler = buckler_leg(rs, L, args) if rank == 0 else None
+    barrier()
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -661,6 +709,7 @@ def run_ours(args):
                                       "the host-buffer leg is PCIe bound, a field element is 255 bits in 32 bytes (nothing to compress)"}},
         "ntt_variants": variants,
         "commit": commit,
+        "buckler": buckler,
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }

@@ -9,6 +9,6 @@ works anywhere, but every compute call needs libringo_b200.so and a B200.
 """
 from . import capi            # noqa: F401
 from .capi import RingoError, lib, load, check  # noqa: F401
-from . import jindo, jindo_host, parallel, buckler  # noqa: F401
+from . import jindo, jindo_host, parallel, buckler, circuits  # noqa: F401
 from .bigpoly import (Field, Batch, Poly, CyclicTransformer, CyclotomicTransformer,  # noqa: F401
                       CyclicEvaluator, CyclotomicEvaluator, MODULI, modulus)

@@ -66,3 +66,23 @@ def test_twin_cdt_slow_path_lower_bound_is_a_lower_bound(product):
                         x += 1
                     assert lb[v0] <= run / norm, (name, k, v0, c)
             assert lb[-1] > 0.9                      # and it is tight enough to settle almost every slow sample
+
+
+def test_mult_circuit_description_matches_the_oracle_compile(product):
+    """ringo-snark_b200/circuits.py carries the compiled form of examples/mult's MultCircuit as plain data (what a Go caller
+    gets from buckler.Compile); it must be what the restated Compile produces."""
+    import oracle
+    from oracle import buckler_ref as B, pyref
+    q = pyref.modulus("zp128")
+    for N in (256, 8192):
+        define, n_pw, n_w = B.mult_circuit(N)
+        ctx = B.Context(q, N, n_pw, n_w)
+        define(ctx, oracle.Field(q))
+        terms, coeffs = ctx.terms(ctx.arith_constraints)
+        d, commit_rank, batch = product.circuits.mult_circuit(q, N)
+        assert d["arith_terms"] == terms and d["arith_coeffs"] == coeffs
+        assert (d["w_cnt"], d["pw_cnt"], d["arith_max_rank"]) == (ctx.w_cnt, ctx.pw_cnt, ctx.arith_max_rank)
+        assert commit_rank == ctx.commit_rank() and batch == ctx.batch()
+        assert d["emb_rank"] == 1 << (max(ctx.arith_max_rank, ctx.sumcheck_max_rank) - 1).bit_length()
+        assert [(k, [tuple(p) for p in pairs]) for k, pairs in d["lin"]] == \
+            [("ntt", [tuple(p) for p in ctx.lin_constraints[id(chk)]]) for chk in ctx.lin_checkers]
