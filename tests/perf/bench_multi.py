@@ -69,34 +69,13 @@ nprv = provers[0]
 par = rs.parallel
 a, b = par.shard_range(instances, rank, world)
 
-# ---- distinct instances (outside the timed region: the reference's user fills the circuit before calling Prove)
-# witnesses of examples/mult: XCoeffs, ZCoeffs, XNTT, ZNTT + the ternary digits of X (inf-norm bound 5: base [3, 1, 1],
-# prover.go:77-86); public: YNTT.  Small values go to Montgomery form with one device product by R^2.
-DIG = np.array([(0, 0, 0), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 1, 0), (1, 1, 1)], dtype=np.uint64)
+# ---- distinct instances (outside the timed region: the reference's user fills the circuit before calling Prove):
+# ringo-snark_b200/circuits.py: X uniform in [0, 5], Y uniform 63-bit, Z = X * Y through the library's negacyclic NTT, ternary digits
 neg = rs.CyclotomicTransformer(fg, N)
-r2 = fo.to_mont([pow(2, 64 * fo.L, q)])[0]
-one_m = fo.to_mont([1])[0]
 
 
 def make_instance(seed):
-    rng = np.random.default_rng(seed)
-    X = rng.integers(0, 6, size=N, dtype=np.uint64)
-    Y = rng.integers(0, 1 << 63, size=N, dtype=np.uint64)
-    raw = np.zeros((5, N, fo.L), dtype=np.uint64)
-    raw[0, :, 0] = X; raw[1, :, 0] = Y
-    for k in range(3):
-        raw[2 + k, :, 0] = DIG[X, k]
-    bt = rs.Batch(fg, 8, N).upload(np.concatenate([raw, np.zeros((3, N, fo.L), dtype=np.uint64)]))
-    u64p = rs.capi.c_u64p
-    rs.check(L.rs_vec_scalar_mul(bt.h, 0, bt.h, 0, r2.ctypes.data_as(u64p), 5))        # canonical small ints -> Montgomery
-    neg.FwdNTTTo(bt, bt, dst_poly=5, src_poly=0, n_polys=2)                            # 5: XNTT, 6: YNTT
-    rs.check(L.rs_vec_mul(bt.h, 7, bt.h, 5, bt.h, 6, 1))                               # 7: ZNTT
-    out = bt.download()
-    zb = rs.Batch(fg, 1, N).upload(out[7:8])
-    neg.InvNTTTo(zb, zb)
-    Z = zb.download()[0]
-    w = np.stack([out[0], Z, out[5], out[7], out[2], out[3], out[4]])                  # X, Z, XNTT, ZNTT, digits
-    return out[6:7].copy(), w
+    return rs.circuits.mult_witness(fg, q, N, seed, transformer=neg)
 
 
 inst = [make_instance(1000 + i) for i in range(a, b)]
@@ -112,7 +91,7 @@ comm = par.NcclComm(rank, world) if world > 1 else None
 for pr in provers:
     pr.prove_raw(inst[0][0], inst[0][1], None)                 # warm-up (twiddle tables, descriptor caches, pinned arenas)
 streams = [torch.cuda.Stream() for _ in range(n_streams)]
-firsts, proofs = [None] * len(inst), [None] * len(inst)
+firsts, proofs, raws = [None] * len(inst), [None] * len(inst), [None] * len(inst)
 
 
 def run(s):
@@ -121,6 +100,7 @@ def run(s):
     for k in range(s, len(inst), n_streams):
         o = provers[s].prove_raw(inst[k][0], inst[k][1], None, phases=False)
         firsts[k] = o["Witness"][0].reshape(-1).copy()
+        raws[k] = o
         if k < n_verify:
             proofs[k] = o
 
@@ -151,6 +131,13 @@ t = torch.tensor([dt], device="cuda")
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 dt = float(t[0])
+# every proof of this rank through the compiled Verifier (rs_buckler_verify), outside the timed region
+tv = time.perf_counter()
+n_ok = sum(1 for k, o in enumerate(raws) if nprv.verify_raw(inst[k][0], o) == 0)
+verify_ms = (time.perf_counter() - tv) * 1e3 / max(1, len(raws))
+tt = torch.tensor([n_ok, len(raws)], device="cuda")
+if world > 1:
+    dist.all_reduce(tt)
 if rank == 0:
     # a sample of the proofs through the restated Verifier (pure Python, ~1.5 s each; outside the timed region)
     V = B.Verifier(C)
@@ -170,7 +157,8 @@ if rank == 0:
         "witness_mcoeff_per_s": coeffs_total / dt / 1e6, "ms_per_proof_per_gpu": dt * 1e3 / max(1, b - a),
         "concurrent_provers_per_gpu": n_streams, "host_sampler_threads_per_prover": threads, "host_cpus": os.cpu_count(),
         "gathered_commitments": list(allc.shape), "all_commitments_distinct": bool(distinct), "transcript_digest": par.transcript_digest(allc),
-        "verified_sample": accepted,
+        "compiled_verifier_accepted": int(tt[0]), "compiled_verifier_checked": int(tt[1]), "verify_ms_per_proof": verify_ms,
+        "restated_verifier_sample": accepted,
         "prover": "rs_buckler_prove (compiled, include/ringo_buckler.h), rand = NULL: randomness drawn inside the timed region",
         "exchange": "rs_allgather_u64 (NCCL behind the C ABI)" if world > 1 else "none (1 GPU)",
         "data": "distinct synthetic instances: X uniform in [0,5], Y uniform 63-bit, Z = X*Y in R_q (library NTT), ternary digits of X",
