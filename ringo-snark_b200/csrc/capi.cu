@@ -61,6 +61,7 @@ int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uin
 int blind(const rs_field *f, uint32_t *polys, const uint32_t *d_blind, size_t n, size_t rank, size_t N);
 int powers(const rs_field *f, uint32_t *out, const uint32_t *c, size_t n);
 int evaluate_many(const rs_field *f, uint32_t *d_results, const void *d_descs, size_t n_polys, const uint32_t *x);
+int twiddles(const rs_field *f, uint32_t *d_tw, uint32_t *d_twinv, const uint32_t *g, const uint32_t *ginv, int logN, int negacyclic);
 enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
 
 // ---- host-side field helpers (setup only) -------------------------------------------------
@@ -422,36 +423,23 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
         memcpy(g, f->one, 4 * n);
         memcpy(ginv, f->one, 4 * n);
     }
-    auto brv = [](size_t i, int bits) { size_t r = 0; for (int k = 0; k < bits; k++) { r = (r << 1) | (i & 1); i >>= 1; } return r; };
-    if (negacyclic) {
-        // tw[brv(i)] = g^i, i < N  (ntt.go:183-192)
-        uint32_t p[RS_MAX_NL], pi[RS_MAX_NL];
-        memcpy(p, f->one, 4 * n); memcpy(pi, f->one, 4 * n);
-        for (size_t i = 0; i < N; i++) {
-            const size_t j = brv(i, logN);
-            memcpy(&t->h_tw[j * n], p, 4 * n);
-            memcpy(&t->h_twinv[j * n], pi, 4 * n);
-            host_mul(f, p, p, g);
-            host_mul(f, pi, pi, ginv);
+    // the tables themselves are generated in HBM (twiddle_kernel: one square-and-multiply per entry instead of the reference's N
+    // sequential products) and read back once: rs_ntt_tables, the N^-1 * tw fold below and the FP64 variant want them on the host
+    const size_t bytes = N * n * 4;
+    {
+        cudaError_t e1 = cudaMalloc((void **)&t->d_tw, bytes), e2 = cudaMalloc((void **)&t->d_twinv, bytes);
+        int rc = (e1 == cudaSuccess && e2 == cudaSuccess) ? RS_OK : set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        if (rc == RS_OK) rc = twiddles(f, t->d_tw, t->d_twinv, g, ginv, logN, negacyclic);
+        if (rc == RS_OK && (cudaMemcpyAsync(t->h_tw.data(), t->d_tw, bytes, cudaMemcpyDeviceToHost, g_stream) != cudaSuccess ||
+                            cudaMemcpyAsync(t->h_twinv.data(), t->d_twinv, bytes, cudaMemcpyDeviceToHost, g_stream) != cudaSuccess ||
+                            cudaStreamSynchronize(g_stream) != cudaSuccess))
+            rc = set_error(RS_ERR_CUDA, "rs_ntt_create: twiddle generation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc != RS_OK) {
+            if (t->d_tw) cudaFree(t->d_tw);
+            if (t->d_twinv) cudaFree(t->d_twinv);
+            delete t;
+            return rc;
         }
-    } else if (N >= 2) {
-        // twRef[brv_{N/2}(i)] = g^i, i < N/2; tw[m+i] = twRef[i], i < m, m = 1,2,..,N/2  (ntt.go:56-84)
-        const size_t H = N / 2;
-        std::vector<uint32_t> ref(H * n), refi(H * n);
-        uint32_t p[RS_MAX_NL], pi[RS_MAX_NL];
-        memcpy(p, f->one, 4 * n); memcpy(pi, f->one, 4 * n);
-        for (size_t i = 0; i < H; i++) {
-            const size_t j = brv(i, logN - 1);
-            memcpy(&ref[j * n], p, 4 * n);
-            memcpy(&refi[j * n], pi, 4 * n);
-            host_mul(f, p, p, g);
-            host_mul(f, pi, pi, ginv);
-        }
-        for (size_t m = 1; m <= H; m <<= 1)
-            for (size_t i = 0; i < m; i++) {
-                memcpy(&t->h_tw[(m + i) * n], &ref[i * n], 4 * n);
-                memcpy(&t->h_twinv[(m + i) * n], &refi[i * n], 4 * n);
-            }
     }
     uint32_t nm[RS_MAX_NL];
     host_set_u64(f, nm, (uint64_t)N);
@@ -486,9 +474,8 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
         memcpy(t->c52.qw, f->q, 32);
         t->has52 = 1;
     }
-    const size_t bytes = N * n * 4;
-    cudaError_t e1 = cudaMalloc((void **)&t->d_tw, bytes), e2 = cudaMalloc((void **)&t->d_twinv, bytes);
-    if (e1 == cudaSuccess && e2 == cudaSuccess && t->has52) {
+    cudaError_t e1 = cudaSuccess, e2 = cudaSuccess;
+    if (t->has52) {
         e1 = cudaMalloc((void **)&t->d_tw52, tw52.size() * 8);
         e2 = cudaMalloc((void **)&t->d_twinv52, twinv52.size() * 8);
         if (e1 == cudaSuccess) e1 = cudaMemcpy(t->d_tw52, tw52.data(), tw52.size() * 8, cudaMemcpyHostToDevice);
@@ -502,8 +489,6 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
         delete t;
         return set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     }
-    cudaMemcpy(t->d_tw, t->h_tw.data(), bytes, cudaMemcpyHostToDevice);
-    cudaMemcpy(t->d_twinv, t->h_twinv.data(), bytes, cudaMemcpyHostToDevice);
     *out = t;
     return RS_OK;
 }

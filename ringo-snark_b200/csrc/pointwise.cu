@@ -466,6 +466,40 @@ __device__ __forceinline__ void pow_small(uint32_t *r, const uint32_t *base, siz
     }
 }
 
+// ---------------------------------------------------------------------------
+// Twiddle tables of NewCyclicTransformer / NewCyclotomicTransformer (math/bigpoly/ntt.go:56-84, :183-192) generated in HBM:
+// the reference fills them with N sequential products; entry k is a fixed power of the generator, so thread k computes it by
+// square-and-multiply (exact field arithmetic: the same canonical elements, compared limb for limb with the oracle's tables).
+//   negacyclic: tw[brv_logN(i)] = g^i                         cyclic: tw[m + i] = g^(brv_(logN-1)(i)), i < m, m = 1, 2, .., N/2
+// ---------------------------------------------------------------------------
+template <int NL, int QS>
+__global__ void __launch_bounds__(128) twiddle_kernel(uint32_t *tw, uint32_t *twinv, const __grid_constant__ Scalar<NL> g,
+                                                      const __grid_constant__ Scalar<NL> ginv, const __grid_constant__ FieldParams<NL> F,
+                                                      int logN, int negacyclic) {
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t N = (size_t)1 << logN;
+    if (k >= N) return;
+    uint32_t r[NL];
+    size_t e;
+    if (negacyclic) {
+        e = (size_t)(__brevll((unsigned long long)k) >> (64 - logN));            // k = brv(i)  <=>  i = brv(k)
+    } else {
+        if (k == 0) {                                                            // tw[0] is never read: the reference leaves it zero
+#pragma unroll
+            for (int l = 0; l < NL; l++) r[l] = 0;
+            st_elem<NL>(tw, r); st_elem<NL>(twinv, r);
+            return;
+        }
+        const int mb = 63 - __clzll((unsigned long long)k);                      // m = 2^mb <= k
+        const size_t i = k - ((size_t)1 << mb);
+        e = logN > 1 ? (size_t)(__brevll((unsigned long long)i) >> (64 - (logN - 1))) : 0;
+    }
+    pow_small<NL, QS>(r, g.v, e, F);
+    st_elem<NL>(tw + k * NL, r);
+    pow_small<NL, QS>(r, ginv.v, e, F);
+    st_elem<NL>(twinv + k * NL, r);
+}
+
 template <int NL, int QS>
 __global__ void __launch_bounds__(256) evaluate_many_kernel(uint32_t *results, const EvalDesc *descs, const __grid_constant__ Scalar<NL> x,
                                                             const __grid_constant__ FieldParams<NL> F) {
@@ -505,6 +539,22 @@ __global__ void __launch_bounds__(256) evaluate_many_kernel(uint32_t *results, c
         __syncthreads();
     }
     if (t < NL) results[(size_t)blockIdx.x * NL + t] = sh[t];
+}
+
+int twiddles(const rs_field *f, uint32_t *d_tw, uint32_t *d_twinv, const uint32_t *g, const uint32_t *ginv, int logN, int negacyclic) {
+    const size_t N = (size_t)1 << logN;
+#define CALL(NL, QS)                                                                                          \
+    {                                                                                                         \
+        FieldParams<NL> F = make_params<NL>(f);                                                               \
+        Scalar<NL> sg, si;                                                                                    \
+        for (int i = 0; i < NL; i++) { sg.v[i] = g[i]; si.v[i] = ginv[i]; }                                   \
+        twiddle_kernel<NL, QS><<<(unsigned)((N + 127) / 128), 128, 0, current_stream()>>>(d_tw, d_twinv, sg, si, F, logN, negacyclic); \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
 }
 
 int evaluate_many(const rs_field *f, uint32_t *d_results, const void *d_descs, size_t n_polys, const uint32_t *x) {
