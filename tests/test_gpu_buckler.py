@@ -239,3 +239,66 @@ def test_self_sampled_prove_verifies(rs, circuit, name, N):
     pf_bad = nprv.prove(pwm, bad, None)
     assert not V.verify(pw, pf_bad)
     assert nprv.verify_raw(pwm, nprv.last_raw) != 0
+
+
+def test_compiled_prove_at_the_example_size_from_the_cached_trace(rs):
+    """examples/mult at its default rank N = 2^13 (BASELINE configs[0]): the compiled prover's proof against the oracle's proof
+    cached in oracle_trace/mult13.pkl (written once by tests/perf/bench_buckler.py --trace: 93 s of pure-Python oracle, so the
+    test only runs where the cache exists), every polynomial bit for bit, and the compiled Verifier accepts it."""
+    import os, pickle, sys
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle_trace", "mult13.pkl")
+    if not os.path.exists(path):
+        pytest.skip("oracle_trace/mult13.pkl not present (python tests/perf/bench_buckler.py 13 mult --trace=oracle_trace/mult13.pkl --oracle-only)")
+    sys.path.insert(0, os.path.dirname(__file__))
+    from oracle import buckler_ref as B, jindo_ref as J
+    from jindo_util import cdt_array, params_dict
+    with open(path, "rb") as fh:
+        saved = pickle.load(fh)
+    assert saved["key"] == (13, "mult", "zp128")
+    rand, pwm, wm = saved["packed"]
+    pf_o = saved["proof"]
+    N = 1 << 13
+    q = pyref.modulus("zp128")
+    fg = rs.Field(q)
+    desc, commit_rank, batch = rs.circuits.mult_circuit(q, N)                      # product-side compiled form of the circuit
+    p = J.new_parameters(q, commit_rank, batch)
+    ecd = J.Encoder(p, J.Tape(b"unused"))
+    gp = rs.jindo.Prover(fg, params_dict(p, ecd), None, None, None, cdt_array(ecd), crs=b"Buckler!", key_from_crs=True)
+    nprv = rs.buckler.NativeProver(fg, q, desc, p, gp)
+    pf = nprv.prove(pwm, wm, rand)
+    assert pf["_eval_point"] == pf_o["_eval_point"] and pf["Evals"] == pf_o["Evals"] and pf["LinCheckMaskSum"] == pf_o["LinCheckMaskSum"]
+    assert pf["Witness"] == [[[list(map(int, l)) for l in poly] for poly in cm] for cm in pf_o["Witness"]]
+    for k in ("Partial", "Encode", "MLWE", "InCommit"):
+        assert pf["EvalProof"][k] == [[list(map(int, l)) for l in poly] for poly in pf_o["EvalProof"][k]], k
+    assert pf["EvalProof"]["PartialMask"] == [list(map(int, l)) for l in pf_o["EvalProof"]["PartialMask"]]
+    assert nprv.verify_raw(pwm, nprv.last_raw) == 0
+    assert nprv.timing["total"] < 500.0                                             # milliseconds, with the phase synchronisations (6-8 ms on a B200)
+
+
+def test_compiled_prover_reproduces_the_committed_digest(rs):
+    """tests/golden/buckler_proof_digests.json holds SHA-256 of the restated prover's proof of the seeded MultCircuit statement
+    (written by tests/golden/make_buckler_digests.py, checked on the CPU by test_oracle_buckler.py).  The compiled GPU prover, fed
+    the same witness and randomness, must produce a proof with that digest."""
+    import json, os, sys
+    sys.path.insert(0, os.path.dirname(__file__)); sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_buckler_digests import proof_digest
+    from test_oracle_buckler import circuit_and_witness
+    from oracle import buckler_ref as B, jindo_ref as J
+    from jindo_util import cdt_array, params_dict, polys_array, tape_arrays
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "buckler_proof_digests.json")))["mult"]
+    q = pyref.modulus(want["field"]); N = want["rank"]
+    fo = oracle.Field(q); fg = rs.Field(q)
+    (define, n_pw, n_w), (pw, w) = circuit_and_witness("mult", q, N, want["witness_seed"])
+    tape = J.Tape(want["tape_seed"].encode())
+    C = B.compile_circuit(q, N, define, n_pw, n_w, want["crs"].encode(), tape)
+    op = B.Prover(C, tape)
+    op.prove(pw, w)                                   # for the randomness trace
+    desc, commit_rank, batch = rs.circuits.mult_circuit(q, N)
+    prv = C.poly_prover
+    gp = rs.jindo.Prover(fg, params_dict(C.jp, prv.ecd), polys_array(prv.ck.In), polys_array(prv.ck.MLWE), polys_array(prv.ck.Out),
+                         cdt_array(prv.ecd), crs=want["crs"].encode())
+    rand = {"blind": op.trace["blind"], "mask": op.trace["mask"], "mask_sum": op.trace["mask_sum"],
+            "tapes": [tape_arrays(fo, C.jp, t) for t in op.trace["commit_traces"]]}
+    nprv = rs.buckler.NativeProver(fg, q, desc, C.jp, gp)
+    pf = nprv.prove(np.stack([fo.to_mont(v) for v in op.trace["pw_full"]]), np.stack([fo.to_mont(v) for v in op.trace["w_full"]]), rand)
+    assert proof_digest(pf, fo.L) == want["sha256"]

@@ -130,6 +130,15 @@ def test_prove_verify(circuit, name, N):
     pf = B.Prover(C, tape).prove(pw, w)
     assert len(pf["Witness"]) == C.ctx.batch() == len(pf["Evals"])
     assert B.Verifier(C).verify(pw, pf)
+    # the committed digest of exactly this proof (tests/golden/make_buckler_digests.py): the restatement, its samplers and its
+    # transcripts have not drifted since the fixture was written
+    import json, os, sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gdir)
+    from make_buckler_digests import proof_digest
+    want = json.load(open(os.path.join(gdir, "buckler_proof_digests.json")))[circuit]
+    assert (want["field"], want["rank"], want["commitments"]) == (name, N, len(pf["Witness"]))
+    assert proof_digest(pf, (q.bit_length() + 63) // 64) == want["sha256"]
     if circuit == "ct":                              # (43 commits per proof: the negative cases run on the two smaller circuits)
         return
     if circuit == "norm":
