@@ -92,6 +92,21 @@ int rs_jindo_set_mlwe_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *i
 /* the next n samples of that sampler (tests) */
 int rs_jindo_mlwe_stream_sample(rs_jindo *j, size_t n, int64_t *out);
 
+/* GPU-resident COSAC sampler of the encoder (Encoder.cosac, jindo/encoder.go:72-74, :166-171; math/csprng/gaussian_cosac.go): the
+ * rows the reference samples with data-dependent rejection loops -- row 0 of every data column (ecdBlindStdDev) and every row of the
+ * mask column (maskBlindStdDev / maskStdDev).  One sampler object is sequential, so the device uses the reference's own model of
+ * parallelism, one fresh sampler per worker (Prover.SafeCopy, prover.go:327-338): worker w = (running count of COSAC coefficients
+ * sampled so far) owns COSACSampler{baseSampler: AES-256-CTR(key_b, IV_b + (w << 16)), roundedSampler: {AES-256-CTR(key_r, IV_r +
+ * (w << 16))}}, key || iv = the 48 bytes given here (SHA-384 of a seed, hashed by the caller like rs_jindo_set_twin_stream's).
+ * Every Commit whose tape has cosac_g == NULL draws its COSAC polynomials from it, digits and float64 centres computed on the
+ * device in the reference's order.  rs_jindo_cosac_sample (tests) returns what a Commit with this first row / these mask rows
+ * draws (n_polys = cols + n_mask_rows polynomials of 256 samples), the index of its first worker, and whether a worker ran out
+ * of its first 8 KiB of keystream (1024 draws; a sample takes about five). */
+int rs_jindo_set_cosac_stream(rs_jindo *j, const uint8_t *key48_base, const uint8_t *key48_rounded, double ecd_blind_std,
+                              double mask_blind_std, double mask_std);
+int rs_jindo_cosac_sample(rs_jindo *j, const uint64_t *first_row, const uint64_t *mask_rows, size_t n_mask_rows, int64_t *out,
+                          uint64_t *worker0, int *overflowed);
+
 /* Randomness / noise inputs of one Commit, in the reference's consumption order. */
 typedef struct rs_jindo_tape {
     const uint64_t *first_row;   /* cols*slots field elements (Montgomery)       prover.go:65-86 */
@@ -102,7 +117,8 @@ typedef struct rs_jindo_tape {
                                     NULL: drawn on the device from the stream set by rs_jindo_set_twin_stream */
     size_t n_twin_u;
     const int64_t *cosac_g;      /* sampled g for the COSAC rows: data columns' row 0 (col order), then
-                                    the mask column's rows in encode order; d values each */
+                                    the mask column's rows in encode order; d values each;
+                                    NULL: sampled on the device from the stream set by rs_jindo_set_cosac_stream */
     size_t n_cosac_polys;
     const int64_t *mlwe;         /* (cols+1)*(in_msis+mlwe)*d noise samples          prover.go:130-139;
                                     with mlwe_mask_only: just the mask column's (in_msis+mlwe)*d samples */

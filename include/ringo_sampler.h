@@ -77,6 +77,9 @@ int rs_tape_builder_create(const rs_jindo_params *p, const rs_jindo_noise *noise
 int rs_tape_builder_create_slots(const rs_jindo_params *p, const rs_jindo_noise *noise, const uint64_t *q, int L64,
                                  int n_threads, int n_slots, const uint8_t *seeds, rs_tape_builder **out);
 void rs_tape_builder_destroy(rs_tape_builder *b);
+/* on != 0: the tapes carry cosac_g = NULL -- the COSAC rows are sampled on the device from the Jindo prover's own stream
+ * (rs_jindo_set_cosac_stream); the builder still draws the first / last / mask row elements and the mask column's MLWE noise */
+int rs_tape_builder_set_device_cosac(rs_tape_builder *b, int on);
 /* n MustSetRandom field elements (rejection sampling over the builder's crypto/rand stand-in), Montgomery limbs */
 int rs_tape_builder_random_elements(rs_tape_builder *b, uint64_t *out_mont, size_t n);
 /* Prover.sumCheckMask (buckler/prover.go:381-397): mask_rank coefficients and maskSum */

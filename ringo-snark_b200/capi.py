@@ -153,6 +153,8 @@ _SIGS = {
     "rs_jindo_set_twin_stream": (ctypes.c_int, [c_vp, c_vp, c_vp]),
     "rs_jindo_twin_stream_draw": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_set_mlwe_stream": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int64]),
+    "rs_jindo_set_cosac_stream": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    "rs_jindo_cosac_sample": (ctypes.c_int, [c_vp, c_vp, c_vp, c_size, c_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int)]),
     "rs_jindo_mlwe_stream_sample": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_commit": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
     "rs_jindo_commit_async": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
@@ -212,6 +214,7 @@ _SIGS = {
                                               c_vp, ctypes.POINTER(c_vp)]),
     "rs_tape_builder_create_slots": (ctypes.c_int, [ctypes.POINTER(JindoParams), ctypes.POINTER(JindoNoise), c_u64p, ctypes.c_int, ctypes.c_int,
                                                     ctypes.c_int, c_vp, ctypes.POINTER(c_vp)]),
+    "rs_tape_builder_set_device_cosac": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "rs_tape_builder_random_elements": (ctypes.c_int, [c_vp, c_vp, c_size]),
     "rs_tape_builder_sum_check_mask": (ctypes.c_int, [c_vp, c_size, c_size, c_vp, c_vp]),
     "rs_tape_builder_destroy": (None, [c_vp]),

@@ -129,6 +129,14 @@ static void aes256_expand(const uint8_t key[32], AesKey &K) {
     }
 }
 
+// shared with cosac_dev.cu
+void aes256_expand_key(const uint8_t key[32], uint32_t rk[60]) {
+    AesKey K;
+    aes256_expand(key, K);
+    memcpy(rk, K.rk, sizeof(K.rk));
+}
+const uint8_t *aes_sbox_host() { return h_sbox; }
+
 struct UniformStream {
     AesKey key;
     u64 iv_hi, iv_lo;

@@ -474,6 +474,12 @@ struct Samplers {
 
 }  // namespace
 
+// the ziggurat tables of gaussian_rounded.go's package init, for the device sampler (cosac_dev.cu)
+extern "C" void rs_zig_tables(uint64_t *kn, double *wn, double *fn) {
+    const Zig &Z = zig();
+    memcpy(kn, Z.kn, sizeof(Z.kn)); memcpy(wn, Z.wn, sizeof(Z.wn)); memcpy(fn, Z.fn, sizeof(Z.fn));
+}
+
 struct rs_uniform { Uniform u; };
 struct rs_rounded { Rounded r; };
 struct rs_cosac { Cosac c; };
@@ -497,6 +503,7 @@ struct rs_tape_builder {
     };
     std::deque<Slot> slot;
     int n_slots = 2;
+    bool device_cosac = false;                    // the COSAC samples are drawn on the device (rs_jindo_set_cosac_stream): skip them here
     ByteSource main_rnd;                          // genFirstLastRow's draws when the workers own their own generators
     std::vector<Staging> staging;
     size_t cap_mask_rows;
@@ -663,6 +670,12 @@ void rs_tape_builder_destroy(rs_tape_builder *b) {
     delete b;
 }
 
+int rs_tape_builder_set_device_cosac(rs_tape_builder *b, int on) {
+    if (!b) return RS_ERR_ARG;
+    b->device_cosac = on != 0;
+    return RS_OK;
+}
+
 int rs_tape_builder_set_random_bytes(rs_tape_builder *b, const uint8_t *bytes, size_t n) {
     if (!b || b->T != 1) return RS_ERR_ARG;
     b->smp[0]->rnd.fixed = bytes; b->smp[0]->rnd.fixed_n = n; b->smp[0]->rnd.fixed_pos = 0;
@@ -710,13 +723,13 @@ int rs_tape_builder_start(rs_tape_builder *b, const uint64_t *v_host, size_t len
             Samplers &S = *b->smp[w];
             for (size_t t = a; t < e && !s.error.load(); t++) {
                 if (t < (size_t)p.cols) {
-                    cosac_poly(b, S.cosac, s.first + t * p.slots * L, p.slots, b->nz.ecd_blind_std, s.cosac + t * 256);
+                    if (!b->device_cosac) cosac_poly(b, S.cosac, s.first + t * p.slots * L, p.slots, b->nz.ecd_blind_std, s.cosac + t * 256);
                 } else {
                     const size_t r = t - p.cols;
                     uint64_t *row = s.mask + r * p.slots * L;
                     for (int i = 0; i < p.slots; i++)
                         if (!set_random(b->f, S.rnd, row + (size_t)i * L)) { s.error = RS_ERR_ARG; break; }
-                    cosac_poly(b, S.cosac, row, p.slots, r == 0 ? b->nz.mask_blind_std : b->nz.mask_std, s.cosac + t * 256);
+                    if (!b->device_cosac) cosac_poly(b, S.cosac, row, p.slots, r == 0 ? b->nz.mask_blind_std : b->nz.mask_std, s.cosac + t * 256);
                 }
             }
             finish_one(b, s);
@@ -772,7 +785,7 @@ int rs_tape_builder_wait(rs_tape_builder *b, int k, rs_jindo_tape *tape, double 
     memset(tape, 0, sizeof(*tape));
     tape->first_row = s.first; tape->last_row = s.last; tape->mask_rows = s.mask; tape->n_mask_rows = s.n_mask_rows;
     tape->twin_u = nullptr; tape->n_twin_u = 0;
-    tape->cosac_g = s.cosac; tape->n_cosac_polys = s.n_cosac;
+    tape->cosac_g = b->device_cosac ? nullptr : s.cosac; tape->n_cosac_polys = s.n_cosac;
     tape->mlwe = s.mlwe; tape->mlwe_mask_only = 1;
     tape->on_device = 0;
     if (host_ms) *host_ms = s.ms;

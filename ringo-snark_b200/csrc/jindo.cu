@@ -79,6 +79,16 @@ void uniform_stream_release(UniformStream *s);
 int uniform_stream_prefetch(UniformStream *s, size_t n);
 }  // namespace rs
 
+namespace rs {
+struct CosacStream;
+int cosac_stream_init(CosacStream **out, const uint8_t kb[48], const uint8_t kr[48], double std_first, double std_mask0, double std_mask);
+void cosac_stream_free(CosacStream *s);
+u64 cosac_stream_workers(const CosacStream *s);
+const int *cosac_stream_overflow_flag(const CosacStream *s);
+int cosac_generate(CosacStream *s, const rs_field *f, const rs_jindo_params &p, const uint32_t *d_first_row, const uint32_t *d_mask_rows,
+                   size_t n_polys, long long *d_out);
+}  // namespace rs
+
 struct rs_jindo {
     std::vector<DescCache> *cache;
     rs::EncDesc *d_ndescs;    // descriptors of the MLWE noise polynomials
@@ -96,6 +106,7 @@ struct rs_jindo {
     u64 base_mont_q[JMAXL]; // base * 2^64 mod q_l
     rs::UniformStream *twin_stream;   // GPU-resident uniform source of the encoder's TwinCDT sampler (aes_ctr.cu)
     rs::UniformStream *mlwe_stream;   // same for Prover.mlweSampler (centre 0: table 0 only)
+    rs::CosacStream *cosac_stream;    // GPU-resident COSAC sampler of the encoder (cosac_dev.cu)
     u64 *d_mlwe_cdt; int mlwe_cdt_len; long long mlwe_tail_lo;
     int no_pair, prefetch;            // RS_JINDO_NOPAIR / RS_JINDO_PREFETCH, read when the handle is created
     cudaStream_t copy_stream;         // rs_jindo_commit_host: uploads of v pieces
@@ -1833,6 +1844,7 @@ void rs_jindo_destroy(rs_jindo *j) {
     if (j->cache) { for (auto &c : *j->cache) cudaFree(c.d_descs); delete j->cache; }
     cudaFree(j->d_ndescs); cudaFree(j->d_ldescs); cudaFree(j->d_zero_g);
     rs::uniform_stream_free(j->twin_stream);
+    rs::cosac_stream_free(j->cosac_stream);
     rs::uniform_stream_free(j->mlwe_stream);
     cudaFree(j->d_mlwe_cdt);
     delete j;
@@ -1898,6 +1910,41 @@ int rs_jindo_set_mlwe_stream(rs_jindo *j, const uint8_t *key32, const uint8_t *i
     RS_CUDA_CHECK(cudaMemcpy(j->d_mlwe_cdt, table0, (size_t)len * 8, cudaMemcpyHostToDevice));
     j->mlwe_cdt_len = len; j->mlwe_tail_lo = tail_lo;
     return rs::uniform_stream_init(&j->mlwe_stream, key32, iv16);
+}
+
+int rs_jindo_set_cosac_stream(rs_jindo *j, const uint8_t *key48_base, const uint8_t *key48_rounded, double ecd_blind_std, double mask_blind_std,
+                              double mask_std) {
+    RS_REQUIRE(j && key48_base && key48_rounded, RS_ERR_ARG, "rs_jindo_set_cosac_stream: null argument");
+    RS_REQUIRE(ecd_blind_std > 0 && mask_blind_std > 0 && mask_std > 0, RS_ERR_ARG, "rs_jindo_set_cosac_stream: standard deviation not positive");
+    if (j->cosac_stream) { rs::cosac_stream_free(j->cosac_stream); j->cosac_stream = nullptr; }
+    return rs::cosac_stream_init(&j->cosac_stream, key48_base, key48_rounded, ecd_blind_std, mask_blind_std, mask_std);
+}
+
+int rs_jindo_cosac_sample(rs_jindo *j, const uint64_t *first_row, const uint64_t *mask_rows, size_t n_mask_rows, int64_t *out, uint64_t *worker0,
+                          int *overflowed) {
+    RS_REQUIRE(j && first_row && mask_rows && out, RS_ERR_ARG, "rs_jindo_cosac_sample: null argument");
+    RS_REQUIRE(j->cosac_stream, RS_ERR_STATE, "rs_jindo_cosac_sample: no stream was set (rs_jindo_set_cosac_stream)");
+    const rs_jindo_params &p = j->p;
+    const size_t NLw = (size_t)j->f->NL, cs = (size_t)p.cols * p.slots, n_polys = (size_t)p.cols + n_mask_rows;
+    if (worker0) *worker0 = rs::cosac_stream_workers(j->cosac_stream);
+    uint32_t *d_el = nullptr;
+    i64 *d_g = nullptr;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_el, (cs + n_mask_rows * p.slots) * NLw * 4 + 16, rs::current_stream()));
+    int rc = RS_OK;
+    if (cudaMallocAsync((void **)&d_g, n_polys * JD * 8, rs::current_stream()) != cudaSuccess) rc = rs::set_error(RS_ERR_CUDA, "rs_jindo_cosac_sample: cudaMallocAsync failed");
+    if (rc == RS_OK && (cudaMemcpyAsync(d_el, first_row, cs * NLw * 4, cudaMemcpyHostToDevice, rs::current_stream()) != cudaSuccess ||
+                        cudaMemcpyAsync(d_el + cs * NLw, mask_rows, n_mask_rows * p.slots * NLw * 4, cudaMemcpyHostToDevice, rs::current_stream()) != cudaSuccess))
+        rc = rs::set_error(RS_ERR_CUDA, "rs_jindo_cosac_sample: upload failed");
+    if (rc == RS_OK) rc = rs::cosac_generate(j->cosac_stream, j->f, p, d_el, d_el + cs * NLw, n_polys, d_g);
+    int flag = 0;
+    if (rc == RS_OK && (cudaMemcpyAsync(out, d_g, n_polys * JD * 8, cudaMemcpyDeviceToHost, rs::current_stream()) != cudaSuccess ||
+                        cudaMemcpyAsync(&flag, rs::cosac_stream_overflow_flag(j->cosac_stream), 4, cudaMemcpyDeviceToHost, rs::current_stream()) != cudaSuccess ||
+                        cudaStreamSynchronize(rs::current_stream()) != cudaSuccess))
+        rc = rs::set_error(RS_ERR_CUDA, "rs_jindo_cosac_sample: %s", cudaGetErrorString(cudaGetLastError()));
+    if (overflowed) *overflowed = flag;
+    cudaFreeAsync(d_el, rs::current_stream());
+    if (d_g) cudaFreeAsync(d_g, rs::current_stream());
+    return rc;
 }
 
 int rs_jindo_mlwe_stream_sample(rs_jindo *j, size_t n, int64_t *out) {
@@ -2252,7 +2299,9 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
     const size_t rank = (size_t)p.cols * (p.rows - 1) * p.slots;
     RS_REQUIRE(len <= rank, RS_ERR_SHAPE, "len(v) > params.rank");                    // prover.go:47-49
     RS_REQUIRE(len >= 1, RS_ERR_SHAPE, "rs_jindo_commit: vector range out of bounds");
-    RS_REQUIRE(tape->first_row && tape->last_row && tape->mask_rows && tape->cosac_g && tape->mlwe, RS_ERR_ARG, "rs_jindo_commit: incomplete tape");
+    RS_REQUIRE(tape->first_row && tape->last_row && tape->mask_rows && tape->mlwe, RS_ERR_ARG, "rs_jindo_commit: incomplete tape");
+    const bool gen_cosac = (tape->cosac_g == nullptr);
+    if (gen_cosac) RS_REQUIRE(j->cosac_stream, RS_ERR_ARG, "rs_jindo_commit: tape carries no COSAC samples and no stream was set (rs_jindo_set_cosac_stream)");
     const int NL = j->f->NL, d = JD, slots = p.slots, rows = p.rows, cols = p.cols;
     const size_t cs = (size_t)cols * slots;
 
@@ -2320,7 +2369,7 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         RS_CUDA_CHECK(cudaMemcpy(j->d_ndescs, ndescs.data(), n_noise * sizeof(EncDesc), cudaMemcpyHostToDevice));
     }
     RS_REQUIRE(tape->n_mask_rows == mask, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of mask rows");
-    RS_REQUIRE(tape->n_cosac_polys == cosac, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of COSAC polynomials");
+    RS_REQUIRE(gen_cosac || tape->n_cosac_polys == cosac, RS_ERR_SHAPE, "rs_jindo_commit: tape has the wrong number of COSAC polynomials");
     const bool gen_mlwe = tape->mlwe_mask_only != 0;
     if (gen_mlwe) RS_REQUIRE(j->mlwe_stream, RS_ERR_ARG, "rs_jindo_commit: tape has mlwe_mask_only set and no stream was set (rs_jindo_set_mlwe_stream)");
     const bool gen_twin = (tape->twin_u == nullptr && twin != 0);
@@ -2343,7 +2392,7 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
 
     // ---- uploads (skipped when the tape is already device resident)
     const bool dev = tape->on_device != 0;
-    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; bool twin_drawn = false, mlwe_owned = false; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
+    uint32_t *d_aux = nullptr; u64 *d_twin = nullptr; bool twin_drawn = false, mlwe_owned = false, cosac_owned = false; i64 *d_cosac = nullptr, *d_mlwe_s = nullptr;
     u64 *d_com = nullptr;
     uint32_t *d_v = nullptr;          // device copy of a host-resident v
 #define RS_TRY(x) do { rc = (x); if (rc) goto fail; } while (0)
@@ -2361,7 +2410,7 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
         if (dev) { d_twin = (u64 *)tape->twin_u; d_cosac = (i64 *)tape->cosac_g; }
         else {
             if (!gen_twin) RS_TRY(upload(&d_twin, (const u64 *)tape->twin_u, twin * d));
-            RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d));
+            if (!gen_cosac) { RS_TRY(upload(&d_cosac, (const i64 *)tape->cosac_g, cosac * d)); cosac_owned = true; }
         }
         if (gen_mlwe) {
             // data columns: Prover.mlweSampler on the device (the whole Commit's draws, so that a column shard sees the
@@ -2375,6 +2424,13 @@ static int commit_impl(rs_jindo *j, const uint32_t *vec, const uint64_t *v_host,
             RS_TRY(upload(&d_mlwe_s, (const i64 *)tape->mlwe, n_noise * d));
             mlwe_owned = true;
         }
+    }
+    if (gen_cosac) {
+        // the COSAC rows (row 0 of the data columns, every row of the mask column) sampled in HBM from the elements just uploaded:
+        // all of them, also for a column shard (the worker numbering is global, like the tape offsets)
+        if (cudaMallocAsync((void **)&d_cosac, cosac * d * 8, current_stream()) != cudaSuccess) { rc = set_error(RS_ERR_CUDA, "rs_jindo_commit: cudaMallocAsync failed"); goto fail; }
+        cosac_owned = true;
+        RS_TRY(rs::cosac_generate(j->cosac_stream, j->f, p, d_aux, d_aux + 2 * cs * NL, cosac, d_cosac));
     }
     if (v_host) {
         // upload v in RS_VCHUNKS pieces on the copy stream; piece k is encoded as soon as it has landed.  Enqueued right behind
@@ -2440,7 +2496,8 @@ fail:
 #undef RS_TRY
     cudaFreeAsync(d_aux, current_stream());
     if (d_v) cudaFreeAsync(d_v, current_stream());
-    if (!dev) { if (!gen_twin) cudaFreeAsync(d_twin, current_stream()); cudaFreeAsync(d_cosac, current_stream()); }
+    if (!dev && !gen_twin) cudaFreeAsync(d_twin, current_stream());
+    if (cosac_owned) cudaFreeAsync(d_cosac, current_stream());
     if (mlwe_owned) cudaFreeAsync(d_mlwe_s, current_stream());
     if (twin_drawn) {
         uniform_stream_release(j->twin_stream);                  // every reader of the draws has been launched

@@ -81,6 +81,9 @@ class TapeBuilder:
         except Exception:
             pass
 
+    def set_device_cosac(self, on=True):
+        check(lib().rs_tape_builder_set_device_cosac(self.h, 1 if on else 0))
+
     def set_random_bytes(self, data):
         self._rand = ctypes.create_string_buffer(bytes(data), len(data))
         check(lib().rs_tape_builder_set_random_bytes(self.h, ctypes.cast(self._rand, c_vp), len(data)))
@@ -228,6 +231,23 @@ class Prover:
         dg = key48(seed)
         check(lib().rs_jindo_set_mlwe_stream(self.h, ctypes.c_char_p(dg[:32]), ctypes.c_char_p(dg[32:48]), _vp(tab), len(tab), lo))
 
+    def SetCosacSeeds(self, seed_base, seed_rounded, noise):
+        """Encoder.cosac on the device (rs_jindo_set_cosac_stream): seeds of its two UniformSamplers (hashed with SHA-384 like
+        NewUniformSamplerWithSeed); noise: dict with ecd_blind_std, mask_blind_std, mask_std"""
+        kb, kr = key48(seed_base), key48(seed_rounded)
+        self._cosac_keys = (kb, kr)
+        check(lib().rs_jindo_set_cosac_stream(self.h, ctypes.c_char_p(kb), ctypes.c_char_p(kr), float(noise["ecd_blind_std"]),
+                                              float(noise["mask_blind_std"]), float(noise["mask_std"])))
+
+    def CosacSample(self, first_row, mask_rows):
+        """the COSAC polynomials a Commit with these rows draws: (g [cols + n_mask_rows, 256], first worker index, overflow flag)"""
+        fr = np.ascontiguousarray(first_row, dtype=np.uint64); mr = np.ascontiguousarray(mask_rows, dtype=np.uint64)
+        n_mask = mr.size // (self.field.L * self.p["slots"])
+        out = np.zeros((self.p["cols"] + n_mask, self.d), dtype=np.int64)
+        w0, ov = ctypes.c_uint64(), ctypes.c_int()
+        check(lib().rs_jindo_cosac_sample(self.h, _vp(fr), _vp(mr), n_mask, _vp(out), ctypes.byref(w0), ctypes.byref(ov)))
+        return out, w0.value, ov.value
+
     def MlweStreamSample(self, n):
         out = np.zeros(n, dtype=np.int64)
         check(lib().rs_jindo_mlwe_stream_sample(self.h, n, _vp(out)))
@@ -268,7 +288,8 @@ class Prover:
         T.n_mask_rows = keep["mask_rows"].size // (L * self.p["slots"])
         if "twin_u" in keep:
             T.twin_u, T.n_twin_u = _vp(keep["twin_u"]), keep["twin_u"].size
-        T.cosac_g, T.n_cosac_polys = _vp(keep["cosac_g"]), keep["cosac_g"].size // self.d
+        if "cosac_g" in keep:
+            T.cosac_g, T.n_cosac_polys = _vp(keep["cosac_g"]), keep["cosac_g"].size // self.d
         T.mlwe = _vp(keep["mlwe"])
         T.mlwe_mask_only = 1 if tape.get("mlwe_mask_only") else 0
         return T, keep

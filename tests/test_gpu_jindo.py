@@ -622,3 +622,95 @@ def test_wire_format_through_the_abi(rs):
     buf = ctypes.create_string_buffer(int(n))
     assert rs.lib().rs_jindo_poly_write_to(poly.ctypes.data_as(ctypes.c_void_p), poly.shape[0], poly.shape[1], ctypes.cast(buf, ctypes.c_void_p), int(n)) == n
     assert buf.raw == J.poly_write_to(prv.ck.In[0][0])
+
+
+def _host_cosac_expected(rs, p, pd, q, L, keys, noise, first_row, mask_rows, worker0):
+    """What the device COSAC sampler must produce: for worker w = worker0 + 256 t + c a fresh host COSACSampler
+    (rs_cosac_create: csprng.COSACSampler restated, pinned to the oracle in test_host_sampler.py) keyed like the device's --
+    the stream's two keys, counters IV + (w << 16) -- asked for Sample(-fp[c], stdDev) once, with the base-b digits and float64
+    centres of encoder.go:120-164 computed here in plain Python floats (IEEE doubles, unfused, same order)."""
+    import ctypes
+    lib = rs.lib()
+    kb, kr = keys
+    R_inv = pow(1 << (64 * L), -1, q)
+    slots, exp, base, cols, N = p.slots, p.exp, p.base, p.cols, 256
+    n_mask = len(mask_rows) // slots
+    out = np.zeros((cols + n_mask, N), dtype=np.int64)
+    ivb, ivr = int.from_bytes(kb[32:], "big"), int.from_bytes(kr[32:], "big")
+    lib.rs_cosac_sample.restype = ctypes.c_int64
+    for t in range(cols + n_mask):
+        rows = first_row[t * slots:(t + 1) * slots] if t < cols else mask_rows[(t - cols) * slots:(t - cols + 1) * slots]
+        digits = [0] * N
+        for i, limbs in enumerate(rows):
+            c = sum(int(v) << (64 * k) for k, v in enumerate(limbs)) * R_inv % q
+            for j in range(exp - 1):
+                digits[j * slots + i] = c % base
+                c //= base
+            digits[(exp - 1) * slots + i] = c & ((1 << 64) - 1)
+        fp = [0.0] * N
+        for i in range(exp):
+            di = pd["delta_inv"][i]
+            if di == 0:
+                continue
+            dd = N - (i + 1) * slots
+            for j, jj in zip(range(0, N - dd), range(dd, N)):
+                fp[jj] += di * float(digits[j])
+            for j, jj in zip(range(N - dd, N), range(0, dd)):
+                fp[jj] -= di * float(digits[j])
+        std = noise["ecd_blind_std"] if t < cols else (noise["mask_blind_std"] if t == cols else noise["mask_std"])
+        for c in range(N):
+            w = worker0 + 256 * t + c
+            kbw = kb[:32] + ((ivb + (w << 16)) % (1 << 128)).to_bytes(16, "big")
+            krw = kr[:32] + ((ivr + (w << 16)) % (1 << 128)).to_bytes(16, "big")
+            h = lib.rs_cosac_create(ctypes.c_char_p(kbw), ctypes.c_char_p(krw))
+            out[t, c] = lib.rs_cosac_sample(h, ctypes.c_double(-fp[c]), ctypes.c_double(std))
+            lib.rs_cosac_destroy(h)
+    return out
+
+
+@pytest.mark.parametrize("name,N", [("zp255", 1024), ("zp128", 700)])
+def test_device_cosac_equals_the_host_samplers(rs, name, N):
+    """rs_jindo_set_cosac_stream: the encoder's COSAC rows sampled on the device, one fresh sampler per coefficient.  Every sample
+    equals what the host restatement of csprng.COSACSampler returns for the same keys / counters / centre / stdDev; a Commit that
+    draws them on the device equals the Commit that is handed the same samples on its tape."""
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    p = J.new_parameters(q, N, 1)
+    tape = J.Tape(b"device-cosac-" + name.encode())
+    prv = J.Prover(p, b"Jindo!", tape)
+    pd = params_dict(p, prv.ecd)
+    gp = rs.jindo.Prover(fg, pd, polys_array(prv.ck.In), polys_array(prv.ck.MLWE), polys_array(prv.ck.Out), cdt_array(prv.ecd))
+    noise = {"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std, "mask_mlwe_std": p.mask_mlwe_std}
+    gp.SetCosacSeeds(b"cosac-base-seed", b"cosac-rounded-seed", noise)
+    rng = np.random.default_rng(11)
+    rnd_elems = lambda n: fo.to_mont([int.from_bytes(rng.bytes(40), "little") % q for _ in range(n)])
+    first = rnd_elems(p.cols * p.slots)
+    mask = rnd_elems(p.rows * p.slots)
+    # small values too: the digits above the first are zero, the centre is tiny
+    first[0] = fo.to_mont([0])[0]; first[1] = fo.to_mont([1])[0]; mask[0] = fo.to_mont([q - 1])[0]
+    for rep in range(2):                                  # the worker counter runs on between calls
+        g, w0, ov = gp.CosacSample(first, mask)
+        assert ov == 0 and w0 == rep * (p.cols + p.rows) * 256
+        want = _host_cosac_expected(rs, p, pd, q, fo.L, gp._cosac_keys, noise, first, mask, w0)
+        assert np.array_equal(g, want), (rep, np.argwhere(g != want)[:5])
+    assert abs(float(g[p.cols + 1:].std()) - p.mask_std) < 0.1 * p.mask_std      # sanity: the spread is the requested one
+    # ---- a whole Commit: cosac_g = NULL on the tape against the same samples supplied
+    v = [int.from_bytes(rng.bytes(40), "little") % q for _ in range(N)]
+    com_o, open_o = prv.commit(v)
+    t_ex = tape_arrays(fo, p, prv.trace)
+    B = rs.Batch(fg, 1, max(N, 8))
+    host = np.zeros((1, max(N, 8), fo.L), dtype=np.uint64); host[0, :N] = fo.to_mont(v)
+    B.upload(host)
+    w0 = 2 * (p.cols + p.rows) * 256
+    n_mask_rows = t_ex["mask_rows"].shape[0] // p.slots
+    want = _host_cosac_expected(rs, p, pd, q, fo.L, gp._cosac_keys, noise, t_ex["first_row"], t_ex["mask_rows"], w0)
+    t_dev = dict(t_ex); t_dev["cosac_g"] = None
+    com_d, op_d = gp.Commit(B, 0, N, t_dev)
+    t_sup = dict(t_ex); t_sup["cosac_g"] = want.reshape(-1)
+    assert want.shape[0] == p.cols + n_mask_rows
+    com_s, op_s = gp.Commit(B, 0, N, t_sup)
+    assert np.array_equal(com_d, com_s)
+    for i in range(p.cols + 1):
+        for jrow in (0, 1, p.rows - 1):
+            assert np.array_equal(op_d.Encode(i, jrow), op_s.Encode(i, jrow)), (i, jrow)
+    assert not np.array_equal(com_d, polys_array(com_o))          # (different COSAC draws than the oracle's own tape)
