@@ -401,10 +401,20 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
     one_thread = rs.jindo.TapeBuilder(pdict, len(cdt[0]), noise, q, threads=1)
     one_thread.start(vp, N, 0); _, sampling_1t_ms = one_thread.wait(0)
     del one_thread
-    t = torch.tensor([ms, e2e_ms, host_tape_ms, seeds_ms, serial_ms], device="cuda")
+    # ---- the same with the COSAC rows sampled on the device too (rs_jindo_set_cosac_stream): the host only draws the
+    # MustSetRandom elements and the mask column's MLWE noise
+    gp.SetCosacSeeds(os.urandom(32), os.urandom(32), noise)
+    tb.set_device_cosac(True)
+    seeds_run(2, True)
+    barrier()
+    devc_ms, devc_sampling_ms = seeds_run(max(steps, 4), True)
+    barrier()
+    cosac_workers, cosac_overflow = gp.CosacStatus()
+    tb.set_device_cosac(False)
+    t = torch.tensor([ms, e2e_ms, host_tape_ms, seeds_ms, serial_ms, devc_ms], device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, host_tape_ms, seeds_ms, serial_ms = (float(x) for x in t)
+    ms, e2e_ms, host_tape_ms, seeds_ms, serial_ms, devc_ms = (float(x) for x in t)
     # algorithmic work per commit: mod-mul-adds of the inner/outer products and NTT butterflies
     macs = (p.cols + 1) * p.in_msis * (p.rows + p.mlwe) * p.d * len(p.q_primes) + p.out_msis * p.in_com_dcmp_len * p.d * len(p.qout_primes)
     out = {
@@ -428,9 +438,19 @@ def commit_leg(rs, L, f, q, args, world, rank, barrier, dist):
                          "partial_at/respond_bytes = x and SHAKE bytes in (vectors encoded on the device), results into pinned memory"},
         "sharded": sharded,
         "gpu_launches_per_commit": int(launches), "deterministic": deterministic,
-        "e2e": {"value": world * 1e3 / seeds_ms, "unit": "polys/s", "ms_per_commit": seeds_ms,
-                "h2d_bytes_per_step": nb + tape_bytes - twin_bytes - (n_noise - (p.in_msis + p.mlwe)) * p.d * 8, "d2h_bytes_per_step": int(com.nbytes),
+        "e2e": {"value": world * 1e3 / devc_ms, "unit": "polys/s", "ms_per_commit": devc_ms,
+                "h2d_bytes_per_step": nb + tape_bytes - twin_bytes - (n_noise - (p.in_msis + p.mlwe)) * p.d * 8 - n_cosac * p.d * 8,
+                "d2h_bytes_per_step": int(com.nbytes),
                 "inputs": "the committed vector in pinned host memory + sampler seeds; nothing pre-sampled",
+                "sampling": {"host_threads": n_thr, "host_ms_per_commit": devc_sampling_ms,
+                             "device": "every Gaussian sampler: encoder TwinCDT rows (%d polys), mlweSampler (%d polys), COSAC rows (%d polys, one fresh "
+                                       "COSACSampler per coefficient, cosac_dev.cu)" % (n_twin, p.cols * (p.in_msis + p.mlwe), n_cosac),
+                             "host": "MustSetRandom elements of the first / last / mask rows and the mask column's rounded-Gaussian MLWE noise",
+                             "cosac_workers": int(cosac_workers), "cosac_overflow": int(cosac_overflow)},
+                "call": "rs_tape_builder_start/wait (device COSAC) + rs_jindo_commit_host: v uploaded in 8 pieces behind the encode kernels"},
+        "e2e_host_cosac": {"value": world * 1e3 / seeds_ms, "unit": "polys/s", "ms_per_commit": seeds_ms,
+                "h2d_bytes_per_step": nb + tape_bytes - twin_bytes - (n_noise - (p.in_msis + p.mlwe)) * p.d * 8, "d2h_bytes_per_step": int(com.nbytes),
+                "inputs": "the committed vector in pinned host memory + sampler seeds; nothing pre-sampled; COSAC rows on the host worker threads",
                 "sampling": {"host_threads": n_thr, "host_ms_per_commit": sampling_ms, "host_ms_per_commit_1_thread": sampling_1t_ms,
                              "overlapped": "tape k+1 is sampled on the worker threads while Commit k runs on the GPU",
                              "no_overlap_ms_per_commit": serial_ms,
@@ -472,14 +492,19 @@ def buckler_leg(rs, L, args):
     pr.enable_sampling({"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std,
                         "mask_mlwe_std": p.mask_mlwe_std}, threads=threads)
     insts = [rs.circuits.mult_witness(f, q, N, 77 + k) for k in range(4)]
-    pr.prove_raw(insts[0][0], insts[0][1], None)
     steps = max(4, min(args.steps, 10))
-    l0 = L.rs_launch_count()
-    t0 = time.perf_counter()
-    for k in range(steps):
-        raw = pr.prove_raw(insts[k % 4][0], insts[k % 4][1], None, phases=False)
-    prove_ms = (time.perf_counter() - t0) * 1e3 / steps
-    launches = (L.rs_launch_count() - l0) // steps
+
+    def timed_prove():
+        pr.prove_raw(insts[0][0], insts[0][1], None)
+        l0 = L.rs_launch_count()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            raw = pr.prove_raw(insts[k % 4][0], insts[k % 4][1], None, phases=False)
+        return (time.perf_counter() - t0) * 1e3 / steps, (L.rs_launch_count() - l0) // steps, raw
+    host_cosac_ms, _, _ = timed_prove()                        # COSAC rows on the host worker threads
+    gp.SetCosacSeeds(os.urandom(32), os.urandom(32), {"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std})
+    pr.set_device_cosac(True)                                  # ... and on the device: the default of this leg
+    prove_ms, launches, raw = timed_prove()
     res = pr.verify_raw(insts[(steps - 1) % 4][0], raw)
     t0 = time.perf_counter()
     for _ in range(3):
@@ -489,11 +514,13 @@ def buckler_leg(rs, L, args):
     pr.prove_raw(insts[0][0], insts[0][1], None, phases=True)
     return {"workload": f"buckler.Prove + Verify, examples/mult MultCircuit, N = 2^13, zp128, {desc['w_cnt']}+{desc['pw_cnt']} witnesses, "
                         f"{batch} Jindo commits (rows {p.rows}, cols {p.cols}, slots {p.slots}) (BASELINE configs[0])",
-            "prove_ms": prove_ms, "proofs_per_s": 1e3 / prove_ms, "verify_ms": verify_ms, "verifier_accepts": res == 0,
+            "prove_ms": prove_ms, "proofs_per_s": 1e3 / prove_ms, "prove_ms_host_cosac": host_cosac_ms,
+            "cosac_overflow": int(gp.CosacStatus()[1]), "verify_ms": verify_ms, "verifier_accepts": res == 0,
             "verifier_rejects_other_statement": wrong != 0, "gpu_launches_per_proof": int(launches),
             "host_sampler_threads": threads,
             "phases_ms_with_syncs": {k: round(v, 3) for k, v in pr.timing.items() if k != "_"},
-            "randomness": "drawn inside the timed region (rs_buckler_prove with rand = NULL)",
+            "randomness": "drawn inside the timed region (rs_buckler_prove with rand = NULL): every Gaussian sampler on the device, "
+                          "MustSetRandom elements and the mask column's noise on the host worker threads",
             "parity": "the same prover with explicit randomness is bit-identical to the restated reference prover "
                       "(tests/test_gpu_buckler.py; tests/perf/bench_buckler.py at this size: 6.0 ms)"}
 

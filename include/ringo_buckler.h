@@ -88,6 +88,9 @@ int rs_buckler_enable_sampling(rs_buckler *b, const rs_jindo_noise *noise, const
  * phase_ms (optional, 16 doubles): wall milliseconds of [0] encode+NTT, [1] commits, [2] arithCheck, [3] linCheck, [4] sumCheck, [5] Evaluate,
  * [6] tape staging, [7] total; Evaluate's parts: [8] batch combination of the openings, [9] Partial, [10] InCommit download + transcript, [11] responses,
  * [12] Poly.Evaluate of the committed vectors.  The stream is synchronised at every boundary when phase_ms is given. */
+/* on != 0: the self-sampled proofs take their COSAC rows from the Jindo prover's device sampler (rs_jindo_set_cosac_stream must
+ * have been called) instead of the host worker threads, which then only draw the MustSetRandom elements and the mask noise */
+int rs_buckler_set_device_cosac(rs_buckler *b, int on);
 /* rand == NULL: self-sampled (see rs_buckler_enable_sampling). */
 int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const rs_buckler_rand *rand,
                      rs_buckler_proof *proof, double *phase_ms);

@@ -104,6 +104,8 @@ int rs_jindo_mlwe_stream_sample(rs_jindo *j, size_t n, int64_t *out);
  * of its first 8 KiB of keystream (1024 draws; a sample takes about five). */
 int rs_jindo_set_cosac_stream(rs_jindo *j, const uint8_t *key48_base, const uint8_t *key48_rounded, double ecd_blind_std,
                               double mask_blind_std, double mask_std);
+/* workers handed out so far and the sticky overflow flag (synchronises the stream) */
+int rs_jindo_cosac_status(rs_jindo *j, uint64_t *workers, int *overflowed);
 int rs_jindo_cosac_sample(rs_jindo *j, const uint64_t *first_row, const uint64_t *mask_rows, size_t n_mask_rows, int64_t *out,
                           uint64_t *worker0, int *overflowed);
 

@@ -359,6 +359,10 @@ class NativeProver:
 
     mont_many = Prover.mont_many
 
+    def set_device_cosac(self, on=True):
+        """self-sampled proofs draw their COSAC rows on the device (the Jindo prover needs SetCosacSeeds first)"""
+        check(lib().rs_buckler_set_device_cosac(self.h, 1 if on else 0))
+
     def enable_sampling(self, noise, threads=4):
         """rs_buckler_enable_sampling: prove_raw(pw, w, None) then draws every random value inside the library (host samplers on
         `threads` worker threads + the Jindo prover's device streams, which must have been seeded: SetTwinSeed / SetMlweSeed)."""

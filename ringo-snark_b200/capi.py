@@ -154,6 +154,7 @@ _SIGS = {
     "rs_jindo_twin_stream_draw": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_set_mlwe_stream": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int64]),
     "rs_jindo_set_cosac_stream": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
+    "rs_jindo_cosac_status": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int)]),
     "rs_jindo_cosac_sample": (ctypes.c_int, [c_vp, c_vp, c_vp, c_size, c_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_int)]),
     "rs_jindo_mlwe_stream_sample": (ctypes.c_int, [c_vp, c_size, c_vp]),
     "rs_jindo_commit": (ctypes.c_int, [c_vp, c_vp, c_size, c_size, ctypes.POINTER(JindoTape), ctypes.POINTER(c_vp), c_vp]),
@@ -188,6 +189,7 @@ _SIGS = {
     # ringo_buckler.h
     "rs_buckler_create": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(BucklerCircuit), c_vp, c_size, ctypes.POINTER(c_vp)]),
     "rs_buckler_enable_sampling": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoNoise), c_u64p, ctypes.c_int]),
+    "rs_buckler_set_device_cosac": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "rs_buckler_destroy": (None, [c_vp]),
     "rs_buckler_batch": (c_size, [c_vp]),
     "rs_buckler_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(BucklerRand), ctypes.POINTER(BucklerProof), ctypes.POINTER(ctypes.c_double)]),

@@ -442,6 +442,11 @@ int rs_buckler_enable_sampling(rs_buckler *b, const rs_jindo_noise *noise, const
     return RS_OK;
 }
 
+int rs_buckler_set_device_cosac(rs_buckler *b, int on) {
+    if (!b || !b->tb) return rs::set_error(RS_ERR_STATE, "rs_buckler_set_device_cosac: call rs_buckler_enable_sampling first");
+    return rs_tape_builder_set_device_cosac(b->tb, on);
+}
+
 int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const rs_buckler_rand *rd, rs_buckler_proof *pf, double *phase_ms) {
     if (!b || !w || !pf || (b->pc && !pw)) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: null argument");
     const bool sampling = (rd == nullptr);       // the prover draws its own randomness, like the reference's Prove

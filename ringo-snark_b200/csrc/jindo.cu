@@ -1920,6 +1920,19 @@ int rs_jindo_set_cosac_stream(rs_jindo *j, const uint8_t *key48_base, const uint
     return rs::cosac_stream_init(&j->cosac_stream, key48_base, key48_rounded, ecd_blind_std, mask_blind_std, mask_std);
 }
 
+int rs_jindo_cosac_status(rs_jindo *j, uint64_t *workers, int *overflowed) {
+    RS_REQUIRE(j && j->cosac_stream, RS_ERR_STATE, "rs_jindo_cosac_status: no stream was set (rs_jindo_set_cosac_stream)");
+    if (workers) *workers = rs::cosac_stream_workers(j->cosac_stream);
+    if (overflowed) {
+        int flag = 0;
+        if (cudaMemcpyAsync(&flag, rs::cosac_stream_overflow_flag(j->cosac_stream), 4, cudaMemcpyDeviceToHost, rs::current_stream()) != cudaSuccess ||
+            cudaStreamSynchronize(rs::current_stream()) != cudaSuccess)
+            return rs::set_error(RS_ERR_CUDA, "rs_jindo_cosac_status: %s", cudaGetErrorString(cudaGetLastError()));
+        *overflowed = flag;
+    }
+    return RS_OK;
+}
+
 int rs_jindo_cosac_sample(rs_jindo *j, const uint64_t *first_row, const uint64_t *mask_rows, size_t n_mask_rows, int64_t *out, uint64_t *worker0,
                           int *overflowed) {
     RS_REQUIRE(j && first_row && mask_rows && out, RS_ERR_ARG, "rs_jindo_cosac_sample: null argument");

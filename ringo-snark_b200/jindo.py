@@ -239,6 +239,12 @@ class Prover:
         check(lib().rs_jindo_set_cosac_stream(self.h, ctypes.c_char_p(kb), ctypes.c_char_p(kr), float(noise["ecd_blind_std"]),
                                               float(noise["mask_blind_std"]), float(noise["mask_std"])))
 
+    def CosacStatus(self):
+        """(workers handed out so far, sticky overflow flag)"""
+        w, ov = ctypes.c_uint64(), ctypes.c_int()
+        check(lib().rs_jindo_cosac_status(self.h, ctypes.byref(w), ctypes.byref(ov)))
+        return w.value, ov.value
+
     def CosacSample(self, first_row, mask_rows):
         """the COSAC polynomials a Commit with these rows draws: (g [cols + n_mask_rows, 256], first worker index, overflow flag)"""
         fr = np.ascontiguousarray(first_row, dtype=np.uint64); mr = np.ascontiguousarray(mask_rows, dtype=np.uint64)

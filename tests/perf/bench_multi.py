@@ -31,6 +31,7 @@ def opt(name, default):
 
 
 instances = int(opt("instances", "256")); logn = int(opt("logn", "13")); threads = int(opt("threads", "4")); n_verify = int(opt("verify", "2"))
+device_cosac = opt("device-cosac", "1") != "0"   # COSAC rows sampled on the device (rs_jindo_set_cosac_stream) instead of the host threads
 n_streams = int(opt("streams", "1"))     # concurrent provers per GPU: one host thread + CUDA stream + prover handle each
 circuit, name = "mult", "zp128"
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -59,8 +60,11 @@ def make_prover():
     gp = rs.jindo.Prover(fg, params_dict(p, C.poly_prover.ecd), None, None, None, cdt_array(C.poly_prover.ecd), crs=b"Buckler!", key_from_crs=True)
     gp.SetTwinSeed(os.urandom(32)); gp.SetMlweSeed(os.urandom(32), p.mlwe_std)
     pr = rs.buckler.NativeProver(fg, q, desc, p, gp)
-    pr.enable_sampling({"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std,
-                        "mask_mlwe_std": p.mask_mlwe_std}, threads=threads)
+    noise = {"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std, "mask_mlwe_std": p.mask_mlwe_std}
+    pr.enable_sampling(noise, threads=threads)
+    if device_cosac:
+        gp.SetCosacSeeds(os.urandom(32), os.urandom(32), noise)
+        pr.set_device_cosac(True)
     return pr
 
 
@@ -155,6 +159,7 @@ if rank == 0:
                     f"({ctx.w_cnt}+{ctx.pw_cnt} witnesses, {ctx.batch()} Jindo commits each) = 2^{np.log2(coeffs_total):.2f} witness coefficients",
         "n_gpus": world, "scaling": "strong", "seconds": dt, "proofs_per_s": instances / dt,
         "witness_mcoeff_per_s": coeffs_total / dt / 1e6, "ms_per_proof_per_gpu": dt * 1e3 / max(1, b - a),
+        "cosac": "device" if device_cosac else "host threads", "cosac_overflow": int(sum(pr.gp.CosacStatus()[1] for pr in provers)) if device_cosac else None,
         "concurrent_provers_per_gpu": n_streams, "host_sampler_threads_per_prover": threads, "host_cpus": os.cpu_count(),
         "gathered_commitments": list(allc.shape), "all_commitments_distinct": bool(distinct), "transcript_digest": par.transcript_digest(allc),
         "compiled_verifier_accepted": int(tt[0]), "compiled_verifier_checked": int(tt[1]), "verify_ms_per_proof": verify_ms,

@@ -239,6 +239,12 @@ def test_self_sampled_prove_verifies(rs, circuit, name, N):
     pf_bad = nprv.prove(pwm, bad, None)
     assert not V.verify(pw, pf_bad)
     assert nprv.verify_raw(pwm, nprv.last_raw) != 0
+    # the same with the COSAC rows drawn by the device sampler (rs_jindo_set_cosac_stream): both Verifiers still accept
+    gp.SetCosacSeeds(os.urandom(32), os.urandom(32), {"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std})
+    nprv.set_device_cosac(True)
+    pf3 = nprv.prove(pwm, wm, None)
+    assert V.verify(pw, pf3) and nprv.verify_raw(pwm, nprv.last_raw) == 0
+    assert gp.CosacStatus()[1] == 0 and gp.CosacStatus()[0] > 0
 
 
 def test_compiled_prove_at_the_example_size_from_the_cached_trace(rs):
