@@ -717,27 +717,39 @@ int rs_reverse_scale(rs_batch *out, size_t op, const rs_batch *v, size_t vp, con
     return reverse_scale(v->f, elem_ptr(out, op), elem_ptr(v, vp), (const uint32_t *)scale, v->rank);
 }
 
+int rs_poly_evaluate_many(const rs_batch *const *batches, const size_t *polys, const size_t *lens, size_t n, const uint64_t *x, uint64_t *results);
+
 int rs_poly_evaluate(const rs_batch *p, size_t poly, size_t n_elems, const uint64_t *x, uint64_t *result) {
     RS_REQUIRE(p && x && result, RS_ERR_ARG, "rs_poly_evaluate: null argument");
     RS_REQUIRE(poly < p->n_polys && n_elems <= p->rank, RS_ERR_SHAPE, "rs_poly_evaluate: range out of bounds");
     const rs_field *f = p->f;
     const int NL = f->NL;
     if (n_elems == 0) { memset(result, 0, 4 * NL); return RS_OK; }
+    // up to 2^16 coefficients: one CTA, 256 chunks (evaluate_many_kernel)
+    if (n_elems <= ((size_t)1 << 16)) return rs_poly_evaluate_many(&p, &poly, &n_elems, 1, x, result);
+    // longer: every thread Horner-evaluates 64 coefficients, then the n / 64 partial values are themselves a polynomial in
+    // x^64, evaluated by the same one-CTA kernel (the one-thread combine this replaces took 31 ms at 2^22 coefficients)
     const int CH = 64;
     const size_t n_chunks = (n_elems + CH - 1) / CH;
     uint32_t xch[RS_MAX_NL];
     uint32_t e[2] = {(uint32_t)CH, 0};
     host_pow(f, xch, (const uint32_t *)x, e, 1);
-    uint32_t *d_partial = nullptr;
-    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_partial, (n_chunks + 1) * NL * 4, g_stream));
-    uint32_t *d_result = d_partial + n_chunks * NL;
-    int rc = horner(f, d_result, d_partial, elem_ptr(p, poly), n_elems, (const uint32_t *)x, xch, CH);
+    struct Desc { const uint32_t *coeffs; size_t n; };
+    uint8_t *d_buf = nullptr;
+    const size_t part_bytes = (n_chunks * NL * 4 + 15) & ~(size_t)15;
+    RS_CUDA_CHECK(cudaMallocAsync((void **)&d_buf, part_bytes + 16 + NL * 4, g_stream));
+    uint32_t *d_partial = (uint32_t *)d_buf, *d_result = (uint32_t *)(d_buf + part_bytes + 16);
+    const Desc h{d_partial, n_chunks};
+    int rc = horner(f, nullptr, d_partial, elem_ptr(p, poly), n_elems, (const uint32_t *)x, xch, CH);
+    cudaError_t e2 = cudaMemcpyAsync(d_buf + part_bytes, &h, sizeof(h), cudaMemcpyHostToDevice, g_stream);
+    if (rc == RS_OK && e2 != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_poly_evaluate: %s", cudaGetErrorString(e2));
+    if (rc == RS_OK) rc = evaluate_many(f, d_result, d_buf + part_bytes, 1, xch);
     if (rc == RS_OK) {
-        cudaError_t e2 = cudaMemcpyAsync(result, d_result, NL * 4, cudaMemcpyDeviceToHost, g_stream);
+        e2 = cudaMemcpyAsync(result, d_result, NL * 4, cudaMemcpyDeviceToHost, g_stream);
         if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(g_stream);
         if (e2 != cudaSuccess) rc = set_error(RS_ERR_CUDA, "rs_poly_evaluate: %s", cudaGetErrorString(e2));
     }
-    cudaFreeAsync(d_partial, g_stream);
+    cudaFreeAsync(d_buf, g_stream);
     return rc;
 }
 

@@ -430,11 +430,11 @@ int horner(const rs_field *f, uint32_t *d_result, uint32_t *d_partial, const uin
         for (int i = 0; i < NL; i++) { sx.v[i] = x[i]; sp.v[i] = x_pow_ch[i]; }                               \
         horner_chunks_kernel<NL, QS><<<(unsigned)((n_chunks + 127) / 128), 128, 0, current_stream()>>>(        \
             d_partial, coeffs, sx, F, n, CH);                                                                 \
-        horner_combine_kernel<NL, QS><<<1, 32, 0, current_stream()>>>(d_result, d_partial, sp, F, n_chunks);   \
+        if (d_result) horner_combine_kernel<NL, QS><<<1, 32, 0, current_stream()>>>(d_result, d_partial, sp, F, n_chunks);   \
     }
     RS_FIELD_DISPATCH(f, CALL)
 #undef CALL
-    count_launch(2);
+    count_launch(d_result ? 2 : 1);
     RS_CUDA_CHECK(cudaGetLastError());
     return RS_OK;
 }

@@ -193,6 +193,12 @@ def test_quorem_aut_reverse_evaluate(rs):
     x = rand_mont(fo, 1, 9)[0]
     for cnt in (n, n - 1, 1, 65, 64, 63):
         assert np.array_equal(B.poly(0).Evaluate(x, cnt), fo.poly_evaluate(a[:cnt], x)), cnt
+    # long vectors (> 2^16 coefficients: chunked Horner, then the partial values evaluated at x^64 by the one-CTA kernel)
+    nl = (1 << 17) + 77
+    al = rand_mont(fo, nl, 15)
+    BL = rs.Batch(fg, 1, nl).upload(al[None])
+    for cnt in (nl, (1 << 16) + 1, (1 << 16) + 64, 1 << 16):
+        assert np.array_equal(BL.poly(0).Evaluate(x, cnt), fo.poly_evaluate(al[:cnt], x)), cnt
     # the batched form (jindo.Prover.Evaluate's closing loop): ragged lengths incl. 1, < 256 and non-multiples of 256
     import ctypes
     lens = [n, n - 1, 1, 255, 256, 257, 1000, 3]
