@@ -47,7 +47,7 @@ struct RingDev {
     int f64_ok;
     // kernel-path switches (tuning / the parity tests of the alternative paths): read from the environment ONCE, when the
     // prover handle is created, never on the Commit path
-    int no_rowsum, no_pipe, no_split, no_small;
+    int no_rowsum, no_pipe, no_split, no_small, use_tma;
 };
 
 struct CrtDev {             // RNSReconstructor constants of the *source* ring (rns.go:33-55)
@@ -799,7 +799,10 @@ constexpr int MP_ROWS = MP_OT + MP_CTC;                         // polynomial ro
 constexpr int MP_STAGE_WORDS = MP_KS * MP_ROWS * MP_MS;         // u64 words per stage
 constexpr int MP_SMEM_BYTES = MP_STAGES * MP_STAGE_WORDS * 8;
 
-template <bool FOLD>
+// TMA == true: the stage's (k, row) segments -- 512 contiguous bytes each -- are fetched by the copy engine (cp.async.bulk,
+// SASS UBLKCP) issued by one warp and counted on an mbarrier per stage (complete_tx), instead of 16-byte LDGSTS pieces issued
+// by every thread with their address arithmetic and a cp.async.wait_group.
+template <bool FOLD, bool TMA>
 __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
                                                                    const u64 *__restrict__ x, const u64 *__restrict__ addend,
                                                                    const __grid_constant__ MatvecGeom G) {
@@ -827,6 +830,12 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
     constexpr int PAIRS_PER_ROUND = MP_THREADS / PIECES;
     __shared__ unsigned long long row_base[MP_ROWS];                // global address of (row, k = 0, this tile's first slot)
     __shared__ unsigned row_step[MP_ROWS];                          // bytes per k-step
+    __shared__ __align__(8) unsigned long long full_bar[MP_STAGES]; // TMA: one transaction barrier per stage
+    if (TMA && threadIdx.x == 0) {
+        for (int st = 0; st < MP_STAGES; st++)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&full_bar[st])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (threadIdx.x < MP_ROWS) {
         const int row = threadIdx.x;
         const u64 *src; size_t step;
@@ -844,6 +853,24 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
     const int piece = threadIdx.x % PIECES, pair0 = threadIdx.x / PIECES;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
     auto load_stage = [&](int it, int buf) {
+        if (TMA) {
+            if (threadIdx.x < 32) {
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar[buf]);
+                if (threadIdx.x == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)(PAIRS * MP_MS * 8)) : "memory");
+                __syncwarp();
+                for (int pair = threadIdx.x; pair < PAIRS; pair += 32) {
+                    const int kl = pair / MP_ROWS, row = pair - kl * MP_ROWS;
+                    int k = it * MP_KS + kl;
+                    if (k >= k_cnt) k = k_cnt > 0 ? k_cnt - 1 : 0;          // tail: harmless duplicate, not accumulated
+                    const unsigned long long src = row_base[row] + (unsigned long long)(unsigned)k * row_step[row];
+                    const unsigned dstp = ring_s + (unsigned)buf * (MP_STAGE_WORDS * 8) + (unsigned)pair * (MP_MS * 8);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dstp), "l"(src), "r"((unsigned)(MP_MS * 8)), "r"(bar) : "memory");
+                }
+            }
+            return;
+        }
         const unsigned dst = ring_s + (unsigned)buf * (MP_STAGE_WORDS * 8) + piece * 16;
 #pragma unroll
         for (int r = 0; r < (PAIRS + PAIRS_PER_ROUND - 1) / PAIRS_PER_ROUND; r++) {
@@ -867,16 +894,24 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
 
     const int n_it = (k_cnt + MP_KS - 1) / MP_KS;
     for (int st = 0; st < MP_STAGES - 1; st++) {
-        if (st < n_it) load_stage(st, st); else asm volatile("cp.async.commit_group;");
+        if (st < n_it) load_stage(st, st); else if (!TMA) asm volatile("cp.async.commit_group;");
     }
     int since = 0;
     for (int it = 0; it < n_it; it++) {
         // groups it and it+1 are in flight: wait for group it, then ONE barrier per iteration -- it publishes stage it and, since
         // every thread has finished iteration it-1 by now, frees that buffer for the load of iteration it + STAGES - 1
-        asm volatile("cp.async.wait_group %0;" ::"n"(MP_STAGES - 2));
+        if (TMA) {
+            // stage it has landed when its barrier has completed phase (it / STAGES): every thread waits on it itself
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar[it % MP_STAGES]);
+            const unsigned parity = (unsigned)((it / MP_STAGES) & 1);
+            asm volatile("{\n\t.reg .pred p;\n\tRS_MP_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra RS_MP_DONE;\n\tbra RS_MP_WAIT;\n\tRS_MP_DONE:\n\t}"
+                         ::"r"(bar), "r"(parity) : "memory");
+        } else {
+            asm volatile("cp.async.wait_group %0;" ::"n"(MP_STAGES - 2));
+        }
         __syncthreads();
         if (it + MP_STAGES - 1 < n_it) load_stage(it + MP_STAGES - 1, (it + MP_STAGES - 1) % MP_STAGES);
-        else asm volatile("cp.async.commit_group;");
+        else if (!TMA) asm volatile("cp.async.commit_group;");
         const u64 *buf = ring + (size_t)(it % MP_STAGES) * MP_STAGE_WORDS;
 #pragma unroll
         for (int kl = 0; kl < MP_KS; kl++) {
@@ -1201,6 +1236,7 @@ static int ring_setup(RingDev &R, CrtDev &C, int n, const u64 *q, const u64 *psi
     R.f64_ok = getenv("RS_JINDO_NOF64") ? 0 : 1;
     R.no_rowsum = getenv("RS_MV_NOROWSUM") ? 1 : 0; R.no_pipe = getenv("RS_MV_NOPIPE") ? 1 : 0; R.no_split = getenv("RS_MV_NOSPLIT") ? 1 : 0;
     R.no_small = getenv("RS_MV_NOSMALL") ? 1 : 0;
+    { const char *e = getenv("RS_MV_TMA"); R.use_tma = e ? atoi(e) : 0; }
     for (int l = 0; l < n; l++) {
         const u64 ql = q[l];
         if (ql >= (1ull << 44)) R.f64_ok = 0;
@@ -1357,8 +1393,10 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
     // large products (inner commit): shared-memory ring version
     if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !R.no_pipe &&
         (unsigned long long)G.key_ks * n_slots * 8 < (1ull << 32) && (unsigned long long)G.x_ks * n_slots * 8 < (1ull << 32)) {
-        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true>, MP_SMEM_BYTES));
-        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false>, MP_SMEM_BYTES));
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true, false>, MP_SMEM_BYTES));
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, false>, MP_SMEM_BYTES));
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true, true>, MP_SMEM_BYTES));
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, true>, MP_SMEM_BYTES));
         dim3 grid(n_slots / MP_MS, (G.O + MP_OT - 1) / MP_OT, (G.C + MP_CTC - 1) / MP_CTC);
         // few column tiles (a column shard of a Commit, a short Commit): cut K so that the grid still covers the chip
         const unsigned ctas = grid.x * grid.y * grid.z;
@@ -1381,8 +1419,13 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
             grid.y *= S;
         }
         u64 *dst = S > 1 ? d_parts : out;
-        if (G.fold_every) matvec_pipe_kernel<true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
-        else matvec_pipe_kernel<false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
+        // rows must be 16-byte aligned 512-byte segments for the bulk copies (they are: polynomial strides are multiples of 2 KiB)
+        const bool tma = R.use_tma && (((uintptr_t)key | (uintptr_t)x) & 15) == 0;
+        if (tma) {
+            if (G.fold_every) matvec_pipe_kernel<true, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
+            else matvec_pipe_kernel<false, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
+        } else if (G.fold_every) matvec_pipe_kernel<true, false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
+        else matvec_pipe_kernel<false, false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         count_launch();
         if (S > 1) {
             reduce_split_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, current_stream()>>>(out, d_parts, S, n_out, G);
