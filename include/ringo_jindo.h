@@ -55,6 +55,31 @@ typedef struct rs_jindo_params {
     double cdt_sigma;
 } rs_jindo_params;
 
+/* Standard deviations of jindo.Parameters (params.go:303-309) the COSAC / rounded samplers need */
+typedef struct rs_jindo_noise {
+    double ecd_blind_std;      /* row 0 of a data column             (COSAC)   */
+    double mask_blind_std;     /* row 0 of the mask column           (COSAC)   */
+    double mask_std;           /* other rows of the mask column      (COSAC)   */
+    double mask_mlwe_std;      /* MLWE noise of the mask column      (rounded) */
+} rs_jindo_noise;
+
+/* jindo.NewParameters(q, targetN, batch) (jindo/params.go:126-321) for callers that do not have the Go library at hand: the
+ * parameter search in the reference's float64 order, the RNS primes and psi by lattigo's conventions (restated, unpinned),
+ * Encoder.deltaInv and the TwinCDT geometry -- everything rs_jindo_create[_crs] and the samplers take.  q_le: the field modulus
+ * (must be b^k + 1, params.go:18-40).  rs_jindo_cdt_tables fills the 128 x p.cdt_len TwinCDT tables (computeCDT,
+ * math/csprng/gaussian_twin_cdt.go:13-35, centres i/128, sigma = ecd_std). */
+typedef struct rs_jindo_derived {
+    rs_jindo_params p;
+    rs_jindo_noise noise;
+    double ecd_std, mlwe_std;              /* params.ecdStdDev / mlweStdDev (sigma of the two TwinCDT samplers) */
+    double res_two_nm, in_com_dcmp_two_nm; /* the verifier's norm bounds (params.go:310-311) */
+    double com_size, pf_size;              /* the size estimate the search minimises, bits */
+    uint64_t rank;                         /* params.rank = cols * (rows - 1) * slots */
+    int32_t batch, in_com_dcmp_len, q_bits, qout_bits;
+} rs_jindo_derived;
+int rs_jindo_new_parameters(const uint64_t *q_le, int L64, uint64_t target_n, int batch, rs_jindo_derived *out);
+int rs_jindo_cdt_tables(const rs_jindo_derived *d, uint64_t *tables);
+
 /* NewProver (jindo/prover.go:28-40): uploads the commit key (ck.In [in_msis][rows], ck.MLWE
  * [in_msis][mlwe] over ringQ; ck.Out [out_msis][(cols+1)*in_msis] over ringQOut) and the
  * 128 x cdt_len TwinCDT tables. */

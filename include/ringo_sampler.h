@@ -53,13 +53,7 @@ int64_t rs_cosac_sample(rs_cosac *c, double center, double std_dev);            
 int rs_compute_cdt(double center, double sigma, uint64_t *table, int cap, int64_t *tail_lo);
 
 /* ---- the host half of a Commit's randomness tape ------------------------------------------------------------- */
-/* Standard deviations of jindo.Parameters (params.go:303-309) the host samplers need */
-typedef struct rs_jindo_noise {
-    double ecd_blind_std;      /* row 0 of a data column             (COSAC)   */
-    double mask_blind_std;     /* row 0 of the mask column           (COSAC)   */
-    double mask_std;           /* other rows of the mask column      (COSAC)   */
-    double mask_mlwe_std;      /* MLWE noise of the mask column      (rounded) */
-} rs_jindo_noise;
+/* rs_jindo_noise (the standard deviations the host samplers need) is declared in ringo_jindo.h */
 
 typedef struct rs_tape_builder rs_tape_builder;
 

@@ -68,8 +68,6 @@ class Prover:
         self.enc = CyclicTransformer(field, N)           # Encoder.ntt (encoder.go:15-20)
         self.emb = CyclicTransformer(field, E)           # polyEval (compile.go:186)
         self.neg = CyclotomicTransformer(field, N)       # nttChecker (linear.go:26-33)
-        self.ringQ = JH.HostRing(jindo_params.d, jindo_params.q_primes, [JH.psi_for(x, jindo_params.d) for x in jindo_params.q_primes])
-        self.ringQOut = JH.HostRing(jindo_params.d, jindo_params.qout_primes, [JH.psi_for(x, jindo_params.d) for x in jindo_params.qout_primes])
 
     # ---- scalars (host) -------------------------------------------------------------------------
     def mont(self, x):

@@ -60,6 +60,14 @@ class JindoNoise(ctypes.Structure):
                 ("mask_mlwe_std", ctypes.c_double)]
 
 
+class JindoDerived(ctypes.Structure):
+    """rs_jindo_derived (include/ringo_jindo.h)"""
+    _fields_ = [("p", JindoParams), ("noise", JindoNoise), ("ecd_std", ctypes.c_double), ("mlwe_std", ctypes.c_double),
+                ("res_two_nm", ctypes.c_double), ("in_com_dcmp_two_nm", ctypes.c_double), ("com_size", ctypes.c_double),
+                ("pf_size", ctypes.c_double), ("rank", ctypes.c_uint64), ("batch", ctypes.c_int32), ("in_com_dcmp_len", ctypes.c_int32),
+                ("q_bits", ctypes.c_int32), ("qout_bits", ctypes.c_int32)]
+
+
 class LinChecker(ctypes.Structure):
     """rs_lin_checker (include/ringo_buckler.h)"""
     _fields_ = [("kind", ctypes.c_int32), ("is_ntt", ctypes.c_int32), ("idx_inv", ctypes.c_int64), ("pairs", c_vp), ("n_pairs", c_size)]
@@ -147,6 +155,8 @@ _SIGS = {
     # ringo_jindo.h
     "rs_jindo_create": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "rs_jindo_create_crs": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams), c_vp, c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "rs_jindo_new_parameters": (ctypes.c_int, [c_u64p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(JindoDerived)]),
+    "rs_jindo_cdt_tables": (ctypes.c_int, [ctypes.POINTER(JindoDerived), c_vp]),
     "rs_jindo_get_params": (ctypes.c_int, [c_vp, ctypes.POINTER(JindoParams)]),
     "rs_jindo_commit_key_download": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp]),
     "rs_jindo_destroy": (None, [c_vp]),

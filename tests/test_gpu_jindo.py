@@ -1,6 +1,8 @@
 """GPU parity tests for the Jindo path (rs_jindo_* through the C ABI) against the oracle
 (oracle/jindo_ref.py) on the same parameters, commit key and randomness tape -- bit-exact on
 every polynomial of the Opening, the Commitment and the Evaluate responses."""
+import os
+
 import numpy as np
 import pytest
 
@@ -432,6 +434,15 @@ def test_commit_mid_size_bit_exact_vs_c_oracle(rs, name, logn, length_off, huge)
     B = rs.Batch(fg, 1, N)
     host = np.zeros((1, N, fo.L), dtype=np.uint64); host[0, :length] = v
     B.upload(host)
+    if logn >= 16:
+        # the same Commit with the mat-vec's TMA loader (cp.async.bulk + mbarrier; opt-in because it measured slower)
+        os.environ["RS_MV_TMA"] = "1"
+        try:
+            gt = rs.jindo.Prover(fg, pd, ck_in, ck_mlwe, ck_out, cdt_array(ecd))
+        finally:
+            del os.environ["RS_MV_TMA"]
+        com_t, _ = gt.Commit(B, 0, length, tape)
+        assert np.array_equal(com_t, exp["commitment"])
     com, op = gp.Commit(B, 0, length, tape)
     assert np.array_equal(com, exp["commitment"])
     for k in range(p.in_com_dcmp_len):

@@ -27,8 +27,9 @@ def test_commitment_serialisation_numpy_equals_lists(product):
 
 
 def test_host_parameters_match_oracle(product):
-    """jindo_host.new_parameters (product side) against the oracle's restatement of jindo.NewParameters for the shapes of
-    SURVEY section 8 (they are independent implementations of params.go:126-321)."""
+    """jindo_host.new_parameters (product side: a thin wrapper over the compiled rs_jindo_new_parameters, csrc/jindo_params.cpp)
+    against the oracle's Python restatement of jindo.NewParameters for the shapes of SURVEY section 8; tests/test_host_params.py
+    compares every field, float and table of the C ABI result itself."""
     JH = product.jindo_host
     for name, n, batch in (("zp255", 1 << 22, 1), ("zp128", 16385, 12), ("zp240", 32769, 43), ("zp220", 2049, 9), ("zp255", 1024, 8)):
         a = JH.new_parameters(pyref.modulus(name), n, batch); b = J.new_parameters(pyref.modulus(name), n, batch)
