@@ -1391,7 +1391,9 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         return RS_OK;
     }
     // large products (inner commit): shared-memory ring version
-    if (G.key_cs == 0 && (long long)G.K * G.C >= 4096 && !R.no_pipe &&
+    // (also a single column with a long K -- the verifier's ck.In x Encode product: split-K fills the chip, the register-tile kernel
+    //  below would walk K = rows sequentially in 160 CTAs)
+    if (G.key_cs == 0 && ((long long)G.K * G.C >= 4096 || (G.C == 1 && G.K >= 1024)) && !R.no_pipe &&
         (unsigned long long)G.key_ks * n_slots * 8 < (1ull << 32) && (unsigned long long)G.x_ks * n_slots * 8 < (1ull << 32)) {
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true, false>, MP_SMEM_BYTES));
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, false>, MP_SMEM_BYTES));

@@ -4,6 +4,7 @@ The reference's own tests only assert Verify(Prove) == true (jindo/jindo_test.go
 same self-check is run on the restatement, together with parameter-table and sampler checks."""
 import hashlib
 
+import numpy as np
 import pytest
 from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
 
@@ -103,4 +104,4 @@ def test_product_host_parameter_mirror_matches_oracle(product):
         d, tables = JH.prover_inputs(ph)
         assert d["delta_inv"] == enc.delta_inv and d["cdt_tail_lo"] == enc.twin.tail_lo
         assert d["psi_q"] == [s.psi for s in po.ringQ.sub] and d["psi_qout"] == [s.psi for s in po.ringQOut.sub]
-        assert tables == enc.twin.tables
+        assert np.array_equal(tables, np.array(enc.twin.tables, dtype=np.uint64))
