@@ -2225,6 +2225,13 @@ int rs_jindo_verify(rs_jindo *j, const uint64_t *x_mont, const uint64_t *commitm
             if (neg) { u64 cy = 1; for (int i = 0; i < JW; i++) { const u64 t = ~V[i] + cy; cy = (cy && t == 0); M[i] = t; } }
             else for (int i = 0; i < JW; i++) M[i] = V[i];
             uint32_t acc[RS_MAX_NL] = {0}, chunk[RS_MAX_NL], t[RS_MAX_NL];
+            bool one_word = true;
+            for (int i = 1; i < JW; i++) one_word &= (M[i] == 0);
+            if (one_word) {                                                            // |V| < 2^64 (every honest digit): one product
+                memset(chunk, 0, sizeof(chunk));
+                chunk[0] = (uint32_t)M[0]; chunk[1] = (uint32_t)(M[0] >> 32);
+                host_mul(f, acc, chunk, f->r2);
+            } else {
             const int n_chunks = (JW + L64 - 1) / L64;
             for (int ch = n_chunks - 1; ch >= 0; ch--) {                               // value = sum chunk_k R^k, Horner in Montgomery form
                 host_mul(f, acc, acc, f->r2);                                          // acc * R
@@ -2232,6 +2239,7 @@ int rs_jindo_verify(rs_jindo *j, const uint64_t *x_mont, const uint64_t *commitm
                 for (int w = 0; w < L64 && ch * L64 + w < JW; w++) { chunk[2 * w] = (uint32_t)M[ch * L64 + w]; chunk[2 * w + 1] = (uint32_t)(M[ch * L64 + w] >> 32); }
                 host_mul(f, t, chunk, f->r2);                                          // to Montgomery (chunk < R; result canonical)
                 host_add(f, acc, acc, t);
+            }
             }
             if (neg) { uint32_t z[RS_MAX_NL] = {0}; bool any = false; for (int i = 0; i < NL; i++) any |= acc[i] != 0;
                        if (any) { u64 br = 0; for (int i = 0; i < NL; i++) { const u64 dd = (u64)f->q[i] - acc[i] - br; z[i] = (uint32_t)dd; br = (dd >> 63) & 1; } memcpy(acc, z, 4 * NL); } }
