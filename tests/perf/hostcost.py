@@ -1,8 +1,9 @@
-"""Host-side cost of the small C-ABI calls a Buckler Prove is made of (mult circuit, N = 2^13 shapes): wall time per call with
-the stream drained before and after.  python tools/hostcost.py [trace.pkl]"""
+"""[tests/perf: developer harness that takes inputs from / checks against the oracle, hence under tests/ -- the product never imports oracle/]
+Host-side cost of the small C-ABI calls a Buckler Prove is made of (mult circuit, N = 2^13 shapes): wall time per call with
+the stream drained before and after.  python tests/perf/hostcost.py [trace.pkl]"""
 import json, os, pickle, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_product
 import oracle

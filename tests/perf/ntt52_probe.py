@@ -1,12 +1,13 @@
-"""FP64-pipe NTT probe (one GPU): pipe microbenchmarks, then for every ntt52 tuning variant the headline transform
+"""[tests/perf: developer harness that takes inputs from / checks against the oracle, hence under tests/ -- the product never imports oracle/]
+FP64-pipe NTT probe (one GPU): pipe microbenchmarks, then for every ntt52 tuning variant the headline transform
 (zp255, rank 2^16, batch 512, all four kinds) timed with CUDA events inside the library and compared bit for bit
 with the integer-pipe kernels (RS_NTT_NO52) on the same input.
 
-    python tools/ntt52_probe.py [--out=FILE] [--batch=512] [--logn=16] [--variants=0,1,2,3]
+    python tests/perf/ntt52_probe.py [--out=FILE] [--batch=512] [--logn=16] [--variants=0,1,2,3]
 """
 import ctypes, json, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench
 import torch

@@ -1,9 +1,10 @@
-"""The compiled Buckler prover alone (no oracle run, no Python mirror): loads a cached oracle trace, proves `reps` times through
+"""[tests/perf: developer harness that takes inputs from / checks against the oracle, hence under tests/ -- the product never imports oracle/]
+The compiled Buckler prover alone (no oracle run, no Python mirror): loads a cached oracle trace, proves `reps` times through
 rs_buckler_prove and prints the wall times -- the command ncu / the launch list is taken of.
-  python tools/prove_native.py [trace.pkl] [reps] [--pinned]"""
+  python tests/perf/prove_native.py [trace.pkl] [reps] [--pinned]"""
 import ctypes, json, os, pickle, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_product
 from oracle import buckler_ref as B, jindo_ref as J, pyref

@@ -1,10 +1,11 @@
-"""Small end-to-end exercise of every kernel family for compute-sanitizer (tools/sanitize.sh): big-field NTTs (integer, FP64 and
+"""[tests/perf: developer harness that takes inputs from / checks against the oracle, hence under tests/ -- the product never imports oracle/]
+Small end-to-end exercise of every kernel family for compute-sanitizer (tools/sanitize.sh): big-field NTTs (integer, FP64 and
 two-pipe kernels), element-wise ops / evalCircuit / QuoRem / Aut, one Jindo Commit (encode_kernel with its named barriers and
 shared queues, matvec_pipe_kernel with its cp.async ring incl. split-K, cut-off kernels, device samplers) and Evaluate.
 Results are checked against the oracle where cheap, so a sanitizer run is also a parity run."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import load_product
 import oracle
