@@ -9,6 +9,7 @@
 //   aes_keystream_kernel   one thread per 16-byte block: T-table AES-256 of (IV + block index)
 //   xor_scan_*             prefix XOR over chunks, independently for each of the 1024 word offsets of a
 //                          chunk, seeded with the sampler's running buffer state (3-phase segmented scan)
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -221,7 +222,8 @@ static int generate(UniformStream *s, u64 pos, size_t n, int b) {
     RS_CUDA_CHECK(cudaMemcpyAsync(state_out, state_in, CH_WORDS * 8, cudaMemcpyDeviceToDevice, st));
     if (n_chunks) {
         u64 *ks = buf + CH_WORDS;
-        aes_keystream_kernel<<<148 * 4, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
+        static const int ctas_per_sm = [] { const char *e = getenv("RS_AES_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 6 ? v : 4; }();
+        aes_keystream_kernel<<<148 * ctas_per_sm, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
         dim3 grid(CH_WORDS / 256, (unsigned)n_seg);
         xor_scan_totals<<<grid, 256, 0, st>>>(s->d_tot, ks, n_chunks, seg);
         xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, state_out, n_seg);
