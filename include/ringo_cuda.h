@@ -49,6 +49,13 @@ typedef struct rs_batch rs_batch;
 int rs_init(int device);                    /* cudaSetDevice + capability check (needs sm_100) */
 int rs_set_stream(void *cuda_stream);       /* stream used by subsequent calls (NULL = default) */
 int rs_sync(void);                          /* cudaStreamSynchronize(current stream) */
+/* stream plumbing for callers that run independent pieces side by side (the compiled Buckler prover issues the Commits of a round
+ * on a few side streams): create / destroy a non-blocking stream, read the calling thread's current one, and make `waiter`
+ * wait -- on the device, no host wait -- for everything enqueued on `signaller` so far */
+void *rs_get_stream(void);
+int rs_stream_create(void **stream_out);
+void rs_stream_destroy(void *stream);
+int rs_stream_wait(void *waiter, void *signaller);
 const char *rs_last_error(void);
 const char *rs_version(void);
 /* number of kernels this library has launched since load (bench.py "gpu_launches") */

@@ -99,6 +99,10 @@ _SIGS = {
     "rs_init": (ctypes.c_int, [ctypes.c_int]),
     "rs_set_stream": (ctypes.c_int, [c_vp]),
     "rs_sync": (ctypes.c_int, []),
+    "rs_get_stream": (c_vp, []),
+    "rs_stream_create": (ctypes.c_int, [ctypes.POINTER(c_vp)]),
+    "rs_stream_destroy": (None, [c_vp]),
+    "rs_stream_wait": (ctypes.c_int, [c_vp, c_vp]),
     "rs_last_error": (ctypes.c_char_p, []),
     "rs_version": (ctypes.c_char_p, []),
     "rs_launch_count": (ctypes.c_ulonglong, []),

@@ -314,6 +314,8 @@ struct rs_buckler {
     // self-sampled proofs (rs_buckler_enable_sampling): host samplers on worker threads, one tape slot per Commit
     rs_tape_builder *tb = nullptr;
     uint64_t *heads = nullptr;      // pinned: the first cols*slots coefficients of every committed vector (genFirstLastRow's input)
+    void *side[4] = {nullptr, nullptr, nullptr, nullptr};   // the Commits of a round run side by side on these streams
+    int n_side = 0;
     rs_batch *vs = nullptr;         // verifier scratch: Encode(linCheckVec) and one Encode(transposed vec) per checker, rank N
     std::vector<uint64_t> r_blind, r_lin_mask, r_sum_mask;
     uint64_t r_lin_sum[32], r_sum_sum[32];
@@ -348,6 +350,7 @@ void rs_buckler_destroy(rs_buckler *b) {
         if (x) rs_batch_free(x);
     for (rs_ntt *t : {b->enc, b->emb, b->neg})
         if (t) rs_ntt_destroy(t);
+    for (void *st : b->side) rs_stream_destroy(st);
     if (b->pin) rs_pinned_free(b->pin);
     if (b->tape_pin) rs_pinned_free(b->tape_pin);
     if (b->heads) rs_pinned_free(b->heads);
@@ -416,6 +419,11 @@ int rs_buckler_create(rs_field *f, rs_jindo *j, const rs_buckler_circuit *c, con
         uint64_t n_can[32] = {0};
         n_can[0] = N;
         rc = rs_field_to_mont(f, b->n_mont, n_can);
+    }
+    {
+        const char *e = getenv("RS_BUCKLER_STREAMS");              // 0: every Commit on the caller's stream
+        const int want = e ? atoi(e) : 4;
+        for (int k = 0; rc == RS_OK && k < want && k < 4; k++) { rc = rs_stream_create(&b->side[k]); if (rc == RS_OK) b->n_side = k + 1; }
     }
     if (rc == RS_OK) {
         b->off_lin_mask = np * N * b->L;
@@ -486,6 +494,8 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     const double t_start = t_last;
     auto mark = [&](int k) {
         if (!phase_ms) return;
+        void *m = rs_get_stream();
+        for (int i = 0; i < b->n_side; i++) rs_stream_wait(m, b->side[i]);
         rs_sync();
         const double t = now_ms();
         t_phase[k] += t - t_last;
@@ -546,8 +556,15 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     std::vector<rs_opening *> opens(n_com, nullptr);
     struct Cleanup {
         std::vector<rs_opening *> &o; rs_opening *extra = nullptr;
-        ~Cleanup() { rs_sync(); for (rs_opening *x : o) if (x) rs_opening_free(x); if (extra) rs_opening_free(extra); }
-    } cleanup{opens};
+        rs_buckler *bb; void *m;
+        ~Cleanup() {
+            rs_set_stream(m);
+            for (int k = 0; k < bb->n_side; k++) rs_stream_wait(m, bb->side[k]);
+            rs_sync();
+            for (rs_opening *x : o) if (x) rs_opening_free(x);
+            if (extra) rs_opening_free(extra);
+        }
+    } cleanup{opens, nullptr, b, rs_get_stream()};
     Transcript tr;
     ShakeWorker shake;
     shake.xof.absorb((const uint8_t *)b->crs.data(), b->crs.size());             // ck.WriteRawTo (jindo/prover.go:222)
@@ -556,13 +573,28 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     const size_t head_cap = (size_t)jp.cols * jp.slots;
     std::vector<size_t> pending;
     std::vector<int> bind_of(n_com);
+    // one Commit, enqueued only, on the next side stream: it starts once everything enqueued on the caller's stream so far (the
+    // committed vector) has run, and runs beside the other Commits of its round and the next round's arithmetic
+    void *const main_stream = rs_get_stream();
+    struct StreamGuard { void *m; ~StreamGuard() { rs_set_stream(m); } } stream_guard{main_stream};
+    auto issue = [&](size_t idx) -> int {
+        void *st = b->n_side ? b->side[idx % (size_t)b->n_side] : main_stream;
+        if (st != main_stream) { RS_B(rs_stream_wait(st, main_stream)); rs_set_stream(st); }
+        const int rc = rs_jindo_commit_async(b->j, views[idx].bt, views[idx].poly, views[idx].len, &tapes[idx], &opens[idx], coms_pin + idx * com_words);
+        rs_set_stream(main_stream);
+        return rc;
+    };
+    auto join_sides = [&]() -> int {
+        for (int k = 0; k < b->n_side; k++) RS_B(rs_stream_wait(main_stream, b->side[k]));
+        return RS_OK;
+    };
     // polyProver.Commit, enqueued only; the commitment lands in pinned memory
     auto commit = [&](size_t idx, rs_batch *bt, size_t poly, size_t len, int bind) -> int {
         if (idx != n_issued) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: commit order");
         views[idx] = View{bt, poly, len};
         bind_of[idx] = bind;
         n_issued++;
-        if (!sampling) return rs_jindo_commit_async(b->j, bt, poly, len, &tapes[idx], &opens[idx], coms_pin + idx * com_words);
+        if (!sampling) return issue(idx);
         // genFirstLastRow (jindo/prover.go:65-86) and the first rows' COSAC centres need the head of the vector on the host
         const size_t head = len < head_cap ? len : head_cap;
         rs_batch *view = nullptr;
@@ -581,7 +613,7 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
                 return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: tape builder start failed");
         for (size_t i : pending) {
             if (rs_tape_builder_wait(b->tb, (int)i, &tapes[i], nullptr) != RS_OK) return rs::set_error(RS_ERR_ARG, "rs_buckler_prove: tape builder failed");
-            RS_B(rs_jindo_commit_async(b->j, views[i].bt, views[i].poly, views[i].len, &tapes[i], &opens[i], coms_pin + i * com_words));
+            RS_B(issue(i));
         }
         pending.clear();
         return RS_OK;
@@ -591,6 +623,7 @@ int rs_buckler_prove(rs_buckler *b, const uint64_t *pw, const uint64_t *w, const
     uint8_t el[8 * 32];
     auto bind_ready = [&](long extra_after_a, const uint64_t *sum_a, long extra_after_b, const uint64_t *sum_b) -> int {
         RS_B(flush());
+        RS_B(join_sides());
         RS_B(rs_sync());
         for (; n_bound < n_issued; n_bound++) {
             RS_B(raw_of(n_bound));

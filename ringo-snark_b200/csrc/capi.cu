@@ -205,6 +205,25 @@ int rs_init(int device) {
 }
 
 int rs_set_stream(void *s) { g_stream = (cudaStream_t)s; return RS_OK; }
+void *rs_get_stream(void) { return (void *)g_stream; }
+int rs_stream_create(void **out) {
+    RS_REQUIRE(out, RS_ERR_ARG, "rs_stream_create: null argument");
+    cudaStream_t st;
+    RS_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *out = (void *)st;
+    return RS_OK;
+}
+void rs_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+// `waiter` continues only after everything enqueued on `signaller` so far has run (an event recorded now; no host wait)
+int rs_stream_wait(void *waiter, void *signaller) {
+    cudaEvent_t e;
+    RS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t r = cudaEventRecord(e, (cudaStream_t)signaller);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent((cudaStream_t)waiter, e, 0);
+    cudaEventDestroy(e);
+    if (r != cudaSuccess) return set_error(RS_ERR_CUDA, "rs_stream_wait: %s", cudaGetErrorString(r));
+    return RS_OK;
+}
 int rs_sync(void) { RS_CUDA_CHECK(cudaStreamSynchronize(g_stream)); return RS_OK; }
 
 void *rs_pinned_alloc(size_t bytes) {
