@@ -499,7 +499,7 @@ def buckler_leg(rs, L, args):
         l0 = L.rs_launch_count()
         t0 = time.perf_counter()
         for k in range(steps):
-            raw = pr.prove_raw(insts[k % 4][0], insts[k % 4][1], None, phases=False)
+            raw = pr.prove_raw(insts[k % 4][0], insts[k % 4][1], None, phases=False, reuse=True)   # proof buffers owned by the caller, as in Go
         return (time.perf_counter() - t0) * 1e3 / steps, (L.rs_launch_count() - l0) // steps, raw
     host_cosac_ms, _, _ = timed_prove()                        # COSAC rows on the host worker threads
     gp.SetCosacSeeds(os.urandom(32), os.urandom(32), {"ecd_blind_std": p.ecd_blind_std, "mask_blind_std": p.mask_blind_std, "mask_std": p.mask_std})

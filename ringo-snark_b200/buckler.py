@@ -408,16 +408,30 @@ class NativeProver:
         R.tapes, R.n_tapes = ctypes.cast(T, capi.c_vp), len(rand["tapes"])
         return R, keep
 
-    def prove_raw(self, pw_mont, w_mont, R, phases=True):
+    def prove_raw(self, pw_mont, w_mont, R, phases=True, reuse=False):
         """rs_buckler_prove on prepared inputs; returns the proof as numpy arrays (no Python-object conversion).
-        phases: also fill self.timing (the library synchronises the stream at every phase boundary to do so)"""
+        phases: also fill self.timing (the library synchronises the stream at every phase boundary to do so).
+        reuse: write into the buffers of the previous call (what a caller with its own proof buffers does; the returned arrays
+        are overwritten by the next call)"""
         p, d, L = self.gp.p, self.gp.d, self.L
         nq, nqo, B = self.gp.n_q, self.gp.n_qout, self.batch
+        out = getattr(self, "_out_bufs", None) if reuse else None
+        if out is None:
+            out = self._new_out_bufs(p, d, L, nq, nqo, B)
+            if reuse:
+                self._out_bufs = out
+        return self._prove_into(out, pw_mont, w_mont, R, phases)
+
+    @staticmethod
+    def _new_out_bufs(p, d, L, nq, nqo, B):
         out = {"Witness": np.zeros((B, p["out_msis"], nqo, d), dtype=np.uint64), "Evals": np.zeros((B, L), dtype=np.uint64),
                "Partial": np.zeros((p["cols"], nq, d), dtype=np.uint64), "PartialMask": np.zeros((nq, d), dtype=np.uint64),
                "Encode": np.zeros((p["rows"], nq, d), dtype=np.uint64), "MLWE": np.zeros((p["mlwe"] + p["in_msis"], nq, d), dtype=np.uint64),
                "InCommit": np.zeros(((p["cols"] + 1) * p["in_msis"], nqo, d), dtype=np.uint64),
                "lin_mask_sum": np.zeros(L, dtype=np.uint64), "sum_mask_sum": np.zeros(L, dtype=np.uint64), "eval_point": np.zeros(L, dtype=np.uint64)}
+        return out
+
+    def _prove_into(self, out, pw_mont, w_mont, R, phases):
         P = capi.BucklerProof()
         vp = lambda a: a.ctypes.data_as(capi.c_vp)
         P.witness, P.evals, P.partial, P.partial_mask = vp(out["Witness"]), vp(out["Evals"]), vp(out["Partial"]), vp(out["PartialMask"])

@@ -403,10 +403,22 @@ struct ByteSource {
             return true;
         }
         if (!drbg_ready) { drbg.init(nullptr); drbg_ready = true; }
-        memset(p, 0, n);
-        drbg.xor_stream(p, n);
+        // the same keystream bytes in the same order, fetched 16 KiB at a time (a MustSetRandom element asks for 16-110 bytes: the
+        // per-call block bookkeeping cost more than the AES)
+        while (n) {
+            if (pool_pos == pool_len) {
+                memset(pool, 0, sizeof(pool));
+                drbg.xor_stream(pool, sizeof(pool));
+                pool_pos = 0; pool_len = sizeof(pool);
+            }
+            const size_t take = n < pool_len - pool_pos ? n : pool_len - pool_pos;
+            memcpy(p, pool + pool_pos, take);
+            pool_pos += take; p += take; n -= take;
+        }
         return true;
     }
+    alignas(16) uint8_t pool[16384];
+    size_t pool_pos = 0, pool_len = 0;
 };
 
 // SetRandom (element.go:303-346): ceil(bits/8) bytes, unused top bits cleared, retry while >= q; the raw limbs ARE the
@@ -416,7 +428,7 @@ bool set_random(const FieldHost &f, ByteSource &src, uint64_t *out) {
     const int b = f.bits % 8 ? f.bits % 8 : 8;
     uint8_t bytes[RS_MAX_NL_HOST * 4];
     for (;;) {
-        memset(bytes, 0, sizeof(bytes));
+        memset(bytes, 0, 8 * (size_t)f.L64);
         if (!src.read(bytes, k)) return false;
         bytes[k - 1] &= (uint8_t)((1u << b) - 1);
         uint64_t limbs[RS_MAX_NL_HOST / 2];
@@ -763,14 +775,13 @@ int rs_tape_builder_random_elements(rs_tape_builder *b, uint64_t *out_mont, size
 int rs_tape_builder_sum_check_mask(rs_tape_builder *b, size_t rank, size_t mask_rank, uint64_t *mask_out, uint64_t *mask_sum_out) {
     if (!b || !mask_out || !mask_sum_out || rank < 1 || mask_rank < rank) return RS_ERR_ARG;
     const size_t L = (size_t)b->f.L64;
-    int rc = rs_tape_builder_random_elements(b, mask_out, rank);
+    // the draws in the reference's order (coefficient 0 .. mask_rank - 1), then the fold: coefficient i - rank only ever
+    // subtracts coefficient i, which is final by then
+    const int rc = rs_tape_builder_random_elements(b, mask_out, mask_rank);
     if (rc) return rc;
     memcpy(mask_sum_out, mask_out, L * 8);
-    for (size_t i = rank; i < mask_rank; i++) {
-        rc = rs_tape_builder_random_elements(b, mask_out + i * L, 1);
-        if (rc) return rc;
+    for (size_t i = rank; i < mask_rank; i++)
         field_sub(b->f, (uint32_t *)(mask_out + (i - rank) * L), (const uint32_t *)(mask_out + (i - rank) * L), (const uint32_t *)(mask_out + i * L));
-    }
     return RS_OK;
 }
 

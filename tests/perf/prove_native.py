@@ -35,7 +35,7 @@ nprv.prove_raw(pwm, wm, R)
 times = []
 for k in range(reps):
     t0 = time.perf_counter()
-    out = nprv.prove_raw(pwm, wm, R, phases=False)
+    out = nprv.prove_raw(pwm, wm, R, phases=False, reuse=True)
     times.append((time.perf_counter() - t0) * 1e3)
 nprv.prove_raw(pwm, wm, R, phases=True)
 ok = out["eval_point"].tolist() == [int(v) for v in nprv.mont_many([saved["proof"]["_eval_point"]])[0]]
