@@ -62,6 +62,7 @@ int blind(const rs_field *f, uint32_t *polys, const uint32_t *d_blind, size_t n,
 int powers(const rs_field *f, uint32_t *out, const uint32_t *c, size_t n);
 int evaluate_many(const rs_field *f, uint32_t *d_results, const void *d_descs, size_t n_polys, const uint32_t *x);
 int twiddles(const rs_field *f, uint32_t *d_tw, uint32_t *d_twinv, const uint32_t *g, const uint32_t *ginv, int logN, int negacyclic);
+int shoup_tables(const rs_field *f, uint32_t *d_sh, const uint32_t *d_tw, size_t n);
 enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
 
 // ---- host-side field helpers (setup only) -------------------------------------------------
@@ -147,6 +148,26 @@ static bool geq(const uint32_t *a, const uint32_t *b, int n) {
     return true;
 }
 
+// z = x * y mod 2^(32 n)
+static void host_mul_lo(uint32_t *z, const uint32_t *x, const uint32_t *y, int n) {
+    uint32_t r[RS_MAX_NL] = {0};
+    for (int i = 0; i < n; i++) {
+        uint64_t c = 0;
+        for (int j = 0; i + j < n; j++) {
+            c += (uint64_t)x[j] * y[i] + r[i + j];
+            r[i + j] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    memcpy(z, r, 4 * n);
+}
+// Shoup pair of a Montgomery-form element e = w R mod q (shoup.cuh): (w, floor(w R / q)) = (e R^-1 mod q, e * (-q^-1) mod R)
+static void host_shoup_pair(const rs_field *f, uint32_t *pair, const uint32_t *e) {
+    uint32_t one[RS_MAX_NL] = {1};
+    host_mul(f, pair, e, one);
+    host_mul_lo(pair + f->NL, e, f->qinv_full, f->NL);
+}
+
 static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 static int ilog2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
@@ -160,7 +181,7 @@ static int ntt_dispatch(const rs_ntt *t, uint32_t *out, const uint32_t *in, size
     }
     switch (t->f->NL) {
         case 4: return ntt_run_l4(t, out, in, n_polys, inverse);
-        case 8: return ntt_run_l8(t, out, in, n_polys, inverse);
+        case 8: return (t->d_tw_sh && t->logN >= 1) ? ntt_run_sh_l8(t, out, in, n_polys, inverse) : ntt_run_l8(t, out, in, n_polys, inverse);
         case 14: return ntt_run_l14(t, out, in, n_polys, inverse);
         case 28: return ntt_run_l28(t, out, in, n_polys, inverse);
     }
@@ -270,6 +291,23 @@ int rs_field_create(const uint64_t *q, int L64, rs_field **out) {
         f->lazy_ok = (c == 0) && !getenv("RS_NTT_NO_LAZY");
         c = 0;
         for (int k = 0; k < n; k++) { c += (uint64_t)f->q[k] * 2; f->q2[k] = (uint32_t)c; c >>= 32; }
+    }
+    // -q^-1 mod 2^(32 n) by Newton (y <- y (2 - q y) doubles the correct low bits), and the validity of the Shoup NTT
+    // kernels (shoup.cuh): 18 q < 5 2^(32 n), the top 64 bits of q at least 2^8, q == 1 mod 2^32; compiled for 8 limbs
+    {
+        uint32_t y[RS_MAX_NL] = {1}, t2[RS_MAX_NL];
+        for (int it = 0; it < 10; it++) {
+            host_mul_lo(t2, f->q, y, n);
+            uint64_t br = 0;
+            for (int k = 0; k < n; k++) { uint64_t d = (uint64_t)(k == 0 ? 2 : 0) - t2[k] - br; t2[k] = (uint32_t)d; br = (d >> 63) & 1; }
+            host_mul_lo(y, y, t2, n);
+        }
+        uint64_t br = 0;
+        for (int k = 0; k < n; k++) { uint64_t d = (uint64_t)0 - y[k] - br; f->qinv_full[k] = (uint32_t)d; br = (d >> 63) & 1; }
+        uint64_t c = 0;
+        for (int k = 0; k < n; k++) { c += (uint64_t)f->q[k] * 18; c >>= 32; }
+        const uint64_t top64 = ((uint64_t)f->q[n - 1] << 32) | f->q[n - 2];
+        f->shoup_ok = f->lazy_ok && n == 8 && f->qs >= 1 && c < 5 && top64 >= 256 && !getenv("RS_NTT_NO_SHOUP");
     }
     *out = f;
     return RS_OK;
@@ -414,6 +452,7 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
     }
     rs_ntt *t = new rs_ntt();
     t->f = f; t->logN = logN; t->negacyclic = negacyclic; t->d_tw = t->d_twinv = nullptr;
+    t->d_tw_sh = t->d_twinv_sh = nullptr;
     t->h_tw.assign(N * n, 0);
     t->h_twinv.assign(N * n, 0);
     // generator search: smallest x >= 2 with (x^((q-1)/order))^(order/2) != 1  (ntt.go:40-53, :167-180)
@@ -465,6 +504,24 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
     host_inverse(f, t->ninv, nm);
     if (N >= 2) host_mul(f, t->ninv_w1, t->ninv, &t->h_twinv[1 * n]);
     else memcpy(t->ninv_w1, t->ninv, 4 * n);
+    // Shoup tables (shoup.cuh): every butterfly product has a table entry as one operand; (w, floor(w R / q)) pairs made in HBM
+    if (f->shoup_ok && N >= 2) {
+        host_shoup_pair(f, t->ninv_sh, t->ninv);
+        host_shoup_pair(f, t->ninv_w1_sh, t->ninv_w1);
+        cudaError_t e1 = cudaMalloc((void **)&t->d_tw_sh, 2 * bytes), e2 = cudaMalloc((void **)&t->d_twinv_sh, 2 * bytes);
+        int rc = (e1 == cudaSuccess && e2 == cudaSuccess) ? RS_OK : set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        if (rc == RS_OK) rc = shoup_tables(f, t->d_tw_sh, t->d_tw, N);
+        if (rc == RS_OK) rc = shoup_tables(f, t->d_twinv_sh, t->d_twinv, N);
+        if (rc == RS_OK && cudaStreamSynchronize(g_stream) != cudaSuccess)
+            rc = set_error(RS_ERR_CUDA, "rs_ntt_create: Shoup table generation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc != RS_OK) {
+            cudaFree(t->d_tw); cudaFree(t->d_twinv);
+            if (t->d_tw_sh) cudaFree(t->d_tw_sh);
+            if (t->d_twinv_sh) cudaFree(t->d_twinv_sh);
+            delete t;
+            return rc;
+        }
+    }
     // ---- FP64-pipe paths (ntt52.cuh), 8-word fields with 2^260 >= 36 q.  Both are bit-exact and both measured no faster than
     // the integer kernels on B200 (a DFMA costs two dispatch cycles, and half-rate instructions of different
     // pipes barely overlap), so they are opt-in: RS_NTT52=1 runs the FP64 kernels alone, RS_NTT_MIX=pf/p the two-pipe kernels.
@@ -505,6 +562,8 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
         if (t->d_twinv) cudaFree(t->d_twinv);
         if (t->d_tw52) cudaFree(t->d_tw52);
         if (t->d_twinv52) cudaFree(t->d_twinv52);
+        if (t->d_tw_sh) cudaFree(t->d_tw_sh);
+        if (t->d_twinv_sh) cudaFree(t->d_twinv_sh);
         delete t;
         return set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     }
@@ -517,6 +576,8 @@ void rs_ntt_destroy(rs_ntt *t) {
     if (t->d_twinv) cudaFree(t->d_twinv);
     if (t->d_tw52) cudaFree(t->d_tw52);
     if (t->d_twinv52) cudaFree(t->d_twinv52);
+    if (t->d_tw_sh) cudaFree(t->d_tw_sh);
+    if (t->d_twinv_sh) cudaFree(t->d_twinv_sh);
     delete t;
 }
 int rs_ntt_rank_log2(const rs_ntt *t) { return t ? t->logN : RS_ERR_ARG; }

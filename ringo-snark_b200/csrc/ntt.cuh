@@ -17,6 +17,7 @@
 // of a round is conflict-free.
 #pragma once
 #include "field.cuh"
+#include "shoup.cuh"
 
 namespace rs {
 
@@ -25,7 +26,14 @@ struct NttConsts {
     FieldParams<NL> F;
     uint32_t ninv[NL];      // N^-1            (Montgomery)   ntt.go:86-87
     uint32_t ninv_w1[NL];   // N^-1 * twinv[1] (Montgomery)
+    // Shoup pairs (plain value, floor(value 2^(32 NL) / q)) of the two constants above (MODE 2 kernels, shoup.cuh)
+    uint32_t ninv_sh[2 * NL];
+    uint32_t ninv_w1_sh[2 * NL];
 };
+
+// arithmetic of a pass: canonical [0, q) Montgomery; lazy [0, 2q) Montgomery (field.cuh); lazy with Shoup products by the
+// (w, w') twiddle pairs and predicated corrections (shoup.cuh; the table has 2 NL words per entry)
+enum { NTT_CANON = 0, NTT_LAZY = 1, NTT_SHOUP = 2 };
 
 struct PassGeom {
     int logN;        // log2 of the transform size
@@ -103,17 +111,25 @@ __device__ __forceinline__ void load_twiddle(uint32_t *w, const uint32_t *__rest
     }
 }
 
+// (w, w') pair of the Shoup table
+template <int NL>
+__device__ __forceinline__ void load_twiddle_pair(uint32_t *w, uint32_t *wp, const uint32_t *__restrict__ tw, unsigned long long idx) {
+    load_twiddle<NL>(w, tw, 2 * idx);
+    load_twiddle<NL>(wp, tw, 2 * idx + 1);
+}
+
 // One radix-2^RR round on the 2^RR register-resident elements x[u][*].
 //   s_top : global stage index of the round's highest local bit (u-bit RR-1)
 //   hi    : index of this group among the groups of the round inside its polynomial
 //   SCALE : (inverse only) the round's last stage is stage 0 of the transform: fold N^-1 in
-//   LAZY  : values are kept in [0, 2q) (field.cuh lazy variants); the caller canonicalises at the end
+//   MODE  : NTT_LAZY / NTT_SHOUP: values are kept in [0, 2q) resp. [0, 2q + delta) (field.cuh, shoup.cuh); the caller canonicalises at the end
 //   TRIV  : the round starts at stage 0 of the transform (s_top == 0, hi == 0): the first twiddle of every
 //           stage is tw[2^s] = 1 (Montgomery one), so those products are skipped -- 7 of the 12 in a
 //           radix-8 round.  x * R * R^-1 = x exactly, so the values are the ones the reference computes.
-template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY, bool TRIV = false>
+template <int NL, int QS, int RR, bool INV, bool SCALE, int MODE, bool TRIV = false>
 __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const uint32_t *__restrict__ tw,
                                             int s_top, unsigned hi, const NttConsts<NL> &C) {
+    constexpr bool LAZY = MODE >= NTT_LAZY, SH = MODE == NTT_SHOUP;
     const FieldParams<NL> &F = C.F;
 #pragma unroll
     for (int bb = 0; bb < RR; bb++) {
@@ -122,11 +138,13 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
         const unsigned long long tbase = (1ull << s) + ((unsigned long long)hi << (RR - 1 - beta));
 #pragma unroll
         for (int g = 0; g < (1 << (RR - 1 - beta)); g++) {
-            uint32_t w[NL];
+            uint32_t w[NL], wp[SH ? NL : 1];
             constexpr bool SC = INV && SCALE;
             const bool last_scaled = SC && (beta == RR - 1);   // compile-time after unrolling
             const bool triv = TRIV && (g == 0);                 // compile-time after unrolling
-            if (!last_scaled && !triv) load_twiddle<NL>(w, tw, tbase + g);
+            if (!last_scaled && !triv) {
+                if constexpr (SH) load_twiddle_pair<NL>(w, wp, tw, tbase + g); else load_twiddle<NL>(w, tw, tbase + g);
+            }
 #pragma unroll
             for (int k = 0; k < (1 << beta); k++) {
                 const int u0 = (g << (beta + 1)) + k, u1 = u0 + (1 << beta);
@@ -137,7 +155,19 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
 #pragma unroll
                         for (int l = 0; l < NL; l++) v[l] = x[u1][l];
                     }
-                    if (LAZY) {
+                    bool done = false;
+                    if constexpr (SH) {
+                        if (!triv) {
+                            // v < 1.56 q: u + v cannot wrap and u - v + 2q cannot be negative (shoup.cuh)
+                            shoup_mul_lazy<NL, QS>(v, x[u1], w, wp, F);
+                            lazy_sub_p<NL>(x[u1], x[u0], v, F.q2);
+                            lazy_add_p<NL>(x[u0], x[u0], v, F.q2);
+                            done = true;
+                        }
+                    }
+                    if (done) {
+                    } else if (LAZY) {
+                        // (MODE 2: the trivial-twiddle butterflies only ever see the exact [0, 2q) outputs of other trivial ones)
                         if (!triv) mont_mul_lazy<NL, QS>(v, x[u1], w, F);
                         mod_sub_m<NL>(x[u1], x[u0], v, F.q2);
                         mod_add_m<NL>(x[u0], x[u0], v, F.q2);
@@ -149,7 +179,11 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
                 } else {
                     // ntt.go:365-370   u' = u+v ; v' = (u-v)*w
                     uint32_t d[NL];
-                    if (LAZY) {
+                    if constexpr (SH) {
+                        // the subtrahend is an arbitrary value: sums keep the exact reduction to [0, 2q)
+                        lazy_sub_p<NL>(d, x[u0], x[u1], F.q2);
+                        mod_add_m<NL>(x[u0], x[u0], x[u1], F.q2);
+                    } else if (LAZY) {
                         mod_sub_m<NL>(d, x[u0], x[u1], F.q2);
                         mod_add_m<NL>(x[u0], x[u0], x[u1], F.q2);
                     } else {
@@ -159,15 +193,21 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
                     if (last_scaled) {
                         // stage m = 1 with the trailing scalarMulVecTo(N^-1) (ntt.go:134-135, :242-243) folded in
                         uint32_t t[NL];
-                        if (LAZY) mont_mul_lazy<NL, QS>(t, x[u0], C.ninv, F); else mont_mul<NL, QS>(t, x[u0], C.ninv, F);
+                        if constexpr (SH) shoup_mul_lazy<NL, QS>(t, x[u0], C.ninv_sh, C.ninv_sh + NL, F);
+                        else if (LAZY) mont_mul_lazy<NL, QS>(t, x[u0], C.ninv, F);
+                        else mont_mul<NL, QS>(t, x[u0], C.ninv, F);
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u0][l] = t[l];
-                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F); else mont_mul<NL, QS>(x[u1], d, C.ninv_w1, F);
+                        if constexpr (SH) shoup_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1_sh, C.ninv_w1_sh + NL, F);
+                        else if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F);
+                        else mont_mul<NL, QS>(x[u1], d, C.ninv_w1, F);
                     } else if (triv) {
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u1][l] = d[l];
                     } else {
-                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F); else mont_mul<NL, QS>(x[u1], d, w, F);
+                        if constexpr (SH) shoup_mul_lazy<NL, QS>(x[u1], d, w, wp, F);
+                        else if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F);
+                        else mont_mul<NL, QS>(x[u1], d, w, F);
                     }
                 }
             }
@@ -177,9 +217,10 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
 
 // rounds of one pass over the tile in shared memory
 //   FINAL : (LAZY only) this round contains the last stage of the transform: bring values back to [0, q)
-template <int NL, int QS, int RR, bool INV, bool SCALE, bool LAZY, bool FINAL, int THREADS, int TS, bool TRIV = false>
+template <int NL, int QS, int RR, bool INV, bool SCALE, int MODE, bool FINAL, int THREADS, int TS, bool TRIV = false>
 __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restrict__ tw, const PassGeom &G,
                                           int lb, unsigned long long tile, const NttConsts<NL> &C) {
+    constexpr bool LAZY = MODE >= NTT_LAZY;
     // group geometry (see header comment): element u of group gid sits at base + u * ustride
     const int K = G.K;
     const int lgu = lb + (G.col_major ? 0 : G.logW);
@@ -209,9 +250,11 @@ __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restri
         uint32_t x[1 << RR][NL];
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) smem_load_elem<NL, TS>(x[u], sm, base + u * ustride);
-        radix_round<NL, QS, RR, INV, SCALE, LAZY, TRIV>(x, tw, s_top, hi, C);
+        radix_round<NL, QS, RR, INV, SCALE, MODE, TRIV>(x, tw, s_top, hi, C);
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) {
+            // (MODE 2 forward: sums may sit up to delta above 2q; the inverse ends with products, below 1.56 q)
+            if (MODE == NTT_SHOUP && FINAL && !INV) cond_sub<NL>(x[u], C.F.q2);
             if (LAZY && FINAL) cond_sub<NL>(x[u], C.F.q);
             smem_store_elem<NL, TS>(sm, base + u * ustride, x[u]);
         }
@@ -254,7 +297,7 @@ __device__ __forceinline__ void move_tile(uint32_t *sm, const uint32_t *gin, uin
 // (in == out for every pass after the first: plain loads on the data, no __restrict__)
 // TS: tile size in elements (THREADS << R in the single-pipe kernels: one group of 2^R elements per thread and round;
 // a larger TS makes every thread walk several groups per round)
-template <int NL, int QS, int R, int THREADS, int TS, bool INV, bool SCALE, bool LAZY, bool LAST, class SYNC>
+template <int NL, int QS, int R, int THREADS, int TS, bool INV, bool SCALE, int LAZY, bool LAST, class SYNC>
 __device__ __forceinline__ void ntt_pass_body(uint32_t *sm, uint32_t *out, const uint32_t *in, const uint32_t *__restrict__ tw,
                                               const NttConsts<NL> &C, const PassGeom &G, unsigned long long tile, SYNC sync) {
     move_tile<NL, THREADS, TS, false>(sm, in, out, G, tile);
@@ -288,7 +331,7 @@ __device__ __forceinline__ void ntt_pass_body(uint32_t *sm, uint32_t *out, const
 
 struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
-template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE, bool LAZY, bool LAST>
+template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE, int LAZY, bool LAST>
 __global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *out, const uint32_t *in,
                                                            const uint32_t *__restrict__ tw,
                                                            const __grid_constant__ NttConsts<NL> C,

@@ -7,6 +7,7 @@
 // All of these stream each coefficient once: one thread per element, 16-byte vector
 // accesses, grid sized in whole waves of the 148 SMs.
 #include "common.cuh"
+#include "shoup.cuh"
 
 namespace rs {
 
@@ -539,6 +540,38 @@ __global__ void __launch_bounds__(256) evaluate_many_kernel(uint32_t *results, c
         __syncthreads();
     }
     if (t < NL) results[(size_t)blockIdx.x * NL + t] = sh[t];
+}
+
+// Shoup pairs of a Montgomery table (shoup.cuh): entry e = w R mod q  ->  (w, floor(w R / q)) = (e R^-1 mod q, e * (-q^-1) mod R)
+template <int NL, int QS>
+__global__ void __launch_bounds__(128) shoup_table_kernel(uint32_t *sh, const uint32_t *tw, size_t n, const __grid_constant__ Scalar<NL> qinv_full,
+                                                          const __grid_constant__ FieldParams<NL> F) {
+    const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t e[NL], w[NL], one[NL], E[NL], O[NL], wp[NL];
+    ld_elem<NL>(e, tw + k * NL);
+#pragma unroll
+    for (int l = 0; l < NL; l++) one[l] = l == 0;
+    mont_mul<NL, QS>(w, e, one, F);
+    tri_lo<NL, false>(E, O, e, qinv_full.v);
+    tri_merge<NL>(wp, E, O);
+    st_elem<NL>(sh + 2 * k * NL, w);
+    st_elem<NL>(sh + (2 * k + 1) * NL, wp);
+}
+
+int shoup_tables(const rs_field *f, uint32_t *d_sh, const uint32_t *d_tw, size_t n) {
+#define CALL(NL, QS)                                                                                          \
+    {                                                                                                         \
+        FieldParams<NL> F = make_params<NL>(f);                                                               \
+        Scalar<NL> qi;                                                                                        \
+        for (int i = 0; i < NL; i++) qi.v[i] = f->qinv_full[i];                                               \
+        shoup_table_kernel<NL, QS><<<(unsigned)((n + 127) / 128), 128, 0, current_stream()>>>(d_sh, d_tw, n, qi, F); \
+    }
+    RS_FIELD_DISPATCH(f, CALL)
+#undef CALL
+    count_launch();
+    RS_CUDA_CHECK(cudaGetLastError());
+    return RS_OK;
 }
 
 int twiddles(const rs_field *f, uint32_t *d_tw, uint32_t *d_twinv, const uint32_t *g, const uint32_t *ginv, int logN, int negacyclic) {
