@@ -26,14 +26,49 @@ struct NttConsts {
     FieldParams<NL> F;
     uint32_t ninv[NL];      // N^-1            (Montgomery)   ntt.go:86-87
     uint32_t ninv_w1[NL];   // N^-1 * twinv[1] (Montgomery)
-    // Shoup pairs (plain value, floor(value 2^(32 NL) / q)) of the two constants above (MODE 2 kernels, shoup.cuh)
-    uint32_t ninv_sh[2 * NL];
-    uint32_t ninv_w1_sh[2 * NL];
 };
 
 // arithmetic of a pass: canonical [0, q) Montgomery; lazy [0, 2q) Montgomery (field.cuh); lazy with Shoup products by the
 // (w, w') twiddle pairs and predicated corrections (shoup.cuh; the table has 2 NL words per entry)
 enum { NTT_CANON = 0, NTT_LAZY = 1, NTT_SHOUP = 2 };
+
+// Moduli compiled into their kernels (FID > 0), as in the reference, whose zp packages are generated per modulus with q as
+// constants (jindo/internal/zp/element.go:32, :78): the limbs of q and 2q become immediates of the multiply-adds and of the
+// predicated corrections (with q a kernel parameter ptxas reloads them under the predicate: 13 LDC per butterfly).
+// FID 0: q is the kernel parameter.  The launcher compares the field's q with the table before it picks FID > 0.
+enum { FID_RUNTIME = 0, FID_ZP255 = 1 };
+template <int NL, int FID> struct FixedField;
+template <> struct FixedField<8, FID_ZP255> {
+    // q = 0x430d45996b62afc2d65643d9e6fb65558e9630dc8c3732810000000000000001 (jindo/internal/zp/element.go:32)
+    RS_HD static constexpr uint32_t q(int i) {
+        constexpr uint32_t v[8] = {0x00000001u, 0x00000000u, 0x8c373281u, 0x8e9630dcu, 0xe6fb6555u, 0xd65643d9u, 0x6b62afc2u, 0x430d4599u};
+        return v[i];
+    }
+    RS_HD static constexpr uint32_t q2(int i) {
+        constexpr uint32_t v[8] = {0x00000002u, 0x00000000u, 0x186e6502u, 0x1d2c61b9u, 0xcdf6caabu, 0xacac87b3u, 0xd6c55f85u, 0x861a8b32u};
+        return v[i];
+    }
+};
+template <int NL, int FID>
+RS_HD bool fixed_field_matches(const uint32_t *q) {
+    if constexpr (FID == FID_RUNTIME) return true;
+    else {
+        for (int i = 0; i < NL; i++) if (q[i] != FixedField<NL, FID>::q(i)) return false;
+        return true;
+    }
+}
+// the field a kernel computes in: the parameter block, or a local copy whose q / 2q are the compiled-in constants
+// (every access is at a compile-time index after unrolling, so the copy never materialises)
+template <int NL, int FID>
+__device__ __forceinline__ FieldParams<NL> kernel_field(const FieldParams<NL> &P) {
+    if constexpr (FID == FID_RUNTIME) return P;
+    else {
+        FieldParams<NL> F = P;
+#pragma unroll
+        for (int i = 0; i < NL; i++) { F.q[i] = FixedField<NL, FID>::q(i); F.q2[i] = FixedField<NL, FID>::q2(i); }
+        return F;
+    }
+}
 
 struct PassGeom {
     int logN;        // log2 of the transform size
@@ -126,11 +161,12 @@ __device__ __forceinline__ void load_twiddle_pair(uint32_t *w, uint32_t *wp, con
 //   TRIV  : the round starts at stage 0 of the transform (s_top == 0, hi == 0): the first twiddle of every
 //           stage is tw[2^s] = 1 (Montgomery one), so those products are skipped -- 7 of the 12 in a
 //           radix-8 round.  x * R * R^-1 = x exactly, so the values are the ones the reference computes.
-template <int NL, int QS, int RR, bool INV, bool SCALE, int MODE, bool TRIV = false>
+template <int NL, int QS, int RR, bool INV, bool SCALE, int MODE, bool TRIV = false, int FID = FID_RUNTIME>
 __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const uint32_t *__restrict__ tw,
                                             int s_top, unsigned hi, const NttConsts<NL> &C) {
     constexpr bool LAZY = MODE >= NTT_LAZY, SH = MODE == NTT_SHOUP;
-    const FieldParams<NL> &F = C.F;
+    static_assert(!(SH && INV), "the Shoup kernels are forward only");
+    const FieldParams<NL> F = kernel_field<NL, FID>(C.F);
 #pragma unroll
     for (int bb = 0; bb < RR; bb++) {
         const int beta = INV ? bb : (RR - 1 - bb);         // u-bit handled by this stage
@@ -179,11 +215,7 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
                 } else {
                     // ntt.go:365-370   u' = u+v ; v' = (u-v)*w
                     uint32_t d[NL];
-                    if constexpr (SH) {
-                        // the subtrahend is an arbitrary value: sums keep the exact reduction to [0, 2q)
-                        lazy_sub_p<NL>(d, x[u0], x[u1], F.q2);
-                        mod_add_m<NL>(x[u0], x[u0], x[u1], F.q2);
-                    } else if (LAZY) {
+                    if (LAZY) {
                         mod_sub_m<NL>(d, x[u0], x[u1], F.q2);
                         mod_add_m<NL>(x[u0], x[u0], x[u1], F.q2);
                     } else {
@@ -193,20 +225,17 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
                     if (last_scaled) {
                         // stage m = 1 with the trailing scalarMulVecTo(N^-1) (ntt.go:134-135, :242-243) folded in
                         uint32_t t[NL];
-                        if constexpr (SH) shoup_mul_lazy<NL, QS>(t, x[u0], C.ninv_sh, C.ninv_sh + NL, F);
-                        else if (LAZY) mont_mul_lazy<NL, QS>(t, x[u0], C.ninv, F);
+                        if (LAZY) mont_mul_lazy<NL, QS>(t, x[u0], C.ninv, F);
                         else mont_mul<NL, QS>(t, x[u0], C.ninv, F);
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u0][l] = t[l];
-                        if constexpr (SH) shoup_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1_sh, C.ninv_w1_sh + NL, F);
-                        else if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F);
+                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F);
                         else mont_mul<NL, QS>(x[u1], d, C.ninv_w1, F);
                     } else if (triv) {
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u1][l] = d[l];
                     } else {
-                        if constexpr (SH) shoup_mul_lazy<NL, QS>(x[u1], d, w, wp, F);
-                        else if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F);
+                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F);
                         else mont_mul<NL, QS>(x[u1], d, w, F);
                     }
                 }
@@ -217,7 +246,7 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
 
 // rounds of one pass over the tile in shared memory
 //   FINAL : (LAZY only) this round contains the last stage of the transform: bring values back to [0, q)
-template <int NL, int QS, int RR, bool INV, bool SCALE, int MODE, bool FINAL, int THREADS, int TS, bool TRIV = false>
+template <int NL, int QS, int RR, bool INV, bool SCALE, int MODE, bool FINAL, int THREADS, int TS, bool TRIV = false, int FID = FID_RUNTIME>
 __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restrict__ tw, const PassGeom &G,
                                           int lb, unsigned long long tile, const NttConsts<NL> &C) {
     constexpr bool LAZY = MODE >= NTT_LAZY;
@@ -250,12 +279,13 @@ __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restri
         uint32_t x[1 << RR][NL];
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) smem_load_elem<NL, TS>(x[u], sm, base + u * ustride);
-        radix_round<NL, QS, RR, INV, SCALE, MODE, TRIV>(x, tw, s_top, hi, C);
+        radix_round<NL, QS, RR, INV, SCALE, MODE, TRIV, FID>(x, tw, s_top, hi, C);
+        const FieldParams<NL> F = kernel_field<NL, FID>(C.F);
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) {
-            // (MODE 2 forward: sums may sit up to delta above 2q; the inverse ends with products, below 1.56 q)
-            if (MODE == NTT_SHOUP && FINAL && !INV) cond_sub<NL>(x[u], C.F.q2);
-            if (LAZY && FINAL) cond_sub<NL>(x[u], C.F.q);
+            // (Shoup kernels: sums may sit up to delta above 2q)
+            if (MODE == NTT_SHOUP && FINAL && !INV) cond_sub<NL>(x[u], F.q2);
+            if (LAZY && FINAL) cond_sub<NL>(x[u], F.q);
             smem_store_elem<NL, TS>(sm, base + u * ustride, x[u]);
         }
     }
@@ -297,7 +327,7 @@ __device__ __forceinline__ void move_tile(uint32_t *sm, const uint32_t *gin, uin
 // (in == out for every pass after the first: plain loads on the data, no __restrict__)
 // TS: tile size in elements (THREADS << R in the single-pipe kernels: one group of 2^R elements per thread and round;
 // a larger TS makes every thread walk several groups per round)
-template <int NL, int QS, int R, int THREADS, int TS, bool INV, bool SCALE, int LAZY, bool LAST, class SYNC>
+template <int NL, int QS, int R, int THREADS, int TS, bool INV, bool SCALE, int LAZY, bool LAST, class SYNC, int FID = FID_RUNTIME>
 __device__ __forceinline__ void ntt_pass_body(uint32_t *sm, uint32_t *out, const uint32_t *in, const uint32_t *__restrict__ tw,
                                               const NttConsts<NL> &C, const PassGeom &G, unsigned long long tile, SYNC sync) {
     move_tile<NL, THREADS, TS, false>(sm, in, out, G, tile);
@@ -313,17 +343,17 @@ __device__ __forceinline__ void ntt_pass_body(uint32_t *sm, uint32_t *out, const
         const int lb = INV ? r * R : K - (r + 1) * R;
         // (the inverse's closing round and the forward's opening round sit at stage 0: trivial first twiddles)
         if (LAST && rem == 0 && r == full - 1) {
-            if (INV && SCALE && G.triv) run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS, INV && SCALE>(sm, tw, G, lb, tile, C);
-            else run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS>(sm, tw, G, lb, tile, C);
-        } else if (!INV && r == 0 && G.s0 == 0 && G.triv) run_round<NL, QS, R, false, false, LAZY, false, THREADS, TS, true>(sm, tw, G, lb, tile, C);
-        else run_round<NL, QS, R, INV, false, LAZY, false, THREADS, TS>(sm, tw, G, lb, tile, C);
+            if (INV && SCALE && G.triv) run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS, INV && SCALE, FID>(sm, tw, G, lb, tile, C);
+            else run_round<NL, QS, R, INV, SCALE, LAZY, true, THREADS, TS, false, FID>(sm, tw, G, lb, tile, C);
+        } else if (!INV && r == 0 && G.s0 == 0 && G.triv) run_round<NL, QS, R, false, false, LAZY, false, THREADS, TS, true, FID>(sm, tw, G, lb, tile, C);
+        else run_round<NL, QS, R, INV, false, LAZY, false, THREADS, TS, false, FID>(sm, tw, G, lb, tile, C);
         sync();
     }
     if (rem) {
         const int lb = INV ? full * R : 0;
-        if (R >= 2 && rem == 1) run_round<NL, QS, 1, INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
-        if (R >= 3 && rem == 2) run_round<NL, QS, (R >= 3 ? 2 : 1), INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
-        if (R >= 4 && rem == 3) run_round<NL, QS, (R >= 4 ? 3 : 1), INV, SCALE, LAZY, LAST, THREADS, TS>(sm, tw, G, lb, tile, C);
+        if (R >= 2 && rem == 1) run_round<NL, QS, 1, INV, SCALE, LAZY, LAST, THREADS, TS, false, FID>(sm, tw, G, lb, tile, C);
+        if (R >= 3 && rem == 2) run_round<NL, QS, (R >= 3 ? 2 : 1), INV, SCALE, LAZY, LAST, THREADS, TS, false, FID>(sm, tw, G, lb, tile, C);
+        if (R >= 4 && rem == 3) run_round<NL, QS, (R >= 4 ? 3 : 1), INV, SCALE, LAZY, LAST, THREADS, TS, false, FID>(sm, tw, G, lb, tile, C);
         sync();
     }
     move_tile<NL, THREADS, TS, true>(sm, in, out, G, tile);
@@ -331,13 +361,13 @@ __device__ __forceinline__ void ntt_pass_body(uint32_t *sm, uint32_t *out, const
 
 struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 
-template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE, int LAZY, bool LAST>
+template <int NL, int QS, int R, int THREADS, int MINB, bool INV, bool SCALE, int LAZY, bool LAST, int FID = FID_RUNTIME>
 __global__ void __launch_bounds__(THREADS, MINB) ntt_pass_kernel(uint32_t *out, const uint32_t *in,
                                                            const uint32_t *__restrict__ tw,
                                                            const __grid_constant__ NttConsts<NL> C,
                                                            const __grid_constant__ PassGeom G) {
     extern __shared__ __align__(16) uint32_t sm[];
-    ntt_pass_body<NL, QS, R, THREADS, (THREADS << R), INV, SCALE, LAZY, LAST>(sm, out, in, tw, C, G, blockIdx.x, CtaSync());
+    ntt_pass_body<NL, QS, R, THREADS, (THREADS << R), INV, SCALE, LAZY, LAST, CtaSync, FID>(sm, out, in, tw, C, G, blockIdx.x, CtaSync());
 }
 
 #endif  // __CUDACC__
