@@ -63,6 +63,7 @@ int powers(const rs_field *f, uint32_t *out, const uint32_t *c, size_t n);
 int evaluate_many(const rs_field *f, uint32_t *d_results, const void *d_descs, size_t n_polys, const uint32_t *x);
 int twiddles(const rs_field *f, uint32_t *d_tw, uint32_t *d_twinv, const uint32_t *g, const uint32_t *ginv, int logN, int negacyclic);
 int shoup_tables(const rs_field *f, uint32_t *d_sh, const uint32_t *d_tw, size_t n);
+bool shoup_inverse_available(const rs_field *f);   // ntt_sh_l8.cu
 enum PwOp { OP_ADD, OP_SUB, OP_NEG, OP_MUL, OP_MULADD, OP_MULSUB, OP_SMUL, OP_SMULADD, OP_SMULSUB };
 
 // ---- host-side field helpers (setup only) -------------------------------------------------
@@ -161,6 +162,13 @@ static void host_mul_lo(uint32_t *z, const uint32_t *x, const uint32_t *y, int n
     }
     memcpy(z, r, 4 * n);
 }
+// Shoup pair of a Montgomery-form element e = w R mod q (shoup.cuh): (w, floor(w R / q)) = (e R^-1 mod q, e * (-q^-1) mod R)
+static void host_shoup_pair(const rs_field *f, uint32_t *pair, const uint32_t *e) {
+    uint32_t one[RS_MAX_NL] = {1};
+    host_mul(f, pair, e, one);
+    host_mul_lo(pair + f->NL, e, f->qinv_full, f->NL);
+}
+
 static bool is_pow2(size_t x) { return x && !(x & (x - 1)); }
 static int ilog2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
@@ -174,9 +182,8 @@ static int ntt_dispatch(const rs_ntt *t, uint32_t *out, const uint32_t *in, size
     }
     switch (t->f->NL) {
         case 4: return ntt_run_l4(t, out, in, n_polys, inverse);
-        // forward transforms of the Shoup-capable fields run the Shoup kernels; the inverse (multiply AFTER the add / sub pair,
-        // exact sums) measured no faster with them and keeps the Montgomery kernels
-        case 8: return (t->d_tw_sh && t->logN >= 1 && !inverse) ? ntt_run_sh_l8(t, out, in, n_polys) : ntt_run_l8(t, out, in, n_polys, inverse);
+        case 8: return (t->d_tw_sh && t->logN >= 1 && (!inverse || t->d_twinv_sh)) ? ntt_run_sh_l8(t, out, in, n_polys, inverse)
+                                                                                  : ntt_run_l8(t, out, in, n_polys, inverse);
         case 14: return ntt_run_l14(t, out, in, n_polys, inverse);
         case 28: return ntt_run_l28(t, out, in, n_polys, inverse);
     }
@@ -447,7 +454,7 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
     }
     rs_ntt *t = new rs_ntt();
     t->f = f; t->logN = logN; t->negacyclic = negacyclic; t->d_tw = t->d_twinv = nullptr;
-    t->d_tw_sh = nullptr;
+    t->d_tw_sh = t->d_twinv_sh = nullptr;
     t->h_tw.assign(N * n, 0);
     t->h_twinv.assign(N * n, 0);
     // generator search: smallest x >= 2 with (x^((q-1)/order))^(order/2) != 1  (ntt.go:40-53, :167-180)
@@ -501,14 +508,20 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
     else memcpy(t->ninv_w1, t->ninv, 4 * n);
     // Shoup tables (shoup.cuh): every butterfly product has a table entry as one operand; (w, floor(w R / q)) pairs made in HBM
     if (f->shoup_ok && N >= 2) {
-        cudaError_t e1 = cudaMalloc((void **)&t->d_tw_sh, 2 * bytes);
-        int rc = (e1 == cudaSuccess) ? RS_OK : set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1));
+        // (the inverse kernels exist for the moduli compiled into their kernels only, see ntt_sh_l8.cu; RS_NTT_NO_SHOUP_INV: off)
+        const bool inv_too = shoup_inverse_available(f) && !getenv("RS_NTT_NO_SHOUP_INV");
+        host_shoup_pair(f, t->ninv_sh, t->ninv);
+        host_shoup_pair(f, t->ninv_w1_sh, t->ninv_w1);
+        cudaError_t e1 = cudaMalloc((void **)&t->d_tw_sh, 2 * bytes), e2 = inv_too ? cudaMalloc((void **)&t->d_twinv_sh, 2 * bytes) : cudaSuccess;
+        int rc = (e1 == cudaSuccess && e2 == cudaSuccess) ? RS_OK : set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
         if (rc == RS_OK) rc = shoup_tables(f, t->d_tw_sh, t->d_tw, N);
+        if (rc == RS_OK && inv_too) rc = shoup_tables(f, t->d_twinv_sh, t->d_twinv, N);
         if (rc == RS_OK && cudaStreamSynchronize(g_stream) != cudaSuccess)
             rc = set_error(RS_ERR_CUDA, "rs_ntt_create: Shoup table generation failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc != RS_OK) {
             cudaFree(t->d_tw); cudaFree(t->d_twinv);
             if (t->d_tw_sh) cudaFree(t->d_tw_sh);
+            if (t->d_twinv_sh) cudaFree(t->d_twinv_sh);
             delete t;
             return rc;
         }
@@ -554,6 +567,7 @@ int rs_ntt_create(rs_field *f, int logN, int negacyclic, rs_ntt **out) {
         if (t->d_tw52) cudaFree(t->d_tw52);
         if (t->d_twinv52) cudaFree(t->d_twinv52);
         if (t->d_tw_sh) cudaFree(t->d_tw_sh);
+        if (t->d_twinv_sh) cudaFree(t->d_twinv_sh);
         delete t;
         return set_error(RS_ERR_CUDA, "rs_ntt_create: cudaMalloc failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
     }
@@ -567,6 +581,7 @@ void rs_ntt_destroy(rs_ntt *t) {
     if (t->d_tw52) cudaFree(t->d_tw52);
     if (t->d_twinv52) cudaFree(t->d_twinv52);
     if (t->d_tw_sh) cudaFree(t->d_tw_sh);
+    if (t->d_twinv_sh) cudaFree(t->d_twinv_sh);
     delete t;
 }
 int rs_ntt_rank_log2(const rs_ntt *t) { return t ? t->logN : RS_ERR_ARG; }

@@ -37,8 +37,9 @@ struct rs_ntt {
     std::vector<uint32_t> h_tw, h_twinv;
     uint32_t ninv[RS_MAX_NL];
     uint32_t ninv_w1[RS_MAX_NL];
-    // Shoup table of the forward transform (shoup.cuh): N entries of 2 NL words (w, floor(w 2^(32 NL) / q)); null: Montgomery kernels
-    uint32_t *d_tw_sh;
+    // Shoup tables (shoup.cuh): N entries of 2 NL words (w, floor(w 2^(32 NL) / q)); null: Montgomery kernels
+    uint32_t *d_tw_sh, *d_twinv_sh;
+    uint32_t ninv_sh[2 * RS_MAX_NL], ninv_w1_sh[2 * RS_MAX_NL];   // the same pairs for N^-1 and N^-1 twinv[1]
     // FP64-pipe path (ntt52.cuh), 8-word fields only: twiddles re-scaled to the 2^260 Montgomery radix, 52-bit limbs
     // as doubles, TW52_STRIDE doubles per entry; has52 == 0: not available for this field
     int has52, variant52;
@@ -92,7 +93,7 @@ void host_set_u64(const rs_field *f, uint32_t *z, uint64_t v);
 // NTT launchers, one translation unit per limb count (ntt_l*.cu)
 int ntt_run_l4(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 int ntt_run_l8(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
-int ntt_run_sh_l8(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys);   // forward transform, Shoup kernels (ntt_sh_l8.cu)
+int ntt_run_sh_l8(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);   // Shoup kernels (ntt_sh_l8.cu)
 int ntt_run_l14(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 int ntt_run_l28(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse);
 // FP64-pipe kernels for the 8-word fields, one translation unit per tuning variant (ntt52_v*.cu)

@@ -26,6 +26,9 @@ struct NttConsts {
     FieldParams<NL> F;
     uint32_t ninv[NL];      // N^-1            (Montgomery)   ntt.go:86-87
     uint32_t ninv_w1[NL];   // N^-1 * twinv[1] (Montgomery)
+    // Shoup pairs (plain value, floor(value 2^(32 NL) / q)) of the two constants above (NTT_SHOUP inverse kernels, shoup.cuh)
+    uint32_t ninv_sh[2 * NL];
+    uint32_t ninv_w1_sh[2 * NL];
 };
 
 // arithmetic of a pass: canonical [0, q) Montgomery; lazy [0, 2q) Montgomery (field.cuh); lazy with Shoup products by the
@@ -165,7 +168,6 @@ template <int NL, int QS, int RR, bool INV, bool SCALE, int MODE, bool TRIV = fa
 __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const uint32_t *__restrict__ tw,
                                             int s_top, unsigned hi, const NttConsts<NL> &C) {
     constexpr bool LAZY = MODE >= NTT_LAZY, SH = MODE == NTT_SHOUP;
-    static_assert(!(SH && INV), "the Shoup kernels are forward only");
     const FieldParams<NL> F = kernel_field<NL, FID>(C.F);
 #pragma unroll
     for (int bb = 0; bb < RR; bb++) {
@@ -215,7 +217,11 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
                 } else {
                     // ntt.go:365-370   u' = u+v ; v' = (u-v)*w
                     uint32_t d[NL];
-                    if (LAZY) {
+                    if constexpr (SH) {
+                        // the subtrahend is an arbitrary value: sums keep the exact reduction to [0, 2q)
+                        lazy_sub_p<NL>(d, x[u0], x[u1], F.q2);
+                        mod_add_m<NL>(x[u0], x[u0], x[u1], F.q2);
+                    } else if (LAZY) {
                         mod_sub_m<NL>(d, x[u0], x[u1], F.q2);
                         mod_add_m<NL>(x[u0], x[u0], x[u1], F.q2);
                     } else {
@@ -225,17 +231,20 @@ __device__ __forceinline__ void radix_round(uint32_t (&x)[1 << RR][NL], const ui
                     if (last_scaled) {
                         // stage m = 1 with the trailing scalarMulVecTo(N^-1) (ntt.go:134-135, :242-243) folded in
                         uint32_t t[NL];
-                        if (LAZY) mont_mul_lazy<NL, QS>(t, x[u0], C.ninv, F);
+                        if constexpr (SH) shoup_mul_lazy<NL, QS>(t, x[u0], C.ninv_sh, C.ninv_sh + NL, F);
+                        else if (LAZY) mont_mul_lazy<NL, QS>(t, x[u0], C.ninv, F);
                         else mont_mul<NL, QS>(t, x[u0], C.ninv, F);
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u0][l] = t[l];
-                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F);
+                        if constexpr (SH) shoup_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1_sh, C.ninv_w1_sh + NL, F);
+                        else if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, C.ninv_w1, F);
                         else mont_mul<NL, QS>(x[u1], d, C.ninv_w1, F);
                     } else if (triv) {
 #pragma unroll
                         for (int l = 0; l < NL; l++) x[u1][l] = d[l];
                     } else {
-                        if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F);
+                        if constexpr (SH) shoup_mul_lazy<NL, QS>(x[u1], d, w, wp, F);
+                        else if (LAZY) mont_mul_lazy<NL, QS>(x[u1], d, w, F);
                         else mont_mul<NL, QS>(x[u1], d, w, F);
                     }
                 }
@@ -283,7 +292,7 @@ __device__ __forceinline__ void run_round(uint32_t *sm, const uint32_t *__restri
         const FieldParams<NL> F = kernel_field<NL, FID>(C.F);
 #pragma unroll
         for (int u = 0; u < (1 << RR); u++) {
-            // (Shoup kernels: sums may sit up to delta above 2q)
+            // (Shoup kernels, forward: sums may sit up to delta above 2q; the inverse ends with products, below 1.56 q)
             if (MODE == NTT_SHOUP && FINAL && !INV) cond_sub<NL>(x[u], F.q2);
             if (LAZY && FINAL) cond_sub<NL>(x[u], F.q);
             smem_store_elem<NL, TS>(sm, base + u * ustride, x[u]);

@@ -65,7 +65,7 @@ int launch_pass(const rs_ntt *t, uint32_t *out, const uint32_t *in, const NttCon
     constexpr int smem = SmemLayout<NL, T::TS>::BYTES;
     RS_CUDA_CHECK(ensure_smem_attr((const void *)kern, smem));
     RS_REQUIRE(tiles <= 0x7fffffffull, RS_ERR_UNSUPPORTED, "ntt: batch too large for one launch");
-    const uint32_t *tw = (MODE == NTT_SHOUP) ? t->d_tw_sh : (INV ? t->d_twinv : t->d_tw);
+    const uint32_t *tw = (MODE == NTT_SHOUP) ? (INV ? t->d_twinv_sh : t->d_tw_sh) : (INV ? t->d_twinv : t->d_tw);
     kern<<<(unsigned)tiles, T::THREADS, smem, current_stream()>>>(out, in, tw, C, G);
     count_launch();
     RS_CUDA_CHECK(cudaGetLastError());
@@ -76,7 +76,7 @@ int launch_pass(const rs_ntt *t, uint32_t *out, const uint32_t *in, const NttCon
 // Plans and launches the passes of one batched transform.
 //   forward : row-major passes over the top stages (s0 = 0 upward), then the contiguous pass
 //   inverse : the same passes in reverse order; the pass that owns stage 0 folds N^-1 in
-//   SHOUP : this translation unit carries the (forward) NTT_SHOUP kernels only (ntt_sh_l*.cu; the caller has checked t->d_tw_sh)
+//   SHOUP : this translation unit carries the NTT_SHOUP kernels only (ntt_sh_l*.cu; the caller has checked t->d_tw_sh)
 //   FID   : modulus compiled into the kernels (ntt.cuh FixedField; the caller has compared t->f->q with it)
 template <int NL, int QS, bool SHOUP = false, int FID = FID_RUNTIME>
 int ntt_run(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, bool inverse) {
@@ -91,6 +91,7 @@ int ntt_run(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, 
     NttConsts<NL> C;
     C.F = make_params<NL>(t->f);
     for (int i = 0; i < NL; i++) { C.ninv[i] = t->ninv[i]; C.ninv_w1[i] = t->ninv_w1[i]; }
+    for (int i = 0; i < 2 * NL; i++) { C.ninv_sh[i] = t->ninv_sh[i]; C.ninv_w1_sh[i] = t->ninv_w1_sh[i]; }
 
     // L2-resident sub-batches (RS_NTT_CHUNK_MB, off by default): a multi-pass transform re-reads what the previous pass wrote;
     // run over sub-batches whose output fits the 126 MB L2, the later passes hit L2 instead of HBM (one HBM round trip per
@@ -148,10 +149,12 @@ int ntt_run(const rs_ntt *t, uint32_t *out, const uint32_t *in, size_t n_polys, 
         int rc;
 #define RS_PASS(INV, LAST, LAZY) launch_pass<NL, QS, INV, LAST, (((NL <= 8) && LAZY) ? NTT_LAZY : NTT_CANON)>(t, out, src, C, G, tiles)
         if constexpr (SHOUP) {
-            // (forward only: capi.cu sends the inverse to the Montgomery kernels)
-            if (inverse) return set_error(RS_ERR_UNSUPPORTED, "ntt: the Shoup kernels are forward only");
-            rc = last ? launch_pass<NL, QS, false, true, NTT_SHOUP, FID>(t, out, src, C, G, tiles)
-                      : launch_pass<NL, QS, false, false, NTT_SHOUP, FID>(t, out, src, C, G, tiles);
+            // (inverse Shoup kernels are instantiated for the compiled-in moduli only: FID > 0)
+            if (!inverse) rc = last ? launch_pass<NL, QS, false, true, NTT_SHOUP, FID>(t, out, src, C, G, tiles)
+                                    : launch_pass<NL, QS, false, false, NTT_SHOUP, FID>(t, out, src, C, G, tiles);
+            else if constexpr (FID != FID_RUNTIME) rc = last ? launch_pass<NL, QS, true, true, NTT_SHOUP, FID>(t, out, src, C, G, tiles)
+                                                             : launch_pass<NL, QS, true, false, NTT_SHOUP, FID>(t, out, src, C, G, tiles);
+            else return set_error(RS_ERR_UNSUPPORTED, "ntt: no inverse Shoup kernels for this modulus");
         } else if (!inverse) rc = last ? (lazy ? RS_PASS(false, true, true) : RS_PASS(false, true, false))
                                 : (lazy ? RS_PASS(false, false, true) : RS_PASS(false, false, false));
         else rc = last ? (lazy ? RS_PASS(true, true, true) : RS_PASS(true, true, false))
