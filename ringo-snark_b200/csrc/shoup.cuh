@@ -122,7 +122,7 @@ RS_HD void tri_hi(uint32_t *h, uint32_t &frac, const uint32_t *x, const uint32_t
         const int jmin = (NL - 2 - i) > 0 ? (NL - 2 - i) : 0;
         {
             bool first = true;
-            int top = 0;
+            int top = 0, jtop = 0;
 #pragma unroll
             for (int j = jmin; j < NL; j++) {
                 if (((i + j) & 1) == 0) {
@@ -130,15 +130,17 @@ RS_HD void tri_hi(uint32_t *h, uint32_t &frac, const uint32_t *x, const uint32_t
                     if (first) c.mad_lo_cc(EH[k], x[j], wp[i], EH[k]); else c.madc_lo_cc(EH[k], x[j], wp[i], EH[k]);
                     c.madc_hi_cc(EH[k + 1], x[j], wp[i], EH[k + 1]);
                     first = false;
-                    top = k + 1;
+                    top = k + 1; jtop = j;
                 }
             }
-            // the chain's carry lands one limb above its top pair: a limb that so far holds carries only
-            if (i > 0 && top + 1 < NL + 2) c.addc(EH[top + 1], EH[top + 1], 0);
+            // A chain that ends with x[NL-1] writes its top limb for the first time (high word + carry cannot overflow): no
+            // carry out.  The other chain ends on a limb the previous row filled: its carry lands one limb higher, in a limb
+            // that so far holds nothing (the next row's x[NL-1] product is the first to add into it).
+            if (i > 0 && jtop != NL - 1 && top + 1 < NL + 2) c.addc(EH[top + 1], EH[top + 1], 0);
         }
         {
             bool first = true;
-            int top = 0;
+            int top = 0, jtop = 0;
 #pragma unroll
             for (int j = jmin; j < NL; j++) {
                 if (((i + j) & 1) == 1) {
@@ -146,10 +148,10 @@ RS_HD void tri_hi(uint32_t *h, uint32_t &frac, const uint32_t *x, const uint32_t
                     if (first) c.mad_lo_cc(OH[k], x[j], wp[i], OH[k]); else c.madc_lo_cc(OH[k], x[j], wp[i], OH[k]);
                     c.madc_hi_cc(OH[k + 1], x[j], wp[i], OH[k + 1]);
                     first = false;
-                    top = k + 1;
+                    top = k + 1; jtop = j;
                 }
             }
-            if (i > 0 && top + 1 < NL + 1) c.addc(OH[top + 1], OH[top + 1], 0);
+            if (i > 0 && jtop != NL - 1 && top + 1 < NL + 1) c.addc(OH[top + 1], OH[top + 1], 0);
         }
     }
     c.add_cc(frac, EH[1], OH[0]);
