@@ -711,12 +711,12 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64x4 (255-bit Montgomery, IMAD.WIDE on 32-bit limbs)", "data": "synthetic",
+        "dtype": "u64x4 (255-bit Montgomery-form elements, IMAD.WIDE on 32-bit limbs, Shoup twiddle products)", "data": "synthetic",
         "config": bench_config(), "host_numa": numa,
         "roofline": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of this launch in the ncu --set full capture
-                     # profiles/ntt_r1f_ncu_batch512_summary.csv (tools/profile_ntt.py zp255 16 512, final kernel shape): 1.076 + 1.016 GB
-                     "traffic": 2.092e9 if (BATCH, LOGN, FIELD) == (512, 16, "zp255") else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant (contiguous) pass in the ncu --set full capture
+                     # profiles/ntt_sh_r2_ncu_batch512_summary.csv (tools/ntt_shoup_probe.py zp255 16 512, Shoup kernels): 1.080 + 1.039 GB
+                     "traffic": 2.119e9 if (BATCH, LOGN, FIELD) == (512, 16, "zp255") else None,
                      "algorithmic_bytes": alg_bytes, "kernel": f"ntt_pass_kernel pass {dom} of {len(passes)}",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                      "note": "kernel is integer-pipe bound, see roofline_imad"},
@@ -726,7 +726,13 @@ def run_ours(args):
                           "peak_source": "rs_bench_imad_peak mode 5 (IMAD.WIDE.U32 with 64-bit addend, changing operands, this run)",
                           "nominal_32bit_imad_peak": 148 * 64 * 1.965, "frac_of_nominal_pairs": imad_ach / (148 * 64 * 1.965 / 2),
                           "note": "one 32x32->64 multiply-add = one IMAD.WIDE (measured 32 lanes/clk/SM) or an IMAD.LO + IMAD.HI pair "
-                                  "(nominal 64 lanes/clk/SM each): the same roof either way"},
+                                  "(nominal 64 lanes/clk/SM each): the same roof either way",
+                          # `achieved` counts SURVEY 8(d)'s ALGORITHMIC multiply-adds (2 l^2 + l = 136 per butterfly).  The forward
+                          # kernels of the 255-bit field execute fewer: Shoup products by the (w, w') twiddle pairs need 86 wide + 16
+                          # half (low-word) multiply-adds = 94 wide equivalents per butterfly (profiles/ntt_sh_r2_opcode_mix.txt),
+                          # so the share of the pipe's peak actually spent multiplying is frac * 94 / 136
+                          "executed_wide_equiv_per_butterfly": 94 if FIELD == "zp255" else None,
+                          "frac_executed": (imad_ach / imad_peak) * 94 / 136 if FIELD == "zp255" else None},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": float(t2.item()), "pipeline": f"{n_chunks} chunks on {n_streams} streams (pinned host memory)",
                 "result_checked": e2e_ok,
