@@ -287,3 +287,34 @@ def test_fp64_pipe_paths_equal_integer_path(rs, name, env, monkeypatch):
         if logN == 9:
             to = oracle.NTT(fo, logN, True)
             assert np.array_equal(Bt.download()[1], to.inv(raw[1]))   # and the oracle itself once
+
+
+@pytest.mark.parametrize("name", ["zp255", "zp240", "zp220", "zp110"])
+@pytest.mark.parametrize("neg", [False, True])
+def test_ntt_raw_extremes(rs, name, neg):
+    """The kernels work on the raw Montgomery words, and the Shoup kernels of the 8-limb fields (csrc/shoup.cuh) keep
+    values in a lazy range just above 2q: polynomials whose RAW words are extreme (all q - 1, alternating 0 / q - 1,
+    q - 1 in one half, top limbs saturated) drive the lazy sums to the top of that range.  Forward and inverse against
+    the oracle, single-pass and multi-pass ranks."""
+    q = pyref.modulus(name)
+    fo = oracle.Field(q); fg = rs.Field(q)
+    for logN in (6, 10, 13):
+        N = 1 << logN
+        top = oracle.ints_to_array([q - 1] * N, fo.L)
+        zero = oracle.ints_to_array([0] * N, fo.L)
+        alt = oracle.ints_to_array([(q - 1) if i & 1 else 0 for i in range(N)], fo.L)
+        half = oracle.ints_to_array([(q - 1) if i < N // 2 else 0 for i in range(N)], fo.L)
+        blocks = oracle.ints_to_array([(q - 1) if (i >> 3) & 1 else 1 for i in range(N)], fo.L)
+        rng = random.Random(logN)
+        hi = oracle.ints_to_array([q - 1 - rng.randrange(1 << 40) for _ in range(N)], fo.L)
+        data = np.stack([top, zero, alt, half, blocks, hi])
+        to = oracle.NTT(fo, logN, neg)
+        tg = (rs.CyclotomicTransformer if neg else rs.CyclicTransformer)(fg, N)
+        src = rs.Batch(fg, len(data), N).upload(data)
+        dst = rs.Batch(fg, len(data), N)
+        tg.FwdNTTTo(dst, src)
+        assert np.array_equal(dst.download(), to.fwd(data)), (name, logN, neg, "fwd")
+        tg.InvNTTTo(dst, src)
+        assert np.array_equal(dst.download(), to.inv(data)), (name, logN, neg, "inv")
+        tg.FwdNTTTo(dst, dst)
+        assert np.array_equal(dst.download(), data), (name, logN, neg, "round trip")
