@@ -751,7 +751,15 @@ def run_ours(args):
         # NTT butterfly) over the measured IMAD.WIDE peak, per GPU
         ach = commit["alg_imad"] / (commit["ms_per_commit"] * 1e-3) / 1e9
         commit["roofline_imad"] = {"bound": "imad", "achieved": ach, "peak": imad_peak, "unit": "G IMAD.WIDE/s", "frac": ach / imad_peak,
-                                   "algorithmic_imad_per_commit": commit.pop("alg_imad")}
+                                   "algorithmic_imad_per_commit": commit.pop("alg_imad"),
+                                   # what the kernels execute is far below SURVEY 8(d)'s count: the RNS residues have 38 bits, a lazy
+                                   # multiply-accumulate is 4 IMAD.WIDE (+ one reduction per output), so `frac` says nothing about pipe
+                                   # occupancy.  Executed: the inner mat-vec's 4 IMAD.WIDE per mod-mul-add over its own launch time
+                                   # (1.04-1.08 ms in profiles/launches_r2m_bench.csv) is 0.55-0.57 of the peak; over the whole Commit:
+                                   "executed_imad_wide_per_mac": 4,
+                                   "frac_executed_matvec_over_commit": 4 * commit["mod_mul_adds"] / (commit["ms_per_commit"] * 1e-3) / 1e9 / imad_peak,
+                                   "note": "frac uses SURVEY 8(d)'s algorithmic 16 multiply-adds per 64-bit mod-mul-add; the kernels execute 4 "
+                                           "(38-bit residues, lazy accumulation): see frac_executed_matvec_over_commit and DESIGN.md section 6"}
     if rank == 0:
         if world == 1:
             threads = os.cpu_count() or 1
