@@ -690,6 +690,17 @@ __device__ __forceinline__ void mac_lazy(uint32_t &s0a, uint32_t &s0b, uint32_t 
     acc_mad(s1, k1, x0);
     acc_mad(s2, k1, x1);
 }
+// the same with the top product k1 x1 accumulated in 32 bits by a plain IMAD (half the pipe cycles of an IMAD.WIDE): valid while
+// K 2^(2 (bits - 32)) < 2^32, i.e. for the 38-bit RNS primes of the 255-bit parameter sets up to K = 2^20 (launch_matvec checks)
+__device__ __forceinline__ void mac_lazy_n(uint32_t &s0a, uint32_t &s0b, uint32_t &s0c, Acc64 &s1, uint32_t &s2, u64 kv, u64 xv) {
+    const uint32_t k0 = (uint32_t)kv, k1 = (uint32_t)(kv >> 32);
+    const uint32_t x0 = (uint32_t)xv, x1 = (uint32_t)(xv >> 32);
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\tmadc.hi.cc.u32 %1, %3, %4, %1;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(s0a), "+r"(s0b), "+r"(s0c) : "r"(k0), "r"(x0));
+    acc_mad(s1, k0, x1);
+    acc_mad(s1, k1, x0);
+    s2 += k1 * x1;
+}
 
 template <int OT, int CT, int WARPS, bool FOLD, int UNR = 2>
 __global__ void __launch_bounds__(32 * WARPS) matvec_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
@@ -802,7 +813,8 @@ constexpr int MP_SMEM_BYTES = MP_STAGES * MP_STAGE_WORDS * 8;
 // TMA == true: the stage's (k, row) segments -- 512 contiguous bytes each -- are fetched by the copy engine (cp.async.bulk,
 // SASS UBLKCP) issued by one warp and counted on an mbarrier per stage (complete_tx), instead of 16-byte LDGSTS pieces issued
 // by every thread with their address arithmetic and a cp.async.wait_group.
-template <bool FOLD, bool TMA>
+// S2N: narrow accumulator for the k1 x1 products (mac_lazy_n; never together with FOLD)
+template <bool FOLD, bool TMA, bool S2N = false>
 __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
                                                                    const u64 *__restrict__ x, const u64 *__restrict__ addend,
                                                                    const __grid_constant__ MatvecGeom G) {
@@ -887,10 +899,11 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
 
     uint32_t s0a[MP_OT][2], s0b[MP_OT][2], s0c[MP_OT][2];
     Acc64 s1[MP_OT][2], s2[MP_OT][2]; u64 s1h[MP_OT][2], s2h[MP_OT][2];
+    uint32_t s2n[MP_OT][2];
 #pragma unroll
     for (int a = 0; a < MP_OT; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = Acc64{0}; s1h[a][b] = s2h[a][b] = 0; }
+        for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = Acc64{0}; s1h[a][b] = s2h[a][b] = 0; s2n[a][b] = 0; }
 
     const int n_it = (k_cnt + MP_KS - 1) / MP_KS;
     for (int st = 0; st < MP_STAGES - 1; st++) {
@@ -926,7 +939,8 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
             for (int a = 0; a < MP_OT; a++)
 #pragma unroll
                 for (int b = 0; b < 2; b++) {
-                    mac_lazy(s0a[a][b], s0b[a][b], s0c[a][b], s1[a][b], s2[a][b], kv[a], xv[b]);
+                    if (S2N) mac_lazy_n(s0a[a][b], s0b[a][b], s0c[a][b], s1[a][b], s2n[a][b], kv[a], xv[b]);
+                    else mac_lazy(s0a[a][b], s0b[a][b], s0c[a][b], s1[a][b], s2[a][b], kv[a], xv[b]);
                 }
             if (FOLD && ++since == G.fold_every) {
                 since = 0;
@@ -939,6 +953,12 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
                     }
             }
         }
+    }
+    if (S2N) {
+#pragma unroll
+        for (int a = 0; a < MP_OT; a++)
+#pragma unroll
+            for (int b = 0; b < 2; b++) s2[a][b].v = s2n[a][b];
     }
     const int slot = slot0 + tx;
 #pragma unroll
@@ -1399,6 +1419,16 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, false>, MP_SMEM_BYTES));
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true, true>, MP_SMEM_BYTES));
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, true>, MP_SMEM_BYTES));
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, false, true>, MP_SMEM_BYTES));
+        // k1 x1 < 2^(2 hb) per term (hb = prime bits - 32): a 32-bit accumulator takes K terms while K 2^(2 hb) < 2^32
+        bool s2_narrow = false;
+        {
+            int bits = 0;
+            for (int l = 0; l < G.n_limbs; l++) { int b = 64 - __builtin_clzll(G.q[l]); if (b > bits) bits = b; }
+            const int hb = bits > 32 ? bits - 32 : 0;
+            static const bool off = getenv("RS_JINDO_NO_S2N") != nullptr;
+            s2_narrow = !off && !G.fold_every && 2 * hb < 32 && (unsigned long long)G.K < (1ull << (32 - 2 * hb));
+        }
         dim3 grid(n_slots / MP_MS, (G.O + MP_OT - 1) / MP_OT, (G.C + MP_CTC - 1) / MP_CTC);
         // few column tiles (a column shard of a Commit, a short Commit): cut K so that the grid still covers the chip
         const unsigned ctas = grid.x * grid.y * grid.z;
@@ -1427,6 +1457,7 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
             if (G.fold_every) matvec_pipe_kernel<true, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
             else matvec_pipe_kernel<false, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         } else if (G.fold_every) matvec_pipe_kernel<true, false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
+        else if (s2_narrow) matvec_pipe_kernel<false, false, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         else matvec_pipe_kernel<false, false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         count_launch();
         if (S > 1) {
