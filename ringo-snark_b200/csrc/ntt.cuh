@@ -62,6 +62,7 @@ RS_HD bool fixed_field_matches(const uint32_t *q) {
 }
 // the field a kernel computes in: the parameter block, or a local copy whose q / 2q are the compiled-in constants
 // (every access is at a compile-time index after unrolling, so the copy never materialises)
+#ifdef __CUDACC__
 template <int NL, int FID>
 __device__ __forceinline__ FieldParams<NL> kernel_field(const FieldParams<NL> &P) {
     if constexpr (FID == FID_RUNTIME) return P;
@@ -72,6 +73,7 @@ __device__ __forceinline__ FieldParams<NL> kernel_field(const FieldParams<NL> &P
         return F;
     }
 }
+#endif
 
 struct PassGeom {
     int logN;        // log2 of the transform size
