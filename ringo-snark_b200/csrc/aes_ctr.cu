@@ -72,6 +72,85 @@ __global__ void __launch_bounds__(256) aes_keystream_kernel(uint4 *__restrict__ 
 #undef ROT24
 }
 
+// ---------------------------------------------------------------------------------------------
+// aes_keystream4_kernel: the same keystream with the lookups cut to ONE byte-permute + ONE shared load each.
+// The kernel above spends ~3.5 ALU instructions per table lookup (byte extract, index scaling, rotation of Te0 into
+// Te1..Te3) and is ALU bound; here the four round tables are stored with a row of 256 bytes per byte value,
+//     byte offset of (table t, value b, lane l)  =  (t >> 1) * 65536 + b * 256 + (t & 1) * 128 + l * 4
+// from a 64 KiB-aligned shared-memory base, so that a lookup address is the lane's base address with its byte 1
+// REPLACED by the state byte -- one PRMT of (state word, lane base) -- and the table is chosen by the immediate offset of
+// the LDS.  Every lane still reads its own bank.  The last round takes S[b] out of byte 1 / 2 of Te0[b] with three byte-permutes
+// per output word, the last of which also puts the word in memory byte order.  128 KiB of tables (+ up to 64 KiB of
+// alignment slack): one 1024-thread CTA per SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int AES4_THREADS = 1024;
+constexpr int AES4_SMEM = 3 * 65536;
+#define RS_LDS(v, addr, OFF) asm("ld.shared.u32 %0, [%1+" #OFF "];" : "=r"(v) : "r"(addr))
+__global__ void __launch_bounds__(AES4_THREADS, 1) aes_keystream4_kernel(uint4 *__restrict__ out, const __grid_constant__ AesKey K,
+                                                                         u64 iv_hi, u64 iv_lo, u64 blk0, size_t n) {
+    extern __shared__ __align__(16) uint8_t aes4_raw[];
+    const unsigned base = ((unsigned)__cvta_generic_to_shared(aes4_raw) + 0xffffu) & ~0xffffu;   // bits 0..15 clear
+    for (int e = threadIdx.x; e < 256 * 4 * 32; e += AES4_THREADS) {
+        const int lane = e & 31, t = (e >> 5) & 3, b = e >> 7;
+        const uint32_t sb = c_sbox[b], s2 = xtime(sb), s3 = s2 ^ sb;
+        uint32_t w = (s2 << 24) | (sb << 16) | (sb << 8) | s3;           // Te0[b] = (02 01 01 03) * S[b], big-endian word
+        w = t == 0 ? w : (t == 1 ? __byte_perm(w, 0, 0x0321) : (t == 2 ? __byte_perm(w, 0, 0x1032) : __byte_perm(w, 0, 0x2103)));
+        const unsigned a = base + (unsigned)(t >> 1) * 65536u + (unsigned)b * 256u + (unsigned)(t & 1) * 128u + (unsigned)lane * 4u;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(w) : "memory");
+    }
+    __syncthreads();
+    const unsigned lb = base + (threadIdx.x & 31) * 4;                 // lane base: byte 1 is zero
+    // bswap of the last round key (the output words are written in memory byte order)
+    const uint32_t k56 = __byte_perm(K.rk[56], 0, 0x0123), k57 = __byte_perm(K.rk[57], 0, 0x0123), k58 = __byte_perm(K.rk[58], 0, 0x0123),
+                   k59 = __byte_perm(K.rk[59], 0, 0x0123);
+    for (size_t i = blockIdx.x * (size_t)AES4_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * AES4_THREADS) {
+        const u64 add = blk0 + i;
+        const u64 lo = iv_lo + add, hi = iv_hi + (lo < add);
+        uint32_t s0 = (uint32_t)(hi >> 32) ^ K.rk[0], s1 = (uint32_t)hi ^ K.rk[1], s2 = (uint32_t)(lo >> 32) ^ K.rk[2], s3 = (uint32_t)lo ^ K.rk[3];
+        // address of (value = byte k of s): lane base with byte 1 replaced
+#define A3(s) __byte_perm((s), lb, 0x7634)
+#define A2(s) __byte_perm((s), lb, 0x7624)
+#define A1(s) __byte_perm((s), lb, 0x7614)
+#define A0(s) __byte_perm((s), lb, 0x7604)
+#define RS_AES_COL(t, a, b, c, d, rkw)                                   \
+        {                                                               \
+            uint32_t v0, v1, v2, v3;                                    \
+            RS_LDS(v0, A3(a), 0); RS_LDS(v1, A2(b), 128); RS_LDS(v2, A1(c), 65536); RS_LDS(v3, A0(d), 65664); \
+            t = v0 ^ v1 ^ v2 ^ v3 ^ (rkw);                              \
+        }
+#pragma unroll
+        for (int r = 1; r < 14; r++) {
+            uint32_t t0, t1, t2, t3;
+            RS_AES_COL(t0, s0, s1, s2, s3, K.rk[4 * r]);
+            RS_AES_COL(t1, s1, s2, s3, s0, K.rk[4 * r + 1]);
+            RS_AES_COL(t2, s2, s3, s0, s1, K.rk[4 * r + 2]);
+            RS_AES_COL(t3, s3, s0, s1, s2, K.rk[4 * r + 3]);
+            s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+        }
+        // final round: S[b] sits in bytes 1 and 2 of Te0[b]
+#define RS_AES_LAST(o, a, b, c, d, kw)                                   \
+        {                                                               \
+            uint32_t v0, v1, v2, v3;                                    \
+            RS_LDS(v0, A3(a), 0); RS_LDS(v1, A2(b), 0); RS_LDS(v2, A1(c), 0); RS_LDS(v3, A0(d), 0); \
+            const uint32_t hi2 = __byte_perm(v0, v1, 0x2600), lo2 = __byte_perm(v2, v3, 0x0015); \
+            o = __byte_perm(hi2, lo2, 0x4523) ^ (kw);                   \
+        }
+        uint32_t o0, o1, o2, o3;
+        RS_AES_LAST(o0, s0, s1, s2, s3, k56);
+        RS_AES_LAST(o1, s1, s2, s3, s0, k57);
+        RS_AES_LAST(o2, s2, s3, s0, s1, k58);
+        RS_AES_LAST(o3, s3, s0, s1, s2, k59);
+        out[i] = make_uint4(o0, o1, o2, o3);
+    }
+#undef A3
+#undef A2
+#undef A1
+#undef A0
+#undef RS_AES_COL
+#undef RS_AES_LAST
+}
+#undef RS_LDS
+
 constexpr int CH_WORDS = 1024;              // u64 words per 8 KiB chunk (uniform.go:12 bufSize)
 
 // phase 1: XOR total of each segment of `seg` chunks, per word offset
@@ -223,7 +302,13 @@ static int generate(UniformStream *s, u64 pos, size_t n, int b) {
     if (n_chunks) {
         u64 *ks = buf + CH_WORDS;
         static const int ctas_per_sm = [] { const char *e = getenv("RS_AES_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 6 ? v : 4; }();
-        aes_keystream_kernel<<<148 * ctas_per_sm, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_chunks * (CH_WORDS / 2));
+        static const bool one_table = getenv("RS_AES_T1") != nullptr;       // the one-table kernel (A/B switch)
+        const size_t n_blocks = n_chunks * (CH_WORDS / 2);
+        if (!one_table && n_blocks >= (size_t)148 * AES4_THREADS) {         // (short draws: the 128 KiB table fill would dominate)
+            RS_CUDA_CHECK(ensure_smem_attr((const void *)aes_keystream4_kernel, AES4_SMEM));
+            aes_keystream4_kernel<<<148, AES4_THREADS, AES4_SMEM, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_blocks);
+        } else
+            aes_keystream_kernel<<<148 * ctas_per_sm, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_blocks);
         dim3 grid(CH_WORDS / 256, (unsigned)n_seg);
         xor_scan_totals<<<grid, 256, 0, st>>>(s->d_tot, ks, n_chunks, seg);
         xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, state_out, n_seg);
