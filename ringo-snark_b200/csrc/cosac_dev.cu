@@ -54,33 +54,45 @@ struct CosacStream {
     int *d_overflow;
 };
 
-// ---- AES-256 block on the T-table replicated over the banks (as aes_keystream_kernel) ------------------------------
-#define TE(b) T[(b) << 5]
-#define ROT8(x) __byte_perm((x), 0, 0x0321)
-#define ROT16(x) __byte_perm((x), 0, 0x1032)
-#define ROT24(x) __byte_perm((x), 0, 0x2103)
+// ---- AES-256 block on two round tables in 256-byte rows (the lookup scheme of aes_keystream4_kernel, aes_ctr.cu) -----------
+// Shared layout: byte offset of (table t in {0, 1}, value b, lane l) = b * 256 + t * 128 + l * 4  (64 KiB; every lane reads its
+// own bank).  A lookup address is ONE byte-permute: byte 0 = 4 * lane, byte 1 = the state byte; Te2 = ROT16(Te0) and
+// Te3 = ROT16(Te1), and the rotation is linear over XOR, so a column costs 4 PRMT + 4 LDS + 1 PRMT + 3 LOP3.
+// T points at the lane's slot of row 0 (Te + 4 * lane bytes); `Sb` is unused (kept in the signatures): the last round
+// takes S[b] out of bytes 1 / 2 of Te0[b].
+#define RS_TOFF(s, SEL) __byte_perm((s), lane4, SEL)
+#define RS_T0(off) (*reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(T0) + (off)))
+#define RS_T1(off) (*reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(T0) + (off) + 128))
+#define RS_COL(a, b, c, d, rkw) (RS_T0(RS_TOFF(a, 0x5534)) ^ RS_T1(RS_TOFF(b, 0x5524)) ^ \
+                                 __byte_perm(RS_T0(RS_TOFF(c, 0x5514)) ^ RS_T1(RS_TOFF(d, 0x5504)), 0, 0x1032) ^ (rkw))
+#define RS_LAST(a, b, c, d, rkw) (__byte_perm(__byte_perm(RS_T0(RS_TOFF(a, 0x5534)), RS_T0(RS_TOFF(b, 0x5524)), 0x2600), \
+                                              __byte_perm(RS_T0(RS_TOFF(c, 0x5514)), RS_T0(RS_TOFF(d, 0x5504)), 0x0015), 0x3254) ^ (rkw))
 __device__ __forceinline__ void aes_block(const uint32_t *rk, u64 hi, u64 lo, const uint32_t *T, const uint32_t *Sb, u64 &w0, u64 &w1) {
+    (void)Sb;
+    const uint32_t lane4 = (threadIdx.x & 31) * 4;
+    const uint32_t *T0 = T - (threadIdx.x & 31);                          // row 0, lane 0 (the permute puts 4 * lane back in)
     uint32_t s0 = (uint32_t)(hi >> 32) ^ rk[0], s1 = (uint32_t)hi ^ rk[1], s2 = (uint32_t)(lo >> 32) ^ rk[2], s3 = (uint32_t)lo ^ rk[3];
 #pragma unroll 1
     for (int r = 1; r < 14; r++) {
-        const uint32_t t0 = TE(s0 >> 24) ^ ROT8(TE((s1 >> 16) & 0xff)) ^ ROT16(TE((s2 >> 8) & 0xff)) ^ ROT24(TE(s3 & 0xff)) ^ rk[4 * r];
-        const uint32_t t1 = TE(s1 >> 24) ^ ROT8(TE((s2 >> 16) & 0xff)) ^ ROT16(TE((s3 >> 8) & 0xff)) ^ ROT24(TE(s0 & 0xff)) ^ rk[4 * r + 1];
-        const uint32_t t2 = TE(s2 >> 24) ^ ROT8(TE((s3 >> 16) & 0xff)) ^ ROT16(TE((s0 >> 8) & 0xff)) ^ ROT24(TE(s1 & 0xff)) ^ rk[4 * r + 2];
-        const uint32_t t3 = TE(s3 >> 24) ^ ROT8(TE((s0 >> 16) & 0xff)) ^ ROT16(TE((s1 >> 8) & 0xff)) ^ ROT24(TE(s2 & 0xff)) ^ rk[4 * r + 3];
+        const uint32_t t0 = RS_COL(s0, s1, s2, s3, rk[4 * r]);
+        const uint32_t t1 = RS_COL(s1, s2, s3, s0, rk[4 * r + 1]);
+        const uint32_t t2 = RS_COL(s2, s3, s0, s1, rk[4 * r + 2]);
+        const uint32_t t3 = RS_COL(s3, s0, s1, s2, rk[4 * r + 3]);
         s0 = t0; s1 = t1; s2 = t2; s3 = t3;
     }
-    const uint32_t o0 = (Sb[s0 >> 24] << 24 | Sb[(s1 >> 16) & 0xff] << 16 | Sb[(s2 >> 8) & 0xff] << 8 | Sb[s3 & 0xff]) ^ rk[56];
-    const uint32_t o1 = (Sb[s1 >> 24] << 24 | Sb[(s2 >> 16) & 0xff] << 16 | Sb[(s3 >> 8) & 0xff] << 8 | Sb[s0 & 0xff]) ^ rk[57];
-    const uint32_t o2 = (Sb[s2 >> 24] << 24 | Sb[(s3 >> 16) & 0xff] << 16 | Sb[(s0 >> 8) & 0xff] << 8 | Sb[s1 & 0xff]) ^ rk[58];
-    const uint32_t o3 = (Sb[s3 >> 24] << 24 | Sb[(s0 >> 16) & 0xff] << 16 | Sb[(s1 >> 8) & 0xff] << 8 | Sb[s2 & 0xff]) ^ rk[59];
+    const uint32_t o0 = RS_LAST(s0, s1, s2, s3, rk[56]);
+    const uint32_t o1 = RS_LAST(s1, s2, s3, s0, rk[57]);
+    const uint32_t o2 = RS_LAST(s2, s3, s0, s1, rk[58]);
+    const uint32_t o3 = RS_LAST(s3, s0, s1, s2, rk[59]);
     // the block's 16 bytes are the big-endian words o0..o3; Sample() reads them 8 at a time, little endian (uniform.go:72-77)
     w0 = (u64)__byte_perm(o0, 0, 0x0123) | ((u64)__byte_perm(o1, 0, 0x0123) << 32);
     w1 = (u64)__byte_perm(o2, 0, 0x0123) | ((u64)__byte_perm(o3, 0, 0x0123) << 32);
 }
-#undef TE
-#undef ROT8
-#undef ROT16
-#undef ROT24
+#undef RS_TOFF
+#undef RS_T0
+#undef RS_T1
+#undef RS_COL
+#undef RS_LAST
 
 // a fresh csprng.UniformSampler: the first 8 KiB of its buffer are the plain keystream
 struct DevUniform {
@@ -172,17 +184,16 @@ __global__ void __launch_bounds__(256) cosac_kernel(i64 *__restrict__ out, const
                                                     const __grid_constant__ CosacKeys K, const __grid_constant__ CosacParams P,
                                                     const __grid_constant__ FieldParams<NL> F, const ZigTab *__restrict__ Z,
                                                     const uint8_t *__restrict__ sbox, int *overflow) {
-    extern __shared__ uint32_t Te[];                 // [256][32]
-    __shared__ uint32_t Sb[256];
+    extern __shared__ uint32_t Te[];                 // [256 values][Te0 x 32 lanes | Te1 x 32 lanes] (see aes_block)
+    __shared__ uint32_t Sb[1];                       // (unused: the last round reads S[b] out of Te0)
     __shared__ double dig[256];
     __shared__ int s_over;
     const int c = threadIdx.x;
     {
         const uint32_t s = sbox[c], s2 = ((s << 1) ^ (((s >> 7) & 1) * 0x1b)) & 0xff, s3 = s2 ^ s;
-        const uint32_t t = (s2 << 24) | (s << 16) | (s << 8) | s3;
+        const uint32_t t = (s2 << 24) | (s << 16) | (s << 8) | s3, t1 = __byte_perm(t, 0, 0x0321);
 #pragma unroll
-        for (int k = 0; k < 32; k++) Te[c * 32 + k] = t;
-        Sb[c] = s;
+        for (int k = 0; k < 32; k++) { Te[c * 64 + k] = t; Te[c * 64 + 32 + k] = t1; }
         if (c == 0) s_over = 0;
     }
     for (int t = blockIdx.x; t < P.n_polys; t += gridDim.x) {
@@ -283,11 +294,12 @@ int cosac_generate(CosacStream *s, const rs_field *f, const rs_jindo_params &p, 
     P.std_first = s->std_first; P.std_mask0 = s->std_mask0; P.std_mask = s->std_mask;
     P.ivb_hi = s->ivb_hi; P.ivb_lo = s->ivb_lo; P.ivr_hi = s->ivr_hi; P.ivr_lo = s->ivr_lo;
     P.worker0 = s->workers;
-    const int smem = 256 * 32 * 4;
-    const unsigned grid = (unsigned)(n_polys < 148 * 6 ? n_polys : 148 * 6);
+    const int smem = 256 * 64 * 4;                   // 64 KiB of round tables per CTA: three 256-thread CTAs per SM
+    const unsigned grid = (unsigned)(n_polys < 148 * 3 ? n_polys : 148 * 3);
 #define CALL(NL, QS)                                                                                                      \
     {                                                                                                                     \
         FieldParams<NL> F = make_params<NL>(f);                                                                           \
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)cosac_kernel<NL, QS>, smem));                                        \
         cosac_kernel<NL, QS><<<grid, 256, smem, current_stream()>>>(d_out, d_first_row, d_mask_rows, s->K, P, F, s->d_zig, s->d_sbox, s->d_overflow); \
     }
     switch (f->NL) {
