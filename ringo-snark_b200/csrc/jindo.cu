@@ -1317,59 +1317,76 @@ static void fill_geom_ring(MatvecGeom &G, const RingDev &R) {
 // the K range optionally split over blockIdx.z into partial sums (reduced mod q, added up by
 // rowsum_reduce_kernel).  Same lazy accumulation and final REDC as matvec_kernel.
 // ---------------------------------------------------------------------------------------------
-template <bool FOLD>
+// V: slots per thread (2: 16-byte loads, half the load instructions and 512-byte warp requests -- the kernel is a latency-bound
+// stream, and wider requests carry more bytes per outstanding load)
+template <bool FOLD, int V = 1>
 __global__ void __launch_bounds__(256) rowsum_kernel(u64 *__restrict__ out, const u64 *__restrict__ key, const u64 *__restrict__ x,
                                                      const u64 *__restrict__ addend, const __grid_constant__ MatvecGeom G, int ksplit) {
-    const int slot = blockIdx.x * 256 + threadIdx.x;
+    const int slot = (blockIdx.x * 256 + threadIdx.x) * V;
     const int cc = blockIdx.y, part = blockIdx.z;
     const int n_slots = G.n_limbs * JD;
     if (slot >= n_slots) return;
-    const int limb = slot / JD;
+    const int limb = slot / JD;                           // (V == 2: JD is even, both slots sit in the same limb)
     const u64 q = G.q[limb], qi = G.qinvneg[limb];
     const size_t pw = (size_t)n_slots;
     const int per = (G.K + ksplit - 1) / ksplit;
     const int k0 = part * per, k1 = (k0 + per < G.K) ? k0 + per : G.K;
-    uint32_t s0a = 0, s0b = 0, s0c = 0;
-    Acc64 s1{0}, s2{0}; u64 s1h = 0, s2h = 0;
+    uint32_t s0a[V], s0b[V], s0c[V];
+    Acc64 s1[V], s2[V]; u64 s1h[V], s2h[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) { s0a[v] = s0b[v] = s0c[v] = 0; s1[v] = s2[v] = Acc64{0}; s1h[v] = s2h[v] = 0; }
     int since = 0;
     const u64 *xp = x + ((size_t)cc * G.x_cs + (size_t)k0 * G.x_ks) * pw + slot;
     const u64 *kp = key + (size_t)k0 * G.key_ks * pw + slot;
     const size_t x_step = (size_t)G.x_ks * pw, k_step = (size_t)G.key_ks * pw;
     constexpr int U = 8;
     for (int k = k0; k < k1; k += U) {
-        u64 kv[U], xv[U];
+        u64 kv[U][V], xv[U][V];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const bool ok = k + u < k1;
-            xv[u] = ok ? __ldg(xp + (size_t)u * x_step) : 0;
-            kv[u] = ok ? __ldg(kp + (size_t)u * k_step) : 0;
+            if (V == 2) {
+                const ulonglong2 a = ok ? __ldg(reinterpret_cast<const ulonglong2 *>(xp + (size_t)u * x_step)) : make_ulonglong2(0, 0);
+                const ulonglong2 b = ok ? __ldg(reinterpret_cast<const ulonglong2 *>(kp + (size_t)u * k_step)) : make_ulonglong2(0, 0);
+                xv[u][0] = a.x; xv[u][V - 1] = a.y; kv[u][0] = b.x; kv[u][V - 1] = b.y;
+            } else {
+                xv[u][0] = ok ? __ldg(xp + (size_t)u * x_step) : 0;
+                kv[u][0] = ok ? __ldg(kp + (size_t)u * k_step) : 0;
+            }
         }
         xp += (size_t)U * x_step; kp += (size_t)U * k_step;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            mac_lazy(s0a, s0b, s0c, s1, s2, kv[u], xv[u]);
+#pragma unroll
+            for (int v = 0; v < V; v++) mac_lazy(s0a[v], s0b[v], s0c[v], s1[v], s2[v], kv[u][v], xv[u][v]);
             if (FOLD && ++since == G.fold_every) {
                 since = 0;
-                s1h += s1.v >> 32; s1.v &= 0xffffffffull;
-                s2h += s2.v >> 32; s2.v &= 0xffffffffull;
+#pragma unroll
+                for (int v = 0; v < V; v++) {
+                    s1h[v] += s1[v].v >> 32; s1[v].v &= 0xffffffffull;
+                    s2h[v] += s2[v].v >> 32; s2[v].v &= 0xffffffffull;
+                }
             }
         }
     }
-    u64 w0 = ((u64)s0b << 32) | s0a, w1 = s0c, w2 = 0;
-    auto add_at32 = [&](u64 v) {
-        const u64 lo = v << 32, hi = v >> 32;
-        const u64 n0 = w0 + lo; const u64 cy = n0 < lo; w0 = n0;
-        const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
-    };
-    auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
-    add_at32(s1.value());
-    add_at64(s2.value());
-    if (FOLD) { add_at64(s1h); const u64 v = s2h; add_at64(v << 32); w2 += v >> 32; }
-    u64 h = w1 >= q ? w1 % q : w1;
-    if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
-    u64 r = redc128(h, w0, q, qi);
-    if (ksplit == 1 && G.has_addend) r = addmod(r, __ldg(addend + (size_t)cc * G.add_cs * pw + slot), q);
-    out[((size_t)part * G.C + cc) * pw + slot] = r;       // ksplit == 1: out[cc]
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+        u64 w0 = ((u64)s0b[v] << 32) | s0a[v], w1 = s0c[v], w2 = 0;
+        auto add_at32 = [&](u64 t) {
+            const u64 lo = t << 32, hi = t >> 32;
+            const u64 n0 = w0 + lo; const u64 cy = n0 < lo; w0 = n0;
+            const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
+        };
+        auto add_at64 = [&](u64 t) { const u64 n1 = w1 + t; w2 += n1 < t; w1 = n1; };
+        add_at32(s1[v].value());
+        add_at64(s2[v].value());
+        if (FOLD) { add_at64(s1h[v]); const u64 t = s2h[v]; add_at64(t << 32); w2 += t >> 32; }
+        u64 h = w1 >= q ? w1 % q : w1;
+        if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
+        u64 r = redc128(h, w0, q, qi);
+        if (ksplit == 1 && G.has_addend) r = addmod(r, __ldg(addend + (size_t)cc * G.add_cs * pw + slot + v), q);
+        out[((size_t)part * G.C + cc) * pw + slot + v] = r;       // ksplit == 1: out[cc]
+    }
 }
 
 __global__ void rowsum_reduce_kernel(u64 *__restrict__ out, const u64 *__restrict__ parts, const u64 *__restrict__ addend,
@@ -1391,14 +1408,20 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
     // single-output products (Evaluate): streaming row sums
     if (G.O == 1 && G.key_cs == 0 && G.out_cs == 1 && !G.accumulate && !R.no_rowsum) {
         // enough CTAs for >= 4 per SM; K is split when there are few output polynomials
-        const int bx = (n_slots + 255) / 256;
+        // two slots per thread (16-byte loads) when the operands allow it
+        static const bool v1_only = getenv("RS_JINDO_ROWSUM_V1") != nullptr;
+        const bool v2 = !v1_only && n_slots % 2 == 0 && ((((uintptr_t)key | (uintptr_t)x) & 15) == 0);
+        const int bx = v2 ? (n_slots / 2 + 255) / 256 : (n_slots + 255) / 256;
         int ksplit = 1;
         while ((long long)bx * G.C * ksplit < 148 * 4 && ksplit * 64 < G.K) ksplit *= 2;
         u64 *d_parts = nullptr;
         if (ksplit > 1) RS_CUDA_CHECK(cudaMallocAsync((void **)&d_parts, (size_t)ksplit * G.C * n_slots * 8, current_stream()));
         dim3 grid(bx, G.C, ksplit);
         u64 *dst = ksplit > 1 ? d_parts : out;
-        if (G.fold_every) rowsum_kernel<true><<<grid, 256, 0, current_stream()>>>(dst, key, x, addend, G, ksplit);
+        if (v2) {
+            if (G.fold_every) rowsum_kernel<true, 2><<<grid, 256, 0, current_stream()>>>(dst, key, x, addend, G, ksplit);
+            else rowsum_kernel<false, 2><<<grid, 256, 0, current_stream()>>>(dst, key, x, addend, G, ksplit);
+        } else if (G.fold_every) rowsum_kernel<true><<<grid, 256, 0, current_stream()>>>(dst, key, x, addend, G, ksplit);
         else rowsum_kernel<false><<<grid, 256, 0, current_stream()>>>(dst, key, x, addend, G, ksplit);
         count_launch();
         if (ksplit > 1) {
