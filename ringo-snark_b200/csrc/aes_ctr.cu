@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) aes_keystream_kernel(uint4 *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// aes_keystream4_kernel: the same keystream with the lookups cut to ONE byte-permute + ONE shared load each.
+// aes_keystream4_scan_kernel (long draws): the same keystream with the lookups cut to ONE byte-permute + ONE shared load each.
 // The kernel above spends ~3.5 ALU instructions per table lookup (byte extract, index scaling, rotation of Te0 into
 // Te1..Te3) and is ALU bound; here the four round tables are stored with a row of 256 bytes per byte value,
 //     byte offset of (table t, value b, lane l)  =  (t >> 1) * 65536 + b * 256 + (t & 1) * 128 + l * 4
@@ -86,10 +86,9 @@ __global__ void __launch_bounds__(256) aes_keystream_kernel(uint4 *__restrict__ 
 constexpr int AES4_THREADS = 1024;
 constexpr int AES4_SMEM = 3 * 65536;
 #define RS_LDS(v, addr, OFF) asm("ld.shared.u32 %0, [%1+" #OFF "];" : "=r"(v) : "r"(addr))
-__global__ void __launch_bounds__(AES4_THREADS, 1) aes_keystream4_kernel(uint4 *__restrict__ out, const __grid_constant__ AesKey K,
-                                                                         u64 iv_hi, u64 iv_lo, u64 blk0, size_t n) {
-    extern __shared__ __align__(16) uint8_t aes4_raw[];
-    const unsigned base = ((unsigned)__cvta_generic_to_shared(aes4_raw) + 0xffffu) & ~0xffffu;   // bits 0..15 clear
+// fills the tables; returns the 64 KiB-aligned base
+__device__ __forceinline__ unsigned aes4_setup(uint8_t *raw) {
+    const unsigned base = ((unsigned)__cvta_generic_to_shared(raw) + 0xffffu) & ~0xffffu;   // bits 0..15 clear
     for (int e = threadIdx.x; e < 256 * 4 * 32; e += AES4_THREADS) {
         const int lane = e & 31, t = (e >> 5) & 3, b = e >> 7;
         const uint32_t sb = c_sbox[b], s2 = xtime(sb), s3 = s2 ^ sb;
@@ -99,49 +98,45 @@ __global__ void __launch_bounds__(AES4_THREADS, 1) aes_keystream4_kernel(uint4 *
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(w) : "memory");
     }
     __syncthreads();
-    const unsigned lb = base + (threadIdx.x & 31) * 4;                 // lane base: byte 1 is zero
-    // bswap of the last round key (the output words are written in memory byte order)
-    const uint32_t k56 = __byte_perm(K.rk[56], 0, 0x0123), k57 = __byte_perm(K.rk[57], 0, 0x0123), k58 = __byte_perm(K.rk[58], 0, 0x0123),
-                   k59 = __byte_perm(K.rk[59], 0, 0x0123);
-    for (size_t i = blockIdx.x * (size_t)AES4_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * AES4_THREADS) {
-        const u64 add = blk0 + i;
-        const u64 lo = iv_lo + add, hi = iv_hi + (lo < add);
-        uint32_t s0 = (uint32_t)(hi >> 32) ^ K.rk[0], s1 = (uint32_t)hi ^ K.rk[1], s2 = (uint32_t)(lo >> 32) ^ K.rk[2], s3 = (uint32_t)lo ^ K.rk[3];
-        // address of (value = byte k of s): lane base with byte 1 replaced
+    return base;
+}
+// keystream block of counter (hi:lo), as the 16 bytes in memory order; lb = table base + 4 * lane, kl[4] = bswap of rk[56..59]
+__device__ __forceinline__ uint4 aes4_block(const AesKey &K, const uint32_t *kl, unsigned lb, u64 hi, u64 lo) {
+    uint32_t s0 = (uint32_t)(hi >> 32) ^ K.rk[0], s1 = (uint32_t)hi ^ K.rk[1], s2 = (uint32_t)(lo >> 32) ^ K.rk[2], s3 = (uint32_t)lo ^ K.rk[3];
+    // address of (value = byte k of s): lane base with byte 1 replaced
 #define A3(s) __byte_perm((s), lb, 0x7634)
 #define A2(s) __byte_perm((s), lb, 0x7624)
 #define A1(s) __byte_perm((s), lb, 0x7614)
 #define A0(s) __byte_perm((s), lb, 0x7604)
 #define RS_AES_COL(t, a, b, c, d, rkw)                                   \
-        {                                                               \
-            uint32_t v0, v1, v2, v3;                                    \
-            RS_LDS(v0, A3(a), 0); RS_LDS(v1, A2(b), 128); RS_LDS(v2, A1(c), 65536); RS_LDS(v3, A0(d), 65664); \
-            t = v0 ^ v1 ^ v2 ^ v3 ^ (rkw);                              \
-        }
-#pragma unroll
-        for (int r = 1; r < 14; r++) {
-            uint32_t t0, t1, t2, t3;
-            RS_AES_COL(t0, s0, s1, s2, s3, K.rk[4 * r]);
-            RS_AES_COL(t1, s1, s2, s3, s0, K.rk[4 * r + 1]);
-            RS_AES_COL(t2, s2, s3, s0, s1, K.rk[4 * r + 2]);
-            RS_AES_COL(t3, s3, s0, s1, s2, K.rk[4 * r + 3]);
-            s0 = t0; s1 = t1; s2 = t2; s3 = t3;
-        }
-        // final round: S[b] sits in bytes 1 and 2 of Te0[b]
-#define RS_AES_LAST(o, a, b, c, d, kw)                                   \
-        {                                                               \
-            uint32_t v0, v1, v2, v3;                                    \
-            RS_LDS(v0, A3(a), 0); RS_LDS(v1, A2(b), 0); RS_LDS(v2, A1(c), 0); RS_LDS(v3, A0(d), 0); \
-            const uint32_t hi2 = __byte_perm(v0, v1, 0x2600), lo2 = __byte_perm(v2, v3, 0x0015); \
-            o = __byte_perm(hi2, lo2, 0x4523) ^ (kw);                   \
-        }
-        uint32_t o0, o1, o2, o3;
-        RS_AES_LAST(o0, s0, s1, s2, s3, k56);
-        RS_AES_LAST(o1, s1, s2, s3, s0, k57);
-        RS_AES_LAST(o2, s2, s3, s0, s1, k58);
-        RS_AES_LAST(o3, s3, s0, s1, s2, k59);
-        out[i] = make_uint4(o0, o1, o2, o3);
+    {                                                                   \
+        uint32_t v0, v1, v2, v3;                                        \
+        RS_LDS(v0, A3(a), 0); RS_LDS(v1, A2(b), 128); RS_LDS(v2, A1(c), 65536); RS_LDS(v3, A0(d), 65664); \
+        t = v0 ^ v1 ^ v2 ^ v3 ^ (rkw);                                  \
     }
+#pragma unroll
+    for (int r = 1; r < 14; r++) {
+        uint32_t t0, t1, t2, t3;
+        RS_AES_COL(t0, s0, s1, s2, s3, K.rk[4 * r]);
+        RS_AES_COL(t1, s1, s2, s3, s0, K.rk[4 * r + 1]);
+        RS_AES_COL(t2, s2, s3, s0, s1, K.rk[4 * r + 2]);
+        RS_AES_COL(t3, s3, s0, s1, s2, K.rk[4 * r + 3]);
+        s0 = t0; s1 = t1; s2 = t2; s3 = t3;
+    }
+    // final round: S[b] sits in bytes 1 and 2 of Te0[b]
+#define RS_AES_LAST(o, a, b, c, d, kw)                                   \
+    {                                                                   \
+        uint32_t v0, v1, v2, v3;                                        \
+        RS_LDS(v0, A3(a), 0); RS_LDS(v1, A2(b), 0); RS_LDS(v2, A1(c), 0); RS_LDS(v3, A0(d), 0); \
+        const uint32_t hi2 = __byte_perm(v0, v1, 0x2600), lo2 = __byte_perm(v2, v3, 0x0015); \
+        o = __byte_perm(hi2, lo2, 0x4523) ^ (kw);                       \
+    }
+    uint32_t o0, o1, o2, o3;
+    RS_AES_LAST(o0, s0, s1, s2, s3, kl[0]);
+    RS_AES_LAST(o1, s1, s2, s3, s0, kl[1]);
+    RS_AES_LAST(o2, s2, s3, s0, s1, kl[2]);
+    RS_AES_LAST(o3, s3, s0, s1, s2, kl[3]);
+    return make_uint4(o0, o1, o2, o3);
 #undef A3
 #undef A2
 #undef A1
@@ -150,6 +145,45 @@ __global__ void __launch_bounds__(AES4_THREADS, 1) aes_keystream4_kernel(uint4 *
 #undef RS_AES_LAST
 }
 #undef RS_LDS
+
+// The keystream with the first two passes of the prefix-XOR scan folded in: a thread owns one 16-byte block offset j of one
+// segment of `seg` consecutive 8 KiB chunks, walks the segment's chunks (block index c * 512 + j), keeps the running XOR and
+// writes IT instead of the raw keystream; the segment totals go to totals[s][2j .. 2j+1].  What is left for after the prefix
+// over the segments is one streaming XOR (xor_prefix_apply).
+__global__ void __launch_bounds__(AES4_THREADS, 1) aes_keystream4_scan_kernel(uint4 *__restrict__ out, uint4 *__restrict__ totals,
+                                                                              const __grid_constant__ AesKey K, u64 iv_hi, u64 iv_lo,
+                                                                              u64 blk0, size_t n_chunks, int seg) {
+    extern __shared__ __align__(16) uint8_t aes4_raw[];
+    const unsigned lb = aes4_setup(aes4_raw) + (threadIdx.x & 31) * 4;
+    const uint32_t kl[4] = {__byte_perm(K.rk[56], 0, 0x0123), __byte_perm(K.rk[57], 0, 0x0123), __byte_perm(K.rk[58], 0, 0x0123),
+                            __byte_perm(K.rk[59], 0, 0x0123)};
+    const size_t n_seg = (n_chunks + seg - 1) / seg;
+    for (size_t pair = blockIdx.x * (size_t)AES4_THREADS + threadIdx.x; pair < n_seg * 512; pair += (size_t)gridDim.x * AES4_THREADS) {
+        const size_t s = pair >> 9, j = pair & 511;
+        const size_t c0 = s * seg, c1 = (c0 + seg < n_chunks) ? c0 + seg : n_chunks;
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        for (size_t c = c0; c < c1; c++) {
+            const size_t i = c * 512 + j;
+            const u64 add = blk0 + i;
+            const u64 lo = iv_lo + add, hi = iv_hi + (lo < add);
+            const uint4 ks = aes4_block(K, kl, lb, hi, lo);
+            acc.x ^= ks.x; acc.y ^= ks.y; acc.z ^= ks.z; acc.w ^= ks.w;
+            out[i] = acc;
+        }
+        totals[pair] = acc;
+    }
+}
+// ks[c][o] ^= pre[c / seg][o]   (pre: the exclusive prefix over segments left by xor_scan_prefix), 16 bytes per thread
+__global__ void __launch_bounds__(256) xor_prefix_apply(uint4 *__restrict__ ks, const uint4 *__restrict__ pre, size_t n_chunks, int seg) {
+    const size_t n = n_chunks * 512;
+    for (size_t i = blockIdx.x * (size_t)256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const size_t c = i >> 9, j = i & 511;
+        const uint4 p = pre[(c / seg) * 512 + j];
+        uint4 v = ks[i];
+        v.x ^= p.x; v.y ^= p.y; v.z ^= p.z; v.w ^= p.w;
+        ks[i] = v;
+    }
+}
 
 constexpr int CH_WORDS = 1024;              // u64 words per 8 KiB chunk (uniform.go:12 bufSize)
 
@@ -277,7 +311,11 @@ static int generate(UniformStream *s, u64 pos, size_t n, int b) {
     const u64 c_start = pos / CH_WORDS + (off ? 1 : 0);                     // first chunk not yet refilled
     const u64 c_end = (pos + n + CH_WORDS - 1) / CH_WORDS;
     const size_t n_chunks = c_end > c_start ? (size_t)(c_end - c_start) : 0;
-    const int seg = n_chunks > 4096 ? 256 : (n_chunks > 64 ? 16 : 1);
+    // long draws: the four-table kernel with the scan's first passes folded in; one (segment, block offset) pair per thread of
+    // one wave of 148 x 1024 threads, i.e. 296 segments
+    static const bool one_table = getenv("RS_AES_T1") != nullptr;           // the one-table kernel + three-pass scan (A/B switch)
+    const bool fused = !one_table && n_chunks * (CH_WORDS / 2) >= (size_t)148 * AES4_THREADS;
+    const int seg = fused ? (int)((n_chunks + 295) / 296) : (n_chunks > 4096 ? 256 : (n_chunks > 64 ? 16 : 1));
     const size_t n_seg = n_chunks ? (n_chunks + seg - 1) / seg : 0;
     RS_CUDA_CHECK(cudaStreamWaitEvent(st, s->consumed[b], 0));              // the last consumer of this buffer is done
     if ((n_chunks + 1) * CH_WORDS > s->buf_words[b] || n_seg * CH_WORDS > s->tot_words) {
@@ -302,18 +340,22 @@ static int generate(UniformStream *s, u64 pos, size_t n, int b) {
     if (n_chunks) {
         u64 *ks = buf + CH_WORDS;
         static const int ctas_per_sm = [] { const char *e = getenv("RS_AES_CTAS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 6 ? v : 4; }();
-        static const bool one_table = getenv("RS_AES_T1") != nullptr;       // the one-table kernel (A/B switch)
         const size_t n_blocks = n_chunks * (CH_WORDS / 2);
-        if (!one_table && n_blocks >= (size_t)148 * AES4_THREADS) {         // (short draws: the 128 KiB table fill would dominate)
-            RS_CUDA_CHECK(ensure_smem_attr((const void *)aes_keystream4_kernel, AES4_SMEM));
-            aes_keystream4_kernel<<<148, AES4_THREADS, AES4_SMEM, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_blocks);
-        } else
-            aes_keystream_kernel<<<148 * ctas_per_sm, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_blocks);
         dim3 grid(CH_WORDS / 256, (unsigned)n_seg);
-        xor_scan_totals<<<grid, 256, 0, st>>>(s->d_tot, ks, n_chunks, seg);
-        xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, state_out, n_seg);
-        xor_scan_apply<<<grid, 256, 0, st>>>(ks, s->d_tot, n_chunks, seg);
-        count_launch(4);
+        if (fused) {
+            RS_CUDA_CHECK(ensure_smem_attr((const void *)aes_keystream4_scan_kernel, AES4_SMEM));
+            aes_keystream4_scan_kernel<<<148, AES4_THREADS, AES4_SMEM, st>>>((uint4 *)ks, (uint4 *)s->d_tot, s->key, s->iv_hi, s->iv_lo,
+                                                                            c_start * (CH_WORDS / 2), n_chunks, seg);
+            xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, state_out, n_seg);
+            xor_prefix_apply<<<148 * 8, 256, 0, st>>>((uint4 *)ks, (const uint4 *)s->d_tot, n_chunks, seg);
+            count_launch(3);
+        } else {
+            aes_keystream_kernel<<<148 * ctas_per_sm, 256, 256 * 32 * 4, st>>>((uint4 *)ks, s->key, s->iv_hi, s->iv_lo, c_start * (CH_WORDS / 2), n_blocks);
+            xor_scan_totals<<<grid, 256, 0, st>>>(s->d_tot, ks, n_chunks, seg);
+            xor_scan_prefix<<<CH_WORDS / 256, 256, 0, st>>>(s->d_tot, state_out, n_seg);
+            xor_scan_apply<<<grid, 256, 0, st>>>(ks, s->d_tot, n_chunks, seg);
+            count_launch(4);
+        }
         RS_CUDA_CHECK(cudaGetLastError());
     }
     RS_CUDA_CHECK(cudaEventRecord(s->ready[b], st));

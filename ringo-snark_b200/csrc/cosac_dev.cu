@@ -54,7 +54,7 @@ struct CosacStream {
     int *d_overflow;
 };
 
-// ---- AES-256 block on two round tables in 256-byte rows (the lookup scheme of aes_keystream4_kernel, aes_ctr.cu) -----------
+// ---- AES-256 block on two round tables in 256-byte rows (the lookup scheme of aes_keystream4_scan_kernel, aes_ctr.cu) -----------
 // Shared layout: byte offset of (table t in {0, 1}, value b, lane l) = b * 256 + t * 128 + l * 4  (64 KiB; every lane reads its
 // own bank).  A lookup address is ONE byte-permute: byte 0 = 4 * lane, byte 1 = the state byte; Te2 = ROT16(Te0) and
 // Te3 = ROT16(Te1), and the rotation is linear over XOR, so a column costs 4 PRMT + 4 LDS + 1 PRMT + 3 LOP3.
