@@ -755,7 +755,7 @@ def run_ours(args):
                                    # what the kernels execute is far below SURVEY 8(d)'s count: the RNS residues have 38 bits, a lazy
                                    # multiply-accumulate is 3 IMAD.WIDE + 1 IMAD (+ one reduction per output), so `frac` says nothing about pipe
                                    # occupancy.  Executed: the inner mat-vec's 3.5 wide equivalents per mod-mul-add over its own launch time
-                                   # (0.95-1.0 ms in profiles/launches_r2n_bench.csv) is about 0.55 of the peak; over the whole Commit:
+                                   # (0.95-1.0 ms in profiles/launches_r2p_bench.csv) is about 0.55 of the peak; over the whole Commit:
                                    "executed_imad_wide_per_mac": 3.5,      # 3 IMAD.WIDE + 1 plain IMAD (k1 x1 in 32 bits)
                                    "frac_executed_matvec_over_commit": 3.5 * commit["mod_mul_adds"] / (commit["ms_per_commit"] * 1e-3) / 1e9 / imad_peak,
                                    "note": "frac uses SURVEY 8(d)'s algorithmic 16 multiply-adds per 64-bit mod-mul-add; the kernels execute 3.5 "
