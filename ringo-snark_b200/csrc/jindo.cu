@@ -649,6 +649,7 @@ struct MatvecGeom {
     int accumulate;      // add the reduced sum to the existing out value
     int has_addend;
     int fold_every;      // reduce the high word mod q every this many terms (0 = never)
+    int kara_sh;         // matvec_pipe_kernel<.., KARA>: residues are split at this many bits (0: unused)
     int k_split;         // matvec_pipe_kernel: the K range is cut into k_split pieces (grid.y carries the piece); piece s writes its
     i64 split_stride;    // reduced partial sums at out + s * split_stride words, summed afterwards by reduce_split_kernel (0/1: off)
     u64 q[JMAXL], qinvneg[JMAXL], r2[JMAXL];
@@ -814,7 +815,11 @@ constexpr int MP_SMEM_BYTES = MP_STAGES * MP_STAGE_WORDS * 8;
 // SASS UBLKCP) issued by one warp and counted on an mbarrier per stage (complete_tx), instead of 16-byte LDGSTS pieces issued
 // by every thread with their address arithmetic and a cp.async.wait_group.
 // S2N: narrow accumulator for the k1 x1 products (mac_lazy_n; never together with FOLD)
-template <bool FOLD, bool TMA, bool S2N = false>
+// KARA: (never together with FOLD / S2N) residues below 2^(2 sh) are split at sh bits, k = k1 2^sh + k0, and a multiply-accumulate
+//       is THREE plain 64-bit IMAD.WIDE: A += k0 x0, B += k1 x1, C += (k0 + k1)(x0 + x1); the middle term is C - A - B.  No carry
+//       word (every product is below 2^(2 sh + 2), launch_matvec checks K 2^(2 sh + 2) < 2^64); the splits cost three ALU
+//       instructions per loaded value, shared by the 2 resp. 5 products the value takes part in.
+template <bool FOLD, bool TMA, bool S2N = false, bool KARA = false>
 __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *__restrict__ out, const u64 *__restrict__ key,
                                                                    const u64 *__restrict__ x, const u64 *__restrict__ addend,
                                                                    const __grid_constant__ MatvecGeom G) {
@@ -900,10 +905,13 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
     uint32_t s0a[MP_OT][2], s0b[MP_OT][2], s0c[MP_OT][2];
     Acc64 s1[MP_OT][2], s2[MP_OT][2]; u64 s1h[MP_OT][2], s2h[MP_OT][2];
     uint32_t s2n[MP_OT][2];
+    Acc64 sk[MP_OT][2];
+    const int kara_sh = G.kara_sh;
+    const uint32_t kara_mask = (1u << kara_sh) - 1u;
 #pragma unroll
     for (int a = 0; a < MP_OT; a++)
 #pragma unroll
-        for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = Acc64{0}; s1h[a][b] = s2h[a][b] = 0; s2n[a][b] = 0; }
+        for (int b = 0; b < 2; b++) { s0a[a][b] = s0b[a][b] = s0c[a][b] = 0; s1[a][b] = s2[a][b] = sk[a][b] = Acc64{0}; s1h[a][b] = s2h[a][b] = 0; s2n[a][b] = 0; }
 
     const int n_it = (k_cnt + MP_KS - 1) / MP_KS;
     for (int st = 0; st < MP_STAGES - 1; st++) {
@@ -935,6 +943,22 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
             for (int a = 0; a < MP_OT; a++) kv[a] = rowp[a * MP_MS];
 #pragma unroll
             for (int b = 0; b < 2; b++) xv[b] = rowp[(MP_OT + ty * 2 + b) * MP_MS];
+            if (KARA) {
+                uint32_t k0[MP_OT], k1[MP_OT], ks[MP_OT], x0[2], x1[2], xs[2];
+#pragma unroll
+                for (int a = 0; a < MP_OT; a++) { k0[a] = (uint32_t)kv[a] & kara_mask; k1[a] = (uint32_t)(kv[a] >> kara_sh); ks[a] = k0[a] + k1[a]; }
+#pragma unroll
+                for (int b = 0; b < 2; b++) { x0[b] = (uint32_t)xv[b] & kara_mask; x1[b] = (uint32_t)(xv[b] >> kara_sh); xs[b] = x0[b] + x1[b]; }
+#pragma unroll
+                for (int a = 0; a < MP_OT; a++)
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        acc_mad(s1[a][b], k0[a], x0[b]);      // A
+                        acc_mad(s2[a][b], k1[a], x1[b]);      // B
+                        acc_mad(sk[a][b], ks[a], xs[b]);      // C
+                    }
+                continue;
+            }
 #pragma unroll
             for (int a = 0; a < MP_OT; a++)
 #pragma unroll
@@ -974,8 +998,15 @@ __global__ void __launch_bounds__(MP_THREADS, MP_MINB) matvec_pipe_kernel(u64 *_
                 const u64 n1 = w1 + hi; u64 cy2 = n1 < hi; const u64 n1b = n1 + cy; cy2 += n1b < n1; w1 = n1b; w2 += cy2;
             };
             auto add_at64 = [&](u64 v) { const u64 n1 = w1 + v; w2 += n1 < v; w1 = n1; };
-            add_at32(s1[a][b].value());
-            add_at64(s2[a][b].value());
+            if (KARA) {
+                // sum = A + (C - A - B) 2^sh + B 2^(2 sh), below 2^128
+                const u64 A = s1[a][b].value(), B = s2[a][b].value(), M = sk[a][b].value() - A - B;
+                const unsigned __int128 t = (unsigned __int128)A + ((unsigned __int128)M << kara_sh) + ((unsigned __int128)B << (2 * kara_sh));
+                w0 = (u64)t; w1 = (u64)(t >> 64);
+            } else {
+                add_at32(s1[a][b].value());
+                add_at64(s2[a][b].value());
+            }
             if (FOLD) { add_at64(s1h[a][b]); const u64 v = s2h[a][b]; add_at64(v << 32); w2 += v >> 32; }
             u64 h = w1 >= q ? w1 % q : w1;
             if (w2) h = addmod(h, mont64(w2 >= q ? w2 % q : w2, G.r2[limb], q, qi), q);
@@ -1443,14 +1474,20 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<true, true>, MP_SMEM_BYTES));
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, true>, MP_SMEM_BYTES));
         RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, false, true>, MP_SMEM_BYTES));
+        RS_CUDA_CHECK(ensure_smem_attr((const void *)matvec_pipe_kernel<false, false, false, true>, MP_SMEM_BYTES));
         // k1 x1 < 2^(2 hb) per term (hb = prime bits - 32): a 32-bit accumulator takes K terms while K 2^(2 hb) < 2^32
-        bool s2_narrow = false;
+        bool s2_narrow = false, kara = false;
         {
             int bits = 0;
             for (int l = 0; l < G.n_limbs; l++) { int b = 64 - __builtin_clzll(G.q[l]); if (b > bits) bits = b; }
             const int hb = bits > 32 ? bits - 32 : 0;
             static const bool off = getenv("RS_JINDO_NO_S2N") != nullptr;
             s2_narrow = !off && !G.fold_every && 2 * hb < 32 && (unsigned long long)G.K < (1ull << (32 - 2 * hb));
+            // Karatsuba split at sh = ceil(bits / 2): three IMAD.WIDE per multiply-accumulate, valid while K 2^(2 sh + 2) < 2^64
+            static const bool kara_on = getenv("RS_JINDO_NO_KARA") == nullptr;
+            const int sh = (bits + 1) / 2;
+            kara = kara_on && !G.fold_every && sh >= 1 && sh <= 30 && (unsigned long long)G.K < (1ull << (62 - 2 * sh));
+            G.kara_sh = kara ? sh : 0;
         }
         dim3 grid(n_slots / MP_MS, (G.O + MP_OT - 1) / MP_OT, (G.C + MP_CTC - 1) / MP_CTC);
         // few column tiles (a column shard of a Commit, a short Commit): cut K so that the grid still covers the chip
@@ -1480,6 +1517,7 @@ static int launch_matvec(u64 *out, const u64 *key, const u64 *x, const u64 *adde
             if (G.fold_every) matvec_pipe_kernel<true, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
             else matvec_pipe_kernel<false, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         } else if (G.fold_every) matvec_pipe_kernel<true, false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
+        else if (kara) matvec_pipe_kernel<false, false, false, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         else if (s2_narrow) matvec_pipe_kernel<false, false, true><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         else matvec_pipe_kernel<false, false><<<grid, MP_THREADS, MP_SMEM_BYTES, current_stream()>>>(dst, key, x, addend, G);
         count_launch();
