@@ -753,12 +753,12 @@ def run_ours(args):
         commit["roofline_imad"] = {"bound": "imad", "achieved": ach, "peak": imad_peak, "unit": "G IMAD.WIDE/s", "frac": ach / imad_peak,
                                    "algorithmic_imad_per_commit": commit.pop("alg_imad"),
                                    # what the kernels execute is far below SURVEY 8(d)'s count: the RNS residues have 38 bits, a lazy
-                                   # multiply-accumulate is 3 IMAD.WIDE + 1 IMAD (+ one reduction per output), so `frac` says nothing about pipe
-                                   # occupancy.  Executed: the inner mat-vec's 3.5 wide equivalents per mod-mul-add over its own launch time
-                                   # (0.95-1.0 ms in profiles/launches_r2p_bench.csv) is about 0.55 of the peak; over the whole Commit:
-                                   "executed_imad_wide_per_mac": 3.5,      # 3 IMAD.WIDE + 1 plain IMAD (k1 x1 in 32 bits)
-                                   "frac_executed_matvec_over_commit": 3.5 * commit["mod_mul_adds"] / (commit["ms_per_commit"] * 1e-3) / 1e9 / imad_peak,
-                                   "note": "frac uses SURVEY 8(d)'s algorithmic 16 multiply-adds per 64-bit mod-mul-add; the kernels execute 3.5 "
+                                   # multiply-accumulate is 3 IMAD.WIDE (+ one reduction per output), so `frac` says nothing about pipe
+                                   # occupancy.  Executed: the inner mat-vec's 3 IMAD.WIDE per mod-mul-add over its own launch time
+                                   # (0.88 ms) is 0.5 of the peak; over the whole Commit:
+                                   "executed_imad_wide_per_mac": 3,        # Karatsuba split of the 38-bit residues: 3 IMAD.WIDE
+                                   "frac_executed_matvec_over_commit": 3 * commit["mod_mul_adds"] / (commit["ms_per_commit"] * 1e-3) / 1e9 / imad_peak,
+                                   "note": "frac uses SURVEY 8(d)'s algorithmic 16 multiply-adds per 64-bit mod-mul-add; the kernels execute 3 "
                                            "(38-bit residues, lazy accumulation): see frac_executed_matvec_over_commit and DESIGN.md section 6"}
     if rank == 0:
         if world == 1:
