@@ -318,3 +318,33 @@ def test_ntt_raw_extremes(rs, name, neg):
         assert np.array_equal(dst.download(), to.inv(data)), (name, logN, neg, "inv")
         tg.FwdNTTTo(dst, dst)
         assert np.array_equal(dst.download(), data), (name, logN, neg, "round trip")
+
+
+def test_shoup_and_montgomery_kernels_agree_over_many_products(rs, monkeypatch):
+    """The Shoup kernels take a slow path when the truncated quotient of a product may be one short (about 8 * 2^-32 of the
+    products, csrc/shoup.cuh).  tests/test_device_shoup_host.py checks that path on engineered operands; here both kernel
+    families run the same 1.3e9 butterfly products of the 255-bit field (a handful of them land on the slow path) and must
+    agree bit for bit.  The Montgomery kernels are selected per field handle by RS_NTT_NO_SHOUP (read by rs_field_create)."""
+    q = pyref.modulus("zp255")
+    logN, n_polys = 16, 256
+    N = 1 << logN
+    monkeypatch.setenv("RS_NTT_NO_SHOUP", "1")
+    f_mont = rs.Field(q)
+    t_mont = rs.CyclotomicTransformer(f_mont, N)
+    monkeypatch.delenv("RS_NTT_NO_SHOUP")
+    f_sh = rs.Field(q)
+    t_sh = rs.CyclotomicTransformer(f_sh, N)
+    rng = np.random.default_rng(0x5348)
+    raw = rng.integers(0, 1 << 63, size=(n_polys, N, f_sh.L), dtype=np.uint64)
+    raw[..., f_sh.L - 1] &= np.uint64((1 << ((q.bit_length() - 1) % 64)) - 1)       # canonical: below q
+    A = rs.Batch(f_sh, n_polys, N).upload(raw)
+    B = rs.Batch(f_mont, n_polys, N).upload(raw)
+    for it in range(10):                       # each output is the next input: fresh canonical values every round
+        t_sh.FwdNTTTo(A, A)
+        t_mont.FwdNTTTo(B, B)
+        a = A.download()
+        assert np.array_equal(a, B.download()), ("forward", it)
+    for it in range(3):
+        t_sh.InvNTTTo(A, A)
+        t_mont.InvNTTTo(B, B)
+        assert np.array_equal(A.download(), B.download()), ("inverse", it)
